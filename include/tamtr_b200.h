@@ -1,0 +1,79 @@
+/*
+ * tamtr_b200 -- C ABI of the B200-native TAM-TR detection-head hot path (sm_100a only, no CPU fallback).
+ *
+ * This is the drop-in boundary: every entry point takes plain device pointers, sizes and a CUDA stream
+ * (no torch types), so any host language can bind it (ctypes binding: tamtr_b200/_lib.py; the reference-side
+ * binding a maintainer would add is shown in INTEGRATION.md).  Each function cites the reference interface
+ * (file:line under the TAM-TR repo) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - all tensors are contiguous, row-major, on the CURRENT device of the calling thread;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only enqueue work;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative TAMTR_E_* for argument errors;
+ *     tamtr_last_error() returns a thread-local message for the last non-zero return;
+ *   - inputs are borrowed for the duration of the enqueued work, outputs are caller-allocated.
+ */
+#ifndef TAMTR_B200_H
+#define TAMTR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAMTR_B200_ABI_VERSION 1
+
+enum tamtr_dtype { TAMTR_F32 = 0, TAMTR_BF16 = 1 };
+
+enum tamtr_error {
+    TAMTR_E_BADARG = -1,       /* null pointer / non-positive size */
+    TAMTR_E_UNSUPPORTED = -2,  /* shape outside the compiled template set (see tamtr_last_error) */
+    TAMTR_E_NODEVICE = -3      /* no sm_100 device visible */
+};
+
+int tamtr_abi_version(void);
+const char *tamtr_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+unsigned long long tamtr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention core op.
+ * Replaces ultralytics/nn/modules/utils.py:42-89 multi_scale_deformable_attn_pytorch (3x F.grid_sample +
+ * stack * weights .sum), i.e. ATen grid_sampler_2d bilinear / zeros padding / align_corners=False
+ * (torch/include/ATen/native/GridSampler.h:27-36, 205-207).
+ *
+ *   value  [B, Lv, H, Dh]  f32 or bf16 (dtype)    level l = tokens [start_l, start_l + H_l*W_l), row-major
+ *   loc    [B, Lq, H, L, P, 2] f32  (x, y) normalised to [0,1]; may leave [0,1] (zeros padding)
+ *   attn   [B, Lq, H, L, P]    f32
+ *   out    [B, Lq, H*Dh]       same dtype as value
+ *   level_shapes_host [L][2] = (H_l, W_l), HOST memory, read during the call (utils.py:56 value_spatial_shapes)
+ * Supported: Dh*sizeof(elt) in {32,64,128,256} bytes, L*P <= 32, sum(H_l*W_l) == Lv.
+ * Index math is bit-exact with the reference: ix = fmaf((2*loc-1)+1, W_l, -1) * 0.5, floor, 4 corners, each
+ * corner contributes iff 0<=x<W_l && 0<=y<H_l.  Accumulation in fp32.
+ */
+int tamtr_msda_forward(const void *value, const float *loc, const float *attn, void *out, int dtype,
+                       int B, int Lv, int H, int Dh, int Lq, int L, int P,
+                       const int32_t *level_shapes_host, void *stream);
+
+/* Backward of the above (what autograd derives for utils.py:42-89: grid_sampler_2d_backward + mul/sum).
+ *   grad_out   [B, Lq, H*Dh]   same dtype as value
+ *   grad_value [B, Lv, H, Dh]  same dtype as value; ZEROED by this call, then accumulated with vector atomics
+ *                              (REDG f32x4 / bf16x8) -> run-to-run bit differences, like grid_sampler backward
+ *   grad_loc   [B, Lq, H, L, P, 2] f32, grad_attn [B, Lq, H, L, P] f32 (fully overwritten)
+ */
+int tamtr_msda_backward(const void *grad_out, const void *value, const float *loc, const float *attn,
+                        void *grad_value, float *grad_loc, float *grad_attn, int dtype,
+                        int B, int Lv, int H, int Dh, int Lq, int L, int P,
+                        const int32_t *level_shapes_host, void *stream);
+
+/* Parity export of the index math alone (the "bit-exact sampling-location indexing" object):
+ *   x0, y0 [B,Lq,H,L,P] int32 = floor(ix), floor(iy);  inb [B,Lq,H,L,P,4] uint8 = in-bounds flags (nw,ne,sw,se).
+ * Runs the same __device__ function the two kernels above use. */
+int tamtr_msda_corners(const float *loc, int32_t *x0, int32_t *y0, uint8_t *inb,
+                       int B, int Lq, int H, int L, int P, const int32_t *level_shapes_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAMTR_B200_H */

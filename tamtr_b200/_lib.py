@@ -1,0 +1,99 @@
+"""ctypes binding of the C ABI in include/tamtr_b200.h (libtamtr_b200.so, built in-tree for sm_100a).
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.  CPU tensors are
+rejected with a message containing 'Not implemented on the CPU' / 'is_cuda', which is what the reference's
+DetectionModel.__init__ dry-run looks for before moving the model to CUDA (ultralytics/nn/tasks.py:256-264).
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtamtr_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+F32, BF16 = 0, 1
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
+
+_lib = None
+
+_vp, _i, _fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p
+_SIGNATURES = {
+    "tamtr_abi_version": (ctypes.c_int, []),
+    "tamtr_last_error": (ctypes.c_char_p, []),
+    "tamtr_launch_count": (ctypes.c_ulonglong, []),
+    "tamtr_msda_forward": (ctypes.c_int, [_vp, _fp, _fp, _vp, _i] + [_i] * 7 + [_vp, _vp]),
+    "tamtr_msda_backward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _i] + [_i] * 7 + [_vp, _vp]),
+    "tamtr_msda_corners": (ctypes.c_int, [_fp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp]),
+}
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a into tamtr_b200/lib/libtamtr_b200.so (nvcc cross-compiles on CPU)."""
+    out = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("tamtr_b200: nvcc build failed\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"tamtr_b200: {LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for this path)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        if handle.tamtr_abi_version() != 1:
+            raise RuntimeError("tamtr_b200: ABI version mismatch between _lib.py and libtamtr_b200.so")
+        _lib = handle
+    return _lib
+
+
+def launch_count():
+    return int(lib().tamtr_launch_count())
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().tamtr_last_error().decode(errors="replace")
+        raise RuntimeError(f"tamtr_b200: {what} failed (code {rc}): {msg}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("tamtr_b200: Not implemented on the CPU (expected is_cuda tensors); "
+                               "this path has hand-written sm_100a kernels only")
+
+
+def dtype_code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"tamtr_b200: dtype {t.dtype} not supported (float32 / bfloat16)") from None
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def shapes_array(shapes):
+    """value_spatial_shapes arrives as a python list of [h, w] (head.py:1215) or a tensor -> host int32[L][2]."""
+    if isinstance(shapes, torch.Tensor):
+        shapes = shapes.tolist()
+    flat = []
+    for h, w in shapes:
+        flat += [int(h), int(w)]
+    return (ctypes.c_int32 * len(flat))(*flat), len(flat) // 2

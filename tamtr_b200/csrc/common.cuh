@@ -1,0 +1,67 @@
+// Shared host/device helpers for the tamtr_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tamtr_b200.h"
+
+namespace tamtr {
+
+void set_error(const char *fmt, ...);
+void count_launch(unsigned n = 1);
+
+#define TAMTR_CHECK_ARG(cond, code, ...)           \
+    do {                                            \
+        if (!(cond)) {                              \
+            ::tamtr::set_error(__VA_ARGS__);        \
+            return (code);                          \
+        }                                           \
+    } while (0)
+
+#define TAMTR_CUDA_OK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ::tamtr::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));         \
+            return (int)_e;                                                              \
+        }                                                                                \
+    } while (0)
+
+constexpr int kMaxLevels = 8;
+constexpr int kMaxSamples = 32;  // L*P
+
+// Pyramid geometry, passed by value (lives in the kernel-parameter constant bank).
+struct Levels {
+    int n;                  // L
+    int P;                  // points per level
+    int h[kMaxLevels];      // H_l
+    int w[kMaxLevels];      // W_l
+    int start[kMaxLevels];  // first token of level l
+    unsigned char level_of[kMaxSamples];  // sample s = l*P + p -> l (saves an integer division per tap)
+};
+
+inline int fill_levels(Levels &lv, int L, int P, const int32_t *shapes_host, int expect_Lv) {
+    if (L < 1 || L > kMaxLevels || P < 1 || L * P > kMaxSamples) return TAMTR_E_UNSUPPORTED;
+    lv.n = L;
+    lv.P = P;
+    long s = 0;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        if (l < L) {
+            lv.h[l] = shapes_host[2 * l];
+            lv.w[l] = shapes_host[2 * l + 1];
+            if (lv.h[l] < 1 || lv.w[l] < 1) return TAMTR_E_BADARG;
+            lv.start[l] = (int)s;
+            s += (long)lv.h[l] * lv.w[l];
+        } else {
+            lv.h[l] = lv.w[l] = 1;
+            lv.start[l] = 0;
+        }
+    }
+    if (expect_Lv >= 0 && s != expect_Lv) return TAMTR_E_BADARG;
+    for (int i = 0; i < kMaxSamples; ++i) lv.level_of[i] = (unsigned char)(i < L * P ? i / P : 0);
+    return 0;
+}
+
+}  // namespace tamtr

@@ -1,0 +1,210 @@
+"""GPU parity tests of the deformable-attention sampler (through the C ABI) against the CPU oracle and the
+golden vectors the reference produced.  Tolerances are the north star's: fp32 <= 1e-4 relative, bf16 <= 2e-2
+relative (against the fp32 reference on bf16-rounded inputs), sampling indices bit-exact."""
+import os
+
+import pytest
+import torch
+
+from oracle import msda
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4      # north star; measured ~1e-7
+BF16_TOL = 2e-2      # north star; measured ~2e-3
+
+
+def rel_l2(x, y):
+    x, y = x.detach().double().cpu(), y.detach().double().cpu()
+    return ((x - y).norm() / y.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def core(golden_dir):
+    return torch.load(os.path.join(golden_dir, "msda_core.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def probe(golden_dir):
+    return torch.load(os.path.join(golden_dir, "msda_index_probe.pt"), weights_only=False)
+
+
+def run_cuda(mod, value, shapes, loc, attn, grad_out, dtype):
+    dev = "cuda"
+    v = value.to(dev, dtype).requires_grad_()
+    l = loc.to(dev).requires_grad_()
+    a = attn.to(dev).requires_grad_()
+    out = mod.ms_deform_attn(v, shapes, l, a)
+    out.backward(grad_out.to(dev, dtype))
+    torch.cuda.synchronize()
+    return out.detach(), v.grad, l.grad, a.grad
+
+
+CASES = ["tiny_nonsquare", "small_dh32", "small_dh64", "small_dh16_L4", "sbase_b2", "syaml_b1"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_matches_reference_golden_and_oracle(cuda_lib, core, name):
+    c = core["cases"][name]
+    value, loc, attn, grad_out = msda.make_inputs(c["seed"], c["B"], c["Lq"], c["H"], c["Dh"], c["shapes"],
+                                                  oob_frac=c["oob_frac"])
+    out, gv, gl, ga = run_cuda(cuda_lib, value, c["shapes"], loc, attn, grad_out, torch.float32)
+    # against the reference's own outputs
+    assert rel_l2(out, c["out"]) < FP32_TOL
+    assert rel_l2(gl, c["grad_loc"]) < FP32_TOL
+    assert rel_l2(ga, c["grad_attn"]) < FP32_TOL
+    if "grad_value" in c:
+        assert rel_l2(gv, c["grad_value"]) < FP32_TOL
+    else:
+        idx, vals = c["grad_value_subset"]
+        assert rel_l2(gv.reshape(-1).cpu()[idx], vals) < FP32_TOL
+        assert abs(gv.double().norm().item() - c["grad_value_norm"]) < FP32_TOL * c["grad_value_norm"]
+    # against the oracle on the same inputs (max-abs as well)
+    o_ref = msda.forward_c(value, c["shapes"], loc, attn)
+    gv_ref, gl_ref, ga_ref = msda.backward_c(grad_out, value, c["shapes"], loc, attn)
+    assert (out.cpu() - o_ref).abs().max() < 1e-4 * o_ref.abs().max()
+    assert rel_l2(gv, gv_ref) < FP32_TOL and rel_l2(gl, gl_ref) < FP32_TOL and rel_l2(ga, ga_ref) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", ["small_dh32", "small_dh64", "small_dh16_L4", "sbase_b2", "syaml_b1"])
+def test_bf16_matches_fp32_reference_on_bf16_rounded_inputs(cuda_lib, core, name):
+    """bf16 contract: value/out/grads in bf16, locations/weights/index math fp32."""
+    c = core["cases"][name]
+    value, loc, attn, grad_out = msda.make_inputs(c["seed"], c["B"], c["Lq"], c["H"], c["Dh"], c["shapes"],
+                                                  oob_frac=c["oob_frac"])
+    v_r, g_r = value.bfloat16().float(), grad_out.bfloat16().float()
+    out, gv, gl, ga = run_cuda(cuda_lib, v_r, c["shapes"], loc, attn, g_r, torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and gv.dtype == torch.bfloat16 and gl.dtype == torch.float32
+    o_ref = msda.forward_c(v_r, c["shapes"], loc, attn)
+    gv_ref, gl_ref, ga_ref = msda.backward_c(g_r, v_r, c["shapes"], loc, attn)
+    assert rel_l2(out, o_ref) < BF16_TOL
+    assert rel_l2(gv, gv_ref) < BF16_TOL
+    assert rel_l2(gl, gl_ref) < BF16_TOL
+    assert rel_l2(ga, ga_ref) < BF16_TOL
+
+
+def _probe_inputs(pts, W, axis):
+    """Identity 'image' spread over heads of 64 channels so that widths up to 320 fit Dh <= 64."""
+    n = pts.numel()
+    Dh = 64
+    H = (W + Dh - 1) // Dh
+    value = torch.zeros(1, W, H, Dh)
+    tok = torch.arange(W)
+    value[0, tok, tok // Dh, tok % Dh] = 1.0
+    loc = torch.zeros(1, n, H, 1, 1, 2)
+    loc[..., axis] = pts.view(1, n, 1, 1, 1)
+    loc[..., 1 - axis] = 0.5
+    shapes = [[1, W]] if axis == 0 else [[W, 1]]
+    return value, loc, torch.ones(1, n, H, 1, 1), shapes
+
+
+@pytest.mark.parametrize("W", [20, 40, 80, 160, 320, 13, 7])
+def test_sampling_index_math_is_bit_exact(cuda_lib, probe, W):
+    """EXACT equality of the sampled identity image (= the bilinear weights, i.e. every bit of ix/iy and every
+    in-bounds decision) with what the reference produced, at pixel centres/edges +-2 ulp and random points."""
+    c = probe["cases"][W]
+    for axis, key in ((0, "x_sparse"), (1, "y_sparse")):
+        value, loc, attn, shapes = _probe_inputs(c["pts"], W, axis)
+        out = cuda_lib.ms_deform_attn(value.cuda(), shapes, loc.cuda(), attn.cuda()).cpu()[0]
+        assert torch.equal(out[:, :W], c[key].to_dense()), f"W={W} axis={axis}"
+        assert torch.count_nonzero(out[:, W:]) == 0
+
+
+@pytest.mark.parametrize("base", [20, 80, 160, 320])
+def test_corner_indices_bit_exact_vs_oracle(cuda_lib, base):
+    shapes = msda.level_shapes(base)
+    adv = msda.adversarial_locations(shapes, H=8, P=4)
+    _, rnd, _, _ = msda.make_inputs(base, 2, 200, 8, 8, shapes, oob_frac=0.3)
+    weird = torch.tensor([float("nan"), float("inf"), -float("inf"), 1e30, -1e30, 0.0, 1.0, -0.0]).repeat(12)
+    weird = weird.view(1, 1, 8, 3, 4, 1).expand(1, 1, 8, 3, 4, 2).contiguous()
+    for loc in (adv, rnd, weird):
+        x0, y0, inb = cuda_lib.ops.ms_deform_attn_corners(loc.cuda(), shapes)
+        rx0, ry0, rinb = msda.corners_c(loc, shapes)
+        assert torch.equal(inb.cpu(), rinb)
+        live = rinb.any(-1)   # fully out-of-bounds taps: corner index is irrelevant (and clamped differently)
+        assert torch.equal(x0.cpu()[live], rx0[live]) and torch.equal(y0.cpu()[live], ry0[live])
+
+
+def test_torch_cuda_grid_sample_obeys_the_same_contract(cuda_lib, probe):
+    """SURVEY.md 7 H1 asks to re-run the probe against torch-CUDA grid_sample on the B200 box: the reference's GPU
+    path (same python code on CUDA tensors) must agree bit-for-bit with the golden taken from its CPU path."""
+    for W in (20, 80, 320):
+        c = probe["cases"][W]
+        n = c["pts"].numel()
+        loc = torch.zeros(1, n, 1, 1, 1, 2)
+        loc[0, :, 0, 0, 0, 0] = c["pts"]
+        loc[0, :, 0, 0, 0, 1] = 0.5
+        out = msda.msda_gridsample_torch(torch.eye(W).view(1, W, 1, W).cuda(), [[1, W]], loc.cuda(),
+                                         torch.ones(1, n, 1, 1, 1).cuda())[0].cpu()
+        assert torch.equal(out, c["x_sparse"].to_dense())
+
+
+def test_full_size_config_properties(cuda_lib):
+    """BASELINE.json config 2 size (S-yaml, B=16, Lq=300, bf16): oracle on one image + size-independent properties
+    (linearity in value, decomposition over attention weights, zero attention -> zero)."""
+    shapes = msda.level_shapes(160)
+    B, Lq, H, Dh = 16, 300, 8, 64
+    value, loc, attn, grad_out = msda.make_inputs(77, B, Lq, H, Dh, shapes, oob_frac=0.2)
+    v, l, a = value.cuda().bfloat16(), loc.cuda(), attn.cuda()
+    out = cuda_lib.ms_deform_attn(v, shapes, l, a)
+    b = 11
+    ref = msda.forward_c(value[b:b + 1].bfloat16().float(), shapes, loc[b:b + 1], attn[b:b + 1])
+    assert rel_l2(out[b:b + 1], ref) < BF16_TOL
+    # linearity in value (fp32 path so that the check is tight)
+    v32 = value.cuda()
+    v2 = torch.randn_like(v32)
+    o1 = cuda_lib.ms_deform_attn(v32, shapes, l, a)
+    o2 = cuda_lib.ms_deform_attn(v2, shapes, l, a)
+    o12 = cuda_lib.ms_deform_attn(v32 + 2.0 * v2, shapes, l, a)
+    assert rel_l2(o12, o1 + 2.0 * o2) < 1e-5
+    # decomposition over levels: sum of per-level outputs == output
+    parts = 0
+    for lvl in range(3):
+        al = torch.zeros_like(a)
+        al[:, :, :, lvl] = a[:, :, :, lvl]
+        parts = parts + cuda_lib.ms_deform_attn(v32, shapes, l, al)
+    assert rel_l2(parts, o1) < 1e-5
+    assert torch.count_nonzero(cuda_lib.ms_deform_attn(v32, shapes, l, torch.zeros_like(a))) == 0
+    # backward at full size against the oracle on one image
+    vv = v32.clone().requires_grad_()
+    ll, aa = l.clone().requires_grad_(), a.clone().requires_grad_()
+    cuda_lib.ms_deform_attn(vv, shapes, ll, aa).backward(grad_out.cuda())
+    gv, gl, ga = msda.backward_c(grad_out[b:b + 1], value[b:b + 1], shapes, loc[b:b + 1], attn[b:b + 1])
+    assert rel_l2(vv.grad[b:b + 1], gv) < FP32_TOL
+    assert rel_l2(ll.grad[b:b + 1], gl) < FP32_TOL and rel_l2(aa.grad[b:b + 1], ga) < FP32_TOL
+
+
+def test_edge_cases(cuda_lib):
+    shapes = [[4, 4]]
+    value = torch.randn(1, 16, 1, 8).cuda()
+    loc = torch.tensor([[-0.5, 0.5], [1.5, 0.5], [0.5, -0.3], [0.5, 1.3], [float("nan"), 0.5], [1e30, 0.5]])
+    loc = loc.view(1, 6, 1, 1, 1, 2).cuda()
+    out = cuda_lib.ms_deform_attn(value, shapes, loc, torch.ones(1, 6, 1, 1, 1).cuda())
+    assert torch.count_nonzero(out) == 0                       # zeros padding, never clamp
+    # single query / single head / 1x1 level; runtime (non-12) sample counts
+    for (B, Lq, H, Dh, shp, P) in [(1, 1, 1, 8, [[1, 1]], 1), (3, 5, 2, 16, [[2, 3], [1, 1]], 2),
+                                   (2, 7, 3, 32, [[5, 4], [3, 2], [2, 1], [1, 1]], 8)]:
+        v, l, a, g = msda.make_inputs(1, B, Lq, H, Dh, shp, P=P, oob_frac=0.3)
+        o = cuda_lib.ms_deform_attn(v.cuda(), shp, l.cuda(), a.cuda())
+        assert rel_l2(o, msda.forward_c(v, shp, l, a)) < FP32_TOL
+    # fp16 values route through fp32 compute
+    v, l, a, g = msda.make_inputs(2, 1, 9, 2, 16, [[6, 6], [3, 3]], P=4)
+    o = cuda_lib.ms_deform_attn(v.cuda().half(), [[6, 6], [3, 3]], l.cuda(), a.cuda())
+    assert o.dtype == torch.float16 and rel_l2(o, msda.forward_c(v.half().float(), [[6, 6], [3, 3]], l, a)) < 2e-3
+    # argument errors raise, they do not fall back
+    with pytest.raises(RuntimeError):
+        cuda_lib.ms_deform_attn(torch.zeros(1, 16, 1, 7).cuda(), shapes, loc, torch.ones(1, 6, 1, 1, 1).cuda())
+    with pytest.raises(RuntimeError):
+        cuda_lib.ms_deform_attn(torch.zeros(1, 15, 1, 8).cuda(), shapes, loc, torch.ones(1, 6, 1, 1, 1).cuda())
+
+
+def test_non_default_stream_and_launch_counter(cuda_lib):
+    shapes = msda.level_shapes(20)
+    v, l, a, g = msda.make_inputs(4, 2, 30, 8, 32, shapes)
+    before = cuda_lib.launch_count()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        o = cuda_lib.ms_deform_attn(v.cuda(), shapes, l.cuda(), a.cuda())
+    s.synchronize()
+    assert cuda_lib.launch_count() == before + 1
+    assert rel_l2(o, msda.forward_c(v, shapes, l, a)) < FP32_TOL
