@@ -73,6 +73,59 @@ int tamtr_msda_backward(const void *grad_out, const void *value, const float *lo
 int tamtr_msda_corners(const float *loc, int32_t *x0, int32_t *y0, uint8_t *inb,
                        int B, int Lq, int H, int L, int P, const int32_t *level_shapes_host, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Sampling locations + attention weights from the fused offset/weight projection.
+ * Replaces ultralytics/nn/modules/transformer.py:278-293 (bias add of the two nn.Linear, softmax over L*P,
+ * loc = ref_xy + off / P * ref_wh * 0.5  [RD == 4]   or   loc = ref_xy + off / (W_l, H_l)  [RD == 2]).
+ *   raw  [M, 3*H*L*P] f32   GEMM output of query x concat(sampling_offsets.weight, attention_weights.weight)^T
+ *                           columns [0, 2*H*L*P) = offsets (h,l,p,xy), then H*L*P logits (h, l*P+p)
+ *   bias [3*H*L*P]    f32   concat(sampling_offsets.bias, attention_weights.bias)
+ *   ref  [M, RL, RD]  f32   RL in {1, L}
+ *   loc  [M, H, L, P, 2], attn [M, H, L, P]  f32
+ * The location arithmetic keeps the reference's op order and per-op fp32 rounding (no FMA contraction).
+ * level_shapes_host may be NULL when RD == 4.
+ */
+int tamtr_locw_forward(const float *raw, const float *bias, const float *ref, float *loc, float *attn,
+                       int M, int H, int L, int P, int RL, int RD, const int32_t *level_shapes_host, void *stream);
+
+/* Backward: grad_raw [M, 3*H*L*P] (gradient w.r.t. the GEMM output, = per-row bias gradient) is fully written;
+ * grad_ref [M, RL, RD] may be NULL (reference boxes are detached in training, transformer.py:889). */
+int tamtr_locw_backward(const float *grad_loc, const float *grad_attn, const float *attn, const float *raw,
+                        const float *bias, const float *ref, float *grad_raw, float *grad_ref,
+                        int M, int H, int L, int P, int RL, int RD, const int32_t *level_shapes_host, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Text-guided classification branch (region-text contrastive head).
+ * Replaces ultralytics/nn/modules/block.py:534-541 ContrastiveHeadMLP.forward:
+ *   out[b,q,k] = <x[b,q,:]/max(|x|,1e-12), w[b,k,:]/max(|w|,1e-12)> * exp(*logit_scale) + *bias
+ *   x [B, Lq, C] f32|bf16 (dtype), w [B, K, C] f32, logit_scale / bias: DEVICE scalars, out [B, Lq, K] f32.
+ * Supported: C % 128 == 0, C <= 1024, K <= 256.
+ */
+int tamtr_contrastive_forward(const void *x, const float *w, const float *logit_scale, const float *bias,
+                              float *out, int dtype, int B, int Lq, int K, int C, void *stream);
+
+/* grad_x [B, Lq, C] (dtype of x); grad_scalars[2] = {d/d logit_scale, d/d bias} (zeroed by the call). */
+int tamtr_contrastive_backward(const float *grad_out, const void *x, const float *w, const float *logit_scale,
+                               void *grad_x, float *grad_scalars, int dtype, int B, int Lq, int K, int C,
+                               void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * BTA-PAN text-image attention gate (max-sigmoid attention), exact-fp32 CUDA-core path.
+ * Replaces ultralytics/nn/extra_modules/block.py:216-220:
+ *   aw[b,m,pix] = sigmoid( max_n <embed[b, m*hc:(m+1)*hc, pix], guide[b,n,m,:]> / sqrt(hc) + bias[m] )
+ *   embed [B, nh*hc, HW] f32|bf16 (NCHW), guide [B, N, nh, hc] f32 (= gl(guide) of block.py:212-213), bias [nh]
+ *   aw [B, nh, HW] f32, amax [B, nh, HW] uint8 (arg max over n, input of the backward)
+ * Supported: hc in {16, 32, 64}, N <= 255.
+ */
+int tamtr_max_sigmoid_forward(const void *embed, const float *guide, const float *bias, float *aw, uint8_t *amax,
+                              int dtype, int B, int nh, int hc, int HW, int N, void *stream);
+
+/* grad_embed [B, nh*hc, HW] (dtype of embed, fully written: the gate's contribution only);
+ * grad_guide [B, N, nh, hc] f32 and grad_bias [nh] f32 are zeroed by the call, then accumulated. */
+int tamtr_max_sigmoid_backward(const float *grad_aw, const float *aw, const uint8_t *amax, const void *embed,
+                               const float *guide, void *grad_embed, float *grad_guide, float *grad_bias,
+                               int dtype, int B, int nh, int hc, int HW, int N, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

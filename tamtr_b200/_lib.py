@@ -27,6 +27,12 @@ _SIGNATURES = {
     "tamtr_msda_forward": (ctypes.c_int, [_vp, _fp, _fp, _vp, _i] + [_i] * 7 + [_vp, _vp]),
     "tamtr_msda_backward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _i] + [_i] * 7 + [_vp, _vp]),
     "tamtr_msda_corners": (ctypes.c_int, [_fp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp]),
+    "tamtr_locw_forward": (ctypes.c_int, [_fp] * 5 + [_i] * 6 + [_vp, _vp]),
+    "tamtr_locw_backward": (ctypes.c_int, [_fp] * 8 + [_i] * 6 + [_vp, _vp]),
+    "tamtr_contrastive_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp] + [_i] * 5 + [_vp]),
+    "tamtr_contrastive_backward": (ctypes.c_int, [_fp, _vp, _fp, _fp, _vp, _fp] + [_i] * 5 + [_vp]),
+    "tamtr_max_sigmoid_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _vp] + [_i] * 6 + [_vp]),
+    "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }
 
 

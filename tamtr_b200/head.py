@@ -1,0 +1,261 @@
+"""Detection heads around the hot path: host-side glue mirroring the reference's heads.
+
+  RTDETRDecoder      ultralytics/nn/modules/head.py:174-435
+  ManbaWorldDecoder  ultralytics/nn/modules/head.py:1005-1290   (the head TAMTR.yaml:67 builds: "MEH")
+  get_cdn_group      ultralytics/models/utils/ops.py:152-291    (contrastive denoising queries)
+
+Same constructor arguments, forward signatures, outputs and state_dict keys.  The glue (1x1 input projection,
+anchors, top-k query selection, denoising group) stays a sequence of library ops as in the reference; the decoder it
+drives runs on the sm_100a kernels (modules.py).  ManbaWorldDecoder's VSSBlocks (VMamba selective scan, an external
+CUDA extension that is not part of the reference tree -- SURVEY.md section 8c) are NOT on this path: they are
+represented by `nn.Identity` placeholders, exactly as the parity oracle does, and a checkpoint's `VSSBlocks.*`
+entries are ignored on load.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .modules import (MLP, ContrastiveHeadMLP, DeformableTransformerDecoder, DeformableTransformerDecoderLayer,
+                      TextDeformableTransformerDecoder)
+
+__all__ = ("RTDETRDecoder", "ManbaWorldDecoder", "get_cdn_group")
+
+
+def _xywh_to_xyxy(b):
+    half = b[..., 2:] / 2
+    return torch.cat([b[..., :2] - half, b[..., :2] + half], -1)
+
+
+def _xyxy_to_xywh(b):
+    return torch.cat([(b[..., :2] + b[..., 2:]) / 2, b[..., 2:] - b[..., :2]], -1)
+
+
+def get_cdn_group(batch, num_classes, num_queries, class_embed, num_dn=100, cls_noise_ratio=0.5,
+                  box_noise_scale=1.0, training=False):
+    """Contrastive denoising group (ops.py:152-291).  Consumes the global RNG in the same order as the reference
+    (label mask, replacement labels, box-noise sign, box-noise magnitude), so seeded runs produce the same queries.
+
+    batch: {'cls' [n], 'bboxes' [n,4] (cx,cy,w,h), 'batch_idx' [n], 'gt_groups' [B ints]}.
+    Returns (dn_embed [B,num_dn,hd], dn_bbox [B,num_dn,4] (logit space), attn_mask [Lq,Lq] bool, dn_meta)."""
+    if (not training) or num_dn <= 0:
+        return None, None, None, None
+    groups = batch["gt_groups"]
+    total, biggest = sum(groups), max(groups)
+    if biggest == 0:
+        return None, None, None, None
+    n_group = max(1, num_dn // biggest)
+    bs = len(groups)
+    gt_cls, gt_box, gt_img = batch["cls"], batch["bboxes"], batch["batch_idx"]
+
+    # every group holds one positive and one negative copy of each ground truth
+    dn_cls = gt_cls.repeat(2 * n_group)
+    dn_box = gt_box.repeat(2 * n_group, 1)
+    dn_img = gt_img.repeat(2 * n_group).view(-1)
+    negatives = torch.arange(total * n_group, dtype=torch.long, device=gt_box.device) + n_group * total
+
+    if cls_noise_ratio > 0:
+        flip = torch.rand(dn_cls.shape) < (cls_noise_ratio * 0.5)
+        where = torch.nonzero(flip).squeeze(-1)
+        dn_cls[where] = torch.randint_like(where, 0, num_classes, dtype=dn_cls.dtype, device=dn_cls.device)
+
+    if box_noise_scale > 0:
+        corners = _xywh_to_xyxy(dn_box)
+        span = (dn_box[..., 2:] * 0.5).repeat(1, 2) * box_noise_scale
+        sign = torch.randint_like(dn_box, 0, 2) * 2.0 - 1.0
+        mag = torch.rand_like(dn_box)
+        mag[negatives] += 1.0            # negatives are pushed 1x..2x the half-size away
+        mag *= sign
+        corners += mag * span
+        corners.clip_(min=0.0, max=1.0)
+        dn_box = torch.logit(_xyxy_to_xywh(corners), eps=1e-6)
+
+    n_dn = int(biggest * 2 * n_group)
+    dev = class_embed.device
+    embed = class_embed[dn_cls.to(dev)]
+    # (the reference fills fp32 buffers on the targets' device and moves them afterwards, ops.py:243-262; filling
+    #  them on the embedding's device is the same result without a host round trip)
+    pad_embed = torch.zeros(bs, n_dn, embed.shape[-1], device=dev, dtype=embed.dtype)
+    pad_box = torch.zeros(bs, n_dn, 4, device=dev, dtype=dn_box.dtype)
+    slot = torch.cat([torch.arange(n, dtype=torch.long) for n in groups])
+    pos_idx = torch.stack([slot + biggest * i for i in range(n_group)], dim=0)
+    slot = torch.cat([slot + biggest * i for i in range(2 * n_group)])
+    where = (dn_img.to(dev).long(), slot.to(dev))
+    pad_embed[where] = embed
+    pad_box[where] = dn_box.to(dev)
+
+    size = n_dn + num_queries
+    mask = torch.zeros([size, size], dtype=torch.bool)
+    mask[n_dn:, :n_dn] = True                       # matching queries never see the denoising queries
+    for i in range(n_group):                        # denoising groups never see each other
+        lo, hi = biggest * 2 * i, biggest * 2 * (i + 1)
+        mask[lo:hi, hi:n_dn] = True
+        mask[lo:hi, :lo] = True
+    meta = {"dn_pos_idx": [p.reshape(-1) for p in pos_idx.cpu().split(list(groups), dim=1)],
+            "dn_num_group": n_group, "dn_num_split": [n_dn, num_queries]}
+    return pad_embed, pad_box, mask.to(dev), meta
+
+
+class _HeadBase(nn.Module):
+    """What RTDETRDecoder and ManbaWorldDecoder share (head.py:184-435 / 1015-1290)."""
+    export = False
+
+    def _build_common(self, nc, ch, hd, nq, nd, label_noise_ratio, box_noise_scale, learnt_init_query):
+        self.hidden_dim = hd
+        self.nl = len(ch)
+        self.nc = nc
+        self.num_queries = nq
+        self.input_proj = nn.ModuleList(
+            nn.Sequential(nn.Conv2d(c, hd, 1, bias=False), nn.BatchNorm2d(hd)) for c in ch)
+        self.denoising_class_embed = nn.Embedding(nc + 1, hd)
+        self.num_denoising = nd
+        self.label_noise_ratio = label_noise_ratio
+        self.box_noise_scale = box_noise_scale
+        self.learnt_init_query = learnt_init_query
+        if learnt_init_query:
+            self.tgt_embed = nn.Embedding(nq, hd)
+        self.query_pos_head = MLP(4, 2 * hd, hd, num_layers=2)
+        self.enc_output = nn.Sequential(nn.Linear(hd, hd), nn.LayerNorm(hd))
+        self.enc_score_head = nn.Linear(hd, nc)
+        self.enc_bbox_head = MLP(hd, hd, 4, num_layers=3)
+
+    @staticmethod
+    def _generate_anchors(shapes, grid_size=0.05, dtype=torch.float32, device="cpu", eps=1e-2):
+        """One anchor per pyramid cell: centre (x+0.5)/W, (y+0.5)/H, size grid_size * 2^level; returned in logit
+        space with invalid (too close to the border) anchors set to +inf (head.py:1177-1200)."""
+        per_level = []
+        for lvl, (h, w) in enumerate(shapes):
+            ys = torch.arange(end=h, dtype=dtype, device=device)
+            xs = torch.arange(end=w, dtype=dtype, device=device)
+            gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+            centre = (torch.stack([gx, gy], -1).unsqueeze(0) + 0.5) / torch.tensor([h, w], dtype=dtype, device=device)
+            size = torch.ones_like(centre) * grid_size * (2.0 ** lvl)
+            per_level.append(torch.cat([centre, size], -1).view(-1, h * w, 4))
+        anchors = torch.cat(per_level, 1)
+        valid = ((anchors > eps) * (anchors < 1 - eps)).all(-1, keepdim=True)
+        anchors = torch.log(anchors / (1 - anchors)).masked_fill(~valid, float("inf"))
+        return anchors, valid
+
+    def _get_encoder_input(self, x):
+        feats, shapes = [], []
+        for proj, fmap in zip(self.input_proj, x):
+            f = proj(fmap)
+            shapes.append([f.shape[2], f.shape[3]])
+            feats.append(f.flatten(2).permute(0, 2, 1))
+        return torch.cat(feats, 1), shapes
+
+    def _get_decoder_input(self, feats, shapes, dn_embed=None, dn_bbox=None):
+        bs = len(feats)
+        anchors, valid = self._generate_anchors(shapes, dtype=feats.dtype, device=feats.device)
+        features = self.enc_output(valid * feats)
+        scores = self.enc_score_head(features)
+        topk = torch.topk(scores.max(-1).values, self.num_queries, dim=1).indices.view(-1)
+        img = torch.arange(end=bs, dtype=topk.dtype).unsqueeze(-1).repeat(1, self.num_queries).view(-1)
+        top_feats = features[img, topk].view(bs, self.num_queries, -1)
+        top_anchors = anchors[:, topk].view(bs, self.num_queries, -1)
+        refer_bbox = self.enc_bbox_head(top_feats) + top_anchors
+        enc_bboxes = refer_bbox.sigmoid()
+        if dn_bbox is not None:
+            refer_bbox = torch.cat([dn_bbox, refer_bbox], 1)
+        enc_scores = scores[img, topk].view(bs, self.num_queries, -1)
+        embeddings = self.tgt_embed.weight.unsqueeze(0).repeat(bs, 1, 1) if self.learnt_init_query else top_feats
+        if self.training:
+            refer_bbox = refer_bbox.detach()
+            if not self.learnt_init_query:
+                embeddings = embeddings.detach()
+        if dn_embed is not None:
+            embeddings = torch.cat([dn_embed, embeddings], 1)
+        return embeddings, refer_bbox, enc_bboxes, enc_scores
+
+    def _cdn(self, batch):
+        return get_cdn_group(batch, self.nc, self.num_queries, self.denoising_class_embed.weight,
+                             self.num_denoising, self.label_noise_ratio, self.box_noise_scale, self.training)
+
+    def _finish(self, dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta):
+        x = dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta
+        if self.training:
+            return x
+        y = torch.cat((dec_bboxes.squeeze(0), dec_scores.squeeze(0).sigmoid()), -1)
+        return y if self.export else (y, x)
+
+    def _reset_common(self):
+        bias_cls = float(-math.log((1 - 0.01) / 0.01)) / 80 * self.nc
+        nn.init.constant_(self.enc_score_head.bias, bias_cls)
+        nn.init.zeros_(self.enc_bbox_head.layers[-1].weight)
+        nn.init.zeros_(self.enc_bbox_head.layers[-1].bias)
+        for reg in self.dec_bbox_head:
+            nn.init.zeros_(reg.layers[-1].weight)
+            nn.init.zeros_(reg.layers[-1].bias)
+        nn.init.xavier_uniform_(self.enc_output[0].weight)
+        bound = 1 / math.sqrt(self.enc_output[0].weight.shape[0])
+        nn.init.uniform_(self.enc_output[0].bias, -bound, bound)
+        if self.learnt_init_query:
+            nn.init.xavier_uniform_(self.tgt_embed.weight)
+        nn.init.xavier_uniform_(self.query_pos_head.layers[0].weight)
+        nn.init.xavier_uniform_(self.query_pos_head.layers[1].weight)
+        for layer in self.input_proj:
+            nn.init.xavier_uniform_(layer[0].weight)
+        return bias_cls
+
+
+class RTDETRDecoder(_HeadBase):
+    """RT-DETR head (head.py:174-435): forward(x: list of NCHW maps, batch=None)."""
+
+    def __init__(self, nc=80, ch=(512, 1024, 2048), hd=256, nq=300, ndp=4, nh=8, ndl=6, d_ffn=1024, eval_idx=-1,
+                 dropout=0., act=nn.ReLU(), nd=100, label_noise_ratio=0.5, box_noise_scale=1.0,
+                 learnt_init_query=False):
+        super().__init__()
+        self.nhead = nh
+        self.num_decoder_layers = ndl
+        self._build_common(nc, ch, hd, nq, nd, label_noise_ratio, box_noise_scale, learnt_init_query)
+        layer = DeformableTransformerDecoderLayer(hd, nh, d_ffn, dropout, act, self.nl, ndp)
+        self.decoder = DeformableTransformerDecoder(hd, layer, ndl, eval_idx)
+        self.dec_score_head = nn.ModuleList([nn.Linear(hd, nc) for _ in range(ndl)])
+        self.dec_bbox_head = nn.ModuleList([MLP(hd, hd, 4, num_layers=3) for _ in range(ndl)])
+        bias_cls = self._reset_common()
+        for cls in self.dec_score_head:
+            nn.init.constant_(cls.bias, bias_cls)
+
+    def forward(self, x, batch=None):
+        feats, shapes = self._get_encoder_input(x)
+        dn_embed, dn_bbox, attn_mask, dn_meta = self._cdn(batch)
+        embed, refer_bbox, enc_bboxes, enc_scores = self._get_decoder_input(feats, shapes, dn_embed, dn_bbox)
+        dec_bboxes, dec_scores = self.decoder(embed, refer_bbox, feats, shapes, self.dec_bbox_head,
+                                              self.dec_score_head, self.query_pos_head, attn_mask=attn_mask)
+        return self._finish(dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta)
+
+
+class ManbaWorldDecoder(_HeadBase):
+    """TAM-TR's Multi-modal Encoder-decoder Head (head.py:1005-1290): forward(x, text [B,K,512], batch=None).
+
+    `VSSBlocks` are identity placeholders (see module docstring); `dims`/`drop_path` are accepted and ignored."""
+
+    def __init__(self, nc=80, ch=(512, 1024, 2048), hd=512, nq=300, ndp=4, nh=8, ndl=6, d_ffn=1024, eval_idx=-1,
+                 dropout=0., act=nn.ReLU(), nd=100, label_noise_ratio=0.5, box_noise_scale=1.0,
+                 learnt_init_query=False, dims=(128, 256, 512), drop_path=(0.1, 0.1, 0.1), embed=512, with_bn=False):
+        super().__init__()
+        if with_bn:
+            raise NotImplementedError("tamtr_b200: BNContrastiveHeadMLP (with_bn=True) is not on the TAMTR.yaml path")
+        self.nhead = nh
+        self.num_decoder_layers = ndl
+        self._build_common(nc, ch, hd, nq, nd, label_noise_ratio, box_noise_scale, learnt_init_query)
+        self.VSSBlocks = nn.ModuleList(nn.Identity() for _ in dims)
+        self.num_Blocks = len(dims)
+        layer = DeformableTransformerDecoderLayer(hd, nh, d_ffn, dropout, act, self.nl, ndp)
+        self.decoder = TextDeformableTransformerDecoder(hd, layer, ndl, eval_idx)
+        self.dec_score_head = nn.ModuleList([ContrastiveHeadMLP() for _ in range(ndl)])
+        self.dec_bbox_head = nn.ModuleList([MLP(hd, hd, 4, num_layers=3) for _ in range(ndl)])
+        self._reset_common()
+
+    def forward(self, x, text, batch=None):
+        x = [blk(f) for blk, f in zip(self.VSSBlocks, x)]
+        feats, shapes = self._get_encoder_input(x)
+        dn_embed, dn_bbox, attn_mask, dn_meta = self._cdn(batch)
+        embed, refer_bbox, enc_bboxes, enc_scores = self._get_decoder_input(feats, shapes, dn_embed, dn_bbox)
+        dec_bboxes, dec_scores = self.decoder(embed, refer_bbox, feats, shapes, text, self.dec_bbox_head,
+                                              self.dec_score_head, self.query_pos_head, attn_mask=attn_mask)
+        return self._finish(dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        state_dict = {k: v for k, v in state_dict.items() if not k.startswith("VSSBlocks.")}
+        return super().load_state_dict(state_dict, strict=strict, **kw)

@@ -1,0 +1,247 @@
+"""Host-side mirror of the reference's module interface for the detection-head hot path.
+
+Same class names, constructor arguments, forward signatures, attribute / parameter names (state_dict keys) and
+error behaviour as the reference, so its checkpoints load and its callers (`parse_model`, `RTDETRDecoder`,
+`ManbaWorldDecoder`) can use these classes unchanged -- but the arithmetic the north star names runs in the
+hand-written sm_100a kernels behind include/tamtr_b200.h (ops.py).  Everything else (GEMMs, LayerNorm, the small
+query self-attention) is a library call, as in the reference.
+
+Reference classes mirrored (file:line under /root/reference/ultralytics):
+  MLP                                  nn/modules/transformer.py:162-176
+  MSDeformAttn                         nn/modules/transformer.py:204-299
+  DeformableTransformerDecoderLayer    nn/modules/transformer.py:498-558
+  DeformableTransformerDecoder         nn/modules/transformer.py:662-716
+  TextDeformableTransformerDecoder     nn/modules/transformer.py:835-891
+  ContrastiveHeadMLP                   nn/modules/block.py:522-541
+  MaxSigmoidAttnBlock                  nn/extra_modules/block.py:194-226
+  inverse_sigmoid                      nn/modules/utils.py:34-39
+"""
+import copy
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+__all__ = ("MLP", "MSDeformAttn", "DeformableTransformerDecoderLayer", "DeformableTransformerDecoder",
+           "TextDeformableTransformerDecoder", "ContrastiveHeadMLP", "MaxSigmoidAttnBlock", "inverse_sigmoid")
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    """log(x / (1 - x)) with both terms clamped to eps (utils.py:34-39)."""
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def _clones(module, n):
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
+
+
+class MLP(nn.Module):
+    """Linear -> ReLU -> ... -> Linear (transformer.py:162-176); parameters live under `layers.{i}`."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        dims = [input_dim] + [hidden_dim] * (num_layers - 1) + [output_dim]
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+
+    def forward(self, x):
+        last = self.num_layers - 1
+        for i, layer in enumerate(self.layers):
+            x = layer(x) if i == last else F.relu(layer(x))
+        return x
+
+
+class MSDeformAttn(nn.Module):
+    """Multi-scale deformable attention (transformer.py:204-299) on the sm_100a sampler.
+
+    forward(query [B,Lq,C], refer_bbox [B,Lq,n_levels|1,2|4], value [B,Lv,C], value_shapes [[h,w]]*L,
+            value_mask [B,Lv] | None) -> [B,Lq,C]
+    """
+
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
+        self.im2col_step = 64
+        self.d_model = d_model
+        self.n_levels = n_levels
+        self.n_heads = n_heads
+        self.n_points = n_points
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        # transformer.py:234-250: offsets start as a ring of directions (one per head) scaled by the point index,
+        # attention logits start at zero (uniform 1/(L*P) weights), projections are Xavier.
+        nn.init.zeros_(self.sampling_offsets.weight)
+        theta = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+        ring = torch.stack([theta.cos(), theta.sin()], -1)
+        ring = ring / ring.abs().max(-1, keepdim=True)[0]
+        ring = ring.view(self.n_heads, 1, 1, 2).repeat(1, self.n_levels, self.n_points, 1)
+        ring = ring * torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, self.n_points, 1)
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(ring.reshape(-1))
+        nn.init.zeros_(self.attention_weights.weight)
+        nn.init.zeros_(self.attention_weights.bias)
+        nn.init.xavier_uniform_(self.value_proj.weight)
+        nn.init.zeros_(self.value_proj.bias)
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        nn.init.zeros_(self.output_proj.bias)
+
+    def forward(self, query, refer_bbox, value, value_shapes, value_mask=None):
+        bs, len_q = query.shape[:2]
+        len_v = value.shape[1]
+        assert sum(s[0] * s[1] for s in value_shapes) == len_v
+        value = self.value_proj(value)
+        if value_mask is not None:
+            value = value.masked_fill(value_mask[..., None], float(0))
+        value = value.view(bs, len_v, self.n_heads, self.d_model // self.n_heads)
+        loc, attn = ops.sampling_locations_and_weights(
+            query, refer_bbox, self.sampling_offsets.weight, self.sampling_offsets.bias,
+            self.attention_weights.weight, self.attention_weights.bias, value_shapes,
+            self.n_heads, self.n_levels, self.n_points)
+        out = ops.ms_deform_attn(value, value_shapes, loc, attn)
+        return self.output_proj(out)
+
+
+class DeformableTransformerDecoderLayer(nn.Module):
+    """Self-attention -> deformable cross-attention -> FFN, post-norm (transformer.py:498-558)."""
+
+    def __init__(self, d_model=256, n_heads=8, d_ffn=1024, dropout=0., act=nn.ReLU(), n_levels=4, n_points=4):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.cross_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout2 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.act = act
+        self.dropout3 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout4 = nn.Dropout(dropout)
+        self.norm3 = nn.LayerNorm(d_model)
+
+    @staticmethod
+    def with_pos_embed(tensor, pos):
+        return tensor if pos is None else tensor + pos
+
+    def forward_ffn(self, tgt):
+        tgt2 = self.linear2(self.dropout3(self.act(self.linear1(tgt))))
+        return self.norm3(tgt + self.dropout4(tgt2))
+
+    def forward(self, embed, refer_bbox, feats, shapes, padding_mask=None, attn_mask=None, query_pos=None):
+        q = k = self.with_pos_embed(embed, query_pos)
+        # need_weights=False: the reference discards the averaged attention map ([0] only, transformer.py:546-547),
+        # so the fused SDPA kernels can be used; the output is the same.
+        tgt = self.self_attn(q.transpose(0, 1), k.transpose(0, 1), embed.transpose(0, 1), attn_mask=attn_mask,
+                             need_weights=False)[0].transpose(0, 1)
+        embed = self.norm1(embed + self.dropout1(tgt))
+        tgt = self.cross_attn(self.with_pos_embed(embed, query_pos), refer_bbox.unsqueeze(2), feats, shapes,
+                              padding_mask)
+        embed = self.norm2(embed + self.dropout2(tgt))
+        return self.forward_ffn(embed)
+
+
+class _DecoderBase(nn.Module):
+    def __init__(self, hidden_dim, decoder_layer, num_layers, eval_idx=-1):
+        super().__init__()
+        self.layers = _clones(decoder_layer, num_layers)
+        self.num_layers = num_layers
+        self.hidden_dim = hidden_dim
+        self.eval_idx = eval_idx if eval_idx >= 0 else num_layers + eval_idx
+
+    def _run(self, embed, refer_bbox, feats, shapes, bbox_head, score_fn, pos_mlp, attn_mask, padding_mask):
+        output = embed
+        dec_bboxes, dec_cls = [], []
+        last_refined = None
+        refer_bbox = refer_bbox.sigmoid()
+        for i, layer in enumerate(self.layers):
+            output = layer(output, refer_bbox, feats, shapes, padding_mask, attn_mask, pos_mlp(refer_bbox))
+            bbox = bbox_head[i](output)
+            refined = torch.sigmoid(bbox + inverse_sigmoid(refer_bbox))
+            if self.training:
+                dec_cls.append(score_fn(i, output))
+                dec_bboxes.append(refined if i == 0 else torch.sigmoid(bbox + inverse_sigmoid(last_refined)))
+            elif i == self.eval_idx:
+                dec_cls.append(score_fn(i, output))
+                dec_bboxes.append(refined)
+                break
+            last_refined = refined
+            refer_bbox = refined.detach() if self.training else refined
+        return torch.stack(dec_bboxes), torch.stack(dec_cls)
+
+
+class DeformableTransformerDecoder(_DecoderBase):
+    """transformer.py:662-716; score heads are plain Linear layers."""
+
+    def forward(self, embed, refer_bbox, feats, shapes, bbox_head, score_head, pos_mlp, attn_mask=None,
+                padding_mask=None):
+        return self._run(embed, refer_bbox, feats, shapes, bbox_head, lambda i, x: score_head[i](x), pos_mlp,
+                         attn_mask, padding_mask)
+
+
+class TextDeformableTransformerDecoder(_DecoderBase):
+    """transformer.py:835-891; score heads take the text embeddings (ContrastiveHeadMLP)."""
+
+    def forward(self, embed, refer_bbox, feats, shapes, text, bbox_head, score_head, pos_mlp, attn_mask=None,
+                padding_mask=None):
+        return self._run(embed, refer_bbox, feats, shapes, bbox_head, lambda i, x: score_head[i](x, text), pos_mlp,
+                         attn_mask, padding_mask)
+
+
+class ContrastiveHeadMLP(nn.Module):
+    """Region-text similarity (block.py:522-541): cosine(x[b,q,:], w[b,k,:]) * exp(logit_scale) + bias."""
+
+    def __init__(self):
+        super().__init__()
+        self.bias = nn.Parameter(torch.tensor([-10.0]))
+        self.logit_scale = nn.Parameter(torch.ones([]) * torch.tensor(1 / 0.07).log())
+
+    def forward(self, x, w):
+        return ops.contrastive_head(x, w, self.logit_scale, self.bias)
+
+
+class _ConvBN(nn.Module):
+    """ultralytics Conv(c1, c2, k, act=False) = Conv2d(bias=False) + BatchNorm2d, keys `conv.*` / `bn.*`
+    (nn/modules/conv.py:23-40)."""
+
+    def __init__(self, c1, c2, k):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, c2, k, 1, k // 2, bias=False)
+        self.bn = nn.BatchNorm2d(c2)
+        self.act = nn.Identity()
+
+    def forward(self, x):
+        return self.bn(self.conv(x))
+
+
+class MaxSigmoidAttnBlock(nn.Module):
+    """BTA-PAN text-image attention (extra_modules/block.py:194-226): per head, the max over text tokens of
+    <x, gl(guide)> / sqrt(hc) + bias, through a sigmoid, gates a 3x3 conv of x."""
+
+    def __init__(self, c1, c2, nh=1, ec=128, gc=512, scale=False):
+        super().__init__()
+        self.nh = nh
+        self.hc = c2 // nh
+        self.ec = _ConvBN(c1, ec, 1) if c1 != ec else None
+        self.gl = nn.Linear(gc, ec)
+        self.bias = nn.Parameter(torch.zeros(nh))
+        self.proj_conv = _ConvBN(c1, c2, 3)
+        self.scale = nn.Parameter(torch.ones(1, nh, 1, 1)) if scale else 1.0
+
+    def forward(self, x, guide):
+        bs, _, h, w = x.shape
+        guide = self.gl(guide).view(bs, -1, self.nh, self.hc)
+        embed = self.ec(x) if self.ec is not None else x
+        aw = ops.max_sigmoid_gate(embed, guide, self.bias, self.nh)          # [B, nh, H, W]
+        aw = aw * self.scale
+        y = self.proj_conv(x).view(bs, self.nh, -1, h, w)
+        return (y * aw.unsqueeze(2).to(y.dtype)).view(bs, -1, h, w)

@@ -88,3 +88,191 @@ def ms_deform_attn_corners(sampling_locations, value_spatial_shapes):
                                            B, Lq, H, L, P, sh, _lib.stream_ptr(loc.device))
     _lib.check(rc, "msda_corners")
     return x0, y0, inb
+
+
+# ------------------------------------------------------------------------------------ offsets / weights projection
+def _proj_gemm(q2, w_cat):
+    """[M,C] x [N,C]^T -> fp32 [M,N].  fp32 inputs: fp32 GEMM; 16-bit inputs: tensor-core GEMM with fp32 accumulate
+    and fp32 OUTPUT, so locations never pass through a 16-bit rounding."""
+    if q2.dtype == torch.float32:
+        return q2 @ w_cat.t()
+    return torch.mm(q2, w_cat.t(), out_dtype=torch.float32)
+
+
+class _LocWFn(torch.autograd.Function):
+    """q2 [M,C], w_cat [3*H*S, C], b_cat [3*H*S], ref [M,RL,RD] -> loc [M,H,L,P,2], attn [M,H,L,P] (fp32).
+
+    forward  = one library GEMM (both Linears of transformer.py:278-279 share their input) + tamtr_locw_forward
+    backward = tamtr_locw_backward + two library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, q2, w_cat, b_cat, ref, shapes, H, L, P):
+        lp = q2.dtype if q2.dtype in (torch.bfloat16, torch.float16) else torch.float32
+        if torch.is_autocast_enabled():
+            lp = torch.get_autocast_dtype("cuda")
+        q2c = q2.contiguous().to(lp)
+        w_c = w_cat.to(lp)
+        raw = _proj_gemm(q2c, w_c)
+        bias = b_cat.contiguous().float()
+        ref32 = ref.contiguous().float()
+        M = raw.shape[0]
+        RL, RD = ref32.shape[-2], ref32.shape[-1]
+        if RD not in (2, 4):
+            raise ValueError(f"Last dim of reference_points must be 2 or 4, but got {RD}.")  # transformer.py:295
+        loc = torch.empty(M, H, L, P, 2, dtype=torch.float32, device=raw.device)
+        attn = torch.empty(M, H, L, P, dtype=torch.float32, device=raw.device)
+        sh, _ = _lib.shapes_array(shapes)
+        with _with_device(raw):
+            rc = _lib.lib().tamtr_locw_forward(raw.data_ptr(), bias.data_ptr(), ref32.data_ptr(), loc.data_ptr(),
+                                               attn.data_ptr(), M, H, L, P, RL, RD, sh, _lib.stream_ptr(raw.device))
+        _lib.check(rc, "locw_forward")
+        ctx.save_for_backward(q2c, w_c, raw, bias, ref32, attn)
+        ctx.dims = (M, H, L, P, RL, RD)
+        ctx.shapes = [list(map(int, s)) for s in shapes]
+        ctx.in_dtypes = (q2.dtype, w_cat.dtype, b_cat.dtype, ref.dtype)
+        return loc, attn
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loc, grad_attn):
+        q2c, w_c, raw, bias, ref32, attn = ctx.saved_tensors
+        M, H, L, P, RL, RD = ctx.dims
+        grad_loc = grad_loc.contiguous().float()
+        grad_attn = grad_attn.contiguous().float()
+        grad_raw = torch.empty_like(raw)
+        need_ref = ctx.needs_input_grad[3]
+        grad_ref = torch.empty_like(ref32) if need_ref else None
+        sh, _ = _lib.shapes_array(ctx.shapes)
+        with _with_device(raw):
+            rc = _lib.lib().tamtr_locw_backward(grad_loc.data_ptr(), grad_attn.data_ptr(), attn.data_ptr(),
+                                                raw.data_ptr(), bias.data_ptr(), ref32.data_ptr(),
+                                                grad_raw.data_ptr(), grad_ref.data_ptr() if need_ref else None,
+                                                M, H, L, P, RL, RD, sh, _lib.stream_ptr(raw.device))
+        _lib.check(rc, "locw_backward")
+        qd, wd, bd, rd = ctx.in_dtypes
+        g_lp = grad_raw.to(w_c.dtype)
+        grad_q = (g_lp @ w_c).to(qd) if ctx.needs_input_grad[0] else None
+        grad_w = None
+        if ctx.needs_input_grad[1]:
+            grad_w = (g_lp.t() @ q2c if w_c.dtype == torch.float32
+                      else torch.mm(g_lp.t(), q2c, out_dtype=torch.float32)).to(wd)
+        grad_b = grad_raw.sum(0).to(bd) if ctx.needs_input_grad[2] else None
+        return grad_q, grad_w, grad_b, (grad_ref.to(rd) if need_ref else None), None, None, None, None
+
+
+def sampling_locations_and_weights(query, refer_bbox, w_off, b_off, w_attn, b_attn, value_shapes, n_heads, n_levels,
+                                   n_points):
+    """transformer.py:278-293 as one GEMM + one fused epilogue kernel.
+
+    query [B,Lq,C]; refer_bbox [B,Lq,RL,2|4]; returns loc [B,Lq,H,L,P,2] and attn [B,Lq,H,L,P], both fp32
+    (index math and softmax stay fp32 whatever the activation dtype)."""
+    _lib.require_cuda(query, refer_bbox)
+    B, Lq, C = query.shape
+    w_cat = torch.cat([w_off, w_attn], 0)
+    b_cat = torch.cat([b_off, b_attn], 0)
+    ref = refer_bbox.reshape(B * Lq, refer_bbox.shape[-2], refer_bbox.shape[-1])
+    loc, attn = _LocWFn.apply(query.reshape(B * Lq, C), w_cat, b_cat, ref, value_shapes, n_heads, n_levels, n_points)
+    return (loc.view(B, Lq, n_heads, n_levels, n_points, 2), attn.view(B, Lq, n_heads, n_levels, n_points))
+
+
+# ------------------------------------------------------------------------------------ contrastive head
+class _ContrastiveFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, logit_scale, bias):
+        x = x.contiguous()
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        w32 = w.contiguous().float()
+        ls = logit_scale.detach().reshape(1).float().contiguous()
+        bs = bias.detach().reshape(1).float().contiguous()
+        B, Lq, C = x.shape
+        K = w32.shape[1]
+        out = torch.empty(B, Lq, K, dtype=torch.float32, device=x.device)
+        with _with_device(x):
+            rc = _lib.lib().tamtr_contrastive_forward(x.data_ptr(), w32.data_ptr(), ls.data_ptr(), bs.data_ptr(),
+                                                      out.data_ptr(), _lib.dtype_code(x), B, Lq, K, C,
+                                                      _lib.stream_ptr(x.device))
+        _lib.check(rc, "contrastive_forward")
+        ctx.save_for_backward(x, w32, ls, bs, out)
+        ctx.w_dtype = w.dtype
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        x, w32, ls, bs, out = ctx.saved_tensors
+        B, Lq, C = x.shape
+        K = w32.shape[1]
+        grad_out = grad_out.contiguous().float()
+        grad_x = torch.empty_like(x)
+        scal = torch.empty(2, dtype=torch.float32, device=x.device)
+        with _with_device(x):
+            rc = _lib.lib().tamtr_contrastive_backward(grad_out.data_ptr(), x.data_ptr(), w32.data_ptr(),
+                                                       ls.data_ptr(), grad_x.data_ptr(), scal.data_ptr(),
+                                                       _lib.dtype_code(x), B, Lq, K, C, _lib.stream_ptr(x.device))
+        _lib.check(rc, "contrastive_backward")
+        grad_w = None
+        if ctx.needs_input_grad[1]:
+            # Text embeddings come from a frozen text model in TAM-TR (rtdetrworld/train.py:147-152), so this branch
+            # is off the hot path; it is a [K,Lq]x[Lq,C] library GEMM per image plus the normalisation Jacobian.
+            xh = torch.nn.functional.normalize(x.float(), dim=-1, eps=1e-12)
+            wn = w32.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+            wh = w32 / wn
+            g_wh = torch.einsum("bqk,bqc->bkc", grad_out * ls.exp(), xh)
+            grad_w = ((g_wh - wh * (wh * g_wh).sum(-1, keepdim=True)) / wn).to(ctx.w_dtype)
+        return grad_x, grad_w, scal[0].reshape(()), scal[1].reshape(1)
+
+
+def contrastive_head(x, w, logit_scale, bias):
+    """block.py:534-541: x [B,Lq,C], w [B,K,C] -> [B,Lq,K]."""
+    _lib.require_cuda(x, w)
+    out = _ContrastiveFn.apply(x, w, logit_scale, bias)
+    return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+
+# ------------------------------------------------------------------------------------ max-sigmoid gate
+class _MaxSigmoidFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, embed, guide, bias, nh):
+        embed = embed.contiguous()
+        if embed.dtype not in (torch.float32, torch.bfloat16):
+            embed = embed.float()
+        B, C, Hh, Ww = embed.shape
+        hc = C // nh
+        g32 = guide.contiguous().float()                 # [B, N, nh, hc]
+        N = g32.shape[1]
+        b32 = bias.contiguous().float()
+        aw = torch.empty(B, nh, Hh, Ww, dtype=torch.float32, device=embed.device)
+        amax = torch.empty(B, nh, Hh, Ww, dtype=torch.uint8, device=embed.device)
+        with _with_device(embed):
+            rc = _lib.lib().tamtr_max_sigmoid_forward(embed.data_ptr(), g32.data_ptr(), b32.data_ptr(), aw.data_ptr(),
+                                                      amax.data_ptr(), _lib.dtype_code(embed), B, nh, hc, Hh * Ww, N,
+                                                      _lib.stream_ptr(embed.device))
+        _lib.check(rc, "max_sigmoid_forward")
+        ctx.save_for_backward(embed, g32, aw, amax)
+        ctx.meta = (B, nh, hc, Hh * Ww, N, guide.dtype, bias.dtype)
+        return aw
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_aw):
+        embed, g32, aw, amax = ctx.saved_tensors
+        B, nh, hc, HW, N, gdt, bdt = ctx.meta
+        grad_aw = grad_aw.contiguous().float()
+        grad_embed = torch.empty_like(embed)
+        grad_guide = torch.empty_like(g32)
+        grad_bias = torch.empty(nh, dtype=torch.float32, device=embed.device)
+        with _with_device(embed):
+            rc = _lib.lib().tamtr_max_sigmoid_backward(grad_aw.data_ptr(), aw.data_ptr(), amax.data_ptr(),
+                                                       embed.data_ptr(), g32.data_ptr(), grad_embed.data_ptr(),
+                                                       grad_guide.data_ptr(), grad_bias.data_ptr(),
+                                                       _lib.dtype_code(embed), B, nh, hc, HW, N,
+                                                       _lib.stream_ptr(embed.device))
+        _lib.check(rc, "max_sigmoid_backward")
+        return grad_embed, grad_guide.to(gdt), grad_bias.to(bdt), None
+
+
+def max_sigmoid_gate(embed, guide, bias, nh):
+    """extra_modules/block.py:216-220: embed [B,nh*hc,H,W], guide [B,N,nh,hc], bias [nh] -> aw [B,nh,H,W] fp32."""
+    _lib.require_cuda(embed, guide, bias)
+    return _MaxSigmoidFn.apply(embed, guide, bias, nh)

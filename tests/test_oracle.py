@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from oracle import msda
+from helpers import check_full_or_subset
 
 
 def rel_l2(x, y):
@@ -31,16 +32,9 @@ def test_c_oracle_matches_reference_golden(core, name):
     value, loc, attn, grad_out = msda.make_inputs(c["seed"], c["B"], c["Lq"], c["H"], c["Dh"], c["shapes"],
                                                   oob_frac=c["oob_frac"])
     out = msda.forward_c(value, c["shapes"], loc, attn)
-    assert rel_l2(out, c["out"]) < 2e-6                      # fp32 tolerance of the north star is 1e-4
     gv, gl, ga = msda.backward_c(grad_out, value, c["shapes"], loc, attn)
-    assert rel_l2(gl, c["grad_loc"]) < 2e-6
-    assert rel_l2(ga, c["grad_attn"]) < 2e-6
-    if "grad_value" in c:
-        assert rel_l2(gv, c["grad_value"]) < 2e-6
-    else:
-        idx, vals = c["grad_value_subset"]
-        assert rel_l2(gv.reshape(-1)[idx], vals) < 2e-6
-        assert abs(gv.double().norm().item() - c["grad_value_norm"]) < 1e-5 * c["grad_value_norm"]
+    for t, key in ((out, "out"), (gv, "grad_value"), (gl, "grad_loc"), (ga, "grad_attn")):
+        check_full_or_subset(t, c, key, 5e-6)                # fp32 tolerance of the north star is 1e-4
 
 
 @pytest.mark.parametrize("name", ["tiny_nonsquare", "small_dh16_L4"])

@@ -1,0 +1,165 @@
+"""CPU tests: pin the functional module restatement (oracle/head_ref.py) against goldens the reference produced."""
+import pytest
+import torch
+
+from helpers import check_full_or_subset, load_golden, probe_loss, rel_l2, subset_err
+from oracle import head_ref, msda, seeding
+from oracle.make_goldens import MAXSIG_CASES, _msda_inputs, _synthetic_targets
+
+TOL = 2e-5
+
+
+def _sd_from_manifest(manifest, seed, special_init=None):
+    """Build a state_dict with the reference's keys/shapes and the deterministic fill (no module needed)."""
+    class Bag(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self._sd = {k: (special_init[k].clone() if special_init and k in special_init else torch.zeros(v))
+                        for k, v in manifest.items()}
+
+        def state_dict(self):
+            return self._sd
+    bag = Bag()
+    seeding.seeded_fill(bag, seed)
+    return bag._sd
+
+
+def _ring_bias(H, L, P):
+    import math
+    th = torch.arange(H, dtype=torch.float32) * (2.0 * math.pi / H)
+    g = torch.stack([th.cos(), th.sin()], -1)
+    g = (g / g.abs().max(-1, keepdim=True)[0]).view(H, 1, 1, 2).repeat(1, L, P, 1)
+    for i in range(P):
+        g[:, :, i, :] *= i + 1
+    return g.reshape(-1)
+
+
+def _special(manifest, H=8, L=3, P=4):
+    out = {}
+    for k in manifest:
+        if k.endswith("sampling_offsets.bias"):
+            out[k] = _ring_bias(H, L, P)
+        if k.endswith("logit_scale"):
+            out[k] = torch.ones([]) * torch.tensor(1 / 0.07).log()
+        if "score_head" in k and k.endswith(".bias") and manifest[k] == (1,):
+            out[k] = torch.tensor([-10.0])
+    return out
+
+
+@pytest.mark.parametrize("name", ["seeded", "seeded_ref2", "seeded_d512"])
+def test_msdeform_attn(name):
+    c = load_golden("modules_msdeform")["cases"][name]
+    sd = _sd_from_manifest(c["manifest"], c["fill"], _special(c["manifest"]))
+    sd = {"m." + k: v.requires_grad_() for k, v in sd.items()}
+    query, ref, value = _msda_inputs(30, 2, 50, c["d"], c["shapes"], c["ref_dim"])
+    query.requires_grad_(), value.requires_grad_()
+    for core in (msda.msda_gridsample_torch, msda.msda_explicit_torch):
+        query.grad = value.grad = None
+        out = head_ref.msdeform_attn(sd, "m", query, ref, value, c["shapes"], c["H"], core=core)
+        probe_loss(out, 31, "probe").backward()
+        assert rel_l2(out, c["out"]) < TOL
+        assert rel_l2(query.grad, c["grad_query"]) < TOL
+        check_full_or_subset(value.grad, c, "grad_value", TOL)
+
+
+def test_decoder_layer():
+    c = load_golden("modules_layer")
+    sd = _sd_from_manifest(c["manifest"], 41, _special(c["manifest"]))
+    sd = {"l." + k: v for k, v in sd.items()}
+    B, Lq, d = c["B"], c["Lq"], c["d"]
+    Lv = sum(h * w for h, w in c["shapes"])
+    embed = seeding.seeded_tensor(42, "embed", (B, Lq, d)).requires_grad_()
+    feats = seeding.seeded_tensor(42, "feats", (B, Lv, d)).requires_grad_()
+    pos = seeding.seeded_tensor(42, "pos", (B, Lq, d))
+    ref = torch.cat([seeding.seeded_uniform(42, "xy", (B, Lq, 2)), seeding.seeded_uniform(42, "wh", (B, Lq, 2), 0.01, 0.3)], -1)
+    mask = torch.zeros(Lq, Lq, dtype=torch.bool)
+    mask[16:, :16] = True
+    mask[:8, 8:16] = True
+    mask[8:16, :8] = True
+    out = head_ref.decoder_layer(sd, "l", embed, ref, feats, c["shapes"], mask, pos, c["H"])
+    probe_loss(out, 43, "probe").backward()
+    assert rel_l2(out, c["out"]) < TOL and rel_l2(embed.grad, c["grad_embed"]) < TOL
+    assert rel_l2(feats.grad, c["grad_feats"]) < TOL
+
+
+@pytest.mark.parametrize("K", [10, 80])
+def test_contrastive_head(K):
+    c = load_golden("modules_contrastive")["cases"][K]
+    sd = {"h.logit_scale": (torch.ones([]) * torch.tensor(1 / 0.07).log()).requires_grad_(),
+          "h.bias": torch.tensor([-10.0]).requires_grad_()}
+    x = seeding.seeded_tensor(50 + K, "x", (2, 300, 512)).requires_grad_()
+    w = seeding.seeded_tensor(50 + K, "w", (2, K, 512)).requires_grad_()
+    out = head_ref.contrastive_head(sd, "h", x, w)
+    probe_loss(out, 51, "probe").backward()
+    assert rel_l2(out, c["out"]) < TOL and rel_l2(w.grad, c["grad_w"]) < TOL
+    check_full_or_subset(x.grad, c, "grad_x", TOL)
+    assert rel_l2(sd["h.logit_scale"].grad, c["grad_logit_scale"]) < TOL
+
+
+@pytest.mark.parametrize("name", list(MAXSIG_CASES))
+def test_max_sigmoid_attn(name):
+    c = load_golden("modules_maxsigmoid")["cases"][name]
+    C, nh, Hh, Ww, N, B = MAXSIG_CASES[name]
+    sd = _sd_from_manifest(c["manifest"], 61)
+    sd = {"a." + k: v for k, v in sd.items()}
+    x0 = seeding.seeded_tensor(62, "x", (B, C, Hh, Ww))
+    guide = seeding.seeded_tensor(62, "guide", (B, N, 512))
+    for mode in ("eval", "train"):
+        x = x0.clone().requires_grad_()
+        g = guide.clone().requires_grad_()
+        out = head_ref.max_sigmoid_attn(sd, "a", x, g, nh, training=(mode == "train"))
+        probe_loss(out, 63, "probe").backward()
+        gold = c[mode]
+        assert subset_err(out, gold["out_subset"]) < TOL
+        assert subset_err(x.grad, gold["grad_x_subset"]) < 5e-5
+        assert rel_l2(g.grad, gold["grad_guide"]) < 5e-5
+
+
+def head_tol(ref32_err, floor=1e-4):
+    """Multi-layer heads amplify fp32 rounding; the golden target is the reference's fp64 output and `ref32_err` is
+    how far the reference's own fp32 run is from it.  Allowed: the north-star 1e-4, or 3x the reference's own error."""
+    return max(floor, 3.0 * ref32_err)
+
+
+def test_rtdetr_head_eval_sbase():
+    c = load_golden("modules_heads")["cases"]["rtdetr_eval_sbase"]
+    sd = _sd_from_manifest(c["manifest"], 71, _special(c["manifest"]))
+    xs = [seeding.seeded_tensor(72, f"x{i}", (2, 256, s, s)) for i, s in enumerate((80, 40, 20))]
+    with torch.no_grad():
+        db, ds, eb, es = head_ref.head(sd, "", xs, 300, 6, 8, training=False)
+    e = c["ref32_err"]
+    assert rel_l2(db, c["dec_bboxes"]) < head_tol(e["dec_bboxes"]) and rel_l2(ds, c["dec_scores"]) < head_tol(e["dec_scores"])
+    assert rel_l2(eb, c["enc_bboxes"]) < TOL and rel_l2(es, c["enc_scores"]) < TOL
+
+
+def test_meh_head_train_small():
+    c = load_golden("modules_heads")["cases"]["meh_syaml_small"]
+    manifest = {k: v for k, v in c["manifest"].items() if not k.startswith("VSSBlocks.")}
+    sd = _sd_from_manifest(manifest, 73, _special(manifest))
+    sd = {k: (v.requires_grad_() if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    B, sizes = c["B"], c["sizes"]
+    xs = [seeding.seeded_tensor(74, f"x{i}", (B, ch, s, s)).requires_grad_() for i, (ch, s) in enumerate(zip((128, 256, 512), sizes))]
+    text = torch.nn.functional.normalize(seeding.seeded_tensor(74, "text", (B, 10, 512)), dim=-1)
+    batch = _synthetic_targets(75, B, 5, 20)
+    assert batch["gt_groups"] == c["batch"]["gt_groups"]
+    # the denoising group is host glue shared with the product (tamtr_b200.head.get_cdn_group); it must reproduce the
+    # reference's queries bit-for-bit under the same seed
+    from tamtr_b200.head import get_cdn_group
+    torch.manual_seed(1234)
+    dn_embed, dn_bbox, attn_mask, meta = get_cdn_group(batch, 10, 100, sd["denoising_class_embed.weight"], 100, 0.5, 1.0, True)
+    assert torch.equal(attn_mask, c["cdn"]["attn_mask"]) and torch.equal(dn_bbox, c["cdn"]["dn_bbox"])
+    assert meta["dn_num_split"] == c["cdn"]["dn_meta"]["dn_num_split"]
+    assert all(torch.equal(a, b) for a, b in zip(meta["dn_pos_idx"], c["cdn"]["dn_meta"]["dn_pos_idx"]))
+    db, ds, eb, es = head_ref.head(sd, "", xs, 100, 3, 8, training=True, text=text, cdn=(dn_embed, dn_bbox, attn_mask))
+    g, e = c["train"], c["train"]["ref32_err"]
+    assert rel_l2(db, g["dec_bboxes"]) < head_tol(e["dec_bboxes"]) and rel_l2(ds, g["dec_scores"]) < head_tol(e["dec_scores"])
+    assert rel_l2(eb, g["enc_bboxes"]) < TOL and rel_l2(es, g["enc_scores"]) < TOL
+    loss = head_ref.surrogate_loss(db, ds, eb, es)
+    assert abs(loss.item() - g["loss"]) < 1e-5 * abs(g["loss"])
+    loss.backward()
+    for x, n in zip(xs, g["grad_x_norms"]):
+        assert abs(x.grad.double().norm().item() - n) < head_tol(e["grad_x2"]) * n
+    assert subset_err(xs[2].grad, g["grad_x2_subset"]) < head_tol(e["grad_x2"])
+    for k, n in g["grad_param_norms"].items():
+        if n > 0:
+            assert abs(sd[k].grad.double().norm().item() - n) < head_tol(e["grad_params"]) * n, k
