@@ -1,0 +1,345 @@
+"""Headline benchmark: TAM-TR detection-head (MEH) forward + backward, images/s, on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): the head TAMTR.yaml:67 builds -- ManbaWorldDecoder(nc=10, ch=[128,256,512],
+hd=512, nq=100, ndp=4, nh=8, ndl=3) = 3 deformable decoder layers over a 160^2/80^2/40^2 pyramid (33 600 tokens,
+d=512, 8 heads x 64) + the text-guided contrastive classification branch on 10 synthetic 512-d text embeddings --
+train mode with a contrastive-denoising group (20..100 synthetic VisDrone-like boxes per image), bf16 autocast,
+batch 16 per GPU, forward + backward (+ one NCCL all-reduce of the flat gradient buffer when N > 1).  VSSBlocks are
+identity (their CUDA extension is not part of the reference tree).  Weights random-init, data
+synthetic.
+
+One JSON line on stdout (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` is the same step
+through the public module API with the step's inputs coming from pinned HOST memory (copy stream, double-buffered)
+and the loss read back to the host every step.  `roofline` is for the dominant hand-written kernel (the sampler's
+backward); per-kernel device times come from CUDA events the C library records on the launching stream around its
+own launches during an instrumented pass over the same K steps.  `cpu_baseline` / `--impl reference`: the CPU
+restatement of the reference's own PyTorch path (oracle/head_ref.py, fp32, all host threads) -- /root/reference is
+pure Python and does not exist on the GPU box, so the "port" stands in for it (kind = "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NC, CH, HD, NQ, NDP, NH, NDL = 10, (128, 256, 512), 512, 100, 4, 8, 3
+SIZES = (160, 80, 40)
+BATCH_PER_GPU = 16
+METRIC = "head fwd+bwd images/sec @640^2"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def synthetic_targets(seed, B, lo=20, hi=100):
+    """VisDrone-shaped ground truth: n ~ U{20..100} small boxes per image, 10 classes."""
+    g = torch.Generator().manual_seed(seed)
+    groups = [int(torch.randint(lo, hi + 1, (1,), generator=g)) for _ in range(B)]
+    groups[0] = hi                    # pin the largest group so every rank/step has the same query count
+    n = sum(groups)
+    boxes = torch.cat([torch.rand(n, 2, generator=g), 0.01 + 0.29 * torch.rand(n, 2, generator=g)], -1)
+    cls = torch.randint(0, NC, (n,), generator=g)
+    idx = torch.cat([torch.full((k,), i, dtype=torch.long) for i, k in enumerate(groups)])
+    return {"cls": cls, "bboxes": boxes, "batch_idx": idx, "gt_groups": groups}
+
+
+def synthetic_inputs(seed, B, dtype):
+    g = torch.Generator().manual_seed(seed)
+    xs = [torch.randn(B, c, s, s, generator=g).to(dtype) for c, s in zip(CH, SIZES)]
+    text = torch.nn.functional.normalize(torch.randn(B, NC, 512, generator=g), dim=-1)
+    return xs, text
+
+
+def loss_fn(out):
+    """Surrogate scalar every head output feeds (same one the parity tests use); the Hungarian-matched detection
+    loss is a 'next' row of SURVEY.md section 8(f)."""
+    db, ds, eb, es = out[:4]
+    return (db.float().square().mean() + 0.1 * ds.float().sigmoid().mean()
+            + eb.float().square().mean() + 0.1 * es.float().sigmoid().mean())
+
+
+# ----------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------- bytes
+def sampler_bytes(B, Lq, value_bytes=2, L=3, P=4):
+    """ALGORITHMIC bytes of one sampler launch (DESIGN.md 'Roofline accounting').
+    fwd: each value byte the gather needs, once (min(dense slab, gathered)) + fp32 loc/attn + output.
+    bwd: grad_out + the same value bytes + loc/attn read + grad_loc/grad_attn write + the dense grad_value written
+         once (its zero-fill is a separate memset node and is NOT counted here, nor timed in this kernel)."""
+    Lv = sum(s * s for s in SIZES)
+    d, Dh = HD, HD // NH
+    gathered = B * Lq * NH * L * P * 4 * Dh
+    val = min(B * Lv * d, gathered) * value_bytes
+    locw = B * Lq * NH * L * P * 3 * 4
+    out = B * Lq * d * value_bytes
+    fwd = val + locw + out
+    bwd = out + val + 2 * locw + min(B * Lv * d, gathered) * value_bytes
+    return fwd, bwd
+
+
+# ----------------------------------------------------------------------------------------------------- CPU port
+def cpu_reference_step(sample_images, threads, steps, warmup, seed=1234):
+    """The reference's own PyTorch path on the host cores (oracle port): fp32, train mode, fwd + bwd."""
+    from oracle import head_ref                 # the ONLY thing on this path: no product code, no CUDA
+    torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    sd = head_ref.meh_state_dict(NC, CH, HD, NDL, NH, seed=seed)
+    sd = {k: (v.requires_grad_() if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    xs, text = synthetic_inputs(seed, sample_images, torch.float32)
+    batch = synthetic_targets(seed, sample_images)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        cdn = head_ref.cdn_group(batch, NC, NQ, sd["denoising_class_embed.weight"])
+        out = head_ref.head(sd, "", xs, NQ, NDL, NH, training=True, text=text, cdn=cdn)
+        loss = head_ref.surrogate_loss(*out)
+        for v in sd.values():
+            if v.requires_grad:
+                v.grad = None
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sample_images * len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 2
+    steps, warmup = min(args.steps, 8), min(args.warmup, 1)
+    ips, sec = cpu_reference_step(sample, cores, steps, warmup)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(),
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} images/step of the same workload (S-yaml head, train fwd+bwd, fp32), "
+                                   f"{steps} steps after {warmup} warm-up, torch CPU with {cores} threads"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def config_dict():
+    return {"workload": "TAM-TR MEH head (ManbaWorldDecoder nc=10 ch=[128,256,512] hd=512 nq=100 ndl=3, VSS=identity) "
+                        "+ text-guided cls branch, train fwd+bwd, CDN 20..100 gt/img, pyramid 160^2/80^2/40^2 @640^2",
+            "batch_per_gpu": BATCH_PER_GPU, "text_tokens": NC, "text_dim": 512,
+            "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="tamtr_b200", choices=["tamtr_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import tamtr_b200
+    from tamtr_b200 import _lib, dp
+    from tamtr_b200.head import ManbaWorldDecoder
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    ws = int(os.environ.get("WORLD_SIZE", 1))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for this path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if ws > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    B = BATCH_PER_GPU
+    torch.manual_seed(1234)                                # same initial weights on every rank (DDP broadcast equivalent)
+    model = ManbaWorldDecoder(NC, list(CH), HD, NQ, NDP, NH, NDL).to(dev).train()
+    # two synthetic batches per rank in pinned host memory (bf16 activations, as a bf16 neck would hand them over)
+    host = []
+    for j in range(2):
+        xs, text = synthetic_inputs(1234 + rank * 7 + j, B, torch.bfloat16)
+        host.append(([x.pin_memory() for x in xs], text.pin_memory()))
+    batch = synthetic_targets(1234 + rank, B)
+    plan = model.plan_cdn(batch)
+    Lq = plan.n_dn + NQ
+
+    step = dp.HeadTrainStep(model, loss_fn, (host[0][0], host[0][1], plan), autocast=torch.bfloat16,
+                            use_graph=not args.no_graph)
+    h2d = sum(x.numel() * x.element_size() for x in host[0][0]) + host[0][1].numel() * host[0][1].element_size()
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ------------------------------------------------------------------ device-resident timing ("value")
+    for _ in range(args.warmup):
+        step.run()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        step.run()
+    e1.record()
+    barrier()
+    sec = dp.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    clk = clocks.stop() if rank == 0 else None
+    launches = (step.launches_per_step * args.steps) if step.graph is not None else (_lib.launch_count() - launches0)
+    value = ws * B * args.steps / sec
+
+    # ------------------------------------------------------------------ end to end from pinned host memory ("e2e")
+    copy_stream = torch.cuda.Stream(dev)
+    staging = [([torch.empty_like(x, device=dev) for x in host[0][0]], torch.empty_like(host[0][1], device=dev))
+               for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def stage(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            for d, h in zip(staging[s][0], host[s][0]):
+                d.copy_(h, non_blocking=True)
+            staging[s][1].copy_(host[s][1], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream(dev)
+        for s in range(2):
+            consumed[s].record(cur)
+        stage(0)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                stage(i + 1)                       # next step's H2D overlaps this step's compute
+            cur.wait_event(ready[s])
+            step.load_inputs((staging[s][0], staging[s][1], None))   # device->static-buffer copy (graph inputs)
+            consumed[s].record(cur)
+            loss = step.run()
+            loss_host.copy_(loss, non_blocking=True)
+            cur.synchronize()                      # the user reads the loss every step
+            float(loss_host)
+
+    e2e_loop(args.warmup)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_loop(args.steps)
+    t1.record()
+    barrier()
+    e2e_sec = dp.max_over_ranks(t0.elapsed_time(t1) / 1e3, dev)
+    e2e_value = ws * B * args.steps / e2e_sec
+
+    # ------------------------------------------------------------------ per-kernel device times (instrumented pass)
+    kern = {}
+    if rank == 0:
+        _lib.profile_enable(True)
+        graph, step.graph = step.graph, None       # eager pass over the same buffers: the library brackets each of
+        for _ in range(args.steps):                # its launches with CUDA events on the launching stream
+            step.run(reduce=False)
+        torch.cuda.synchronize(dev)
+        step.graph = graph
+        kern = _lib.profile_read()
+        _lib.profile_enable(False)
+    barrier()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        fwd_b, bwd_b = sampler_bytes(B, Lq)
+        per_kernel = {k: {"avg_us": ms / n * 1e3, "launches_per_step": n / args.steps} for k, (ms, n) in kern.items()}
+        bwd_us = per_kernel.get("msda_bwd", {}).get("avg_us")
+        fwd_us = per_kernel.get("msda_fwd", {}).get("avg_us")
+        roof = {"bound": "hbm", "kernel": "msda_bwd_kernel<bf16,LPC=8,NS=12>", "achieved": bwd_b / (bwd_us * 1e3) if bwd_us else None,
+                "peak": peak, "unit": "GB/s", "frac": (bwd_b / (bwd_us * 1e3) / peak) if bwd_us else None,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": bwd_b, "avg_us": bwd_us,
+                "fwd": {"kernel": "msda_fwd_kernel<bf16,LPC=8,NS=12>", "achieved": fwd_b / (fwd_us * 1e3) if fwd_us else None,
+                        "frac": (fwd_b / (fwd_us * 1e3) / peak) if fwd_us else None, "algorithmic_bytes": fwd_b,
+                        "avg_us": fwd_us}}
+        ncu = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(ncu):
+            try:
+                roof["traffic"] = json.load(open(ncu)).get("msda_bwd_dram_bytes_per_launch")
+            except Exception:
+                pass
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": ws, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": dict(config_dict(), queries=Lq, cuda_graph=step.graph is not None,
+                               parallelism=f"dp{ws}" if ws > 1 else "single"),
+                "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": e2e_sec / args.steps * 1e3},
+                "gpu_launches": int(launches),
+                "roofline": roof, "kernels": per_kernel}
+        if not args.no_cpu_baseline and ws == 1:
+            cores = os.cpu_count() or 1
+            ips, s = cpu_reference_step(2, cores, 2, 1)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": "2 images/step of the same workload (fp32 train fwd+bwd), 2 timed steps "
+                                              f"after 1 warm-up, torch CPU {cores} threads, {s:.1f} s/step"}
+        print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

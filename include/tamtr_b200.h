@@ -37,6 +37,18 @@ const char *tamtr_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 unsigned long long tamtr_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled, every kernel launch of this library is bracketed by
+ * CUDA events on its launching stream (skipped while that stream is being captured into a CUDA graph).
+ * tamtr_profile_enable(on) also clears what was recorded; tamtr_profile_read synchronises and sums. */
+enum tamtr_kernel {
+    TAMTR_K_MSDA_FWD = 0, TAMTR_K_MSDA_BWD, TAMTR_K_LOCW_FWD, TAMTR_K_LOCW_BWD, TAMTR_K_CONTRASTIVE_FWD,
+    TAMTR_K_CONTRASTIVE_BWD, TAMTR_K_MAX_SIGMOID_FWD, TAMTR_K_MAX_SIGMOID_BWD, TAMTR_K_MAX_SIGMOID_TC_FWD,
+    TAMTR_K_COUNT
+};
+int tamtr_profile_enable(int on);
+int tamtr_profile_read(int kernel_id, double *total_ms, unsigned long long *launches);
+const char *tamtr_kernel_name(int kernel_id);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Multi-scale deformable attention core op.
  * Replaces ultralytics/nn/modules/utils.py:42-89 multi_scale_deformable_attn_pytorch (3x F.grid_sample +

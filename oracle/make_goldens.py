@@ -269,7 +269,9 @@ def gen_heads(ns):
         return (None if e is None else e.to(class_embed.dtype)), (None if b is None else b.to(class_embed.dtype)), mask, meta
     ns.ops.get_cdn_group = cdn_any_dtype
     try:
-        for name, sizes, B in (("meh_syaml_small", (40, 20, 10), 2), ("meh_syaml_full", (160, 80, 40), 1)):
+        # batch >= 2 on purpose: torch's CPU BatchNorm backward is wrong at batch 1 for this op sequence
+        # (oracle/head_ref.py::_ContiguousGrad), so a batch-1 golden of the reference's CPU path would pin a bug.
+        for name, sizes, B in (("meh_syaml_small", (40, 20, 10), 2), ("meh_syaml_full", (160, 80, 40), 2)):
             torch.manual_seed(0)
             m = ns.ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3)
             manifest = seeding.seeded_fill(m, 73)

@@ -24,6 +24,10 @@ _SIGNATURES = {
     "tamtr_abi_version": (ctypes.c_int, []),
     "tamtr_last_error": (ctypes.c_char_p, []),
     "tamtr_launch_count": (ctypes.c_ulonglong, []),
+    "tamtr_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "tamtr_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                          ctypes.POINTER(ctypes.c_ulonglong)]),
+    "tamtr_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),
     "tamtr_msda_forward": (ctypes.c_int, [_vp, _fp, _fp, _vp, _i] + [_i] * 7 + [_vp, _vp]),
     "tamtr_msda_backward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _i] + [_i] * 7 + [_vp, _vp]),
     "tamtr_msda_corners": (ctypes.c_int, [_fp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp]),
@@ -69,6 +73,25 @@ def lib():
 
 def launch_count():
     return int(lib().tamtr_launch_count())
+
+
+def profile_enable(on=True):
+    """Bracket every kernel launch of the library with CUDA events on its stream (clears previous records)."""
+    lib().tamtr_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """-> {kernel_name: (total_ms, launches)} for kernels launched since profile_enable(True)."""
+    out = {}
+    for kid in range(64):
+        name = lib().tamtr_kernel_name(kid).decode()
+        if not name:
+            break
+        ms, n = ctypes.c_double(0), ctypes.c_ulonglong(0)
+        lib().tamtr_profile_read(kid, ctypes.byref(ms), ctypes.byref(n))
+        if n.value:
+            out[name] = (ms.value, int(n.value))
+    return out
 
 
 def check(rc, what):

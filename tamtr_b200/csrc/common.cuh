@@ -12,6 +12,19 @@ namespace tamtr {
 void set_error(const char *fmt, ...);
 void count_launch(unsigned n = 1);
 
+enum KernelId { K_MSDA_FWD = 0, K_MSDA_BWD, K_LOCW_FWD, K_LOCW_BWD, K_CTR_FWD, K_CTR_BWD, K_GATE_FWD, K_GATE_BWD,
+                K_GATE_TC_FWD, K_COUNT };
+
+// RAII pair of CUDA events around one kernel launch (no-op unless tamtr_profile_enable(1)).
+struct KernelTimer {
+    KernelTimer(int id, cudaStream_t st);
+    ~KernelTimer();
+    int id_;
+    cudaStream_t st_;
+    bool live_;
+    cudaEvent_t a_, b_;
+};
+
 #define TAMTR_CHECK_ARG(cond, code, ...)           \
     do {                                            \
         if (!(cond)) {                              \

@@ -192,6 +192,7 @@ extern "C" int tamtr_contrastive_forward(const void *x, const float *w, const fl
     if (rc) return rc;
     const dim3 grid((Lq + kCtrWarps - 1) / kCtrWarps, B);
     cudaStream_t st = (cudaStream_t)stream;
+    KernelTimer timer(K_CTR_FWD, st);
     if (dtype == TAMTR_F32)
         contrastive_fwd_kernel<float><<<grid, kCtrWarps * 32, 0, st>>>((const float *)x, w, logit_scale, bias, out, Lq,
                                                                         K, C);
@@ -213,6 +214,7 @@ extern "C" int tamtr_contrastive_backward(const float *grad_out, const void *x, 
     const dim3 grid((Lq + kCtrWarps - 1) / kCtrWarps, B);
     cudaStream_t st = (cudaStream_t)stream;
     TAMTR_CUDA_OK(cudaMemsetAsync(grad_scalars, 0, 2 * sizeof(float), st));
+    KernelTimer timer(K_CTR_BWD, st);
     if (dtype == TAMTR_F32)
         contrastive_bwd_kernel<float><<<grid, kCtrWarps * 32, 0, st>>>(grad_out, (const float *)x, w, logit_scale,
                                                                         (float *)grad_x, grad_scalars, Lq, K, C);

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -19,8 +21,61 @@ void set_error(const char *fmt, ...) {
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- per-kernel CUDA-event timing (bench.py's roofline numbers): events are recorded on the launching stream,
+// immediately around the kernel launch; disabled by default and skipped while the stream is being captured.
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+struct EventPair { cudaEvent_t a, b; };
+static std::vector<EventPair> g_prof[K_COUNT];
+static const char *g_names[K_COUNT] = {"msda_fwd", "msda_bwd", "locw_fwd", "locw_bwd", "contrastive_fwd",
+                                       "contrastive_bwd", "max_sigmoid_fwd", "max_sigmoid_bwd", "max_sigmoid_tc_fwd"};
+
+KernelTimer::KernelTimer(int id, cudaStream_t st) : id_(id), st_(st), live_(false) {
+    if (!g_prof_on) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    if (cudaEventCreate(&a_) != cudaSuccess || cudaEventCreate(&b_) != cudaSuccess) return;
+    cudaEventRecord(a_, st);
+    live_ = true;
+}
+
+KernelTimer::~KernelTimer() {
+    if (!live_) return;
+    cudaEventRecord(b_, st_);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof[id_].push_back({a_, b_});
+}
+
 }  // namespace tamtr
 
 extern "C" int tamtr_abi_version(void) { return TAMTR_B200_ABI_VERSION; }
 extern "C" const char *tamtr_last_error(void) { return tamtr::g_err; }
 extern "C" unsigned long long tamtr_launch_count(void) { return tamtr::g_launches.load(); }
+
+extern "C" int tamtr_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(tamtr::g_prof_mu);
+    for (auto &v : tamtr::g_prof) {
+        for (auto &e : v) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        v.clear();
+    }
+    tamtr::g_prof_on = on != 0;
+    return 0;
+}
+
+extern "C" int tamtr_profile_read(int kernel_id, double *total_ms, unsigned long long *launches) {
+    if (kernel_id < 0 || kernel_id >= tamtr::K_COUNT || !total_ms || !launches) return TAMTR_E_BADARG;
+    std::lock_guard<std::mutex> lk(tamtr::g_prof_mu);
+    double sum = 0.0;
+    for (auto &e : tamtr::g_prof[kernel_id]) {
+        cudaEventSynchronize(e.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) sum += ms;
+    }
+    *total_ms = sum;
+    *launches = tamtr::g_prof[kernel_id].size();
+    return 0;
+}
+
+extern "C" const char *tamtr_kernel_name(int kernel_id) {
+    return (kernel_id >= 0 && kernel_id < tamtr::K_COUNT) ? tamtr::g_names[kernel_id] : "";
+}

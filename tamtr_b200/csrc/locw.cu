@@ -145,6 +145,7 @@ extern "C" int tamtr_locw_forward(const float *raw, const float *bias, const flo
     const int rc = check_locw(M, H, L, P, RL, RD, level_shapes_host, lv);
     if (rc) return rc;
     const int n = M * H;
+    KernelTimer timer(K_LOCW_FWD, (cudaStream_t)stream);
     locw_fwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(raw, bias, ref, loc, attn, lv, M, H, RL, RD);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
@@ -165,6 +166,7 @@ extern "C" int tamtr_locw_backward(const float *grad_loc, const float *grad_attn
         count_launch();
     }
     const int n = M * H;
+    KernelTimer timer(K_LOCW_BWD, st);
     locw_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(grad_loc, grad_attn, attn, raw, bias, ref, grad_raw, grad_ref, lv,
                                                       M, H, RL, RD);
     count_launch();

@@ -134,6 +134,7 @@ extern "C" int tamtr_max_sigmoid_forward(const void *embed, const float *guide, 
                     N * hc);
 #define ARGS_F(T) (const T *)embed, guide, bias, aw, amax, nh, HW, N
     {
+        KernelTimer timer(K_GATE_FWD, st);
         const dim3 grid((HW + kGateThreads - 1) / kGateThreads, nh, B);
         if (dtype == TAMTR_F32) {
             if (hc == 16) gate_fwd_kernel<float, 16><<<grid, kGateThreads, smem, st>>>(ARGS_F(float));
@@ -167,6 +168,7 @@ extern "C" int tamtr_max_sigmoid_backward(const float *grad_aw, const float *aw,
     TAMTR_CUDA_OK(cudaMemsetAsync(grad_bias, 0, sizeof(float) * (size_t)nh, st));
 #define ARGS_B(T) grad_aw, aw, amax, (const T *)embed, guide, (T *)grad_embed, grad_guide, grad_bias, nh, HW, N
     {
+        KernelTimer timer(K_GATE_BWD, st);
         const dim3 grid((HW + kGateThreads - 1) / kGateThreads, nh, B);
         if (dtype == TAMTR_F32) {
             if (hc == 16) gate_bwd_kernel<float, 16><<<grid, kGateThreads, smem, st>>>(ARGS_B(float));

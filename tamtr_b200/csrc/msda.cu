@@ -326,6 +326,7 @@ static int launch_fwd(const void *value, const float *loc, const float *attn, vo
                       int Lq, int H, int Lv, cudaStream_t st) {
     const long total = (long)B * Lq * H;
     const int grid = (int)((total + kWarpsPerCta - 1) / kWarpsPerCta);
+    KernelTimer timer(K_MSDA_FWD, st);
     if (lv.n * lv.P == 12)
         msda_fwd_kernel<T, LPC, 12><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)value, loc, attn, (T *)out, lv, Lq,
                                                                          H, Lv, (int)total);
@@ -345,6 +346,7 @@ static int launch_bwd(const void *grad_out, const void *value, const float *loc,
     const long total = (long)B * Lq * H;
     const int grid = (int)((total + kWarpsPerCta - 1) / kWarpsPerCta);
     TAMTR_CUDA_OK(cudaMemsetAsync(grad_value, 0, (size_t)B * Lv * H * DH * sizeof(T), st));
+    KernelTimer timer(K_MSDA_BWD, st);
     if (lv.n * lv.P == 12)
         msda_bwd_kernel<T, LPC, 12><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)grad_out, (const T *)value, loc,
                                                                          attn, (T *)grad_value, grad_loc, grad_attn,

@@ -1,0 +1,147 @@
+"""Data-parallel head training step (forward + backward + gradient all-reduce), one process per GPU.
+
+The reference trains with torch DDP: batch sharded by DistributedSampler, one bucketed NCCL all-reduce (mean) of all
+gradients per backward (ultralytics/engine/trainer.py:241, 252; data/build.py:104).  The path shards by image with
+no data-path collective; the only exchange step is that gradient all-reduce.  B200-first restatement:
+
+* every parameter's .grad is a view into ONE flat fp32 buffer -> the exchange is a single NCCL all-reduce over
+  NVLink/NVSwitch (no bucket copies), issued right after the backward;
+* forward + backward of the step are captured ONCE into a CUDA graph (static input buffers, the denoising group is
+  planned on the host per batch exactly as the reference does and only its embedding gather is in the graph), so the
+  ~1.5k small launches of the step cost one graph launch instead of Python/launch latency;
+* host inputs arrive through pinned staging buffers on a copy stream (double-buffered), overlapping the previous
+  step's compute.
+
+`HeadTrainStep` is device-agnostic where it can be: with `use_graph=False` and a CPU module it runs the same
+flat-gradient / all-reduce logic under the gloo backend, which is how tests/test_dp_cpu.py covers the N>1 path.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_indices(n_items, rank, world_size):
+    """Contiguous, balanced shard of `n_items` independent units (images) for `rank` -- no collective involved."""
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+class FlatGrads:
+    """All parameter gradients as views of one flat buffer (DDP's gradient_as_bucket_view, single bucket)."""
+
+    def __init__(self, params, dtype=torch.float32):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=dtype, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self):
+        """One all-reduce (sum) + scale: the DDP semantics of trainer.py:241 (mean over ranks)."""
+        rank, ws = world()
+        if ws > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(ws)
+        return self.flat
+
+
+class HeadTrainStep:
+    """forward + backward (+ all-reduce) of a detection head on static buffers.
+
+    module     : tamtr_b200.head.ManbaWorldDecoder / RTDETRDecoder (train mode), or any module for the CPU tests
+    loss_fn    : maps the module's outputs to a scalar
+    example    : tuple of example inputs (tensors / CdnPlan / None) fixing every shape
+    autocast   : torch dtype or None
+    use_graph  : capture forward+backward into a CUDA graph (CUDA only)
+    """
+
+    def __init__(self, module, loss_fn, example, autocast=None, use_graph=True, warmup=3):
+        self.module, self.loss_fn, self.autocast = module, loss_fn, autocast
+        self.flat = FlatGrads(module.parameters())
+        self.device = self.flat.flat.device
+        self.cuda = self.device.type == "cuda"
+        self.use_graph = use_graph and self.cuda
+        self.static = [self._to_static(a) for a in example]
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.graph = None
+        self.launches_per_step = None
+        if self.use_graph:
+            self._capture(warmup)
+
+    def _to_static(self, a):
+        if isinstance(a, torch.Tensor):
+            return a.detach().to(self.device).clone()
+        if isinstance(a, (list, tuple)):
+            return type(a)(self._to_static(x) for x in a)
+        if hasattr(a, "to") and hasattr(a, "materialize"):      # CdnPlan
+            return a.to(self.device)
+        return a
+
+    def _fwd_bwd(self):
+        self.flat.zero_()
+        if self.autocast is not None:
+            with torch.autocast(self.device.type, dtype=self.autocast):
+                out = self.module(*self.static)
+        else:
+            out = self.module(*self.static)
+        loss = self.loss_fn(out)
+        loss.backward()
+        self.loss.copy_(loss.detach())
+
+    def _capture(self, warmup):
+        from . import _lib
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._fwd_bwd()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self._fwd_bwd()
+        self.launches_per_step = _lib.launch_count() - before
+        torch.cuda.synchronize(self.device)
+
+    def load_inputs(self, inputs, non_blocking=True):
+        """Copy a new batch (same shapes) into the static buffers."""
+        def cp(dst, src):
+            if isinstance(dst, torch.Tensor):
+                dst.copy_(src, non_blocking=non_blocking)
+            elif isinstance(dst, (list, tuple)):
+                for d, s in zip(dst, src):
+                    cp(d, s)
+        for d, s in zip(self.static, inputs):
+            cp(d, s)
+
+    def run(self, reduce=True):
+        """One step on whatever is in the static buffers; returns the (device) loss tensor."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._fwd_bwd()
+        if reduce:
+            self.flat.all_reduce_mean()
+        return self.loss
+
+
+def max_over_ranks(seconds, device):
+    """Multi-GPU timings are the max over ranks (never a wall clock of rank 0 alone)."""
+    rank, ws = world()
+    t = torch.tensor([seconds], dtype=torch.float64, device=device)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -19,7 +19,7 @@ import torch.nn as nn
 from .modules import (MLP, ContrastiveHeadMLP, DeformableTransformerDecoder, DeformableTransformerDecoderLayer,
                       TextDeformableTransformerDecoder)
 
-__all__ = ("RTDETRDecoder", "ManbaWorldDecoder", "get_cdn_group")
+__all__ = ("RTDETRDecoder", "ManbaWorldDecoder", "get_cdn_group", "plan_cdn_group", "CdnPlan")
 
 
 def _xywh_to_xyxy(b):
@@ -31,19 +31,43 @@ def _xyxy_to_xywh(b):
     return torch.cat([(b[..., :2] + b[..., 2:]) / 2, b[..., 2:] - b[..., :2]], -1)
 
 
-def get_cdn_group(batch, num_classes, num_queries, class_embed, num_dn=100, cls_noise_ratio=0.5,
-                  box_noise_scale=1.0, training=False):
-    """Contrastive denoising group (ops.py:152-291).  Consumes the global RNG in the same order as the reference
-    (label mask, replacement labels, box-noise sign, box-noise magnitude), so seeded runs produce the same queries.
+class CdnPlan:
+    """Host-side result of the denoising-group construction: everything except the (learnable) class-embedding
+    lookup.  Splitting it off lets a training step be captured in a CUDA graph: the plan is built per batch on the
+    host exactly as the reference does, the graph only contains the embedding gather."""
 
-    batch: {'cls' [n], 'bboxes' [n,4] (cx,cy,w,h), 'batch_idx' [n], 'gt_groups' [B ints]}.
-    Returns (dn_embed [B,num_dn,hd], dn_bbox [B,num_dn,4] (logit space), attn_mask [Lq,Lq] bool, dn_meta)."""
+    def __init__(self, dn_cls, dn_box, dn_img, slot, mask, meta, bs, n_dn):
+        self.dn_cls, self.dn_box, self.dn_img, self.slot = dn_cls, dn_box, dn_img, slot
+        self.mask, self.meta, self.bs, self.n_dn = mask, meta, bs, n_dn
+
+    def to(self, device):
+        return CdnPlan(self.dn_cls.to(device), self.dn_box.to(device), self.dn_img.to(device).long(),
+                       self.slot.to(device), self.mask.to(device), self.meta, self.bs, self.n_dn)
+
+    def materialize(self, class_embed):
+        dev = class_embed.device
+        embed = class_embed[self.dn_cls.to(dev)]
+        # (the reference fills fp32 buffers on the targets' device and moves them afterwards, ops.py:243-262; filling
+        #  them on the embedding's device is the same result without a host round trip)
+        pad_embed = torch.zeros(self.bs, self.n_dn, embed.shape[-1], device=dev, dtype=embed.dtype)
+        pad_box = torch.zeros(self.bs, self.n_dn, 4, device=dev, dtype=self.dn_box.dtype)
+        where = (self.dn_img.to(dev).long(), self.slot.to(dev))
+        pad_embed[where] = embed
+        pad_box[where] = self.dn_box.to(dev)
+        return pad_embed, pad_box, self.mask.to(dev), self.meta
+
+
+def plan_cdn_group(batch, num_classes, num_queries, num_dn=100, cls_noise_ratio=0.5, box_noise_scale=1.0,
+                   training=False):
+    """Host part of get_cdn_group (ops.py:152-291).  Consumes the global RNG in the same order as the reference
+    (label mask, replacement labels, box-noise sign, box-noise magnitude), so seeded runs produce the same queries.
+    Returns a CdnPlan or None."""
     if (not training) or num_dn <= 0:
-        return None, None, None, None
+        return None
     groups = batch["gt_groups"]
     total, biggest = sum(groups), max(groups)
     if biggest == 0:
-        return None, None, None, None
+        return None
     n_group = max(1, num_dn // biggest)
     bs = len(groups)
     gt_cls, gt_box, gt_img = batch["cls"], batch["bboxes"], batch["batch_idx"]
@@ -71,18 +95,9 @@ def get_cdn_group(batch, num_classes, num_queries, class_embed, num_dn=100, cls_
         dn_box = torch.logit(_xyxy_to_xywh(corners), eps=1e-6)
 
     n_dn = int(biggest * 2 * n_group)
-    dev = class_embed.device
-    embed = class_embed[dn_cls.to(dev)]
-    # (the reference fills fp32 buffers on the targets' device and moves them afterwards, ops.py:243-262; filling
-    #  them on the embedding's device is the same result without a host round trip)
-    pad_embed = torch.zeros(bs, n_dn, embed.shape[-1], device=dev, dtype=embed.dtype)
-    pad_box = torch.zeros(bs, n_dn, 4, device=dev, dtype=dn_box.dtype)
     slot = torch.cat([torch.arange(n, dtype=torch.long) for n in groups])
     pos_idx = torch.stack([slot + biggest * i for i in range(n_group)], dim=0)
     slot = torch.cat([slot + biggest * i for i in range(2 * n_group)])
-    where = (dn_img.to(dev).long(), slot.to(dev))
-    pad_embed[where] = embed
-    pad_box[where] = dn_box.to(dev)
 
     size = n_dn + num_queries
     mask = torch.zeros([size, size], dtype=torch.bool)
@@ -93,7 +108,19 @@ def get_cdn_group(batch, num_classes, num_queries, class_embed, num_dn=100, cls_
         mask[lo:hi, :lo] = True
     meta = {"dn_pos_idx": [p.reshape(-1) for p in pos_idx.cpu().split(list(groups), dim=1)],
             "dn_num_group": n_group, "dn_num_split": [n_dn, num_queries]}
-    return pad_embed, pad_box, mask.to(dev), meta
+    return CdnPlan(dn_cls.long(), dn_box, dn_img, slot, mask, meta, bs, n_dn)
+
+
+def get_cdn_group(batch, num_classes, num_queries, class_embed, num_dn=100, cls_noise_ratio=0.5,
+                  box_noise_scale=1.0, training=False):
+    """Contrastive denoising group, same signature and results as the reference (ops.py:152-291).
+
+    batch: {'cls' [n], 'bboxes' [n,4] (cx,cy,w,h), 'batch_idx' [n], 'gt_groups' [B ints]}.
+    Returns (dn_embed [B,num_dn,hd], dn_bbox [B,num_dn,4] (logit space), attn_mask [Lq,Lq] bool, dn_meta)."""
+    plan = plan_cdn_group(batch, num_classes, num_queries, num_dn, cls_noise_ratio, box_noise_scale, training)
+    if plan is None:
+        return None, None, None, None
+    return plan.materialize(class_embed)
 
 
 class _HeadBase(nn.Module):
@@ -144,13 +171,24 @@ class _HeadBase(nn.Module):
             feats.append(f.flatten(2).permute(0, 2, 1))
         return torch.cat(feats, 1), shapes
 
+    def _anchors(self, shapes, dtype, device):
+        """Anchors depend only on the pyramid geometry: built once per (shapes, dtype, device) instead of on every
+        forward (the reference rebuilds them each call, head.py:1226) -- also keeps host->device copies out of
+        CUDA-graph capture."""
+        key = (tuple(map(tuple, shapes)), dtype, str(device))
+        cache = self.__dict__.setdefault("_anchor_cache", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = self._generate_anchors(shapes, dtype=dtype, device=device)
+        return cache[key]
+
     def _get_decoder_input(self, feats, shapes, dn_embed=None, dn_bbox=None):
         bs = len(feats)
-        anchors, valid = self._generate_anchors(shapes, dtype=feats.dtype, device=feats.device)
+        anchors, valid = self._anchors(shapes, feats.dtype, feats.device)
         features = self.enc_output(valid * feats)
         scores = self.enc_score_head(features)
         topk = torch.topk(scores.max(-1).values, self.num_queries, dim=1).indices.view(-1)
-        img = torch.arange(end=bs, dtype=topk.dtype).unsqueeze(-1).repeat(1, self.num_queries).view(-1)
+        img = torch.arange(end=bs, dtype=topk.dtype, device=topk.device).unsqueeze(-1).repeat(1, self.num_queries).view(-1)
         top_feats = features[img, topk].view(bs, self.num_queries, -1)
         top_anchors = anchors[:, topk].view(bs, self.num_queries, -1)
         refer_bbox = self.enc_bbox_head(top_feats) + top_anchors
@@ -168,8 +206,20 @@ class _HeadBase(nn.Module):
         return embeddings, refer_bbox, enc_bboxes, enc_scores
 
     def _cdn(self, batch):
+        if isinstance(batch, CdnPlan):      # pre-planned on the host (dp.HeadTrainStep): only the embedding gather
+            return batch.materialize(self.denoising_class_embed.weight)
         return get_cdn_group(batch, self.nc, self.num_queries, self.denoising_class_embed.weight,
                              self.num_denoising, self.label_noise_ratio, self.box_noise_scale, self.training)
+
+    def plan_cdn(self, batch):
+        """Host-side half of the denoising group for `batch`; pass the result as `batch` to forward()."""
+        return plan_cdn_group(batch, self.nc, self.num_queries, self.num_denoising, self.label_noise_ratio,
+                              self.box_noise_scale, self.training)
+
+    def __getstate__(self):     # keep the anchor cache out of pickles / deep copies (checkpoints, EMA)
+        state = dict(self.__dict__)
+        state.pop("_anchor_cache", None)
+        return state
 
     def _finish(self, dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta):
         x = dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta

@@ -108,7 +108,7 @@ class _LocWFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q2, w_cat, b_cat, ref, shapes, H, L, P):
         lp = q2.dtype if q2.dtype in (torch.bfloat16, torch.float16) else torch.float32
-        if torch.is_autocast_enabled():
+        if torch.is_autocast_enabled("cuda"):
             lp = torch.get_autocast_dtype("cuda")
         q2c = q2.contiguous().to(lp)
         w_c = w_cat.to(lp)

@@ -163,3 +163,27 @@ def test_meh_head_train_small():
     for k, n in g["grad_param_norms"].items():
         if n > 0:
             assert abs(sd[k].grad.double().norm().item() - n) < head_tol(e["grad_params"]) * n, k
+
+
+def test_torch_cpu_batchnorm_bug_at_batch_one():
+    """Documents why head goldens use batch >= 2: on CPU, BatchNorm backward with a permuted grad_output is wrong
+    at batch 1 (the bias gradient must equal the plain sum of the incoming gradient)."""
+    torch.manual_seed(0)
+    conv, bn = torch.nn.Conv2d(8, 16, 1, bias=False).double(), torch.nn.BatchNorm2d(16).double()
+    errs = {}
+    for B in (1, 2):
+        bn.zero_grad()
+        g = torch.randn(B, 36, 16).double()
+        out = bn(conv(torch.randn(B, 8, 6, 6).double())).flatten(2).permute(0, 2, 1)
+        out.backward(g)
+        truth = g.sum((0, 1))
+        errs[B] = ((bn.bias.grad - truth).norm() / truth.norm()).item()
+    assert errs[2] < 1e-12
+    if errs[1] > 1e-6:      # present in torch 2.11.0; if a later torch fixes it this test still passes
+        assert errs[1] > 0.1
+    # the oracle's identity keeps the batch-1 gradient right
+    bn.zero_grad()
+    g = torch.randn(1, 36, 16).double()
+    y = head_ref._ContiguousGrad.apply(bn(conv(torch.randn(1, 8, 6, 6).double())))
+    y.flatten(2).permute(0, 2, 1).backward(g)
+    assert ((bn.bias.grad - g.sum((0, 1))).norm() / g.sum((0, 1)).norm()).item() < 1e-12
