@@ -275,7 +275,7 @@ def gen_heads(ns):
             torch.manual_seed(0)
             m = ns.ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3)
             manifest = seeding.seeded_fill(m, 73)
-            xs = [seeding.seeded_tensor(74, f"x{i}", (B, c, s, s)) for i, (c, s) in enumerate(zip((128, 256, 512), sizes))]
+            xs = [seeding.seeded_smooth_map(74, f"x{i}", (B, c, s, s)) for i, (c, s) in enumerate(zip((128, 256, 512), sizes))]
             text = F_normalize(seeding.seeded_tensor(74, "text", (B, 10, 512)))
             batch = _synthetic_targets(75, B, 5, 20)
             case = dict(manifest=manifest, sizes=sizes, B=B, batch=batch)

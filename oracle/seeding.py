@@ -55,3 +55,13 @@ def seeded_tensor(seed, name, shape, scale=1.0):
 
 def seeded_uniform(seed, name, shape, lo=0.0, hi=1.0):
     return lo + (hi - lo) * torch.rand(tuple(shape), generator=_gen(seed, name))
+
+
+def seeded_smooth_map(seed, name, shape, factor=4):
+    """Smooth synthetic feature map [B,C,H,W]: a coarse seeded random grid upsampled bilinearly.  Real pyramid
+    features are spatially smooth; with white noise the derivative of a bilinear sample w.r.t. its location is pure
+    noise of size W * |v|, which makes every gradient that flows through the sampling offsets chaotic in fp32 (the
+    reference's own fp32 and fp64 runs then disagree at the percent level) and useless as a parity target."""
+    B, C, H, W = shape
+    coarse = torch.randn(B, C, max(2, H // factor), max(2, W // factor), generator=_gen(seed, name))
+    return torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=True).contiguous()

@@ -138,7 +138,7 @@ def test_meh_head_train_small():
     sd = _sd_from_manifest(manifest, 73, _special(manifest))
     sd = {k: (v.requires_grad_() if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
     B, sizes = c["B"], c["sizes"]
-    xs = [seeding.seeded_tensor(74, f"x{i}", (B, ch, s, s)).requires_grad_() for i, (ch, s) in enumerate(zip((128, 256, 512), sizes))]
+    xs = [seeding.seeded_smooth_map(74, f"x{i}", (B, ch, s, s)).requires_grad_() for i, (ch, s) in enumerate(zip((128, 256, 512), sizes))]
     text = torch.nn.functional.normalize(seeding.seeded_tensor(74, "text", (B, 10, 512)), dim=-1)
     batch = _synthetic_targets(75, B, 5, 20)
     assert batch["gt_groups"] == c["batch"]["gt_groups"]

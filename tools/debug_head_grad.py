@@ -14,7 +14,7 @@ for sizes, B in (((160, 80, 40), 1), ((40, 20, 10), 2), ((80, 40, 20), 1)):
     sd = {k: v.detach().clone().cpu() for k, v in m.state_dict().items()}
     sd = {k: (v.requires_grad_() if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
     m.cuda().train()
-    xs_c = [seeding.seeded_tensor(74, f"x{i}", (B, ch, s, s)).requires_grad_() for i, (ch, s) in enumerate(zip((128, 256, 512), sizes))]
+    xs_c = [seeding.seeded_smooth_map(74, f"x{i}", (B, ch, s, s)).requires_grad_() for i, (ch, s) in enumerate(zip((128, 256, 512), sizes))]
     xs = [x.detach().cuda().requires_grad_() for x in xs_c]
     text = torch.nn.functional.normalize(seeding.seeded_tensor(74, "text", (B, 10, 512)), dim=-1)
     batch = _synthetic_targets(75, B, 5, 20)
