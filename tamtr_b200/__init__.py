@@ -11,5 +11,6 @@ The product path never imports `oracle/` and has no CPU fallback.
 from . import _lib, ops  # noqa: F401
 from ._lib import build, launch_count  # noqa: F401
 from .ops import ms_deform_attn  # noqa: F401
+from .patch import disable, enable, enabled  # noqa: F401
 
 __version__ = "0.1.0"
