@@ -60,24 +60,29 @@ const char *tamtr_kernel_name(int kernel_id);
  *   attn   [B, Lq, H, L, P]    f32
  *   out    [B, Lq, H*Dh]       same dtype as value
  *   level_shapes_host [L][2] = (H_l, W_l), HOST memory, read during the call (utils.py:56 value_spatial_shapes)
+ *   value_token_stride: elements between consecutive tokens of `value` (0 = H*Dh, contiguous).  A larger stride
+ *     lets one GEMM project the values of all decoder layers at once ([B, Lv, n_layers*H*Dh]; transformer.py:273 is
+ *     called per layer on the same `feats`, transformer.py:870) and each layer sample its own column slice.
  * Supported: Dh*sizeof(elt) in {32,64,128,256} bytes, L*P <= 32, sum(H_l*W_l) == Lv.
  * Index math is bit-exact with the reference: ix = fmaf((2*loc-1)+1, W_l, -1) * 0.5, floor, 4 corners, each
  * corner contributes iff 0<=x<W_l && 0<=y<H_l.  Accumulation in fp32.
  */
 int tamtr_msda_forward(const void *value, const float *loc, const float *attn, void *out, int dtype,
                        int B, int Lv, int H, int Dh, int Lq, int L, int P,
-                       const int32_t *level_shapes_host, void *stream);
+                       const int32_t *level_shapes_host, int value_token_stride, void *stream);
 
 /* Backward of the above (what autograd derives for utils.py:42-89: grid_sampler_2d_backward + mul/sum).
  *   grad_out   [B, Lq, H*Dh]   same dtype as value
- *   grad_value [B, Lv, H, Dh]  same dtype as value; ZEROED by this call, then accumulated with vector atomics
- *                              (REDG f32x4 / bf16x8) -> run-to-run bit differences, like grid_sampler backward
+ *   grad_value [B, Lv, H, Dh]  same dtype and token stride as value; zeroed by this call when zero_grad_value != 0
+ *                              (otherwise the caller zeroed the whole strided buffer once for all layers), then
+ *                              accumulated with vector atomics (REDG f32x4 / bf16x8) -> run-to-run bit differences,
+ *                              like grid_sampler backward
  *   grad_loc   [B, Lq, H, L, P, 2] f32, grad_attn [B, Lq, H, L, P] f32 (fully overwritten)
  */
 int tamtr_msda_backward(const void *grad_out, const void *value, const float *loc, const float *attn,
                         void *grad_value, float *grad_loc, float *grad_attn, int dtype,
                         int B, int Lv, int H, int Dh, int Lq, int L, int P,
-                        const int32_t *level_shapes_host, void *stream);
+                        const int32_t *level_shapes_host, int value_token_stride, int zero_grad_value, void *stream);
 
 /* Parity export of the index math alone (the "bit-exact sampling-location indexing" object):
  *   x0, y0 [B,Lq,H,L,P] int32 = floor(ix), floor(iy);  inb [B,Lq,H,L,P,4] uint8 = in-bounds flags (nw,ne,sw,se).

@@ -111,14 +111,13 @@ constexpr int kMaxTaps = 4 * kMaxSamples;
 // offset = element offset of the corner's Dh-vector inside image b's value slab, or -1 when out of bounds.
 template <int DH>
 __device__ __forceinline__ void stage_taps(int2 *taps, const float *__restrict__ loc, const float *__restrict__ attn,
-                                           const Levels &lv, size_t qh, int S, int h, int H, int lane) {
+                                           const Levels &lv, size_t qh, int S, int h, int rowstride, int lane) {
     if (lane < S) {
         const int l = lv.level_of[lane];
         const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + qh * S + lane);
         const float a = __ldg(attn + qh * S + lane);
         const int Hl = lv.h[l], Wl = lv.w[l];
         const Tap t = make_tap(xy.x, xy.y, Hl, Wl);
-        const int rowstride = H * DH;
         const int o_nw = (lv.start[l] + t.y0 * Wl + t.x0) * rowstride + h * DH;
         const bool vx0 = (t.x0 >= 0) & (t.x0 < Wl), vx1 = (t.x0 >= -1) & (t.x0 < Wl - 1);
         const bool vy0 = (t.y0 >= 0) & (t.y0 < Hl), vy1 = (t.y0 >= -1) & (t.y0 < Hl - 1);
@@ -158,7 +157,7 @@ __device__ __forceinline__ uint4 gather16(const void *base, int off_elems, int e
 template <typename T, int LPC, int NS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 msda_fwd_kernel(const T *__restrict__ value, const float *__restrict__ loc, const float *__restrict__ attn,
-                T *__restrict__ out, const Levels lv, int Lq, int H, int Lv, int total) {
+                T *__restrict__ out, const Levels lv, int Lq, int H, int Lv, int total, int tok_stride) {
     constexpr int VEC = Vec<T>::N;
     constexpr int DH = LPC * VEC;
     constexpr int CPL = 32 / LPC;  // corners gathered per warp-wide load
@@ -171,10 +170,10 @@ msda_fwd_kernel(const T *__restrict__ value, const float *__restrict__ loc, cons
     const int h = qh % H;
     const int b = qh / (Lq * H);
     int2 *taps = s_taps[wic];
-    stage_taps<DH>(taps, loc, attn, lv, (size_t)qh, S, h, H, lane);
+    stage_taps<DH>(taps, loc, attn, lv, (size_t)qh, S, h, tok_stride, lane);
 
     const int cs = lane / LPC, cg = lane % LPC;
-    const T *vbase = value + (size_t)b * Lv * H * DH + cg * VEC;
+    const T *vbase = value + (size_t)b * Lv * tok_stride + cg * VEC;
     const int npairs = 4 * S;
     float acc[VEC];
 #pragma unroll
@@ -217,7 +216,7 @@ template <typename T, int LPC, int NS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 msda_bwd_kernel(const T *__restrict__ grad_out, const T *__restrict__ value, const float *__restrict__ loc,
                 const float *__restrict__ attn, T *__restrict__ grad_value, float *__restrict__ grad_loc,
-                float *__restrict__ grad_attn, const Levels lv, int Lq, int H, int Lv, int total) {
+                float *__restrict__ grad_attn, const Levels lv, int Lq, int H, int Lv, int total, int tok_stride) {
     constexpr int VEC = Vec<T>::N;
     constexpr int DH = LPC * VEC;
     constexpr int CPL = 32 / LPC;
@@ -232,12 +231,11 @@ msda_bwd_kernel(const T *__restrict__ grad_out, const T *__restrict__ value, con
     const int b = qh / (Lq * H);
     int2 *taps = s_taps[wic];
     float *dots = s_dots[wic];
-    stage_taps<DH>(taps, loc, attn, lv, (size_t)qh, S, h, H, lane);
+    stage_taps<DH>(taps, loc, attn, lv, (size_t)qh, S, h, tok_stride, lane);
 
     const int cs = lane / LPC, cg = lane % LPC;
-    const size_t slab = (size_t)b * Lv * H * DH + cg * VEC;
-    const T *vbase = value + slab;
-    T *gvbase = grad_value + slab;
+    const T *vbase = value + (size_t)b * Lv * tok_stride + cg * VEC;
+    T *gvbase = grad_value + (size_t)b * Lv * tok_stride + cg * VEC;   // same token stride as value
     float g[VEC];
     Vec<T>::load(grad_out + (size_t)qh * DH + cg * VEC, g);
     const int npairs = 4 * S;
@@ -323,16 +321,16 @@ __global__ void msda_corners_kernel(const float *__restrict__ loc, int32_t *__re
 // ------------------------------------------------------------------------------------------- dispatch
 template <typename T, int LPC>
 static int launch_fwd(const void *value, const float *loc, const float *attn, void *out, const Levels &lv, int B,
-                      int Lq, int H, int Lv, cudaStream_t st) {
+                      int Lq, int H, int Lv, int tok_stride, cudaStream_t st) {
     const long total = (long)B * Lq * H;
     const int grid = (int)((total + kWarpsPerCta - 1) / kWarpsPerCta);
     KernelTimer timer(K_MSDA_FWD, st);
     if (lv.n * lv.P == 12)
         msda_fwd_kernel<T, LPC, 12><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)value, loc, attn, (T *)out, lv, Lq,
-                                                                         H, Lv, (int)total);
+                                                                         H, Lv, (int)total, tok_stride);
     else
         msda_fwd_kernel<T, LPC, 0><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)value, loc, attn, (T *)out, lv, Lq,
-                                                                        H, Lv, (int)total);
+                                                                        H, Lv, (int)total, tok_stride);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
@@ -341,27 +339,29 @@ static int launch_fwd(const void *value, const float *loc, const float *attn, vo
 template <typename T, int LPC>
 static int launch_bwd(const void *grad_out, const void *value, const float *loc, const float *attn, void *grad_value,
                       float *grad_loc, float *grad_attn, const Levels &lv, int B, int Lq, int H, int Lv,
-                      cudaStream_t st) {
-    constexpr int DH = LPC * Vec<T>::N;
+                      int tok_stride, int zero_grad_value, cudaStream_t st) {
     const long total = (long)B * Lq * H;
     const int grid = (int)((total + kWarpsPerCta - 1) / kWarpsPerCta);
-    TAMTR_CUDA_OK(cudaMemsetAsync(grad_value, 0, (size_t)B * Lv * H * DH * sizeof(T), st));
+    if (zero_grad_value) {
+        TAMTR_CUDA_OK(cudaMemsetAsync(grad_value, 0, (size_t)B * Lv * tok_stride * sizeof(T), st));
+        count_launch();
+    }
     KernelTimer timer(K_MSDA_BWD, st);
     if (lv.n * lv.P == 12)
         msda_bwd_kernel<T, LPC, 12><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)grad_out, (const T *)value, loc,
                                                                          attn, (T *)grad_value, grad_loc, grad_attn,
-                                                                         lv, Lq, H, Lv, (int)total);
+                                                                         lv, Lq, H, Lv, (int)total, tok_stride);
     else
         msda_bwd_kernel<T, LPC, 0><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)grad_out, (const T *)value, loc,
                                                                         attn, (T *)grad_value, grad_loc, grad_attn, lv,
-                                                                        Lq, H, Lv, (int)total);
-    count_launch(2);  // memset node + kernel
+                                                                        Lq, H, Lv, (int)total, tok_stride);
+    count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 static int check_common(int dtype, int B, int Lv, int H, int Dh, int Lq, int L, int P, const int32_t *shapes,
-                        Levels &lv, int &lpc) {
+                        int &tok_stride, Levels &lv, int &lpc) {
     TAMTR_CHECK_ARG(dtype == TAMTR_F32 || dtype == TAMTR_BF16, TAMTR_E_UNSUPPORTED, "msda: dtype %d not supported",
                     dtype);
     TAMTR_CHECK_ARG(B > 0 && Lv > 0 && H > 0 && Dh > 0 && Lq > 0 && shapes, TAMTR_E_BADARG,
@@ -373,7 +373,10 @@ static int check_common(int dtype, int B, int Lv, int H, int Dh, int Lq, int L, 
     const int rc = fill_levels(lv, L, P, shapes, Lv);
     TAMTR_CHECK_ARG(rc == 0, rc, "msda: bad levels (L=%d P=%d, need L<=%d, L*P<=%d, sum(H_l*W_l)==Lv=%d)", L, P,
                     kMaxLevels, kMaxSamples, Lv);
-    TAMTR_CHECK_ARG((long)Lv * H * Dh < (1L << 31) && (long)B * Lq * H < (1L << 31), TAMTR_E_UNSUPPORTED,
+    if (tok_stride <= 0) tok_stride = H * Dh;
+    TAMTR_CHECK_ARG(tok_stride >= H * Dh && (tok_stride * (dtype == TAMTR_F32 ? 4 : 2)) % 16 == 0, TAMTR_E_BADARG,
+                    "msda: token stride %d must be >= H*Dh = %d and 16-byte aligned", tok_stride, H * Dh);
+    TAMTR_CHECK_ARG((long)Lv * tok_stride < (1L << 31) && (long)B * Lq * H < (1L << 31), TAMTR_E_UNSUPPORTED,
                     "msda: per-image value slab or query count exceeds int32 indexing");
     return 0;
 }
@@ -384,14 +387,15 @@ using namespace tamtr;
 
 extern "C" int tamtr_msda_forward(const void *value, const float *loc, const float *attn, void *out, int dtype, int B,
                                   int Lv, int H, int Dh, int Lq, int L, int P, const int32_t *level_shapes_host,
-                                  void *stream) {
+                                  int value_token_stride, void *stream) {
     TAMTR_CHECK_ARG(value && loc && attn && out, TAMTR_E_BADARG, "msda_forward: null pointer");
     Levels lv;
     int lpc = 0;
-    const int rc = check_common(dtype, B, Lv, H, Dh, Lq, L, P, level_shapes_host, lv, lpc);
+    int ts = value_token_stride;
+    const int rc = check_common(dtype, B, Lv, H, Dh, Lq, L, P, level_shapes_host, ts, lv, lpc);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-#define FWD(T, N) return launch_fwd<T, N>(value, loc, attn, out, lv, B, Lq, H, Lv, st)
+#define FWD(T, N) return launch_fwd<T, N>(value, loc, attn, out, lv, B, Lq, H, Lv, ts, st)
     if (dtype == TAMTR_F32) {
         switch (lpc) { case 2: FWD(float, 2); case 4: FWD(float, 4); case 8: FWD(float, 8); case 16: FWD(float, 16); }
     } else {
@@ -406,16 +410,19 @@ extern "C" int tamtr_msda_forward(const void *value, const float *loc, const flo
 
 extern "C" int tamtr_msda_backward(const void *grad_out, const void *value, const float *loc, const float *attn,
                                    void *grad_value, float *grad_loc, float *grad_attn, int dtype, int B, int Lv, int H,
-                                   int Dh, int Lq, int L, int P, const int32_t *level_shapes_host, void *stream) {
+                                   int Dh, int Lq, int L, int P, const int32_t *level_shapes_host,
+                                   int value_token_stride, int zero_grad_value, void *stream) {
     TAMTR_CHECK_ARG(grad_out && value && loc && attn && grad_value && grad_loc && grad_attn, TAMTR_E_BADARG,
                     "msda_backward: null pointer");
     Levels lv;
     int lpc = 0;
-    const int rc = check_common(dtype, B, Lv, H, Dh, Lq, L, P, level_shapes_host, lv, lpc);
+    int ts = value_token_stride;
+    const int rc = check_common(dtype, B, Lv, H, Dh, Lq, L, P, level_shapes_host, ts, lv, lpc);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-#define BWD(T, N) \
-    return launch_bwd<T, N>(grad_out, value, loc, attn, grad_value, grad_loc, grad_attn, lv, B, Lq, H, Lv, st)
+#define BWD(T, N)                                                                                                  \
+    return launch_bwd<T, N>(grad_out, value, loc, attn, grad_value, grad_loc, grad_attn, lv, B, Lq, H, Lv, ts, \
+                            zero_grad_value, st)
     if (dtype == TAMTR_F32) {
         switch (lpc) { case 2: BWD(float, 2); case 4: BWD(float, 4); case 8: BWD(float, 8); case 16: BWD(float, 16); }
     } else {

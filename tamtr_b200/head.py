@@ -16,6 +16,7 @@ import math
 import torch
 import torch.nn as nn
 
+from . import ops
 from .modules import (MLP, ContrastiveHeadMLP, DeformableTransformerDecoder, DeformableTransformerDecoderLayer,
                       TextDeformableTransformerDecoder)
 
@@ -182,20 +183,43 @@ class _HeadBase(nn.Module):
             cache[key] = self._generate_anchors(shapes, dtype=dtype, device=device)
         return cache[key]
 
-    def _get_decoder_input(self, feats, shapes, dn_embed=None, dn_bbox=None):
-        bs = len(feats)
+    # Query selection (head.py:1220-1264).  The reference runs enc_output / enc_score_head over ALL B*Lv tokens with
+    # autograd on, although only the B*nq selected rows ever receive a gradient (both consumers are row gathers):
+    # its backward is a dense LayerNorm + two dense GEMMs (2 x 282 GFLOP at TAMTR.yaml shapes) over tensors that are
+    # zero outside 0.3 % of their rows, plus two materialised [B, Lv, d] zero tensors.  Here the dense pass only ranks
+    # the tokens (no graph, nothing saved); the selected rows are then recomputed differentiably, and their gradient
+    # reaches `feats` as a row-sparse in-place update (ops.GradHub).  Same values, same gradients.
+    sparse_query_selection = True
+
+    def _rank_tokens(self, feats, valid):
+        with torch.no_grad():
+            features = self.enc_output(valid * feats)
+            return self.enc_score_head(features).max(-1).values              # [B, Lv]
+
+    def _get_decoder_input(self, feats, shapes, dn_embed=None, dn_bbox=None, hub=None):
+        bs, n_tok = feats.shape[0], feats.shape[1]
         anchors, valid = self._anchors(shapes, feats.dtype, feats.device)
-        features = self.enc_output(valid * feats)
-        scores = self.enc_score_head(features)
-        topk = torch.topk(scores.max(-1).values, self.num_queries, dim=1).indices.view(-1)
-        img = torch.arange(end=bs, dtype=topk.dtype, device=topk.device).unsqueeze(-1).repeat(1, self.num_queries).view(-1)
-        top_feats = features[img, topk].view(bs, self.num_queries, -1)
+        if self.sparse_query_selection and hub is not None:
+            topk = torch.topk(self._rank_tokens(feats, valid), self.num_queries, dim=1).indices.view(-1)
+            img = torch.arange(end=bs, dtype=topk.dtype, device=topk.device).unsqueeze(-1).repeat(
+                1, self.num_queries).view(-1)
+            rows = ops.select_rows(feats, img * n_tok + topk, hub)              # [B*nq, d]
+            rows = valid.view(-1)[topk].unsqueeze(-1) * rows
+            top_feats = self.enc_output(rows).view(bs, self.num_queries, -1)
+            enc_scores = self.enc_score_head(top_feats)
+        else:
+            features = self.enc_output(valid * feats)
+            scores = self.enc_score_head(features)
+            topk = torch.topk(scores.max(-1).values, self.num_queries, dim=1).indices.view(-1)
+            img = torch.arange(end=bs, dtype=topk.dtype, device=topk.device).unsqueeze(-1).repeat(
+                1, self.num_queries).view(-1)
+            top_feats = features[img, topk].view(bs, self.num_queries, -1)
+            enc_scores = scores[img, topk].view(bs, self.num_queries, -1)
         top_anchors = anchors[:, topk].view(bs, self.num_queries, -1)
         refer_bbox = self.enc_bbox_head(top_feats) + top_anchors
         enc_bboxes = refer_bbox.sigmoid()
         if dn_bbox is not None:
             refer_bbox = torch.cat([dn_bbox, refer_bbox], 1)
-        enc_scores = scores[img, topk].view(bs, self.num_queries, -1)
         embeddings = self.tgt_embed.weight.unsqueeze(0).repeat(bs, 1, 1) if self.learnt_init_query else top_feats
         if self.training:
             refer_bbox = refer_bbox.detach()
@@ -204,6 +228,15 @@ class _HeadBase(nn.Module):
         if dn_embed is not None:
             embeddings = torch.cat([dn_embed, embeddings], 1)
         return embeddings, refer_bbox, enc_bboxes, enc_scores
+
+    def _encode(self, x):
+        """input projection + (when the CUDA path applies) the gradient hub on the token tensor."""
+        feats, shapes = self._get_encoder_input(x)
+        hub = None
+        if self.sparse_query_selection and feats.is_cuda:
+            hub = ops.GradHub()
+            feats = ops.grad_hub(feats, hub)
+        return feats, shapes, hub
 
     def _cdn(self, batch):
         if isinstance(batch, CdnPlan):      # pre-planned on the host (dp.HeadTrainStep): only the embedding gather
@@ -267,9 +300,9 @@ class RTDETRDecoder(_HeadBase):
             nn.init.constant_(cls.bias, bias_cls)
 
     def forward(self, x, batch=None):
-        feats, shapes = self._get_encoder_input(x)
+        feats, shapes, hub = self._encode(x)
         dn_embed, dn_bbox, attn_mask, dn_meta = self._cdn(batch)
-        embed, refer_bbox, enc_bboxes, enc_scores = self._get_decoder_input(feats, shapes, dn_embed, dn_bbox)
+        embed, refer_bbox, enc_bboxes, enc_scores = self._get_decoder_input(feats, shapes, dn_embed, dn_bbox, hub)
         dec_bboxes, dec_scores = self.decoder(embed, refer_bbox, feats, shapes, self.dec_bbox_head,
                                               self.dec_score_head, self.query_pos_head, attn_mask=attn_mask)
         return self._finish(dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta)
@@ -299,9 +332,9 @@ class ManbaWorldDecoder(_HeadBase):
 
     def forward(self, x, text, batch=None):
         x = [blk(f) for blk, f in zip(self.VSSBlocks, x)]
-        feats, shapes = self._get_encoder_input(x)
+        feats, shapes, hub = self._encode(x)
         dn_embed, dn_bbox, attn_mask, dn_meta = self._cdn(batch)
-        embed, refer_bbox, enc_bboxes, enc_scores = self._get_decoder_input(feats, shapes, dn_embed, dn_bbox)
+        embed, refer_bbox, enc_bboxes, enc_scores = self._get_decoder_input(feats, shapes, dn_embed, dn_bbox, hub)
         dec_bboxes, dec_scores = self.decoder(embed, refer_bbox, feats, shapes, text, self.dec_bbox_head,
                                               self.dec_score_head, self.query_pos_head, attn_mask=attn_mask)
         return self._finish(dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta)

@@ -95,19 +95,24 @@ class MSDeformAttn(nn.Module):
         nn.init.xavier_uniform_(self.output_proj.weight)
         nn.init.zeros_(self.output_proj.bias)
 
-    def forward(self, query, refer_bbox, value, value_shapes, value_mask=None):
+    def forward(self, query, refer_bbox, value, value_shapes, value_mask=None, projected_value=None, arena=None):
+        """`projected_value` / `arena`: optional [B,Lv,H,Dh] view produced by the decoder's batched value projection
+        (ops.split_values) -- then `value` is not projected again here."""
         bs, len_q = query.shape[:2]
         len_v = value.shape[1]
         assert sum(s[0] * s[1] for s in value_shapes) == len_v
-        value = self.value_proj(value)
-        if value_mask is not None:
-            value = value.masked_fill(value_mask[..., None], float(0))
-        value = value.view(bs, len_v, self.n_heads, self.d_model // self.n_heads)
+        if projected_value is None:
+            value = self.value_proj(value)
+            if value_mask is not None:
+                value = value.masked_fill(value_mask[..., None], float(0))
+            value = value.view(bs, len_v, self.n_heads, self.d_model // self.n_heads)
+        else:
+            value = projected_value
         loc, attn = ops.sampling_locations_and_weights(
             query, refer_bbox, self.sampling_offsets.weight, self.sampling_offsets.bias,
             self.attention_weights.weight, self.attention_weights.bias, value_shapes,
             self.n_heads, self.n_levels, self.n_points)
-        out = ops.ms_deform_attn(value, value_shapes, loc, attn)
+        out = ops.ms_deform_attn(value, value_shapes, loc, attn, arena)
         return self.output_proj(out)
 
 
@@ -137,7 +142,8 @@ class DeformableTransformerDecoderLayer(nn.Module):
         tgt2 = self.linear2(self.dropout3(self.act(self.linear1(tgt))))
         return self.norm3(tgt + self.dropout4(tgt2))
 
-    def forward(self, embed, refer_bbox, feats, shapes, padding_mask=None, attn_mask=None, query_pos=None):
+    def forward(self, embed, refer_bbox, feats, shapes, padding_mask=None, attn_mask=None, query_pos=None,
+                projected_value=None, arena=None):
         q = k = self.with_pos_embed(embed, query_pos)
         # need_weights=False: the reference discards the averaged attention map ([0] only, transformer.py:546-547),
         # so the fused SDPA kernels can be used; the output is the same.
@@ -145,7 +151,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
                              need_weights=False)[0].transpose(0, 1)
         embed = self.norm1(embed + self.dropout1(tgt))
         tgt = self.cross_attn(self.with_pos_embed(embed, query_pos), refer_bbox.unsqueeze(2), feats, shapes,
-                              padding_mask)
+                              padding_mask, projected_value, arena)
         embed = self.norm2(embed + self.dropout2(tgt))
         return self.forward_ffn(embed)
 
@@ -158,13 +164,36 @@ class _DecoderBase(nn.Module):
         self.hidden_dim = hidden_dim
         self.eval_idx = eval_idx if eval_idx >= 0 else num_layers + eval_idx
 
+    batched_value_projection = True
+
+    def _project_values(self, feats, padding_mask, n_used):
+        """transformer.py:273 runs value_proj inside every layer on the SAME `feats` (transformer.py:870): do all
+        layers with one [d, n*d] GEMM and hand each layer a column-slice view (head-major, what the sampler reads)."""
+        if not (self.batched_value_projection and feats.is_cuda and padding_mask is None and n_used > 1):
+            return [None] * n_used, None
+        attns = [l.cross_attn for l in self.layers[:n_used]]
+        if any(type(a) is not MSDeformAttn for a in attns):
+            return [None] * n_used, None
+        w = torch.cat([a.value_proj.weight for a in attns], 0)
+        b = torch.cat([a.value_proj.bias for a in attns], 0)
+        arena = ops.ValueArena()
+        value_all = F.linear(feats, w, b)
+        if not value_all.requires_grad:
+            d = attns[0].d_model
+            bs, lv = feats.shape[:2]
+            return [value_all[:, :, i * d:(i + 1) * d].view(bs, lv, attns[0].n_heads, -1) for i in range(n_used)], None
+        return list(ops.split_values(value_all, arena, n_used, attns[0].n_heads)), arena
+
     def _run(self, embed, refer_bbox, feats, shapes, bbox_head, score_fn, pos_mlp, attn_mask, padding_mask):
         output = embed
         dec_bboxes, dec_cls = [], []
         last_refined = None
         refer_bbox = refer_bbox.sigmoid()
+        n_used = self.num_layers if self.training else self.eval_idx + 1
+        values, arena = self._project_values(feats, padding_mask, n_used)
         for i, layer in enumerate(self.layers):
-            output = layer(output, refer_bbox, feats, shapes, padding_mask, attn_mask, pos_mlp(refer_bbox))
+            output = layer(output, refer_bbox, feats, shapes, padding_mask, attn_mask, pos_mlp(refer_bbox),
+                           values[i] if i < n_used else None, arena)
             bbox = bbox_head[i](output)
             refined = torch.sigmoid(bbox + inverse_sigmoid(refer_bbox))
             if self.training:

@@ -13,13 +13,74 @@ def _with_device(t):
     return torch.cuda.device(t.device)
 
 
+def _value_layout(value):
+    """value [B, Lv, H, Dh] either contiguous or a column slice of a wider [B, Lv, C_total] buffer (batched value
+    projection).  Returns (tensor to pass, token stride in elements)."""
+    B, Lv, H, Dh = value.shape
+    st = value.stride()
+    if st[3] == 1 and st[2] == Dh and st[1] >= H * Dh and (st[0] == Lv * st[1] or B == 1) \
+            and (st[1] * value.element_size()) % 16 == 0 and (value.storage_offset() * value.element_size()) % 16 == 0:
+        return value, st[1]
+    value = value.contiguous()
+    return value, H * Dh
+
+
+class ValueArena:
+    """Shared gradient buffer for the value tensors of all decoder layers.
+
+    The decoder projects `feats` once for every layer (one [d, n_layers*d] GEMM); each layer's sampler reads its
+    column slice.  In the backward every sampler accumulates into ITS slice of one zero-initialised
+    [B, Lv, n_layers*d] buffer, which then feeds a single dgrad and a single wgrad GEMM -- no per-layer dense
+    gradient tensors, no gradient-accumulation passes over [B, Lv, d]."""
+
+    def __init__(self):
+        self.buf = None
+
+    def grad_buffer(self, like):
+        if self.buf is None:
+            self.buf = torch.zeros(like.shape, dtype=like.dtype, device=like.device)
+        return self.buf
+
+
+class _SplitValueFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value_all, arena, n, H):
+        B, Lv, C = value_all.shape
+        d = C // n
+        ctx.arena, ctx.n, ctx.d = arena, n, d
+        ctx.meta = (value_all.shape, value_all.dtype, value_all.device)
+        ctx.set_materialize_grads(False)
+        arena.base = value_all
+        return tuple(value_all[:, :, i * d:(i + 1) * d].view(B, Lv, H, d // H) for i in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        arena, n, d = ctx.arena, ctx.n, ctx.d
+        buf, arena.buf, arena.base = arena.buf, None, None
+        shape, dtype, device = ctx.meta
+        if buf is None:
+            buf = torch.zeros(shape, dtype=dtype, device=device)
+        for i, g in enumerate(grads):
+            if g is None:
+                continue
+            sl = buf[:, :, i * d:(i + 1) * d]
+            if g.data_ptr() != sl.data_ptr():          # gradient did not come through the arena: add it
+                sl.add_(g.reshape(shape[0], shape[1], d))
+        return buf, None, None, None
+
+
+def split_values(value_all, arena, n_layers, n_heads):
+    """[B, Lv, n_layers*d] -> n_layers views [B, Lv, H, Dh] sharing `arena` for their gradients."""
+    return _SplitValueFn.apply(value_all, arena, n_layers, n_heads)
+
+
 class _MSDeformAttnFn(torch.autograd.Function):
     """value [B,Lv,H,Dh] (f32|bf16), loc [B,Lq,H,L,P,2] f32, attn [B,Lq,H,L,P] f32 -> out [B,Lq,H*Dh]."""
 
     @staticmethod
-    def forward(ctx, value, loc, attn, shapes):
+    def forward(ctx, value, loc, attn, shapes, arena):
         _lib.require_cuda(value, loc, attn)
-        value = value.contiguous()
+        value, tok_stride = _value_layout(value)
         loc = loc.contiguous().float()
         attn = attn.contiguous().float()
         B, Lv, H, Dh = value.shape
@@ -30,11 +91,13 @@ class _MSDeformAttnFn(torch.autograd.Function):
         out = torch.empty(B, Lq, H * Dh, dtype=value.dtype, device=value.device)
         with _with_device(value):
             rc = _lib.lib().tamtr_msda_forward(value.data_ptr(), loc.data_ptr(), attn.data_ptr(), out.data_ptr(),
-                                               _lib.dtype_code(value), B, Lv, H, Dh, Lq, L, P, sh,
+                                               _lib.dtype_code(value), B, Lv, H, Dh, Lq, L, P, sh, tok_stride,
                                                _lib.stream_ptr(value.device))
         _lib.check(rc, "msda_forward")
         ctx.save_for_backward(value, loc, attn)
         ctx.shapes = [list(map(int, s)) for s in (shapes.tolist() if isinstance(shapes, torch.Tensor) else shapes)]
+        ctx.tok_stride = tok_stride
+        ctx.arena = arena if (arena is not None and tok_stride != H * Dh) else None
         return out
 
     @staticmethod
@@ -45,7 +108,21 @@ class _MSDeformAttnFn(torch.autograd.Function):
         B, Lv, H, Dh = value.shape
         _, Lq, _, L, P, _ = loc.shape
         sh, _ = _lib.shapes_array(ctx.shapes)
-        grad_value = torch.empty_like(value)          # zeroed by the C call
+        tok_stride = ctx.tok_stride
+        if ctx.arena is not None:
+            # accumulate into this layer's column slice of the shared, already zeroed buffer
+            base = ctx.arena.base
+            buf = ctx.arena.grad_buffer(base)
+            off = value.storage_offset() - base.storage_offset()
+            grad_value = buf.view(-1)[off:].as_strided(value.shape, value.stride())
+            zero = 0
+        elif tok_stride != H * Dh:
+            grad_value = torch.empty(B, Lv, H, Dh, dtype=value.dtype, device=value.device)
+            tok_stride, zero = H * Dh, 1
+            value = value.contiguous()
+        else:
+            grad_value = torch.empty_like(value)          # zeroed by the C call
+            zero = 1
         grad_loc = torch.empty_like(loc)
         grad_attn = torch.empty_like(attn)
         # grad_value is accumulated with vector atomics -> run-to-run bit differences, exactly like the
@@ -60,18 +137,19 @@ class _MSDeformAttnFn(torch.autograd.Function):
             rc = _lib.lib().tamtr_msda_backward(grad_out.data_ptr(), value.data_ptr(), loc.data_ptr(),
                                                 attn.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(),
                                                 grad_attn.data_ptr(), _lib.dtype_code(value), B, Lv, H, Dh, Lq, L, P,
-                                                sh, _lib.stream_ptr(value.device))
+                                                sh, tok_stride, zero, _lib.stream_ptr(value.device))
         _lib.check(rc, "msda_backward")
-        return grad_value, grad_loc, grad_attn, None
+        return grad_value, grad_loc, grad_attn, None, None
 
 
-def ms_deform_attn(value, value_spatial_shapes, sampling_locations, attention_weights):
-    """Drop-in for multi_scale_deformable_attn_pytorch (utils.py:42).  fp16 values are computed in fp32."""
+def ms_deform_attn(value, value_spatial_shapes, sampling_locations, attention_weights, arena=None):
+    """Drop-in for multi_scale_deformable_attn_pytorch (utils.py:42).  fp16 values are computed in fp32.
+    `arena`: optional ops.ValueArena when `value` is one of the views returned by split_values()."""
     _lib.require_cuda(value, sampling_locations, attention_weights)
     if value.dtype == torch.float16 or value.dtype == torch.float64:
-        out = _MSDeformAttnFn.apply(value.float(), sampling_locations, attention_weights, value_spatial_shapes)
+        out = _MSDeformAttnFn.apply(value.float(), sampling_locations, attention_weights, value_spatial_shapes, None)
         return out.to(value.dtype)
-    return _MSDeformAttnFn.apply(value, sampling_locations, attention_weights, value_spatial_shapes)
+    return _MSDeformAttnFn.apply(value, sampling_locations, attention_weights, value_spatial_shapes, arena)
 
 
 def ms_deform_attn_corners(sampling_locations, value_spatial_shapes):
@@ -276,3 +354,66 @@ def max_sigmoid_gate(embed, guide, bias, nh):
     """extra_modules/block.py:216-220: embed [B,nh*hc,H,W], guide [B,N,nh,hc], bias [nh] -> aw [B,nh,H,W] fp32."""
     _lib.require_cuda(embed, guide, bias)
     return _MaxSigmoidFn.apply(embed, guide, bias, nh)
+
+
+# ------------------------------------------------------------------------------------ sparse-gradient plumbing
+class GradHub:
+    """Collects row-sparse gradients for one activation so that they are added IN PLACE to the dense gradient that
+    the other consumers produce, instead of each materialising a mostly-zero tensor of the activation's size.
+
+    Used for `feats` [B, Lv, d] in the detection heads: the decoder layers send it a dense gradient (value_proj),
+    the query-selection branch only touches B*nq of its B*Lv rows (head.py:1233-1254 gathers top-k rows)."""
+
+    def __init__(self):
+        self.pending = []
+
+
+class _HubFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, hub):
+        ctx.hub = hub
+        ctx.set_materialize_grads(False)
+        ctx.meta = (x.shape, x.dtype, x.device)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        hub = ctx.hub
+        if g is None:
+            if not hub.pending:
+                return None, None
+            shape, dtype, device = ctx.meta
+            g = torch.zeros(shape, dtype=dtype, device=device)
+        elif hub.pending and not g.is_contiguous():
+            g = g.contiguous()
+        for idx, rows in hub.pending:
+            g.view(-1, g.shape[-1]).index_add_(0, idx, rows.to(g.dtype))
+        hub.pending.clear()
+        return g, None
+
+
+class _SelectRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flat_idx, hub):
+        ctx.hub = hub
+        ctx.save_for_backward(flat_idx)
+        return x.reshape(-1, x.shape[-1])[flat_idx]
+
+    @staticmethod
+    def backward(ctx, g):
+        (flat_idx,) = ctx.saved_tensors
+        ctx.hub.pending.append((flat_idx, g))
+        return None, None, None
+
+
+def grad_hub(x, hub):
+    """Identity on `x`; row-sparse gradients registered on `hub` are folded into x's gradient in place."""
+    return _HubFn.apply(x, hub) if x.requires_grad else x
+
+
+def select_rows(x, flat_idx, hub):
+    """x.reshape(-1, C)[flat_idx] whose backward is a row-sparse update routed through `hub` (x must be the output
+    of grad_hub(..., hub))."""
+    if not x.requires_grad:
+        return x.reshape(-1, x.shape[-1])[flat_idx]
+    return _SelectRowsFn.apply(x, flat_idx, hub)

@@ -54,11 +54,14 @@ def test_argument_validation_without_gpu():
     lib = _lib.lib()
     sh = (ctypes.c_int32 * 2)(2, 2)
     # null pointers -> TAMTR_E_BADARG before any CUDA call
-    rc = lib.tamtr_msda_forward(None, None, None, None, 0, 1, 4, 1, 8, 1, 1, 1, sh, None)
+    rc = lib.tamtr_msda_forward(None, None, None, None, 0, 1, 4, 1, 8, 1, 1, 1, sh, 0, None)
     assert rc == -1 and b"null" in lib.tamtr_last_error()
     # unsupported head dim
-    rc = lib.tamtr_msda_forward(1, 1, 1, 1, 0, 1, 4, 1, 7, 1, 1, 1, sh, None)
+    rc = lib.tamtr_msda_forward(1, 1, 1, 1, 0, 1, 4, 1, 7, 1, 1, 1, sh, 0, None)
     assert rc == -2
     # level shapes do not add up to Lv
-    rc = lib.tamtr_msda_forward(1, 1, 1, 1, 0, 1, 5, 1, 8, 1, 1, 1, sh, None)
+    rc = lib.tamtr_msda_forward(1, 1, 1, 1, 0, 1, 5, 1, 8, 1, 1, 1, sh, 0, None)
+    assert rc == -1
+    # token stride smaller than H*Dh
+    rc = lib.tamtr_msda_forward(1, 1, 1, 1, 0, 1, 4, 1, 8, 1, 1, 1, sh, 4, None)
     assert rc == -1

@@ -202,3 +202,31 @@ def test_non_default_stream_and_launch_counter(cuda_lib):
     s.synchronize()
     assert cuda_lib.launch_count() == before + 1
     assert rel_l2(o, msda.forward_c(v, shapes, l, a)) < FP32_TOL
+
+
+def test_strided_value_views_and_arena(cuda_lib):
+    """Batched value projection: each layer samples a column slice of one [B, Lv, n*d] buffer and accumulates its
+    value gradient into the matching slice of ONE shared buffer (ops.ValueArena)."""
+    from tamtr_b200 import ops
+    shapes = msda.level_shapes(20)
+    B, Lq, H, Dh, n = 2, 40, 8, 32, 3
+    d = H * Dh
+    Lv = sum(h * w for h, w in shapes)
+    g = torch.Generator().manual_seed(3)
+    value_all = torch.randn(B, Lv, n * d, generator=g)
+    ins = [msda.make_inputs(10 + i, B, Lq, H, Dh, shapes, oob_frac=0.2) for i in range(n)]
+    for dtype, tol in ((torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)):
+        va = value_all.to(dtype).cuda().requires_grad_()
+        arena = ops.ValueArena()
+        views = ops.split_values(va * 1.0, arena, n, H)
+        total = 0
+        refs = []
+        for i, (_, loc, attn, gout) in enumerate(ins):
+            out = cuda_lib.ms_deform_attn(views[i], shapes, loc.cuda(), attn.cuda(), arena)
+            total = total + (out.float() * gout.cuda()).sum()
+            v_i = value_all[:, :, i * d:(i + 1) * d].to(dtype).float().reshape(B, Lv, H, Dh)
+            assert rel_l2(out, msda.forward_c(v_i, shapes, loc, attn)) < tol
+            refs.append(msda.backward_c(gout.to(dtype).float(), v_i, shapes, loc, attn)[0].reshape(B, Lv, d))
+        total.backward()
+        assert rel_l2(va.grad, torch.cat(refs, -1)) < tol
+        assert arena.buf is None            # consumed by the split node
