@@ -137,6 +137,13 @@ int tamtr_contrastive_backward(const float *grad_out, const void *x, const float
 int tamtr_max_sigmoid_forward(const void *embed, const float *guide, const float *bias, float *aw, uint8_t *amax,
                               int dtype, int B, int nh, int hc, int HW, int N, void *stream);
 
+/* Same gate on the tensor cores for bf16 activations: tcgen05.mma (M=128 pixels, N=pad16(N), K=hc=32) with TMEM
+ * accumulators, TMA-staged 128B-swizzled tiles of `embed` (MN-major A operand straight from NCHW), warp-specialised
+ * producer / MMA / epilogue.  embed bf16 [B, nh*32, HW] (16-byte aligned, HW % 8 == 0), guide f32 [B,N,nh,32]
+ * (rounded to bf16 inside), N <= 128.  Same outputs as tamtr_max_sigmoid_forward; the backward is shared. */
+int tamtr_max_sigmoid_tc_forward(const void *embed_bf16, const float *guide, const float *bias, float *aw,
+                                 uint8_t *amax, int B, int nh, int hc, int HW, int N, void *stream);
+
 /* grad_embed [B, nh*hc, HW] (dtype of embed, fully written: the gate's contribution only);
  * grad_guide [B, N, nh, hc] f32 and grad_bias [nh] f32 are zeroed by the call, then accumulated. */
 int tamtr_max_sigmoid_backward(const float *grad_aw, const float *aw, const uint8_t *amax, const void *embed,

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "tamtr_contrastive_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp] + [_i] * 5 + [_vp]),
     "tamtr_contrastive_backward": (ctypes.c_int, [_fp, _vp, _fp, _fp, _vp, _fp] + [_i] * 5 + [_vp]),
     "tamtr_max_sigmoid_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _vp] + [_i] * 6 + [_vp]),
+    "tamtr_max_sigmoid_tc_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }
 

@@ -309,9 +309,17 @@ def contrastive_head(x, w, logit_scale, bias):
 
 
 # ------------------------------------------------------------------------------------ max-sigmoid gate
+def _gate_uses_tensor_cores(embed, hc, HW, N, use_tensor_cores):
+    ok = embed.dtype == torch.bfloat16 and hc == 32 and HW % 8 == 0 and N <= 128 and embed.data_ptr() % 16 == 0
+    if use_tensor_cores and not ok:
+        raise RuntimeError("tamtr_b200: tensor-core max-sigmoid gate needs bf16 activations, hc == 32, H*W % 8 == 0, "
+                           "N <= 128")
+    return ok if use_tensor_cores is None else bool(use_tensor_cores)
+
+
 class _MaxSigmoidFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, embed, guide, bias, nh):
+    def forward(ctx, embed, guide, bias, nh, use_tensor_cores=None):
         embed = embed.contiguous()
         if embed.dtype not in (torch.float32, torch.bfloat16):
             embed = embed.float()
@@ -323,9 +331,14 @@ class _MaxSigmoidFn(torch.autograd.Function):
         aw = torch.empty(B, nh, Hh, Ww, dtype=torch.float32, device=embed.device)
         amax = torch.empty(B, nh, Hh, Ww, dtype=torch.uint8, device=embed.device)
         with _with_device(embed):
-            rc = _lib.lib().tamtr_max_sigmoid_forward(embed.data_ptr(), g32.data_ptr(), b32.data_ptr(), aw.data_ptr(),
-                                                      amax.data_ptr(), _lib.dtype_code(embed), B, nh, hc, Hh * Ww, N,
-                                                      _lib.stream_ptr(embed.device))
+            if _gate_uses_tensor_cores(embed, hc, Hh * Ww, N, use_tensor_cores):
+                rc = _lib.lib().tamtr_max_sigmoid_tc_forward(embed.data_ptr(), g32.data_ptr(), b32.data_ptr(),
+                                                             aw.data_ptr(), amax.data_ptr(), B, nh, hc, Hh * Ww, N,
+                                                             _lib.stream_ptr(embed.device))
+            else:
+                rc = _lib.lib().tamtr_max_sigmoid_forward(embed.data_ptr(), g32.data_ptr(), b32.data_ptr(),
+                                                          aw.data_ptr(), amax.data_ptr(), _lib.dtype_code(embed), B,
+                                                          nh, hc, Hh * Ww, N, _lib.stream_ptr(embed.device))
         _lib.check(rc, "max_sigmoid_forward")
         ctx.save_for_backward(embed, g32, aw, amax)
         ctx.meta = (B, nh, hc, Hh * Ww, N, guide.dtype, bias.dtype)
@@ -347,13 +360,15 @@ class _MaxSigmoidFn(torch.autograd.Function):
                                                        _lib.dtype_code(embed), B, nh, hc, HW, N,
                                                        _lib.stream_ptr(embed.device))
         _lib.check(rc, "max_sigmoid_backward")
-        return grad_embed, grad_guide.to(gdt), grad_bias.to(bdt), None
+        return grad_embed, grad_guide.to(gdt), grad_bias.to(bdt), None, None
 
 
-def max_sigmoid_gate(embed, guide, bias, nh):
-    """extra_modules/block.py:216-220: embed [B,nh*hc,H,W], guide [B,N,nh,hc], bias [nh] -> aw [B,nh,H,W] fp32."""
+def max_sigmoid_gate(embed, guide, bias, nh, use_tensor_cores=None):
+    """extra_modules/block.py:216-220: embed [B,nh*hc,H,W], guide [B,N,nh,hc], bias [nh] -> aw [B,nh,H,W] fp32.
+    bf16 activations with hc == 32 run on the tcgen05 kernel (csrc/maxsig_tc.cu); fp32 ones on the exact CUDA-core
+    kernel.  `use_tensor_cores` forces the choice (tests / benchmarks)."""
     _lib.require_cuda(embed, guide, bias)
-    return _MaxSigmoidFn.apply(embed, guide, bias, nh)
+    return _MaxSigmoidFn.apply(embed, guide, bias, nh, use_tensor_cores)
 
 
 # ------------------------------------------------------------------------------------ sparse-gradient plumbing
