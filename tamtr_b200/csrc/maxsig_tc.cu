@@ -259,8 +259,10 @@ extern "C" int tamtr_max_sigmoid_tc_forward(const void *embed_bf16, const float 
 
     const int Npad = ((N + 15) / 16) * 16;
     const int n_tiles = (HW + kTcTileM - 1) / kTcTileM;
-    // enough CTAs for ~2 per SM; each CTA walks the tiles of its (b, m) with stride gridDim.x
-    int chunks = (2 * 148 + B * nh - 1) / (B * nh);
+    // one wave of (at most) 2 CTAs per SM: each CTA walks the tiles of its (b, m) with stride gridDim.x
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+    int chunks = (2 * n_sm) / (B * nh);
     if (chunks < 1) chunks = 1;
     if (chunks > n_tiles) chunks = n_tiles;
     const size_t smem = sizeof(TcSmem) + 1024;
