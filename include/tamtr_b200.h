@@ -150,6 +150,36 @@ int tamtr_max_sigmoid_backward(const float *grad_aw, const float *aw, const uint
                                const float *guide, void *grad_embed, float *grad_guide, float *grad_bias,
                                int dtype, int B, int nh, int hc, int HW, int N, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Encoder-side token kernels (everything on the [B, Lv, d] token tensor that is not a GEMM).
+ *
+ * Token-major BatchNorm of `input_proj` (ultralytics/nn/modules/head.py:1202-1218: conv1x1 + BatchNorm2d in NCHW, then
+ * flatten(2).permute(0,2,1) + cat).  The 1x1 conv is a GEMM that writes [B, HW_l, d] into the level's slice of the
+ * token tensor; the statistics and both normalisation passes are:
+ *   tamtr_col_reduce2: partial[cta][0][c] = sum_rows a[r][c], partial[cta][1][c] = sum_rows a[r][c]*b[r][c] over the
+ *                      tokens [tok0, tok0+ntok) of every image; n_cta = tamtr_col_reduce2_ctas(B, ntok); fp32 sums
+ *   tamtr_affine_rows: out[b,t,c] = A[l][c]*a[b,t,c] + Bc[l][c]*b[b,t,c] + Cc[l][c], l = level of token t
+ *                      (b / Bc may be NULL); level_starts_host = first token of each of the L levels
+ * a, b, out: [B, Lv, d] f32|bf16 (dtype); A, Bc, Cc: [L, d] f32.  d % (16/sizeof) == 0, d <= 1024.
+ */
+int tamtr_col_reduce2_ctas(int B, int ntok);
+int tamtr_col_reduce2(const void *a, const void *b, float *partial, int dtype, int B, int Lv, int d, int tok0, int ntok,
+                      void *stream);
+int tamtr_affine_rows(void *out, const void *a, const void *b, const float *A, const float *Bc, const float *Cc,
+                      int dtype, int B, int Lv, int d, int L, const int32_t *level_starts_host, void *stream);
+
+/* Query-selection ranking (head.py:1229-1237: enc_output = Linear + LayerNorm over all tokens, enc_score_head, max over
+ * classes), fused after the two GEMMs:
+ *   E   [B*Lv, d] f32|bf16 = feats @ enc_output.0.weight^T (no bias, no validity mask)
+ *   raw [B*Lv, nc] f32     = E @ (enc_score_head.weight * ln.weight)^T
+ *   v = valid[t] ? E + enc_bias : enc_bias; (mean, rstd) = LayerNorm statistics of v (eps)
+ *   out[row] = max_k rstd * (raw[k] + bw[k] - mean*sw[k]) + ck[k]        (raw treated as 0 for invalid tokens)
+ *   bw[k] = enc_bias . W'[k], sw[k] = sum_c W'[k][c], ck[k] = ln.bias . score_w[k] + score_b[k]
+ */
+int tamtr_rank_tokens(const void *E, const float *raw, const float *enc_bias, const uint8_t *valid, const float *bw,
+                      const float *sw, const float *ck, float *out, int dtype, int B, int Lv, int d, int nc, float eps,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

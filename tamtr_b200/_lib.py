@@ -36,6 +36,10 @@ _SIGNATURES = {
     "tamtr_contrastive_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp] + [_i] * 5 + [_vp]),
     "tamtr_contrastive_backward": (ctypes.c_int, [_fp, _vp, _fp, _fp, _vp, _fp] + [_i] * 5 + [_vp]),
     "tamtr_max_sigmoid_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _vp] + [_i] * 6 + [_vp]),
+    "tamtr_col_reduce2_ctas": (ctypes.c_int, [_i, _i]),
+    "tamtr_col_reduce2": (ctypes.c_int, [_vp, _vp, _fp] + [_i] * 6 + [_vp]),
+    "tamtr_affine_rows": (ctypes.c_int, [_vp, _vp, _vp, _fp, _fp, _fp] + [_i] * 5 + [_vp, _vp]),
+    "tamtr_rank_tokens": (ctypes.c_int, [_vp, _fp, _fp, _vp, _fp, _fp, _fp, _fp] + [_i] * 5 + [ctypes.c_float, _vp]),
     "tamtr_max_sigmoid_tc_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }

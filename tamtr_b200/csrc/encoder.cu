@@ -1,0 +1,269 @@
+// Encoder-side token kernels of the detection heads (sm_100a): everything that touches the [B, Lv, d] token tensor
+// outside the GEMMs.  All three are single-pass, HBM-bound streaming kernels (16-byte accesses, fp32 accumulate).
+//
+// * tamtr_col_reduce2 / tamtr_affine_rows -- BatchNorm of `input_proj` in TOKEN-MAJOR layout.  The reference computes
+//   conv1x1 + BatchNorm2d in NCHW and then flatten(2).permute(0,2,1) + cat (ultralytics/nn/modules/head.py:1202-1218):
+//   four passes over the level plus a strided transpose copy, and their mirror images in the backward.  Here the
+//   1x1 conv is a GEMM that writes [B, HW_l, d] straight into the level's slice of the token tensor, the batch
+//   statistics are column reductions (sum a, sum a*b) and normalisation / its backward are one affine pass
+//   out = A*a + Bc*b + Cc with per-(level, channel) coefficients (ops.py::_InputProjFn has the algebra).
+// * tamtr_rank_tokens -- query-selection ranking (head.py:1229-1237): per token LayerNorm statistics of
+//   enc_output.0's GEMM row, folded with the skinny score GEMM, max over classes.  Replaces valid-mask multiply,
+//   LayerNorm (fp32 materialisation of [B, Lv, d]), cast, Linear(d -> nc) epilogue and max.
+#include "common.cuh"
+
+namespace tamtr {
+
+constexpr int kEncThreads = 256;
+
+template <typename T> struct Pack;                 // 16-byte pack of T <-> fp32
+template <> struct Pack<float> {
+    static constexpr int N = 4;
+    __device__ static __forceinline__ void load(const float *p, float (&f)[4]) {
+        const float4 v = *reinterpret_cast<const float4 *>(p);
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    }
+    __device__ static __forceinline__ void store(float *p, const float (&f)[4]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+};
+template <> struct Pack<__nv_bfloat16> {
+    static constexpr int N = 8;
+    __device__ static __forceinline__ void load(const __nv_bfloat16 *p, float (&f)[8]) {
+        const uint4 u = *reinterpret_cast<const uint4 *>(p);
+        f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+        f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+        f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+        f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+    }
+    __device__ static __forceinline__ uint32_t pack2(float lo, float hi) {
+        uint32_t r;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        return r;
+    }
+    __device__ static __forceinline__ void store(__nv_bfloat16 *p, const float (&f)[8]) {
+        *reinterpret_cast<uint4 *>(p) =
+            make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+};
+
+// partial[cta][0][c] = sum over the CTA's rows of a[r][c], partial[cta][1][c] = sum of a[r][c] * b[r][c].
+// Rows are the tokens [tok0, tok0 + ntok) of every image of a [B, Lv, d] tensor.  Thread = one 16-byte column pack;
+// blockDim.x = d / N packs, blockDim.y row lanes; the y lanes are combined through shared memory.
+template <typename T>
+__global__ void col_reduce2_kernel(const T *__restrict__ a, const T *__restrict__ b, float *__restrict__ partial,
+                                   int Lv, int d, int tok0, int ntok, long rows, int rows_per_cta) {
+    constexpr int N = Pack<T>::N;
+    extern __shared__ float s_red[];   // [blockDim.y][2][d]
+    const int col = threadIdx.x * N;
+    float sa[N], sab[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) sa[i] = sab[i] = 0.f;
+    const long r0 = (long)blockIdx.x * rows_per_cta;
+    const long r1 = min(rows, r0 + rows_per_cta);
+    for (long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        const long img = r / ntok, t = tok0 + r % ntok;
+        const size_t off = ((size_t)img * Lv + t) * d + col;
+        float fa[N], fb[N];
+        Pack<T>::load(a + off, fa);
+        Pack<T>::load(b + off, fb);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { sa[i] += fa[i]; sab[i] = fmaf(fa[i], fb[i], sab[i]); }
+    }
+    float *mine = s_red + (size_t)threadIdx.y * 2 * d;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { mine[col + i] = sa[i]; mine[d + col + i] = sab[i]; }
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    for (int j = tid; j < 2 * d; j += nthr) {
+        float s = 0.f;
+        for (int y = 0; y < blockDim.y; ++y) s += s_red[(size_t)y * 2 * d + j];
+        partial[(size_t)blockIdx.x * 2 * d + j] = s;
+    }
+}
+
+struct RowLevels {
+    int n;
+    int start[kMaxLevels + 1];   // token starts, start[n] = Lv
+};
+
+// out[b,t,c] = A[l][c] * a[b,t,c] + Bc[l][c] * b[b,t,c] + Cc[l][c]    (l = level of token t; b may be null)
+template <typename T, bool HAS_B>
+__global__ void __launch_bounds__(kEncThreads)
+affine_rows_kernel(T *__restrict__ out, const T *__restrict__ a, const T *__restrict__ b, const float *__restrict__ A,
+                   const float *__restrict__ Bc, const float *__restrict__ Cc, const RowLevels lv, int Lv, int d,
+                   size_t n_packs) {
+    constexpr int N = Pack<T>::N;
+    const int packs_per_row = d / N;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_packs; p += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = p / packs_per_row;
+        const int col = (int)(p % packs_per_row) * N;
+        const int t = (int)(row % Lv);
+        int l = 0;
+#pragma unroll
+        for (int i = 1; i < kMaxLevels; ++i) l += (i < lv.n && t >= lv.start[i]) ? 1 : 0;
+        const size_t off = row * d + col;
+        float fa[N], fb[N], fo[N];
+        Pack<T>::load(a + off, fa);
+        if (HAS_B) Pack<T>::load(b + off, fb);
+        const float *pa = A + (size_t)l * d + col, *pb = Bc + (size_t)l * d + col, *pc = Cc + (size_t)l * d + col;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            float v = fmaf(__ldg(pa + i), fa[i], __ldg(pc + i));
+            if (HAS_B) v = fmaf(__ldg(pb + i), fb[i], v);
+            fo[i] = v;
+        }
+        Pack<T>::store(out + off, fo);
+    }
+}
+
+// One warp per token.  v = valid ? E[row] + enc_bias : enc_bias;  (mean, rstd) = LayerNorm statistics of v;
+// score_k = rstd * (raw[row][k] + bw[k] - mean * sw[k]) + ck[k];  out[row] = max_k score_k
+//   raw = E @ (score_w * ln_w)^T  (library GEMM on the un-biased rows),  bw = enc_bias . W', sw = sum_c W'[k][c],
+//   ck = ln_b . score_w[k] + score_b[k].  Invalid tokens (anchor too close to the border, head.py:1195-1199) have the
+//   constant row enc_bias: raw is ignored for them (raw_invalid = 0).
+template <typename T>
+__global__ void __launch_bounds__(kEncThreads)
+rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const float *__restrict__ enc_bias,
+                   const uint8_t *__restrict__ valid, const float *__restrict__ bw, const float *__restrict__ sw,
+                   const float *__restrict__ ck, float *__restrict__ out, long rows, int Lv, int d, int nc, float eps) {
+    constexpr int N = Pack<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (kEncThreads / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const bool ok = valid[row % Lv] != 0;
+    float s = 0.f, ss = 0.f;
+    float v[4][N];                     // the row stays in registers: d <= 4 * 32 * N
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int c = (p * 32 + lane) * N;
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[p][i] = 0.f;
+        if (c < d) {
+            float e[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) e[i] = 0.f;
+            if (ok) Pack<T>::load(E + (size_t)row * d + c, e);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                v[p][i] = e[i] + __ldg(enc_bias + c + i);
+                s += v[p][i];
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    const float mean = s / (float)d;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int c = (p * 32 + lane) * N;
+        if (c < d) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) { const float dlt = v[p][i] - mean; ss = fmaf(dlt, dlt, ss); }
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+    const float rstd = rsqrtf(ss / (float)d + eps);
+    float best = -INFINITY;
+    for (int k = lane; k < nc; k += 32) {
+        const float r = ok ? __ldg(raw + (size_t)row * nc + k) : 0.f;
+        best = fmaxf(best, rstd * (r + __ldg(bw + k) - mean * __ldg(sw + k)) + __ldg(ck + k));
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, m));
+    if (lane == 0) out[row] = best;
+}
+
+static int enc_check(int dtype, int d) {
+    TAMTR_CHECK_ARG(dtype == TAMTR_F32 || dtype == TAMTR_BF16, TAMTR_E_UNSUPPORTED, "encoder: dtype %d", dtype);
+    const int n = dtype == TAMTR_F32 ? 4 : 8;
+    TAMTR_CHECK_ARG(d > 0 && d % n == 0 && d <= 1024, TAMTR_E_UNSUPPORTED,
+                    "encoder: channel dim %d unsupported (multiple of %d, <= 1024)", d, n);
+    return 0;
+}
+
+}  // namespace tamtr
+
+using namespace tamtr;
+
+extern "C" int tamtr_col_reduce2_ctas(int B, int ntok) {
+    const long rows = (long)B * ntok;
+    long n = (rows + 127) / 128;
+    if (n > 592) n = 592;   // 4 CTAs per SM
+    return (int)(n < 1 ? 1 : n);
+}
+
+extern "C" int tamtr_col_reduce2(const void *a, const void *b, float *partial, int dtype, int B, int Lv, int d, int tok0,
+                                 int ntok, void *stream) {
+    TAMTR_CHECK_ARG(a && b && partial, TAMTR_E_BADARG, "col_reduce2: null pointer");
+    TAMTR_CHECK_ARG(B > 0 && ntok > 0 && tok0 >= 0 && tok0 + ntok <= Lv, TAMTR_E_BADARG, "col_reduce2: bad token range");
+    const int rc = enc_check(dtype, d);
+    if (rc) return rc;
+    const long rows = (long)B * ntok;
+    const int ctas = tamtr_col_reduce2_ctas(B, ntok);
+    const int rpc = (int)((rows + ctas - 1) / ctas);
+    const int n = dtype == TAMTR_F32 ? 4 : 8;
+    const int bx = d / n;
+    int by = kEncThreads / bx;
+    if (by < 1) by = 1;
+    const size_t smem = sizeof(float) * (size_t)by * 2 * d;
+    TAMTR_CHECK_ARG(smem <= 48 * 1024, TAMTR_E_UNSUPPORTED, "col_reduce2: d = %d needs too much shared memory", d);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TAMTR_F32)
+        col_reduce2_kernel<float><<<ctas, dim3(bx, by), smem, st>>>((const float *)a, (const float *)b, partial, Lv, d,
+                                                                    tok0, ntok, rows, rpc);
+    else
+        col_reduce2_kernel<__nv_bfloat16><<<ctas, dim3(bx, by), smem, st>>>(
+            (const __nv_bfloat16 *)a, (const __nv_bfloat16 *)b, partial, Lv, d, tok0, ntok, rows, rpc);
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tamtr_affine_rows(void *out, const void *a, const void *b, const float *A, const float *Bc, const float *Cc,
+                                 int dtype, int B, int Lv, int d, int L, const int32_t *level_starts_host, void *stream) {
+    TAMTR_CHECK_ARG(out && a && A && Cc && level_starts_host, TAMTR_E_BADARG, "affine_rows: null pointer");
+    TAMTR_CHECK_ARG(!b || Bc, TAMTR_E_BADARG, "affine_rows: b given without Bc");
+    TAMTR_CHECK_ARG(B > 0 && Lv > 0 && L >= 1 && L <= kMaxLevels, TAMTR_E_BADARG, "affine_rows: bad sizes");
+    const int rc = enc_check(dtype, d);
+    if (rc) return rc;
+    RowLevels lv;
+    lv.n = L;
+    for (int i = 0; i <= kMaxLevels; ++i) lv.start[i] = i < L ? level_starts_host[i] : Lv;
+    const int n = dtype == TAMTR_F32 ? 4 : 8;
+    const size_t n_packs = (size_t)B * Lv * d / n;
+    size_t blocks = (n_packs + kEncThreads - 1) / kEncThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+#define AFF(T, HB) affine_rows_kernel<T, HB><<<(unsigned)blocks, kEncThreads, 0, st>>>((T *)out, (const T *)a, (const T *)b, A, Bc, Cc, lv, Lv, d, n_packs)
+    if (dtype == TAMTR_F32) { if (b) AFF(float, true); else AFF(float, false); }
+    else { if (b) AFF(__nv_bfloat16, true); else AFF(__nv_bfloat16, false); }
+#undef AFF
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tamtr_rank_tokens(const void *E, const float *raw, const float *enc_bias, const uint8_t *valid,
+                                 const float *bw, const float *sw, const float *ck, float *out, int dtype, int B, int Lv,
+                                 int d, int nc, float eps, void *stream) {
+    TAMTR_CHECK_ARG(E && raw && enc_bias && valid && bw && sw && ck && out, TAMTR_E_BADARG, "rank_tokens: null pointer");
+    TAMTR_CHECK_ARG(B > 0 && Lv > 0 && nc > 0, TAMTR_E_BADARG, "rank_tokens: bad sizes");
+    const int rc = enc_check(dtype, d);
+    if (rc) return rc;
+    const int n = dtype == TAMTR_F32 ? 4 : 8;
+    TAMTR_CHECK_ARG(d <= 4 * 32 * n, TAMTR_E_UNSUPPORTED, "rank_tokens: d = %d too large", d);
+    const long rows = (long)B * Lv;
+    const unsigned blocks = (unsigned)((rows + kEncThreads / 32 - 1) / (kEncThreads / 32));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TAMTR_F32)
+        rank_tokens_kernel<float><<<blocks, kEncThreads, 0, st>>>((const float *)E, raw, enc_bias, valid, bw, sw, ck, out,
+                                                                  rows, Lv, d, nc, eps);
+    else
+        rank_tokens_kernel<__nv_bfloat16><<<blocks, kEncThreads, 0, st>>>((const __nv_bfloat16 *)E, raw, enc_bias, valid,
+                                                                          bw, sw, ck, out, rows, Lv, d, nc, eps);
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}

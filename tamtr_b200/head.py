@@ -164,7 +164,17 @@ class _HeadBase(nn.Module):
         anchors = torch.log(anchors / (1 - anchors)).masked_fill(~valid, float("inf"))
         return anchors, valid
 
+    fused_input_proj = True
+
+    def _fusable_input_proj(self, x):
+        return (self.fused_input_proj and x[0].is_cuda and all(
+            isinstance(p, nn.Sequential) and len(p) == 2 and isinstance(p[0], nn.Conv2d) and p[0].bias is None
+            and p[0].kernel_size == (1, 1) and p[0].stride == (1, 1) and p[0].groups == 1
+            and isinstance(p[1], nn.BatchNorm2d) and p[1].affine for p in self.input_proj))
+
     def _get_encoder_input(self, x):
+        if self._fusable_input_proj(x):
+            return ops.input_proj_tokens(list(x), self.input_proj, self.training)
         feats, shapes = [], []
         for proj, fmap in zip(self.input_proj, x):
             f = proj(fmap)
@@ -192,6 +202,12 @@ class _HeadBase(nn.Module):
     sparse_query_selection = True
 
     def _rank_tokens(self, feats, valid):
+        if feats.is_cuda and feats.dtype in (torch.float32, torch.bfloat16) and self.fused_input_proj:
+            cache = self.__dict__.setdefault("_anchor_cache", {})
+            key = ("valid_u8", valid.data_ptr())
+            if key not in cache:
+                cache[key] = valid.view(-1).to(torch.uint8).contiguous()
+            return ops.rank_tokens(feats, cache[key], self.enc_output[0], self.enc_output[1], self.enc_score_head)
         with torch.no_grad():
             features = self.enc_output(valid * feats)
             return self.enc_score_head(features).max(-1).values              # [B, Lv]

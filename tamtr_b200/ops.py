@@ -4,6 +4,8 @@
 ultralytics/nn/modules/utils.py:42 multi_scale_deformable_attn_pytorch(value, value_spatial_shapes,
 sampling_locations, attention_weights) so that tamtr_b200.enable() can rebind that name to it.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -432,3 +434,174 @@ def select_rows(x, flat_idx, hub):
     if not x.requires_grad:
         return x.reshape(-1, x.shape[-1])[flat_idx]
     return _SelectRowsFn.apply(x, flat_idx, hub)
+
+
+# ------------------------------------------------------------------------------------ token-major input projection
+def _col_reduce2(a, b, tok0, ntok):
+    """-> (sum_rows a, sum_rows a*b) over tokens [tok0, tok0+ntok) of every image, float64 [d] each."""
+    B, Lv, d = a.shape
+    n_cta = _lib.lib().tamtr_col_reduce2_ctas(B, ntok)
+    partial = torch.empty(n_cta, 2, d, dtype=torch.float32, device=a.device)
+    with _with_device(a):
+        rc = _lib.lib().tamtr_col_reduce2(a.data_ptr(), b.data_ptr(), partial.data_ptr(), _lib.dtype_code(a), B, Lv, d,
+                                          tok0, ntok, _lib.stream_ptr(a.device))
+    _lib.check(rc, "col_reduce2")
+    s = partial.double().sum(0)
+    return s[0], s[1]
+
+
+def _affine_rows(a, b, A, Bc, Cc, starts):
+    B, Lv, d = a.shape
+    out = torch.empty_like(a)
+    st = (ctypes.c_int32 * len(starts))(*starts)
+    with _with_device(a):
+        rc = _lib.lib().tamtr_affine_rows(out.data_ptr(), a.data_ptr(), b.data_ptr() if b is not None else None,
+                                          A.data_ptr(), Bc.data_ptr() if Bc is not None else None, Cc.data_ptr(),
+                                          _lib.dtype_code(a), B, Lv, d, len(starts), st, _lib.stream_ptr(a.device))
+    _lib.check(rc, "affine_rows")
+    return out
+
+
+class _InputProjFn(torch.autograd.Function):
+    """input_proj of the heads (head.py:1202-1218: per level Conv2d(1x1, bias=False) + BatchNorm2d, then
+    flatten(2).permute(0,2,1) and cat) computed directly in token-major layout:
+
+      pre[b, s_l:e_l, :] = x_l[b]^T W_l^T            one batched GEMM per level, written in place into its slice
+      train: mu, var = column statistics of the slice (tamtr_col_reduce2), running stats updated like nn.BatchNorm2d
+      feats = pre * (gamma*rstd) + (beta - mu*gamma*rstd)                     (tamtr_affine_rows)
+
+    backward:  d_beta = sum G, d_gamma = rstd * (sum G*pre - mu * sum G)       (tamtr_col_reduce2 on (G, pre))
+               d_pre  = gamma*rstd * (G - d_beta/M - xhat*d_gamma/M)  as  A*G + Bc*pre + Cc  (tamtr_affine_rows)
+               dW_l = sum_b x_l[b] d_pre_l[b],  dx_l[b] = W_l^T d_pre_l[b]^T   (library GEMMs)
+    """
+
+    @staticmethod
+    def forward(ctx, bns, training, n_levels, *t):
+        xs, ws, gammas, betas = t[:n_levels], t[n_levels:2 * n_levels], t[2 * n_levels:3 * n_levels], t[3 * n_levels:]
+        lp = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else xs[0].dtype
+        if lp not in (torch.float32, torch.bfloat16):
+            lp = torch.float32
+        B, d = xs[0].shape[0], ws[0].shape[0]
+        hw = [x.shape[2] * x.shape[3] for x in xs]
+        starts = [sum(hw[:i]) for i in range(n_levels)]
+        Lv = sum(hw)
+        dev = xs[0].device
+        pre = torch.empty(B, Lv, d, dtype=lp, device=dev)
+        xl, wl = [], []
+        for l in range(n_levels):
+            a = xs[l].to(lp).flatten(2)                                   # [B, C, HW]  (NCHW, no copy when already lp)
+            w = ws[l].reshape(d, -1).to(lp)                               # [d, C]
+            torch.bmm(a.transpose(1, 2), w.t().unsqueeze(0).expand(B, -1, -1), out=pre[:, starts[l]:starts[l] + hw[l]])
+            xl.append(a)
+            wl.append(w)
+        scale = torch.empty(n_levels, d, dtype=torch.float32, device=dev)
+        shift = torch.empty_like(scale)
+        mus, rstds = [], []
+        for l, bn in enumerate(bns):
+            M = B * hw[l]
+            if training or bn.running_mean is None:
+                s1, s2 = _col_reduce2(pre, pre, starts[l], hw[l])
+                mu = s1 / M
+                var = (s2 / M - mu * mu).clamp_min(0.0)
+                if training and bn.running_mean is not None:
+                    with torch.no_grad():
+                        mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+                        bn.running_mean.mul_(1 - mom).add_(mu.to(bn.running_mean.dtype), alpha=mom)
+                        bn.running_var.mul_(1 - mom).add_((var * (M / max(M - 1, 1))).to(bn.running_var.dtype), alpha=mom)
+                        bn.num_batches_tracked += 1
+            else:
+                mu, var = bn.running_mean.double(), bn.running_var.double()
+            rstd = torch.rsqrt(var + bn.eps)
+            sc = gammas[l].double() * rstd
+            scale[l] = sc.float()
+            shift[l] = (betas[l].double() - mu * sc).float()
+            mus.append(mu)
+            rstds.append(rstd)
+        feats = _affine_rows(pre, None, scale, None, shift, starts)
+        ctx.save_for_backward(pre, *xl, *wl, *gammas, *mus, *rstds)
+        ctx.meta = (n_levels, hw, starts, training, [x.dtype for x in xs], [w.dtype for w in ws],
+                    [g.dtype for g in gammas], [x.shape for x in xs], [w.shape for w in ws])
+        return feats
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, G):
+        n, hw, starts, training, xdt, wdt, gdt, xshape, wshape = ctx.meta
+        sv = ctx.saved_tensors
+        pre = sv[0]
+        xl, wl, gammas = sv[1:1 + n], sv[1 + n:1 + 2 * n], sv[1 + 2 * n:1 + 3 * n]
+        mus, rstds = sv[1 + 3 * n:1 + 4 * n], sv[1 + 4 * n:1 + 5 * n]
+        G = G.contiguous().to(pre.dtype)
+        B, Lv, d = pre.shape
+        dev = pre.device
+        A = torch.empty(n, d, dtype=torch.float32, device=dev)
+        Bc = torch.zeros_like(A)
+        Cc = torch.zeros_like(A)
+        d_gamma, d_beta = [], []
+        for l in range(n):
+            M = B * hw[l]
+            sg, sgp = _col_reduce2(G, pre, starts[l], hw[l])
+            dgam = rstds[l] * (sgp - mus[l] * sg)
+            a = gammas[l].double() * rstds[l]
+            A[l] = a.float()
+            if training:
+                Bc[l] = (-a * rstds[l] * dgam / M).float()
+                Cc[l] = (-a * sg / M + a * rstds[l] * mus[l] * dgam / M).float()
+            d_gamma.append(dgam.to(gdt[l]))
+            d_beta.append(sg.to(gdt[l]))
+        dpre = _affine_rows(G, pre if training else None, A, Bc if training else None, Cc, starts)
+        d_x, d_w = [], []
+        for l in range(n):
+            dp = dpre[:, starts[l]:starts[l] + hw[l]]                                    # [B, HW, d]
+            if ctx.needs_input_grad[3 + n + l]:
+                d_w.append(torch.bmm(xl[l], dp).float().sum(0).t().reshape(wshape[l]).to(wdt[l]))
+            else:
+                d_w.append(None)
+            if ctx.needs_input_grad[3 + l]:
+                gx = torch.bmm(wl[l].t().unsqueeze(0).expand(B, -1, -1), dp.transpose(1, 2))   # [B, C, HW]
+                d_x.append(gx.reshape(xshape[l]).to(xdt[l]))
+            else:
+                d_x.append(None)
+        return (None, None, None, *d_x, *d_w, *d_gamma, *d_beta)
+
+
+def input_proj_tokens(xs, projs, training):
+    """xs: list of NCHW maps; projs: ModuleList of Sequential(Conv2d(1x1, bias=False), BatchNorm2d).
+    Returns feats [B, sum(H_l*W_l), d] and the level shapes (head.py:1202-1218)."""
+    _lib.require_cuda(*xs)
+    convs, bns = [p[0] for p in projs], [p[1] for p in projs]
+    n = len(xs)
+    feats = _InputProjFn.apply(bns, training, n, *xs, *[c.weight for c in convs], *[b.weight for b in bns],
+                               *[b.bias for b in bns])
+    return feats, [[x.shape[2], x.shape[3]] for x in xs]
+
+
+def rank_tokens(feats, valid_u8, enc_linear, enc_norm, score_linear):
+    """Query-selection ranking (head.py:1229-1237) without autograd: max over classes of
+    enc_score_head(LayerNorm(enc_output.0(valid * feats))) for every token -> [B, Lv] fp32."""
+    B, Lv, d = feats.shape
+    with torch.no_grad():
+        lp = feats.dtype
+        f2 = feats.reshape(B * Lv, d)
+        Wp = score_linear.weight.float() * enc_norm.weight.float()                 # [nc, d]
+        if lp == torch.float32:
+            E = f2 @ enc_linear.weight.float().t()
+            raw = E @ Wp.t()
+        else:
+            with torch.autocast("cuda", enabled=False):
+                E = f2 @ enc_linear.weight.to(lp).t()
+                raw = torch.mm(E, Wp.to(lp).t(), out_dtype=torch.float32)
+        eb = enc_linear.bias.float().contiguous()
+        bw = (Wp @ eb).contiguous()
+        sw = Wp.sum(1).contiguous()
+        ck = (score_linear.weight.float() @ enc_norm.bias.float() + score_linear.bias.float()).contiguous()
+        nc = Wp.shape[0]
+        out = torch.empty(B, Lv, dtype=torch.float32, device=feats.device)
+        raw = raw.contiguous()
+        with _with_device(feats):
+            rc = _lib.lib().tamtr_rank_tokens(E.data_ptr(), raw.data_ptr(), eb.data_ptr(), valid_u8.data_ptr(),
+                                              bw.data_ptr(), sw.data_ptr(), ck.data_ptr(), out.data_ptr(),
+                                              _lib.dtype_code(E), B, Lv, d, nc, float(enc_norm.eps),
+                                              _lib.stream_ptr(feats.device))
+        _lib.check(rc, "rank_tokens")
+    return out
