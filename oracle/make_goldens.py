@@ -237,16 +237,29 @@ def gen_heads(ns):
         return ((a.double() - b.double()).norm() / b.double().norm()).item()
 
     # --- RT-DETR head, eval, S-base
+    def selection_margin(m, xs, nq):
+        """gap between the last selected and the first rejected token score (head.py:1237): the goldens must not sit on
+        a near-tie, or two correct implementations legitimately select different queries."""
+        with torch.no_grad():
+            feats, shapes = m._get_encoder_input(xs)
+            anchors, valid = m._generate_anchors(shapes, dtype=feats.dtype, device=feats.device)
+            sc = m.enc_score_head(m.enc_output(valid * feats)).max(-1).values.sort(1, descending=True).values
+        return (sc[:, nq - 1] - sc[:, nq]).min().item()
+
     torch.manual_seed(0)
     m = ns.RTDETRDecoder(nc=10, ch=(256, 256, 256)).eval()
     manifest = seeding.seeded_fill(m, 71)
-    xs = [seeding.seeded_tensor(72, f"x{i}", (2, 256, s, s)) for i, s in enumerate((80, 40, 20))]
+    for in_seed in range(72, 200):
+        xs = [seeding.seeded_tensor(in_seed, f"x{i}", (2, 256, s, s)) for i, s in enumerate((80, 40, 20))]
+        if selection_margin(m, xs, 300) > 2e-3:
+            break
+    rt_seed = in_seed
     with torch.no_grad():
         y32, (db32, ds32, eb32, es32, _) = m(xs)
         m.double()
         y, (db, ds, eb, es, _) = m([x.double() for x in xs])
     out["cases"]["rtdetr_eval_sbase"] = dict(
-        manifest=manifest, y=y.float(), dec_bboxes=db.float(), dec_scores=ds.float(), enc_bboxes=eb.float(),
+        manifest=manifest, input_seed=rt_seed, y=y.float(), dec_bboxes=db.float(), dec_scores=ds.float(), enc_bboxes=eb.float(),
         enc_scores=es.float(),
         ref32_err=dict(y=rel(y32, y), dec_bboxes=rel(db32, db), dec_scores=rel(ds32, ds), enc_bboxes=rel(eb32, eb),
                        enc_scores=rel(es32, es)))
@@ -275,10 +288,17 @@ def gen_heads(ns):
             torch.manual_seed(0)
             m = ns.ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3)
             manifest = seeding.seeded_fill(m, 73)
-            xs = [seeding.seeded_smooth_map(74, f"x{i}", (B, c, s, s)) for i, (c, s) in enumerate(zip((128, 256, 512), sizes))]
+            for in_seed in range(74, 200):
+                xs = [seeding.seeded_smooth_map(in_seed, f"x{i}", (B, c, s, s)) for i, (c, s) in enumerate(zip((128, 256, 512), sizes))]
+                m.train()
+                ok_train = selection_margin(m, xs, 100) > 2e-3      # (batch statistics differ between train and eval)
+                m.eval()
+                if ok_train and selection_margin(m, xs, 100) > 2e-3:
+                    break
+            m.train()
             text = F_normalize(seeding.seeded_tensor(74, "text", (B, 10, 512)))
             batch = _synthetic_targets(75, B, 5, 20)
-            case = dict(manifest=manifest, sizes=sizes, B=B, batch=batch)
+            case = dict(manifest=manifest, sizes=sizes, B=B, batch=batch, input_seed=in_seed)
             runs = {}
             sd0 = {k: v.clone() for k, v in m.state_dict().items()}
             for prec in ("f32", "f64"):

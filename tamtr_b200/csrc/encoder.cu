@@ -88,29 +88,34 @@ struct RowLevels {
 };
 
 // out[b,t,c] = A[l][c] * a[b,t,c] + Bc[l][c] * b[b,t,c] + Cc[l][c]    (l = level of token t; b may be null)
+// blockDim.x = d / N column packs (each thread keeps its per-level coefficients in registers while it walks down
+// the rows of one level), blockDim.y row lanes; blockIdx.y = level, blockIdx.x strides over that level's rows.
 template <typename T, bool HAS_B>
-__global__ void __launch_bounds__(kEncThreads)
-affine_rows_kernel(T *__restrict__ out, const T *__restrict__ a, const T *__restrict__ b, const float *__restrict__ A,
-                   const float *__restrict__ Bc, const float *__restrict__ Cc, const RowLevels lv, int Lv, int d,
-                   size_t n_packs) {
+__global__ void affine_rows_kernel(T *__restrict__ out, const T *__restrict__ a, const T *__restrict__ b,
+                                   const float *__restrict__ A, const float *__restrict__ Bc,
+                                   const float *__restrict__ Cc, const RowLevels lv, int B, int Lv, int d) {
     constexpr int N = Pack<T>::N;
-    const int packs_per_row = d / N;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_packs; p += (size_t)gridDim.x * blockDim.x) {
-        const size_t row = p / packs_per_row;
-        const int col = (int)(p % packs_per_row) * N;
-        const int t = (int)(row % Lv);
-        int l = 0;
+    const int l = blockIdx.y;
+    const int col = threadIdx.x * N;
+    const int tok0 = lv.start[l], ntok = lv.start[l + 1] - tok0;
+    float ca[N], cb[N], cc[N];
 #pragma unroll
-        for (int i = 1; i < kMaxLevels; ++i) l += (i < lv.n && t >= lv.start[i]) ? 1 : 0;
-        const size_t off = row * d + col;
+    for (int i = 0; i < N; ++i) {
+        ca[i] = __ldg(A + (size_t)l * d + col + i);
+        cc[i] = __ldg(Cc + (size_t)l * d + col + i);
+        cb[i] = HAS_B ? __ldg(Bc + (size_t)l * d + col + i) : 0.f;
+    }
+    const int rows = B * ntok;
+    for (int r = blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += gridDim.x * blockDim.y) {
+        const int img = r / ntok, t = tok0 + r - img * ntok;
+        const size_t off = ((size_t)img * Lv + t) * d + col;
         float fa[N], fb[N], fo[N];
         Pack<T>::load(a + off, fa);
         if (HAS_B) Pack<T>::load(b + off, fb);
-        const float *pa = A + (size_t)l * d + col, *pb = Bc + (size_t)l * d + col, *pc = Cc + (size_t)l * d + col;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            float v = fmaf(__ldg(pa + i), fa[i], __ldg(pc + i));
-            if (HAS_B) v = fmaf(__ldg(pb + i), fb[i], v);
+            float v = fmaf(ca[i], fa[i], cc[i]);
+            if (HAS_B) v = fmaf(cb[i], fb[i], v);
             fo[i] = v;
         }
         Pack<T>::store(out + off, fo);
@@ -122,57 +127,69 @@ affine_rows_kernel(T *__restrict__ out, const T *__restrict__ a, const T *__rest
 //   raw = E @ (score_w * ln_w)^T  (library GEMM on the un-biased rows),  bw = enc_bias . W', sw = sum_c W'[k][c],
 //   ck = ln_b . score_w[k] + score_b[k].  Invalid tokens (anchor too close to the border, head.py:1195-1199) have the
 //   constant row enc_bias: raw is ignored for them (raw_invalid = 0).
-template <typename T>
+template <typename T, int PP>   // PP = 16-byte packs per lane = ceil(d / (32 * N))
 __global__ void __launch_bounds__(kEncThreads)
 rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const float *__restrict__ enc_bias,
                    const uint8_t *__restrict__ valid, const float *__restrict__ bw, const float *__restrict__ sw,
                    const float *__restrict__ ck, float *__restrict__ out, long rows, int Lv, int d, int nc, float eps) {
     constexpr int N = Pack<T>::N;
+    constexpr int TOK = 4;            // tokens per warp: 4 * PP independent 16-byte loads in flight per lane
     const int lane = threadIdx.x & 31;
-    const long row = (long)blockIdx.x * (kEncThreads / 32) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const bool ok = valid[row % Lv] != 0;
-    float s = 0.f, ss = 0.f;
-    float v[4][N];                     // the row stays in registers: d <= 4 * 32 * N
+    const long row0 = ((long)blockIdx.x * (kEncThreads / 32) + (threadIdx.x >> 5)) * TOK;
+    if (row0 >= rows) return;
+    float v[TOK][PP][N];
+    bool ok[TOK];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
+    for (int t = 0; t < TOK; ++t) {
+        const long row = row0 + t;
+        ok[t] = row < rows && valid[row % Lv] != 0;
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+            const int c = (p * 32 + lane) * N;
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[t][p][i] = 0.f;
+            if (ok[t] && c < d) Pack<T>::load(E + (size_t)row * d + c, v[t][p]);
+        }
+    }
+    float eb[PP][N];
+#pragma unroll
+    for (int p = 0; p < PP; ++p) {
         const int c = (p * 32 + lane) * N;
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[p][i] = 0.f;
-        if (c < d) {
-            float e[N];
+        for (int i = 0; i < N; ++i) eb[p][i] = c < d ? __ldg(enc_bias + c + i) : 0.f;
+    }
 #pragma unroll
-            for (int i = 0; i < N; ++i) e[i] = 0.f;
-            if (ok) Pack<T>::load(E + (size_t)row * d + c, e);
+    for (int t = 0; t < TOK; ++t) {
+        const long row = row0 + t;
+        if (row >= rows) break;      // warp-uniform
+        float s = 0.f, ss = 0.f;
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                v[p][i] = e[i] + __ldg(enc_bias + c + i);
-                s += v[p][i];
+        for (int p = 0; p < PP; ++p)
+#pragma unroll
+            for (int i = 0; i < N; ++i) { v[t][p][i] += eb[p][i]; s += v[t][p][i]; }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+        const float mean = s / (float)d;
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+            const int c = (p * 32 + lane) * N;
+            if (c < d) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) { const float dlt = v[t][p][i] - mean; ss = fmaf(dlt, dlt, ss); }
             }
         }
-    }
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-    const float mean = s / (float)d;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const int c = (p * 32 + lane) * N;
-        if (c < d) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) { const float dlt = v[p][i] - mean; ss = fmaf(dlt, dlt, ss); }
+        for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+        const float rstd = rsqrtf(ss / (float)d + eps);
+        float best = -INFINITY;
+        for (int k = lane; k < nc; k += 32) {
+            const float r = ok[t] ? __ldg(raw + (size_t)row * nc + k) : 0.f;
+            best = fmaxf(best, rstd * (r + __ldg(bw + k) - mean * __ldg(sw + k)) + __ldg(ck + k));
         }
-    }
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
-    const float rstd = rsqrtf(ss / (float)d + eps);
-    float best = -INFINITY;
-    for (int k = lane; k < nc; k += 32) {
-        const float r = ok ? __ldg(raw + (size_t)row * nc + k) : 0.f;
-        best = fmaxf(best, rstd * (r + __ldg(bw + k) - mean * __ldg(sw + k)) + __ldg(ck + k));
+        for (int m = 16; m > 0; m >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, m));
+        if (lane == 0) out[row] = best;
     }
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, m));
-    if (lane == 0) out[row] = best;
 }
 
 static int enc_check(int dtype, int d) {
@@ -232,11 +249,12 @@ extern "C" int tamtr_affine_rows(void *out, const void *a, const void *b, const 
     lv.n = L;
     for (int i = 0; i <= kMaxLevels; ++i) lv.start[i] = i < L ? level_starts_host[i] : Lv;
     const int n = dtype == TAMTR_F32 ? 4 : 8;
-    const size_t n_packs = (size_t)B * Lv * d / n;
-    size_t blocks = (n_packs + kEncThreads - 1) / kEncThreads;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    const int bx = d / n;
+    int by = kEncThreads / bx;
+    if (by < 1) by = 1;
+    const dim3 block(bx, by), grid(148 * 4, L);
     cudaStream_t st = (cudaStream_t)stream;
-#define AFF(T, HB) affine_rows_kernel<T, HB><<<(unsigned)blocks, kEncThreads, 0, st>>>((T *)out, (const T *)a, (const T *)b, A, Bc, Cc, lv, Lv, d, n_packs)
+#define AFF(T, HB) affine_rows_kernel<T, HB><<<grid, block, 0, st>>>((T *)out, (const T *)a, (const T *)b, A, Bc, Cc, lv, B, Lv, d)
     if (dtype == TAMTR_F32) { if (b) AFF(float, true); else AFF(float, false); }
     else { if (b) AFF(__nv_bfloat16, true); else AFF(__nv_bfloat16, false); }
 #undef AFF
@@ -255,14 +273,14 @@ extern "C" int tamtr_rank_tokens(const void *E, const float *raw, const float *e
     const int n = dtype == TAMTR_F32 ? 4 : 8;
     TAMTR_CHECK_ARG(d <= 4 * 32 * n, TAMTR_E_UNSUPPORTED, "rank_tokens: d = %d too large", d);
     const long rows = (long)B * Lv;
-    const unsigned blocks = (unsigned)((rows + kEncThreads / 32 - 1) / (kEncThreads / 32));
+    const long per_cta = (kEncThreads / 32) * 4;
+    const unsigned blocks = (unsigned)((rows + per_cta - 1) / per_cta);
+    const int pp = (d + 32 * n - 1) / (32 * n);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == TAMTR_F32)
-        rank_tokens_kernel<float><<<blocks, kEncThreads, 0, st>>>((const float *)E, raw, enc_bias, valid, bw, sw, ck, out,
-                                                                  rows, Lv, d, nc, eps);
-    else
-        rank_tokens_kernel<__nv_bfloat16><<<blocks, kEncThreads, 0, st>>>((const __nv_bfloat16 *)E, raw, enc_bias, valid,
-                                                                          bw, sw, ck, out, rows, Lv, d, nc, eps);
+#define RANK(T, PPV) rank_tokens_kernel<T, PPV><<<blocks, kEncThreads, 0, st>>>((const T *)E, raw, enc_bias, valid, bw, sw, ck, out, rows, Lv, d, nc, eps)
+    if (dtype == TAMTR_F32) { if (pp <= 1) RANK(float, 1); else if (pp <= 2) RANK(float, 2); else RANK(float, 4); }
+    else { if (pp <= 1) RANK(__nv_bfloat16, 1); else if (pp <= 2) RANK(__nv_bfloat16, 2); else RANK(__nv_bfloat16, 4); }
+#undef RANK
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;

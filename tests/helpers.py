@@ -45,3 +45,17 @@ def filled_state_dict(module, seed, manifest=None):
         assert got == ref, ("state_dict keys/shapes differ from the reference",
                             set(got.items()) ^ set(ref.items()))
     return {k: v.detach().clone() for k, v in module.state_dict().items()}
+
+
+def align_queries(ours_boxes, ours_scores, gold_boxes, gold_scores):
+    """Query order comes from a top-k over thousands of scores: two implementations that agree to 1e-6 can still swap
+    near-tied neighbours.  Match rows through their encoder outputs (boxes alone are not distinct: many saturate at 1.0
+    with the seeded weights).  Returns (index of the golden row for each of our rows, matched mask)."""
+    a = torch.cat([ours_boxes, ours_scores], -1).detach().double().cpu()
+    b = torch.cat([gold_boxes, gold_scores], -1).detach().double().cpu()
+    dist, idx = torch.cdist(a, b).min(-1)                                          # [B, nq]
+    return idx, dist < 1e-3
+
+
+def gather_rows(t, idx):
+    return torch.gather(t, 1, idx.unsqueeze(-1).expand(-1, -1, t.shape[-1]))
