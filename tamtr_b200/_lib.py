@@ -24,6 +24,7 @@ _SIGNATURES = {
     "tamtr_abi_version": (ctypes.c_int, []),
     "tamtr_last_error": (ctypes.c_char_p, []),
     "tamtr_launch_count": (ctypes.c_ulonglong, []),
+    "tamtr_memset_zero": (ctypes.c_int, [_vp, ctypes.c_ulonglong, _vp]),
     "tamtr_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "tamtr_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_ulonglong)]),
@@ -39,7 +40,7 @@ _SIGNATURES = {
     "tamtr_col_reduce2_ctas": (ctypes.c_int, [_i, _i]),
     "tamtr_col_reduce2": (ctypes.c_int, [_vp, _vp, _fp] + [_i] * 6 + [_vp]),
     "tamtr_affine_rows": (ctypes.c_int, [_vp, _vp, _vp, _fp, _fp, _fp] + [_i] * 5 + [_vp, _vp]),
-    "tamtr_rank_tokens": (ctypes.c_int, [_vp, _fp, _fp, _vp, _fp, _fp, _fp, _fp] + [_i] * 5 + [ctypes.c_float, _vp]),
+    "tamtr_rank_tokens": (ctypes.c_int, [_vp, _fp, _fp, _vp, _fp, _fp, _fp, _fp] + [_i] * 6 + [ctypes.c_float, _vp]),
     "tamtr_max_sigmoid_tc_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }
@@ -78,6 +79,15 @@ def lib():
 
 def launch_count():
     return int(lib().tamtr_launch_count())
+
+
+def zeros_like_fast(t):
+    """torch.zeros_like through a memset node instead of a fill kernel."""
+    out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+    with torch.cuda.device(t.device):
+        check(lib().tamtr_memset_zero(out.data_ptr(), out.numel() * out.element_size(), stream_ptr(t.device)),
+              "memset_zero")
+    return out
 
 
 def profile_enable(on=True):

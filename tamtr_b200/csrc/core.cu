@@ -79,3 +79,10 @@ extern "C" int tamtr_profile_read(int kernel_id, double *total_ms, unsigned long
 extern "C" const char *tamtr_kernel_name(int kernel_id) {
     return (kernel_id >= 0 && kernel_id < tamtr::K_COUNT) ? tamtr::g_names[kernel_id] : "";
 }
+
+extern "C" int tamtr_memset_zero(void *ptr, unsigned long long bytes, void *stream) {
+    TAMTR_CHECK_ARG(ptr != nullptr, TAMTR_E_BADARG, "memset_zero: null pointer");
+    TAMTR_CUDA_OK(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
+    tamtr::count_launch();
+    return 0;
+}

@@ -131,7 +131,8 @@ template <typename T, int PP>   // PP = 16-byte packs per lane = ceil(d / (32 * 
 __global__ void __launch_bounds__(kEncThreads)
 rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const float *__restrict__ enc_bias,
                    const uint8_t *__restrict__ valid, const float *__restrict__ bw, const float *__restrict__ sw,
-                   const float *__restrict__ ck, float *__restrict__ out, long rows, int Lv, int d, int nc, float eps) {
+                   const float *__restrict__ ck, float *__restrict__ out, long rows, int Lv, int d, int nc, int raw_stride,
+                   float eps) {
     constexpr int N = Pack<T>::N;
     constexpr int TOK = 4;            // tokens per warp: 4 * PP independent 16-byte loads in flight per lane
     const int lane = threadIdx.x & 31;
@@ -158,37 +159,68 @@ rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const
 #pragma unroll
         for (int i = 0; i < N; ++i) eb[p][i] = c < d ? __ldg(enc_bias + c + i) : 0.f;
     }
+    // the TOK tokens are reduced in lockstep so that their shuffle / load chains overlap (ILP across tokens)
+    float s[TOK], ss[TOK], best[TOK];
 #pragma unroll
     for (int t = 0; t < TOK; ++t) {
-        const long row = row0 + t;
-        if (row >= rows) break;      // warp-uniform
-        float s = 0.f, ss = 0.f;
+        s[t] = 0.f;
 #pragma unroll
         for (int p = 0; p < PP; ++p)
 #pragma unroll
-            for (int i = 0; i < N; ++i) { v[t][p][i] += eb[p][i]; s += v[t][p][i]; }
+            for (int i = 0; i < N; ++i) { v[t][p][i] += eb[p][i]; s[t] += v[t][p][i]; }
+    }
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-        const float mean = s / (float)d;
+    for (int m = 16; m > 0; m >>= 1)
+#pragma unroll
+        for (int t = 0; t < TOK; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], m);
+#pragma unroll
+    for (int t = 0; t < TOK; ++t) {
+        const float mean = s[t] / (float)d;
+        s[t] = mean;
+        ss[t] = 0.f;
 #pragma unroll
         for (int p = 0; p < PP; ++p) {
             const int c = (p * 32 + lane) * N;
             if (c < d) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) { const float dlt = v[t][p][i] - mean; ss = fmaf(dlt, dlt, ss); }
+                for (int i = 0; i < N; ++i) { const float dlt = v[t][p][i] - mean; ss[t] = fmaf(dlt, dlt, ss[t]); }
             }
         }
+    }
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
-        const float rstd = rsqrtf(ss / (float)d + eps);
-        float best = -INFINITY;
-        for (int k = lane; k < nc; k += 32) {
-            const float r = ok[t] ? __ldg(raw + (size_t)row * nc + k) : 0.f;
-            best = fmaxf(best, rstd * (r + __ldg(bw + k) - mean * __ldg(sw + k)) + __ldg(ck + k));
+    for (int m = 16; m > 0; m >>= 1)
+#pragma unroll
+        for (int t = 0; t < TOK; ++t) ss[t] += __shfl_xor_sync(0xffffffffu, ss[t], m);
+    const float cbw = lane < nc ? __ldg(bw + lane) : 0.f, csw = lane < nc ? __ldg(sw + lane) : 0.f,
+                cck = lane < nc ? __ldg(ck + lane) : 0.f;
+#pragma unroll
+    for (int t = 0; t < TOK; ++t) {
+        const long row = row0 + t;
+        const float rstd = rsqrtf(ss[t] / (float)d + eps);
+        best[t] = -INFINITY;
+        if (row < rows) {
+            if (nc <= 32) {
+                if (lane < nc) {
+                    const float r = ok[t] ? __ldg(raw + (size_t)row * raw_stride + lane) : 0.f;
+                    best[t] = rstd * (r + cbw - s[t] * csw) + cck;
+                }
+            } else {
+                for (int k = lane; k < nc; k += 32) {
+                    const float r = ok[t] ? __ldg(raw + (size_t)row * raw_stride + k) : 0.f;
+                    best[t] = fmaxf(best[t], rstd * (r + __ldg(bw + k) - s[t] * __ldg(sw + k)) + __ldg(ck + k));
+                }
+            }
         }
+    }
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, m));
-        if (lane == 0) out[row] = best;
+    for (int m = 16; m > 0; m >>= 1)
+#pragma unroll
+        for (int t = 0; t < TOK; ++t) best[t] = fmaxf(best[t], __shfl_xor_sync(0xffffffffu, best[t], m));
+    if (lane < TOK && row0 + lane < rows) {
+        float o = best[0];
+#pragma unroll
+        for (int t = 1; t < TOK; ++t) o = lane == t ? best[t] : o;
+        out[row0 + lane] = o;
     }
 }
 
@@ -265,9 +297,9 @@ extern "C" int tamtr_affine_rows(void *out, const void *a, const void *b, const 
 
 extern "C" int tamtr_rank_tokens(const void *E, const float *raw, const float *enc_bias, const uint8_t *valid,
                                  const float *bw, const float *sw, const float *ck, float *out, int dtype, int B, int Lv,
-                                 int d, int nc, float eps, void *stream) {
+                                 int d, int nc, int raw_stride, float eps, void *stream) {
     TAMTR_CHECK_ARG(E && raw && enc_bias && valid && bw && sw && ck && out, TAMTR_E_BADARG, "rank_tokens: null pointer");
-    TAMTR_CHECK_ARG(B > 0 && Lv > 0 && nc > 0, TAMTR_E_BADARG, "rank_tokens: bad sizes");
+    TAMTR_CHECK_ARG(B > 0 && Lv > 0 && nc > 0 && raw_stride >= nc, TAMTR_E_BADARG, "rank_tokens: bad sizes");
     const int rc = enc_check(dtype, d);
     if (rc) return rc;
     const int n = dtype == TAMTR_F32 ? 4 : 8;
@@ -277,7 +309,7 @@ extern "C" int tamtr_rank_tokens(const void *E, const float *raw, const float *e
     const unsigned blocks = (unsigned)((rows + per_cta - 1) / per_cta);
     const int pp = (d + 32 * n - 1) / (32 * n);
     cudaStream_t st = (cudaStream_t)stream;
-#define RANK(T, PPV) rank_tokens_kernel<T, PPV><<<blocks, kEncThreads, 0, st>>>((const T *)E, raw, enc_bias, valid, bw, sw, ck, out, rows, Lv, d, nc, eps)
+#define RANK(T, PPV) rank_tokens_kernel<T, PPV><<<blocks, kEncThreads, 0, st>>>((const T *)E, raw, enc_bias, valid, bw, sw, ck, out, rows, Lv, d, nc, raw_stride, eps)
     if (dtype == TAMTR_F32) { if (pp <= 1) RANK(float, 1); else if (pp <= 2) RANK(float, 2); else RANK(float, 4); }
     else { if (pp <= 1) RANK(__nv_bfloat16, 1); else if (pp <= 2) RANK(__nv_bfloat16, 2); else RANK(__nv_bfloat16, 4); }
 #undef RANK

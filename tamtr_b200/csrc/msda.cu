@@ -109,13 +109,29 @@ constexpr int kMaxTaps = 4 * kMaxSamples;
 // Phase 1 (shared by fwd and bwd): lane s < L*P does the index math of sample s ONCE and writes its four
 // (corner offset, weight) taps to this warp's smem slice as two 16-byte stores.
 // offset = element offset of the corner's Dh-vector inside image b's value slab, or -1 when out of bounds.
+struct SampleIn {   // one lane's sampling location + attention weight (lanes >= L*P hold zeros)
+    float x, y, a;
+};
+
+__device__ __forceinline__ SampleIn fetch_sample(const float *__restrict__ loc, const float *__restrict__ attn,
+                                                 size_t qh, int S, int lane) {
+    SampleIn in = {0.f, 0.f, 0.f};
+    if (lane < S) {
+        const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + qh * S + lane);
+        in.x = xy.x;
+        in.y = xy.y;
+        in.a = __ldg(attn + qh * S + lane);
+    }
+    return in;
+}
+
 template <int DH>
-__device__ __forceinline__ void stage_taps(int2 *taps, const float *__restrict__ loc, const float *__restrict__ attn,
-                                           const Levels &lv, size_t qh, int S, int h, int rowstride, int lane) {
+__device__ __forceinline__ void stage_taps(int2 *taps, const SampleIn in, const Levels &lv, int S, int h, int rowstride,
+                                           int lane) {
     if (lane < S) {
         const int l = lv.level_of[lane];
-        const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + qh * S + lane);
-        const float a = __ldg(attn + qh * S + lane);
+        const float2 xy = make_float2(in.x, in.y);
+        const float a = in.a;
         const int Hl = lv.h[l], Wl = lv.w[l];
         const Tap t = make_tap(xy.x, xy.y, Hl, Wl);
         const int o_nw = (lv.start[l] + t.y0 * Wl + t.x0) * rowstride + h * DH;
@@ -164,48 +180,57 @@ msda_fwd_kernel(const T *__restrict__ value, const float *__restrict__ loc, cons
     __shared__ int2 s_taps[kWarpsPerCta][kMaxTaps];
 
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qh = blockIdx.x * kWarpsPerCta + wic;
+    int qh = blockIdx.x * kWarpsPerCta + wic;
     if (qh >= total) return;  // warp-uniform; no block-wide barrier below
     const int S = NS > 0 ? NS : lv.n * lv.P;
-    const int h = qh % H;
-    const int b = qh / (Lq * H);
-    int2 *taps = s_taps[wic];
-    stage_taps<DH>(taps, loc, attn, lv, (size_t)qh, S, h, tok_stride, lane);
-
+    const int stride = gridDim.x * kWarpsPerCta;   // persistent warps: item qh, qh + stride, ...
     const int cs = lane / LPC, cg = lane % LPC;
-    const T *vbase = value + (size_t)b * Lv * tok_stride + cg * VEC;
     const int npairs = 4 * S;
-    float acc[VEC];
-#pragma unroll
-    for (int c = 0; c < VEC; ++c) acc[c] = 0.0f;
-
+    int2 *taps = s_taps[wic];
     constexpr int ITERS = NS > 0 ? (4 * NS + CPL - 1) / CPL : 0;
     constexpr int CHUNK = NS > 0 ? (ITERS < 12 ? ITERS : 12) : 4;
-    for (int base = 0; base < npairs; base += CPL * CHUNK) {
-        uint4 v[CHUNK];
-        float w[CHUNK];
+
+    SampleIn cur = fetch_sample(loc, attn, (size_t)qh, S, lane);
+    for (; qh < total; qh += stride) {
+        // software pipeline: the next item's locations/weights are requested before this item's gather is issued,
+        // so a warp pays ONE exposed DRAM round trip per item instead of two dependent ones
+        SampleIn nxt = {0.f, 0.f, 0.f};
+        if (qh + stride < total) nxt = fetch_sample(loc, attn, (size_t)(qh + stride), S, lane);
+        const int h = qh % H;
+        const int b = qh / (Lq * H);
+        stage_taps<DH>(taps, cur, lv, S, h, tok_stride, lane);
+        const T *vbase = value + (size_t)b * Lv * tok_stride + cg * VEC;
+        float acc[VEC];
 #pragma unroll
-        for (int i = 0; i < CHUNK; ++i) {  // issue every load of the chunk before the first use
-            const int pair = base + i * CPL + cs;
-            int2 t = make_int2(-1, 0);
-            if (pair < npairs) t = taps[pair];
-            w[i] = __int_as_float(t.y);
-            v[i] = gather16(vbase, t.x, (int)sizeof(T));
+        for (int c = 0; c < VEC; ++c) acc[c] = 0.0f;
+        for (int base = 0; base < npairs; base += CPL * CHUNK) {
+            uint4 v[CHUNK];
+            float w[CHUNK];
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) {  // issue every load of the chunk before the first use
+                const int pair = base + i * CPL + cs;
+                int2 t = make_int2(-1, 0);
+                if (pair < npairs) t = taps[pair];
+                w[i] = __int_as_float(t.y);
+                v[i] = gather16(vbase, t.x, (int)sizeof(T));
+            }
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) {
+                float f[VEC];
+                Vec<T>::unpack(v[i], f);
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w[i], f[c], acc[c]);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < CHUNK; ++i) {
-            float f[VEC];
-            Vec<T>::unpack(v[i], f);
+        for (int m = LPC; m < 32; m <<= 1) {
 #pragma unroll
-            for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w[i], f[c], acc[c]);
+            for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], m);
         }
+        if (cs == 0) Vec<T>::store(out + (size_t)qh * DH + cg * VEC, acc);
+        __syncwarp();   // taps are rewritten by the next item
+        cur = nxt;
     }
-#pragma unroll
-    for (int m = LPC; m < 32; m <<= 1) {
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], m);
-    }
-    if (cs == 0) Vec<T>::store(out + (size_t)qh * DH + cg * VEC, acc);
 }
 
 // ------------------------------------------------------------------------------------------- backward
@@ -224,76 +249,87 @@ msda_bwd_kernel(const T *__restrict__ grad_out, const T *__restrict__ value, con
     __shared__ float s_dots[kWarpsPerCta][kMaxTaps];
 
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qh = blockIdx.x * kWarpsPerCta + wic;
+    int qh = blockIdx.x * kWarpsPerCta + wic;
     if (qh >= total) return;
     const int S = NS > 0 ? NS : lv.n * lv.P;
-    const int h = qh % H;
-    const int b = qh / (Lq * H);
+    const int stride = gridDim.x * kWarpsPerCta;
     int2 *taps = s_taps[wic];
     float *dots = s_dots[wic];
-    stage_taps<DH>(taps, loc, attn, lv, (size_t)qh, S, h, tok_stride, lane);
-
     const int cs = lane / LPC, cg = lane % LPC;
-    const T *vbase = value + (size_t)b * Lv * tok_stride + cg * VEC;
-    T *gvbase = grad_value + (size_t)b * Lv * tok_stride + cg * VEC;   // same token stride as value
-    float g[VEC];
-    Vec<T>::load(grad_out + (size_t)qh * DH + cg * VEC, g);
     const int npairs = 4 * S;
-
     constexpr int ITERS = NS > 0 ? (4 * NS + CPL - 1) / CPL : 0;
     constexpr int CHUNK = NS > 0 ? (ITERS < 12 ? ITERS : 12) : 4;
-    for (int base = 0; base < npairs; base += CPL * CHUNK) {
-        uint4 v[CHUNK];
-        int off[CHUNK];
-        float w[CHUNK];
-#pragma unroll
-        for (int i = 0; i < CHUNK; ++i) {
-            const int pair = base + i * CPL + cs;
-            int2 t = make_int2(-1, 0);
-            if (pair < npairs) t = taps[pair];
-            off[i] = t.x;
-            w[i] = __int_as_float(t.y);
-            v[i] = gather16(vbase, t.x, (int)sizeof(T));
-        }
-#pragma unroll
-        for (int i = 0; i < CHUNK; ++i) {
-            if (off[i] >= 0) {
-                float gv[VEC];
-#pragma unroll
-                for (int c = 0; c < VEC; ++c) gv[c] = w[i] * g[c];
-                Vec<T>::red_add(gvbase + off[i], gv);
-            }
-            float f[VEC];
-            Vec<T>::unpack(v[i], f);
-            float d = 0.0f;
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) d = fmaf(g[c], f[c], d);
-#pragma unroll
-            for (int m = 1; m < LPC; m <<= 1) d += __shfl_xor_sync(0xffffffffu, d, m);
-            const int pair = base + i * CPL + cs;
-            if (cg == 0 && pair < npairs) dots[pair] = d;  // out-of-bounds corners: v == 0 -> d == 0
-        }
-    }
-    __syncwarp();
 
-    const int P = lv.P;
-    for (int s = lane; s < S; s += 32) {
-        const int l = s / P;
-        const int Hl = lv.h[l], Wl = lv.w[l];
-        const size_t si = (size_t)qh * S + s;
-        const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + si);
-        const float a = __ldg(attn + si);
-        const Tap t = make_tap(xy.x, xy.y, Hl, Wl);
-        const float4 d = *reinterpret_cast<const float4 *>(dots + 4 * s);
-        const float tx = t.ix - t.fx, ty = t.iy - t.fy;
-        const float ux = (t.fx + 1.0f) - t.ix, uy = (t.fy + 1.0f) - t.iy;
-        // grid_sampler_2d_backward: gix = -nw*(y1-iy) + ne*(y1-iy) - sw*(iy-y0) + se*(iy-y0), giy analogous
-        const float ga = (ux * uy) * d.x + (tx * uy) * d.y + (ux * ty) * d.z + (tx * ty) * d.w;
-        const float gix = a * (uy * (d.y - d.x) + ty * (d.w - d.z));
-        const float giy = a * (ux * (d.z - d.x) + tx * (d.w - d.y));
-        // d ix / d loc_x = (W_l / 2) * 2   (GridSampler.h:51 times d(2*loc-1)/d loc)
-        reinterpret_cast<float2 *>(grad_loc)[si] = make_float2(gix * (float)Wl, giy * (float)Hl);
-        grad_attn[si] = ga;
+    SampleIn cur = fetch_sample(loc, attn, (size_t)qh, S, lane);
+    uint4 graw = __ldg(reinterpret_cast<const uint4 *>(grad_out + (size_t)qh * DH + cg * VEC));
+    for (; qh < total; qh += stride) {
+        // software pipeline: next item's locations / weights / grad_out row are in flight during this item's gather
+        SampleIn nxt = {0.f, 0.f, 0.f};
+        uint4 gnext = make_uint4(0u, 0u, 0u, 0u);
+        if (qh + stride < total) {
+            nxt = fetch_sample(loc, attn, (size_t)(qh + stride), S, lane);
+            gnext = __ldg(reinterpret_cast<const uint4 *>(grad_out + (size_t)(qh + stride) * DH + cg * VEC));
+        }
+        const int h = qh % H;
+        const int b = qh / (Lq * H);
+        stage_taps<DH>(taps, cur, lv, S, h, tok_stride, lane);
+        const T *vbase = value + (size_t)b * Lv * tok_stride + cg * VEC;
+        T *gvbase = grad_value + (size_t)b * Lv * tok_stride + cg * VEC;   // same token stride as value
+        float g[VEC];
+        Vec<T>::unpack(graw, g);
+        for (int base = 0; base < npairs; base += CPL * CHUNK) {
+            uint4 v[CHUNK];
+            int off[CHUNK];
+            float w[CHUNK];
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) {
+                const int pair = base + i * CPL + cs;
+                int2 t = make_int2(-1, 0);
+                if (pair < npairs) t = taps[pair];
+                off[i] = t.x;
+                w[i] = __int_as_float(t.y);
+                v[i] = gather16(vbase, t.x, (int)sizeof(T));
+            }
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) {
+                if (off[i] >= 0) {
+                    float gv[VEC];
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) gv[c] = w[i] * g[c];
+                    Vec<T>::red_add(gvbase + off[i], gv);
+                }
+                float f[VEC];
+                Vec<T>::unpack(v[i], f);
+                float d = 0.0f;
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) d = fmaf(g[c], f[c], d);
+#pragma unroll
+                for (int m = 1; m < LPC; m <<= 1) d += __shfl_xor_sync(0xffffffffu, d, m);
+                const int pair = base + i * CPL + cs;
+                if (cg == 0 && pair < npairs) dots[pair] = d;  // out-of-bounds corners: v == 0 -> d == 0
+            }
+        }
+        __syncwarp();
+
+        if (lane < S) {      // lane s still holds sample s (L*P <= 32)
+            const int l = lv.level_of[lane];
+            const int Hl = lv.h[l], Wl = lv.w[l];
+            const size_t si = (size_t)qh * S + lane;
+            const Tap t = make_tap(cur.x, cur.y, Hl, Wl);
+            const float4 d = *reinterpret_cast<const float4 *>(dots + 4 * lane);
+            const float tx = t.ix - t.fx, ty = t.iy - t.fy;
+            const float ux = (t.fx + 1.0f) - t.ix, uy = (t.fy + 1.0f) - t.iy;
+            // grid_sampler_2d_backward: gix = -nw*(y1-iy) + ne*(y1-iy) - sw*(iy-y0) + se*(iy-y0), giy analogous
+            const float ga = (ux * uy) * d.x + (tx * uy) * d.y + (ux * ty) * d.z + (tx * ty) * d.w;
+            const float gix = cur.a * (uy * (d.y - d.x) + ty * (d.w - d.z));
+            const float giy = cur.a * (ux * (d.z - d.x) + tx * (d.w - d.y));
+            // d ix / d loc_x = (W_l / 2) * 2   (GridSampler.h:51 times d(2*loc-1)/d loc)
+            reinterpret_cast<float2 *>(grad_loc)[si] = make_float2(gix * (float)Wl, giy * (float)Hl);
+            grad_attn[si] = ga;
+        }
+        __syncwarp();   // taps / dots are rewritten by the next item
+        cur = nxt;
+        graw = gnext;
     }
 }
 
@@ -319,11 +355,21 @@ __global__ void msda_corners_kernel(const float *__restrict__ loc, int32_t *__re
 }
 
 // ------------------------------------------------------------------------------------------- dispatch
+// Persistent launch: one wave of `ctas_per_sm` CTAs per SM (or fewer when there is less work); every warp then walks
+// items qh, qh + grid*8, ... so that the prefetch of the next item overlaps the gather of the current one.
+static int persistent_grid(long total, int ctas_per_sm) {
+    static int n_sm = 0;
+    if (n_sm == 0 && cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess) n_sm = 148;
+    const long need = (total + kWarpsPerCta - 1) / kWarpsPerCta;
+    const long wave = (long)n_sm * ctas_per_sm;
+    return (int)(need < wave ? need : wave);
+}
+
 template <typename T, int LPC>
 static int launch_fwd(const void *value, const float *loc, const float *attn, void *out, const Levels &lv, int B,
                       int Lq, int H, int Lv, int tok_stride, cudaStream_t st) {
     const long total = (long)B * Lq * H;
-    const int grid = (int)((total + kWarpsPerCta - 1) / kWarpsPerCta);
+    const int grid = persistent_grid(total, 3);
     KernelTimer timer(K_MSDA_FWD, st);
     if (lv.n * lv.P == 12)
         msda_fwd_kernel<T, LPC, 12><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)value, loc, attn, (T *)out, lv, Lq,
@@ -341,7 +387,7 @@ static int launch_bwd(const void *grad_out, const void *value, const float *loc,
                       float *grad_loc, float *grad_attn, const Levels &lv, int B, int Lq, int H, int Lv,
                       int tok_stride, int zero_grad_value, cudaStream_t st) {
     const long total = (long)B * Lq * H;
-    const int grid = (int)((total + kWarpsPerCta - 1) / kWarpsPerCta);
+    const int grid = persistent_grid(total, 2);
     if (zero_grad_value) {
         TAMTR_CUDA_OK(cudaMemsetAsync(grad_value, 0, (size_t)B * Lv * tok_stride * sizeof(T), st));
         count_launch();

@@ -40,7 +40,7 @@ class ValueArena:
 
     def grad_buffer(self, like):
         if self.buf is None:
-            self.buf = torch.zeros(like.shape, dtype=like.dtype, device=like.device)
+            self.buf = _lib.zeros_like_fast(like)
         return self.buf
 
 
@@ -584,24 +584,27 @@ def rank_tokens(feats, valid_u8, enc_linear, enc_norm, score_linear):
         lp = feats.dtype
         f2 = feats.reshape(B * Lv, d)
         Wp = score_linear.weight.float() * enc_norm.weight.float()                 # [nc, d]
+        nc = Wp.shape[0]
+        npad = (nc + 15) // 16 * 16            # keeps the skinny GEMM on 16-byte aligned (tensor-core) kernels
+        Wpad = torch.zeros(npad, d, dtype=torch.float32, device=feats.device)
+        Wpad[:nc] = Wp
         if lp == torch.float32:
             E = f2 @ enc_linear.weight.float().t()
-            raw = E @ Wp.t()
+            raw = E @ Wpad.t()
         else:
             with torch.autocast("cuda", enabled=False):
                 E = f2 @ enc_linear.weight.to(lp).t()
-                raw = torch.mm(E, Wp.to(lp).t(), out_dtype=torch.float32)
+                raw = torch.mm(E, Wpad.to(lp).t(), out_dtype=torch.float32)
         eb = enc_linear.bias.float().contiguous()
         bw = (Wp @ eb).contiguous()
         sw = Wp.sum(1).contiguous()
         ck = (score_linear.weight.float() @ enc_norm.bias.float() + score_linear.bias.float()).contiguous()
-        nc = Wp.shape[0]
         out = torch.empty(B, Lv, dtype=torch.float32, device=feats.device)
         raw = raw.contiguous()
         with _with_device(feats):
             rc = _lib.lib().tamtr_rank_tokens(E.data_ptr(), raw.data_ptr(), eb.data_ptr(), valid_u8.data_ptr(),
                                               bw.data_ptr(), sw.data_ptr(), ck.data_ptr(), out.data_ptr(),
-                                              _lib.dtype_code(E), B, Lv, d, nc, float(enc_norm.eps),
+                                              _lib.dtype_code(E), B, Lv, d, nc, npad, float(enc_norm.eps),
                                               _lib.stream_ptr(feats.device))
         _lib.check(rc, "rank_tokens")
     return out

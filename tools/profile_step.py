@@ -31,3 +31,11 @@ tot = sum(v[1] for v in agg.values())
 print(f"steps={args.steps} total kernel time/step = {tot/args.steps/1e3:.3f} ms, kernels/step = {sum(v[0] for v in agg.values())/args.steps:.0f}")
 for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:args.top]:
     print(f"{t/args.steps:10.1f} us {100*t/tot:5.1f}%  x{c/args.steps:6.1f}  {name}")
+
+print("---- individual launches > 40 us (one step)")
+evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+n = len(evs) // args.steps
+for ev in evs[:n]:
+    if ev.device_time > 40:
+        print(f"{ev.device_time:9.1f} us  {ev.name[:150]}")
