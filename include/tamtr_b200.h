@@ -80,11 +80,14 @@ int tamtr_msda_forward(const void *value, const float *loc, const float *attn, v
  *                              accumulated with vector atomics (REDG f32x4 / bf16x8) -> run-to-run bit differences,
  *                              like grid_sampler backward
  *   grad_loc   [B, Lq, H, L, P, 2] f32, grad_attn [B, Lq, H, L, P] f32 (fully overwritten)
+ *   tap_weight_sum [B, Lq, H] f32 or NULL: sum of the in-bounds A*w_k of each (query, head); the column sums of
+ *                  grad_value (= value_proj's bias gradient) are sum_q tap_weight_sum[q,h] * grad_out[q,h,:]
  */
 int tamtr_msda_backward(const void *grad_out, const void *value, const float *loc, const float *attn,
                         void *grad_value, float *grad_loc, float *grad_attn, int dtype,
                         int B, int Lv, int H, int Dh, int Lq, int L, int P,
-                        const int32_t *level_shapes_host, int value_token_stride, int zero_grad_value, void *stream);
+                        const int32_t *level_shapes_host, int value_token_stride, int zero_grad_value,
+                        float *tap_weight_sum, void *stream);
 
 /* Parity export of the index math alone (the "bit-exact sampling-location indexing" object):
  *   x0, y0 [B,Lq,H,L,P] int32 = floor(ix), floor(iy);  inb [B,Lq,H,L,P,4] uint8 = in-bounds flags (nw,ne,sw,se).

@@ -136,14 +136,18 @@ rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const
     constexpr int N = Pack<T>::N;
     constexpr int TOK = 4;            // tokens per warp: 4 * PP independent 16-byte loads in flight per lane
     const int lane = threadIdx.x & 31;
-    const long row0 = ((long)blockIdx.x * (kEncThreads / 32) + (threadIdx.x >> 5)) * TOK;
-    if (row0 >= rows) return;
+    const int nrows = (int)rows;      // B*Lv < 2^31 (checked by the launcher): 32-bit index math
+    const int row0 = (blockIdx.x * (kEncThreads / 32) + (threadIdx.x >> 5)) * TOK;
+    if (row0 >= nrows) return;
     float v[TOK][PP][N];
     bool ok[TOK];
+    const int t0 = row0 % Lv;
 #pragma unroll
     for (int t = 0; t < TOK; ++t) {
-        const long row = row0 + t;
-        ok[t] = row < rows && valid[row % Lv] != 0;
+        const int row = row0 + t;
+        int tok = t0 + t;
+        tok = tok >= Lv ? tok - Lv : tok;
+        ok[t] = row < nrows && valid[tok] != 0;
 #pragma unroll
         for (int p = 0; p < PP; ++p) {
             const int c = (p * 32 + lane) * N;
@@ -157,8 +161,13 @@ rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const
     for (int p = 0; p < PP; ++p) {
         const int c = (p * 32 + lane) * N;
 #pragma unroll
-        for (int i = 0; i < N; ++i) eb[p][i] = c < d ? __ldg(enc_bias + c + i) : 0.f;
+        for (int i = 0; i < N; i += 4) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < d) q = __ldg(reinterpret_cast<const float4 *>(enc_bias + c + i));
+            eb[p][i] = q.x; eb[p][i + 1] = q.y; eb[p][i + 2] = q.z; eb[p][i + 3] = q.w;
+        }
     }
+    const float inv_d = 1.0f / (float)d;
     // the TOK tokens are reduced in lockstep so that their shuffle / load chains overlap (ILP across tokens)
     float s[TOK], ss[TOK], best[TOK];
 #pragma unroll
@@ -175,7 +184,7 @@ rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const
         for (int t = 0; t < TOK; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], m);
 #pragma unroll
     for (int t = 0; t < TOK; ++t) {
-        const float mean = s[t] / (float)d;
+        const float mean = s[t] * inv_d;
         s[t] = mean;
         ss[t] = 0.f;
 #pragma unroll
@@ -195,10 +204,10 @@ rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const
                 cck = lane < nc ? __ldg(ck + lane) : 0.f;
 #pragma unroll
     for (int t = 0; t < TOK; ++t) {
-        const long row = row0 + t;
-        const float rstd = rsqrtf(ss[t] / (float)d + eps);
+        const int row = row0 + t;
+        const float rstd = rsqrtf(ss[t] * inv_d + eps);
         best[t] = -INFINITY;
-        if (row < rows) {
+        if (row < nrows) {
             if (nc <= 32) {
                 if (lane < nc) {
                     const float r = ok[t] ? __ldg(raw + (size_t)row * raw_stride + lane) : 0.f;
@@ -216,7 +225,7 @@ rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const
     for (int m = 16; m > 0; m >>= 1)
 #pragma unroll
         for (int t = 0; t < TOK; ++t) best[t] = fmaxf(best[t], __shfl_xor_sync(0xffffffffu, best[t], m));
-    if (lane < TOK && row0 + lane < rows) {
+    if (lane < TOK && row0 + lane < nrows) {
         float o = best[0];
 #pragma unroll
         for (int t = 1; t < TOK; ++t) o = lane == t ? best[t] : o;
@@ -305,6 +314,7 @@ extern "C" int tamtr_rank_tokens(const void *E, const float *raw, const float *e
     const int n = dtype == TAMTR_F32 ? 4 : 8;
     TAMTR_CHECK_ARG(d <= 4 * 32 * n, TAMTR_E_UNSUPPORTED, "rank_tokens: d = %d too large", d);
     const long rows = (long)B * Lv;
+    TAMTR_CHECK_ARG(rows < (1L << 31) - 64, TAMTR_E_UNSUPPORTED, "rank_tokens: too many tokens");
     const long per_cta = (kEncThreads / 32) * 4;
     const unsigned blocks = (unsigned)((rows + per_cta - 1) / per_cta);
     const int pp = (d + 32 * n - 1) / (32 * n);

@@ -6,7 +6,7 @@
 // as a warp-specialised persistent-per-(b,m) kernel:
 //   warp 0   TMA producer : cp.async.bulk.tensor.2d loads the 32-channel x 128-pixel tile of `embed` (NCHW: pixels are
 //                           contiguous, so the tile is an MN-major A operand) as two 64-pixel boxes, 128B-swizzled,
-//                           into a 4-stage shared-memory ring (mbarrier complete_tx)
+//                           into an 8-stage shared-memory ring (mbarrier complete_tx)
 //   warp 1   MMA issuer   : one elected lane issues 2 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=Npad, K=16 each;
 //                           K = hc = 32) per tile into one of two TMEM accumulator stages; tcgen05.commit releases the
 //                           smem stage and publishes the accumulator
@@ -25,7 +25,7 @@ namespace tamtr {
 
 constexpr int kTcTileM = 128;                       // pixels per tile = UMMA M = TMEM lanes
 constexpr int kTcHc = 32;                           // channels per head = K
-constexpr int kTcStages = 4;                        // smem ring depth
+constexpr int kTcStages = 8;                        // smem ring depth: 2 CTAs/SM x 8 x 8 KB = 128 KB in flight per SM
 constexpr int kTcAccStages = 2;                     // TMEM accumulator double buffer
 constexpr int kTcAccCols = 128;                     // columns reserved per accumulator stage (Npad <= 128)
 constexpr int kTcABytes = kTcHc * kTcTileM * 2;     // 8192: two 64-pixel boxes of 32 rows x 128 B

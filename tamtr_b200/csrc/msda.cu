@@ -241,7 +241,8 @@ template <typename T, int LPC, int NS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 msda_bwd_kernel(const T *__restrict__ grad_out, const T *__restrict__ value, const float *__restrict__ loc,
                 const float *__restrict__ attn, T *__restrict__ grad_value, float *__restrict__ grad_loc,
-                float *__restrict__ grad_attn, const Levels lv, int Lq, int H, int Lv, int total, int tok_stride) {
+                float *__restrict__ grad_attn, float *__restrict__ tap_weight_sum, const Levels lv, int Lq, int H,
+                int Lv, int total, int tok_stride) {
     constexpr int VEC = Vec<T>::N;
     constexpr int DH = LPC * VEC;
     constexpr int CPL = 32 / LPC;
@@ -327,6 +328,20 @@ msda_bwd_kernel(const T *__restrict__ grad_out, const T *__restrict__ value, con
             reinterpret_cast<float2 *>(grad_loc)[si] = make_float2(gix * (float)Wl, giy * (float)Hl);
             grad_attn[si] = ga;
         }
+        if (tap_weight_sum) {
+            // sum of the in-bounds tap weights A*w_k of this (query, head): the column sums of grad_value -- i.e. the
+            // value_proj bias gradient -- follow from it as sum_q tap_weight_sum[q,h] * grad_out[q,h,:] without ever
+            // reading the dense [B, Lv, d] gradient back (ops.py::_ValueProjFn)
+            float ws = 0.f;
+            if (lane < S) {
+                const int4 lo = *reinterpret_cast<const int4 *>(taps + 4 * lane);
+                const int4 hi = *reinterpret_cast<const int4 *>(taps + 4 * lane + 2);
+                ws = __int_as_float(lo.y) + __int_as_float(lo.w) + __int_as_float(hi.y) + __int_as_float(hi.w);
+            }
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, m);
+            if (lane == 0) tap_weight_sum[qh] = ws;
+        }
         __syncwarp();   // taps / dots are rewritten by the next item
         cur = nxt;
         graw = gnext;
@@ -384,8 +399,8 @@ static int launch_fwd(const void *value, const float *loc, const float *attn, vo
 
 template <typename T, int LPC>
 static int launch_bwd(const void *grad_out, const void *value, const float *loc, const float *attn, void *grad_value,
-                      float *grad_loc, float *grad_attn, const Levels &lv, int B, int Lq, int H, int Lv,
-                      int tok_stride, int zero_grad_value, cudaStream_t st) {
+                      float *grad_loc, float *grad_attn, float *tap_weight_sum, const Levels &lv, int B, int Lq, int H,
+                      int Lv, int tok_stride, int zero_grad_value, cudaStream_t st) {
     const long total = (long)B * Lq * H;
     const int grid = persistent_grid(total, 2);
     if (zero_grad_value) {
@@ -396,11 +411,13 @@ static int launch_bwd(const void *grad_out, const void *value, const float *loc,
     if (lv.n * lv.P == 12)
         msda_bwd_kernel<T, LPC, 12><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)grad_out, (const T *)value, loc,
                                                                          attn, (T *)grad_value, grad_loc, grad_attn,
-                                                                         lv, Lq, H, Lv, (int)total, tok_stride);
+                                                                         tap_weight_sum, lv, Lq, H, Lv, (int)total,
+                                                                         tok_stride);
     else
         msda_bwd_kernel<T, LPC, 0><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)grad_out, (const T *)value, loc,
-                                                                        attn, (T *)grad_value, grad_loc, grad_attn, lv,
-                                                                        Lq, H, Lv, (int)total, tok_stride);
+                                                                        attn, (T *)grad_value, grad_loc, grad_attn,
+                                                                        tap_weight_sum, lv, Lq, H, Lv, (int)total,
+                                                                        tok_stride);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
@@ -457,7 +474,7 @@ extern "C" int tamtr_msda_forward(const void *value, const float *loc, const flo
 extern "C" int tamtr_msda_backward(const void *grad_out, const void *value, const float *loc, const float *attn,
                                    void *grad_value, float *grad_loc, float *grad_attn, int dtype, int B, int Lv, int H,
                                    int Dh, int Lq, int L, int P, const int32_t *level_shapes_host,
-                                   int value_token_stride, int zero_grad_value, void *stream) {
+                                   int value_token_stride, int zero_grad_value, float *tap_weight_sum, void *stream) {
     TAMTR_CHECK_ARG(grad_out && value && loc && attn && grad_value && grad_loc && grad_attn, TAMTR_E_BADARG,
                     "msda_backward: null pointer");
     Levels lv;
@@ -467,8 +484,8 @@ extern "C" int tamtr_msda_backward(const void *grad_out, const void *value, cons
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
 #define BWD(T, N)                                                                                                  \
-    return launch_bwd<T, N>(grad_out, value, loc, attn, grad_value, grad_loc, grad_attn, lv, B, Lq, H, Lv, ts, \
-                            zero_grad_value, st)
+    return launch_bwd<T, N>(grad_out, value, loc, attn, grad_value, grad_loc, grad_attn, tap_weight_sum, lv, B, Lq, \
+                            H, Lv, ts, zero_grad_value, st)
     if (dtype == TAMTR_F32) {
         switch (lpc) { case 2: BWD(float, 2); case 4: BWD(float, 4); case 8: BWD(float, 8); case 16: BWD(float, 16); }
     } else {

@@ -176,13 +176,13 @@ class _DecoderBase(nn.Module):
             return [None] * n_used, None
         w = torch.cat([a.value_proj.weight for a in attns], 0)
         b = torch.cat([a.value_proj.bias for a in attns], 0)
-        arena = ops.ValueArena()
-        value_all = F.linear(feats, w, b)
-        if not value_all.requires_grad:
+        if not (torch.is_grad_enabled() and (feats.requires_grad or w.requires_grad)):
+            value_all = F.linear(feats, w, b)
             d = attns[0].d_model
             bs, lv = feats.shape[:2]
             return [value_all[:, :, i * d:(i + 1) * d].view(bs, lv, attns[0].n_heads, -1) for i in range(n_used)], None
-        return list(ops.split_values(value_all, arena, n_used, attns[0].n_heads)), arena
+        arena = ops.ValueArena()
+        return list(ops.project_values(feats, w, b, arena, n_used, attns[0].n_heads)), arena
 
     def _run(self, embed, refer_bbox, feats, shapes, bbox_head, score_fn, pos_mlp, attn_mask, padding_mask):
         output = embed

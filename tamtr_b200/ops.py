@@ -28,15 +28,18 @@ def _value_layout(value):
 
 
 class ValueArena:
-    """Shared gradient buffer for the value tensors of all decoder layers.
+    """Shared gradient state for the value tensors of all decoder layers.
 
     The decoder projects `feats` once for every layer (one [d, n_layers*d] GEMM); each layer's sampler reads its
     column slice.  In the backward every sampler accumulates into ITS slice of one zero-initialised
-    [B, Lv, n_layers*d] buffer, which then feeds a single dgrad and a single wgrad GEMM -- no per-layer dense
-    gradient tensors, no gradient-accumulation passes over [B, Lv, d]."""
+    [B, Lv, n_layers*d] buffer (memset node), which then feeds a single dgrad and a single wgrad GEMM -- no per-layer
+    dense gradient tensors and no gradient-accumulation passes over [B, Lv, d].  The bias gradient (column sums of
+    that buffer) is assembled from the samplers' per-(query, head) tap-weight sums instead of re-reading it."""
 
     def __init__(self):
         self.buf = None
+        self.base = None
+        self.bias_grad = {}       # column offset of a layer's slice -> [d] fp32
 
     def grad_buffer(self, like):
         if self.buf is None:
@@ -44,36 +47,60 @@ class ValueArena:
         return self.buf
 
 
-class _SplitValueFn(torch.autograd.Function):
+class _ValueProjFn(torch.autograd.Function):
+    """value_all = feats @ W_cat^T + b_cat, returned as n per-layer head-major views [B, Lv, H, Dh]
+    (transformer.py:273 for all layers at once).  Library GEMMs; the backward consumes the arena."""
+
     @staticmethod
-    def forward(ctx, value_all, arena, n, H):
-        B, Lv, C = value_all.shape
-        d = C // n
+    def forward(ctx, feats, w_cat, b_cat, arena, n, H):
+        lp = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else feats.dtype
+        B, Lv, C = feats.shape
+        f2 = feats.reshape(B * Lv, C).to(lp)
+        w = w_cat.to(lp)
+        value_all = torch.addmm(b_cat.to(lp), f2, w.t()).view(B, Lv, -1)
+        d = value_all.shape[-1] // n
+        ctx.save_for_backward(f2, w)
         ctx.arena, ctx.n, ctx.d = arena, n, d
-        ctx.meta = (value_all.shape, value_all.dtype, value_all.device)
+        ctx.meta = (value_all.shape, value_all.dtype, value_all.device, feats.dtype, w_cat.dtype, b_cat.dtype, feats.shape)
         ctx.set_materialize_grads(False)
         arena.base = value_all
         return tuple(value_all[:, :, i * d:(i + 1) * d].view(B, Lv, H, d // H) for i in range(n))
 
     @staticmethod
     def backward(ctx, *grads):
+        f2, w = ctx.saved_tensors
         arena, n, d = ctx.arena, ctx.n, ctx.d
+        shape, dtype, device, fdt, wdt, bdt, fshape = ctx.meta
         buf, arena.buf, arena.base = arena.buf, None, None
-        shape, dtype, device = ctx.meta
         if buf is None:
-            buf = torch.zeros(shape, dtype=dtype, device=device)
+            buf = _lib.zeros_like_fast(torch.empty(shape, dtype=dtype, device=device))
+        from_arena = True
         for i, g in enumerate(grads):
             if g is None:
                 continue
             sl = buf[:, :, i * d:(i + 1) * d]
             if g.data_ptr() != sl.data_ptr():          # gradient did not come through the arena: add it
                 sl.add_(g.reshape(shape[0], shape[1], d))
-        return buf, None, None, None
+                from_arena = False
+        g2 = buf.view(-1, shape[-1])
+        grad_feats = (g2 @ w).view(fshape).to(fdt) if ctx.needs_input_grad[0] else None
+        grad_w = None
+        if ctx.needs_input_grad[1]:
+            grad_w = (g2.t() @ f2 if dtype == torch.float32 else torch.mm(g2.t(), f2, out_dtype=torch.float32)).to(wdt)
+        grad_b = None
+        if ctx.needs_input_grad[2]:
+            if from_arena and all(i * d in arena.bias_grad or grads[i] is None for i in range(n)):
+                parts = [arena.bias_grad.get(i * d) for i in range(n)]
+                grad_b = torch.cat([p if p is not None else torch.zeros(d, device=device) for p in parts]).to(bdt)
+            else:
+                grad_b = g2.float().sum(0).to(bdt)
+        arena.bias_grad = {}
+        return grad_feats, grad_w, grad_b, None, None, None
 
 
-def split_values(value_all, arena, n_layers, n_heads):
-    """[B, Lv, n_layers*d] -> n_layers views [B, Lv, H, Dh] sharing `arena` for their gradients."""
-    return _SplitValueFn.apply(value_all, arena, n_layers, n_heads)
+def project_values(feats, w_cat, b_cat, arena, n_layers, n_heads):
+    """One GEMM for the value projections of all decoder layers -> n_layers views [B, Lv, H, Dh] that share `arena`."""
+    return _ValueProjFn.apply(feats, w_cat, b_cat, arena, n_layers, n_heads)
 
 
 class _MSDeformAttnFn(torch.autograd.Function):
@@ -111,6 +138,7 @@ class _MSDeformAttnFn(torch.autograd.Function):
         _, Lq, _, L, P, _ = loc.shape
         sh, _ = _lib.shapes_array(ctx.shapes)
         tok_stride = ctx.tok_stride
+        wsum = None
         if ctx.arena is not None:
             # accumulate into this layer's column slice of the shared, already zeroed buffer
             base = ctx.arena.base
@@ -118,6 +146,7 @@ class _MSDeformAttnFn(torch.autograd.Function):
             off = value.storage_offset() - base.storage_offset()
             grad_value = buf.view(-1)[off:].as_strided(value.shape, value.stride())
             zero = 0
+            wsum = torch.empty(B, Lq, H, dtype=torch.float32, device=value.device)
         elif tok_stride != H * Dh:
             grad_value = torch.empty(B, Lv, H, Dh, dtype=value.dtype, device=value.device)
             tok_stride, zero = H * Dh, 1
@@ -139,8 +168,12 @@ class _MSDeformAttnFn(torch.autograd.Function):
             rc = _lib.lib().tamtr_msda_backward(grad_out.data_ptr(), value.data_ptr(), loc.data_ptr(),
                                                 attn.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(),
                                                 grad_attn.data_ptr(), _lib.dtype_code(value), B, Lv, H, Dh, Lq, L, P,
-                                                sh, tok_stride, zero, _lib.stream_ptr(value.device))
+                                                sh, tok_stride, zero, wsum.data_ptr() if wsum is not None else None,
+                                                _lib.stream_ptr(value.device))
         _lib.check(rc, "msda_backward")
+        if wsum is not None:      # value_proj bias gradient of this layer: sum_q wsum[q,h] * grad_out[q,h,:]
+            ctx.arena.bias_grad[off % base.shape[-1]] = torch.einsum(
+                "bqh,bqhc->hc", wsum, grad_out.view(B, Lq, H, Dh).float()).reshape(-1)
         return grad_value, grad_loc, grad_attn, None, None
 
 

@@ -213,20 +213,28 @@ def test_strided_value_views_and_arena(cuda_lib):
     d = H * Dh
     Lv = sum(h * w for h, w in shapes)
     g = torch.Generator().manual_seed(3)
-    value_all = torch.randn(B, Lv, n * d, generator=g)
+    feats = torch.randn(B, Lv, 64, generator=g)
+    w_cat = torch.randn(n * d, 64, generator=g) / 8
+    b_cat = torch.randn(n * d, generator=g)
     ins = [msda.make_inputs(10 + i, B, Lq, H, Dh, shapes, oob_frac=0.2) for i in range(n)]
     for dtype, tol in ((torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)):
-        va = value_all.to(dtype).cuda().requires_grad_()
+        fc = feats.to(dtype).cuda().requires_grad_()
+        wc = w_cat.to(dtype).cuda().requires_grad_()
+        bc = b_cat.to(dtype).cuda().requires_grad_()
+        value_all = (fc.detach().float().cpu() @ wc.detach().float().cpu().t() + bc.detach().float().cpu()).to(dtype).float()
         arena = ops.ValueArena()
-        views = ops.split_values(va * 1.0, arena, n, H)
+        views = ops.project_values(fc, wc, bc, arena, n, H)
         total = 0
         refs = []
         for i, (_, loc, attn, gout) in enumerate(ins):
             out = cuda_lib.ms_deform_attn(views[i], shapes, loc.cuda(), attn.cuda(), arena)
             total = total + (out.float() * gout.cuda()).sum()
-            v_i = value_all[:, :, i * d:(i + 1) * d].to(dtype).float().reshape(B, Lv, H, Dh)
+            v_i = value_all[:, :, i * d:(i + 1) * d].reshape(B, Lv, H, Dh)
             assert rel_l2(out, msda.forward_c(v_i, shapes, loc, attn)) < tol
             refs.append(msda.backward_c(gout.to(dtype).float(), v_i, shapes, loc, attn)[0].reshape(B, Lv, d))
         total.backward()
-        assert rel_l2(va.grad, torch.cat(refs, -1)) < tol
-        assert arena.buf is None            # consumed by the split node
+        gall = torch.cat(refs, -1)                                            # reference grad of value_all
+        assert rel_l2(bc.grad, gall.sum((0, 1))) < tol                        # bias grad from the tap-weight sums
+        assert rel_l2(wc.grad, gall.reshape(-1, n * d).t() @ fc.detach().float().cpu().reshape(-1, 64)) < tol
+        assert rel_l2(fc.grad, gall @ wc.detach().float().cpu()) < tol
+        assert arena.buf is None            # consumed by the projection node
