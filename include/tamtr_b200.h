@@ -116,6 +116,13 @@ int tamtr_locw_backward(const float *grad_loc, const float *grad_attn, const flo
                         const float *bias, const float *ref, float *grad_raw, float *grad_ref,
                         int M, int H, int L, int P, int RL, int RD, const int32_t *level_shapes_host, void *stream);
 
+/* Iterative box refinement of the decoders (transformer.py:875,882 / 699,706; inverse_sigmoid: utils.py:34-39):
+ *   out = sigmoid(bbox + log(clamp(ref,0,1).clamp(min=eps) / (1 - clamp(ref,0,1)).clamp(min=eps)))     all f32 [n]
+ * backward: grad_bbox always, grad_ref optional (NULL when the reference boxes are detached). */
+int tamtr_box_refine_forward(const float *bbox, const float *ref, float *out, int n, float eps, void *stream);
+int tamtr_box_refine_backward(const float *grad_out, const float *out, const float *ref, float *grad_bbox,
+                              float *grad_ref, int n, float eps, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Text-guided classification branch (region-text contrastive head).
  * Replaces ultralytics/nn/modules/block.py:534-541 ContrastiveHeadMLP.forward:

@@ -34,6 +34,8 @@ _SIGNATURES = {
     "tamtr_msda_corners": (ctypes.c_int, [_fp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp]),
     "tamtr_locw_forward": (ctypes.c_int, [_fp] * 5 + [_i] * 6 + [_vp, _vp]),
     "tamtr_locw_backward": (ctypes.c_int, [_fp] * 8 + [_i] * 6 + [_vp, _vp]),
+    "tamtr_box_refine_forward": (ctypes.c_int, [_fp, _fp, _fp, _i, ctypes.c_float, _vp]),
+    "tamtr_box_refine_backward": (ctypes.c_int, [_fp, _fp, _fp, _fp, _fp, _i, ctypes.c_float, _vp]),
     "tamtr_contrastive_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _fp] + [_i] * 5 + [_vp]),
     "tamtr_contrastive_backward": (ctypes.c_int, [_fp, _vp, _fp, _fp, _vp, _fp] + [_i] * 5 + [_vp]),
     "tamtr_max_sigmoid_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _vp] + [_i] * 6 + [_vp]),

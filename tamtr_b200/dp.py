@@ -4,8 +4,8 @@ The reference trains with torch DDP: batch sharded by DistributedSampler, one bu
 gradients per backward (ultralytics/engine/trainer.py:241, 252; data/build.py:104).  The path shards by image with
 no data-path collective; the only exchange step is that gradient all-reduce.  B200-first restatement:
 
-* every parameter's .grad is a view into ONE flat fp32 buffer -> the exchange is a single NCCL all-reduce over
-  NVLink/NVSwitch (no bucket copies), issued right after the backward;
+* the gradients are packed into ONE flat fp32 buffer by a single multi-tensor copy at the end of the backward -> the
+  exchange is a single NCCL all-reduce over NVLink/NVSwitch, issued right after the backward;
 * forward + backward of the step are captured ONCE into a CUDA graph (static input buffers, the denoising group is
   planned on the host per batch exactly as the reference does and only its embedding gather is in the graph), so the
   ~1.5k small launches of the step cost one graph launch instead of Python/launch latency;
@@ -33,20 +33,39 @@ def shard_indices(n_items, rank, world_size):
 
 
 class FlatGrads:
-    """All parameter gradients as views of one flat buffer (DDP's gradient_as_bucket_view, single bucket)."""
+    """One flat buffer for all parameter gradients (DDP's gradient_as_bucket_view with a single bucket).
+
+    Gradients are NOT accumulated into the buffer by autograd (that is one tiny `grad += g` launch per parameter,
+    ~130 for the MEH head): the backward writes fresh .grad tensors, `gather()` packs them with one multi-tensor
+    copy, and the exchange is a single all-reduce over the flat buffer."""
 
     def __init__(self, params, dtype=torch.float32):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=dtype, device=dev)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
 
-    def zero_(self):
-        self.flat.zero_()
+    def clear(self):
+        for p in self.params:
+            p.grad = None
+
+    def gather(self):
+        """Pack the parameters' .grad tensors into the flat buffer (one fused multi-tensor copy)."""
+        dst, src = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                dst.append(v)
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        return self.flat
 
     def all_reduce_mean(self):
         """One all-reduce (sum) + scale: the DDP semantics of trainer.py:241 (mean over ranks)."""
@@ -55,6 +74,11 @@ class FlatGrads:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(ws)
         return self.flat
+
+    def scatter(self):
+        """Point every .grad at its (reduced) slice of the flat buffer, e.g. before an optimizer step."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
 
 class HeadTrainStep:
@@ -70,6 +94,7 @@ class HeadTrainStep:
     def __init__(self, module, loss_fn, example, autocast=None, use_graph=True, warmup=3):
         self.module, self.loss_fn, self.autocast = module, loss_fn, autocast
         self.flat = FlatGrads(module.parameters())
+        self.pack_grads = world()[1] > 1 or not use_graph     # single process: gradients can stay where autograd put them
         self.device = self.flat.flat.device
         self.cuda = self.device.type == "cuda"
         self.use_graph = use_graph and self.cuda
@@ -90,7 +115,7 @@ class HeadTrainStep:
         return a
 
     def _fwd_bwd(self):
-        self.flat.zero_()
+        self.flat.clear()
         if self.autocast is not None:
             with torch.autocast(self.device.type, dtype=self.autocast):
                 out = self.module(*self.static)
@@ -99,6 +124,8 @@ class HeadTrainStep:
         loss = self.loss_fn(out)
         loss.backward()
         self.loss.copy_(loss.detach())
+        if self.pack_grads:
+            self.flat.gather()
 
     def _capture(self, warmup):
         from . import _lib
@@ -133,7 +160,7 @@ class HeadTrainStep:
             self.graph.replay()
         else:
             self._fwd_bwd()
-        if reduce:
+        if reduce and self.pack_grads:
             self.flat.all_reduce_mean()
         return self.loss
 

@@ -195,10 +195,11 @@ class _DecoderBase(nn.Module):
             output = layer(output, refer_bbox, feats, shapes, padding_mask, attn_mask, pos_mlp(refer_bbox),
                            values[i] if i < n_used else None, arena)
             bbox = bbox_head[i](output)
-            refined = torch.sigmoid(bbox + inverse_sigmoid(refer_bbox))
+            refine = ops.box_refine          # sigmoid(bbox + inverse_sigmoid(ref)) as one kernel
+            refined = refine(bbox, refer_bbox)
             if self.training:
                 dec_cls.append(score_fn(i, output))
-                dec_bboxes.append(refined if i == 0 else torch.sigmoid(bbox + inverse_sigmoid(last_refined)))
+                dec_bboxes.append(refined if i == 0 else refine(bbox, last_refined))
             elif i == self.eval_idx:
                 dec_cls.append(score_fn(i, output))
                 dec_bboxes.append(refined)

@@ -288,6 +288,43 @@ def sampling_locations_and_weights(query, refer_bbox, w_off, b_off, w_attn, b_at
     return (loc.view(B, Lq, n_heads, n_levels, n_points, 2), attn.view(B, Lq, n_heads, n_levels, n_points))
 
 
+# ------------------------------------------------------------------------------------ box refinement
+class _BoxRefineFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bbox, ref, eps):
+        b32 = bbox.contiguous().float()
+        r32 = ref.contiguous().float()
+        out = torch.empty_like(b32)
+        with _with_device(b32):
+            rc = _lib.lib().tamtr_box_refine_forward(b32.data_ptr(), r32.data_ptr(), out.data_ptr(), b32.numel(),
+                                                     float(eps), _lib.stream_ptr(b32.device))
+        _lib.check(rc, "box_refine_forward")
+        ctx.save_for_backward(out, r32)
+        ctx.eps = float(eps)
+        ctx.dtypes = (bbox.dtype, ref.dtype)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        out, r32 = ctx.saved_tensors
+        g = g.contiguous().float()
+        gb = torch.empty_like(out)
+        gr = torch.empty_like(out) if ctx.needs_input_grad[1] else None
+        with _with_device(out):
+            rc = _lib.lib().tamtr_box_refine_backward(g.data_ptr(), out.data_ptr(), r32.data_ptr(), gb.data_ptr(),
+                                                      gr.data_ptr() if gr is not None else None, out.numel(), ctx.eps,
+                                                      _lib.stream_ptr(out.device))
+        _lib.check(rc, "box_refine_backward")
+        return gb.to(ctx.dtypes[0]), (gr.to(ctx.dtypes[1]) if gr is not None else None), None
+
+
+def box_refine(bbox, ref, eps=1e-5):
+    """sigmoid(bbox + inverse_sigmoid(ref)) (transformer.py:875; utils.py:34-39) as one kernel; fp32 result."""
+    _lib.require_cuda(bbox, ref)
+    return _BoxRefineFn.apply(bbox, ref, eps)
+
+
 # ------------------------------------------------------------------------------------ contrastive head
 class _ContrastiveFn(torch.autograd.Function):
     @staticmethod

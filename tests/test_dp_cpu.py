@@ -47,6 +47,7 @@ def _worker(rank, ws, port, out):
             grads.append(torch.cat([p.grad.reshape(-1) for p in m2.parameters()]))
         expect = torch.stack(grads).mean(0)
         ok_grad = torch.allclose(flat, expect, atol=1e-6)
+        step.flat.scatter()
         views_ok = all(p.grad.data_ptr() >= step.flat.flat.data_ptr() for p in model.parameters())
         t = dp.max_over_ranks(1.0 + rank, torch.device("cpu"))
         second = step.run()                                    # grads are re-zeroed each step, not accumulated
