@@ -202,6 +202,7 @@ def main():
     dev = torch.device("cuda", local)
     if ws > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
 
