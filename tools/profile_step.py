@@ -39,3 +39,13 @@ n = len(evs) // args.steps
 for ev in evs[:n]:
     if ev.device_time > 40:
         print(f"{ev.device_time:9.1f} us  {ev.name[:150]}")
+print("---- small kernels (< 12 us) by name, one step")
+small = collections.defaultdict(lambda: [0, 0.0])
+for ev in evs[:n]:
+    if ev.device_time <= 12:
+        nm = re.sub(r"\(.*", "", ev.name)[:110]
+        small[nm][0] += 1; small[nm][1] += ev.device_time
+tot_s = sum(v[1] for v in small.values()); cnt_s = sum(v[0] for v in small.values())
+print(f"small kernels: {cnt_s} launches, {tot_s/1e3:.3f} ms")
+for nm, (c, t) in sorted(small.items(), key=lambda kv: -kv[1][0])[:28]:
+    print(f"  x{c:4d} {t:8.1f} us  {nm}")
