@@ -225,7 +225,9 @@ class _LocWFn(torch.autograd.Function):
             lp = torch.get_autocast_dtype("cuda")
         q2c = q2.contiguous().to(lp)
         w_c = w_cat.to(lp)
-        raw = _proj_gemm(q2c, w_c)
+        with torch.autocast("cuda", enabled=False):     # the epilogue kernel needs the fp32 GEMM output as is
+            raw = _proj_gemm(q2c, w_c)
+        assert raw.dtype == torch.float32
         bias = b_cat.contiguous().float()
         ref32 = ref.contiguous().float()
         M = raw.shape[0]
@@ -650,7 +652,9 @@ def rank_tokens(feats, valid_u8, enc_linear, enc_norm, score_linear):
     """Query-selection ranking (head.py:1229-1237) without autograd: max over classes of
     enc_score_head(LayerNorm(enc_output.0(valid * feats))) for every token -> [B, Lv] fp32."""
     B, Lv, d = feats.shape
-    with torch.no_grad():
+    # every tensor handed to the kernel is built with autocast OFF: under an outer autocast a plain `@` would silently
+    # produce bf16 where the C ABI expects fp32
+    with torch.no_grad(), torch.autocast("cuda", enabled=False):
         lp = feats.dtype
         f2 = feats.reshape(B * Lv, d)
         Wp = score_linear.weight.float() * enc_norm.weight.float()                 # [nc, d]
@@ -662,15 +666,15 @@ def rank_tokens(feats, valid_u8, enc_linear, enc_norm, score_linear):
             E = f2 @ enc_linear.weight.float().t()
             raw = E @ Wpad.t()
         else:
-            with torch.autocast("cuda", enabled=False):
-                E = f2 @ enc_linear.weight.to(lp).t()
-                raw = torch.mm(E, Wpad.to(lp).t(), out_dtype=torch.float32)
+            E = f2 @ enc_linear.weight.to(lp).t()
+            raw = torch.mm(E, Wpad.to(lp).t(), out_dtype=torch.float32)
         eb = enc_linear.bias.float().contiguous()
-        bw = (Wp @ eb).contiguous()
-        sw = Wp.sum(1).contiguous()
-        ck = (score_linear.weight.float() @ enc_norm.bias.float() + score_linear.bias.float()).contiguous()
+        bw = (Wp @ eb).float().contiguous()
+        sw = Wp.sum(1).float().contiguous()
+        ck = (score_linear.weight.float() @ enc_norm.bias.float() + score_linear.bias.float()).float().contiguous()
         out = torch.empty(B, Lv, dtype=torch.float32, device=feats.device)
         raw = raw.contiguous()
+        assert raw.dtype == torch.float32 and bw.dtype == torch.float32 and ck.dtype == torch.float32
         with _with_device(feats):
             rc = _lib.lib().tamtr_rank_tokens(E.data_ptr(), raw.data_ptr(), eb.data_ptr(), valid_u8.data_ptr(),
                                               bw.data_ptr(), sw.data_ptr(), ck.data_ptr(), out.data_ptr(),

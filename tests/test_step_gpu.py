@@ -44,6 +44,23 @@ def test_graph_replay_and_fused_cast_match_plain_autocast(cuda_lib):
         out = m([x.cuda() for x in xs], text.cuda(), plan.to("cuda"))
     loss_ref = _loss(out)
     loss_ref.backward()
+    # the head under bf16 autocast selects (almost) the same queries as its fp32 run: guards the fused ranking path
+    with torch.no_grad():
+        feats, shapes, hub = m._encode([x.cuda().float() for x in xs])
+        anchors, valid = m._anchors(shapes, feats.dtype, feats.device)
+        r32 = m._rank_tokens(feats, valid)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            fb, shapes, hub = m._encode([x.cuda() for x in xs])
+            a2, v2 = m._anchors(shapes, fb.dtype, fb.device)
+            r16 = m._rank_tokens(fb, v2)
+    assert rel_l2(r16, r32) < 2e-2
+    m.zero_grad(set_to_none=True)
+    for p in m.parameters():
+        p.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m([x.cuda() for x in xs], text.cuda(), plan.to("cuda"))
+    loss_ref = _loss(out)
+    loss_ref.backward()
     g_ref = _grads(m)
     sd = {k: v.clone() for k, v in m.state_dict().items()}      # BN running stats moved: restore for each variant
     for graph, fused in ((False, True), (True, True), (True, False)):
