@@ -184,6 +184,9 @@ def main():
     ap.add_argument("--impl", default="tamtr_b200", choices=["tamtr_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--launch-list", action="store_true",
+                    help="eager steps only (no e2e / instrumented pass / CPU baseline): the command to run under "
+                         "`ncu --metrics gpu__time_duration.sum` for profiles/launches_*.csv")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -219,7 +222,13 @@ def main():
     Lq = plan.n_dn + NQ
 
     step = dp.HeadTrainStep(model, loss_fn, (host[0][0], host[0][1], plan), autocast=torch.bfloat16,
-                            use_graph=not args.no_graph)
+                            use_graph=not (args.no_graph or args.launch_list))
+    if args.launch_list:
+        for _ in range(args.warmup + args.steps):
+            step.run()
+        torch.cuda.synchronize(dev)
+        print(json.dumps({"launch_list": True, "steps": args.steps, "warmup": args.warmup}))
+        return
     h2d = sum(x.numel() * x.element_size() for x in host[0][0]) + host[0][1].numel() * host[0][1].element_size()
 
     def barrier():

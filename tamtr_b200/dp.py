@@ -123,7 +123,10 @@ class HeadTrainStep:
     loss_fn    : maps the module's outputs to a scalar
     example    : tuple of example inputs (tensors / CdnPlan / None) fixing every shape
     autocast   : torch dtype or None
-    use_graph  : capture forward+backward into a CUDA graph (CUDA only)
+    use_graph  : capture forward+backward into a CUDA graph (CUDA only).  As for any whole-network capture, eager
+                 forward/backward passes of the SAME module instance done earlier in the process must have run on a
+                 side stream (autograd's gradient accumulators remember the stream of their first use); the warm-up
+                 here does.
     """
 
     def __init__(self, module, loss_fn, example, autocast=None, use_graph=True, warmup=3, fused_param_cast=True):
