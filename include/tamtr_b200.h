@@ -156,6 +156,21 @@ int tamtr_max_sigmoid_forward(const void *embed, const float *guide, const float
 int tamtr_max_sigmoid_tc_forward(const void *embed_bf16, const float *guide, const float *bias, float *aw,
                                  uint8_t *amax, int B, int nh, int hc, int HW, int N, void *stream);
 
+/* The gated 3x3 projection of the same block (ultralytics/nn/extra_modules/block.py:222-225: proj_conv = Conv2d 3x3 pad 1
+ * + BatchNorm2d, then `x * aw.unsqueeze(2)`) as ONE tensor-core kernel: implicit GEMM (M = pixels, N = Cout, K = 9*Cin),
+ * tcgen05.mma with TMEM accumulators, TMA boxes whose out-of-bounds zero fill is the conv padding, epilogue
+ *   y[b,h,w,co] = (conv[b,h,w,co] * bn_scale[co] + bn_shift[co]) * gate[b, co / (Cout/nh), h, w]     (gate may be NULL).
+ * Channels-last operands: x [B,H,W,Cin] bf16, w [Cout,3,3,Cin] bf16 (= weight.permute(0,2,3,1)), y [B,H,W,Cout] bf16,
+ * gate f32 [B,nh,H,W] (the `aw` of tamtr_max_sigmoid_*_forward), bn_scale/bn_shift f32 [Cout] (the BatchNorm affine:
+ * gamma*rstd, beta - mean*gamma*rstd).  Cin % 64 == 0, Cout % 32 == 0, Cout <= 256, (Cout/nh) % 32 == 0. */
+int tamtr_gate_conv3x3_tc_forward(const void *x_nhwc, const void *w_ohwi, const float *bn_scale, const float *bn_shift,
+                                  const float *gate, void *y_nhwc, int B, int H, int W, int Cin, int Cout, int nh,
+                                  void *stream);
+
+/* [B, C, HW] -> [B, HW, C] (f32 | bf16): the layout change in front of the channels-last tensor-core kernel when the
+ * caller holds NCHW maps (the reference's layout). */
+int tamtr_nchw_to_nhwc(const void *x, void *y, int dtype, int B, int C, int HW, void *stream);
+
 /* grad_embed [B, nh*hc, HW] (dtype of embed, fully written: the gate's contribution only);
  * grad_guide [B, N, nh, hc] f32 and grad_bias [nh] f32 are zeroed by the call, then accumulated. */
 int tamtr_max_sigmoid_backward(const float *grad_aw, const float *aw, const uint8_t *amax, const void *embed,

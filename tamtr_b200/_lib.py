@@ -44,6 +44,8 @@ _SIGNATURES = {
     "tamtr_affine_rows": (ctypes.c_int, [_vp, _vp, _vp, _fp, _fp, _fp] + [_i] * 5 + [_vp, _vp]),
     "tamtr_rank_tokens": (ctypes.c_int, [_vp, _fp, _fp, _vp, _fp, _fp, _fp, _fp] + [_i] * 6 + [ctypes.c_float, _vp]),
     "tamtr_max_sigmoid_tc_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _vp] + [_i] * 5 + [_vp]),
+    "tamtr_gate_conv3x3_tc_forward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _fp, _vp] + [_i] * 6 + [_vp]),
+    "tamtr_nchw_to_nhwc": (ctypes.c_int, [_vp, _vp] + [_i] * 4 + [_vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }
 

@@ -273,5 +273,15 @@ class MaxSigmoidAttnBlock(nn.Module):
         embed = self.ec(x) if self.ec is not None else x
         aw = ops.max_sigmoid_gate(embed, guide, self.bias, self.nh)          # [B, nh, H, W]
         aw = aw * self.scale
-        y = self.proj_conv(x).view(bs, self.nh, -1, h, w)
-        return (y * aw.unsqueeze(2).to(y.dtype)).view(bs, -1, h, w)
+        pc = self.proj_conv
+        if ops.gate_conv3x3_supported(x, pc.conv.weight, self.nh):
+            bn = pc.bn
+            if not (self.training or torch.is_grad_enabled()) and bn.running_var is not None:
+                # inference: conv + folded BatchNorm + gate in one tensor-core kernel (channels-last output)
+                s = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+                t = bn.bias.float() - bn.running_mean.float() * s
+                return ops.gate_conv3x3(x, pc.conv.weight, s, t, aw, self.nh)
+            y = bn(ops.conv3x3_tc(x, pc.conv.weight))
+        else:
+            y = pc(x)
+        return (y.view(bs, self.nh, -1, h, w) * aw.unsqueeze(2).to(y.dtype)).view(bs, -1, h, w)

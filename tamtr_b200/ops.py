@@ -445,6 +445,85 @@ def max_sigmoid_gate(embed, guide, bias, nh, use_tensor_cores=None):
     return _MaxSigmoidFn.apply(embed, guide, bias, nh, use_tensor_cores)
 
 
+def to_channels_last(x):
+    """[B, C, H, W] -> the same logical tensor in channels-last memory ([B, H, W, C] storage).  No copy when the caller
+    already holds channels-last maps; otherwise one pass of tamtr_nchw_to_nhwc."""
+    _lib.require_cuda(x)
+    B, C, H, W = x.shape
+    if x.permute(0, 2, 3, 1).is_contiguous():
+        return x
+    x = x.contiguous()
+    out = torch.empty((B, H, W, C), dtype=x.dtype, device=x.device)
+    with _with_device(x):
+        _lib.check(_lib.lib().tamtr_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), _lib.dtype_code(x), B, C, H * W,
+                                                 _lib.stream_ptr(x.device)), "nchw_to_nhwc")
+    return out.permute(0, 3, 1, 2)
+
+
+def gate_conv3x3_supported(x, weight, nh):
+    co, ci, kh, kw = weight.shape
+    return (x.is_cuda and x.dtype == torch.bfloat16 and kh == 3 and kw == 3 and ci % 64 == 0 and co % 32 == 0
+            and 32 <= co <= 256 and co % nh == 0 and (co // nh) % 32 == 0)
+
+
+def _gate_conv3x3_launch(x, weight, bn_scale, bn_shift, gate, nh):
+    B, Ci, H, W = x.shape
+    Co = weight.shape[0]
+    x_cl = to_channels_last(x)                                        # storage [B, H, W, Ci]
+    w_ohwi = weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    s32 = bn_scale.detach().float().contiguous()
+    t32 = bn_shift.detach().float().contiguous()
+    g32 = None if gate is None else gate.detach().float().contiguous()
+    y = torch.empty((B, H, W, Co), dtype=torch.bfloat16, device=x.device)
+    with _with_device(x):
+        rc = _lib.lib().tamtr_gate_conv3x3_tc_forward(x_cl.data_ptr(), w_ohwi.data_ptr(), s32.data_ptr(), t32.data_ptr(),
+                                                      None if g32 is None else g32.data_ptr(), y.data_ptr(), B, H, W,
+                                                      Ci, Co, nh, _lib.stream_ptr(x.device))
+    _lib.check(rc, "gate_conv3x3_tc_forward")
+    return x_cl, y.permute(0, 3, 1, 2)                                # logical [B, Co, H, W], channels-last memory
+
+
+def gate_conv3x3(x, weight, bn_scale, bn_shift, gate, nh):
+    """extra_modules/block.py:222-225 with BatchNorm folded to an affine: (conv3x3(x) * bn_scale + bn_shift) * gate,
+    one tcgen05 kernel (csrc/gateconv_tc.cu).  x [B,Ci,H,W] bf16 (NCHW or channels-last), weight [Co,Ci,3,3],
+    gate [B,nh,H,W] or None -> [B,Co,H,W] bf16 in channels-last memory.  Inference path: no autograd."""
+    _lib.require_cuda(x, weight, bn_scale, bn_shift, gate)
+    if not gate_conv3x3_supported(x, weight, nh):
+        raise RuntimeError("tamtr_b200: gate_conv3x3 needs bf16 activations, a 3x3 kernel, Cin % 64 == 0, "
+                           "Cout % 32 == 0, Cout <= 256 and (Cout / nh) % 32 == 0")
+    return _gate_conv3x3_launch(x, weight, bn_scale, bn_shift, gate, nh)[1]
+
+
+class _Conv3x3TcFn(torch.autograd.Function):
+    """The raw 3x3 convolution (stride 1, pad 1, no bias) on the tcgen05 kernel; dgrad / wgrad are library calls."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        co = weight.shape[0]
+        one = torch.ones(co, dtype=torch.float32, device=x.device)
+        x_cl, y = _gate_conv3x3_launch(x, weight, one, torch.zeros_like(one), None, 1)
+        ctx.save_for_backward(x_cl, weight)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x_cl, weight = ctx.saved_tensors
+        gx, gw, _ = torch.ops.aten.convolution_backward(
+            gy.to(x_cl.dtype), x_cl, weight.to(x_cl.dtype), None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        return gx, None if gw is None else gw.to(weight.dtype)
+
+
+def conv3x3_tc(x, weight):
+    """Conv2d(k=3, s=1, p=1, bias=False) of `proj_conv` for bf16 activations (training path: BatchNorm statistics and
+    the gate multiply stay outside)."""
+    _lib.require_cuda(x, weight)
+    if not gate_conv3x3_supported(x, weight, 1):
+        raise RuntimeError("tamtr_b200: conv3x3_tc needs bf16 activations, Cin % 64 == 0, Cout % 32 == 0, Cout <= 256")
+    return _Conv3x3TcFn.apply(x, weight)
+
+
 # ------------------------------------------------------------------------------------ sparse-gradient plumbing
 class GradHub:
     """Collects row-sparse gradients for one activation so that they are added IN PLACE to the dense gradient that
