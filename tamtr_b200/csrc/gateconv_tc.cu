@@ -9,35 +9,45 @@
 // at C = 256, far above the ridge.  Layout: activations channels-last ([B, H, W, C] bf16), weights [Cout, 3, 3, Cin]
 // bf16, so both UMMA operands are K-major and every smem row is one pixel's (one filter's) 64-channel slice = 128 B.
 //
-// CTA tile = 256 output pixels (a TW x 256/TW patch of one image) x all Cout channels, as two M=128 halves whose
-// fp32 accumulators fill TMEM (2 x 256 columns).  K loop = 9 taps x Cin/64 blocks.  Per K block:
-//   warp 0   TMA producer : ONE cp.async.bulk.tensor.4d box (64 ch, TW, 256/TW, 1) at (c0, x0+dx-1, y0+dy-1, b) -- the
-//                           halo is the tensor map's out-of-bounds zero fill, there is no im2col buffer and no padding
-//                           branch -- plus one 2-D box (64, Cout) of the weights; 128B swizzle; 3-stage 64 KB ring
-//   warp 1   MMA issuer   : 2 halves x 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=Cout, K=16), the weight tile in
-//                           shared memory is read by both halves (so smem fill traffic per flop is that of a 256x256 tile)
+// CTA tile = 256 output pixels (a TW x TH patch of one image, TW*TH = 256) x all Cout channels, as two M=128 halves
+// whose fp32 accumulators fill TMEM (2 x 256 columns).  K loop = Cin/64 channel blocks x 3 column taps x 3 row taps.
+//   warp 0   TMA producer : per (channel block, dx) ONE cp.async.bulk.tensor.4d box (64 ch, TW, TH+2, 1) at
+//                           (c0, x0+dx-1, y0-1, b): the patch with its two halo rows.  The halo and the image border
+//                           are the tensor map's out-of-bounds zero fill -- no im2col buffer, no padding branch.  The
+//                           three row taps dy of that dx are the SAME shared-memory buffer read at a start address
+//                           shifted by dy*TW rows (a multiple of the 1024-byte swizzle atom), so x leaves L2 3.4 times
+//                           instead of 9 (the kernel is L2->SM bound otherwise: first version, 64 KB per K block,
+//                           ran at 82 % of the measured ~6300 B/clk L2 cap with the tensor pipe 54 % busy).
+//                           Per K block one 2-D box (64, Cout) of the weights.  128B swizzle; 3 A slots + 3 B stages.
+//   warp 1   MMA issuer   : 2 halves x 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=Cout, K=16); the weight tile in
+//                           shared memory is read by both halves
 //   warps 2-9 epilogue    : tcgen05.ld 32 lanes x 32 columns, y = (acc*s + t) * gate, bf16 pack, 16-byte stores
 //                           (each thread owns one pixel = one contiguous Cout*2-byte row of the channels-last output)
+#include <stdlib.h>
+
 #include "tc_ptx.cuh"
 
 namespace tamtr {
 
-constexpr int kCvStages = 3;
+constexpr int kCvStages = 3;                         // weight (B) stages
+constexpr int kCvASlots = 3;                         // activation (A) slots: one (channel block, dx) patch each
 constexpr int kCvKBlk = 64;                          // channels per K block: 64 bf16 = one 128-byte swizzled row
 constexpr int kCvTilePix = 256;                      // output pixels per CTA tile (two UMMA M=128 halves)
-constexpr int kCvABytes = kCvTilePix * kCvKBlk * 2;  // 32 KB
+constexpr int kCvABytes = 40 * 1024;                 // TW*(TH+2) rows of 128 B: 272 / 288 / 320 rows for TW = 8/16/32
 constexpr int kCvMaxCout = 256;
 constexpr int kCvBBytes = kCvMaxCout * kCvKBlk * 2;  // 32 KB
 constexpr int kCvThreads = 320;                      // producer warp, MMA warp, 8 epilogue warps
 constexpr int kCvTmemCols = 512;
 
 struct CvSmem {
-    alignas(1024) uint8_t a[kCvStages][kCvABytes];
+    alignas(1024) uint8_t a[kCvASlots][kCvABytes];
     alignas(1024) uint8_t b[kCvStages][kCvBBytes];
     alignas(16) float scale[kCvMaxCout];
     alignas(16) float shift[kCvMaxCout];
     alignas(8) uint64_t full[kCvStages];
     uint64_t empty[kCvStages];
+    uint64_t a_full[kCvASlots];
+    uint64_t a_empty[kCvASlots];
     uint64_t acc_full;
     uint64_t acc_empty;
     uint32_t tmem_base;
@@ -61,6 +71,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// One accumulator row (= one output pixel, Cout channels) from TMEM: y = (acc * s + t) * gate[head], packed to bf16 and
+// written as 16-byte vectors into the pixel's contiguous channels-last row.
+__device__ __forceinline__ void epilogue_row(uint32_t taddr, __nv_bfloat16 *dst, const float *gate_px, const float *scale,
+                                             const float *shift, int Cout, int hc, size_t HW, bool live) {
+    for (int c0 = 0; c0 < Cout; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        float gt = 1.0f;
+        if (gate_px != nullptr && live) gt = __ldg(gate_px + (size_t)(c0 / hc) * HW);
+        uint4 o[4];
+        uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = *reinterpret_cast<const float4 *>(&scale[c0 + j]);
+            const float4 t4 = *reinterpret_cast<const float4 *>(&shift[c0 + j]);
+            const float f0 = fmaf(__uint_as_float(v[j + 0]), s4.x, t4.x) * gt;
+            const float f1 = fmaf(__uint_as_float(v[j + 1]), s4.y, t4.y) * gt;
+            const float f2 = fmaf(__uint_as_float(v[j + 2]), s4.z, t4.z) * gt;
+            const float f3 = fmaf(__uint_as_float(v[j + 3]), s4.w, t4.w) * gt;
+            __nv_bfloat162 lo = __floats2bfloat162_rn(f0, f1), hi = __floats2bfloat162_rn(f2, f3);
+            ow[j / 2] = *reinterpret_cast<uint32_t *>(&lo);
+            ow[j / 2 + 1] = *reinterpret_cast<uint32_t *>(&hi);
+        }
+        if (live) {
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d4[q] = o[q];
+        }
+    }
+}
+
 struct CvGeom {
     int B, H, W, Cin, Cout, nh;
     int TW, TH;            // tile = TW x TH pixels, TW * TH = 256, TW a power of two
@@ -77,11 +118,12 @@ gate_conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int tiles_img = g.tiles_x * g.tiles_y;
     const int n_tiles = g.B * tiles_img;
     const int kc_per_tap = g.Cin / kCvKBlk;
-    const int n_kb = 9 * kc_per_tap;
-    const uint32_t stage_bytes = (uint32_t)kCvABytes + (uint32_t)g.Cout * kCvKBlk * 2;
+    const uint32_t a_bytes = (uint32_t)g.TW * (g.TH + 2) * kCvKBlk * 2;
+    const uint32_t b_bytes = (uint32_t)g.Cout * kCvKBlk * 2;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kCvStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        for (int s = 0; s < kCvASlots; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], 1); }
         mbar_init(&sm.acc_full, 1);
         mbar_init(&sm.acc_empty, kCvThreads - 64);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -103,18 +145,22 @@ gate_conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     if (warp == 0) {
         // ===== TMA producer
         if (lane == 0) {
-            uint32_t kbg = 0;
+            uint32_t kbg = 0, an = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int b = t / tiles_img, r = t - b * tiles_img;
                 const int x0 = (r % g.tiles_x) * g.TW, y0 = (r / g.tiles_x) * g.TH;
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                    for (int kc = 0; kc < kc_per_tap; ++kc, ++kbg) {
-                        const int s = kbg % kCvStages;
-                        mbar_wait(&sm.empty[s], ((kbg / kCvStages) & 1) ^ 1);
-                        mbar_expect_tx(&sm.full[s], stage_bytes);
-                        tma_load_4d(sm.a[s], &tmap_x, &sm.full[s], kc * kCvKBlk, x0 + dx, y0 + dy, b);
-                        tma_load_2d(sm.b[s], &tmap_w, &sm.full[s], tap * g.Cin + kc * kCvKBlk, 0);
+                for (int kc = 0; kc < kc_per_tap; ++kc) {
+                    for (int dxi = 0; dxi < 3; ++dxi, ++an) {
+                        const int slot = an % kCvASlots;
+                        mbar_wait(&sm.a_empty[slot], ((an / kCvASlots) & 1) ^ 1);
+                        mbar_expect_tx(&sm.a_full[slot], a_bytes);
+                        tma_load_4d(sm.a[slot], &tmap_x, &sm.a_full[slot], kc * kCvKBlk, x0 + dxi - 1, y0 - 1, b);
+                        for (int dyi = 0; dyi < 3; ++dyi, ++kbg) {
+                            const int s = kbg % kCvStages;
+                            mbar_wait(&sm.empty[s], ((kbg / kCvStages) & 1) ^ 1);
+                            mbar_expect_tx(&sm.full[s], b_bytes);
+                            tma_load_2d(sm.b[s], &tmap_w, &sm.full[s], (dyi * 3 + dxi) * g.Cin + kc * kCvKBlk, 0);
+                        }
                     }
                 }
             }
@@ -124,24 +170,31 @@ gate_conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         if (lane == 0) {
             // instruction descriptor: D = f32, A = B = bf16, both K-major, N = Cout, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.Cout >> 3) << 17) | ((128u >> 4) << 24);
-            uint32_t kbg = 0;
+            uint32_t kbg = 0, an = 0;
             int it = 0;
+            const uint32_t row_shift = (uint32_t)g.TW * 128;          // one image row of the patch, in bytes
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
                 mbar_wait(&sm.acc_empty, (it & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kb = 0; kb < n_kb; ++kb, ++kbg) {
-                    const int s = kbg % kCvStages;
-                    mbar_wait(&sm.full[s], (kbg / kCvStages) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_u32(sm.a[s]), b_addr = smem_u32(sm.b[s]);
+                for (int ks = 0; ks < 3 * kc_per_tap; ++ks, ++an) {   // (channel block, dx) patches
+                    const int slot = an % kCvASlots;
+                    mbar_wait(&sm.a_full[slot], (an / kCvASlots) & 1);
+                    const uint32_t a_slot = smem_u32(sm.a[slot]);
+                    for (int dyi = 0; dyi < 3; ++dyi, ++kbg) {
+                        const int s = kbg % kCvStages;
+                        mbar_wait(&sm.full[s], (kbg / kCvStages) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_addr = a_slot + dyi * row_shift, b_addr = smem_u32(sm.b[s]);
 #pragma unroll
-                    for (int k = 0; k < kCvKBlk / 16; ++k) {
-                        const uint64_t bd = make_desc_k128(b_addr + k * 32);
-                        const uint32_t acc = (kb | k) ? 1u : 0u;
-                        umma_f16(tmem_base, make_desc_k128(a_addr + k * 32), bd, idesc, acc);
-                        umma_f16(tmem_base + kCvMaxCout, make_desc_k128(a_addr + kCvABytes / 2 + k * 32), bd, idesc, acc);
+                        for (int k = 0; k < kCvKBlk / 16; ++k) {
+                            const uint64_t bd = make_desc_k128(b_addr + k * 32);
+                            const uint32_t acc = (ks | dyi | k) ? 1u : 0u;
+                            umma_f16(tmem_base, make_desc_k128(a_addr + k * 32), bd, idesc, acc);
+                            umma_f16(tmem_base + kCvMaxCout, make_desc_k128(a_addr + 128 * 128 + k * 32), bd, idesc, acc);
+                        }
+                        umma_commit(&sm.empty[s]);
                     }
-                    umma_commit(&sm.empty[s]);
+                    umma_commit(&sm.a_empty[slot]);
                 }
                 umma_commit(&sm.acc_full);
             }
@@ -163,31 +216,8 @@ gate_conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * kCvMaxCout;
             __nv_bfloat16 *dst = y + ((size_t)b * HW + pix) * g.Cout;
-            for (int c0 = 0; c0 < g.Cout; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                float gt = 1.0f;
-                if (gate != nullptr && live) gt = __ldg(gate + ((size_t)b * g.nh + c0 / hc) * HW + pix);
-                uint4 o[4];
-                uint32_t *ow = reinterpret_cast<uint32_t *>(o);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 s4 = *reinterpret_cast<const float4 *>(&sm.scale[c0 + j]);
-                    const float4 t4 = *reinterpret_cast<const float4 *>(&sm.shift[c0 + j]);
-                    const float f0 = fmaf(__uint_as_float(v[j + 0]), s4.x, t4.x) * gt;
-                    const float f1 = fmaf(__uint_as_float(v[j + 1]), s4.y, t4.y) * gt;
-                    const float f2 = fmaf(__uint_as_float(v[j + 2]), s4.z, t4.z) * gt;
-                    const float f3 = fmaf(__uint_as_float(v[j + 3]), s4.w, t4.w) * gt;
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(f0, f1), hi = __floats2bfloat162_rn(f2, f3);
-                    ow[j / 2] = *reinterpret_cast<uint32_t *>(&lo);
-                    ow[j / 2 + 1] = *reinterpret_cast<uint32_t *>(&hi);
-                }
-                if (live) {
-                    uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) d4[q] = o[q];
-                }
-            }
+            const float *gate_px = gate == nullptr ? nullptr : gate + (size_t)b * g.nh * HW + pix;
+            epilogue_row(taddr, dst, gate_px, sm.scale, sm.shift, g.Cout, hc, HW, live);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&sm.acc_empty);
         }
@@ -196,6 +226,216 @@ gate_conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCvTmemCols));
+    }
+}
+
+
+// ===================================================================================================================
+// CTA-pair version (cta_group::2).  ncu on the single-CTA kernel above: every tcgen05.mma (M=128, N=256, K=16) takes
+// ~198 clk instead of 128 -- it fetches 12 KB of operands from shared memory per instruction, and the operand fetch
+// runs at ~64 B/clk/SM (tensor pipe 64.7 % of active cycles, exactly that ratio).  With two SMs on one M=256 x N=256
+// tile each CTA supplies its own 128 pixel rows of A and only HALF of the weight tile (N/2 rows), i.e. 8 KB per
+// instruction -> the fetch matches the 128-clk MMA.  Each CTA's TMEM holds its 128 rows x 256 columns, double-buffered
+// (2 x 256 columns), so the epilogue of tile i overlaps the main loop of tile i+1.
+//   per CTA: warp 0 TMA producer (its own pixel rows + its half of the weights, completion signalled on the LEADER's
+//   mbarriers), warp 1 TMEM allocation (+ MMA issue in the leader CTA only; tcgen05.commit multicast to both CTAs),
+//   warps 2-5 epilogue of the CTA's own 128 pixels.
+constexpr int kPrASlots = 4;
+constexpr int kPrABytes = 24 * 1024;                 // TW*(128/TW+2) rows of 128 B: 144 / 160 / 192 rows for TW = 8/16/32
+constexpr int kPrBStages = 6;
+constexpr int kPrBBytes = (kCvMaxCout / 2) * kCvKBlk * 2;   // 16 KB: this CTA's half of the weight tile
+constexpr int kPrThreads = 192;
+constexpr int kPrAccStages = 2;
+
+struct PrSmem {
+    alignas(1024) uint8_t a[kPrASlots][kPrABytes];
+    alignas(1024) uint8_t b[kPrBStages][kPrBBytes];
+    alignas(16) float scale[kCvMaxCout];
+    alignas(16) float shift[kCvMaxCout];
+    alignas(8) uint64_t b_full[kPrBStages];
+    uint64_t b_empty[kPrBStages];
+    uint64_t a_full[kPrASlots];
+    uint64_t a_empty[kPrASlots];
+    uint64_t acc_full[kPrAccStages];
+    uint64_t acc_empty[kPrAccStages];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void *dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1,
+                                             int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void *dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in BOTH CTAs of the pair once all prior MMAs have completed
+__device__ __forceinline__ void umma2_commit_both(uint64_t *bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPrThreads, 1)
+gate_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                         const float *__restrict__ bn_scale, const float *__restrict__ bn_shift,
+                         const float *__restrict__ gate, __nv_bfloat16 *__restrict__ y, const CvGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    PrSmem &sm = *reinterpret_cast<PrSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int tiles_img = g.tiles_x * g.tiles_y;
+    const int n_tiles = g.B * tiles_img;
+    const int kc_per_tap = g.Cin / kCvKBlk;
+    const int THc = g.TH / 2;                         // image rows of the pair tile owned by one CTA (TW * THc = 128)
+    const uint32_t a_bytes = (uint32_t)g.TW * (THc + 2) * kCvKBlk * 2;
+    const uint32_t b_bytes = (uint32_t)(g.Cout / 2) * kCvKBlk * 2;
+
+    if (threadIdx.x == 0) {
+        // full barriers live in the leader: ONE arrival (the leader's expect_tx of both CTAs' bytes); the peer's TMA only
+        // contributes complete_tx (a remote arrive per stage costs the peer producer a MEMBAR: measured 3.4x slower)
+        for (int s = 0; s < kPrBStages; ++s) { mbar_init(&sm.b_full[s], 1); mbar_init(&sm.b_empty[s], 1); }
+        for (int s = 0; s < kPrASlots; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], 1); }
+        for (int s = 0; s < kPrAccStages; ++s) { mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.acc_empty[s], 2 * 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
+                     "n"(kCvTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    for (int c = threadIdx.x; c < g.Cout; c += kPrThreads) {
+        sm.scale[c] = __ldg(bn_scale + c);
+        sm.shift[c] = __ldg(bn_shift + c);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                               // the peer's mbarriers exist before anything signals them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own pixel rows, own half of the weight rows; completion -> leader's barriers
+        if (lane == 0) {
+            uint32_t kbg = 0, an = 0;
+            for (int t = pair; t < n_tiles; t += n_pairs) {
+                const int b = t / tiles_img, r = t - b * tiles_img;
+                const int x0 = (r % g.tiles_x) * g.TW, y0 = (r / g.tiles_x) * g.TH + (int)rank * THc;
+                for (int kc = 0; kc < kc_per_tap; ++kc) {
+                    for (int dxi = 0; dxi < 3; ++dxi, ++an) {
+                        const int slot = an % kPrASlots;
+                        mbar_wait(&sm.a_empty[slot], ((an / kPrASlots) & 1) ^ 1);
+                        const uint32_t abar = map_to_cta(&sm.a_full[slot], 0);
+                        if (rank == 0) mbar_expect_tx(&sm.a_full[slot], 2 * a_bytes);
+                        tma2_load_4d(sm.a[slot], &tmap_x, abar, kc * kCvKBlk, x0 + dxi - 1, y0 - 1, b);
+                        for (int dyi = 0; dyi < 3; ++dyi, ++kbg) {
+                            const int s = kbg % kPrBStages;
+                            mbar_wait(&sm.b_empty[s], ((kbg / kPrBStages) & 1) ^ 1);
+                            const uint32_t bbar = map_to_cta(&sm.b_full[s], 0);
+                            if (rank == 0) mbar_expect_tx(&sm.b_full[s], 2 * b_bytes);
+                            tma2_load_2d(sm.b[s], &tmap_w, bbar, (dyi * 3 + dxi) * g.Cin + kc * kCvKBlk,
+                                         (int)rank * (g.Cout / 2));
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: leader CTA only, one lane
+        if (rank == 0 && lane == 0) {
+            // instruction descriptor: D = f32, A = B = bf16, both K-major, N = Cout, M = 256 (128 rows per CTA)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.Cout >> 3) << 17) | ((256u >> 4) << 24);
+            uint32_t kbg = 0, an = 0;
+            int it = 0;
+            const uint32_t row_shift = (uint32_t)g.TW * 128;
+            for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
+                const int as = it % kPrAccStages;
+                mbar_wait(&sm.acc_empty[as], ((it / kPrAccStages) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_base + as * kCvMaxCout;
+                for (int ks = 0; ks < 3 * kc_per_tap; ++ks, ++an) {
+                    const int slot = an % kPrASlots;
+                    mbar_wait(&sm.a_full[slot], (an / kPrASlots) & 1);
+                    const uint32_t a_slot = smem_u32(sm.a[slot]);
+                    for (int dyi = 0; dyi < 3; ++dyi, ++kbg) {
+                        const int s = kbg % kPrBStages;
+                        mbar_wait(&sm.b_full[s], (kbg / kPrBStages) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_addr = a_slot + dyi * row_shift, b_addr = smem_u32(sm.b[s]);
+#pragma unroll
+                        for (int k = 0; k < kCvKBlk / 16; ++k)
+                            umma2_f16(d, make_desc_k128(a_addr + k * 32), make_desc_k128(b_addr + k * 32), idesc,
+                                      (ks | dyi | k) ? 1u : 0u);
+                        umma2_commit_both(&sm.b_empty[s]);
+                    }
+                    umma2_commit_both(&sm.a_empty[slot]);
+                }
+                umma2_commit_both(&sm.acc_full[as]);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): warp w owns TMEM lanes 32*(w%4).. = pixels of this CTA's half of the pair tile
+        const int quarter = warp & 3;
+        const int p = quarter * 32 + lane;
+        const int px_in = p & (g.TW - 1), py_in = p / g.TW + (int)rank * THc;
+        const int hc = g.Cout / g.nh;
+        const size_t HW = (size_t)g.H * g.W;
+        int it = 0;
+        for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
+            const int as = it % kPrAccStages;
+            const int b = t / tiles_img, r = t - b * tiles_img;
+            const int px = (r % g.tiles_x) * g.TW + px_in, py = (r / g.tiles_x) * g.TH + py_in;
+            const bool live = px < g.W && py < g.H;
+            const size_t pix = (size_t)py * g.W + px;
+            mbar_wait(&sm.acc_full[as], (it / kPrAccStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kCvMaxCout;
+            __nv_bfloat16 *dst = y + ((size_t)b * HW + pix) * g.Cout;
+            const float *gate_px = gate == nullptr ? nullptr : gate + (size_t)b * g.nh * HW + pix;
+            epilogue_row(taddr, dst, gate_px, sm.scale, sm.shift, g.Cout, hc, HW, live);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_cta(&sm.acc_empty[as], 0));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                               // nobody leaves while the pair's MMAs / multicast arrives can touch it
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCvTmemCols));
     }
 }
 
@@ -279,11 +519,15 @@ extern "C" int tamtr_gate_conv3x3_tc_forward(const void *x_nhwc, const void *w_o
     g.tiles_x = (W + g.TW - 1) / g.TW;
     g.tiles_y = (H + g.TH - 1) / g.TH;
 
+    // Two SMs per tile (cta_group::2) unless the debug override TAMTR_GATECONV_SINGLE_CTA=1 asks for the single-CTA kernel.
+    static const bool single = [] { const char *e = getenv("TAMTR_GATECONV_SINGLE_CTA"); return e && e[0] == '1'; }();
+    const int box_rows = single ? g.TH + 2 : g.TH / 2 + 2;     // image rows per activation box (with the two halo rows)
+    const int box_cout = single ? Cout : Cout / 2;             // weight rows per CTA
     CUtensorMap tmap_x, tmap_w;
     {
         const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-        const cuuint32_t box[4] = {(cuuint32_t)kCvKBlk, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)kCvKBlk, (cuuint32_t)g.TW, (cuuint32_t)box_rows, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         const CUresult cr = encode(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(x_nhwc), dims, strides,
                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -293,7 +537,7 @@ extern "C" int tamtr_gate_conv3x3_tc_forward(const void *x_nhwc, const void *w_o
     {
         const cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
         const cuuint64_t strides[1] = {(cuuint64_t)9 * Cin * 2};
-        const cuuint32_t box[2] = {(cuuint32_t)kCvKBlk, (cuuint32_t)Cout};
+        const cuuint32_t box[2] = {(cuuint32_t)kCvKBlk, (cuuint32_t)box_cout};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult cr = encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(w_ohwi), dims, strides,
                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -304,20 +548,28 @@ extern "C" int tamtr_gate_conv3x3_tc_forward(const void *x_nhwc, const void *w_o
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
     const long n_tiles = (long)B * g.tiles_x * g.tiles_y;
-    // persistent CTAs, one per SM; equalise the number of tiles per CTA so the last wave is not ragged
-    const long waves = (n_tiles + n_sm - 1) / n_sm;
-    const int grid = (int)((n_tiles + waves - 1) / waves);
-    const size_t smem = sizeof(CvSmem) + 1024;
+    // persistent CTAs (single) / CTA pairs, one per SM; equalise the number of tiles each walks so the last wave is
+    // not ragged
+    const long workers = single ? n_sm : n_sm / 2;
+    const long waves = (n_tiles + workers - 1) / workers;
+    const int n_work = (int)((n_tiles + waves - 1) / waves);
+    cudaStream_t st = (cudaStream_t)stream;
     static bool attr_set = false;
     if (!attr_set) {
-        TAMTR_CUDA_OK(cudaFuncSetAttribute(gate_conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TAMTR_CUDA_OK(cudaFuncSetAttribute(gate_conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(CvSmem) + 1024)));
+        TAMTR_CUDA_OK(cudaFuncSetAttribute(gate_conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(PrSmem) + 1024)));
         attr_set = true;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     {
         KernelTimer timer(K_GATE_CONV_TC, st);
-        gate_conv3x3_tc_kernel<<<grid, kCvThreads, smem, st>>>(tmap_x, tmap_w, bn_scale, bn_shift, gate,
-                                                               (__nv_bfloat16 *)y_nhwc, g);
+        if (single)
+            gate_conv3x3_tc_kernel<<<n_work, kCvThreads, sizeof(CvSmem) + 1024, st>>>(
+                tmap_x, tmap_w, bn_scale, bn_shift, gate, (__nv_bfloat16 *)y_nhwc, g);
+        else
+            gate_conv3x3_pair_kernel<<<2 * n_work, kPrThreads, sizeof(PrSmem) + 1024, st>>>(
+                tmap_x, tmap_w, bn_scale, bn_shift, gate, (__nv_bfloat16 *)y_nhwc, g);
     }
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
