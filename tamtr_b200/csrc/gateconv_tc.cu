@@ -58,6 +58,22 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t addr) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// The same descriptor split into its 32-bit halves: only the low word (start address >> 4, LBO) changes between MMAs,
+// so the issue loop adds small constants to it instead of rebuilding 64-bit values (the single issuing thread's
+// instruction count is what bounds the MMA rate once the operands are in place).
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return (addr >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_of(uint32_t lo) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi));
+    return d;
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -106,6 +122,7 @@ struct CvGeom {
     int B, H, W, Cin, Cout, nh;
     int TW, TH;            // tile = TW x TH pixels, TW * TH = 256, TW a power of two
     int tiles_x, tiles_y;  // per image
+    int debug;             // timing experiments only (TAMTR_GATECONV_DEBUG): bit 0 = epilogue does not store
 };
 
 __global__ void __launch_bounds__(kCvThreads, 1)
@@ -166,37 +183,42 @@ gate_conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp walks the loop (uniform control flow and registers), one elected lane issues
+        {
             // instruction descriptor: D = f32, A = B = bf16, both K-major, N = Cout, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.Cout >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a_lo0 = desc_lo(smem_u32(sm.a[0])), b_lo0 = desc_lo(smem_u32(sm.b[0]));
+            const uint32_t row_shift = (uint32_t)g.TW * 128 >> 4;     // one image row of the patch, in descriptor units
             uint32_t kbg = 0, an = 0;
             int it = 0;
-            const uint32_t row_shift = (uint32_t)g.TW * 128;          // one image row of the patch, in bytes
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
                 mbar_wait(&sm.acc_empty, (it & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int ks = 0; ks < 3 * kc_per_tap; ++ks, ++an) {   // (channel block, dx) patches
                     const int slot = an % kCvASlots;
                     mbar_wait(&sm.a_full[slot], (an / kCvASlots) & 1);
-                    const uint32_t a_slot = smem_u32(sm.a[slot]);
-                    for (int dyi = 0; dyi < 3; ++dyi, ++kbg) {
+                    uint32_t a_lo = a_lo0 + slot * (kCvABytes >> 4);
+                    for (int dyi = 0; dyi < 3; ++dyi, ++kbg, a_lo += row_shift) {
                         const int s = kbg % kCvStages;
                         mbar_wait(&sm.full[s], (kbg / kCvStages) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_addr = a_slot + dyi * row_shift, b_addr = smem_u32(sm.b[s]);
+                        const uint32_t b_lo = b_lo0 + s * (kCvBBytes >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < kCvKBlk / 16; ++k) {
-                            const uint64_t bd = make_desc_k128(b_addr + k * 32);
-                            const uint32_t acc = (ks | dyi | k) ? 1u : 0u;
-                            umma_f16(tmem_base, make_desc_k128(a_addr + k * 32), bd, idesc, acc);
-                            umma_f16(tmem_base + kCvMaxCout, make_desc_k128(a_addr + 128 * 128 + k * 32), bd, idesc, acc);
+                            for (int k = 0; k < kCvKBlk / 16; ++k) {
+                                const uint64_t bd = desc_of(b_lo + 2 * k);
+                                const uint32_t acc = (ks | dyi | k) ? 1u : 0u;
+                                umma_f16(tmem_base, desc_of(a_lo + 2 * k), bd, idesc, acc);
+                                umma_f16(tmem_base + kCvMaxCout, desc_of(a_lo + (128 * 128 >> 4) + 2 * k), bd, idesc, acc);
+                            }
+                            umma_commit(&sm.empty[s]);
+                            if (dyi == 2) umma_commit(&sm.a_empty[slot]);
                         }
-                        umma_commit(&sm.empty[s]);
+                        __syncwarp();
                     }
-                    umma_commit(&sm.a_empty[slot]);
                 }
-                umma_commit(&sm.acc_full);
+                if (elect_one()) umma_commit(&sm.acc_full);
+                __syncwarp();
             }
         }
     } else {
@@ -240,16 +262,19 @@ gate_conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 //   per CTA: warp 0 TMA producer (its own pixel rows + its half of the weights, completion signalled on the LEADER's
 //   mbarriers), warp 1 TMEM allocation (+ MMA issue in the leader CTA only; tcgen05.commit multicast to both CTAs),
 //   warps 2-5 epilogue of the CTA's own 128 pixels.
-constexpr int kPrASlots = 4;
-constexpr int kPrABytes = 24 * 1024;                 // TW*(128/TW+2) rows of 128 B: 144 / 160 / 192 rows for TW = 8/16/32
-constexpr int kPrBStages = 6;
+constexpr int kPrASlots = 3;
+constexpr int kPrABytes = 32 * 1024;                 // TW*(THc+2) <= 256 rows of 128 B
+constexpr int kPrBStages = 5;
 constexpr int kPrBBytes = (kCvMaxCout / 2) * kCvKBlk * 2;   // 16 KB: this CTA's half of the weight tile
 constexpr int kPrThreads = 192;
 constexpr int kPrAccStages = 2;
+constexpr int kPrOutCh = 64;                         // channels per epilogue chunk = one 128-byte swizzled row per pixel
+constexpr int kPrOutBytes = 128 * kPrOutCh * 2;      // 16 KB
 
 struct PrSmem {
     alignas(1024) uint8_t a[kPrASlots][kPrABytes];
     alignas(1024) uint8_t b[kPrBStages][kPrBBytes];
+    alignas(1024) uint8_t out[2][kPrOutBytes];      // epilogue staging for the TMA store (128 pixels x 64 channels)
     alignas(16) float scale[kCvMaxCout];
     alignas(16) float shift[kCvMaxCout];
     alignas(8) uint64_t b_full[kPrBStages];
@@ -308,10 +333,18 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t *bar) {
         : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPrThreads, 1)
 gate_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                         const float *__restrict__ bn_scale, const float *__restrict__ bn_shift,
-                         const float *__restrict__ gate, __nv_bfloat16 *__restrict__ y, const CvGeom g) {
+                         const __grid_constant__ CUtensorMap tmap_y, const float *__restrict__ bn_scale,
+                         const float *__restrict__ bn_shift, const float *__restrict__ gate, const CvGeom g) {
     extern __shared__ uint8_t smem_raw[];
     PrSmem &sm = *reinterpret_cast<PrSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -320,7 +353,7 @@ gate_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     const int tiles_img = g.tiles_x * g.tiles_y;
     const int n_tiles = g.B * tiles_img;
     const int kc_per_tap = g.Cin / kCvKBlk;
-    const int THc = g.TH / 2;                         // image rows of the pair tile owned by one CTA (TW * THc = 128)
+    const int THc = g.TH / 2;                         // image rows of the pair tile owned by one CTA (TW * THc <= 128)
     const uint32_t a_bytes = (uint32_t)g.TW * (THc + 2) * kCvKBlk * 2;
     const uint32_t b_bytes = (uint32_t)(g.Cout / 2) * kCvKBlk * 2;
 
@@ -374,13 +407,14 @@ gate_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: leader CTA only, one lane
-        if (rank == 0 && lane == 0) {
+        // ===== MMA issuer: leader CTA only; the whole warp walks the loop, one elected lane issues
+        if (rank == 0) {
             // instruction descriptor: D = f32, A = B = bf16, both K-major, N = Cout, M = 256 (128 rows per CTA)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.Cout >> 3) << 17) | ((256u >> 4) << 24);
+            const uint32_t a_lo0 = desc_lo(smem_u32(sm.a[0])), b_lo0 = desc_lo(smem_u32(sm.b[0]));
+            const uint32_t row_shift = (uint32_t)g.TW * 128 >> 4;
             uint32_t kbg = 0, an = 0;
             int it = 0;
-            const uint32_t row_shift = (uint32_t)g.TW * 128;
             for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
                 const int as = it % kPrAccStages;
                 mbar_wait(&sm.acc_empty[as], ((it / kPrAccStages) & 1) ^ 1);
@@ -389,47 +423,92 @@ gate_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                 for (int ks = 0; ks < 3 * kc_per_tap; ++ks, ++an) {
                     const int slot = an % kPrASlots;
                     mbar_wait(&sm.a_full[slot], (an / kPrASlots) & 1);
-                    const uint32_t a_slot = smem_u32(sm.a[slot]);
-                    for (int dyi = 0; dyi < 3; ++dyi, ++kbg) {
+                    uint32_t a_lo = a_lo0 + slot * (kPrABytes >> 4);
+                    for (int dyi = 0; dyi < 3; ++dyi, ++kbg, a_lo += row_shift) {
                         const int s = kbg % kPrBStages;
                         mbar_wait(&sm.b_full[s], (kbg / kPrBStages) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_addr = a_slot + dyi * row_shift, b_addr = smem_u32(sm.b[s]);
+                        const uint32_t b_lo = b_lo0 + s * (kPrBBytes >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < kCvKBlk / 16; ++k)
-                            umma2_f16(d, make_desc_k128(a_addr + k * 32), make_desc_k128(b_addr + k * 32), idesc,
-                                      (ks | dyi | k) ? 1u : 0u);
-                        umma2_commit_both(&sm.b_empty[s]);
+                            for (int k = 0; k < kCvKBlk / 16; ++k)
+                                umma2_f16(d, desc_of(a_lo + 2 * k), desc_of(b_lo + 2 * k), idesc, (ks | dyi | k) ? 1u : 0u);
+                            umma2_commit_both(&sm.b_empty[s]);
+                            if (dyi == 2) umma2_commit_both(&sm.a_empty[slot]);
+                        }
+                        __syncwarp();
                     }
-                    umma2_commit_both(&sm.a_empty[slot]);
                 }
-                umma2_commit_both(&sm.acc_full[as]);
+                if (elect_one()) umma2_commit_both(&sm.acc_full[as]);
+                __syncwarp();
             }
         }
     } else {
-        // ===== epilogue (both CTAs): warp w owns TMEM lanes 32*(w%4).. = pixels of this CTA's half of the pair tile
+        // ===== epilogue (both CTAs): warp w owns TMEM lanes 32*(w%4).. = pixels of this CTA's half of the pair tile.
+        // 64 channels at a time: TMEM -> registers -> (acc*s + t)*gate -> bf16 -> the pixel's 128-byte row of a swizzled
+        // staging tile -> ONE TMA store of the (64 ch, TW, THc) box; the tensor map clips the ragged image border.
+        // (Direct 16-byte global stores from the 32 pixel-owning lanes touch 32 lines per instruction: measured 8 us of
+        // the 90 us kernel, they contend with the tensor cores' operand reads in the shared L1/smem array.)
         const int quarter = warp & 3;
         const int p = quarter * 32 + lane;
-        const int px_in = p & (g.TW - 1), py_in = p / g.TW + (int)rank * THc;
+        const int et = (int)threadIdx.x - 64;
+        const int px_in = p % g.TW, py_in = p / g.TW + (int)rank * THc;   // rows p >= TW*THc of the M=128 block are idle
         const int hc = g.Cout / g.nh;
         const size_t HW = (size_t)g.H * g.W;
+        const uint32_t row_off = (uint32_t)p * 128, sw = (uint32_t)(p & 7);
+        uint32_t chunk = 0;
         int it = 0;
         for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
             const int as = it % kPrAccStages;
             const int b = t / tiles_img, r = t - b * tiles_img;
-            const int px = (r % g.tiles_x) * g.TW + px_in, py = (r / g.tiles_x) * g.TH + py_in;
-            const bool live = px < g.W && py < g.H;
-            const size_t pix = (size_t)py * g.W + px;
+            const int x0 = (r % g.tiles_x) * g.TW, y0 = (r / g.tiles_x) * g.TH;
+            const int px = x0 + px_in, py = y0 + py_in;
+            const bool live = p < g.TW * THc && px < g.W && py < g.H;
+            const float *gate_px = (gate == nullptr || !live) ? nullptr : gate + (size_t)b * g.nh * HW + (size_t)py * g.W + px;
             mbar_wait(&sm.acc_full[as], (it / kPrAccStages) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kCvMaxCout;
-            __nv_bfloat16 *dst = y + ((size_t)b * HW + pix) * g.Cout;
-            const float *gate_px = gate == nullptr ? nullptr : gate + (size_t)b * g.nh * HW + pix;
-            epilogue_row(taddr, dst, gate_px, sm.scale, sm.shift, g.Cout, hc, HW, live);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(map_to_cta(&sm.acc_empty[as], 0));
+            for (int c0 = 0; c0 < g.Cout; c0 += kPrOutCh, ++chunk) {
+                uint8_t *stage = sm.out[chunk & 1];
+                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store of chunk-2 has read it
+                epilogue_bar();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int cc = c0 + 32 * h;
+                    uint32_t v[32];
+                    tmem_ld32(taddr + cc, v);
+                    const float gt = gate_px != nullptr ? __ldg(gate_px + (size_t)(cc / hc) * HW) : 1.0f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int j = 0; j < 8; j += 4) {
+                            const float4 s4 = *reinterpret_cast<const float4 *>(&sm.scale[cc + q * 8 + j]);
+                            const float4 t4 = *reinterpret_cast<const float4 *>(&sm.shift[cc + q * 8 + j]);
+                            const float f0 = fmaf(__uint_as_float(v[q * 8 + j + 0]), s4.x, t4.x) * gt;
+                            const float f1 = fmaf(__uint_as_float(v[q * 8 + j + 1]), s4.y, t4.y) * gt;
+                            const float f2 = fmaf(__uint_as_float(v[q * 8 + j + 2]), s4.z, t4.z) * gt;
+                            const float f3 = fmaf(__uint_as_float(v[q * 8 + j + 3]), s4.w, t4.w) * gt;
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(f0, f1), hi = __floats2bfloat162_rn(f2, f3);
+                            o[j / 2] = *reinterpret_cast<uint32_t *>(&lo);
+                            o[j / 2 + 1] = *reinterpret_cast<uint32_t *>(&hi);
+                        }
+                        // 16-byte piece (h*4 + q) of this pixel's row, at its 128B-swizzled position
+                        const uint32_t piece = (uint32_t)(h * 4 + q) ^ sw;
+                        *reinterpret_cast<uint4 *>(stage + row_off + piece * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                if (c0 + kPrOutCh >= g.Cout) {                        // all TMEM reads of this tile done: hand it back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(map_to_cta(&sm.acc_empty[as], 0));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                epilogue_bar();
+                if (et == 0 && !(g.debug & 1)) tma_store_4d(&tmap_y, stage, c0, x0, y0 + (int)rank * THc, b);
+            }
         }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -504,23 +583,38 @@ extern "C" int tamtr_gate_conv3x3_tc_forward(const void *x_nhwc, const void *w_o
     EncodeTiledFn encode = get_encode();
     TAMTR_CHECK_ARG(encode != nullptr, TAMTR_E_NODEVICE, "gate_conv3x3_tc: cuTensorMapEncodeTiled unavailable");
 
-    // tile shape: the power-of-two TW x 256/TW patch that covers the map with the fewest tiles
-    CvGeom g{B, H, W, Cin, Cout, nh, 16, 16, 0, 0};
-    long best = -1;
-    for (int tw = 8; tw <= 32; tw *= 2) {
-        const int th = kCvTilePix / tw;
-        const long n = (long)((W + tw - 1) / tw) * ((H + th - 1) / th);
-        if (best < 0 || n < best || (n == best && tw == 16)) {
-            best = n;
-            g.TW = tw;
-            g.TH = th;
+    // Two SMs per tile (cta_group::2) unless the debug override TAMTR_GATECONV_SINGLE_CTA=1 asks for the single-CTA kernel.
+    static const bool single = [] { const char *e = getenv("TAMTR_GATECONV_SINGLE_CTA"); return e && e[0] == '1'; }();
+    CvGeom g{B, H, W, Cin, Cout, nh, 16, 16, 0, 0, 0};
+    { const char *e = getenv("TAMTR_GATECONV_DEBUG"); if (e) g.debug = atoi(e); }
+    if (single) {
+        // the power-of-two TW x 256/TW patch that covers the map with the fewest tiles
+        long best = -1;
+        for (int tw = 8; tw <= 32; tw *= 2) {
+            const int th = kCvTilePix / tw;
+            const long n = (long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+            if (best < 0 || n < best || (n == best && tw == 16)) { best = n; g.TW = tw; g.TH = th; }
+        }
+    } else {
+        // per CTA a TW x THc patch (TW a multiple of 8 so that a row tap is a whole number of swizzle atoms,
+        // TW*THc <= 128 = UMMA rows, TW*(THc+2) <= 256 patch rows); the pair stacks two of them.  Fewest tiles wins, then the
+        // fuller M block, then the smaller patch.
+        long best_n = -1;
+        int best_fill = 0, best_rows = 0;
+        for (int tw = 8; tw <= 80; tw += 8) {
+            const int thc = 128 / tw, rows = tw * (thc + 2);
+            if (thc < 1 || rows > 256) continue;
+            const long n = (long)((W + tw - 1) / tw) * ((H + 2 * thc - 1) / (2 * thc));
+            const int fill = tw * thc;
+            if (best_n < 0 || n < best_n || (n == best_n && (fill > best_fill || (fill == best_fill && rows < best_rows)))) {
+                best_n = n; best_fill = fill; best_rows = rows;
+                g.TW = tw; g.TH = 2 * thc;
+            }
         }
     }
     g.tiles_x = (W + g.TW - 1) / g.TW;
     g.tiles_y = (H + g.TH - 1) / g.TH;
 
-    // Two SMs per tile (cta_group::2) unless the debug override TAMTR_GATECONV_SINGLE_CTA=1 asks for the single-CTA kernel.
-    static const bool single = [] { const char *e = getenv("TAMTR_GATECONV_SINGLE_CTA"); return e && e[0] == '1'; }();
     const int box_rows = single ? g.TH + 2 : g.TH / 2 + 2;     // image rows per activation box (with the two halo rows)
     const int box_cout = single ? Cout : Cout / 2;             // weight rows per CTA
     CUtensorMap tmap_x, tmap_w;
@@ -543,6 +637,18 @@ extern "C" int tamtr_gate_conv3x3_tc_forward(const void *x_nhwc, const void *w_o
                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         TAMTR_CHECK_ARG(cr == CUDA_SUCCESS, TAMTR_E_BADARG, "gate_conv3x3_tc: tensor map (w) failed (%d)", (int)cr);
+    }
+
+    CUtensorMap tmap_y;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)kPrOutCh, (cuuint32_t)g.TW, (cuuint32_t)g.TH / 2, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult cr = encode(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y_nhwc, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TAMTR_CHECK_ARG(cr == CUDA_SUCCESS, TAMTR_E_BADARG, "gate_conv3x3_tc: tensor map (y) failed (%d)", (int)cr);
     }
 
     int n_sm = 148;
@@ -569,7 +675,7 @@ extern "C" int tamtr_gate_conv3x3_tc_forward(const void *x_nhwc, const void *w_o
                 tmap_x, tmap_w, bn_scale, bn_shift, gate, (__nv_bfloat16 *)y_nhwc, g);
         else
             gate_conv3x3_pair_kernel<<<2 * n_work, kPrThreads, sizeof(PrSmem) + 1024, st>>>(
-                tmap_x, tmap_w, bn_scale, bn_shift, gate, (__nv_bfloat16 *)y_nhwc, g);
+                tmap_x, tmap_w, tmap_y, bn_scale, bn_shift, gate, g);
     }
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());

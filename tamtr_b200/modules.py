@@ -267,6 +267,17 @@ class MaxSigmoidAttnBlock(nn.Module):
         self.proj_conv = _ConvBN(c1, c2, 3)
         self.scale = nn.Parameter(torch.ones(1, nh, 1, 1)) if scale else 1.0
 
+    def _folded_bn(self, bn):
+        """BatchNorm2d in eval mode as a per-channel affine (fp32), cached until a parameter or statistic changes."""
+        key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+        hit = getattr(self, "_fold_cache", None)
+        if hit is None or hit[0] != key:
+            s = bn.weight.detach().float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+            t = bn.bias.detach().float() - bn.running_mean.float() * s
+            hit = (key, s.contiguous(), t.contiguous())
+            self._fold_cache = hit
+        return hit[1], hit[2]
+
     def forward(self, x, guide):
         bs, _, h, w = x.shape
         guide = self.gl(guide).view(bs, -1, self.nh, self.hc)
@@ -278,8 +289,7 @@ class MaxSigmoidAttnBlock(nn.Module):
             bn = pc.bn
             if not (self.training or torch.is_grad_enabled()) and bn.running_var is not None:
                 # inference: conv + folded BatchNorm + gate in one tensor-core kernel (channels-last output)
-                s = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
-                t = bn.bias.float() - bn.running_mean.float() * s
+                s, t = self._folded_bn(bn)
                 return ops.gate_conv3x3(x, pc.conv.weight, s, t, aw, self.nh)
             y = bn(ops.conv3x3_tc(x, pc.conv.weight))
         else:

@@ -466,11 +466,27 @@ def gate_conv3x3_supported(x, weight, nh):
             and 32 <= co <= 256 and co % nh == 0 and (co // nh) % 32 == 0)
 
 
+_OHWI_CACHE = {}
+
+
+def _weight_ohwi(weight):
+    """[Co, Ci, 3, 3] -> bf16 [Co, 3, 3, Ci] (the K-major B operand), cached per (storage, version): inference calls
+    the block with the same weights every time."""
+    key = (weight.data_ptr(), weight._version, weight.dtype, tuple(weight.shape), weight.device)
+    hit = _OHWI_CACHE.get(key)
+    if hit is None:
+        if len(_OHWI_CACHE) >= 32:
+            _OHWI_CACHE.clear()
+        hit = weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        _OHWI_CACHE[key] = hit
+    return hit
+
+
 def _gate_conv3x3_launch(x, weight, bn_scale, bn_shift, gate, nh):
     B, Ci, H, W = x.shape
     Co = weight.shape[0]
     x_cl = to_channels_last(x)                                        # storage [B, H, W, Ci]
-    w_ohwi = weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    w_ohwi = _weight_ohwi(weight)
     s32 = bn_scale.detach().float().contiguous()
     t32 = bn_shift.detach().float().contiguous()
     g32 = None if gate is None else gate.detach().float().contiguous()
@@ -494,14 +510,21 @@ def gate_conv3x3(x, weight, bn_scale, bn_shift, gate, nh):
     return _gate_conv3x3_launch(x, weight, bn_scale, bn_shift, gate, nh)[1]
 
 
+_IDENTITY_AFFINE = {}
+
+
 class _Conv3x3TcFn(torch.autograd.Function):
     """The raw 3x3 convolution (stride 1, pad 1, no bias) on the tcgen05 kernel; dgrad / wgrad are library calls."""
 
     @staticmethod
     def forward(ctx, x, weight):
         co = weight.shape[0]
-        one = torch.ones(co, dtype=torch.float32, device=x.device)
-        x_cl, y = _gate_conv3x3_launch(x, weight, one, torch.zeros_like(one), None, 1)
+        key = (co, x.device)
+        if key not in _IDENTITY_AFFINE:
+            _IDENTITY_AFFINE[key] = (torch.ones(co, dtype=torch.float32, device=x.device),
+                                     torch.zeros(co, dtype=torch.float32, device=x.device))
+        one, zero = _IDENTITY_AFFINE[key]
+        x_cl, y = _gate_conv3x3_launch(x, weight, one, zero, None, 1)
         ctx.save_for_backward(x_cl, weight)
         return y
 
