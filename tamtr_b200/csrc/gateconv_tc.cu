@@ -545,6 +545,47 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const T *__restrict__
     }
 }
 
+// bf16 fast path: 64 channels x 128 pixels per CTA, 16-byte global accesses on both sides.  Shared memory holds 32-bit
+// words = (pixel 2q, pixel 2q+1) of one channel; the output side reads 8 channels of one pixel pair and splits the
+// halves with byte permutes, so each thread stores two full 16-byte pieces (8 channels of one pixel each).
+__global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const uint16_t *__restrict__ x, uint16_t *__restrict__ y,
+                                                                int C, int HW) {
+    __shared__ uint32_t tile[64][65];
+    const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 128;
+    const uint16_t *xb = x + (size_t)b * C * HW;
+    uint16_t *yb = y + (size_t)b * C * HW;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int piece = threadIdx.x + 256 * i;          // 64 channels x 16 pieces of 8 pixels
+        const int c = piece >> 4, k = piece & 15;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c0 + c < C && p0 + 8 * k < HW) v = *reinterpret_cast<const uint4 *>(xb + (size_t)(c0 + c) * HW + p0 + 8 * k);
+        tile[c][4 * k + 0] = v.x;
+        tile[c][4 * k + 1] = v.y;
+        tile[c][4 * k + 2] = v.z;
+        tile[c][4 * k + 3] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int item = threadIdx.x + 256 * i;           // 64 pixel pairs x 8 channel groups of 8
+        const int cg = item & 7, pp = item >> 3;
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = tile[8 * cg + j][pp];
+        uint4 lo, hi;
+        lo.x = __byte_perm(w[0], w[1], 0x5410); hi.x = __byte_perm(w[0], w[1], 0x7632);
+        lo.y = __byte_perm(w[2], w[3], 0x5410); hi.y = __byte_perm(w[2], w[3], 0x7632);
+        lo.z = __byte_perm(w[4], w[5], 0x5410); hi.z = __byte_perm(w[4], w[5], 0x7632);
+        lo.w = __byte_perm(w[6], w[7], 0x5410); hi.w = __byte_perm(w[6], w[7], 0x7632);
+        const int pix = p0 + 2 * pp, c = c0 + 8 * cg;
+        if (c < C) {
+            if (pix < HW) *reinterpret_cast<uint4 *>(yb + (size_t)pix * C + c) = lo;
+            if (pix + 1 < HW) *reinterpret_cast<uint4 *>(yb + (size_t)(pix + 1) * C + c) = hi;
+        }
+    }
+}
+
 }  // namespace tamtr
 
 using namespace tamtr;
@@ -557,7 +598,10 @@ extern "C" int tamtr_nchw_to_nhwc(const void *x, void *y, int dtype, int B, int 
     cudaStream_t st = (cudaStream_t)stream;
     {
         KernelTimer timer(K_NHWC, st);
-        if (dtype == TAMTR_BF16)
+        if (dtype == TAMTR_BF16 && HW % 8 == 0 && C % 8 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0)
+            nchw_to_nhwc_bf16_kernel<<<dim3((HW + 127) / 128, (C + 63) / 64, B), 256, 0, st>>>(
+                (const uint16_t *)x, (uint16_t *)y, C, HW);
+        else if (dtype == TAMTR_BF16)
             nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, C, HW);
         else
             nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>((const float *)x, (float *)y, C, HW);

@@ -59,6 +59,10 @@ def test_channels_last_input_is_used_in_place(cuda_lib):
     assert ops.to_channels_last(x_cl).data_ptr() == x_cl.data_ptr()
     conv = ops.to_channels_last(xc)
     assert torch.equal(conv, xc) and conv.permute(0, 2, 3, 1).is_contiguous()     # our layout kernel is exact
+    for shape in ((2, 72, 8, 13), (1, 256, 40, 40), (3, 8, 4, 2)):                # bf16 vector path: ragged tiles both ways
+        xb = seeding.seeded_tensor(7, "xb", shape).bfloat16().cuda()
+        got = ops.to_channels_last(xb)
+        assert torch.equal(got, xb) and got.permute(0, 2, 3, 1).is_contiguous()
     xf = seeding.seeded_tensor(6, "xf", (2, 37, 13, 11)).cuda()                   # fp32, ragged everything
     assert torch.equal(ops.to_channels_last(xf), xf)
     assert torch.equal(ops.conv3x3_tc(x_cl, w.cuda()), ops.conv3x3_tc(xc, w.cuda()))
