@@ -195,6 +195,20 @@ int tamtr_col_reduce2(const void *a, const void *b, float *partial, int dtype, i
 int tamtr_affine_rows(void *out, const void *a, const void *b, const float *A, const float *Bc, const float *Cc,
                       int dtype, int B, int Lv, int d, int L, const int32_t *level_starts_host, void *stream);
 
+/* BatchNorm bookkeeping for one level between the two passes above (one thread per channel, fp64 inside):
+ *   forward : from the partials of tamtr_col_reduce2(pre, pre) over M = B*ntok rows (use_batch_stats) or from the running
+ *             statistics: scale = gamma*rstd, shift = beta - mu*scale (the A / Cc rows of tamtr_affine_rows), mu and
+ *             rstd (f64 [d]) for the backward; with batch statistics and running_mean != NULL the running statistics
+ *             are updated like nn.BatchNorm2d (momentum, unbiased variance).
+ *   backward: from the partials of tamtr_col_reduce2(G, pre): A, Bc, Cc rows of the backward affine pass, d_gamma,
+ *             d_beta (f32 [d]).  batch_stats = 0 (eval-mode statistics) gives Bc = Cc = 0. */
+int tamtr_bn_forward_coeffs(const float *partial, int n_cta, double M, const float *gamma, const float *beta, double eps,
+                            int use_batch_stats, double momentum, float *running_mean, float *running_var, float *scale,
+                            float *shift, double *mu, double *rstd, int d, void *stream);
+int tamtr_bn_backward_coeffs(const float *partial, int n_cta, double M, const float *gamma, const double *mu,
+                             const double *rstd, int batch_stats, float *A, float *Bc, float *Cc, float *d_gamma,
+                             float *d_beta, int d, void *stream);
+
 /* Query-selection ranking (head.py:1229-1237: enc_output = Linear + LayerNorm over all tokens, enc_score_head, max over
  * classes), fused after the two GEMMs:
  *   E   [B*Lv, d] f32|bf16 = feats @ enc_output.0.weight^T (no bias, no validity mask)
@@ -207,6 +221,22 @@ int tamtr_affine_rows(void *out, const void *a, const void *b, const float *A, c
 int tamtr_rank_tokens(const void *E, const float *raw, const float *enc_bias, const uint8_t *valid, const float *bw,
                       const float *sw, const float *ck, float *out, int dtype, int B, int Lv, int d, int nc,
                       int raw_stride, float eps, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Residual add + LayerNorm of the decoder layers (ultralytics/nn/modules/transformer.py:548,553,537:
+ * `embed = self.normN(embed + self.dropoutN(tgt))`, dropout p = 0) -- one kernel forward, one backward.
+ *   forward : z = x + res (res may be NULL), y = (z - mean) * rstd * w + b over the last dimension d.
+ *             x, res, y: [rows, d] f32|bf16 (each with its own dtype code); w, b f32 [d]; z f32 [rows, d] and
+ *             mean, rstd f32 [rows] are written for the backward (any of them may be NULL at inference).
+ *   backward: dx / dres (either may be NULL) = d(loss)/dz in the dtype of x / res; dwb f32 [2, d] = (dw, db), zeroed
+ *             by the call (memset node) and accumulated with one fp32 reduction per column and CTA.
+ * d % 128 == 0, 128 <= d <= 512. */
+int tamtr_add_layernorm_forward(const void *x, int x_dtype, const void *res, int res_dtype, const float *w, const float *b,
+                                void *y, int y_dtype, float *z, float *mean, float *rstd, int rows, int d, float eps,
+                                void *stream);
+int tamtr_add_layernorm_backward(const void *dy, int dy_dtype, const float *z, const float *mean, const float *rstd,
+                                 const float *w, void *dx, int dx_dtype, void *dres, int dres_dtype, float *dwb, int rows,
+                                 int d, void *stream);
 
 #ifdef __cplusplus
 }

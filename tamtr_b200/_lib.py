@@ -46,6 +46,13 @@ _SIGNATURES = {
     "tamtr_max_sigmoid_tc_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_gate_conv3x3_tc_forward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _fp, _vp] + [_i] * 6 + [_vp]),
     "tamtr_nchw_to_nhwc": (ctypes.c_int, [_vp, _vp] + [_i] * 4 + [_vp]),
+    "tamtr_add_layernorm_forward": (ctypes.c_int, [_vp, _i, _vp, _i, _fp, _fp, _vp, _i, _fp, _fp, _fp, _i, _i,
+                                                   ctypes.c_float, _vp]),
+    "tamtr_add_layernorm_backward": (ctypes.c_int, [_vp, _i, _fp, _fp, _fp, _fp, _vp, _i, _vp, _i, _fp, _i, _i, _vp]),
+    "tamtr_bn_forward_coeffs": (ctypes.c_int, [_fp, _i, ctypes.c_double, _fp, _fp, ctypes.c_double, _i, ctypes.c_double,
+                                               _fp, _fp, _fp, _fp, _vp, _vp, _i, _vp]),
+    "tamtr_bn_backward_coeffs": (ctypes.c_int, [_fp, _i, ctypes.c_double, _fp, _vp, _vp, _i, _fp, _fp, _fp, _fp, _fp,
+                                                _i, _vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }
 

@@ -82,6 +82,69 @@ __global__ void col_reduce2_kernel(const T *__restrict__ a, const T *__restrict_
     }
 }
 
+// BatchNorm bookkeeping of one pyramid level, one thread per channel: folds the column-reduction partials (in fp64:
+// var = E[x^2] - mu^2 cancels) and emits everything the affine pass needs.  Replaces ~15 single-digit-microsecond
+// library launches per level and direction (fp64 sum over the partials + scalar algebra on [d] vectors).
+//   forward : mu = S1/M, var = max(S2/M - mu^2, 0), rstd = 1/sqrt(var + eps),
+//             scale = gamma*rstd, shift = beta - mu*scale; running stats <- (1-mom)*old + mom*(mu, var*M/(M-1))
+__global__ void bn_forward_coeffs_kernel(const float *__restrict__ partial, int n_cta, double M, const float *__restrict__ gamma,
+                                         const float *__restrict__ beta, double eps, int use_batch_stats, double momentum,
+                                         float *__restrict__ running_mean, float *__restrict__ running_var,
+                                         float *__restrict__ scale, float *__restrict__ shift, double *__restrict__ mu_out,
+                                         double *__restrict__ rstd_out, int d) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    double mu, var;
+    if (use_batch_stats) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < n_cta; ++i) {
+            s1 += (double)partial[(size_t)i * 2 * d + c];
+            s2 += (double)partial[(size_t)i * 2 * d + d + c];
+        }
+        mu = s1 / M;
+        var = s2 / M - mu * mu;
+        if (var < 0.0) var = 0.0;
+        if (running_mean != nullptr) {
+            const double unbiased = var * (M / (M > 1.0 ? M - 1.0 : 1.0));
+            running_mean[c] = (float)((double)running_mean[c] * (1.0 - momentum)) + (float)mu * (float)momentum;
+            running_var[c] = (float)((double)running_var[c] * (1.0 - momentum)) + (float)unbiased * (float)momentum;
+        }
+    } else {
+        mu = (double)running_mean[c];
+        var = (double)running_var[c];
+    }
+    const double rstd = 1.0 / sqrt(var + eps);
+    const double sc = (double)gamma[c] * rstd;
+    scale[c] = (float)sc;
+    shift[c] = (float)((double)beta[c] - mu * sc);
+    mu_out[c] = mu;
+    rstd_out[c] = rstd;
+}
+
+//   backward: SG = sum G, SGP = sum G*pre;  d_beta = SG, d_gamma = rstd*(SGP - mu*SG), a = gamma*rstd,
+//             d_pre = A*G + Bc*pre + Cc with A = a, Bc = -a*rstd*d_gamma/M, Cc = -a*SG/M + a*rstd*mu*d_gamma/M
+//             (eval-mode statistics: Bc = Cc = 0)
+__global__ void bn_backward_coeffs_kernel(const float *__restrict__ partial, int n_cta, double M,
+                                          const float *__restrict__ gamma, const double *__restrict__ mu,
+                                          const double *__restrict__ rstd, int batch_stats, float *__restrict__ A,
+                                          float *__restrict__ Bc, float *__restrict__ Cc, float *__restrict__ d_gamma,
+                                          float *__restrict__ d_beta, int d) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    double sg = 0.0, sgp = 0.0;
+    for (int i = 0; i < n_cta; ++i) {
+        sg += (double)partial[(size_t)i * 2 * d + c];
+        sgp += (double)partial[(size_t)i * 2 * d + d + c];
+    }
+    const double dgam = rstd[c] * (sgp - mu[c] * sg);
+    const double a = (double)gamma[c] * rstd[c];
+    A[c] = (float)a;
+    Bc[c] = batch_stats ? (float)(-a * rstd[c] * dgam / M) : 0.f;
+    Cc[c] = batch_stats ? (float)(-a * sg / M + a * rstd[c] * mu[c] * dgam / M) : 0.f;
+    d_gamma[c] = (float)dgam;
+    d_beta[c] = (float)sg;
+}
+
 struct RowLevels {
     int n;
     int start[kMaxLevels + 1];   // token starts, start[n] = Lv
@@ -323,6 +386,36 @@ extern "C" int tamtr_rank_tokens(const void *E, const float *raw, const float *e
     if (dtype == TAMTR_F32) { if (pp <= 1) RANK(float, 1); else if (pp <= 2) RANK(float, 2); else RANK(float, 4); }
     else { if (pp <= 1) RANK(__nv_bfloat16, 1); else if (pp <= 2) RANK(__nv_bfloat16, 2); else RANK(__nv_bfloat16, 4); }
 #undef RANK
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tamtr_bn_forward_coeffs(const float *partial, int n_cta, double M, const float *gamma, const float *beta,
+                                       double eps, int use_batch_stats, double momentum, float *running_mean,
+                                       float *running_var, float *scale, float *shift, double *mu, double *rstd, int d,
+                                       void *stream) {
+    TAMTR_CHECK_ARG(gamma && beta && scale && shift && mu && rstd, TAMTR_E_BADARG, "bn_forward_coeffs: null pointer");
+    TAMTR_CHECK_ARG(d > 0 && M > 0, TAMTR_E_BADARG, "bn_forward_coeffs: bad sizes");
+    TAMTR_CHECK_ARG(use_batch_stats ? (partial != nullptr && n_cta > 0) : (running_mean && running_var), TAMTR_E_BADARG,
+                    "bn_forward_coeffs: statistics source missing");
+    TAMTR_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), TAMTR_E_BADARG,
+                    "bn_forward_coeffs: running_mean / running_var must come together");
+    bn_forward_coeffs_kernel<<<(d + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        partial, n_cta, M, gamma, beta, eps, use_batch_stats, momentum, running_mean, running_var, scale, shift, mu, rstd, d);
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tamtr_bn_backward_coeffs(const float *partial, int n_cta, double M, const float *gamma, const double *mu,
+                                        const double *rstd, int batch_stats, float *A, float *Bc, float *Cc,
+                                        float *d_gamma, float *d_beta, int d, void *stream) {
+    TAMTR_CHECK_ARG(partial && gamma && mu && rstd && A && Bc && Cc && d_gamma && d_beta, TAMTR_E_BADARG,
+                    "bn_backward_coeffs: null pointer");
+    TAMTR_CHECK_ARG(d > 0 && M > 0 && n_cta > 0, TAMTR_E_BADARG, "bn_backward_coeffs: bad sizes");
+    bn_backward_coeffs_kernel<<<(d + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, n_cta, M, gamma, mu, rstd,
+                                                                                 batch_stats, A, Bc, Cc, d_gamma, d_beta, d);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;

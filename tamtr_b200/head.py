@@ -47,7 +47,7 @@ class CdnPlan:
 
     def materialize(self, class_embed):
         dev = class_embed.device
-        embed = class_embed[self.dn_cls.to(dev)]
+        embed = ops.embed_rows(class_embed, self.dn_cls.to(dev))
         # (the reference fills fp32 buffers on the targets' device and moves them afterwards, ops.py:243-262; filling
         #  them on the embedding's device is the same result without a host round trip)
         pad_embed = torch.zeros(self.bs, self.n_dn, embed.shape[-1], device=dev, dtype=embed.dtype)

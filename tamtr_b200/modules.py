@@ -138,9 +138,17 @@ class DeformableTransformerDecoderLayer(nn.Module):
     def with_pos_embed(tensor, pos):
         return tensor if pos is None else tensor + pos
 
+    def _add_norm(self, x, y, drop, norm):
+        """norm(x + dropout(y)): fused residual + LayerNorm kernel (dropout is the identity in TAM-TR, p = 0)."""
+        if ((drop.p == 0.0 or not self.training) and ops.add_layer_norm_supported(x, x.shape[-1])
+                and isinstance(norm, nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
+                and tuple(norm.normalized_shape) == (x.shape[-1],)):
+            return ops.add_layer_norm(x, y, norm)
+        return norm(x + drop(y))
+
     def forward_ffn(self, tgt):
         tgt2 = self.linear2(self.dropout3(self.act(self.linear1(tgt))))
-        return self.norm3(tgt + self.dropout4(tgt2))
+        return self._add_norm(tgt, tgt2, self.dropout4, self.norm3)
 
     def forward(self, embed, refer_bbox, feats, shapes, padding_mask=None, attn_mask=None, query_pos=None,
                 projected_value=None, arena=None):
@@ -149,10 +157,10 @@ class DeformableTransformerDecoderLayer(nn.Module):
         # so the fused SDPA kernels can be used; the output is the same.
         tgt = self.self_attn(q.transpose(0, 1), k.transpose(0, 1), embed.transpose(0, 1), attn_mask=attn_mask,
                              need_weights=False)[0].transpose(0, 1)
-        embed = self.norm1(embed + self.dropout1(tgt))
+        embed = self._add_norm(embed, tgt, self.dropout1, self.norm1)
         tgt = self.cross_attn(self.with_pos_embed(embed, query_pos), refer_bbox.unsqueeze(2), feats, shapes,
                               padding_mask, projected_value, arena)
-        embed = self.norm2(embed + self.dropout2(tgt))
+        embed = self._add_norm(embed, tgt, self.dropout2, self.norm2)
         return self.forward_ffn(embed)
 
 

@@ -445,6 +445,76 @@ def max_sigmoid_gate(embed, guide, bias, nh, use_tensor_cores=None):
     return _MaxSigmoidFn.apply(embed, guide, bias, nh, use_tensor_cores)
 
 
+# ------------------------------------------------------------------------------------ residual add + LayerNorm
+def add_layer_norm_supported(x, d):
+    return x.is_cuda and d % 128 == 0 and 128 <= d <= 512 and x.dtype in (torch.float32, torch.bfloat16)
+
+
+class _AddLayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, weight, bias, eps):
+        d = x.shape[-1]
+        xc = x.contiguous()
+        rc_ = None if res is None else res.contiguous()
+        if rc_ is not None and rc_.dtype not in (torch.float32, torch.bfloat16):
+            rc_ = rc_.float()
+        rows = xc.numel() // d
+        out_dtype = torch.float32 if (xc.dtype == torch.float32 or (rc_ is not None and rc_.dtype == torch.float32)
+                                      or torch.is_autocast_enabled("cuda")) else xc.dtype
+        w32 = weight.detach().float().contiguous()
+        b32 = bias.detach().float().contiguous()
+        y = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
+        need = any(ctx.needs_input_grad[:4])
+        z = torch.empty(xc.shape, dtype=torch.float32, device=xc.device) if need else None
+        mean = torch.empty(rows, dtype=torch.float32, device=xc.device) if need else None
+        rstd = torch.empty(rows, dtype=torch.float32, device=xc.device) if need else None
+        with _with_device(xc):
+            rc = _lib.lib().tamtr_add_layernorm_forward(
+                xc.data_ptr(), _lib.dtype_code(xc), None if rc_ is None else rc_.data_ptr(),
+                0 if rc_ is None else _lib.dtype_code(rc_), w32.data_ptr(), b32.data_ptr(), y.data_ptr(),
+                _lib.dtype_code(y), None if z is None else z.data_ptr(), None if mean is None else mean.data_ptr(),
+                None if rstd is None else rstd.data_ptr(), rows, d, float(eps), _lib.stream_ptr(xc.device))
+        _lib.check(rc, "add_layernorm_forward")
+        if need:
+            ctx.save_for_backward(z, mean, rstd, w32)
+            ctx.meta = (xc.dtype, None if rc_ is None else rc_.dtype, weight.dtype, bias.dtype, rows, d)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        z, mean, rstd, w32 = ctx.saved_tensors
+        xdt, rdt, wdt, bdt, rows, d = ctx.meta
+        gy = gy.contiguous()
+        if gy.dtype not in (torch.float32, torch.bfloat16):
+            gy = gy.float()
+        dev = gy.device
+        need_x, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and rdt is not None
+        dx = torch.empty(z.shape, dtype=xdt, device=dev) if need_x else None
+        # one tensor serves both inputs when they share a dtype
+        if need_r and need_x and rdt == xdt:
+            dres, dres_ptr = dx, None
+        else:
+            dres = torch.empty(z.shape, dtype=rdt, device=dev) if need_r else None
+            dres_ptr = None if dres is None else dres.data_ptr()
+        dwb = torch.empty(2, d, dtype=torch.float32, device=dev)       # zeroed by the call
+        with _with_device(gy):
+            rc = _lib.lib().tamtr_add_layernorm_backward(
+                gy.data_ptr(), _lib.dtype_code(gy), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), w32.data_ptr(),
+                None if dx is None else dx.data_ptr(), 0 if dx is None else _lib.dtype_code(dx), dres_ptr,
+                0 if dres_ptr is None else _lib.dtype_code(dres), dwb.data_ptr(), rows, d, _lib.stream_ptr(dev))
+        _lib.check(rc, "add_layernorm_backward")
+        return dx, dres, dwb[0].to(wdt), dwb[1].to(bdt), None
+
+
+def add_layer_norm(x, res, norm):
+    """`norm(x + res)` (res may be None) for an nn.LayerNorm over the last dimension: one kernel each way
+    (csrc/layernorm.cu).  Output is fp32 when an input is fp32 or under autocast (autocast runs layer_norm in fp32),
+    otherwise the input dtype."""
+    _lib.require_cuda(x, res)
+    return _AddLayerNormFn.apply(x, res, norm.weight, norm.bias, norm.eps)
+
+
 def to_channels_last(x):
     """[B, C, H, W] -> the same logical tensor in channels-last memory ([B, H, W, C] storage).  No copy when the caller
     already holds channels-last maps; otherwise one pass of tamtr_nchw_to_nhwc."""
@@ -610,9 +680,39 @@ def select_rows(x, flat_idx, hub):
     return _SelectRowsFn.apply(x, flat_idx, hub)
 
 
+class _EmbedRowsFn(torch.autograd.Function):
+    """weight[idx] for a SMALL table hit by many indices (the denoising class embedding: 11 rows, thousands of
+    lookups, models/utils/ops.py:243).  The library backward sorts the indices and serialises the colliding rows
+    (161 us at TAM-TR shapes); as a one-hot GEMM [rows, n]^T @ grad it is a few microseconds and deterministic."""
+
+    @staticmethod
+    def forward(ctx, weight, idx):
+        ctx.save_for_backward(idx)
+        ctx.n = weight.shape[0]
+        ctx.wdt = weight.dtype
+        return weight[idx]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        with torch.autocast("cuda", enabled=False):
+            onehot = torch.zeros(idx.numel(), ctx.n, dtype=torch.float32, device=g.device)
+            onehot.scatter_(1, idx.view(-1, 1), 1.0)
+            gw = onehot.t() @ g.reshape(idx.numel(), -1).float()
+        return gw.to(ctx.wdt), None
+
+
+def embed_rows(weight, idx):
+    if not (weight.is_cuda and weight.requires_grad and torch.is_grad_enabled()):
+        return weight[idx]
+    return _EmbedRowsFn.apply(weight, idx)
+
+
 # ------------------------------------------------------------------------------------ token-major input projection
-def _col_reduce2(a, b, tok0, ntok):
-    """-> (sum_rows a, sum_rows a*b) over tokens [tok0, tok0+ntok) of every image, float64 [d] each."""
+def _col_reduce2_partials(a, b, tok0, ntok):
+    """Per-CTA partial sums [n_cta, 2, d] fp32 of (a, a*b) over tokens [tok0, tok0+ntok) of every image; the fold to
+    fp64 totals happens inside tamtr_bn_*_coeffs."""
     B, Lv, d = a.shape
     n_cta = _lib.lib().tamtr_col_reduce2_ctas(B, ntok)
     partial = torch.empty(n_cta, 2, d, dtype=torch.float32, device=a.device)
@@ -620,8 +720,7 @@ def _col_reduce2(a, b, tok0, ntok):
         rc = _lib.lib().tamtr_col_reduce2(a.data_ptr(), b.data_ptr(), partial.data_ptr(), _lib.dtype_code(a), B, Lv, d,
                                           tok0, ntok, _lib.stream_ptr(a.device))
     _lib.check(rc, "col_reduce2")
-    s = partial.double().sum(0)
-    return s[0], s[1]
+    return partial
 
 
 def _affine_rows(a, b, A, Bc, Cc, starts):
@@ -670,27 +769,35 @@ class _InputProjFn(torch.autograd.Function):
             wl.append(w)
         scale = torch.empty(n_levels, d, dtype=torch.float32, device=dev)
         shift = torch.empty_like(scale)
-        mus, rstds = [], []
+        stats = torch.empty(n_levels, 2, d, dtype=torch.float64, device=dev)          # (mu, rstd) per level
         for l, bn in enumerate(bns):
-            M = B * hw[l]
-            if training or bn.running_mean is None:
-                s1, s2 = _col_reduce2(pre, pre, starts[l], hw[l])
-                mu = s1 / M
-                var = (s2 / M - mu * mu).clamp_min(0.0)
-                if training and bn.running_mean is not None:
-                    with torch.no_grad():
-                        mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
-                        bn.running_mean.mul_(1 - mom).add_(mu.to(bn.running_mean.dtype), alpha=mom)
-                        bn.running_var.mul_(1 - mom).add_((var * (M / max(M - 1, 1))).to(bn.running_var.dtype), alpha=mom)
-                        bn.num_batches_tracked += 1
-            else:
-                mu, var = bn.running_mean.double(), bn.running_var.double()
-            rstd = torch.rsqrt(var + bn.eps)
-            sc = gammas[l].double() * rstd
-            scale[l] = sc.float()
-            shift[l] = (betas[l].double() - mu * sc).float()
-            mus.append(mu)
-            rstds.append(rstd)
+            batch_stats = training or bn.running_mean is None
+            partial = _col_reduce2_partials(pre, pre, starts[l], hw[l]) if batch_stats else None
+            update = batch_stats and training and bn.running_mean is not None
+            mom = 0.0
+            if update:
+                mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+            rm = rv = None
+            if bn.running_mean is not None and (update or not batch_stats):
+                rm, rv = bn.running_mean, bn.running_var
+                if rm.dtype != torch.float32 or rv.dtype != torch.float32 or not rm.is_contiguous():
+                    rm, rv = rm.float().contiguous(), rv.float().contiguous()
+            g32, b32 = gammas[l].detach().float().contiguous(), betas[l].detach().float().contiguous()
+            with _with_device(pre):
+                rc = _lib.lib().tamtr_bn_forward_coeffs(
+                    None if partial is None else partial.data_ptr(), 0 if partial is None else partial.shape[0],
+                    float(B * hw[l]), g32.data_ptr(), b32.data_ptr(), float(bn.eps), int(batch_stats), float(mom),
+                    None if rm is None else rm.data_ptr(), None if rv is None else rv.data_ptr(), scale[l].data_ptr(),
+                    shift[l].data_ptr(), stats[l, 0].data_ptr(), stats[l, 1].data_ptr(), d, _lib.stream_ptr(dev))
+            _lib.check(rc, "bn_forward_coeffs")
+            if update:
+                with torch.no_grad():
+                    if rm is not bn.running_mean:
+                        bn.running_mean.copy_(rm)
+                        bn.running_var.copy_(rv)
+                    bn.num_batches_tracked += 1
+        mus = [stats[l, 0] for l in range(n_levels)]
+        rstds = [stats[l, 1] for l in range(n_levels)]
         feats = _affine_rows(pre, None, scale, None, shift, starts)
         ctx.save_for_backward(pre, *xl, *wl, *gammas, *mus, *rstds)
         ctx.meta = (n_levels, hw, starts, training, [x.dtype for x in xs], [w.dtype for w in ws],
@@ -709,20 +816,21 @@ class _InputProjFn(torch.autograd.Function):
         B, Lv, d = pre.shape
         dev = pre.device
         A = torch.empty(n, d, dtype=torch.float32, device=dev)
-        Bc = torch.zeros_like(A)
-        Cc = torch.zeros_like(A)
+        Bc = torch.empty_like(A)
+        Cc = torch.empty_like(A)
+        dgb = torch.empty(n, 2, d, dtype=torch.float32, device=dev)
         d_gamma, d_beta = [], []
         for l in range(n):
-            M = B * hw[l]
-            sg, sgp = _col_reduce2(G, pre, starts[l], hw[l])
-            dgam = rstds[l] * (sgp - mus[l] * sg)
-            a = gammas[l].double() * rstds[l]
-            A[l] = a.float()
-            if training:
-                Bc[l] = (-a * rstds[l] * dgam / M).float()
-                Cc[l] = (-a * sg / M + a * rstds[l] * mus[l] * dgam / M).float()
-            d_gamma.append(dgam.to(gdt[l]))
-            d_beta.append(sg.to(gdt[l]))
+            partial = _col_reduce2_partials(G, pre, starts[l], hw[l])
+            g32 = gammas[l].detach().float().contiguous()
+            with _with_device(pre):
+                rc = _lib.lib().tamtr_bn_backward_coeffs(
+                    partial.data_ptr(), partial.shape[0], float(B * hw[l]), g32.data_ptr(), mus[l].data_ptr(),
+                    rstds[l].data_ptr(), int(training), A[l].data_ptr(), Bc[l].data_ptr(), Cc[l].data_ptr(),
+                    dgb[l, 0].data_ptr(), dgb[l, 1].data_ptr(), d, _lib.stream_ptr(dev))
+            _lib.check(rc, "bn_backward_coeffs")
+            d_gamma.append(dgb[l, 0].to(gdt[l]))
+            d_beta.append(dgb[l, 1].to(gdt[l]))
         dpre = _affine_rows(G, pre if training else None, A, Bc if training else None, Cc, starts)
         d_x, d_w = [], []
         for l in range(n):

@@ -1,0 +1,70 @@
+"""GPU parity of the fused residual + LayerNorm kernels (csrc/layernorm.cu) against the reference's op sequence
+`norm(embed + tgt)` (ultralytics/nn/modules/transformer.py:548,553,537) evaluated by torch on the CPU in fp64/fp32."""
+import pytest
+import torch
+import torch.nn as nn
+
+from helpers import rel_l2
+from oracle import seeding
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, res, w, b, eps, probe):
+    x, w, b = x.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
+    r = None if res is None else res.double().requires_grad_()
+    y = torch.nn.functional.layer_norm(x if r is None else x + r, (x.shape[-1],), w, b, eps)
+    (y * probe.double()).sum().backward()
+    return y.detach(), x.grad, None if r is None else r.grad, w.grad, b.grad
+
+
+@pytest.mark.parametrize("rows_shape,d", [((16, 300), 512), ((2, 37), 256), ((1, 1), 128), ((3, 1000), 384)])
+@pytest.mark.parametrize("xdt,rdt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                     (torch.bfloat16, torch.bfloat16), (torch.float32, None)])
+def test_add_layer_norm_matches_reference(cuda_lib, rows_shape, d, xdt, rdt):
+    from tamtr_b200 import ops
+    shape = (*rows_shape, d)
+    x = (seeding.seeded_tensor(d, "x", shape) * 2 + 0.5).to(xdt)
+    res = None if rdt is None else seeding.seeded_tensor(d, "r", shape).to(rdt)
+    norm = nn.LayerNorm(d)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.2 * seeding.seeded_tensor(d, "w", (d,)))
+        norm.bias.copy_(0.1 * seeding.seeded_tensor(d, "b", (d,)))
+    probe = seeding.seeded_tensor(d, "p", shape)
+    y_ref, gx_ref, gr_ref, gw_ref, gb_ref = _ref(x.float(), None if res is None else res.float(), norm.weight.detach(),
+                                                 norm.bias.detach(), norm.eps, probe)
+    norm = norm.cuda()
+    xc = x.cuda().requires_grad_()
+    rc = None if res is None else res.cuda().requires_grad_()
+    y = ops.add_layer_norm(xc, rc, norm)
+    all_bf16 = xdt == torch.bfloat16 and rdt in (torch.bfloat16, None)
+    assert y.dtype == (torch.bfloat16 if all_bf16 else torch.float32)
+    (y.float() * probe.cuda()).sum().backward()
+    out_tol = 5e-3 if all_bf16 else 1e-5
+    assert rel_l2(y, y_ref) < out_tol, rel_l2(y, y_ref)
+    # gradients w.r.t. bf16 inputs are rounded once to bf16
+    assert rel_l2(xc.grad, gx_ref) < (5e-3 if xdt == torch.bfloat16 else 1e-5)
+    if rc is not None:
+        assert rc.grad.dtype == rdt and rel_l2(rc.grad, gr_ref) < (5e-3 if rdt == torch.bfloat16 else 1e-5)
+    par_tol = 5e-3 if all_bf16 else 1e-5             # an all-bf16 output hands the backward a bf16-rounded gradient
+    assert rel_l2(norm.weight.grad, gw_ref) < par_tol and rel_l2(norm.bias.grad, gb_ref) < par_tol
+
+
+def test_decoder_layer_uses_fused_norms(cuda_lib):
+    """3 fused forward + 3 fused backward launches per decoder layer."""
+    import tamtr_b200
+    from tamtr_b200 import _lib
+    from tamtr_b200.modules import DeformableTransformerDecoderLayer
+    layer = DeformableTransformerDecoderLayer(256, 8, 512, 0.0, nn.ReLU(), 3, 4).cuda()
+    shapes = [[20, 20], [10, 10], [5, 5]]
+    B, Lq = 2, 50
+    embed = torch.randn(B, Lq, 256, device="cuda", requires_grad=True)
+    feats = torch.randn(B, 525, 256, device="cuda")
+    refer = torch.rand(B, Lq, 4, device="cuda")
+    _lib.profile_enable(True)
+    out = layer(embed, refer, feats, shapes, None, None, torch.randn(B, Lq, 256, device="cuda"))
+    out.sum().backward()
+    torch.cuda.synchronize()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    assert prof["add_layernorm_fwd"][1] == 3 and prof["add_layernorm_bwd"][1] == 3
