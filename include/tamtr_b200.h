@@ -209,6 +209,10 @@ int tamtr_bn_backward_coeffs(const float *partial, int n_cta, double M, const fl
                              const double *rstd, int batch_stats, float *A, float *Bc, float *Cc, float *d_gamma,
                              float *d_beta, int d, void *stream);
 
+/* out[c] = sum_r g[r][c]: bias gradient of the decoder's Linear layers (g: [rows, n] f32|bf16, n % (16/sizeof) == 0,
+ * out f32 [n], zeroed by the call and accumulated with one fp32 reduction per column and CTA). */
+int tamtr_col_sum(const void *g, float *out, int dtype, int rows, int n, void *stream);
+
 /* Query-selection ranking (head.py:1229-1237: enc_output = Linear + LayerNorm over all tokens, enc_score_head, max over
  * classes), fused after the two GEMMs:
  *   E   [B*Lv, d] f32|bf16 = feats @ enc_output.0.weight^T (no bias, no validity mask)

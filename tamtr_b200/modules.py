@@ -51,7 +51,7 @@ class MLP(nn.Module):
     def forward(self, x):
         last = self.num_layers - 1
         for i, layer in enumerate(self.layers):
-            x = layer(x) if i == last else F.relu(layer(x))
+            x = ops.linear(x, layer) if i == last else F.relu(ops.linear(x, layer))
         return x
 
 
@@ -113,7 +113,7 @@ class MSDeformAttn(nn.Module):
             self.attention_weights.weight, self.attention_weights.bias, value_shapes,
             self.n_heads, self.n_levels, self.n_points)
         out = ops.ms_deform_attn(value, value_shapes, loc, attn, arena)
-        return self.output_proj(out)
+        return ops.linear(out, self.output_proj)
 
 
 class DeformableTransformerDecoderLayer(nn.Module):
@@ -147,7 +147,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
         return norm(x + drop(y))
 
     def forward_ffn(self, tgt):
-        tgt2 = self.linear2(self.dropout3(self.act(self.linear1(tgt))))
+        tgt2 = ops.linear(self.dropout3(self.act(ops.linear(tgt, self.linear1))), self.linear2)
         return self._add_norm(tgt, tgt2, self.dropout4, self.norm3)
 
     def forward(self, embed, refer_bbox, feats, shapes, padding_mask=None, attn_mask=None, query_pos=None,
@@ -155,8 +155,13 @@ class DeformableTransformerDecoderLayer(nn.Module):
         q = k = self.with_pos_embed(embed, query_pos)
         # need_weights=False: the reference discards the averaged attention map ([0] only, transformer.py:546-547),
         # so the fused SDPA kernels can be used; the output is the same.
-        tgt = self.self_attn(q.transpose(0, 1), k.transpose(0, 1), embed.transpose(0, 1), attn_mask=attn_mask,
-                             need_weights=False)[0].transpose(0, 1)
+        mha = self.self_attn
+        if (embed.is_cuda and mha._qkv_same_embed_dim and mha.in_proj_bias is not None and mha.bias_k is None
+                and not mha.add_zero_attn):
+            tgt = ops.self_attention(mha, q, embed, attn_mask)
+        else:
+            tgt = mha(q.transpose(0, 1), k.transpose(0, 1), embed.transpose(0, 1), attn_mask=attn_mask,
+                      need_weights=False)[0].transpose(0, 1)
         embed = self._add_norm(embed, tgt, self.dropout1, self.norm1)
         tgt = self.cross_attn(self.with_pos_embed(embed, query_pos), refer_bbox.unsqueeze(2), feats, shapes,
                               padding_mask, projected_value, arena)

@@ -445,6 +445,117 @@ def max_sigmoid_gate(embed, guide, bias, nh, use_tensor_cores=None):
     return _MaxSigmoidFn.apply(embed, guide, bias, nh, use_tensor_cores)
 
 
+# ------------------------------------------------------------------------------------ Linear layers of the decoder
+def _lowp(*tensors):
+    """dtype a Linear computes in: the autocast dtype when autocast is on (as F.linear would), else the input's."""
+    return torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else tensors[0].dtype
+
+
+def col_sum(g2):
+    """sum over rows of g2 [rows, n] -> fp32 [n] (tamtr_col_sum); library reduction for shapes the kernel does not take."""
+    rows, n = g2.shape
+    np_ = 4 if g2.dtype == torch.float32 else 8
+    if g2.dtype not in (torch.float32, torch.bfloat16) or n % np_ != 0 or g2.data_ptr() % 16 != 0 or not g2.is_contiguous():
+        return g2.float().sum(0)
+    out = torch.empty(n, dtype=torch.float32, device=g2.device)
+    with _with_device(g2):
+        _lib.check(_lib.lib().tamtr_col_sum(g2.data_ptr(), out.data_ptr(), _lib.dtype_code(g2), rows, n,
+                                            _lib.stream_ptr(g2.device)), "col_sum")
+    return out
+
+
+class _LinearFn(torch.autograd.Function):
+    """F.linear with the same arithmetic (library GEMMs, bias in the GEMM epilogue) whose backward computes the bias
+    gradient with tamtr_col_sum instead of the library's generic reduction."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lp = _lowp(x)
+        x2 = x.reshape(-1, x.shape[-1]).to(lp)
+        w = weight.to(lp)
+        y = torch.addmm(bias.to(lp), x2, w.t()) if bias is not None else x2 @ w.t()
+        ctx.save_for_backward(x2, w)
+        ctx.meta = (x.shape, x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x2, w = ctx.saved_tensors
+        xshape, xdt, wdt, bdt = ctx.meta
+        g2 = g.reshape(-1, g.shape[-1]).to(w.dtype).contiguous()
+        dx = (g2 @ w).view(xshape).to(xdt) if ctx.needs_input_grad[0] else None
+        dw = (g2.t() @ x2).to(wdt) if ctx.needs_input_grad[1] else None
+        db = col_sum(g2).to(bdt) if (bdt is not None and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def linear(x, layer):
+    """`layer(x)` for an nn.Linear on CUDA tensors (transformer.py:166-176, 535-537, ...)."""
+    if not x.is_cuda:
+        return layer(x)
+    return _LinearFn.apply(x, layer.weight, layer.bias)
+
+
+class _InProjFn(torch.autograd.Function):
+    """Packed input projection of nn.MultiheadAttention when query and key share their input (decoder self-attention,
+    transformer.py:544-547: q = k = embed + pos, v = embed): two GEMMs, gradients written into ONE [3d, d] / [3d]
+    buffer so that in_proj_weight / in_proj_bias receive a single gradient tensor."""
+
+    @staticmethod
+    def forward(ctx, xqk, xv, weight, bias):
+        lp = _lowp(xqk)
+        d = weight.shape[1]
+        a = xqk.reshape(-1, d).to(lp)
+        c = xv.reshape(-1, d).to(lp)
+        w = weight.to(lp)
+        b = bias.to(lp)
+        qk = torch.addmm(b[:2 * d], a, w[:2 * d].t())
+        v = torch.addmm(b[2 * d:], c, w[2 * d:].t())
+        ctx.save_for_backward(a, c, w)
+        ctx.meta = (xqk.shape, xqk.dtype, xv.dtype, weight.dtype, bias.dtype)
+        lead = xqk.shape[:-1]
+        return qk.view(*lead, 2 * d), v.view(*lead, d)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gqk, gv):
+        a, c, w = ctx.saved_tensors
+        xshape, qdt, vdt, wdt, bdt = ctx.meta
+        d = w.shape[1]
+        gqk2 = gqk.reshape(-1, 2 * d).to(w.dtype).contiguous()
+        gv2 = gv.reshape(-1, d).to(w.dtype).contiguous()
+        dxqk = (gqk2 @ w[:2 * d]).view(xshape).to(qdt) if ctx.needs_input_grad[0] else None
+        dxv = (gv2 @ w[2 * d:]).view(xshape).to(vdt) if ctx.needs_input_grad[1] else None
+        dw = db = None
+        if ctx.needs_input_grad[2]:
+            dw = torch.empty_like(w)
+            torch.mm(gqk2.t(), a, out=dw[:2 * d])
+            torch.mm(gv2.t(), c, out=dw[2 * d:])
+            dw = dw.to(wdt)
+        if ctx.needs_input_grad[3]:
+            db = torch.cat([col_sum(gqk2), col_sum(gv2)]).to(bdt)
+        return dxqk, dxv, dw, db
+
+
+def self_attention(mha, x_qk, x_v, attn_mask=None):
+    """nn.MultiheadAttention(x_qk, x_qk, x_v, attn_mask=..., need_weights=False)[0] for batch-first [B, L, d] inputs
+    (the reference feeds it sequence-first through two transposes, transformer.py:546): packed in-projection,
+    F.scaled_dot_product_attention, out-projection.  attn_mask: bool [L, L] with True = blocked (nn.MultiheadAttention's
+    convention) or an additive float mask."""
+    B, L, d = x_qk.shape
+    H = mha.num_heads
+    qk, v = _InProjFn.apply(x_qk, x_v, mha.in_proj_weight, mha.in_proj_bias)
+    q = qk[..., :d].view(B, L, H, d // H).transpose(1, 2)
+    k = qk[..., d:].view(B, L, H, d // H).transpose(1, 2)
+    v = v.view(B, L, H, d // H).transpose(1, 2)
+    if attn_mask is not None and attn_mask.dtype == torch.bool:
+        attn_mask = attn_mask.logical_not()                            # SDPA: True = attend
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask,
+                                                         dropout_p=mha.dropout if mha.training else 0.0)
+    return linear(o.transpose(1, 2).reshape(B, L, d), mha.out_proj)
+
+
 # ------------------------------------------------------------------------------------ residual add + LayerNorm
 def add_layer_norm_supported(x, d):
     return x.is_cuda and d % 128 == 0 and 128 <= d <= 512 and x.dtype in (torch.float32, torch.bfloat16)

@@ -68,3 +68,51 @@ def test_decoder_layer_uses_fused_norms(cuda_lib):
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     assert prof["add_layernorm_fwd"][1] == 3 and prof["add_layernorm_bwd"][1] == 3
+
+
+# ---------------------------------------------------------------------------------------------- Linear / self-attention
+@pytest.mark.parametrize("rows,n,dt", [(4800, 512, torch.bfloat16), (4800, 1024, torch.float32), (37, 8, torch.bfloat16),
+                                       (1, 1536, torch.float32), (1000, 136, torch.bfloat16)])
+def test_col_sum(cuda_lib, rows, n, dt):
+    from tamtr_b200 import ops
+    g = seeding.seeded_tensor(rows, "g", (rows, n)).to(dt)
+    got = ops.col_sum(g.cuda())
+    assert got.dtype == torch.float32
+    assert rel_l2(got, g.double().sum(0)) < 1e-6
+
+
+def test_linear_and_self_attention_match_the_modules(cuda_lib):
+    """ops.linear / ops.self_attention against nn.Linear / nn.MultiheadAttention called the way the reference calls
+    them (sequence-first through transposes, bool mask with True = blocked; transformer.py:544-547), on the CPU."""
+    from tamtr_b200 import ops
+    torch.manual_seed(0)
+    B, L, d, H = 3, 50, 256, 8
+    mha = nn.MultiheadAttention(d, H)
+    lin = nn.Linear(d, 72)
+    x = seeding.seeded_tensor(1, "x", (B, L, d))
+    pos = seeding.seeded_tensor(1, "pos", (B, L, d))
+    mask = torch.rand(L, L) < 0.2
+    mask.fill_diagonal_(False)
+    probe = seeding.seeded_tensor(1, "p", (B, L, 72))
+
+    def run(mod_mha, mod_lin, xx, pp, mm, pr, ours):
+        xx = xx.clone().requires_grad_()
+        q = xx + pp
+        if ours:
+            t = ops.self_attention(mod_mha, q, xx, mm)
+            y = ops.linear(t, mod_lin)
+        else:
+            t = mod_mha(q.transpose(0, 1), q.transpose(0, 1), xx.transpose(0, 1), attn_mask=mm)[0].transpose(0, 1)
+            y = mod_lin(t)
+        (y * pr).sum().backward()
+        return y.detach(), xx.grad, [p.grad.clone() for p in list(mod_mha.parameters()) + list(mod_lin.parameters())]
+
+    y_ref, gx_ref, gp_ref = run(mha, lin, x, pos, mask, probe, False)
+    mha.zero_grad()
+    lin.zero_grad()
+    mha.cuda()
+    lin.cuda()
+    y, gx, gp = run(mha, lin, x.cuda(), pos.cuda(), mask.cuda(), probe.cuda(), True)
+    assert rel_l2(y, y_ref) < 1e-5 and rel_l2(gx, gx_ref) < 1e-5
+    for a, b in zip(gp, gp_ref):
+        assert rel_l2(a, b) < 1e-5
