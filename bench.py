@@ -46,6 +46,48 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS burst: the kernel is timed alone)"
+    return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
+def gate_conv_roofline(dev, iters=20):
+    """Kernel 2 (the tensor-bound one, BASELINE.json configs[2] at its largest point: 6400 image tokens x C=256, 10 text
+    tokens, batch 16): the fused 3x3 projection + BatchNorm affine + text gate on tcgen05.  Device time per launch from
+    the library's own CUDA events on the launching stream; three rotating buffer sets (315 MB > L2)."""
+    from tamtr_b200 import _lib, ops
+    B, C, nh, H, W, N = 16, 256, 8, 80, 80, 10
+    g = torch.Generator().manual_seed(7)
+    xs = [torch.randn(B, C, H, W, generator=g).bfloat16().to(dev).contiguous(memory_format=torch.channels_last)
+          for _ in range(3)]
+    w = (torch.randn(C, C, 3, 3, generator=g) * (2.0 / (9 * C)) ** 0.5).bfloat16().to(dev)
+    s = (1.0 + 0.1 * torch.randn(C, generator=g)).to(dev)
+    t = (0.1 * torch.randn(C, generator=g)).to(dev)
+    guide = (0.3 * torch.randn(B, N, nh, C // nh, generator=g)).to(dev)
+    bias = torch.zeros(nh, device=dev)
+    with torch.no_grad():
+        gates = [ops.max_sigmoid_gate(x, guide, bias, nh) for x in xs]
+        for i in range(5):
+            ops.gate_conv3x3(xs[i % 3], w, s, t, gates[i % 3], nh)
+        torch.cuda.synchronize(dev)
+        _lib.profile_enable(True)
+        for i in range(iters):
+            ops.gate_conv3x3(xs[i % 3], w, s, t, gates[i % 3], nh)
+        torch.cuda.synchronize(dev)
+        ms, n = _lib.profile_read()["gate_conv3x3_tc_fwd"]
+        _lib.profile_enable(False)
+    flops = 2.0 * B * H * W * 9 * C * C
+    us = ms / n * 1e3
+    peak, src = tensor_peak()
+    return {"bound": "tensor", "kernel": "gate_conv3x3_pair_kernel (tcgen05.mma cta_group::2, TMEM, TMA)",
+            "achieved": flops / us / 1e6, "peak": peak, "unit": "TFLOP/s", "frac": flops / us / 1e6 / peak,
+            "traffic": None, "peak_source": src, "algorithmic_flops": flops, "avg_us": us, "launches": n,
+            "workload": "BTA-PAN text-guided 3x3 projection + BN + gate, B=16 C=256 80x80 (6400 tokens) N=10, bf16"}
+
+
 def synthetic_targets(seed, B, lo=20, hi=100):
     """VisDrone-shaped ground truth: n ~ U{20..100} small boxes per image, 10 classes."""
     g = torch.Generator().manual_seed(seed)
@@ -340,6 +382,14 @@ def main():
                         "ms_per_step": e2e_sec / args.steps * 1e3},
                 "gpu_launches": int(launches),
                 "roofline": roof, "kernels": per_kernel}
+        if ws == 1:
+            try:
+                line["roofline_tensor"] = gate_conv_roofline(dev)
+                ncu = os.path.join(ROOT, "profiles", "traffic.json")
+                if os.path.exists(ncu):
+                    line["roofline_tensor"]["traffic"] = json.load(open(ncu)).get("gate_conv_dram_bytes_per_launch")
+            except Exception as e:      # the headline line must not depend on the secondary kernel
+                line["roofline_tensor"] = {"error": str(e)[:200]}
         if not args.no_cpu_baseline and ws == 1:
             cores = os.cpu_count() or 1
             ips, s = cpu_reference_step(2, cores, 2, 1)

@@ -116,6 +116,35 @@ class MSDeformAttn(nn.Module):
         return ops.linear(out, self.output_proj)
 
 
+# The forward() methods below are also bound onto the REFERENCE's classes by patch.enable(), so they may only touch
+# attributes the reference's __init__ creates: helpers are module-level functions, not methods.
+def _add_norm(layer, x, y, drop, norm):
+    """norm(x + dropout(y)): fused residual + LayerNorm kernel (dropout is the identity in TAM-TR, p = 0)."""
+    if ((drop.p == 0.0 or not layer.training) and ops.add_layer_norm_supported(x, x.shape[-1])
+            and isinstance(norm, nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
+            and tuple(norm.normalized_shape) == (x.shape[-1],)):
+        return ops.add_layer_norm(x, y, norm)
+    return norm(x + drop(y))
+
+
+def _ffn(layer, tgt):
+    tgt2 = ops.linear(layer.dropout3(layer.act(ops.linear(tgt, layer.linear1))), layer.linear2)
+    return _add_norm(layer, tgt, tgt2, layer.dropout4, layer.norm3)
+
+
+def _folded_bn(block, bn):
+    """BatchNorm2d in eval mode as a per-channel affine (fp32), cached on the block until a parameter or statistic
+    changes."""
+    key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+    hit = block.__dict__.get("_tamtr_fold_cache")
+    if hit is None or hit[0] != key:
+        s = bn.weight.detach().float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+        t = bn.bias.detach().float() - bn.running_mean.float() * s
+        hit = (key, s.contiguous(), t.contiguous())
+        block.__dict__["_tamtr_fold_cache"] = hit
+    return hit[1], hit[2]
+
+
 class DeformableTransformerDecoderLayer(nn.Module):
     """Self-attention -> deformable cross-attention -> FFN, post-norm (transformer.py:498-558)."""
 
@@ -138,17 +167,8 @@ class DeformableTransformerDecoderLayer(nn.Module):
     def with_pos_embed(tensor, pos):
         return tensor if pos is None else tensor + pos
 
-    def _add_norm(self, x, y, drop, norm):
-        """norm(x + dropout(y)): fused residual + LayerNorm kernel (dropout is the identity in TAM-TR, p = 0)."""
-        if ((drop.p == 0.0 or not self.training) and ops.add_layer_norm_supported(x, x.shape[-1])
-                and isinstance(norm, nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
-                and tuple(norm.normalized_shape) == (x.shape[-1],)):
-            return ops.add_layer_norm(x, y, norm)
-        return norm(x + drop(y))
-
     def forward_ffn(self, tgt):
-        tgt2 = ops.linear(self.dropout3(self.act(ops.linear(tgt, self.linear1))), self.linear2)
-        return self._add_norm(tgt, tgt2, self.dropout4, self.norm3)
+        return _ffn(self, tgt)
 
     def forward(self, embed, refer_bbox, feats, shapes, padding_mask=None, attn_mask=None, query_pos=None,
                 projected_value=None, arena=None):
@@ -162,11 +182,11 @@ class DeformableTransformerDecoderLayer(nn.Module):
         else:
             tgt = mha(q.transpose(0, 1), k.transpose(0, 1), embed.transpose(0, 1), attn_mask=attn_mask,
                       need_weights=False)[0].transpose(0, 1)
-        embed = self._add_norm(embed, tgt, self.dropout1, self.norm1)
+        embed = _add_norm(self, embed, tgt, self.dropout1, self.norm1)
         tgt = self.cross_attn(self.with_pos_embed(embed, query_pos), refer_bbox.unsqueeze(2), feats, shapes,
                               padding_mask, projected_value, arena)
-        embed = self._add_norm(embed, tgt, self.dropout2, self.norm2)
-        return self.forward_ffn(embed)
+        embed = _add_norm(self, embed, tgt, self.dropout2, self.norm2)
+        return _ffn(self, embed)
 
 
 class _DecoderBase(nn.Module):
@@ -280,17 +300,6 @@ class MaxSigmoidAttnBlock(nn.Module):
         self.proj_conv = _ConvBN(c1, c2, 3)
         self.scale = nn.Parameter(torch.ones(1, nh, 1, 1)) if scale else 1.0
 
-    def _folded_bn(self, bn):
-        """BatchNorm2d in eval mode as a per-channel affine (fp32), cached until a parameter or statistic changes."""
-        key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
-        hit = getattr(self, "_fold_cache", None)
-        if hit is None or hit[0] != key:
-            s = bn.weight.detach().float() * torch.rsqrt(bn.running_var.float() + bn.eps)
-            t = bn.bias.detach().float() - bn.running_mean.float() * s
-            hit = (key, s.contiguous(), t.contiguous())
-            self._fold_cache = hit
-        return hit[1], hit[2]
-
     def forward(self, x, guide):
         bs, _, h, w = x.shape
         guide = self.gl(guide).view(bs, -1, self.nh, self.hc)
@@ -302,7 +311,7 @@ class MaxSigmoidAttnBlock(nn.Module):
             bn = pc.bn
             if not (self.training or torch.is_grad_enabled()) and bn.running_var is not None:
                 # inference: conv + folded BatchNorm + gate in one tensor-core kernel (channels-last output)
-                s, t = self._folded_bn(bn)
+                s, t = _folded_bn(self, bn)
                 return ops.gate_conv3x3(x, pc.conv.weight, s, t, aw, self.nh)
             y = bn(ops.conv3x3_tc(x, pc.conv.weight))
         else:
