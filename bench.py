@@ -107,12 +107,37 @@ def synthetic_inputs(seed, B, dtype):
     return xs, text
 
 
-def loss_fn(out):
-    """Surrogate scalar every head output feeds (same one the parity tests use); the Hungarian-matched detection
-    loss is a 'next' row of SURVEY.md section 8(f)."""
+def surrogate_loss_fn(out):
+    """Cheap scalar every head output feeds (--loss surrogate; the round-1 numbers before the device-side matcher)."""
     db, ds, eb, es = out[:4]
     return (db.float().square().mean() + 0.1 * ds.float().sigmoid().mean()
             + eb.float().square().mean() + 0.1 * es.float().sigmoid().mean())
+
+
+def split_outputs(out):
+    """ultralytics/nn/tasks.py:606-621: split the denoising queries off and prepend the encoder proposals."""
+    dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta = out
+    dn_bboxes = dn_scores = None
+    if dn_meta is not None:
+        dn_bboxes, dec_bboxes = torch.split(dec_bboxes, dn_meta["dn_num_split"], dim=2)
+        dn_scores, dec_scores = torch.split(dec_scores, dn_meta["dn_num_split"], dim=2)
+    dec_bboxes = torch.cat([enc_bboxes.unsqueeze(0), dec_bboxes])
+    dec_scores = torch.cat([enc_scores.unsqueeze(0), dec_scores])
+    return dec_bboxes, dec_scores, dn_bboxes, dn_scores, dn_meta
+
+
+def make_detection_loss(batch, dev):
+    """The reference's training loss (nn/tasks.py:578-624: RTDETRDetectionLoss(use_vfl=True) on the encoder proposals +
+    every decoder layer + the denoising queries) with the Hungarian matching on the device."""
+    from tamtr_b200.loss import RTDETRDetectionLoss
+    crit = RTDETRDetectionLoss(nc=NC, use_vfl=True)
+    targets = {"cls": batch["cls"].to(dev), "bboxes": batch["bboxes"].to(dev), "gt_groups": batch["gt_groups"]}
+
+    def fn(out):
+        db, ds, dnb, dns, meta = split_outputs(out)
+        f = (lambda t: None if t is None else t.float())
+        return sum(crit((db.float(), ds.float()), targets, dn_bboxes=f(dnb), dn_scores=f(dns), dn_meta=meta).values())
+    return fn
 
 
 # ----------------------------------------------------------------------------------------------------- clocks
@@ -165,9 +190,9 @@ def sampler_bytes(B, Lq, value_bytes=2, L=3, P=4):
 
 
 # ----------------------------------------------------------------------------------------------------- CPU port
-def cpu_reference_step(sample_images, threads, steps, warmup, seed=1234):
+def cpu_reference_step(sample_images, threads, steps, warmup, seed=1234, loss_kind="surrogate"):
     """The reference's own PyTorch path on the host cores (oracle port): fp32, train mode, fwd + bwd."""
-    from oracle import head_ref                 # the ONLY thing on this path: no product code, no CUDA
+    from oracle import head_ref, loss_ref       # the ONLY things on this path: no product code, no CUDA
     torch.set_num_threads(threads)
     torch.manual_seed(seed)
     sd = head_ref.meh_state_dict(NC, CH, HD, NDL, NH, seed=seed)
@@ -179,7 +204,13 @@ def cpu_reference_step(sample_images, threads, steps, warmup, seed=1234):
         t0 = time.perf_counter()
         cdn = head_ref.cdn_group(batch, NC, NQ, sd["denoising_class_embed.weight"])
         out = head_ref.head(sd, "", xs, NQ, NDL, NH, training=True, text=text, cdn=cdn)
-        loss = head_ref.surrogate_loss(*out)
+        if loss_kind == "surrogate":
+            loss = head_ref.surrogate_loss(*out)
+        else:       # the reference's RTDETRDetectionLoss with scipy's linear_sum_assignment on the host (ops.py:117)
+            meta = head_ref.cdn_meta(batch, NQ) if cdn is not None else None
+            db, ds, dnb, dns, meta = split_outputs((*out, meta))
+            loss = sum(loss_ref.rtdetr_detection_loss(db, ds, batch["bboxes"], batch["cls"], batch["gt_groups"], NC,
+                                                      dn_bboxes=dnb, dn_scores=dns, dn_meta=meta).values())
         for v in sd.values():
             if v.requires_grad:
                 v.grad = None
@@ -197,12 +228,12 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample = 2
     steps, warmup = min(args.steps, 8), min(args.warmup, 1)
-    ips, sec = cpu_reference_step(sample, cores, steps, warmup)
+    ips, sec = cpu_reference_step(sample, cores, steps, warmup, loss_kind=args.loss)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(),
+        "config": config_dict(args.loss),
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} images/step of the same workload (S-yaml head, train fwd+bwd, fp32), "
                                    f"{steps} steps after {warmup} warm-up, torch CPU with {cores} threads"},
@@ -210,8 +241,13 @@ def run_reference(args):
     }), flush=True)
 
 
-def config_dict():
-    return {"workload": "TAM-TR MEH head (ManbaWorldDecoder nc=10 ch=[128,256,512] hd=512 nq=100 ndl=3, VSS=identity) "
+LOSS_NAMES = {"detection": "RTDETRDetectionLoss(use_vfl) on encoder proposals + 3 decoder layers + denoising queries, "
+                           "Hungarian matching per layer (nn/tasks.py:578-624)",
+              "surrogate": "mean-square / mean-sigmoid scalar over all outputs"}
+
+
+def config_dict(loss_kind="surrogate"):
+    return {"loss": LOSS_NAMES[loss_kind], "workload": "TAM-TR MEH head (ManbaWorldDecoder nc=10 ch=[128,256,512] hd=512 nq=100 ndl=3, VSS=identity) "
                         "+ text-guided cls branch, train fwd+bwd, CDN 20..100 gt/img, pyramid 160^2/80^2/40^2 @640^2",
             "batch_per_gpu": BATCH_PER_GPU, "text_tokens": NC, "text_dim": 512,
             "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush"}
@@ -225,6 +261,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="tamtr_b200", choices=["tamtr_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--loss", default="surrogate", choices=["detection", "surrogate"],
+                    help="what drives the backward.  surrogate (default): a cheap scalar over all head outputs, so that the "
+                         "timed region is the head's forward + backward (BASELINE.json's metric); detection: the "
+                         "reference's RTDETRDetectionLoss on top (Hungarian matching on the device; scipy on the host in "
+                         "the reference arm).  With the default, the detection-loss step is also timed and reported as "
+                         "`with_detection_loss`.")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--launch-list", action="store_true",
                     help="eager steps only (no e2e / instrumented pass / CPU baseline): the command to run under "
@@ -263,6 +305,7 @@ def main():
     plan = model.plan_cdn(batch)
     Lq = plan.n_dn + NQ
 
+    loss_fn = make_detection_loss(batch, dev) if args.loss == "detection" else surrogate_loss_fn
     step = dp.HeadTrainStep(model, loss_fn, (host[0][0], host[0][1], plan), autocast=torch.bfloat16,
                             use_graph=not (args.no_graph or args.launch_list))
     if args.launch_list:
@@ -375,13 +418,33 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": ws, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": dict(config_dict(), queries=Lq, cuda_graph=step.graph is not None,
+                "config": dict(config_dict(args.loss), queries=Lq, cuda_graph=step.graph is not None,
                                parallelism=f"dp{ws}" if ws > 1 else "single"),
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": e2e_sec / args.steps * 1e3},
                 "gpu_launches": int(launches),
                 "roofline": roof, "kernels": per_kernel}
+        if ws == 1 and args.loss == "surrogate":
+            try:        # the same step with the reference's detection loss on top (device-side Hungarian matching)
+                step2 = dp.HeadTrainStep(model, make_detection_loss(batch, dev), (host[0][0], host[0][1], plan),
+                                         autocast=torch.bfloat16, use_graph=not args.no_graph)
+                for _ in range(args.warmup):
+                    step2.run()
+                torch.cuda.synchronize(dev)
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                d0.record()
+                for _ in range(args.steps):
+                    step2.run()
+                d1.record()
+                torch.cuda.synchronize(dev)
+                dsec = d0.elapsed_time(d1) / 1e3
+                line["with_detection_loss"] = {"value": B * args.steps / dsec, "unit": "images/s",
+                                               "ms_per_step": dsec / args.steps * 1e3, "loss": LOSS_NAMES["detection"],
+                                               "loss_value": float(step2.loss)}
+                del step2
+            except Exception as e:
+                line["with_detection_loss"] = {"error": str(e)[:200]}
         if ws == 1:
             try:
                 line["roofline_tensor"] = gate_conv_roofline(dev)
@@ -392,7 +455,7 @@ def main():
                 line["roofline_tensor"] = {"error": str(e)[:200]}
         if not args.no_cpu_baseline and ws == 1:
             cores = os.cpu_count() or 1
-            ips, s = cpu_reference_step(2, cores, 2, 1)
+            ips, s = cpu_reference_step(2, cores, 2, 1, loss_kind=args.loss)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": "2 images/step of the same workload (fp32 train fwd+bwd), 2 timed steps "
                                               f"after 1 warm-up, torch CPU {cores} threads, {s:.1f} s/step"}

@@ -246,15 +246,16 @@ int tamtr_add_layernorm_backward(const void *dy, int dy_dtype, const float *z, c
  * Query <-> ground-truth matching on the device: scipy.optimize.linear_sum_assignment as the reference calls it per
  * image on the host (ultralytics/models/utils/ops.py:116-121), same algorithm (Crouse / Jonker-Volgenant shortest
  * augmenting path), fp64 arithmetic and tie order, one warp per (layer, image).
- *   C            f32 [n_layers, bs, nq, total_gt]  cost matrices (finite values), image b owns the columns
- *                [gt_start[b], gt_start[b+1])
+ *   C            f32 [n_layers, bs, nq, c_cols]  cost matrices (finite values).  padded = 0: c_cols = total number of
+ *                gts and image b owns the columns [gt_start[b], gt_start[b+1]) (the reference's layout, ops.py:104-116);
+ *                padded = 1: c_cols >= max_gt and image b owns the columns [0, n_gt[b]) of its own matrix
  *   gt_start_dev int32 [bs+1] (device), out_start_dev int32 [bs] (device): first output slot of image b
  *                = sum_{b' < b} min(nq, n_gt[b'])
  *   out_q, out_g int64 [n_layers, out_layer_stride]: matched (query index, GLOBAL gt index) pairs of each image in
  *                ascending query order, min(nq, n_gt[b]) pairs per image
  *   max_gt       the largest n_gt[b] (host) */
 int tamtr_linear_sum_assignment(const float *C, const int *gt_start_dev, const int *out_start_dev, long long *out_q,
-                                long long *out_g, int n_layers, int bs, int nq, int total_gt, int max_gt,
+                                long long *out_g, int n_layers, int bs, int nq, int c_cols, int padded, int max_gt,
                                 long long out_layer_stride, void *stream);
 
 #ifdef __cplusplus

@@ -54,7 +54,7 @@ _SIGNATURES = {
     "tamtr_bn_backward_coeffs": (ctypes.c_int, [_fp, _i, ctypes.c_double, _fp, _vp, _vp, _i, _fp, _fp, _fp, _fp, _fp,
                                                 _i, _vp]),
     "tamtr_col_sum": (ctypes.c_int, [_vp, _fp, _i, _i, _i, _vp]),
-    "tamtr_linear_sum_assignment": (ctypes.c_int, [_fp, _vp, _vp, _vp, _vp] + [_i] * 5 + [ctypes.c_longlong, _vp]),
+    "tamtr_linear_sum_assignment": (ctypes.c_int, [_fp, _vp, _vp, _vp, _vp] + [_i] * 6 + [ctypes.c_longlong, _vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }
 

@@ -35,13 +35,14 @@ __device__ __forceinline__ bool asg_better(const AsgKey &b, const AsgKey &a) {
 
 __global__ void __launch_bounds__(kAsgThreads)
 lsap_kernel(const float *__restrict__ C, const int *__restrict__ gt_start, const int *__restrict__ out_start,
-            long long *__restrict__ out_q, long long *__restrict__ out_g, int bs, int nq, int total_gt, int max_cols,
-            int stage_elems, long long out_layer_stride) {
+            long long *__restrict__ out_q, long long *__restrict__ out_g, int bs, int nq, int c_cols, int padded,
+            int max_cols, int stage_elems, long long out_layer_stride) {
     extern __shared__ unsigned char smem[];
     const int b = blockIdx.x, layer = blockIdx.y;
     const int g0 = gt_start[b], ng = gt_start[b + 1] - g0;
     if (ng <= 0) return;
-    const float *Cb = C + ((size_t)layer * bs + b) * (size_t)nq * total_gt + g0;   // Cb[q * total_gt + g]
+    const int total_gt = c_cols;                                                   // row pitch of C
+    const float *Cb = C + ((size_t)layer * bs + b) * (size_t)nq * total_gt + (padded ? 0 : g0);   // Cb[q * pitch + g]
     const bool rows_are_gt = ng < nq;       // SciPy transposes only when there are MORE rows (queries) than columns
     const int nr = rows_are_gt ? ng : nq, nc = rows_are_gt ? nq : ng;
 
@@ -160,9 +161,10 @@ using namespace tamtr;
 
 extern "C" int tamtr_linear_sum_assignment(const float *C, const int *gt_start_dev, const int *out_start_dev,
                                            long long *out_q, long long *out_g, int n_layers, int bs, int nq,
-                                           int total_gt, int max_gt, long long out_layer_stride, void *stream) {
+                                           int c_cols, int padded, int max_gt, long long out_layer_stride,
+                                           void *stream) {
     TAMTR_CHECK_ARG(C && gt_start_dev && out_start_dev && out_q && out_g, TAMTR_E_BADARG, "linear_sum_assignment: null pointer");
-    TAMTR_CHECK_ARG(n_layers > 0 && bs > 0 && nq > 0 && total_gt > 0 && max_gt > 0 && max_gt <= total_gt, TAMTR_E_BADARG,
+    TAMTR_CHECK_ARG(n_layers > 0 && bs > 0 && nq > 0 && c_cols > 0 && max_gt > 0 && max_gt <= c_cols, TAMTR_E_BADARG,
                     "linear_sum_assignment: bad sizes");
     TAMTR_CHECK_ARG(bs <= 65535 && n_layers <= 65535, TAMTR_E_UNSUPPORTED, "linear_sum_assignment: grid too large");
     const int max_cols = nq > max_gt ? nq : max_gt;
@@ -177,7 +179,7 @@ extern "C" int tamtr_linear_sum_assignment(const float *C, const int *gt_start_d
     const size_t smem = fixed + want;
     TAMTR_CUDA_OK(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lsap_kernel<<<dim3(bs, n_layers), kAsgThreads, smem, (cudaStream_t)stream>>>(
-        C, gt_start_dev, out_start_dev, out_q, out_g, bs, nq, total_gt, max_cols, (int)(want / sizeof(float)),
+        C, gt_start_dev, out_start_dev, out_q, out_g, bs, nq, c_cols, padded, max_cols, (int)(want / sizeof(float)),
         out_layer_stride);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());

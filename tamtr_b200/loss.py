@@ -97,6 +97,13 @@ class _Groups:
                                     or [torch.zeros(0, dtype=torch.long)]).to(device)
         self.max_gt = max([int(n) for n in gt_groups] + [0])
         self.total_gt = starts[-1]
+        # global gt index of column g of image b's own (padded) cost matrix; padding columns repeat a valid index
+        pad = torch.zeros(len(gt_groups), max(self.max_gt, 1), dtype=torch.long)
+        for b, n in enumerate(gt_groups):
+            if n:
+                pad[b, :n] = torch.arange(starts[b], starts[b] + int(n))
+                pad[b, n:] = starts[b]
+        self.pad_index = pad.to(device)
 
     @classmethod
     def get(cls, gt_groups, nq, device):
@@ -109,23 +116,24 @@ class _Groups:
         return hit
 
 
-def linear_sum_assignment(C, gt_groups):
-    """C: [n_layers, bs, nq, total_gt] fp32 cost matrices on the device, image b owns the next gt_groups[b] columns.
+def linear_sum_assignment(C, gt_groups, padded=False):
+    """C: [n_layers, bs, nq, total_gt] fp32 cost matrices on the device, image b owns the next gt_groups[b] columns
+    (padded=True: [n_layers, bs, nq, >= max_gt], image b owns the first gt_groups[b] columns of its own matrix).
     Returns (image idx [P], query idx [n_layers, P], global gt idx [n_layers, P]) with P = sum_b min(nq, gt_groups[b]);
     per image the pairs are in ascending query order, exactly what scipy.optimize.linear_sum_assignment returns for
     C[l, b][:, columns of b] (ops.py:116-121)."""
     _lib.require_cuda(C)
-    n_layers, bs, nq, total_gt = C.shape
+    n_layers, bs, nq, c_cols = C.shape
     grp = _Groups.get(gt_groups, nq, C.device)
-    assert grp.total_gt == total_gt and len(gt_groups) == bs
+    assert len(gt_groups) == bs and (c_cols >= grp.max_gt if padded else grp.total_gt == c_cols)
     out_q = torch.empty(n_layers, grp.n_pairs, dtype=torch.long, device=C.device)
     out_g = torch.empty_like(out_q)
     if grp.n_pairs:
         C = C.contiguous().float()
         with torch.cuda.device(C.device):
             rc = _lib.lib().tamtr_linear_sum_assignment(C.data_ptr(), grp.gt_start.data_ptr(), grp.out_start.data_ptr(),
-                                                        out_q.data_ptr(), out_g.data_ptr(), n_layers, bs, nq, total_gt,
-                                                        grp.max_gt, grp.n_pairs, _lib.stream_ptr(C.device))
+                                                        out_q.data_ptr(), out_g.data_ptr(), n_layers, bs, nq, c_cols,
+                                                        int(padded), grp.max_gt, grp.n_pairs, _lib.stream_ptr(C.device))
         _lib.check(rc, "linear_sum_assignment")
     return grp.pair_image, out_q, out_g
 
@@ -164,10 +172,37 @@ class HungarianMatcher(nn.Module):
         C = self.cost_gain['class'] * cost_class + self.cost_gain['bbox'] * cost_bbox + self.cost_gain['giou'] * cost_giou
         return torch.where(torch.isfinite(C), C, torch.zeros((), dtype=C.dtype, device=C.device))
 
+    def cost_matrix_per_image(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, gt_groups):
+        """[n_layers, bs, nq, .] -> [n_layers, bs, nq, max_gt]: only each image's OWN ground truths (the reference's
+        [bs*nq, total_gt] matrix prices every query against every image's boxes and then throws all but one block per
+        image away, ops.py:104-116).  Element-wise the same arithmetic, so the kept entries are bit-identical."""
+        grp = _Groups.get(gt_groups, pred_scores.shape[2], pred_scores.device)
+        gtb = gt_bboxes[grp.pad_index].unsqueeze(1)                                    # [bs, 1, max_gt, 4]
+        cls = gt_cls[grp.pad_index]                                                    # [bs, max_gt]
+        p = pred_scores.detach()
+        p = F.sigmoid(p) if self.use_fl else F.softmax(p, dim=-1)
+        n_l, bs, nq = p.shape[:3]
+        p = torch.gather(p, 3, cls.view(1, bs, 1, -1).expand(n_l, bs, nq, -1))
+        box = pred_bboxes.detach()
+        if self.use_fl:
+            neg_cost_class = (1 - self.alpha) * (p ** self.gamma) * (-(1 - p + 1e-8).log())
+            pos_cost_class = self.alpha * ((1 - p) ** self.gamma) * (-(p + 1e-8).log())
+            cost_class = pos_cost_class - neg_cost_class
+        else:
+            cost_class = -p
+        cost_bbox = (box.unsqueeze(-2) - gtb).abs().sum(-1)
+        cost_giou = 1.0 - bbox_iou(box.unsqueeze(-2), gtb, xywh=True, RIOU=True).squeeze(-1)
+        C = self.cost_gain['class'] * cost_class + self.cost_gain['bbox'] * cost_bbox + self.cost_gain['giou'] * cost_giou
+        return torch.where(torch.isfinite(C), C, torch.zeros((), dtype=C.dtype, device=C.device))
+
     def match_layers(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, gt_groups):
         """pred_* [n_layers, bs, nq, .] -> (image idx [P], query idx [n_layers, P], gt idx [n_layers, P])."""
-        C = self.cost_matrix(pred_bboxes.float(), pred_scores.float(), gt_bboxes.float(), gt_cls)
-        return linear_sum_assignment(C, gt_groups)
+        if sum(gt_groups) == 0:
+            z = torch.zeros(0, dtype=torch.long, device=pred_bboxes.device)
+            e = torch.zeros(pred_bboxes.shape[0], 0, dtype=torch.long, device=pred_bboxes.device)
+            return z, e, e.clone()
+        C = self.cost_matrix_per_image(pred_bboxes.float(), pred_scores.float(), gt_bboxes.float(), gt_cls, gt_groups)
+        return linear_sum_assignment(C, gt_groups, padded=True)
 
     def forward(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, gt_groups, masks=None, gt_mask=None):
         bs, nq, nc = pred_scores.shape
@@ -255,40 +290,93 @@ class DETRLoss(nn.Module):
         return loss
 
     def _get_loss_aux(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, gt_groups, match_indices=None, postfix='',
-                      masks=None, gt_mask=None, layer_matches=None):
+                      masks=None, gt_mask=None):
         loss = torch.zeros(3, device=pred_bboxes.device)
         if match_indices is None and self.use_uni_match:
             match_indices = self.matcher(pred_bboxes[self.uni_match_ind], pred_scores[self.uni_match_ind], gt_bboxes,
                                          gt_cls, gt_groups)
         for i, aux_bboxes in enumerate(pred_bboxes):
             aux_scores = None if pred_scores is None else pred_scores[i]
-            mi = match_indices if (match_indices is not None or layer_matches is None) else layer_matches[i]
-            loss_ = self._get_loss(aux_bboxes, aux_scores, gt_bboxes, gt_cls, gt_groups, postfix=postfix, match_indices=mi)
+            loss_ = self._get_loss(aux_bboxes, aux_scores, gt_bboxes, gt_cls, gt_groups, postfix=postfix,
+                                   match_indices=match_indices)
             if aux_scores is not None:
                 loss[0] = loss[0] + loss_[f'loss_class{postfix}']
             loss[1] = loss[1] + loss_[f'loss_bbox{postfix}']
             loss[2] = loss[2] + loss_[f'loss_giou{postfix}']
         return {f'loss_class_aux{postfix}': loss[0], f'loss_bbox_aux{postfix}': loss[1], f'loss_giou_aux{postfix}': loss[2]}
 
+    def _get_loss_layers(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, img, q, g, postfix=''):
+        """All layers at once (the reference loops, loss.py:232-243; same arithmetic per layer, one set of kernels):
+        pred_* [n_l, bs, nq, .], img [P], q / g [n_l, P] (or [P] for the fixed denoising matches).  Returns the loss dict
+        of loss.py:328-373: last layer + the sum over the auxiliary layers."""
+        n_l, bs, nq = pred_bboxes.shape[:3]
+        P = img.numel()
+        if q.dim() == 1:
+            q, g = q.expand(n_l, P), g.expand(n_l, P)
+        lay = torch.arange(n_l, device=img.device).unsqueeze(1).expand(n_l, P)
+        idx = (lay, img.expand(n_l, P), q)
+        pb, gb = pred_bboxes[idx], gt_bboxes[g]                                        # [n_l, P, 4]
+        bbox = self.loss_gain['bbox'] * (pb - gb).abs().sum((1, 2)) / P
+        giou = self.loss_gain['giou'] * ((1.0 - bbox_iou(pb, gb, xywh=True, RIOU=True)).sum((1, 2)) / P)
+        out = {}
+        if pred_scores is not None:
+            targets = torch.full((n_l, bs, nq), self.nc, device=pred_scores.device, dtype=gt_cls.dtype)
+            targets[idx] = gt_cls[g]
+            gt_scores = torch.zeros((n_l, bs, nq), device=pred_scores.device)
+            gt_scores[idx] = bbox_iou(pb.detach(), gb, xywh=True).squeeze(-1)
+            one_hot = torch.zeros((n_l, bs, nq, self.nc + 1), dtype=torch.int64, device=targets.device)
+            one_hot.scatter_(3, targets.unsqueeze(-1), 1)
+            one_hot = one_hot[..., :-1]
+            gt_s = gt_scores.unsqueeze(-1) * one_hot
+            if self.fl:
+                if self.vfl:
+                    weight = 0.75 * pred_scores.sigmoid().pow(2.0) * (1 - one_hot) + gt_s * one_hot
+                    with torch.autocast("cuda", enabled=False):
+                        cls = (F.binary_cross_entropy_with_logits(pred_scores.float(), gt_s.float(), reduction='none')
+                               * weight).mean(2).sum((1, 2))
+                else:
+                    label = one_hot.float()
+                    l = F.binary_cross_entropy_with_logits(pred_scores, label, reduction='none')
+                    pr = pred_scores.sigmoid()
+                    p_t = label * pr + (1 - label) * (1 - pr)
+                    cls = (l * (1.0 - p_t) ** 1.5 * (label * 0.25 + (1 - label) * 0.75)).mean(2).sum((1, 2))
+                cls = cls / (max(P, 1) / nq)
+            else:
+                cls = nn.BCEWithLogitsLoss(reduction='none')(pred_scores, gt_s).mean(2).sum((1, 2))
+            cls = cls * self.loss_gain['class']
+            out[f'loss_class{postfix}'] = cls[-1]
+        out[f'loss_bbox{postfix}'] = bbox[-1]
+        out[f'loss_giou{postfix}'] = giou[-1]
+        if self.aux_loss:
+            zero = torch.zeros((), device=pred_bboxes.device)
+            out[f'loss_class_aux{postfix}'] = cls[:-1].sum() if pred_scores is not None else zero
+            out[f'loss_bbox_aux{postfix}'] = bbox[:-1].sum()
+            out[f'loss_giou_aux{postfix}'] = giou[:-1].sum()
+        return out
+
     def forward(self, pred_bboxes, pred_scores, batch, postfix='', **kwargs):
         """pred_bboxes [l, b, query, 4], pred_scores [l, b, query, nc] (or None); batch: cls / bboxes / gt_groups."""
         self.device = pred_bboxes.device
         match_indices = kwargs.get('match_indices', None)
         gt_cls, gt_bboxes, gt_groups = batch['cls'], batch['bboxes'], batch['gt_groups']
-        layer_matches = None
-        if (match_indices is None and pred_scores is not None and not self.use_uni_match and sum(gt_groups) > 0
-                and pred_bboxes.is_cuda):
+        batched = pred_bboxes.is_cuda and not self.use_uni_match and sum(gt_groups) > 0
+        if batched and isinstance(match_indices, tuple) and match_indices[0].numel() > 0:
+            # fixed matches (denoising queries): the same pairs for every layer
+            pb = pred_bboxes if self.aux_loss else pred_bboxes[-1:]
+            ps = pred_scores if (self.aux_loss or pred_scores is None) else pred_scores[-1:]
+            return self._get_loss_layers(pb, ps, gt_bboxes, gt_cls, *match_indices, postfix=postfix)
+        if batched and match_indices is None and pred_scores is not None:
             # every layer's assignment in ONE launch (the reference matches layer by layer, loss.py:293-300, 232-243)
             n_l = pred_bboxes.shape[0] if self.aux_loss else 1
             img, q, g = self.matcher.match_layers(pred_bboxes[-n_l:], pred_scores[-n_l:], gt_bboxes, gt_cls, gt_groups)
-            layer_matches = [(img, q[i], g[i]) for i in range(n_l)]
-        last = layer_matches[-1] if layer_matches is not None else match_indices
+            if img.numel() > 0:
+                return self._get_loss_layers(pred_bboxes[-n_l:], pred_scores[-n_l:], gt_bboxes, gt_cls, img, q, g,
+                                             postfix=postfix)
         total_loss = self._get_loss(pred_bboxes[-1], None if pred_scores is None else pred_scores[-1], gt_bboxes, gt_cls,
-                                    gt_groups, postfix=postfix, match_indices=last)
+                                    gt_groups, postfix=postfix, match_indices=match_indices)
         if self.aux_loss:
             total_loss.update(self._get_loss_aux(pred_bboxes[:-1], None if pred_scores is None else pred_scores[:-1],
-                                                 gt_bboxes, gt_cls, gt_groups, match_indices, postfix,
-                                                 layer_matches=None if layer_matches is None else layer_matches[:-1]))
+                                                 gt_bboxes, gt_cls, gt_groups, match_indices, postfix))
         return total_loss
 
 
