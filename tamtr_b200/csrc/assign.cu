@@ -92,14 +92,23 @@ lsap_kernel(const float *__restrict__ C, const int *__restrict__ gt_start, const
                 const AsgKey k{s, row4col[j] < 0 ? it : -1, it};
                 if (asg_better(k, best)) best = k;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                AsgKey other;
-                other.val = __shfl_xor_sync(0xffffffffu, best.val, o);
-                other.free_pos = __shfl_xor_sync(0xffffffffu, best.free_pos, o);
-                other.pos = __shfl_xor_sync(0xffffffffu, best.pos, o);
-                if (asg_better(other, best)) best = other;
+            // warp arg-min with SciPy's tie order, as integer reductions (redux.sync): the fp64 value through its
+            // order-preserving 64-bit image (high word, then low word among the lanes that tie on the high word), then
+            // among the lanes at the minimum the largest unassigned position, else the smallest position
+            unsigned long long ord = ~0ull;
+            if (best.pos >= 0) {
+                const long long bits = __double_as_longlong(best.val + 0.0);          // (-0.0 -> +0.0)
+                ord = bits < 0 ? ~(unsigned long long)bits : (unsigned long long)bits ^ 0x8000000000000000ull;
             }
+            const unsigned hi = (unsigned)(ord >> 32), lo = (unsigned)ord;
+            const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+            const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+            const bool at_min = best.pos >= 0 && hi == mhi && lo == mlo;
+            const int mfree = __reduce_max_sync(0xffffffffu, at_min ? best.free_pos : -1);
+            const int mpos = mfree >= 0 ? mfree : __reduce_min_sync(0xffffffffu, at_min ? best.pos : 0x7fffffff);
+            const unsigned long long mord = ((unsigned long long)mhi << 32) | mlo;
+            best.pos = mord == ~0ull ? -1 : mpos;
+            best.val = __longlong_as_double((long long)((mord >> 63) ? mord ^ 0x8000000000000000ull : ~mord));
             min_val = best.val;
             if (best.pos < 0 || min_val == CUDART_INF) { sink = -2; break; }    // infeasible (cannot happen: costs are finite)
             const int j = remaining[best.pos];
