@@ -346,3 +346,26 @@ def test_modules_survive_deepcopy_pickle_and_half(cuda_lib):
     assert rel_l2(b, a) < 5e-3          # weights went through fp16
     h = m2(query.cuda().half(), ref.cuda().half(), value.cuda().half(), [[8, 8], [4, 4], [2, 2]])
     assert h.dtype == torch.float16 and rel_l2(h, a) < 2e-2
+
+
+def test_meh_head_inference_1280(cuda_lib):
+    """BASELINE.json config 5: high-resolution inference, 1280x1280 -> pyramid 320^2/160^2/80^2 (134 400 tokens),
+    900 queries, one image per GPU.  The product head on the GPU against the oracle restatement of the reference's op
+    sequence on the host CPU (fp32); rows are aligned through the predicted boxes (top-k may swap near-tied tokens)."""
+    from tamtr_b200.head import ManbaWorldDecoder
+    nq = 900
+    m = ManbaWorldDecoder(10, [128, 256, 512], 512, nq, 4, 8, 3)
+    sd = filled_state_dict(m, 81)
+    m.cuda().eval()
+    xs = [seeding.seeded_smooth_map(82, f"x{i}", (1, ch, s, s)) for i, (ch, s) in enumerate(zip((128, 256, 512), (320, 160, 80)))]
+    text = torch.nn.functional.normalize(seeding.seeded_tensor(83, "text", (1, 10, 512)), dim=-1)
+    with torch.no_grad():
+        y, (db, ds, eb, es, _) = m([x.cuda() for x in xs], text.cuda())
+        rb, rs, reb, res = head_ref.head({k: v.cpu() for k, v in sd.items()}, "", xs, nq, 3, 8, training=False, text=text)
+    assert y.shape == (1, nq, 14) and db.shape[2] == nq
+    y_ref = torch.cat([rb[-1], rs[-1].sigmoid()], -1)
+    dist, idx = torch.cdist(y[..., :4].double().cpu(), y_ref[..., :4].double()).min(-1)
+    ok = dist < 1e-3
+    assert ok.float().mean() > 0.97, ok.float().mean()
+    sel = ok.unsqueeze(-1)
+    assert rel_l2(y.cpu() * sel, gather_rows(y_ref, idx) * sel) < 2e-2

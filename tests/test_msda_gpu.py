@@ -238,3 +238,24 @@ def test_strided_value_views_and_arena(cuda_lib):
         assert rel_l2(wc.grad, gall.reshape(-1, n * d).t() @ fc.detach().float().cpu().reshape(-1, 64)) < tol
         assert rel_l2(fc.grad, gall @ wc.detach().float().cpu()) < tol
         assert arena.buf is None            # consumed by the projection node
+
+
+def test_config5_inference_size(cuda_lib):
+    """BASELINE.json config 5 (1280x1280, S-yaml pyramid 320^2/160^2/80^2 = 134 400 tokens, 900 queries, d = 512):
+    the sampler forward at the largest single-image size against the C oracle, fp32 and bf16, plus the
+    size-independent properties (linearity, zero attention)."""
+    shapes = msda.level_shapes(320)
+    B, Lq, H, Dh = 2, 900, 8, 64
+    value, loc, attn, _ = msda.make_inputs(55, B, Lq, H, Dh, shapes, oob_frac=0.1)
+    assert value.shape[1] == 134400
+    v32, l, a = value.cuda(), loc.cuda(), attn.cuda()
+    out32 = cuda_lib.ms_deform_attn(v32, shapes, l, a)
+    ref = msda.forward_c(value[1:2], shapes, loc[1:2], attn[1:2])
+    assert rel_l2(out32[1:2], ref) < FP32_TOL
+    out16 = cuda_lib.ms_deform_attn(v32.bfloat16(), shapes, l, a)
+    ref16 = msda.forward_c(value[1:2].bfloat16().float(), shapes, loc[1:2], attn[1:2])
+    assert out16.dtype == torch.bfloat16 and rel_l2(out16[1:2], ref16) < BF16_TOL
+    v2 = torch.randn_like(v32)
+    o2 = cuda_lib.ms_deform_attn(v2, shapes, l, a)
+    assert rel_l2(cuda_lib.ms_deform_attn(v32 - 0.5 * v2, shapes, l, a), out32 - 0.5 * o2) < 1e-5
+    assert torch.count_nonzero(cuda_lib.ms_deform_attn(v32, shapes, l, torch.zeros_like(a))) == 0
