@@ -1,0 +1,214 @@
+"""VSSBlock / SS2D of TAM-TR's MEH head (ultralytics/nn/modules/head.py:1092-1098: one VSSBlock(hidden_dim=ch_l,
+drop_path=0.1) per pyramid level, applied channel-last in front of input_proj, head.py:1134) with the selective scan on
+the sm_100a kernels of csrc/sscan.cu.
+
+Mirrors (same class names, constructor arguments of the configuration TAM-TR builds, state_dict keys):
+  VSSBlock      nn/extra_modules/VManba/vmamba.py:1169-1257   (forward_type "v2", mlp_ratio 4, GELU, post_norm False)
+  SS2D          vmamba.py:330-470 (__initv2__), :898-1038 (forward_corev2 / forwardv2)
+  Mlp           vmamba.py:107-125
+  CrossScan / CrossMerge  csms6s.py:4-47,  SelectiveScanCore  csms6s.py:252-270
+The reference calls the un-vendored extension `selective_scan_cuda_core` for the scan; `selective_scan` below has that
+call's argument meaning (u, delta, A, B, C, D, delta_bias, delta_softplus) and raises for CPU tensors like every other
+op of this package.  Everything around the scan is library code (GEMMs, depth-wise conv, LayerNorm), as in the
+reference.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+__all__ = ("VSSBlock", "SS2D", "Mlp", "DropPath", "selective_scan", "cross_scan", "cross_merge")
+
+
+class _SelectiveScanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D, delta_bias):
+        u, delta, A, B, C = (t.contiguous().float() for t in (u, delta, A, B, C))
+        D = None if D is None else D.contiguous().float()
+        delta_bias = None if delta_bias is None else delta_bias.contiguous().float()
+        Bn, KD, L = u.shape
+        K, N = B.shape[1], A.shape[1]
+        need = any(ctx.needs_input_grad)
+        y = torch.empty_like(u)
+        lib = _lib.lib()
+        ckpt = torch.empty(Bn, KD, lib.tamtr_selective_scan_segments(L), N, dtype=torch.float32, device=u.device) \
+            if need else None
+        with torch.cuda.device(u.device):
+            rc = lib.tamtr_selective_scan_forward(
+                u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr(),
+                None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(), y.data_ptr(),
+                None if ckpt is None else ckpt.data_ptr(), Bn, KD, KD // K, N, L, _lib.stream_ptr(u.device))
+        _lib.check(rc, "selective_scan_forward")
+        if need:
+            ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, ckpt)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        u, delta, A, B, C, D, delta_bias, ckpt = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        Bn, KD, L = u.shape
+        K, N = B.shape[1], A.shape[1]
+        g_u, g_dt = torch.empty_like(u), torch.empty_like(delta)
+        g_A, g_B, g_C = torch.empty_like(A), torch.empty_like(B), torch.empty_like(C)     # zeroed by the call
+        g_D = None if D is None else torch.empty_like(D)
+        g_bias = None if delta_bias is None else torch.empty_like(delta_bias)
+        with torch.cuda.device(u.device):
+            rc = _lib.lib().tamtr_selective_scan_backward(
+                u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr(),
+                None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(), dy.data_ptr(),
+                ckpt.data_ptr(), g_u.data_ptr(), g_dt.data_ptr(), g_A.data_ptr(), g_B.data_ptr(), g_C.data_ptr(),
+                None if g_D is None else g_D.data_ptr(), None if g_bias is None else g_bias.data_ptr(), Bn, KD, KD // K, N,
+                L, _lib.stream_ptr(u.device))
+        _lib.check(rc, "selective_scan_backward")
+        return g_u, g_dt, g_A, g_B, g_C, g_D, g_bias
+
+
+def selective_scan(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=True):
+    """u, delta [b, K*D, L]; A [K*D, 16]; B, C [b, K, 16, L]; D, delta_bias [K*D] -> y [b, K*D, L] fp32
+    (csms6s.py:252-270 / vmamba.py:962-990)."""
+    _lib.require_cuda(u, delta, A, B, C, D, delta_bias)
+    if not delta_softplus:
+        raise RuntimeError("tamtr_b200: selective_scan without softplus is not on TAM-TR's path (vmamba.py:907)")
+    return _SelectiveScanFn.apply(u, delta, A, B, C, D, delta_bias)
+
+
+def cross_scan(x):
+    """[b, d, h, w] -> [b, 4, d, h*w]: row-major, column-major and both reversed (csms6s.py:6-13)."""
+    a = x.flatten(2)
+    c = x.transpose(2, 3).flatten(2)
+    return torch.stack([a, c, a.flip(-1), c.flip(-1)], 1)
+
+
+def cross_merge(ys, h, w):
+    """[b, 4, d, h*w] -> [b, d, h*w] (csms6s.py:27-34)."""
+    b, _, d, l = ys.shape
+    s = ys[:, 0:2] + ys[:, 2:4].flip(-1)
+    return s[:, 0] + s[:, 1].reshape(b, d, w, h).transpose(2, 3).reshape(b, d, l)
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample (timm.layers.DropPath, used at vmamba.py:1232)."""
+
+    def __init__(self, drop_prob=0.0, scale_by_keep=True):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.scale_by_keep = scale_by_keep
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+        if keep > 0.0 and self.scale_by_keep:
+            mask.div_(keep)
+        return x * mask
+
+
+class Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features or in_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+
+
+class SS2D(nn.Module):
+    """2-D selective scan block, forward_type "v2" (vmamba.py:330-470, 898-1038): channel-last in and out."""
+
+    def __init__(self, d_model=96, d_state=16, ssm_ratio=2.0, dt_rank="auto", act_layer=nn.SiLU, d_conv=3, conv_bias=True,
+                 dropout=0.0, bias=False, dt_min=0.001, dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4,
+                 initialize="v0", forward_type="v2", channel_first=False):
+        super().__init__()
+        if forward_type != "v2" or channel_first or initialize != "v0" or d_conv != 3:
+            raise NotImplementedError("tamtr_b200: only the SS2D configuration TAM-TR builds (vmamba.py:1205-1226)")
+        d_inner = int(ssm_ratio * d_model)
+        dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        k_group = 4
+        self.d_conv, self.channel_first = d_conv, channel_first
+        self.in_proj = nn.Linear(d_model, d_inner * 2, bias=bias)
+        self.act = act_layer()
+        self.conv2d = nn.Conv2d(d_inner, d_inner, d_conv, padding=(d_conv - 1) // 2, groups=d_inner, bias=conv_bias)
+        self.x_proj_weight = nn.Parameter(torch.stack(
+            [nn.Linear(d_inner, dt_rank + d_state * 2, bias=False).weight for _ in range(k_group)], 0).detach())
+        self.out_norm = nn.LayerNorm(d_inner)
+        self.out_proj = nn.Linear(d_inner, d_model, bias=bias)
+        self.dropout = nn.Dropout(dropout) if dropout > 0.0 else nn.Identity()
+        # dt projections, A, D (vmamba.py:152-205)
+        std = dt_rank ** -0.5 * dt_scale
+        w, bs = [], []
+        for _ in range(k_group):
+            lin = nn.Linear(dt_rank, d_inner, bias=True)
+            if dt_init == "constant":
+                nn.init.constant_(lin.weight, std)
+            else:
+                nn.init.uniform_(lin.weight, -std, std)
+            dt = torch.exp(torch.rand(d_inner) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min)).clamp(min=dt_init_floor)
+            w.append(lin.weight.detach())
+            bs.append(dt + torch.log(-torch.expm1(-dt)))
+        self.dt_projs_weight = nn.Parameter(torch.stack(w, 0))                 # (K, inner, rank)
+        self.dt_projs_bias = nn.Parameter(torch.stack(bs, 0))                  # (K, inner)
+        A = torch.arange(1, d_state + 1, dtype=torch.float32).repeat(k_group * d_inner, 1)
+        self.A_logs = nn.Parameter(torch.log(A))                               # (K * inner, N)
+        self.Ds = nn.Parameter(torch.ones(k_group * d_inner))
+        self.A_logs._no_weight_decay = True
+        self.Ds._no_weight_decay = True
+
+    def forward_core(self, x):
+        """[b, d, h, w] -> [b, h, w, d] (vmamba.py:937-1017 with force_fp32, SelectiveScanCore)."""
+        b, d, h, w = x.shape
+        k, r = self.dt_projs_weight.shape[0], self.dt_projs_weight.shape[2]
+        n = self.A_logs.shape[1]
+        l = h * w
+        xs = cross_scan(x)
+        x_dbl = torch.einsum("b k d l, k c d -> b k c l", xs, self.x_proj_weight)
+        dts, Bs, Cs = torch.split(x_dbl, [r, n, n], dim=2)
+        dts = torch.einsum("b k r l, k d r -> b k d l", dts, self.dt_projs_weight)
+        ys = selective_scan(xs.reshape(b, -1, l).float(), dts.contiguous().view(b, -1, l).float(),
+                            -torch.exp(self.A_logs.float()), Bs.contiguous().float(), Cs.contiguous().float(),
+                            self.Ds.float(), self.dt_projs_bias.view(-1).float(), True)
+        y = cross_merge(ys.view(b, k, -1, l), h, w)
+        y = self.out_norm(y.transpose(1, 2).contiguous()).view(b, h, w, -1)
+        return y.to(x.dtype)
+
+    def forward(self, x):
+        x = self.in_proj(x)
+        x, z = x.chunk(2, dim=-1)
+        z = self.act(z.clone())
+        x = self.act(self.conv2d(x.permute(0, 3, 1, 2).contiguous()))
+        y = self.forward_core(x) * z
+        return self.dropout(self.out_proj(y))
+
+
+class VSSBlock(nn.Module):
+    """x + drop_path(SS2D(norm(x))), then x + drop_path(Mlp(norm2(x))) on channel-last maps (vmamba.py:1236-1250)."""
+
+    def __init__(self, hidden_dim=0, drop_path=0.0, norm_layer=nn.LayerNorm, channel_first=False, ssm_d_state=16,
+                 ssm_ratio=2.0, ssm_dt_rank="auto", ssm_act_layer=nn.SiLU, ssm_conv=3, ssm_conv_bias=True, ssm_drop_rate=0.0,
+                 ssm_init="v0", forward_type="v2", mlp_ratio=4.0, mlp_act_layer=nn.GELU, mlp_drop_rate=0.0, gmlp=False,
+                 use_checkpoint=False, post_norm=False, **kwargs):
+        super().__init__()
+        if channel_first or gmlp or post_norm or use_checkpoint or ssm_ratio <= 0 or mlp_ratio <= 0:
+            raise NotImplementedError("tamtr_b200: only the VSSBlock configuration TAM-TR builds (head.py:1095-1098)")
+        self.ssm_branch, self.mlp_branch = True, True
+        self.use_checkpoint, self.post_norm = use_checkpoint, post_norm
+        self.norm = norm_layer(hidden_dim)
+        self.op = SS2D(d_model=hidden_dim, d_state=ssm_d_state, ssm_ratio=ssm_ratio, dt_rank=ssm_dt_rank,
+                       act_layer=ssm_act_layer, d_conv=ssm_conv, conv_bias=ssm_conv_bias, dropout=ssm_drop_rate,
+                       initialize=ssm_init, forward_type=forward_type, channel_first=channel_first)
+        self.drop_path = DropPath(drop_path)
+        self.norm2 = norm_layer(hidden_dim)
+        self.mlp = Mlp(in_features=hidden_dim, hidden_features=int(hidden_dim * mlp_ratio), act_layer=mlp_act_layer,
+                       drop=mlp_drop_rate)
+
+    def forward(self, input):
+        x = input + self.drop_path(self.op(self.norm(input)))
+        return x + self.drop_path(self.mlp(self.norm2(x)))

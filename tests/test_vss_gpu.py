@@ -1,0 +1,71 @@
+"""GPU: the selective-scan kernels (csrc/sscan.cu) against the oracle restatement of the published recurrence
+(oracle/vss_ref.selective_scan + autograd), and the product VSSBlock against the UNMODIFIED reference VSSBlock
+(tests/golden/vss.pt).  Tolerances: fp32 <= 1e-4 relative on outputs (north_star); the gradients that are sums over
+thousands of positions / channels (dA, dB, dC, d bias) <= 1e-3."""
+import pytest
+import torch
+
+from helpers import load_golden, rel_l2
+from oracle import seeding, vss_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _scan_inputs(seed, b, k, d, l, big_dt=False):
+    n = 16
+    u = seeding.seeded_tensor(seed, "u", (b, k * d, l))
+    delta = seeding.seeded_tensor(seed, "dt", (b, k * d, l)) * (8.0 if big_dt else 1.0) - (0.0 if big_dt else 2.0)
+    A = -(0.5 + 15.5 * seeding.seeded_uniform(seed, "A", (k * d, n)))
+    B = seeding.seeded_tensor(seed, "B", (b, k, n, l))
+    C = seeding.seeded_tensor(seed, "C", (b, k, n, l))
+    D = 1.0 + 0.2 * seeding.seeded_tensor(seed, "D", (k * d,))
+    bias = seeding.seeded_tensor(seed, "bias", (k * d,)) - 3.0
+    return [u, delta, A, B, C, D, bias]
+
+
+@pytest.mark.parametrize("b,k,d,l,big", [(2, 4, 128, 70, False), (1, 2, 256, 257, False), (1, 4, 128, 64, True),
+                                         (3, 1, 128, 1, False), (1, 4, 128, 33, False)])
+def test_selective_scan_matches_oracle(cuda_lib, b, k, d, l, big):
+    from tamtr_b200.vss import selective_scan
+    ins = _scan_inputs(l, b, k, d, l, big)
+    ref_in = [t.clone().requires_grad_() for t in ins]
+    y_ref = vss_ref.selective_scan(*ref_in, True)
+    probe = seeding.seeded_tensor(l, "p", y_ref.shape)
+    (y_ref * probe).sum().backward()
+    cu = [t.cuda().requires_grad_() for t in ins]
+    y = selective_scan(*cu, True)
+    (y * probe.cuda()).sum().backward()
+    assert rel_l2(y, y_ref) < 1e-4, rel_l2(y, y_ref)
+    names = ["u", "delta", "A", "B", "C", "D", "bias"]
+    for name, a, r in zip(names, cu, ref_in):
+        tol = 1e-4 if name in ("u", "delta") else 1e-3
+        assert rel_l2(a.grad, r.grad) < tol, (name, rel_l2(a.grad, r.grad))
+    with torch.no_grad():                                            # inference: no checkpoints, same values
+        assert torch.equal(selective_scan(*[t.detach() for t in cu], True), y.detach())
+
+
+@pytest.mark.parametrize("name", ["c128_12x16", "c256_9x9", "c512_8x10"])
+def test_vss_block_matches_reference(cuda_lib, name):
+    from tamtr_b200.vss import VSSBlock
+    gold = load_golden("vss")["cases"][name]
+    c, b, h, w = gold["shape"]
+    blk = VSSBlock(hidden_dim=c, drop_path=0.0)
+    assert {k: tuple(v.shape) for k, v in blk.state_dict().items()} == gold["manifest"]
+    vss_ref.seed_block(blk, gold["param_seed"])
+    blk.cuda()
+    x = seeding.seeded_tensor(600 + c, "x", (b, h, w, c)).cuda().requires_grad_()
+    probe = seeding.seeded_tensor(600 + c, "probe", (b, h, w, c)).cuda()
+    y = blk(x)
+    (y * probe).sum().backward()
+    assert rel_l2(y, gold["y"]) < 1e-4 and rel_l2(x.grad, gold["grad_x"]) < 1e-4
+    for k, p in blk.named_parameters():
+        n = gold["grad_param_norms"][k]
+        assert abs(p.grad.double().norm().item() - n) < 1e-3 * max(n, 1e-6), k
+    assert rel_l2(blk.op.A_logs.grad, gold["grad_A_logs"]) < 1e-3
+    assert rel_l2(blk.op.x_proj_weight.grad, gold["grad_x_proj"]) < 1e-3
+    assert rel_l2(blk.op.dt_projs_bias.grad, gold["grad_dt_bias"]) < 1e-3
+    blk.train()
+    blk.drop_path.drop_prob = 0.1                                    # head.py:1097: stochastic depth in training
+    torch.manual_seed(0)
+    out = blk(x.detach())
+    assert out.shape == x.shape and torch.isfinite(out).all()
