@@ -246,8 +246,9 @@ LOSS_NAMES = {"detection": "RTDETRDetectionLoss(use_vfl) on encoder proposals + 
               "surrogate": "mean-square / mean-sigmoid scalar over all outputs"}
 
 
-def config_dict(loss_kind="surrogate"):
-    return {"loss": LOSS_NAMES[loss_kind], "workload": "TAM-TR MEH head (ManbaWorldDecoder nc=10 ch=[128,256,512] hd=512 nq=100 ndl=3, VSS=identity) "
+def config_dict(loss_kind="surrogate", vss=False):
+    return {"loss": LOSS_NAMES[loss_kind], "vss_blocks": "selective-scan kernels" if vss else "identity",
+            "workload": "TAM-TR MEH head (ManbaWorldDecoder nc=10 ch=[128,256,512] hd=512 nq=100 ndl=3) "
                         "+ text-guided cls branch, train fwd+bwd, CDN 20..100 gt/img, pyramid 160^2/80^2/40^2 @640^2",
             "batch_per_gpu": BATCH_PER_GPU, "text_tokens": NC, "text_dim": 512,
             "l2": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no explicit flush"}
@@ -268,6 +269,11 @@ def main():
                          "the reference arm).  With the default, the detection-loss step is also timed and reported as "
                          "`with_detection_loss`.")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--vss", action="store_true",
+                    help="run the head's three VSSBlocks for real (selective-scan kernels) instead of identities.  Off by "
+                         "default: the reference cannot run them without its un-vendored CUDA extension, so the reference "
+                         "arm and the head-level parity fixtures are identity-VSS; with the default the VSS-on step is "
+                         "also timed once and reported as `with_vss`.")
     ap.add_argument("--launch-list", action="store_true",
                     help="eager steps only (no e2e / instrumented pass / CPU baseline): the command to run under "
                          "`ncu --metrics gpu__time_duration.sum` for profiles/launches_*.csv")
@@ -295,7 +301,7 @@ def main():
 
     B = BATCH_PER_GPU
     torch.manual_seed(1234)                                # same initial weights on every rank (DDP broadcast equivalent)
-    model = ManbaWorldDecoder(NC, list(CH), HD, NQ, NDP, NH, NDL).to(dev).train()
+    model = ManbaWorldDecoder(NC, list(CH), HD, NQ, NDP, NH, NDL, vss=args.vss).to(dev).train()
     # two synthetic batches per rank in pinned host memory (bf16 activations, as a bf16 neck would hand them over)
     host = []
     for j in range(2):
@@ -418,7 +424,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": ws, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": dict(config_dict(args.loss), queries=Lq, cuda_graph=step.graph is not None,
+                "config": dict(config_dict(args.loss, args.vss), queries=Lq, cuda_graph=step.graph is not None,
                                parallelism=f"dp{ws}" if ws > 1 else "single"),
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -445,6 +451,31 @@ def main():
                 del step2
             except Exception as e:
                 line["with_detection_loss"] = {"error": str(e)[:200]}
+        if ws == 1 and not args.vss:
+            try:        # the same step with the three VSSBlocks running (head.py:1092-1098,1134)
+                torch.manual_seed(1234)
+                model_v = ManbaWorldDecoder(NC, list(CH), HD, NQ, NDP, NH, NDL, vss=True).to(dev).train()
+                for blk in model_v.VSSBlocks:
+                    blk.drop_path.drop_prob = 0.0            # stochastic depth draws random numbers: not graph-replayable
+                step3 = dp.HeadTrainStep(model_v, surrogate_loss_fn, (host[0][0], host[0][1], plan),
+                                         autocast=torch.bfloat16, use_graph=not args.no_graph, warmup=1)
+                nv = max(2, args.steps // 4)
+                step3.run()
+                torch.cuda.synchronize(dev)
+                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                v0.record()
+                for _ in range(nv):
+                    step3.run()
+                v1.record()
+                torch.cuda.synchronize(dev)
+                vsec = v0.elapsed_time(v1) / 1e3
+                line["with_vss"] = {"value": B * nv / vsec, "unit": "images/s", "ms_per_step": vsec / nv * 1e3, "steps": nv,
+                                    "note": "VSSBlocks on the selective-scan kernels (fp32 scan as vmamba.py:985 forces), "
+                                            "drop_path 0; parity for the scan is pinned to the published recurrence only"}
+                del step3, model_v
+                torch.cuda.empty_cache()
+            except Exception as e:
+                line["with_vss"] = {"error": str(e)[:200]}
         if ws == 1:
             try:
                 line["roofline_tensor"] = gate_conv_roofline(dev)

@@ -265,7 +265,7 @@ int tamtr_linear_sum_assignment(const float *C, const int *gt_start_dev, const i
  * its call signature and the published recurrence (Gu & Dao, "Mamba", 2023):
  *   delta = softplus(dt + bias) (identity above 20); h_t = exp(delta_t*A)*h_{t-1} + delta_t*B_t*u_t; y_t = <C_t,h_t> + D*u_t
  * u, dt, y, dy, g_u, g_dt: f32 [Bn, KD, L]; A, g_A: f32 [KD, N]; Bm, Cm, g_B, g_C: f32 [Bn, KD/Dg, N, L];
- * D, bias, g_D, g_bias: f32 [KD] (D / bias may be NULL).  N = 16, Dg (channels per scan direction) % 128 == 0.
+ * D, bias, g_D, g_bias: f32 [KD] (D / bias may be NULL).  N = 16, Dg (channels per scan direction) % 32 == 0.
  * ckpt: f32 [Bn, KD, tamtr_selective_scan_segments(L), N], written by the forward (may be NULL at inference), read by the
  * backward.  g_A, g_B, g_C, g_D, g_bias are zeroed by the call and accumulated (fp32 reductions over batch / channels). */
 int tamtr_selective_scan_segments(int L);

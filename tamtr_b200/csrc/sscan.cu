@@ -8,117 +8,143 @@
 // Shapes as the reference passes them (vmamba.py:977-990): u, dt, y [b, K*D, L]; A [K*D, N]; B, C [b, K, N, L];
 // D, bias [K*D]; fp32 throughout (vmamba.py:985-986 forces fp32 into the scan).  N = 16 states.
 //
-// Mapping: thread = one channel with its 16 states in registers, CTA = 128 consecutive channels of one (image, scan
-// direction), walking the L positions in tiles of 32.  Tiles of u / dt / dy are staged through shared memory with
-// coalesced row reads (L is the contiguous dimension) and read back conflict-free (pitch 33); the B / C rows of the
-// group are staged once per tile and read as broadcasts.  The bound is the SFU: 16 exp per position and channel.
-// The forward also writes the state every 64 positions; the backward walks the segments in reverse, recomputes the
-// states of a segment from its checkpoint (sub-checkpoints every 4 positions in shared memory, the 4 positions
-// in registers) and accumulates dB / dC across the CTA's channels with a 32-value warp transpose-reduction.
+// Mapping: 4 lanes per channel, each with 4 of the 16 states in registers; CTA = 32 consecutive channels of one (image,
+// scan direction) = 128 threads, walking the L positions in tiles of 32.  (A first version with one thread per channel
+// and 16 states each left one warp per scheduler at the head's largest level -- 128 CTAs -- and ran at 7 % of the SFU
+// bound; splitting the states over lanes quadruples the resident warps.)  Tiles of u / delta / dy are staged through
+// shared memory with coalesced row reads (L is the contiguous dimension; softplus is applied once per element while
+// staging) and read back as conflict-free broadcasts (pitch 33); the B / C rows of the group are staged once per tile.
+// The bound is the SFU: 16 exp per position and channel.  The forward also writes the state every 32 positions; the
+// backward walks the segments in reverse, recomputes the states of a segment from its checkpoint (sub-checkpoints every
+// 4 positions in shared memory, the 4 positions in registers) and accumulates dB / dC across the CTA's channels with a
+// warp transpose-reduction before one shared-memory reduction per warp and value.
 #include "common.cuh"
 
 namespace tamtr {
 
 constexpr int kScN = 16;          // states
-constexpr int kScCh = 128;        // channels (threads) per CTA
+constexpr int kScSg = 4;          // lanes per channel
+constexpr int kScNs = kScN / kScSg;   // states per lane
+constexpr int kScThreads = 128;
+constexpr int kScCh = kScThreads / kScSg;   // 32 channels per CTA
 constexpr int kScT = 32;          // positions per tile
-constexpr int kScSeg = 64;        // positions per checkpoint segment
+constexpr int kScSeg = 32;        // positions per checkpoint segment (= one tile)
 constexpr int kScSub = 4;         // positions recomputed into registers at a time (backward)
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float softplus20(float x) { return x > 20.0f ? x : log1pf(__expf(x)); }
+// exp2 on the SFU (ex2.approx: <= 2 ulp; arguments here are <= 0, results in (0, 1])
+__device__ __forceinline__ float ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
-// stage rows [ch0, ch0+128) x positions [t0, t0+32) of a [rows, L] array into tile[128][33] (zero past L)
-__device__ __forceinline__ void stage_rows(float (*tile)[kScT + 1], const float *__restrict__ src, size_t row0, int L,
-                                           int t0) {
+// ---- asynchronous staging (cp.async, 4-byte elements: the pitch-33 tiles are not 16-byte aligned): the next tile is
+// in flight while the current one is scanned.  ncu on the synchronous version: 6.1 warps per issue stalled on the long
+// scoreboard (global loads of the staging phase), SFU pipe 17 %, DRAM 8 % -- pure exposed memory latency.
+__device__ __forceinline__ void cp_async4(float *dst, const float *src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int n = valid ? 4 : 0;                       // src-size 0: the 4 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void stage_rows_async(float (*tile)[kScT + 1], const float *__restrict__ src, size_t row0,
+                                                 int L, int t0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = warp; r < kScCh; r += kScCh / 32) {
+    for (int r = warp; r < kScCh; r += kScThreads / 32) {
         const int t = t0 + lane;
-        tile[r][lane] = t < L ? __ldg(src + (row0 + r) * (size_t)L + t) : 0.0f;
+        cp_async4(&tile[r][lane], src + (row0 + r) * (size_t)L + min(t, L - 1), t < L);
+    }
+}
+__device__ __forceinline__ void stage_bc_async(float (*tile)[kScT + 1], const float *__restrict__ src, size_t grp, int L,
+                                               int t0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int n = warp; n < kScN; n += kScThreads / 32) {
+        const int t = t0 + lane;
+        cp_async4(&tile[n][lane], src + (grp * kScN + n) * (size_t)L + min(t, L - 1), t < L);
     }
 }
 
-// tile[16][32] of B or C for group (b, k): src [b, K, N, L]
-__device__ __forceinline__ void stage_bc(float (*tile)[kScT], const float *__restrict__ src, size_t grp, int L, int t0) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int n = warp; n < kScN; n += kScCh / 32) {
-        const int t = t0 + lane;
-        tile[n][lane] = t < L ? __ldg(src + (grp * kScN + n) * (size_t)L + t) : 0.0f;
-    }
-}
-
-__global__ void __launch_bounds__(kScCh)
+__global__ void __launch_bounds__(kScThreads)
 sscan_fwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, const float *__restrict__ A,
                  const float *__restrict__ Bm, const float *__restrict__ Cm, const float *__restrict__ Dv,
                  const float *__restrict__ bias, float *__restrict__ y, float *__restrict__ ckpt, int KD, int Dg, int L,
                  int n_seg) {
-    __shared__ float s_u[kScCh][kScT + 1], s_dt[kScCh][kScT + 1];   // y overwrites u in place (static smem <= 48 KB)
-    __shared__ float s_b[kScN][kScT], s_c[kScN][kScT];
-    const int b = blockIdx.y, ch0 = blockIdx.x * kScCh, ch = ch0 + threadIdx.x;
+    __shared__ float s_u[2][kScCh][kScT + 1], s_dl[2][kScCh][kScT + 1];
+    __shared__ float s_b[2][kScN][kScT + 1], s_c[2][kScN][kScT + 1];   // pitch 33: the warp's 4 state groups hit 4 banks
+    __shared__ float s_yp[kScThreads][kScT + 1];        // per-lane partial outputs: summed over the 4 lanes when stored
+    const int b = blockIdx.y, ch0 = blockIdx.x * kScCh;
+    const int c = threadIdx.x >> 2, sg = threadIdx.x & 3, ch = ch0 + c, n0 = sg * kScNs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t row0 = (size_t)b * KD + ch0;
     const size_t grp = (size_t)b * (KD / Dg) + ch0 / Dg;
-    float a2[kScN], h[kScN];
+    float a2[kScNs], h[kScNs];
 #pragma unroll
-    for (int n = 0; n < kScN; ++n) { a2[n] = __ldg(A + (size_t)ch * kScN + n) * kLog2e; h[n] = 0.0f; }
-    const float dsk = Dv != nullptr ? __ldg(Dv + ch) : 0.0f, bs = bias != nullptr ? __ldg(bias + ch) : 0.0f;
-    float *ck = ckpt != nullptr ? ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN : nullptr;
+    for (int j = 0; j < kScNs; ++j) { a2[j] = __ldg(A + (size_t)ch * kScN + n0 + j) * kLog2e; h[j] = 0.0f; }
+    const float dsk = Dv != nullptr ? __ldg(Dv + ch) : 0.0f;
+    float *ck = ckpt != nullptr ? ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN + n0 : nullptr;
 
-    for (int t0 = 0; t0 < L; t0 += kScT) {
+    auto prefetch = [&](int buf, int t0) {
+        stage_rows_async(s_u[buf], u, row0, L, t0);
+        stage_rows_async(s_dl[buf], dt, row0, L, t0);
+        stage_bc_async(s_b[buf], Bm, grp, L, t0);
+        stage_bc_async(s_c[buf], Cm, grp, L, t0);
+        cp_async_commit();
+    };
+    prefetch(0, 0);
+    int buf = 0;
+    for (int t0 = 0; t0 < L; t0 += kScT, buf ^= 1) {
+        if (t0 + kScT < L) { prefetch(buf ^ 1, t0 + kScT); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();
-        stage_rows(s_u, u, row0, L, t0);
-        stage_rows(s_dt, dt, row0, L, t0);
-        stage_bc(s_b, Bm, grp, L, t0);
-        stage_bc(s_c, Cm, grp, L, t0);
-        __syncthreads();
-        if (ck != nullptr && t0 % kScSeg == 0) {            // state BEFORE position t0
-            float4 *dst = reinterpret_cast<float4 *>(ck + (size_t)(t0 / kScSeg) * kScN);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+        // delta = softplus(dt + bias), once per element, in place (zero past L: h is then left unchanged)
+        for (int r = warp; r < kScCh; r += kScThreads / 32) {
+            const float v = s_dl[buf][r][lane] + (bias != nullptr ? __ldg(bias + ch0 + r) : 0.0f);
+            s_dl[buf][r][lane] = t0 + lane < L ? softplus20(v) : 0.0f;
         }
-        const int tn = min(kScT, L - t0);
-        for (int t = 0; t < tn; ++t) {
-            const float ut = s_u[threadIdx.x][t];
-            const float dl = softplus20(s_dt[threadIdx.x][t] + bs);
+        __syncthreads();
+        if (ck != nullptr && t0 % kScSeg == 0)              // state BEFORE position t0
+            *reinterpret_cast<float4 *>(ck + (size_t)(t0 / kScSeg) * kScN) = make_float4(h[0], h[1], h[2], h[3]);
+        // a fixed trip count lets the compiler hoist the loads / exps of 8 positions ahead of the only true dependency,
+        // the 4-cycle FFMA chain on h
+#pragma unroll 8
+        for (int t = 0; t < kScT; ++t) {
+            const float ut = s_u[buf][c][t], dl = s_dl[buf][c][t];
             const float du = dl * ut;
-            float acc = dsk * ut;
+            float acc = sg == 0 ? dsk * ut : 0.0f;
 #pragma unroll
-            for (int n = 0; n < kScN; ++n) {
-                h[n] = fmaf(exp2f(dl * a2[n]), h[n], du * s_b[n][t]);
-                acc = fmaf(s_c[n][t], h[n], acc);
+            for (int j = 0; j < kScNs; ++j) {
+                h[j] = fmaf(ex2(dl * a2[j]), h[j], du * s_b[buf][n0 + j][t]);
+                acc = fmaf(s_c[buf][n0 + j][t], h[j], acc);
             }
-            s_u[threadIdx.x][t] = acc;
+            s_yp[threadIdx.x][t] = acc;
         }
         __syncthreads();
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int r = warp; r < kScCh; r += kScCh / 32)
-            if (t0 + lane < L) y[(row0 + r) * (size_t)L + t0 + lane] = s_u[r][lane];
+        for (int r = warp; r < kScCh; r += kScThreads / 32)
+            if (t0 + lane < L)
+                y[(row0 + r) * (size_t)L + t0 + lane] = (s_yp[4 * r][lane] + s_yp[4 * r + 1][lane]) + (s_yp[4 * r + 2][lane] + s_yp[4 * r + 3][lane]);
+        // (the next iteration's first __syncthreads orders these reads of s_yp before its writes)
     }
-}
-
-// sum over the 32 lanes of v[i] -> returned to lane i (31 shuffles for 32 values)
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int i = 0; i < s; ++i) {
-            const float send = up ? v[i] : v[i + s];
-            const float got = __shfl_xor_sync(0xffffffffu, send, s);
-            v[i] = (up ? v[i + s] : v[i]) + got;
-        }
-    }
-    return v[0];
 }
 
 struct ScBwdSmem {
-    float u[kScCh][kScT + 1], dt[kScCh][kScT + 1], dy[kScCh][kScT + 1];   // current tile (reverse order)
-    float du[kScCh][kScT + 1], ddt[kScCh][kScT + 1];                      // outputs of the tile
-    float b[kScN][kScT], c[kScN][kScT];
-    float db[kScN][kScT], dc[kScN][kScT];                                // CTA-level dB / dC of the tile
-    float sub[kScSeg / kScSub][kScN][kScCh];                             // states before every 4th position of a segment
+    float u[2][kScCh][kScT + 1], dl[2][kScCh][kScT + 1], dy[2][kScCh][kScT + 1];   // double-buffered segment tiles
+    float b[2][kScN][kScT + 1], c[2][kScN][kScT + 1];
+    float raw[kScCh][kScT + 1];                                 // dt + bias (softplus' needs it)
+    float du[kScCh][kScT + 1], ddt[kScCh][kScT + 1];            // outputs of the segment
+    float db[kScN][kScT + 1], dc[kScN][kScT + 1];               // CTA-level dB / dC of the segment
+    float sub[kScSeg / kScSub][kScThreads][kScNs];              // states before every 4th position of the segment
 };
 
-__global__ void __launch_bounds__(kScCh)
+// One segment (= one 32-position tile) at a time, last to first: its tiles are prefetched (cp.async) while the previous
+// one is processed; the states inside the segment are recomputed from the forward's checkpoint (pass 1, keeping the state
+// before every 4th position), then the segment is walked backwards in groups of 4 positions held in registers (pass 2).
+// Positions past L are staged as zeros and contribute nothing, so every segment is walked in full.
+__global__ void __launch_bounds__(kScThreads)
 sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, const float *__restrict__ A,
                  const float *__restrict__ Bm, const float *__restrict__ Cm, const float *__restrict__ Dv,
                  const float *__restrict__ bias, const float *__restrict__ dy, const float *__restrict__ ckpt,
@@ -127,126 +153,143 @@ sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
                  int n_seg) {
     extern __shared__ unsigned char sc_raw[];
     ScBwdSmem &sm = *reinterpret_cast<ScBwdSmem *>(sc_raw);
-    const int b = blockIdx.y, ch0 = blockIdx.x * kScCh, ch = ch0 + threadIdx.x;
+    const int b = blockIdx.y, ch0 = blockIdx.x * kScCh;
+    const int c = threadIdx.x >> 2, sg = threadIdx.x & 3, ch = ch0 + c, n0 = sg * kScNs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t row0 = (size_t)b * KD + ch0;
     const size_t grp = (size_t)b * (KD / Dg) + ch0 / Dg;
-    float a1[kScN], a2[kScN], dh[kScN], dA[kScN];
+    float a1[kScNs], a2[kScNs], dh[kScNs], dA[kScNs];
 #pragma unroll
-    for (int n = 0; n < kScN; ++n) {
-        a1[n] = __ldg(A + (size_t)ch * kScN + n);
-        a2[n] = a1[n] * kLog2e;
-        dh[n] = dA[n] = 0.0f;
+    for (int j = 0; j < kScNs; ++j) {
+        a1[j] = __ldg(A + (size_t)ch * kScN + n0 + j);
+        a2[j] = a1[j] * kLog2e;
+        dh[j] = dA[j] = 0.0f;
     }
-    const float dsk = Dv != nullptr ? __ldg(Dv + ch) : 0.0f, bs = bias != nullptr ? __ldg(bias + ch) : 0.0f;
+    const float dsk = Dv != nullptr ? __ldg(Dv + ch) : 0.0f;
     float dD = 0.0f, dbias = 0.0f;
-    const float *ck = ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN;
+    const float *ck = ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN + n0;
 
-    for (int seg = n_seg - 1; seg >= 0; --seg) {
-        const int s0 = seg * kScSeg, sn = min(kScSeg, L - s0);
-        // ---- pass 1: recompute the segment forward, keep the state before every 4th position
-        float h[kScN];
+    auto prefetch = [&](int buf, int t0) {
+        stage_rows_async(sm.u[buf], u, row0, L, t0);
+        stage_rows_async(sm.dl[buf], dt, row0, L, t0);
+        stage_rows_async(sm.dy[buf], dy, row0, L, t0);
+        stage_bc_async(sm.b[buf], Bm, grp, L, t0);
+        stage_bc_async(sm.c[buf], Cm, grp, L, t0);
+        cp_async_commit();
+    };
+    prefetch(0, (n_seg - 1) * kScSeg);
+    int buf = 0;
+    for (int seg = n_seg - 1; seg >= 0; --seg, buf ^= 1) {
+        const int t0 = seg * kScSeg;
+        if (seg > 0) { prefetch(buf ^ 1, t0 - kScSeg); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();                                           // (also: the previous segment's outputs were stored)
+        for (int r = warp; r < kScCh; r += kScThreads / 32) {
+            const float v = sm.dl[buf][r][lane] + (bias != nullptr ? __ldg(bias + ch0 + r) : 0.0f);
+            sm.raw[r][lane] = v;
+            sm.dl[buf][r][lane] = t0 + lane < L ? softplus20(v) : 0.0f;
+        }
+        for (int i = threadIdx.x; i < kScN * (kScT + 1); i += kScThreads) { (&sm.db[0][0])[i] = 0.0f; (&sm.dc[0][0])[i] = 0.0f; }
+        __syncthreads();
+        // ---- pass 1: recompute the segment forward from its checkpoint
         {
-            const float4 *src = reinterpret_cast<const float4 *>(ck + (size_t)seg * kScN);
+            const float4 v = *reinterpret_cast<const float4 *>(ck + (size_t)seg * kScN);
+            float h[kScNs] = {v.x, v.y, v.z, v.w};
+#pragma unroll 8
+            for (int t = 0; t < kScT; ++t) {
+                if ((t & (kScSub - 1)) == 0)
+                    *reinterpret_cast<float4 *>(sm.sub[t / kScSub][threadIdx.x]) = make_float4(h[0], h[1], h[2], h[3]);
+                const float dl = sm.dl[buf][c][t];
+                const float du = dl * sm.u[buf][c][t];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 v = src[q];
-                h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+                for (int j = 0; j < kScNs; ++j) h[j] = fmaf(ex2(dl * a2[j]), h[j], du * sm.b[buf][n0 + j][t]);
             }
         }
-        for (int t0 = s0; t0 < s0 + sn; t0 += kScT) {
-            __syncthreads();
-            stage_rows(sm.u, u, row0, L, t0);
-            stage_rows(sm.dt, dt, row0, L, t0);
-            stage_bc(sm.b, Bm, grp, L, t0);
-            __syncthreads();
-            const int tn = min(kScT, s0 + sn - t0);
-            for (int t = 0; t < tn; ++t) {
-                if (((t0 - s0 + t) & (kScSub - 1)) == 0) {
-#pragma unroll
-                    for (int n = 0; n < kScN; ++n) sm.sub[(t0 - s0 + t) / kScSub][n][threadIdx.x] = h[n];
-                }
-                const float dl = softplus20(sm.dt[threadIdx.x][t] + bs);
-                const float du = dl * sm.u[threadIdx.x][t];
-#pragma unroll
-                for (int n = 0; n < kScN; ++n) h[n] = fmaf(exp2f(dl * a2[n]), h[n], du * sm.b[n][t]);
+        // ---- pass 2: groups of 4 positions, last to first (each thread reads back only its own sub-checkpoints)
+        for (int g0 = kScT - kScSub; g0 >= 0; g0 -= kScSub) {
+            float hist[kScSub + 1][kScNs];                       // hist[j] = state before position g0 + j
+            {
+                const float4 v = *reinterpret_cast<const float4 *>(sm.sub[g0 / kScSub][threadIdx.x]);
+                hist[0][0] = v.x; hist[0][1] = v.y; hist[0][2] = v.z; hist[0][3] = v.w;
             }
-        }
-        // ---- pass 2: tiles of the segment in reverse; inside a tile, groups of 4 positions in reverse
-        for (int t0 = s0 + ((sn - 1) / kScT) * kScT; t0 >= s0; t0 -= kScT) {
-            __syncthreads();
-            stage_rows(sm.u, u, row0, L, t0);
-            stage_rows(sm.dt, dt, row0, L, t0);
-            stage_rows(sm.dy, dy, row0, L, t0);
-            stage_bc(sm.b, Bm, grp, L, t0);
-            stage_bc(sm.c, Cm, grp, L, t0);
-            for (int i = threadIdx.x; i < kScN * kScT; i += kScCh) { (&sm.db[0][0])[i] = 0.0f; (&sm.dc[0][0])[i] = 0.0f; }
-            __syncthreads();
-            const int tn = min(kScT, s0 + sn - t0);
-            for (int g0 = ((tn - 1) / kScSub) * kScSub; g0 >= 0; g0 -= kScSub) {
-                const int gn = min(kScSub, tn - g0);
-                // states h_{t-1} (hist[j]) for the positions of the group, from the sub-checkpoint
-                float hist[kScSub + 1][kScN];
 #pragma unroll
-                for (int n = 0; n < kScN; ++n) hist[0][n] = sm.sub[(t0 - s0 + g0) / kScSub][n][threadIdx.x];
+            for (int j = 0; j < kScSub; ++j) {
+                const float dl = sm.dl[buf][c][g0 + j];
+                const float du = dl * sm.u[buf][c][g0 + j];
 #pragma unroll
-                for (int j = 0; j < kScSub; ++j) {
-                    const float dl = j < gn ? softplus20(sm.dt[threadIdx.x][g0 + j] + bs) : 0.0f;
-                    const float du = dl * (j < gn ? sm.u[threadIdx.x][g0 + j] : 0.0f);
+                for (int q = 0; q < kScNs; ++q)
+                    hist[j + 1][q] = fmaf(ex2(dl * a2[q]), hist[j][q], du * sm.b[buf][n0 + q][g0 + j]);
+            }
 #pragma unroll
-                    for (int n = 0; n < kScN; ++n)
-                        hist[j + 1][n] = j < gn ? fmaf(exp2f(dl * a2[n]), hist[j][n], du * sm.b[n][g0 + j]) : hist[j][n];
+            for (int j = kScSub - 1; j >= 0; --j) {
+                const int t = g0 + j;
+                const float ut = sm.u[buf][c][t], dl = sm.dl[buf][c][t], gy = sm.dy[buf][c][t];
+                float d_dl = 0.0f, d_u = 0.0f;
+                float red[2 * kScNs];                            // dB then dC contributions of this lane's 4 states
+#pragma unroll
+                for (int q = 0; q < kScNs; ++q) {
+                    const float an = ex2(dl * a2[q]);
+                    const float bn = sm.b[buf][n0 + q][t];
+                    dh[q] = fmaf(sm.c[buf][n0 + q][t], gy, dh[q]);             // dL/dh_t
+                    red[kScNs + q] = gy * hist[j + 1][q];
+                    red[q] = dh[q] * dl * ut;
+                    const float dah = dh[q] * an * hist[j][q];                 // dh * a * h_{t-1}
+                    d_dl = fmaf(dah, a1[q], fmaf(dh[q] * bn, ut, d_dl));
+                    dA[q] = fmaf(dah, dl, dA[q]);
+                    d_u = fmaf(dh[q] * bn, dl, d_u);
+                    dh[q] *= an;                                               // dL/dh_{t-1}
                 }
+                // sums over the 16 states of the channel: across its 4 lanes
+                d_dl += __shfl_xor_sync(0xffffffffu, d_dl, 1);
+                d_u += __shfl_xor_sync(0xffffffffu, d_u, 1);
+                d_dl += __shfl_xor_sync(0xffffffffu, d_dl, 2);
+                d_u += __shfl_xor_sync(0xffffffffu, d_u, 2);
+                // dB / dC: sum over the warp's 8 channels (lane bits 2..4), 8 values -> 1 per lane in 7 shuffles
 #pragma unroll
-                for (int j = kScSub - 1; j >= 0; --j) {
-                    if (j >= gn) continue;
-                    const int t = g0 + j;
-                    const float ut = sm.u[threadIdx.x][t], raw = sm.dt[threadIdx.x][t] + bs;
-                    const float dl = softplus20(raw);
-                    const float gy = sm.dy[threadIdx.x][t];
-                    float d_dl = 0.0f, d_u = dsk * gy;
-                    float red[32];
+                for (int s = 4; s >= 1; s >>= 1) {
+                    const bool up = (lane & (s << 2)) != 0;
 #pragma unroll
-                    for (int n = 0; n < kScN; ++n) {
-                        const float an = exp2f(dl * a2[n]);
-                        const float bn = sm.b[n][t];
-                        dh[n] = fmaf(sm.c[n][t], gy, dh[n]);                    // dL/dh_t
-                        red[kScN + n] = gy * hist[j + 1][n];                     // dC contribution
-                        red[n] = dh[n] * dl * ut;                                // dB contribution
-                        const float dah = dh[n] * an * hist[j][n];               // dh * a * h_{t-1}
-                        d_dl = fmaf(dah, a1[n], fmaf(dh[n] * bn, ut, d_dl));
-                        dA[n] = fmaf(dah, dl, dA[n]);
-                        d_u = fmaf(dh[n] * bn, dl, d_u);
-                        dh[n] *= an;                                             // dL/dh_{t-1}
+                    for (int i = 0; i < s; ++i) {
+                        const float send = up ? red[i] : red[i + s];
+                        const float got = __shfl_xor_sync(0xffffffffu, send, s << 2);
+                        red[i] = (up ? red[i + s] : red[i]) + got;
                     }
-                    const float r = warp_transpose_sum(red, lane);               // lane i: sum over the warp's channels
-                    if (lane < kScN) atomicAdd(&sm.db[lane][t], r); else atomicAdd(&sm.dc[lane - kScN][t], r);
+                }
+                {   // this lane now holds value index v = (lane >> 2) & 7 of state group sg: v < 4 -> dB, else dC
+                    const int v = (lane >> 2) & 7;
+                    float *dst = v < kScNs ? &sm.db[n0 + v][t] : &sm.dc[n0 + v - kScNs][t];
+                    atomicAdd(dst, red[0]);
+                }
+                if (sg == 0) {
+                    const float raw = sm.raw[c][t];
+                    d_u = fmaf(dsk, gy, d_u);
                     dD = fmaf(gy, ut, dD);
                     const float d_raw = raw > 20.0f ? d_dl : d_dl * (1.0f / (1.0f + __expf(-raw)));
                     dbias += d_raw;
-                    sm.du[threadIdx.x][t] = d_u;
-                    sm.ddt[threadIdx.x][t] = d_raw;
+                    sm.du[c][t] = d_u;
+                    sm.ddt[c][t] = d_raw;
                 }
             }
-            __syncthreads();
-            for (int r = warp; r < kScCh; r += kScCh / 32) {
-                if (t0 + lane < s0 + sn) {
-                    g_u[(row0 + r) * (size_t)L + t0 + lane] = sm.du[r][lane];
-                    g_dt[(row0 + r) * (size_t)L + t0 + lane] = sm.ddt[r][lane];
-                }
+        }
+        __syncthreads();
+        for (int r = warp; r < kScCh; r += kScThreads / 32) {
+            if (t0 + lane < L) {
+                g_u[(row0 + r) * (size_t)L + t0 + lane] = sm.du[r][lane];
+                g_dt[(row0 + r) * (size_t)L + t0 + lane] = sm.ddt[r][lane];
             }
-            for (int n = warp; n < kScN; n += kScCh / 32) {
-                if (t0 + lane < s0 + sn) {
-                    atomicAdd(g_B + (grp * kScN + n) * (size_t)L + t0 + lane, sm.db[n][lane]);
-                    atomicAdd(g_C + (grp * kScN + n) * (size_t)L + t0 + lane, sm.dc[n][lane]);
-                }
+        }
+        for (int n = warp; n < kScN; n += kScThreads / 32) {
+            if (t0 + lane < L) {
+                atomicAdd(g_B + (grp * kScN + n) * (size_t)L + t0 + lane, sm.db[n][lane]);
+                atomicAdd(g_C + (grp * kScN + n) * (size_t)L + t0 + lane, sm.dc[n][lane]);
             }
         }
     }
 #pragma unroll
-    for (int n = 0; n < kScN; ++n) atomicAdd(g_A + (size_t)ch * kScN + n, dA[n]);   // over the batch
-    if (g_D != nullptr) atomicAdd(g_D + ch, dD);
-    if (g_bias != nullptr) atomicAdd(g_bias + ch, dbias);
+    for (int j = 0; j < kScNs; ++j) atomicAdd(g_A + (size_t)ch * kScN + n0 + j, dA[j]);   // over the batch
+    if (sg == 0) {
+        if (g_D != nullptr) atomicAdd(g_D + ch, dD);
+        if (g_bias != nullptr) atomicAdd(g_bias + ch, dbias);
+    }
 }
 
 }  // namespace tamtr
@@ -258,6 +301,7 @@ static int sscan_check(int Bn, int KD, int Dg, int N, int L) {
     TAMTR_CHECK_ARG(N == kScN, TAMTR_E_UNSUPPORTED, "selective_scan: d_state = %d unsupported (16)", N);
     TAMTR_CHECK_ARG(KD % Dg == 0 && Dg % kScCh == 0, TAMTR_E_UNSUPPORTED,
                     "selective_scan: channels per direction (%d) must be a multiple of %d", Dg, kScCh);
+    TAMTR_CHECK_ARG(KD / kScCh <= 2147483647 / 1, TAMTR_E_UNSUPPORTED, "selective_scan: too many channels");
     TAMTR_CHECK_ARG(Bn <= 65535, TAMTR_E_UNSUPPORTED, "selective_scan: batch too large");
     return 0;
 }
@@ -273,7 +317,7 @@ extern "C" int tamtr_selective_scan_forward(const float *u, const float *dt, con
     cudaStream_t st = (cudaStream_t)stream;
     {
         KernelTimer timer(K_SSCAN_FWD, st);
-        sscan_fwd_kernel<<<dim3(KD / kScCh, Bn), kScCh, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, ckpt, KD, Dg, L,
+        sscan_fwd_kernel<<<dim3(KD / kScCh, Bn), kScThreads, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, ckpt, KD, Dg, L,
                                                                 tamtr_selective_scan_segments(L));
     }
     count_launch();
@@ -305,7 +349,7 @@ extern "C" int tamtr_selective_scan_backward(const float *u, const float *dt, co
     }
     {
         KernelTimer timer(K_SSCAN_BWD, st);
-        sscan_bwd_kernel<<<dim3(KD / kScCh, Bn), kScCh, sizeof(ScBwdSmem), st>>>(
+        sscan_bwd_kernel<<<dim3(KD / kScCh, Bn), kScThreads, sizeof(ScBwdSmem), st>>>(
             u, dt, A, Bm, Cm, D, bias, dy, ckpt, g_u, g_dt, g_A, g_B, g_C, g_D, g_bias, KD, Dg, L,
             tamtr_selective_scan_segments(L));
     }

@@ -6,10 +6,9 @@
 
 Same constructor arguments, forward signatures, outputs and state_dict keys.  The glue (1x1 input projection,
 anchors, top-k query selection, denoising group) stays a sequence of library ops as in the reference; the decoder it
-drives runs on the sm_100a kernels (modules.py).  ManbaWorldDecoder's VSSBlocks (VMamba selective scan, an external
-CUDA extension that is not part of the reference tree -- SURVEY.md section 8c) are NOT on this path: they are
-represented by `nn.Identity` placeholders, exactly as the parity oracle does, and a checkpoint's `VSSBlocks.*`
-entries are ignored on load.
+drives runs on the sm_100a kernels (modules.py).  ManbaWorldDecoder's VSSBlocks (VMamba selective scan; the reference
+needs an external CUDA extension for them that is not part of its tree -- SURVEY.md section 8c) run on the kernels of
+csrc/sscan.cu (vss.py); `vss=False` replaces them by identities, the configuration of the head-level parity fixtures.
 """
 import math
 
@@ -17,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .vss import VSSBlock
 from .modules import (MLP, ContrastiveHeadMLP, DeformableTransformerDecoder, DeformableTransformerDecoderLayer,
                       TextDeformableTransformerDecoder)
 
@@ -327,18 +327,24 @@ class RTDETRDecoder(_HeadBase):
 class ManbaWorldDecoder(_HeadBase):
     """TAM-TR's Multi-modal Encoder-decoder Head (head.py:1005-1290): forward(x, text [B,K,512], batch=None).
 
-    `VSSBlocks` are identity placeholders (see module docstring); `dims`/`drop_path` are accepted and ignored."""
+    `VSSBlocks` (head.py:1092-1098): one VMamba VSSBlock per pyramid level in front of input_proj, on the selective-scan
+    kernels of csrc/sscan.cu (tamtr_b200/vss.py).  `vss=False` replaces them by identities -- the configuration the
+    head-level parity fixtures and the CPU reference arm use, because the reference cannot run its own VSSBlocks without
+    the un-vendored `selective_scan_cuda_core` extension; `VSSBlocks.*` checkpoint entries are then skipped on load."""
 
     def __init__(self, nc=80, ch=(512, 1024, 2048), hd=512, nq=300, ndp=4, nh=8, ndl=6, d_ffn=1024, eval_idx=-1,
                  dropout=0., act=nn.ReLU(), nd=100, label_noise_ratio=0.5, box_noise_scale=1.0,
-                 learnt_init_query=False, dims=(128, 256, 512), drop_path=(0.1, 0.1, 0.1), embed=512, with_bn=False):
+                 learnt_init_query=False, dims=(128, 256, 512), drop_path=(0.1, 0.1, 0.1), embed=512, with_bn=False,
+                 vss=True):
         super().__init__()
         if with_bn:
             raise NotImplementedError("tamtr_b200: BNContrastiveHeadMLP (with_bn=True) is not on the TAMTR.yaml path")
         self.nhead = nh
         self.num_decoder_layers = ndl
         self._build_common(nc, ch, hd, nq, nd, label_noise_ratio, box_noise_scale, learnt_init_query)
-        self.VSSBlocks = nn.ModuleList(nn.Identity() for _ in dims)
+        self.vss = bool(vss)
+        self.VSSBlocks = nn.ModuleList(VSSBlock(hidden_dim=d, drop_path=p) if vss else nn.Identity()
+                                       for d, p in zip(dims, drop_path))
         self.num_Blocks = len(dims)
         layer = DeformableTransformerDecoderLayer(hd, nh, d_ffn, dropout, act, self.nl, ndp)
         self.decoder = TextDeformableTransformerDecoder(hd, layer, ndl, eval_idx)
@@ -347,7 +353,8 @@ class ManbaWorldDecoder(_HeadBase):
         self._reset_common()
 
     def forward(self, x, text, batch=None):
-        x = [blk(f) for blk, f in zip(self.VSSBlocks, x)]
+        if self.vss:        # head.py:1134: channel-last in and out
+            x = [blk(f.permute(0, 2, 3, 1)).permute(0, 3, 1, 2) for blk, f in zip(self.VSSBlocks, x)]
         feats, shapes, hub = self._encode(x)
         dn_embed, dn_bbox, attn_mask, dn_meta = self._cdn(batch)
         embed, refer_bbox, enc_bboxes, enc_scores = self._get_decoder_input(feats, shapes, dn_embed, dn_bbox, hub)
@@ -356,5 +363,6 @@ class ManbaWorldDecoder(_HeadBase):
         return self._finish(dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
-        state_dict = {k: v for k, v in state_dict.items() if not k.startswith("VSSBlocks.")}
+        if not self.vss:
+            state_dict = {k: v for k, v in state_dict.items() if not k.startswith("VSSBlocks.")}
         return super().load_state_dict(state_dict, strict=strict, **kw)

@@ -231,7 +231,7 @@ def test_meh_head_train_and_eval(cuda_lib, name):
     denoising group, forward + backward; then eval."""
     from tamtr_b200.head import ManbaWorldDecoder
     c = load_golden("modules_heads")["cases"][name]
-    m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3)
+    m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3, vss=False)
     filled_state_dict(m, 73, c["manifest"])
     m.cuda().train()
     B, sizes = c["B"], c["sizes"]
@@ -299,7 +299,7 @@ def test_text_decoder_bf16_autocast(cuda_lib):
     gradients is: not worse than that (x1.25)."""
     from tamtr_b200.head import ManbaWorldDecoder
     c = load_golden("modules_heads")["cases"]["meh_syaml_small"]
-    m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3)
+    m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3, vss=False)
     filled_state_dict(m, 73, c["manifest"])
     m.cuda().train()
     sd = {k: v.detach() for k, v in m.state_dict().items()}
@@ -354,7 +354,7 @@ def test_meh_head_inference_1280(cuda_lib):
     sequence on the host CPU (fp32); rows are aligned through the predicted boxes (top-k may swap near-tied tokens)."""
     from tamtr_b200.head import ManbaWorldDecoder
     nq = 900
-    m = ManbaWorldDecoder(10, [128, 256, 512], 512, nq, 4, 8, 3)
+    m = ManbaWorldDecoder(10, [128, 256, 512], 512, nq, 4, 8, 3, vss=False)
     sd = filled_state_dict(m, 81)
     m.cuda().eval()
     xs = [seeding.seeded_smooth_map(82, f"x{i}", (1, ch, s, s)) for i, (ch, s) in enumerate(zip((128, 256, 512), (320, 160, 80)))]

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 def _setup(B=2, sizes=(40, 20, 10)):
     from tamtr_b200.head import ManbaWorldDecoder
     torch.manual_seed(0)
-    m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3).cuda().train()
+    m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3, vss=False).cuda().train()
     xs = [seeding.seeded_smooth_map(5, f"x{i}", (B, c, s, s)).bfloat16() for i, (c, s) in enumerate(zip((128, 256, 512), sizes))]
     text = torch.nn.functional.normalize(seeding.seeded_tensor(5, "t", (B, 10, 512)), dim=-1)
     g = torch.Generator().manual_seed(1)

@@ -5,7 +5,7 @@ from helpers import *
 from oracle import head_ref, seeding
 from tamtr_b200.head import ManbaWorldDecoder
 torch.backends.cudnn.allow_tf32 = False
-m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3)
+m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3, vss=False)
 filled_state_dict(m, 73, None)
 m.cuda().train(); m.num_denoising = 0
 sizes = (40, 20, 10)

@@ -6,7 +6,7 @@ from oracle import head_ref, seeding
 from tamtr_b200.head import ManbaWorldDecoder
 torch.backends.cudnn.allow_tf32 = False
 c = load_golden("modules_heads")["cases"]["meh_syaml_small"]
-m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3)
+m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3, vss=False)
 filled_state_dict(m, 73, c["manifest"])
 m.cuda().train()
 sd = {k: v.detach() for k, v in m.state_dict().items()}

@@ -9,7 +9,7 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 c = load_golden("modules_heads")["cases"]["meh_syaml_full"]
 for sizes, B in (((160, 80, 40), 1), ((40, 20, 10), 2), ((80, 40, 20), 1)):
-    m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3)
+    m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3, vss=False)
     filled_state_dict(m, 73, None)
     sd = {k: v.detach().clone().cpu() for k, v in m.state_dict().items()}
     sd = {k: (v.requires_grad_() if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
