@@ -21,6 +21,12 @@ void set_error(const char *fmt, ...) {
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int sm_count() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
 // ---- per-kernel CUDA-event timing (bench.py's roofline numbers): events are recorded on the launching stream,
 // immediately around the kernel launch; disabled by default and skipped while the stream is being captured.
 static std::mutex g_prof_mu;

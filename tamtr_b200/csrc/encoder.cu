@@ -492,7 +492,7 @@ extern "C" int tamtr_col_sum(const void *g, float *out, int dtype, int rows, int
     TAMTR_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)n * sizeof(float), st));
     const int gx = (n / np + 31) / 32;
     int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+    n_sm = ::tamtr::sm_count();
     int gy = (2 * n_sm + gx - 1) / gx;                       // ~2 CTAs per SM in total
     const int max_gy = (rows + 15) / 16;                     // at least 16 rows per CTA
     if (gy > max_gy) gy = max_gy;

@@ -696,7 +696,7 @@ extern "C" int tamtr_gate_conv3x3_tc_forward(const void *x_nhwc, const void *w_o
     }
 
     int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+    n_sm = ::tamtr::sm_count();
     const long n_tiles = (long)B * g.tiles_x * g.tiles_y;
     // persistent CTAs (single) / CTA pairs, one per SM; equalise the number of tiles each walks so the last wave is
     // not ragged
@@ -704,13 +704,15 @@ extern "C" int tamtr_gate_conv3x3_tc_forward(const void *x_nhwc, const void *w_o
     const long waves = (n_tiles + workers - 1) / workers;
     const int n_work = (int)((n_tiles + waves - 1) / waves);
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};          // cudaFuncSetAttribute is per device
+    int dev_id = 0;
+    TAMTR_CUDA_OK(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
         TAMTR_CUDA_OK(cudaFuncSetAttribute(gate_conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(sizeof(CvSmem) + 1024)));
         TAMTR_CUDA_OK(cudaFuncSetAttribute(gate_conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(sizeof(PrSmem) + 1024)));
-        attr_set = true;
+        if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
     {
         KernelTimer timer(K_GATE_CONV_TC, st);

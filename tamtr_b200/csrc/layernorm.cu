@@ -151,7 +151,7 @@ add_layernorm_bwd_kernel(const void *__restrict__ dy, int dy_dtype, const float 
 
 static int ln_ctas(int rows) {
     int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+    n_sm = ::tamtr::sm_count();
     const int need = (rows + kLnWarps - 1) / kLnWarps;
     return need < 2 * n_sm ? need : 2 * n_sm;
 }

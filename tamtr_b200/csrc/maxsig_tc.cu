@@ -203,15 +203,17 @@ extern "C" int tamtr_max_sigmoid_tc_forward(const void *embed_bf16, const float 
     const int n_tiles = (HW + kTcTileM - 1) / kTcTileM;
     // one wave of (at most) 2 CTAs per SM: each CTA walks the tiles of its (b, m) with stride gridDim.x
     int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+    n_sm = ::tamtr::sm_count();
     int chunks = (2 * n_sm) / (B * nh);
     if (chunks < 1) chunks = 1;
     if (chunks > n_tiles) chunks = n_tiles;
     const size_t smem = sizeof(TcSmem) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};          // cudaFuncSetAttribute is per device
+    int dev_id = 0;
+    TAMTR_CUDA_OK(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
         TAMTR_CUDA_OK(cudaFuncSetAttribute(gate_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     {

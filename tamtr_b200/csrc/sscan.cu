@@ -341,11 +341,13 @@ extern "C" int tamtr_selective_scan_backward(const float *u, const float *dt, co
     TAMTR_CUDA_OK(cudaMemsetAsync(g_C, 0, grp_elems * sizeof(float), st));
     if (g_D) TAMTR_CUDA_OK(cudaMemsetAsync(g_D, 0, (size_t)KD * sizeof(float), st));
     if (g_bias) TAMTR_CUDA_OK(cudaMemsetAsync(g_bias, 0, (size_t)KD * sizeof(float), st));
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};          // cudaFuncSetAttribute is per device
+    int dev_id = 0;
+    TAMTR_CUDA_OK(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
         TAMTR_CUDA_OK(cudaFuncSetAttribute(sscan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(ScBwdSmem)));
-        attr_set = true;
+        if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
     {
         KernelTimer timer(K_SSCAN_BWD, st);

@@ -134,15 +134,15 @@ def _ffn(layer, tgt):
 
 def _folded_bn(block, bn):
     """BatchNorm2d in eval mode as a per-channel affine (fp32), cached on the block until a parameter or statistic
-    changes."""
-    key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+    changes (the entry keeps the four source tensors and is valid only for those very objects at those versions)."""
+    src = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
     hit = block.__dict__.get("_tamtr_fold_cache")
-    if hit is None or hit[0] != key:
+    if hit is None or any(a is not b for a, b in zip(hit[0], src)) or hit[1] != tuple(t._version for t in src):
         s = bn.weight.detach().float() * torch.rsqrt(bn.running_var.float() + bn.eps)
         t = bn.bias.detach().float() - bn.running_mean.float() * s
-        hit = (key, s.contiguous(), t.contiguous())
+        hit = (src, tuple(t_._version for t_ in src), s.contiguous(), t.contiguous())
         block.__dict__["_tamtr_fold_cache"] = hit
-    return hit[1], hit[2]
+    return hit[2], hit[3]
 
 
 class DeformableTransformerDecoderLayer(nn.Module):

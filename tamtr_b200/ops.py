@@ -651,16 +651,24 @@ _OHWI_CACHE = {}
 
 
 def _weight_ohwi(weight):
-    """[Co, Ci, 3, 3] -> bf16 [Co, 3, 3, Ci] (the K-major B operand), cached per (storage, version): inference calls
-    the block with the same weights every time."""
-    key = (weight.data_ptr(), weight._version, weight.dtype, tuple(weight.shape), weight.device)
-    hit = _OHWI_CACHE.get(key)
-    if hit is None:
-        if len(_OHWI_CACHE) >= 32:
+    """[Co, Ci, 3, 3] -> bf16 [Co, 3, 3, Ci] (the K-major B operand), cached per weight TENSOR OBJECT and version:
+    inference calls the block with the same parameter every time.  The entry holds a weak reference and is only used
+    when it still points at this very tensor (an address or id can be recycled by another tensor)."""
+    import weakref
+    hit = _OHWI_CACHE.get(id(weight))
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
+        return hit[2]
+    if len(_OHWI_CACHE) >= 64:
+        for k in [k for k, v in _OHWI_CACHE.items() if v[0]() is None]:
+            del _OHWI_CACHE[k]
+        if len(_OHWI_CACHE) >= 64:
             _OHWI_CACHE.clear()
-        hit = weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-        _OHWI_CACHE[key] = hit
-    return hit
+    out = weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    try:
+        _OHWI_CACHE[id(weight)] = (weakref.ref(weight), weight._version, out)
+    except TypeError:
+        pass
+    return out
 
 
 def _gate_conv3x3_launch(x, weight, bn_scale, bn_shift, gate, nh):
