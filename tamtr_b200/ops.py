@@ -271,7 +271,7 @@ class _LocWFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             grad_w = (g_lp.t() @ q2c if w_c.dtype == torch.float32
                       else torch.mm(g_lp.t(), q2c, out_dtype=torch.float32)).to(wd)
-        grad_b = grad_raw.sum(0).to(bd) if ctx.needs_input_grad[2] else None
+        grad_b = col_sum(grad_raw).to(bd) if ctx.needs_input_grad[2] else None
         return grad_q, grad_w, grad_b, (grad_ref.to(rd) if need_ref else None), None, None, None, None
 
 
