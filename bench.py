@@ -352,7 +352,8 @@ def main():
                for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event() for _ in range(2)]
 
     def stage(i):
         s = i % 2
@@ -364,10 +365,14 @@ def main():
             ready[s].record(copy_stream)
 
     def e2e_loop(n):
+        """Every step: H2D of its inputs (copy stream, overlapping the previous step), the step, D2H of its loss.  The host
+        reads step i's loss right after it has enqueued step i+1 (a training loop logging its loss does the same), so the
+        device is never idle waiting for the host; every step's loss is read."""
         cur = torch.cuda.current_stream(dev)
         for s in range(2):
             consumed[s].record(cur)
         stage(0)
+        losses = []
         for i in range(n):
             s = i % 2
             if i + 1 < n:
@@ -376,9 +381,16 @@ def main():
             step.load_inputs((staging[s][0], staging[s][1], None))   # device->static-buffer copy (graph inputs)
             consumed[s].record(cur)
             loss = step.run()
-            loss_host.copy_(loss, non_blocking=True)
-            cur.synchronize()                      # the user reads the loss every step
-            float(loss_host)
+            loss_host[s].copy_(loss, non_blocking=True)
+            loss_done[s].record(cur)
+            if i > 0:
+                loss_done[1 - s].synchronize()
+                losses.append(float(loss_host[1 - s]))
+        if n > 0:
+            loss_done[(n - 1) % 2].synchronize()
+            losses.append(float(loss_host[(n - 1) % 2]))
+        assert len(losses) == n
+        return losses
 
     e2e_loop(args.warmup)
     barrier()
@@ -389,6 +401,16 @@ def main():
     barrier()
     e2e_sec = dp.max_over_ranks(t0.elapsed_time(t1) / 1e3, dev)
     e2e_value = ws * B * args.steps / e2e_sec
+    # the host->device link on its own (explains e2e when it, not the step, is the longer leg)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        c0.record(copy_stream)
+        for _ in range(4):
+            for d, h in zip(staging[0][0], host[0][0]):
+                d.copy_(h, non_blocking=True)
+        c1.record(copy_stream)
+    copy_stream.synchronize()
+    h2d_gbs = 4 * sum(x.numel() * x.element_size() for x in host[0][0]) / (c0.elapsed_time(c1) / 1e3) / 1e9
 
     # ------------------------------------------------------------------ per-kernel device times (instrumented pass)
     kern = {}
@@ -428,7 +450,8 @@ def main():
                                parallelism=f"dp{ws}" if ws > 1 else "single"),
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "ms_per_step": e2e_sec / args.steps * 1e3},
+                        "ms_per_step": e2e_sec / args.steps * 1e3, "h2d_link_gbs_measured": h2d_gbs,
+                        "h2d_ms_per_step_at_link_rate": h2d / h2d_gbs / 1e6},
                 "gpu_launches": int(launches),
                 "roofline": roof, "kernels": per_kernel}
         if ws == 1 and args.loss == "surrogate":

@@ -71,8 +71,11 @@ class FlatGrads:
         """One all-reduce (sum) + scale: the DDP semantics of trainer.py:241 (mean over ranks)."""
         rank, ws = world()
         if ws > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(ws)
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)      # the division happens inside the collective
+            else:                                                     # gloo (CPU tests) has no AVG
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+                self.flat.div_(ws)
         return self.flat
 
     def scatter(self):
