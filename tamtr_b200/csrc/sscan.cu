@@ -53,20 +53,30 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ void stage_rows_async(float (*tile)[kScT + 1], const float *__restrict__ src, size_t row0,
-                                                 int L, int t0) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = warp; r < kScCh; r += kScThreads / 32) {
-        const int t = t0 + lane;
-        cp_async4(&tile[r][lane], src + (row0 + r) * (size_t)L + min(t, L - 1), t < L);
-    }
-}
-__device__ __forceinline__ void stage_bc_async(float (*tile)[kScT + 1], const float *__restrict__ src, size_t grp, int L,
+// ---- tile layouts (per buffer).  The LSU pipe was the co-bottleneck of the first cp.async version (60 % busy: ten
+// 4-byte shared loads per lane and position), so operands that are consumed together are stored together:
+//   ud[c][t]   = {u, delta}            one 8-byte load per lane and position   (pitch 33 elements: conflict-free rows)
+//   udyr[c][t] = {u, delta, dy, raw}   one 16-byte load (backward)
+//   bn[t][n], cn[t][n] (pitch 20)      one 16-byte load for the lane's 4 states; the warp's 4 state groups read 64
+//                                      contiguous bytes, the 8 channels of the warp share them (broadcast)
+constexpr int kScBcPitch = 20;
+
+__device__ __forceinline__ void stage_bc_async(float (*tile)[kScBcPitch], const float *__restrict__ src, size_t grp, int L,
                                                int t0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int n = warp; n < kScN; n += kScThreads / 32) {
         const int t = t0 + lane;
-        cp_async4(&tile[n][lane], src + (grp * kScN + n) * (size_t)L + min(t, L - 1), t < L);
+        cp_async4(&tile[lane][n], src + (grp * kScN + n) * (size_t)L + min(t, L - 1), t < L);
+    }
+}
+// rows [ch0, ch0+32) x positions [t0, t0+32) of a [rows, L] array into component `comp` of a tile of NC-float elements
+template <int NC>
+__device__ __forceinline__ void stage_rows_async(float *tile, int comp, const float *__restrict__ src, size_t row0, int L,
+                                                 int t0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < kScCh; r += kScThreads / 32) {
+        const int t = t0 + lane;
+        cp_async4(tile + ((size_t)r * (kScT + 1) + lane) * NC + comp, src + (row0 + r) * (size_t)L + min(t, L - 1), t < L);
     }
 }
 
@@ -75,8 +85,8 @@ sscan_fwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
                  const float *__restrict__ Bm, const float *__restrict__ Cm, const float *__restrict__ Dv,
                  const float *__restrict__ bias, float *__restrict__ y, float *__restrict__ ckpt, int KD, int Dg, int L,
                  int n_seg) {
-    __shared__ float s_u[2][kScCh][kScT + 1], s_dl[2][kScCh][kScT + 1];
-    __shared__ float s_b[2][kScN][kScT + 1], s_c[2][kScN][kScT + 1];   // pitch 33: the warp's 4 state groups hit 4 banks
+    __shared__ __align__(16) float2 s_ud[2][kScCh][kScT + 1];
+    __shared__ __align__(16) float s_b[2][kScT][kScBcPitch], s_c[2][kScT][kScBcPitch];
     __shared__ float s_yp[kScThreads][kScT + 1];        // per-lane partial outputs: summed over the 4 lanes when stored
     const int b = blockIdx.y, ch0 = blockIdx.x * kScCh;
     const int c = threadIdx.x >> 2, sg = threadIdx.x & 3, ch = ch0 + c, n0 = sg * kScNs;
@@ -86,12 +96,12 @@ sscan_fwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
     float a2[kScNs], h[kScNs];
 #pragma unroll
     for (int j = 0; j < kScNs; ++j) { a2[j] = __ldg(A + (size_t)ch * kScN + n0 + j) * kLog2e; h[j] = 0.0f; }
-    const float dsk = Dv != nullptr ? __ldg(Dv + ch) : 0.0f;
+    const float dsk = (Dv != nullptr && sg == 0) ? __ldg(Dv + ch) : 0.0f;     // the skip term rides on lane 0's partial
     float *ck = ckpt != nullptr ? ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN + n0 : nullptr;
 
     auto prefetch = [&](int buf, int t0) {
-        stage_rows_async(s_u[buf], u, row0, L, t0);
-        stage_rows_async(s_dl[buf], dt, row0, L, t0);
+        stage_rows_async<2>(&s_ud[buf][0][0].x, 0, u, row0, L, t0);
+        stage_rows_async<2>(&s_ud[buf][0][0].x, 1, dt, row0, L, t0);
         stage_bc_async(s_b[buf], Bm, grp, L, t0);
         stage_bc_async(s_c[buf], Cm, grp, L, t0);
         cp_async_commit();
@@ -103,25 +113,25 @@ sscan_fwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
         __syncthreads();
         // delta = softplus(dt + bias), once per element, in place (zero past L: h is then left unchanged)
         for (int r = warp; r < kScCh; r += kScThreads / 32) {
-            const float v = s_dl[buf][r][lane] + (bias != nullptr ? __ldg(bias + ch0 + r) : 0.0f);
-            s_dl[buf][r][lane] = t0 + lane < L ? softplus20(v) : 0.0f;
+            const float v = s_ud[buf][r][lane].y + (bias != nullptr ? __ldg(bias + ch0 + r) : 0.0f);
+            s_ud[buf][r][lane].y = t0 + lane < L ? softplus20(v) : 0.0f;
         }
         __syncthreads();
-        if (ck != nullptr && t0 % kScSeg == 0)              // state BEFORE position t0
+        if (ck != nullptr)                                  // state BEFORE position t0 (one segment = one tile)
             *reinterpret_cast<float4 *>(ck + (size_t)(t0 / kScSeg) * kScN) = make_float4(h[0], h[1], h[2], h[3]);
-        // a fixed trip count lets the compiler hoist the loads / exps of 8 positions ahead of the only true dependency,
-        // the 4-cycle FFMA chain on h
+        // fixed trip count: the loads / exps of 8 positions are hoisted ahead of the only true dependency, the 4-cycle
+        // FFMA chain on h
 #pragma unroll 8
         for (int t = 0; t < kScT; ++t) {
-            const float ut = s_u[buf][c][t], dl = s_dl[buf][c][t];
-            const float du = dl * ut;
-            float acc = sg == 0 ? dsk * ut : 0.0f;
-#pragma unroll
-            for (int j = 0; j < kScNs; ++j) {
-                h[j] = fmaf(ex2(dl * a2[j]), h[j], du * s_b[buf][n0 + j][t]);
-                acc = fmaf(s_c[buf][n0 + j][t], h[j], acc);
-            }
-            s_yp[threadIdx.x][t] = acc;
+            const float2 ud = s_ud[buf][c][t];
+            const float4 b4 = *reinterpret_cast<const float4 *>(&s_b[buf][t][n0]);
+            const float4 c4 = *reinterpret_cast<const float4 *>(&s_c[buf][t][n0]);
+            const float du = ud.y * ud.x;
+            h[0] = fmaf(ex2(ud.y * a2[0]), h[0], du * b4.x);
+            h[1] = fmaf(ex2(ud.y * a2[1]), h[1], du * b4.y);
+            h[2] = fmaf(ex2(ud.y * a2[2]), h[2], du * b4.z);
+            h[3] = fmaf(ex2(ud.y * a2[3]), h[3], du * b4.w);
+            s_yp[threadIdx.x][t] = fmaf(c4.x, h[0], fmaf(c4.y, h[1], fmaf(c4.z, h[2], fmaf(c4.w, h[3], dsk * ud.x))));
         }
         __syncthreads();
         for (int r = warp; r < kScCh; r += kScThreads / 32)
@@ -132,9 +142,8 @@ sscan_fwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
 }
 
 struct ScBwdSmem {
-    float u[2][kScCh][kScT + 1], dl[2][kScCh][kScT + 1], dy[2][kScCh][kScT + 1];   // double-buffered segment tiles
-    float b[2][kScN][kScT + 1], c[2][kScN][kScT + 1];
-    float raw[kScCh][kScT + 1];                                 // dt + bias (softplus' needs it)
+    float4 udyr[2][kScCh][kScT + 1];                            // {u, delta, dy, dt + bias}, double-buffered
+    float b[2][kScT][kScBcPitch], c[2][kScT][kScBcPitch];
     float du[kScCh][kScT + 1], ddt[kScCh][kScT + 1];            // outputs of the segment
     float db[kScN][kScT + 1], dc[kScN][kScT + 1];               // CTA-level dB / dC of the segment
     float sub[kScSeg / kScSub][kScThreads][kScNs];              // states before every 4th position of the segment
@@ -151,7 +160,7 @@ sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
                  float *__restrict__ g_u, float *__restrict__ g_dt, float *__restrict__ g_A, float *__restrict__ g_B,
                  float *__restrict__ g_C, float *__restrict__ g_D, float *__restrict__ g_bias, int KD, int Dg, int L,
                  int n_seg) {
-    extern __shared__ unsigned char sc_raw[];
+    extern __shared__ __align__(16) unsigned char sc_raw[];
     ScBwdSmem &sm = *reinterpret_cast<ScBwdSmem *>(sc_raw);
     const int b = blockIdx.y, ch0 = blockIdx.x * kScCh;
     const int c = threadIdx.x >> 2, sg = threadIdx.x & 3, ch = ch0 + c, n0 = sg * kScNs;
@@ -170,9 +179,10 @@ sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
     const float *ck = ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN + n0;
 
     auto prefetch = [&](int buf, int t0) {
-        stage_rows_async(sm.u[buf], u, row0, L, t0);
-        stage_rows_async(sm.dl[buf], dt, row0, L, t0);
-        stage_rows_async(sm.dy[buf], dy, row0, L, t0);
+        float *base = &sm.udyr[buf][0][0].x;
+        stage_rows_async<4>(base, 0, u, row0, L, t0);
+        stage_rows_async<4>(base, 3, dt, row0, L, t0);
+        stage_rows_async<4>(base, 2, dy, row0, L, t0);
         stage_bc_async(sm.b[buf], Bm, grp, L, t0);
         stage_bc_async(sm.c[buf], Cm, grp, L, t0);
         cp_async_commit();
@@ -184,9 +194,10 @@ sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
         if (seg > 0) { prefetch(buf ^ 1, t0 - kScSeg); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();                                           // (also: the previous segment's outputs were stored)
         for (int r = warp; r < kScCh; r += kScThreads / 32) {
-            const float v = sm.dl[buf][r][lane] + (bias != nullptr ? __ldg(bias + ch0 + r) : 0.0f);
-            sm.raw[r][lane] = v;
-            sm.dl[buf][r][lane] = t0 + lane < L ? softplus20(v) : 0.0f;
+            float4 e = sm.udyr[buf][r][lane];
+            e.w += bias != nullptr ? __ldg(bias + ch0 + r) : 0.0f;
+            e.y = t0 + lane < L ? softplus20(e.w) : 0.0f;
+            sm.udyr[buf][r][lane] = e;
         }
         for (int i = threadIdx.x; i < kScN * (kScT + 1); i += kScThreads) { (&sm.db[0][0])[i] = 0.0f; (&sm.dc[0][0])[i] = 0.0f; }
         __syncthreads();
@@ -198,45 +209,56 @@ sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
             for (int t = 0; t < kScT; ++t) {
                 if ((t & (kScSub - 1)) == 0)
                     *reinterpret_cast<float4 *>(sm.sub[t / kScSub][threadIdx.x]) = make_float4(h[0], h[1], h[2], h[3]);
-                const float dl = sm.dl[buf][c][t];
-                const float du = dl * sm.u[buf][c][t];
-#pragma unroll
-                for (int j = 0; j < kScNs; ++j) h[j] = fmaf(ex2(dl * a2[j]), h[j], du * sm.b[buf][n0 + j][t]);
+                const float4 e = sm.udyr[buf][c][t];
+                const float4 b4 = *reinterpret_cast<const float4 *>(&sm.b[buf][t][n0]);
+                const float du = e.y * e.x;
+                h[0] = fmaf(ex2(e.y * a2[0]), h[0], du * b4.x);
+                h[1] = fmaf(ex2(e.y * a2[1]), h[1], du * b4.y);
+                h[2] = fmaf(ex2(e.y * a2[2]), h[2], du * b4.z);
+                h[3] = fmaf(ex2(e.y * a2[3]), h[3], du * b4.w);
             }
         }
         // ---- pass 2: groups of 4 positions, last to first (each thread reads back only its own sub-checkpoints)
         for (int g0 = kScT - kScSub; g0 >= 0; g0 -= kScSub) {
             float hist[kScSub + 1][kScNs];                       // hist[j] = state before position g0 + j
+            float an[kScSub][kScNs], bq[kScSub][kScNs];          // exp(delta*A) and B of the group, reused by the reverse walk
+            float4 ev[kScSub];
             {
                 const float4 v = *reinterpret_cast<const float4 *>(sm.sub[g0 / kScSub][threadIdx.x]);
                 hist[0][0] = v.x; hist[0][1] = v.y; hist[0][2] = v.z; hist[0][3] = v.w;
             }
 #pragma unroll
             for (int j = 0; j < kScSub; ++j) {
-                const float dl = sm.dl[buf][c][g0 + j];
-                const float du = dl * sm.u[buf][c][g0 + j];
+                ev[j] = sm.udyr[buf][c][g0 + j];
+                const float4 b4 = *reinterpret_cast<const float4 *>(&sm.b[buf][g0 + j][n0]);
+                bq[j][0] = b4.x; bq[j][1] = b4.y; bq[j][2] = b4.z; bq[j][3] = b4.w;
+                const float du = ev[j].y * ev[j].x;
 #pragma unroll
-                for (int q = 0; q < kScNs; ++q)
-                    hist[j + 1][q] = fmaf(ex2(dl * a2[q]), hist[j][q], du * sm.b[buf][n0 + q][g0 + j]);
+                for (int q = 0; q < kScNs; ++q) {
+                    an[j][q] = ex2(ev[j].y * a2[q]);
+                    hist[j + 1][q] = fmaf(an[j][q], hist[j][q], du * bq[j][q]);
+                }
             }
 #pragma unroll
             for (int j = kScSub - 1; j >= 0; --j) {
                 const int t = g0 + j;
-                const float ut = sm.u[buf][c][t], dl = sm.dl[buf][c][t], gy = sm.dy[buf][c][t];
+                const float ut = ev[j].x, dl = ev[j].y, gy = ev[j].z;
+                const float4 c4 = *reinterpret_cast<const float4 *>(&sm.c[buf][t][n0]);
+                const float cq[kScNs] = {c4.x, c4.y, c4.z, c4.w};
                 float d_dl = 0.0f, d_u = 0.0f;
                 float red[2 * kScNs];                            // dB then dC contributions of this lane's 4 states
+                const float dlu = dl * ut;
 #pragma unroll
                 for (int q = 0; q < kScNs; ++q) {
-                    const float an = ex2(dl * a2[q]);
-                    const float bn = sm.b[buf][n0 + q][t];
-                    dh[q] = fmaf(sm.c[buf][n0 + q][t], gy, dh[q]);             // dL/dh_t
+                    dh[q] = fmaf(cq[q], gy, dh[q]);                            // dL/dh_t
                     red[kScNs + q] = gy * hist[j + 1][q];
-                    red[q] = dh[q] * dl * ut;
-                    const float dah = dh[q] * an * hist[j][q];                 // dh * a * h_{t-1}
-                    d_dl = fmaf(dah, a1[q], fmaf(dh[q] * bn, ut, d_dl));
+                    red[q] = dh[q] * dlu;
+                    const float dah = dh[q] * an[j][q] * hist[j][q];           // dh * a * h_{t-1}
+                    const float dhb = dh[q] * bq[j][q];
+                    d_dl = fmaf(dah, a1[q], fmaf(dhb, ut, d_dl));
                     dA[q] = fmaf(dah, dl, dA[q]);
-                    d_u = fmaf(dh[q] * bn, dl, d_u);
-                    dh[q] *= an;                                               // dL/dh_{t-1}
+                    d_u = fmaf(dhb, dl, d_u);
+                    dh[q] *= an[j][q];                                         // dL/dh_{t-1}
                 }
                 // sums over the 16 states of the channel: across its 4 lanes
                 d_dl += __shfl_xor_sync(0xffffffffu, d_dl, 1);
@@ -260,7 +282,7 @@ sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
                     atomicAdd(dst, red[0]);
                 }
                 if (sg == 0) {
-                    const float raw = sm.raw[c][t];
+                    const float raw = ev[j].w;
                     d_u = fmaf(dsk, gy, d_u);
                     dD = fmaf(gy, ut, dD);
                     const float d_raw = raw > 20.0f ? d_dl : d_dl * (1.0f / (1.0f + __expf(-raw)));
