@@ -264,18 +264,19 @@ int tamtr_linear_sum_assignment(const float *C, const int *gt_start_dev, const i
  * `selective_scan_cuda_core` (fwd/bwd) there; that extension is not in the reference tree, so these entry points follow
  * its call signature and the published recurrence (Gu & Dao, "Mamba", 2023):
  *   delta = softplus(dt + bias) (identity above 20); h_t = exp(delta_t*A)*h_{t-1} + delta_t*B_t*u_t; y_t = <C_t,h_t> + D*u_t
- * u, dt, y, dy, g_u, g_dt: f32 [Bn, KD, L]; A, g_A: f32 [KD, N]; Bm, Cm, g_B, g_C: f32 [Bn, KD/Dg, N, L];
+ * u, dt, g_u, g_dt: f32 | bf16 (in_dtype; bf16 needs an even L -- converted on load, the arithmetic is fp32 either way, as
+ * vmamba.py:985-986 forces) [Bn, KD, L]; y, dy: f32 [Bn, KD, L]; A, g_A: f32 [KD, N]; Bm, Cm, g_B, g_C: f32 [Bn, KD/Dg, N, L];
  * D, bias, g_D, g_bias: f32 [KD] (D / bias may be NULL).  N = 16, Dg (channels per scan direction) % 32 == 0.
  * ckpt: f32 [Bn, KD, tamtr_selective_scan_segments(L), N], written by the forward (may be NULL at inference), read by the
  * backward.  g_A, g_B, g_C, g_D, g_bias are zeroed by the call and accumulated (fp32 reductions over batch / channels). */
 int tamtr_selective_scan_segments(int L);
-int tamtr_selective_scan_forward(const float *u, const float *dt, const float *A, const float *Bm, const float *Cm,
-                                 const float *D, const float *bias, float *y, float *ckpt, int Bn, int KD, int Dg, int N,
-                                 int L, void *stream);
-int tamtr_selective_scan_backward(const float *u, const float *dt, const float *A, const float *Bm, const float *Cm,
-                                  const float *D, const float *bias, const float *dy, const float *ckpt, float *g_u,
-                                  float *g_dt, float *g_A, float *g_B, float *g_C, float *g_D, float *g_bias, int Bn, int KD,
-                                  int Dg, int N, int L, void *stream);
+int tamtr_selective_scan_forward(const void *u, const void *dt, int in_dtype, const float *A, const float *Bm,
+                                 const float *Cm, const float *D, const float *bias, float *y, float *ckpt, int Bn, int KD,
+                                 int Dg, int N, int L, void *stream);
+int tamtr_selective_scan_backward(const void *u, const void *dt, int in_dtype, const float *A, const float *Bm,
+                                  const float *Cm, const float *D, const float *bias, const float *dy, const float *ckpt,
+                                  void *g_u, void *g_dt, float *g_A, float *g_B, float *g_C, float *g_D, float *g_bias,
+                                  int Bn, int KD, int Dg, int N, int L, void *stream);
 
 #ifdef __cplusplus
 }

@@ -56,8 +56,8 @@ _SIGNATURES = {
     "tamtr_col_sum": (ctypes.c_int, [_vp, _fp, _i, _i, _i, _vp]),
     "tamtr_linear_sum_assignment": (ctypes.c_int, [_fp, _vp, _vp, _vp, _vp] + [_i] * 6 + [ctypes.c_longlong, _vp]),
     "tamtr_selective_scan_segments": (ctypes.c_int, [_i]),
-    "tamtr_selective_scan_forward": (ctypes.c_int, [_fp] * 9 + [_i] * 5 + [_vp]),
-    "tamtr_selective_scan_backward": (ctypes.c_int, [_fp] * 16 + [_i] * 5 + [_vp]),
+    "tamtr_selective_scan_forward": (ctypes.c_int, [_vp, _vp, _i] + [_fp] * 7 + [_i] * 5 + [_vp]),
+    "tamtr_selective_scan_backward": (ctypes.c_int, [_vp, _vp, _i] + [_fp] * 7 + [_vp, _vp] + [_fp] * 5 + [_i] * 5 + [_vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }
 

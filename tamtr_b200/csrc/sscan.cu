@@ -80,12 +80,40 @@ __device__ __forceinline__ void stage_rows_async(float *tile, int comp, const fl
     }
 }
 
+// bf16 rows: positions in pairs (4-byte cp.async; L even), tile16[32][16] words; lanes 0-15 / 16-31 take two rows at once
+__device__ __forceinline__ void stage_rows16_async(uint32_t (*tile16)[kScT / 2], const __nv_bfloat16 *__restrict__ src,
+                                                   size_t row0, int L, int t0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, l16 = lane & 15;
+    for (int r = warp * 2 + half; r < kScCh; r += 2 * (kScThreads / 32)) {
+        const int t = t0 + 2 * l16;
+        const unsigned d = (unsigned)__cvta_generic_to_shared(&tile16[r][l16]);
+        const __nv_bfloat16 *g = src + (row0 + r) * (size_t)L + min(t, L - 2);
+        const int n = t < L ? 4 : 0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(g), "r"(n) : "memory");
+    }
+}
+__device__ __forceinline__ float bf16_at(const uint32_t (*tile16)[kScT / 2], int r, int t) {
+    const uint32_t w = tile16[r][t >> 1];
+    return __uint_as_float((t & 1) ? (w & 0xffff0000u) : (w << 16));
+}
+template <bool BF16> struct ScIn { using type = float; };
+template <> struct ScIn<true> { using type = __nv_bfloat16; };
+template <bool BF16> __device__ __forceinline__ void sc_store(void *p, size_t i, float v) {
+    if (BF16) reinterpret_cast<__nv_bfloat16 *>(p)[i] = __float2bfloat16_rn(v); else reinterpret_cast<float *>(p)[i] = v;
+}
+
+template <bool BF16>
 __global__ void __launch_bounds__(kScThreads)
-sscan_fwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, const float *__restrict__ A,
+sscan_fwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, const float *__restrict__ A,
                  const float *__restrict__ Bm, const float *__restrict__ Cm, const float *__restrict__ Dv,
                  const float *__restrict__ bias, float *__restrict__ y, float *__restrict__ ckpt, int KD, int Dg, int L,
                  int n_seg) {
-    __shared__ __align__(16) float2 s_ud[2][kScCh][kScT + 1];
+    using TIn = typename ScIn<BF16>::type;
+    const TIn *__restrict__ u = reinterpret_cast<const TIn *>(u_);
+    const TIn *__restrict__ dt = reinterpret_cast<const TIn *>(dt_);
+    __shared__ __align__(16) float2 s_ud[BF16 ? 1 : 2][kScCh][kScT + 1];   // bf16 inputs: filled by the conversion pass only
+    __shared__ uint32_t s_u16[BF16 ? 2 : 1][BF16 ? kScCh : 1][kScT / 2], s_d16[BF16 ? 2 : 1][BF16 ? kScCh : 1][kScT / 2];
     __shared__ __align__(16) float s_b[2][kScT][kScBcPitch], s_c[2][kScT][kScBcPitch];
     __shared__ float s_yp[kScThreads][kScT + 1];        // per-lane partial outputs: summed over the 4 lanes when stored
     const int b = blockIdx.y, ch0 = blockIdx.x * kScCh;
@@ -100,8 +128,13 @@ sscan_fwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
     float *ck = ckpt != nullptr ? ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN + n0 : nullptr;
 
     auto prefetch = [&](int buf, int t0) {
-        stage_rows_async<2>(&s_ud[buf][0][0].x, 0, u, row0, L, t0);
-        stage_rows_async<2>(&s_ud[buf][0][0].x, 1, dt, row0, L, t0);
+        if constexpr (BF16) {
+            stage_rows16_async(s_u16[buf], u, row0, L, t0);
+            stage_rows16_async(s_d16[buf], dt, row0, L, t0);
+        } else {
+            stage_rows_async<2>(&s_ud[BF16 ? 0 : buf][0][0].x, 0, u, row0, L, t0);
+            stage_rows_async<2>(&s_ud[BF16 ? 0 : buf][0][0].x, 1, dt, row0, L, t0);
+        }
         stage_bc_async(s_b[buf], Bm, grp, L, t0);
         stage_bc_async(s_c[buf], Cm, grp, L, t0);
         cp_async_commit();
@@ -113,8 +146,15 @@ sscan_fwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
         __syncthreads();
         // delta = softplus(dt + bias), once per element, in place (zero past L: h is then left unchanged)
         for (int r = warp; r < kScCh; r += kScThreads / 32) {
-            const float v = s_ud[buf][r][lane].y + (bias != nullptr ? __ldg(bias + ch0 + r) : 0.0f);
-            s_ud[buf][r][lane].y = t0 + lane < L ? softplus20(v) : 0.0f;
+            float v;
+            if constexpr (BF16) {
+                v = bf16_at(s_d16[buf], r, lane);
+                s_ud[BF16 ? 0 : buf][r][lane].x = t0 + lane < L ? bf16_at(s_u16[buf], r, lane) : 0.0f;
+            } else {
+                v = s_ud[BF16 ? 0 : buf][r][lane].y;
+            }
+            v += bias != nullptr ? __ldg(bias + ch0 + r) : 0.0f;
+            s_ud[BF16 ? 0 : buf][r][lane].y = t0 + lane < L ? softplus20(v) : 0.0f;
         }
         __syncthreads();
         if (ck != nullptr)                                  // state BEFORE position t0 (one segment = one tile)
@@ -123,7 +163,7 @@ sscan_fwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
         // FFMA chain on h
 #pragma unroll 8
         for (int t = 0; t < kScT; ++t) {
-            const float2 ud = s_ud[buf][c][t];
+            const float2 ud = s_ud[BF16 ? 0 : buf][c][t];
             const float4 b4 = *reinterpret_cast<const float4 *>(&s_b[buf][t][n0]);
             const float4 c4 = *reinterpret_cast<const float4 *>(&s_c[buf][t][n0]);
             const float du = ud.y * ud.x;
@@ -141,27 +181,33 @@ sscan_fwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
     }
 }
 
-struct ScBwdSmem {
+template <bool BF16> struct ScBwdSmem {
     float4 udyr[2][kScCh][kScT + 1];                            // {u, delta, dy, dt + bias}, double-buffered
     float b[2][kScT][kScBcPitch], c[2][kScT][kScBcPitch];
     float du[kScCh][kScT + 1], ddt[kScCh][kScT + 1];            // outputs of the segment
     float db[kScN][kScT + 1], dc[kScN][kScT + 1];               // CTA-level dB / dC of the segment
     float sub[kScSeg / kScSub][kScThreads][kScNs];              // states before every 4th position of the segment
+    // bf16 inputs as they arrive (converted when the tile lands); not allocated for fp32 inputs
+    uint32_t u16[BF16 ? 2 : 1][BF16 ? kScCh : 1][kScT / 2], d16[BF16 ? 2 : 1][BF16 ? kScCh : 1][kScT / 2];
 };
 
 // One segment (= one 32-position tile) at a time, last to first: its tiles are prefetched (cp.async) while the previous
 // one is processed; the states inside the segment are recomputed from the forward's checkpoint (pass 1, keeping the state
 // before every 4th position), then the segment is walked backwards in groups of 4 positions held in registers (pass 2).
 // Positions past L are staged as zeros and contribute nothing, so every segment is walked in full.
+template <bool BF16>
 __global__ void __launch_bounds__(kScThreads)
-sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, const float *__restrict__ A,
+sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, const float *__restrict__ A,
                  const float *__restrict__ Bm, const float *__restrict__ Cm, const float *__restrict__ Dv,
                  const float *__restrict__ bias, const float *__restrict__ dy, const float *__restrict__ ckpt,
-                 float *__restrict__ g_u, float *__restrict__ g_dt, float *__restrict__ g_A, float *__restrict__ g_B,
+                 void *__restrict__ g_u, void *__restrict__ g_dt, float *__restrict__ g_A, float *__restrict__ g_B,
                  float *__restrict__ g_C, float *__restrict__ g_D, float *__restrict__ g_bias, int KD, int Dg, int L,
                  int n_seg) {
+    using TIn = typename ScIn<BF16>::type;
+    const TIn *__restrict__ u = reinterpret_cast<const TIn *>(u_);
+    const TIn *__restrict__ dt = reinterpret_cast<const TIn *>(dt_);
     extern __shared__ __align__(16) unsigned char sc_raw[];
-    ScBwdSmem &sm = *reinterpret_cast<ScBwdSmem *>(sc_raw);
+    ScBwdSmem<BF16> &sm = *reinterpret_cast<ScBwdSmem<BF16> *>(sc_raw);
     const int b = blockIdx.y, ch0 = blockIdx.x * kScCh;
     const int c = threadIdx.x >> 2, sg = threadIdx.x & 3, ch = ch0 + c, n0 = sg * kScNs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -180,8 +226,13 @@ sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
 
     auto prefetch = [&](int buf, int t0) {
         float *base = &sm.udyr[buf][0][0].x;
-        stage_rows_async<4>(base, 0, u, row0, L, t0);
-        stage_rows_async<4>(base, 3, dt, row0, L, t0);
+        if constexpr (BF16) {
+            stage_rows16_async(sm.u16[buf], u, row0, L, t0);
+            stage_rows16_async(sm.d16[buf], dt, row0, L, t0);
+        } else {
+            stage_rows_async<4>(base, 0, u, row0, L, t0);
+            stage_rows_async<4>(base, 3, dt, row0, L, t0);
+        }
         stage_rows_async<4>(base, 2, dy, row0, L, t0);
         stage_bc_async(sm.b[buf], Bm, grp, L, t0);
         stage_bc_async(sm.c[buf], Cm, grp, L, t0);
@@ -195,6 +246,10 @@ sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
         __syncthreads();                                           // (also: the previous segment's outputs were stored)
         for (int r = warp; r < kScCh; r += kScThreads / 32) {
             float4 e = sm.udyr[buf][r][lane];
+            if constexpr (BF16) {
+                e.x = t0 + lane < L ? bf16_at(sm.u16[buf], r, lane) : 0.0f;
+                e.w = bf16_at(sm.d16[buf], r, lane);
+            }
             e.w += bias != nullptr ? __ldg(bias + ch0 + r) : 0.0f;
             e.y = t0 + lane < L ? softplus20(e.w) : 0.0f;
             sm.udyr[buf][r][lane] = e;
@@ -295,8 +350,8 @@ sscan_bwd_kernel(const float *__restrict__ u, const float *__restrict__ dt, cons
         __syncthreads();
         for (int r = warp; r < kScCh; r += kScThreads / 32) {
             if (t0 + lane < L) {
-                g_u[(row0 + r) * (size_t)L + t0 + lane] = sm.du[r][lane];
-                g_dt[(row0 + r) * (size_t)L + t0 + lane] = sm.ddt[r][lane];
+                sc_store<BF16>(g_u, (row0 + r) * (size_t)L + t0 + lane, sm.du[r][lane]);
+                sc_store<BF16>(g_dt, (row0 + r) * (size_t)L + t0 + lane, sm.ddt[r][lane]);
             }
         }
         for (int n = warp; n < kScN; n += kScThreads / 32) {
@@ -330,31 +385,47 @@ static int sscan_check(int Bn, int KD, int Dg, int N, int L) {
 
 extern "C" int tamtr_selective_scan_segments(int L) { return L > 0 ? (L + kScSeg - 1) / kScSeg : 0; }
 
-extern "C" int tamtr_selective_scan_forward(const float *u, const float *dt, const float *A, const float *Bm,
+static int sscan_check_in(int in_dtype, const void *u, const void *dt, int L) {
+    TAMTR_CHECK_ARG(in_dtype == TAMTR_F32 || in_dtype == TAMTR_BF16, TAMTR_E_UNSUPPORTED, "selective_scan: dtype %d", in_dtype);
+    if (in_dtype == TAMTR_BF16)
+        TAMTR_CHECK_ARG(L % 2 == 0 && (((uintptr_t)u | (uintptr_t)dt) & 3) == 0, TAMTR_E_UNSUPPORTED,
+                        "selective_scan: bf16 inputs need an even L (%d) and 4-byte aligned rows", L);
+    return 0;
+}
+
+extern "C" int tamtr_selective_scan_forward(const void *u, const void *dt, int in_dtype, const float *A, const float *Bm,
                                             const float *Cm, const float *D, const float *bias, float *y, float *ckpt,
                                             int Bn, int KD, int Dg, int N, int L, void *stream) {
     TAMTR_CHECK_ARG(u && dt && A && Bm && Cm && y, TAMTR_E_BADARG, "selective_scan_forward: null pointer");
-    const int rc = sscan_check(Bn, KD, Dg, N, L);
+    int rc = sscan_check(Bn, KD, Dg, N, L);
+    if (rc) return rc;
+    rc = sscan_check_in(in_dtype, u, dt, L);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     {
         KernelTimer timer(K_SSCAN_FWD, st);
-        sscan_fwd_kernel<<<dim3(KD / kScCh, Bn), kScThreads, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, ckpt, KD, Dg, L,
-                                                                tamtr_selective_scan_segments(L));
+        if (in_dtype == TAMTR_BF16)
+            sscan_fwd_kernel<true><<<dim3(KD / kScCh, Bn), kScThreads, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, ckpt, KD, Dg, L,
+                                                                          tamtr_selective_scan_segments(L));
+        else
+            sscan_fwd_kernel<false><<<dim3(KD / kScCh, Bn), kScThreads, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, ckpt, KD, Dg, L,
+                                                                           tamtr_selective_scan_segments(L));
     }
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-extern "C" int tamtr_selective_scan_backward(const float *u, const float *dt, const float *A, const float *Bm,
+extern "C" int tamtr_selective_scan_backward(const void *u, const void *dt, int in_dtype, const float *A, const float *Bm,
                                              const float *Cm, const float *D, const float *bias, const float *dy,
-                                             const float *ckpt, float *g_u, float *g_dt, float *g_A, float *g_B,
+                                             const float *ckpt, void *g_u, void *g_dt, float *g_A, float *g_B,
                                              float *g_C, float *g_D, float *g_bias, int Bn, int KD, int Dg, int N, int L,
                                              void *stream) {
     TAMTR_CHECK_ARG(u && dt && A && Bm && Cm && dy && ckpt && g_u && g_dt && g_A && g_B && g_C, TAMTR_E_BADARG,
                     "selective_scan_backward: null pointer");
-    const int rc = sscan_check(Bn, KD, Dg, N, L);
+    int rc = sscan_check(Bn, KD, Dg, N, L);
+    if (rc) return rc;
+    rc = sscan_check_in(in_dtype, u, dt, L);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t grp_elems = (size_t)Bn * (KD / Dg) * kScN * L;
@@ -367,15 +438,22 @@ extern "C" int tamtr_selective_scan_backward(const float *u, const float *dt, co
     int dev_id = 0;
     TAMTR_CUDA_OK(cudaGetDevice(&dev_id));
     if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
-        TAMTR_CUDA_OK(cudaFuncSetAttribute(sscan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(ScBwdSmem)));
+        TAMTR_CUDA_OK(cudaFuncSetAttribute(sscan_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(ScBwdSmem<false>)));
+        TAMTR_CUDA_OK(cudaFuncSetAttribute(sscan_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(ScBwdSmem<true>)));
         if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
     {
         KernelTimer timer(K_SSCAN_BWD, st);
-        sscan_bwd_kernel<<<dim3(KD / kScCh, Bn), kScThreads, sizeof(ScBwdSmem), st>>>(
-            u, dt, A, Bm, Cm, D, bias, dy, ckpt, g_u, g_dt, g_A, g_B, g_C, g_D, g_bias, KD, Dg, L,
-            tamtr_selective_scan_segments(L));
+        if (in_dtype == TAMTR_BF16)
+            sscan_bwd_kernel<true><<<dim3(KD / kScCh, Bn), kScThreads, sizeof(ScBwdSmem<true>), st>>>(
+                u, dt, A, Bm, Cm, D, bias, dy, ckpt, g_u, g_dt, g_A, g_B, g_C, g_D, g_bias, KD, Dg, L,
+                tamtr_selective_scan_segments(L));
+        else
+            sscan_bwd_kernel<false><<<dim3(KD / kScCh, Bn), kScThreads, sizeof(ScBwdSmem<false>), st>>>(
+                u, dt, A, Bm, Cm, D, bias, dy, ckpt, g_u, g_dt, g_A, g_B, g_C, g_D, g_bias, KD, Dg, L,
+                tamtr_selective_scan_segments(L));
     }
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());

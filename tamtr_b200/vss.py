@@ -26,19 +26,26 @@ __all__ = ("VSSBlock", "SS2D", "Mlp", "DropPath", "selective_scan", "cross_scan"
 class _SelectiveScanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, delta, A, B, C, D, delta_bias):
-        u, delta, A, B, C = (t.contiguous().float() for t in (u, delta, A, B, C))
+        # u / delta may stay bf16 (converted on load inside the kernel: the same values the reference's to_fp32() produces,
+        # vmamba.py:985-986, without two passes over [b, K*D, L]); everything else fp32
+        lowp = (u.dtype == torch.bfloat16 and delta.dtype == torch.bfloat16 and u.shape[-1] % 2 == 0)
+        if lowp:
+            u, delta = u.contiguous(), delta.contiguous()
+        else:
+            u, delta = u.contiguous().float(), delta.contiguous().float()
+        A, B, C = (t.contiguous().float() for t in (A, B, C))
         D = None if D is None else D.contiguous().float()
         delta_bias = None if delta_bias is None else delta_bias.contiguous().float()
         Bn, KD, L = u.shape
         K, N = B.shape[1], A.shape[1]
         need = any(ctx.needs_input_grad)
-        y = torch.empty_like(u)
+        y = torch.empty(u.shape, dtype=torch.float32, device=u.device)
         lib = _lib.lib()
         ckpt = torch.empty(Bn, KD, lib.tamtr_selective_scan_segments(L), N, dtype=torch.float32, device=u.device) \
             if need else None
         with torch.cuda.device(u.device):
             rc = lib.tamtr_selective_scan_forward(
-                u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr(),
+                u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
                 None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(), y.data_ptr(),
                 None if ckpt is None else ckpt.data_ptr(), Bn, KD, KD // K, N, L, _lib.stream_ptr(u.device))
         _lib.check(rc, "selective_scan_forward")
@@ -59,7 +66,7 @@ class _SelectiveScanFn(torch.autograd.Function):
         g_bias = None if delta_bias is None else torch.empty_like(delta_bias)
         with torch.cuda.device(u.device):
             rc = _lib.lib().tamtr_selective_scan_backward(
-                u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr(),
+                u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
                 None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(), dy.data_ptr(),
                 ckpt.data_ptr(), g_u.data_ptr(), g_dt.data_ptr(), g_A.data_ptr(), g_B.data_ptr(), g_C.data_ptr(),
                 None if g_D is None else g_D.data_ptr(), None if g_bias is None else g_bias.data_ptr(), Bn, KD, KD // K, N,
@@ -172,7 +179,7 @@ class SS2D(nn.Module):
         x_dbl = torch.einsum("b k d l, k c d -> b k c l", xs, self.x_proj_weight)
         dts, Bs, Cs = torch.split(x_dbl, [r, n, n], dim=2)
         dts = torch.einsum("b k r l, k d r -> b k d l", dts, self.dt_projs_weight)
-        ys = selective_scan(xs.reshape(b, -1, l).float(), dts.contiguous().view(b, -1, l).float(),
+        ys = selective_scan(xs.reshape(b, -1, l), dts.contiguous().view(b, -1, l),     # fp32 or bf16: converted on load
                             -torch.exp(self.A_logs.float()), Bs.contiguous().float(), Cs.contiguous().float(),
                             self.Ds.float(), self.dt_projs_bias.view(-1).float(), True)
         y = cross_merge(ys.view(b, k, -1, l), h, w)

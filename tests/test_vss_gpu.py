@@ -69,3 +69,28 @@ def test_vss_block_matches_reference(cuda_lib, name):
     torch.manual_seed(0)
     out = blk(x.detach())
     assert out.shape == x.shape and torch.isfinite(out).all()
+
+
+def test_bf16_inputs_are_converted_on_load(cuda_lib):
+    """u / delta in bf16 (what SS2D hands over under autocast): the kernel converts on load, so the result is bit-identical
+    to the reference's order of operations -- cast to fp32 first (vmamba.py:985-986), then scan -- and the input
+    gradients are that path's gradients rounded once to bf16."""
+    from tamtr_b200.vss import selective_scan
+    ins = _scan_inputs(5, 2, 4, 128, 96)
+    u16, d16 = ins[0].bfloat16().cuda(), ins[1].bfloat16().cuda()
+    rest = [t.cuda() for t in ins[2:]]
+    a = [u16.clone().requires_grad_(), d16.clone().requires_grad_()] + [t.clone().requires_grad_() for t in rest]
+    b = [u16.float().requires_grad_(), d16.float().requires_grad_()] + [t.clone().requires_grad_() for t in rest]
+    ya, yb = selective_scan(*a, True), selective_scan(*b, True)
+    assert ya.dtype == torch.float32 and torch.equal(ya, yb)
+    probe = seeding.seeded_tensor(5, "p", ya.shape).cuda()
+    (ya * probe).sum().backward()
+    (yb * probe).sum().backward()
+    assert a[0].grad.dtype == torch.bfloat16
+    assert torch.equal(a[0].grad, b[0].grad.bfloat16()) and torch.equal(a[1].grad, b[1].grad.bfloat16())
+    for x, y in zip(a[2:], b[2:]):
+        assert rel_l2(x.grad, y.grad) < 1e-5                         # fp32 reductions with atomics: order may differ
+    odd = _scan_inputs(6, 1, 4, 128, 81)                             # odd L: rows are not 4-byte aligned -> fp32 path
+    y_odd = selective_scan(odd[0].bfloat16().cuda(), odd[1].bfloat16().cuda(), *[t.cuda() for t in odd[2:]], True)
+    ref = vss_ref.selective_scan(odd[0].bfloat16().float(), odd[1].bfloat16().float(), *odd[2:], True)
+    assert rel_l2(y_odd, ref) < 1e-4
