@@ -89,6 +89,25 @@ int tamtr_msda_backward(const void *grad_out, const void *value, const float *lo
                         const int32_t *level_shapes_host, int value_token_stride, int zero_grad_value,
                         float *tap_weight_sum, void *stream);
 
+/* The same sampler with a different number of points on each level: the reference's "decoupled" cross-attention pair
+ * multi_scale_deformable_attn_pytorch_cls (ultralytics/nn/modules/utils.py:92-140, points 2/4/6 on the three levels) and
+ * multi_scale_deformable_attn_pytorch_box (utils.py:143-191, points 6/4/2), called from MSDeformAttncls / MSDeformAttnbox
+ * (nn/modules/transformer.py:396,494).
+ *   points_host [L] int32, HOST memory: points of level l; samples are ordered level by level, exactly like the
+ *                 reference's torch.split(sampling_grids, points, dim=-2) (utils.py:108,159)
+ *   loc  [B, Lq, H, S, 2] f32, attn [B, Lq, H, S] f32 (the reference's [B,Lq,H,L,P] view with L*P == S), S = sum(points) <= 32
+ * Everything else (value layout, token stride, index-math contract, gradients) as in tamtr_msda_forward / _backward. */
+int tamtr_msda_forward_ragged(const void *value, const float *loc, const float *attn, void *out, int dtype,
+                              int B, int Lv, int H, int Dh, int Lq, int L, const int32_t *points_host,
+                              const int32_t *level_shapes_host, int value_token_stride, void *stream);
+int tamtr_msda_backward_ragged(const void *grad_out, const void *value, const float *loc, const float *attn,
+                               void *grad_value, float *grad_loc, float *grad_attn, int dtype,
+                               int B, int Lv, int H, int Dh, int Lq, int L, const int32_t *points_host,
+                               const int32_t *level_shapes_host, int value_token_stride, int zero_grad_value,
+                               float *tap_weight_sum, void *stream);
+int tamtr_msda_corners_ragged(const float *loc, int32_t *x0, int32_t *y0, uint8_t *inb, int B, int Lq, int H, int L,
+                              const int32_t *points_host, const int32_t *level_shapes_host, void *stream);
+
 /* Parity export of the index math alone (the "bit-exact sampling-location indexing" object):
  *   x0, y0 [B,Lq,H,L,P] int32 = floor(ix), floor(iy);  inb [B,Lq,H,L,P,4] uint8 = in-bounds flags (nw,ne,sw,se).
  * Runs the same __device__ function the two kernels above use. */
@@ -277,6 +296,15 @@ int tamtr_selective_scan_backward(const void *u, const void *dt, int in_dtype, c
                                   const float *Cm, const float *D, const float *bias, const float *dy, const float *ckpt,
                                   void *g_u, void *g_dt, float *g_A, float *g_B, float *g_C, float *g_D, float *g_bias,
                                   int Bn, int KD, int Dg, int N, int L, void *stream);
+
+/* The four scan orders of SS2D (ultralytics/nn/extra_modules/VManba/csms6s.py:4-47), one pass each way:
+ *   tamtr_cross_scan : x [Bn, D, H, W] -> xs [Bn, 4, D, H*W]  (row-major, column-major, both reversed)   = CrossScan.forward
+ *                                                                                                       = CrossMerge.backward
+ *   tamtr_cross_merge: ys [Bn, 4, D, H*W] -> y [Bn, D, H*W] = (ys0 + flip(ys2)) + transpose(ys1 + flip(ys3))
+ *                                                                              = CrossMerge.forward = CrossScan.backward
+ * f32 | bf16 (same dtype in and out; bf16 sums are rounded where the reference's tensor adds round). */
+int tamtr_cross_scan(const void *x, void *xs, int dtype, int Bn, int D, int H, int W, void *stream);
+int tamtr_cross_merge(const void *ys, void *y, int dtype, int Bn, int D, int H, int W, void *stream);
 
 #ifdef __cplusplus
 }

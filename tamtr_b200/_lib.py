@@ -32,6 +32,10 @@ _SIGNATURES = {
     "tamtr_msda_forward": (ctypes.c_int, [_vp, _fp, _fp, _vp, _i] + [_i] * 7 + [_vp, _i, _vp]),
     "tamtr_msda_backward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _i] + [_i] * 7 + [_vp, _i, _i, _fp, _vp]),
     "tamtr_msda_corners": (ctypes.c_int, [_fp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp]),
+    "tamtr_msda_forward_ragged": (ctypes.c_int, [_vp, _fp, _fp, _vp, _i] + [_i] * 6 + [_vp, _vp, _i, _vp]),
+    "tamtr_msda_backward_ragged": (ctypes.c_int, [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _i] + [_i] * 6
+                                   + [_vp, _vp, _i, _i, _fp, _vp]),
+    "tamtr_msda_corners_ragged": (ctypes.c_int, [_fp, _vp, _vp, _vp] + [_i] * 4 + [_vp, _vp, _vp]),
     "tamtr_locw_forward": (ctypes.c_int, [_fp] * 5 + [_i] * 6 + [_vp, _vp]),
     "tamtr_locw_backward": (ctypes.c_int, [_fp] * 8 + [_i] * 6 + [_vp, _vp]),
     "tamtr_box_refine_forward": (ctypes.c_int, [_fp, _fp, _fp, _i, ctypes.c_float, _vp]),
@@ -58,6 +62,8 @@ _SIGNATURES = {
     "tamtr_selective_scan_segments": (ctypes.c_int, [_i]),
     "tamtr_selective_scan_forward": (ctypes.c_int, [_vp, _vp, _i] + [_fp] * 7 + [_i] * 5 + [_vp]),
     "tamtr_selective_scan_backward": (ctypes.c_int, [_vp, _vp, _i] + [_fp] * 7 + [_vp, _vp] + [_fp] * 5 + [_i] * 5 + [_vp]),
+    "tamtr_cross_scan": (ctypes.c_int, [_vp, _vp] + [_i] * 5 + [_vp]),
+    "tamtr_cross_merge": (ctypes.c_int, [_vp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }
 

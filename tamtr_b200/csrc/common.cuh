@@ -49,17 +49,29 @@ constexpr int kMaxSamples = 32;  // L*P
 // Pyramid geometry, passed by value (lives in the kernel-parameter constant bank).
 struct Levels {
     int n;                  // L
-    int P;                  // points per level
+    int P;                  // points per level (0 when the levels have different point counts)
+    int S;                  // samples per (query, head) = sum of the points of all levels
     int h[kMaxLevels];      // H_l
     int w[kMaxLevels];      // W_l
     int start[kMaxLevels];  // first token of level l
     unsigned char level_of[kMaxSamples];  // sample s = l*P + p -> l (saves an integer division per tap)
 };
 
-inline int fill_levels(Levels &lv, int L, int P, const int32_t *shapes_host, int expect_Lv) {
-    if (L < 1 || L > kMaxLevels || P < 1 || L * P > kMaxSamples) return TAMTR_E_UNSUPPORTED;
+// points_host == nullptr: P points on every level (sample s = l*P + p); otherwise points_host[l] points on level l,
+// samples ordered level by level (the torch.split(..., [2, 4, 6], dim=-2) of utils.py:108 / [6, 4, 2] of utils.py:159).
+inline int fill_levels(Levels &lv, int L, int P, const int32_t *shapes_host, int expect_Lv,
+                       const int32_t *points_host = nullptr) {
+    if (L < 1 || L > kMaxLevels) return TAMTR_E_UNSUPPORTED;
+    int S = 0;
+    for (int l = 0; l < L; ++l) {
+        const int pl = points_host ? points_host[l] : P;
+        if (pl < 1) return TAMTR_E_BADARG;
+        S += pl;
+        if (S > kMaxSamples) return TAMTR_E_UNSUPPORTED;
+    }
     lv.n = L;
-    lv.P = P;
+    lv.P = points_host ? 0 : P;
+    lv.S = S;
     long s = 0;
     for (int l = 0; l < kMaxLevels; ++l) {
         if (l < L) {
@@ -74,7 +86,9 @@ inline int fill_levels(Levels &lv, int L, int P, const int32_t *shapes_host, int
         }
     }
     if (expect_Lv >= 0 && s != expect_Lv) return TAMTR_E_BADARG;
-    for (int i = 0; i < kMaxSamples; ++i) lv.level_of[i] = (unsigned char)(i < L * P ? i / P : 0);
+    for (int i = 0; i < kMaxSamples; ++i) lv.level_of[i] = 0;
+    for (int l = 0, i = 0; l < L; ++l)
+        for (int p = 0; p < (points_host ? points_host[l] : P); ++p) lv.level_of[i++] = (unsigned char)l;
     return 0;
 }
 

@@ -182,7 +182,7 @@ msda_fwd_kernel(const T *__restrict__ value, const float *__restrict__ loc, cons
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int qh = blockIdx.x * kWarpsPerCta + wic;
     if (qh >= total) return;  // warp-uniform; no block-wide barrier below
-    const int S = NS > 0 ? NS : lv.n * lv.P;
+    const int S = NS > 0 ? NS : lv.S;
     const int stride = gridDim.x * kWarpsPerCta;   // persistent warps: item qh, qh + stride, ...
     const int cs = lane / LPC, cg = lane % LPC;
     const int npairs = 4 * S;
@@ -252,7 +252,7 @@ msda_bwd_kernel(const T *__restrict__ grad_out, const T *__restrict__ value, con
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int qh = blockIdx.x * kWarpsPerCta + wic;
     if (qh >= total) return;
-    const int S = NS > 0 ? NS : lv.n * lv.P;
+    const int S = NS > 0 ? NS : lv.S;
     const int stride = gridDim.x * kWarpsPerCta;
     int2 *taps = s_taps[wic];
     float *dots = s_dots[wic];
@@ -353,8 +353,7 @@ __global__ void msda_corners_kernel(const float *__restrict__ loc, int32_t *__re
                                     uint8_t *__restrict__ inb, const Levels lv, long n_samples) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_samples) return;
-    const int S = lv.n * lv.P;
-    const int l = (int)(i % S) / lv.P;
+    const int l = lv.level_of[(int)(i % lv.S)];
     const int Hl = lv.h[l], Wl = lv.w[l];
     const float2 xy = reinterpret_cast<const float2 *>(loc)[i];
     const Tap t = make_tap(xy.x, xy.y, Hl, Wl);
@@ -386,7 +385,7 @@ static int launch_fwd(const void *value, const float *loc, const float *attn, vo
     const long total = (long)B * Lq * H;
     const int grid = persistent_grid(total, 3);
     KernelTimer timer(K_MSDA_FWD, st);
-    if (lv.n * lv.P == 12)
+    if (lv.S == 12)
         msda_fwd_kernel<T, LPC, 12><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)value, loc, attn, (T *)out, lv, Lq,
                                                                          H, Lv, (int)total, tok_stride);
     else
@@ -408,7 +407,7 @@ static int launch_bwd(const void *grad_out, const void *value, const float *loc,
         count_launch();
     }
     KernelTimer timer(K_MSDA_BWD, st);
-    if (lv.n * lv.P == 12)
+    if (lv.S == 12)
         msda_bwd_kernel<T, LPC, 12><<<grid, kWarpsPerCta * 32, 0, st>>>((const T *)grad_out, (const T *)value, loc,
                                                                          attn, (T *)grad_value, grad_loc, grad_attn,
                                                                          tap_weight_sum, lv, Lq, H, Lv, (int)total,
@@ -424,7 +423,7 @@ static int launch_bwd(const void *grad_out, const void *value, const float *loc,
 }
 
 static int check_common(int dtype, int B, int Lv, int H, int Dh, int Lq, int L, int P, const int32_t *shapes,
-                        int &tok_stride, Levels &lv, int &lpc) {
+                        int &tok_stride, Levels &lv, int &lpc, const int32_t *points = nullptr) {
     TAMTR_CHECK_ARG(dtype == TAMTR_F32 || dtype == TAMTR_BF16, TAMTR_E_UNSUPPORTED, "msda: dtype %d not supported",
                     dtype);
     TAMTR_CHECK_ARG(B > 0 && Lv > 0 && H > 0 && Dh > 0 && Lq > 0 && shapes, TAMTR_E_BADARG,
@@ -433,8 +432,8 @@ static int check_common(int dtype, int B, int Lv, int H, int Dh, int Lq, int L, 
     TAMTR_CHECK_ARG(bytes == 32 || bytes == 64 || bytes == 128 || bytes == 256, TAMTR_E_UNSUPPORTED,
                     "msda: head_dim %d (%d bytes) unsupported; need Dh*sizeof in {32,64,128,256}", Dh, bytes);
     lpc = bytes / 16;
-    const int rc = fill_levels(lv, L, P, shapes, Lv);
-    TAMTR_CHECK_ARG(rc == 0, rc, "msda: bad levels (L=%d P=%d, need L<=%d, L*P<=%d, sum(H_l*W_l)==Lv=%d)", L, P,
+    const int rc = fill_levels(lv, L, P, shapes, Lv, points);
+    TAMTR_CHECK_ARG(rc == 0, rc, "msda: bad levels (L=%d P=%d, need L<=%d, samples<=%d, sum(H_l*W_l)==Lv=%d)", L, P,
                     kMaxLevels, kMaxSamples, Lv);
     if (tok_stride <= 0) tok_stride = H * Dh;
     TAMTR_CHECK_ARG(tok_stride >= H * Dh && (tok_stride * (dtype == TAMTR_F32 ? 4 : 2)) % 16 == 0, TAMTR_E_BADARG,
@@ -448,14 +447,14 @@ static int check_common(int dtype, int B, int Lv, int H, int Dh, int Lq, int L, 
 
 using namespace tamtr;
 
-extern "C" int tamtr_msda_forward(const void *value, const float *loc, const float *attn, void *out, int dtype, int B,
-                                  int Lv, int H, int Dh, int Lq, int L, int P, const int32_t *level_shapes_host,
-                                  int value_token_stride, void *stream) {
+static int msda_forward_impl(const void *value, const float *loc, const float *attn, void *out, int dtype, int B, int Lv,
+                             int H, int Dh, int Lq, int L, int P, const int32_t *points_host,
+                             const int32_t *level_shapes_host, int value_token_stride, void *stream) {
     TAMTR_CHECK_ARG(value && loc && attn && out, TAMTR_E_BADARG, "msda_forward: null pointer");
     Levels lv;
     int lpc = 0;
     int ts = value_token_stride;
-    const int rc = check_common(dtype, B, Lv, H, Dh, Lq, L, P, level_shapes_host, ts, lv, lpc);
+    const int rc = check_common(dtype, B, Lv, H, Dh, Lq, L, P, level_shapes_host, ts, lv, lpc, points_host);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
 #define FWD(T, N) return launch_fwd<T, N>(value, loc, attn, out, lv, B, Lq, H, Lv, ts, st)
@@ -471,16 +470,31 @@ extern "C" int tamtr_msda_forward(const void *value, const float *loc, const flo
     return TAMTR_E_UNSUPPORTED;
 }
 
-extern "C" int tamtr_msda_backward(const void *grad_out, const void *value, const float *loc, const float *attn,
-                                   void *grad_value, float *grad_loc, float *grad_attn, int dtype, int B, int Lv, int H,
-                                   int Dh, int Lq, int L, int P, const int32_t *level_shapes_host,
-                                   int value_token_stride, int zero_grad_value, float *tap_weight_sum, void *stream) {
+extern "C" int tamtr_msda_forward(const void *value, const float *loc, const float *attn, void *out, int dtype, int B,
+                                  int Lv, int H, int Dh, int Lq, int L, int P, const int32_t *level_shapes_host,
+                                  int value_token_stride, void *stream) {
+    return msda_forward_impl(value, loc, attn, out, dtype, B, Lv, H, Dh, Lq, L, P, nullptr, level_shapes_host,
+                             value_token_stride, stream);
+}
+
+extern "C" int tamtr_msda_forward_ragged(const void *value, const float *loc, const float *attn, void *out, int dtype,
+                                         int B, int Lv, int H, int Dh, int Lq, int L, const int32_t *points_host,
+                                         const int32_t *level_shapes_host, int value_token_stride, void *stream) {
+    TAMTR_CHECK_ARG(points_host, TAMTR_E_BADARG, "msda_forward_ragged: null points_host");
+    return msda_forward_impl(value, loc, attn, out, dtype, B, Lv, H, Dh, Lq, L, 0, points_host, level_shapes_host,
+                             value_token_stride, stream);
+}
+
+static int msda_backward_impl(const void *grad_out, const void *value, const float *loc, const float *attn,
+                              void *grad_value, float *grad_loc, float *grad_attn, int dtype, int B, int Lv, int H, int Dh,
+                              int Lq, int L, int P, const int32_t *points_host, const int32_t *level_shapes_host,
+                              int value_token_stride, int zero_grad_value, float *tap_weight_sum, void *stream) {
     TAMTR_CHECK_ARG(grad_out && value && loc && attn && grad_value && grad_loc && grad_attn, TAMTR_E_BADARG,
                     "msda_backward: null pointer");
     Levels lv;
     int lpc = 0;
     int ts = value_token_stride;
-    const int rc = check_common(dtype, B, Lv, H, Dh, Lq, L, P, level_shapes_host, ts, lv, lpc);
+    const int rc = check_common(dtype, B, Lv, H, Dh, Lq, L, P, level_shapes_host, ts, lv, lpc, points_host);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
 #define BWD(T, N)                                                                                                  \
@@ -498,16 +512,46 @@ extern "C" int tamtr_msda_backward(const void *grad_out, const void *value, cons
     return TAMTR_E_UNSUPPORTED;
 }
 
-extern "C" int tamtr_msda_corners(const float *loc, int32_t *x0, int32_t *y0, uint8_t *inb, int B, int Lq, int H,
-                                  int L, int P, const int32_t *level_shapes_host, void *stream) {
+extern "C" int tamtr_msda_backward(const void *grad_out, const void *value, const float *loc, const float *attn,
+                                   void *grad_value, float *grad_loc, float *grad_attn, int dtype, int B, int Lv, int H,
+                                   int Dh, int Lq, int L, int P, const int32_t *level_shapes_host,
+                                   int value_token_stride, int zero_grad_value, float *tap_weight_sum, void *stream) {
+    return msda_backward_impl(grad_out, value, loc, attn, grad_value, grad_loc, grad_attn, dtype, B, Lv, H, Dh, Lq, L, P,
+                              nullptr, level_shapes_host, value_token_stride, zero_grad_value, tap_weight_sum, stream);
+}
+
+extern "C" int tamtr_msda_backward_ragged(const void *grad_out, const void *value, const float *loc, const float *attn,
+                                          void *grad_value, float *grad_loc, float *grad_attn, int dtype, int B, int Lv,
+                                          int H, int Dh, int Lq, int L, const int32_t *points_host,
+                                          const int32_t *level_shapes_host, int value_token_stride, int zero_grad_value,
+                                          float *tap_weight_sum, void *stream) {
+    TAMTR_CHECK_ARG(points_host, TAMTR_E_BADARG, "msda_backward_ragged: null points_host");
+    return msda_backward_impl(grad_out, value, loc, attn, grad_value, grad_loc, grad_attn, dtype, B, Lv, H, Dh, Lq, L, 0,
+                              points_host, level_shapes_host, value_token_stride, zero_grad_value, tap_weight_sum, stream);
+}
+
+static int msda_corners_impl(const float *loc, int32_t *x0, int32_t *y0, uint8_t *inb, int B, int Lq, int H, int L, int P,
+                             const int32_t *points_host, const int32_t *level_shapes_host, void *stream) {
     TAMTR_CHECK_ARG(loc && x0 && y0 && inb && level_shapes_host, TAMTR_E_BADARG, "msda_corners: null pointer");
     TAMTR_CHECK_ARG(B > 0 && Lq > 0 && H > 0, TAMTR_E_BADARG, "msda_corners: non-positive size");
     Levels lv;
-    const int rc = fill_levels(lv, L, P, level_shapes_host, -1);
+    const int rc = fill_levels(lv, L, P, level_shapes_host, -1, points_host);
     TAMTR_CHECK_ARG(rc == 0, rc, "msda_corners: bad levels");
-    const long n = (long)B * Lq * H * L * P;
+    const long n = (long)B * Lq * H * lv.S;
     msda_corners_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(loc, x0, y0, inb, lv, n);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int tamtr_msda_corners(const float *loc, int32_t *x0, int32_t *y0, uint8_t *inb, int B, int Lq, int H,
+                                  int L, int P, const int32_t *level_shapes_host, void *stream) {
+    return msda_corners_impl(loc, x0, y0, inb, B, Lq, H, L, P, nullptr, level_shapes_host, stream);
+}
+
+extern "C" int tamtr_msda_corners_ragged(const float *loc, int32_t *x0, int32_t *y0, uint8_t *inb, int B, int Lq, int H,
+                                         int L, const int32_t *points_host, const int32_t *level_shapes_host,
+                                         void *stream) {
+    TAMTR_CHECK_ARG(points_host, TAMTR_E_BADARG, "msda_corners_ragged: null points_host");
+    return msda_corners_impl(loc, x0, y0, inb, B, Lq, H, L, 0, points_host, level_shapes_host, stream);
 }

@@ -104,25 +104,36 @@ def project_values(feats, w_cat, b_cat, arena, n_layers, n_heads):
 
 
 class _MSDeformAttnFn(torch.autograd.Function):
-    """value [B,Lv,H,Dh] (f32|bf16), loc [B,Lq,H,L,P,2] f32, attn [B,Lq,H,L,P] f32 -> out [B,Lq,H*Dh]."""
+    """value [B,Lv,H,Dh] (f32|bf16), loc [B,Lq,H,L,P,2] f32, attn [B,Lq,H,L,P] f32 -> out [B,Lq,H*Dh].
+    `points` (tuple of per-level point counts, or None): the ragged variants of utils.py:92-191, where loc is
+    [B,Lq,H,sum(points),2] and attn any [B,Lq,H,...] with sum(points) entries per head."""
 
     @staticmethod
-    def forward(ctx, value, loc, attn, shapes, arena):
+    def forward(ctx, value, loc, attn, shapes, arena, points=None):
         _lib.require_cuda(value, loc, attn)
         value, tok_stride = _value_layout(value)
         loc = loc.contiguous().float()
         attn = attn.contiguous().float()
         B, Lv, H, Dh = value.shape
-        _, Lq, _, L, P, _ = loc.shape
         sh, nl = _lib.shapes_array(shapes)
-        if nl != L:
-            raise RuntimeError(f"tamtr_b200: {nl} level shapes given but sampling_locations has {L} levels")
+        Lq = loc.shape[1]
         out = torch.empty(B, Lq, H * Dh, dtype=value.dtype, device=value.device)
-        with _with_device(value):
-            rc = _lib.lib().tamtr_msda_forward(value.data_ptr(), loc.data_ptr(), attn.data_ptr(), out.data_ptr(),
-                                               _lib.dtype_code(value), B, Lv, H, Dh, Lq, L, P, sh, tok_stride,
-                                               _lib.stream_ptr(value.device))
+        if points is None:
+            _, _, _, L, P, _ = loc.shape
+            if nl != L:
+                raise RuntimeError(f"tamtr_b200: {nl} level shapes given but sampling_locations has {L} levels")
+            with _with_device(value):
+                rc = _lib.lib().tamtr_msda_forward(value.data_ptr(), loc.data_ptr(), attn.data_ptr(), out.data_ptr(),
+                                                   _lib.dtype_code(value), B, Lv, H, Dh, Lq, L, P, sh, tok_stride,
+                                                   _lib.stream_ptr(value.device))
+        else:
+            pts = _points_array(points, nl, loc, attn)
+            with _with_device(value):
+                rc = _lib.lib().tamtr_msda_forward_ragged(value.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                                                          out.data_ptr(), _lib.dtype_code(value), B, Lv, H, Dh, Lq, nl,
+                                                          pts, sh, tok_stride, _lib.stream_ptr(value.device))
         _lib.check(rc, "msda_forward")
+        ctx.points = None if points is None else tuple(int(p) for p in points)
         ctx.save_for_backward(value, loc, attn)
         ctx.shapes = [list(map(int, s)) for s in (shapes.tolist() if isinstance(shapes, torch.Tensor) else shapes)]
         ctx.tok_stride = tok_stride
@@ -135,8 +146,8 @@ class _MSDeformAttnFn(torch.autograd.Function):
         value, loc, attn = ctx.saved_tensors
         grad_out = grad_out.contiguous().to(value.dtype)
         B, Lv, H, Dh = value.shape
-        _, Lq, _, L, P, _ = loc.shape
-        sh, _ = _lib.shapes_array(ctx.shapes)
+        Lq = loc.shape[1]
+        sh, nl = _lib.shapes_array(ctx.shapes)
         tok_stride = ctx.tok_stride
         wsum = None
         if ctx.arena is not None:
@@ -165,16 +176,61 @@ class _MSDeformAttnFn(torch.autograd.Function):
             else:
                 raise RuntimeError("tamtr_b200 ms_deform_attn backward does not have a deterministic implementation")
         with _with_device(value):
-            rc = _lib.lib().tamtr_msda_backward(grad_out.data_ptr(), value.data_ptr(), loc.data_ptr(),
-                                                attn.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(),
-                                                grad_attn.data_ptr(), _lib.dtype_code(value), B, Lv, H, Dh, Lq, L, P,
-                                                sh, tok_stride, zero, wsum.data_ptr() if wsum is not None else None,
-                                                _lib.stream_ptr(value.device))
+            if ctx.points is None:
+                L, P = loc.shape[3], loc.shape[4]
+                rc = _lib.lib().tamtr_msda_backward(grad_out.data_ptr(), value.data_ptr(), loc.data_ptr(),
+                                                    attn.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(),
+                                                    grad_attn.data_ptr(), _lib.dtype_code(value), B, Lv, H, Dh, Lq, L, P,
+                                                    sh, tok_stride, zero, wsum.data_ptr() if wsum is not None else None,
+                                                    _lib.stream_ptr(value.device))
+            else:
+                pts = _points_array(ctx.points, nl, loc, attn)
+                rc = _lib.lib().tamtr_msda_backward_ragged(grad_out.data_ptr(), value.data_ptr(), loc.data_ptr(),
+                                                           attn.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(),
+                                                           grad_attn.data_ptr(), _lib.dtype_code(value), B, Lv, H, Dh, Lq,
+                                                           nl, pts, sh, tok_stride, zero,
+                                                           wsum.data_ptr() if wsum is not None else None,
+                                                           _lib.stream_ptr(value.device))
         _lib.check(rc, "msda_backward")
         if wsum is not None:      # value_proj bias gradient of this layer: sum_q wsum[q,h] * grad_out[q,h,:]
             ctx.arena.bias_grad[off % base.shape[-1]] = torch.einsum(
                 "bqh,bqhc->hc", wsum, grad_out.view(B, Lq, H, Dh).float()).reshape(-1)
-        return grad_value, grad_loc, grad_attn, None, None
+        return grad_value, grad_loc, grad_attn, None, None, None
+
+
+def _points_array(points, n_levels, loc, attn):
+    """int32[L] host array of per-level point counts, checked against the tensors' sample counts."""
+    import ctypes
+    pts = [int(p) for p in points]
+    if len(pts) != n_levels:
+        raise RuntimeError(f"tamtr_b200: {len(pts)} point counts given for {n_levels} levels")
+    S = sum(pts)
+    if loc.dim() != 5 or loc.shape[3] != S or loc.shape[4] != 2:
+        raise RuntimeError(f"tamtr_b200: sampling_locations {tuple(loc.shape)} must be [B, Lq, H, {S}, 2]")
+    if attn.shape[:3] != loc.shape[:3] or attn[0, 0, 0].numel() != S:
+        raise RuntimeError(f"tamtr_b200: attention_weights {tuple(attn.shape)} must hold {S} weights per (query, head)")
+    return (ctypes.c_int32 * n_levels)(*pts)
+
+
+def ms_deform_attn_ragged(value, value_spatial_shapes, sampling_locations, attention_weights, points):
+    """The core op with a different number of points on each level: `points[l]` consecutive samples of
+    sampling_locations [B,Lq,H,sum(points),2] belong to level l (the torch.split of utils.py:108 / :159)."""
+    _lib.require_cuda(value, sampling_locations, attention_weights)
+    if value.dtype == torch.float16 or value.dtype == torch.float64:
+        out = _MSDeformAttnFn.apply(value.float(), sampling_locations, attention_weights, value_spatial_shapes, None,
+                                    tuple(points))
+        return out.to(value.dtype)
+    return _MSDeformAttnFn.apply(value, sampling_locations, attention_weights, value_spatial_shapes, None, tuple(points))
+
+
+def ms_deform_attn_cls(value, value_spatial_shapes, sampling_locations, attention_weights):
+    """Drop-in for multi_scale_deformable_attn_pytorch_cls (utils.py:92-140): 2 / 4 / 6 points on the three levels."""
+    return ms_deform_attn_ragged(value, value_spatial_shapes, sampling_locations, attention_weights, (2, 4, 6))
+
+
+def ms_deform_attn_box(value, value_spatial_shapes, sampling_locations, attention_weights):
+    """Drop-in for multi_scale_deformable_attn_pytorch_box (utils.py:143-191): 6 / 4 / 2 points on the three levels."""
+    return ms_deform_attn_ragged(value, value_spatial_shapes, sampling_locations, attention_weights, (6, 4, 2))
 
 
 def ms_deform_attn(value, value_spatial_shapes, sampling_locations, attention_weights, arena=None):

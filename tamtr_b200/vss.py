@@ -84,18 +84,63 @@ def selective_scan(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=Tr
     return _SelectiveScanFn.apply(u, delta, A, B, C, D, delta_bias)
 
 
+def _cross_launch(fn_name, src, out, b, d, h, w):
+    with torch.cuda.device(src.device):
+        rc = getattr(_lib.lib(), fn_name)(src.data_ptr(), out.data_ptr(), _lib.dtype_code(src), b, d, h, w,
+                                          _lib.stream_ptr(src.device))
+    _lib.check(rc, fn_name)
+    return out
+
+
+def _cross_prep(t):
+    t = t.contiguous()
+    return t if t.dtype in (torch.float32, torch.bfloat16) else t.float()
+
+
+class _CrossScanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _cross_prep(x)
+        b, d, h, w = x.shape
+        ctx.hw = (h, w)
+        return _cross_launch("tamtr_cross_scan", x, torch.empty(b, 4, d, h * w, dtype=x.dtype, device=x.device), b, d, h, w)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        g = _cross_prep(g)
+        b, _, d, l = g.shape
+        h, w = ctx.hw
+        return _cross_launch("tamtr_cross_merge", g, torch.empty(b, d, h, w, dtype=g.dtype, device=g.device), b, d, h, w)
+
+
+class _CrossMergeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ys, h, w):
+        ys = _cross_prep(ys)
+        b, _, d, l = ys.shape
+        ctx.hw = (h, w)
+        return _cross_launch("tamtr_cross_merge", ys, torch.empty(b, d, l, dtype=ys.dtype, device=ys.device), b, d, h, w)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        g = _cross_prep(g)
+        b, d, l = g.shape
+        h, w = ctx.hw
+        return _cross_launch("tamtr_cross_scan", g, torch.empty(b, 4, d, l, dtype=g.dtype, device=g.device), b, d, h, w), None, None
+
+
 def cross_scan(x):
-    """[b, d, h, w] -> [b, 4, d, h*w]: row-major, column-major and both reversed (csms6s.py:6-13)."""
-    a = x.flatten(2)
-    c = x.transpose(2, 3).flatten(2)
-    return torch.stack([a, c, a.flip(-1), c.flip(-1)], 1)
+    """[b, d, h, w] -> [b, 4, d, h*w]: row-major, column-major and both reversed (csms6s.py:6-13), one pass."""
+    _lib.require_cuda(x)
+    return _CrossScanFn.apply(x)
 
 
 def cross_merge(ys, h, w):
-    """[b, 4, d, h*w] -> [b, d, h*w] (csms6s.py:27-34)."""
-    b, _, d, l = ys.shape
-    s = ys[:, 0:2] + ys[:, 2:4].flip(-1)
-    return s[:, 0] + s[:, 1].reshape(b, d, w, h).transpose(2, 3).reshape(b, d, l)
+    """[b, 4, d, h*w] -> [b, d, h*w] (csms6s.py:27-34), one pass."""
+    _lib.require_cuda(ys)
+    return _CrossMergeFn.apply(ys, h, w)
 
 
 class DropPath(nn.Module):

@@ -94,3 +94,31 @@ def test_bf16_inputs_are_converted_on_load(cuda_lib):
     y_odd = selective_scan(odd[0].bfloat16().cuda(), odd[1].bfloat16().cuda(), *[t.cuda() for t in odd[2:]], True)
     ref = vss_ref.selective_scan(odd[0].bfloat16().float(), odd[1].bfloat16().float(), *odd[2:], True)
     assert rel_l2(y_odd, ref) < 1e-4
+
+
+@pytest.mark.parametrize("b,d,h,w", [(2, 5, 12, 16), (1, 3, 33, 70), (2, 4, 64, 31), (1, 2, 1, 7)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cross_scan_and_merge_are_exact(cuda_lib, b, d, h, w, dtype):
+    """csrc/crossscan.cu against the reference's flatten / transpose / flip / stack sequence (oracle/vss_ref.cross_scan,
+    cross_merge = csms6s.py:6-13, 27-34): pure data movement and two-term sums in the reference's association, so
+    EXACT in fp32 and in bf16 (sums rounded where the reference's tensor adds round), forward and backward."""
+    from tamtr_b200.vss import cross_merge, cross_scan
+    x = seeding.seeded_tensor(11, "x", (b, d, h, w)).to(dtype)
+    xg = x.cuda().requires_grad_()
+    xr = x.clone().requires_grad_()
+    xs, xs_ref = cross_scan(xg), vss_ref.cross_scan(xr)
+    assert xs.shape == (b, 4, d, h * w) and torch.equal(xs.cpu(), xs_ref)
+    probe = seeding.seeded_tensor(12, "p", xs_ref.shape).to(dtype)
+    xs.backward(probe.cuda())
+    xs_ref.backward(probe)
+    # CrossScan.backward is CrossMerge.forward (csms6s.py:17-24): same association, so exact as well
+    assert torch.equal(xg.grad.cpu(), vss_ref.cross_merge(probe, h, w).view(b, d, h, w))
+    if dtype == torch.float32:
+        assert rel_l2(xg.grad, xr.grad) < 1e-6                        # autograd of the oracle sums in another order
+    ys = seeding.seeded_tensor(13, "ys", (b, 4, d, h * w)).to(dtype)
+    yg = ys.cuda().requires_grad_()
+    y = cross_merge(yg, h, w)
+    assert torch.equal(y.cpu(), vss_ref.cross_merge(ys, h, w))
+    gp = seeding.seeded_tensor(14, "g", (b, d, h * w)).to(dtype)
+    y.backward(gp.cuda())
+    assert torch.equal(yg.grad.cpu(), vss_ref.cross_scan(gp.view(b, d, h, w)))
