@@ -104,6 +104,62 @@ def gen_index_probe(ns):
     _save("msda_index_probe", out)
 
 
+RAGGED_CASES = {
+    # name: (seed, B, Lq, H, Dh, shapes)
+    "tiny_nonsquare": (41, 2, 19, 4, 8, [[9, 13], [5, 7], [3, 4]]),
+    "small_dh32": (42, 2, 50, 8, 32, [[20, 20], [10, 10], [5, 5]]),
+    "small_dh64": (43, 1, 40, 8, 64, [[24, 16], [12, 8], [6, 4]]),
+}
+
+
+def gen_ragged(ns):
+    """multi_scale_deformable_attn_pytorch_cls / _box (utils.py:92-191): 2/4/6 and 6/4/2 points per level."""
+    out = {"source": "ultralytics/nn/modules/utils.py:92-140 (_cls, points 2/4/6) and :143-191 (_box, points 6/4/2), torch "
+                     + torch.__version__ + " CPU fp32", "cases": {}}
+    for kind, points, ref in (("cls", (2, 4, 6), ns.utils.multi_scale_deformable_attn_pytorch_cls),
+                              ("box", (6, 4, 2), ns.utils.multi_scale_deformable_attn_pytorch_box)):
+        for name, (seed, B, Lq, H, Dh, shapes) in RAGGED_CASES.items():
+            value, loc, attn, grad_out = msda.make_ragged_inputs(seed, B, Lq, H, Dh, shapes, points)
+            value.requires_grad_(), loc.requires_grad_(), attn.requires_grad_()
+            o = ref(value, shapes, loc, attn)
+            o.backward(grad_out)
+            case = dict(seed=seed, B=B, Lq=Lq, H=H, Dh=Dh, shapes=shapes, points=points, out=o.detach().clone(),
+                        grad_loc=loc.grad.clone(), grad_attn=attn.grad.clone())
+            if value.numel() <= 60_000:
+                case["grad_value"] = value.grad.clone()
+            else:
+                case["grad_value_subset"] = _subset(value.grad, 8000, seed + 1000)
+                case["grad_value_norm"] = value.grad.double().norm().item()
+            out["cases"][kind + "_" + name] = case
+    # the two attention modules and the decoupled decoder layer that calls them (transformer.py:300-495, 561-658)
+    shapes = [[20, 20], [10, 10], [5, 5]]
+    d, H, B, Lq = 256, 8, 2, 48
+    torch.manual_seed(0)
+    layer = ns.transformer.DecouplingDeformableTransformerDecoderLayer(d, H, 512, 0.0, torch.nn.ReLU(), 3, 4)
+    manifest = seeding.seeded_fill(layer, 44)
+    Lv = sum(h * w for h, w in shapes)
+    embed = seeding.seeded_tensor(45, "embed", (B, Lq, d)).requires_grad_()
+    embed1 = seeding.seeded_tensor(45, "embed1", (B, Lq, d)).requires_grad_()
+    # smooth maps: with white-noise features a sample within rounding distance of a cell edge flips a whole gradient row
+    feats = seeding.seeded_smooth_tokens(45, "feats", B, d, shapes, factor=2).requires_grad_()
+    ref_box = torch.cat([seeding.seeded_uniform(45, "ref_xy", (B, Lq, 2)),
+                         seeding.seeded_uniform(45, "ref_wh", (B, Lq, 2), 0.01, 0.3)], -1)
+    pos = seeding.seeded_tensor(45, "pos", (B, Lq, d))
+    mask = torch.zeros(Lq, Lq, dtype=torch.bool)
+    mask[:16, 16:] = True
+    mask[16:, :16] = True
+    o_cls, o_box = layer(embed, embed1, ref_box, feats, shapes, None, mask, pos)
+    (_probe_loss(o_cls, 46, "p_cls") + _probe_loss(o_box, 46, "p_box")).backward()
+    out["layer"] = dict(manifest=manifest, fill_seed=44, d=d, H=H, B=B, Lq=Lq, d_ffn=512, shapes=shapes,
+                        out_cls=o_cls.detach().clone(), out_box=o_box.detach().clone(),
+                        grad_embed=embed.grad.clone(), grad_embed1=embed1.grad.clone(),
+                        grad_feats_subset=_subset(feats.grad, 8000, 48), grad_feats_norm=feats.grad.double().norm().item(),
+                        # small parameters in full, the big matrices as fixed random subsets
+                        param_grads={k: (v.grad.clone() if v.numel() <= 4096 else _subset(v.grad, 2000, 47))
+                                     for k, v in layer.named_parameters() if v.grad is not None})
+    _save("msda_ragged", out)
+
+
 # ------------------------------------------------------------------------------------------------ modules
 def _probe_loss(out, seed, name):
     return (out * seeding.seeded_tensor(seed, name, out.shape)).sum()
@@ -357,7 +413,7 @@ def F_normalize(t):
 
 
 GENERATORS = {"core": gen_core, "index_probe": gen_index_probe, "msdeform": gen_msdeform, "layer": gen_layer,
-              "contrastive": gen_contrastive, "maxsigmoid": gen_maxsigmoid, "heads": gen_heads}
+              "contrastive": gen_contrastive, "maxsigmoid": gen_maxsigmoid, "heads": gen_heads, "ragged": gen_ragged}
 
 
 def main(argv):

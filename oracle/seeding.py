@@ -65,3 +65,10 @@ def seeded_smooth_map(seed, name, shape, factor=4):
     B, C, H, W = shape
     coarse = torch.randn(B, C, max(2, H // factor), max(2, W // factor), generator=_gen(seed, name))
     return torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=True).contiguous()
+
+
+def seeded_smooth_tokens(seed, name, B, d, shapes, factor=4):
+    """Token tensor [B, sum(h*w), d] whose levels are smooth maps (seeded_smooth_map), flattened row-major and
+    concatenated in pyramid order like head.py:1210-1218."""
+    levels = [seeded_smooth_map(seed, f"{name}{i}", (B, d, int(h), int(w)), factor) for i, (h, w) in enumerate(shapes)]
+    return torch.cat([m.flatten(2).permute(0, 2, 1) for m in levels], 1).contiguous()

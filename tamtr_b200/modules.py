@@ -25,7 +25,8 @@ import torch.nn.functional as F
 
 from . import ops
 
-__all__ = ("MLP", "MSDeformAttn", "DeformableTransformerDecoderLayer", "DeformableTransformerDecoder",
+__all__ = ("MLP", "MSDeformAttn", "MSDeformAttncls", "MSDeformAttnbox", "DeformableTransformerDecoderLayer",
+           "DecouplingDeformableTransformerDecoderLayer", "DeformableTransformerDecoder",
            "TextDeformableTransformerDecoder", "ContrastiveHeadMLP", "MaxSigmoidAttnBlock", "inverse_sigmoid")
 
 
@@ -116,6 +117,48 @@ class MSDeformAttn(nn.Module):
         return ops.linear(out, self.output_proj)
 
 
+def _ragged_attn_forward(attn_mod, points, query, refer_bbox, value, value_shapes, value_mask):
+    """MSDeformAttncls / MSDeformAttnbox forward (transformer.py:347-397, :445-495): the projections, softmax and
+    location math are those of MSDeformAttn on the flat [.., n_levels*n_points, 2] view; only the split of the samples
+    over the levels differs (`points`, utils.py:108 / :159)."""
+    bs, len_q = query.shape[:2]
+    len_v = value.shape[1]
+    assert sum(s[0] * s[1] for s in value_shapes) == len_v
+    n_s = attn_mod.n_levels * attn_mod.n_points
+    if len(value_shapes) != len(points) or n_s != sum(points):
+        raise RuntimeError(f"tamtr_b200: the reference splits {n_s} samples as {list(points)} over {len(points)} levels "
+                           f"(utils.py:108,159); got n_levels={attn_mod.n_levels}, n_points={attn_mod.n_points}, "
+                           f"{len(value_shapes)} value shapes")
+    if refer_bbox.shape[-1] != 4:
+        # the reference's 2-d branch broadcasts a 5-d offset tensor against a 6-d normaliser and cannot run
+        raise ValueError(f"Last dim of reference_points must be 2 or 4, but got {refer_bbox.shape[-1]}.")
+    value = attn_mod.value_proj(value)
+    if value_mask is not None:
+        value = value.masked_fill(value_mask[..., None], float(0))
+    value = value.view(bs, len_v, attn_mod.n_heads, attn_mod.d_model // attn_mod.n_heads)
+    loc, attn = ops.sampling_locations_and_weights(
+        query, refer_bbox, attn_mod.sampling_offsets.weight, attn_mod.sampling_offsets.bias,
+        attn_mod.attention_weights.weight, attn_mod.attention_weights.bias, value_shapes,
+        attn_mod.n_heads, attn_mod.n_levels, attn_mod.n_points)
+    out = ops.ms_deform_attn_ragged(value, value_shapes, loc.view(bs, len_q, attn_mod.n_heads, n_s, 2), attn, points)
+    return ops.linear(out, attn_mod.output_proj)
+
+
+class MSDeformAttncls(MSDeformAttn):
+    """Classification-branch deformable attention of the decoupled decoder layer (transformer.py:300-397):
+    2 / 4 / 6 points on the three pyramid levels, largest map first."""
+
+    def forward(self, query, refer_bbox, value, value_shapes, value_mask=None):
+        return _ragged_attn_forward(self, (2, 4, 6), query, refer_bbox, value, value_shapes, value_mask)
+
+
+class MSDeformAttnbox(MSDeformAttn):
+    """Box-branch deformable attention (transformer.py:400-495): 6 / 4 / 2 points on the three levels."""
+
+    def forward(self, query, refer_bbox, value, value_shapes, value_mask=None):
+        return _ragged_attn_forward(self, (6, 4, 2), query, refer_bbox, value, value_shapes, value_mask)
+
+
 # The forward() methods below are also bound onto the REFERENCE's classes by patch.enable(), so they may only touch
 # attributes the reference's __init__ creates: helpers are module-level functions, not methods.
 def _add_norm(layer, x, y, drop, norm):
@@ -187,6 +230,71 @@ class DeformableTransformerDecoderLayer(nn.Module):
                               padding_mask, projected_value, arena)
         embed = _add_norm(self, embed, tgt, self.dropout2, self.norm2)
         return _ffn(self, embed)
+
+
+def _self_attention(mha, q, k, v, attn_mask):
+    if (v.is_cuda and mha._qkv_same_embed_dim and mha.in_proj_bias is not None and mha.bias_k is None
+            and not mha.add_zero_attn):
+        return ops.self_attention(mha, q, v, attn_mask)
+    return mha(q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1), attn_mask=attn_mask,
+               need_weights=False)[0].transpose(0, 1)
+
+
+class DecouplingDeformableTransformerDecoderLayer(nn.Module):
+    """Decoder layer with separate classification / box streams (transformer.py:561-658): self-attention on the
+    classification stream, MSDeformAttncls on it, MSDeformAttnbox on the box stream, one FFN each."""
+
+    def __init__(self, d_model=256, n_heads=8, d_ffn=1024, dropout=0., act=nn.ReLU(), n_levels=4, n_points=4):
+        super().__init__()
+        self.self_attn1 = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.cross_attn_cls = MSDeformAttncls(d_model, n_levels, n_heads, n_points)
+        self.cross_attn_box = MSDeformAttnbox(d_model, n_levels, n_heads, n_points)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.dropout4 = nn.Dropout(dropout)
+        self.norm4 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.act = act
+        self.dropout5 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout6 = nn.Dropout(dropout)
+        self.norm5 = nn.LayerNorm(d_model)
+        self.linear3 = nn.Linear(d_model, d_ffn)
+        self.dropout7 = nn.Dropout(dropout)
+        self.linear4 = nn.Linear(d_ffn, d_model)
+        self.dropout8 = nn.Dropout(dropout)
+        self.norm6 = nn.LayerNorm(d_model)
+
+    @staticmethod
+    def with_pos_embed(tensor, pos):
+        return tensor if pos is None else tensor + pos
+
+    def forward_ffn1(self, tgt):
+        tgt2 = ops.linear(self.dropout5(self.act(ops.linear(tgt, self.linear1))), self.linear2)
+        return _add_norm(self, tgt, tgt2, self.dropout6, self.norm5)
+
+    def forward_ffn2(self, tgt):
+        tgt2 = ops.linear(self.dropout7(self.act(ops.linear(tgt, self.linear3))), self.linear4)
+        return _add_norm(self, tgt, tgt2, self.dropout8, self.norm6)
+
+    def forward(self, embed, embed1, refer_bbox, feats, shapes, padding_mask=None, attn_mask=None, query_pos=None,
+                dn_meta=None):
+        with_pos = DecouplingDeformableTransformerDecoderLayer.with_pos_embed
+        q = k = with_pos(embed, query_pos)
+        tgt = _self_attention(self.self_attn1, q, k, embed, attn_mask)
+        embed = _add_norm(self, embed, tgt, self.dropout1, self.norm1)
+        tgt = self.cross_attn_cls(with_pos(embed, query_pos), refer_bbox.unsqueeze(2), feats, shapes, padding_mask)
+        embed = _add_norm(self, embed, tgt, self.dropout3, self.norm3)
+        tgt = self.cross_attn_box(with_pos(embed1, query_pos), refer_bbox.unsqueeze(2), feats, shapes, padding_mask)
+        embed1 = _add_norm(self, embed1, tgt, self.dropout4, self.norm4)
+        # forward_ffn1 / forward_ffn2 (transformer.py:609-619), written out so that the patched reference class needs no
+        # other rebinding
+        t2 = ops.linear(self.dropout5(self.act(ops.linear(embed, self.linear1))), self.linear2)
+        out_cls = _add_norm(self, embed, t2, self.dropout6, self.norm5)
+        t2 = ops.linear(self.dropout7(self.act(ops.linear(embed1, self.linear3))), self.linear4)
+        return out_cls, _add_norm(self, embed1, t2, self.dropout8, self.norm6)
 
 
 class _DecoderBase(nn.Module):

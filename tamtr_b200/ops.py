@@ -259,6 +259,26 @@ def ms_deform_attn_corners(sampling_locations, value_spatial_shapes):
     return x0, y0, inb
 
 
+def ms_deform_attn_corners_ragged(sampling_locations, value_spatial_shapes, points):
+    """Index-math export for the ragged variants: (x0, y0) int32 [B,Lq,H,S], in-bounds flags uint8 [B,Lq,H,S,4]."""
+    import ctypes
+    _lib.require_cuda(sampling_locations)
+    loc = sampling_locations.contiguous().float()
+    B, Lq, H, S, _ = loc.shape
+    sh, nl = _lib.shapes_array(value_spatial_shapes)
+    pts = [int(p) for p in points]
+    if len(pts) != nl or sum(pts) != S:
+        raise RuntimeError(f"tamtr_b200: points {pts} do not describe {S} samples on {nl} levels")
+    x0 = torch.empty(B, Lq, H, S, dtype=torch.int32, device=loc.device)
+    y0 = torch.empty_like(x0)
+    inb = torch.empty(B, Lq, H, S, 4, dtype=torch.uint8, device=loc.device)
+    with _with_device(loc):
+        rc = _lib.lib().tamtr_msda_corners_ragged(loc.data_ptr(), x0.data_ptr(), y0.data_ptr(), inb.data_ptr(), B, Lq, H,
+                                                  nl, (ctypes.c_int32 * nl)(*pts), sh, _lib.stream_ptr(loc.device))
+    _lib.check(rc, "msda_corners_ragged")
+    return x0, y0, inb
+
+
 # ------------------------------------------------------------------------------------ offsets / weights projection
 def _proj_gemm(q2, w_cat):
     """[M,C] x [N,C]^T -> fp32 [M,N].  fp32 inputs: fp32 GEMM; 16-bit inputs: tensor-core GEMM with fp32 accumulate

@@ -9,6 +9,8 @@ state_dict keys keep working unchanged.  What is rebound:
   ultralytics.nn.modules.utils.multi_scale_deformable_attn_pytorch        (utils.py:42)       -> ops.ms_deform_attn
   ultralytics.nn.modules.transformer.multi_scale_deformable_attn_pytorch  (name imported at transformer.py:12)
   MSDeformAttn.forward                        (transformer.py:252)  -> fused projection epilogue + sampler
+  multi_scale_deformable_attn_pytorch_cls / _box (utils.py:92,143)  -> ops.ms_deform_attn_cls / _box (ragged sampler)
+  MSDeformAttncls / MSDeformAttnbox .forward  (transformer.py:347,445), DecouplingDeformableTransformerDecoderLayer.forward (:621)
   DeformableTransformerDecoderLayer.forward   (transformer.py:539)  -> same math, need_weights=False self-attention
   ContrastiveHeadMLP.forward                  (block.py:534)        -> fused contrastive head
   MaxSigmoidAttnBlock.forward                 (extra_modules/block.py:208 and its copy in modules/block.py)
@@ -42,6 +44,14 @@ def enable(package="ultralytics"):
     _rebind(U, "multi_scale_deformable_attn_pytorch", ops.ms_deform_attn)
     _rebind(T, "multi_scale_deformable_attn_pytorch", ops.ms_deform_attn)
     _rebind(T.MSDeformAttn, "forward", modules.MSDeformAttn.forward)
+    for name, fn in (("multi_scale_deformable_attn_pytorch_cls", ops.ms_deform_attn_cls),
+                     ("multi_scale_deformable_attn_pytorch_box", ops.ms_deform_attn_box)):
+        for mod in (U, T):
+            if hasattr(mod, name):
+                _rebind(mod, name, fn)
+    for name in ("MSDeformAttncls", "MSDeformAttnbox", "DecouplingDeformableTransformerDecoderLayer"):
+        if hasattr(T, name):
+            _rebind(getattr(T, name), "forward", getattr(modules, name).forward)
     _rebind(T.DeformableTransformerDecoderLayer, "forward", modules.DeformableTransformerDecoderLayer.forward)
     if hasattr(B, "ContrastiveHeadMLP"):
         _rebind(B.ContrastiveHeadMLP, "forward", modules.ContrastiveHeadMLP.forward)

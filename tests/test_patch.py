@@ -70,3 +70,34 @@ def test_mirror_state_dicts_load_into_each_other():
     ref_m.load_state_dict(mine.state_dict(), strict=True)
     # vss=False (the configuration of the head-level fixtures): VSSBlocks.* entries of a checkpoint are skipped
     ManbaWorldDecoder(10, [32, 64, 128], 64, 20, 4, 8, 2, vss=False).load_state_dict(ref_m.state_dict(), strict=True)
+
+
+def test_enable_covers_the_decoupled_branch():
+    """The cls / box samplers, their attention modules and the decoupled decoder layer (utils.py:92-191,
+    transformer.py:300-495, 561-658) are rebound too, restored by disable(), and share state_dict keys with our mirrors."""
+    import tamtr_b200
+    from tamtr_b200 import modules
+    ns = reference_loader.hot_path()
+    T, U = ns.transformer, ns.utils
+    before = (U.multi_scale_deformable_attn_pytorch_cls, T.multi_scale_deformable_attn_pytorch_box,
+              T.MSDeformAttncls.forward, T.DecouplingDeformableTransformerDecoderLayer.forward)
+    layer = T.DecouplingDeformableTransformerDecoderLayer(64, 4, 128, 0.0, torch.nn.ReLU(), 3, 4)
+    ours = modules.DecouplingDeformableTransformerDecoderLayer(64, 4, 128, 0.0, torch.nn.ReLU(), 3, 4)
+    ours.load_state_dict(layer.state_dict(), strict=True)
+    layer.load_state_dict(ours.state_dict(), strict=True)
+    tamtr_b200.enable()
+    try:
+        assert U.multi_scale_deformable_attn_pytorch_cls is tamtr_b200.ops.ms_deform_attn_cls
+        assert T.multi_scale_deformable_attn_pytorch_cls is tamtr_b200.ops.ms_deform_attn_cls
+        assert T.multi_scale_deformable_attn_pytorch_box is tamtr_b200.ops.ms_deform_attn_box
+        assert T.MSDeformAttncls.forward is modules.MSDeformAttncls.forward
+        assert T.MSDeformAttnbox.forward is modules.MSDeformAttnbox.forward
+        x = torch.zeros(1, 5, 64)
+        with pytest.raises(RuntimeError, match="is_cuda|Not implemented on the CPU"):
+            layer(x, x, torch.rand(1, 5, 4), torch.zeros(1, 21, 64), [[4, 4], [2, 2], [1, 1]])
+    finally:
+        tamtr_b200.disable()
+    assert (U.multi_scale_deformable_attn_pytorch_cls, T.multi_scale_deformable_attn_pytorch_box,
+            T.MSDeformAttncls.forward, T.DecouplingDeformableTransformerDecoderLayer.forward) == before
+    o_cls, o_box = layer(x, x, torch.rand(1, 5, 4), torch.zeros(1, 21, 64), [[4, 4], [2, 2], [1, 1]])
+    assert o_cls.shape == o_box.shape == (1, 5, 64)
