@@ -27,8 +27,8 @@ constexpr int kScSg = 4;          // lanes per channel
 constexpr int kScNs = kScN / kScSg;   // states per lane
 constexpr int kScThreads = 128;
 constexpr int kScCh = kScThreads / kScSg;   // 32 channels per CTA
-constexpr int kScT = 32;          // positions per tile
-constexpr int kScSeg = 32;        // positions per checkpoint segment (= one tile)
+constexpr int kScT = 32;          // positions per forward tile
+constexpr int kScSeg = 16;        // positions per checkpoint segment = one backward tile
 constexpr int kScSub = 4;         // positions recomputed into registers at a time (backward)
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -157,12 +157,14 @@ sscan_fwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
             s_ud[BF16 ? 0 : buf][r][lane].y = t0 + lane < L ? softplus20(v) : 0.0f;
         }
         __syncthreads();
-        if (ck != nullptr)                                  // state BEFORE position t0 (one segment = one tile)
-            *reinterpret_cast<float4 *>(ck + (size_t)(t0 / kScSeg) * kScN) = make_float4(h[0], h[1], h[2], h[3]);
-        // fixed trip count: the loads / exps of 8 positions are hoisted ahead of the only true dependency, the 4-cycle
+        // fixed trip counts: the loads / exps of 8 positions are hoisted ahead of the only true dependency, the 4-cycle
         // FFMA chain on h
+#pragma unroll
+        for (int sgm = 0; sgm < kScT / kScSeg; ++sgm) {
+        if (ck != nullptr && t0 + sgm * kScSeg < L)         // state BEFORE the segment's first position
+            *reinterpret_cast<float4 *>(ck + (size_t)(t0 / kScSeg + sgm) * kScN) = make_float4(h[0], h[1], h[2], h[3]);
 #pragma unroll 8
-        for (int t = 0; t < kScT; ++t) {
+        for (int t = sgm * kScSeg; t < (sgm + 1) * kScSeg; ++t) {
             const float2 ud = s_ud[BF16 ? 0 : buf][c][t];
             const float4 b4 = *reinterpret_cast<const float4 *>(&s_b[buf][t][n0]);
             const float4 c4 = *reinterpret_cast<const float4 *>(&s_c[buf][t][n0]);
@@ -173,6 +175,7 @@ sscan_fwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
             h[3] = fmaf(ex2(ud.y * a2[3]), h[3], du * b4.w);
             s_yp[threadIdx.x][t] = fmaf(c4.x, h[0], fmaf(c4.y, h[1], fmaf(c4.z, h[2], fmaf(c4.w, h[3], dsk * ud.x))));
         }
+        }
         __syncthreads();
         for (int r = warp; r < kScCh; r += kScThreads / 32)
             if (t0 + lane < L)
@@ -181,22 +184,59 @@ sscan_fwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
     }
 }
 
+// ---- backward tiles: kScSeg (16) positions, so that a CTA needs ~33 KB of shared memory and <= 128 registers per thread
+// and FOUR CTAs fit an SM.  (The first version -- 32-position tiles, 81 KB, 163 registers -- fitted two: the 512 CTAs of
+// the head's largest level ran as two waves of 296 + 216 at IPC 1.2.)  A warp-wide staging instruction covers 32 / T rows.
+template <int T>
+__device__ __forceinline__ void stage_rows_f32_t(float (*tile)[T + 1], const float *__restrict__ src, size_t row0, int L,
+                                                 int t0) {
+    constexpr int RPW = 32 / T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / T, tl = lane % T;
+    for (int r = warp * RPW + sub; r < kScCh; r += RPW * (kScThreads / 32)) {
+        const int t = t0 + tl;
+        cp_async4(&tile[r][tl], src + (row0 + r) * (size_t)L + min(t, L - 1), t < L);
+    }
+}
+template <int T>
+__device__ __forceinline__ void stage_rows_bf16_t(uint32_t (*tile)[T / 2], const __nv_bfloat16 *__restrict__ src, size_t row0,
+                                                  int L, int t0) {
+    constexpr int WPR = T / 2, RPW = 32 / WPR;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / WPR, wl = lane % WPR;
+    for (int r = warp * RPW + sub; r < kScCh; r += RPW * (kScThreads / 32)) {
+        const int t = t0 + 2 * wl;
+        const unsigned d = (unsigned)__cvta_generic_to_shared(&tile[r][wl]);
+        const __nv_bfloat16 *g = src + (row0 + r) * (size_t)L + min(t, L - 2);
+        const int n = t < L ? 4 : 0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(g), "r"(n) : "memory");
+    }
+}
+template <int T>
+__device__ __forceinline__ void stage_bc_t(float (*tile)[kScBcPitch], const float *__restrict__ src, size_t grp, int L, int t0) {
+    constexpr int RPW = 32 / T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / T, tl = lane % T;
+    for (int n = warp * RPW + sub; n < kScN; n += RPW * (kScThreads / 32)) {
+        const int t = t0 + tl;
+        cp_async4(&tile[tl][n], src + (grp * kScN + n) * (size_t)L + min(t, L - 1), t < L);
+    }
+}
+
+constexpr int kBwT = kScSeg;
 template <bool BF16> struct ScBwdSmem {
-    float4 udyr[2][kScCh][kScT + 1];                            // {u, delta, dy, dt + bias}, double-buffered
-    float b[2][kScT][kScBcPitch], c[2][kScT][kScBcPitch];
-    float du[kScCh][kScT + 1], ddt[kScCh][kScT + 1];            // outputs of the segment
-    float db[kScN][kScT + 1], dc[kScN][kScT + 1];               // CTA-level dB / dC of the segment
-    float sub[kScSeg / kScSub][kScThreads][kScNs];              // states before every 4th position of the segment
-    // bf16 inputs as they arrive (converted when the tile lands); not allocated for fp32 inputs
-    uint32_t u16[BF16 ? 2 : 1][BF16 ? kScCh : 1][kScT / 2], d16[BF16 ? 2 : 1][BF16 ? kScCh : 1][kScT / 2];
+    float4 udyr[kScCh][kBwT + 1];                               // {u, delta, dy, dt + bias}; .z / .w become d_u / d_raw
+    float dy[2][kScCh][kBwT + 1];                               // raw tiles as they arrive, double-buffered
+    float b[2][kBwT][kScBcPitch], c[2][kBwT][kScBcPitch];
+    float db[kScN][kBwT + 1], dc[kScN][kBwT + 1];               // CTA-level dB / dC of the segment
+    float sub[kBwT / kScSub][kScThreads][kScNs];                // states before every 4th position of the segment
+    uint32_t u16[BF16 ? 2 : 1][BF16 ? kScCh : 1][kBwT / 2], d16[BF16 ? 2 : 1][BF16 ? kScCh : 1][kBwT / 2];
+    float u32[BF16 ? 1 : 2][BF16 ? 1 : kScCh][kBwT + 1], d32[BF16 ? 1 : 2][BF16 ? 1 : kScCh][kBwT + 1];
 };
 
-// One segment (= one 32-position tile) at a time, last to first: its tiles are prefetched (cp.async) while the previous
-// one is processed; the states inside the segment are recomputed from the forward's checkpoint (pass 1, keeping the state
-// before every 4th position), then the segment is walked backwards in groups of 4 positions held in registers (pass 2).
+// One segment (16 positions) at a time, last to first: its tiles are prefetched (cp.async) while the previous one is
+// processed; the states inside the segment are recomputed from the forward's checkpoint (pass 1, keeping the state before
+// every 4th position), then the segment is walked backwards in groups of 4 positions held in registers (pass 2).
 // Positions past L are staged as zeros and contribute nothing, so every segment is walked in full.
 template <bool BF16>
-__global__ void __launch_bounds__(kScThreads)
+__global__ void __launch_bounds__(kScThreads, 4)
 sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, const float *__restrict__ A,
                  const float *__restrict__ Bm, const float *__restrict__ Cm, const float *__restrict__ Dv,
                  const float *__restrict__ bias, const float *__restrict__ dy, const float *__restrict__ ckpt,
@@ -204,6 +244,7 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
                  float *__restrict__ g_C, float *__restrict__ g_D, float *__restrict__ g_bias, int KD, int Dg, int L,
                  int n_seg) {
     using TIn = typename ScIn<BF16>::type;
+    constexpr int T = kBwT, RPW = 32 / T;
     const TIn *__restrict__ u = reinterpret_cast<const TIn *>(u_);
     const TIn *__restrict__ dt = reinterpret_cast<const TIn *>(dt_);
     extern __shared__ __align__(16) unsigned char sc_raw[];
@@ -211,6 +252,7 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
     const int b = blockIdx.y, ch0 = blockIdx.x * kScCh;
     const int c = threadIdx.x >> 2, sg = threadIdx.x & 3, ch = ch0 + c, n0 = sg * kScNs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int srow = lane / T, tl = lane % T;                      // staging / store role of this lane
     const size_t row0 = (size_t)b * KD + ch0;
     const size_t grp = (size_t)b * (KD / Dg) + ch0 / Dg;
     float a1[kScNs], a2[kScNs], dh[kScNs], dA[kScNs];
@@ -225,17 +267,16 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
     const float *ck = ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN + n0;
 
     auto prefetch = [&](int buf, int t0) {
-        float *base = &sm.udyr[buf][0][0].x;
         if constexpr (BF16) {
-            stage_rows16_async(sm.u16[buf], u, row0, L, t0);
-            stage_rows16_async(sm.d16[buf], dt, row0, L, t0);
+            stage_rows_bf16_t<T>(sm.u16[buf], u, row0, L, t0);
+            stage_rows_bf16_t<T>(sm.d16[buf], dt, row0, L, t0);
         } else {
-            stage_rows_async<4>(base, 0, u, row0, L, t0);
-            stage_rows_async<4>(base, 3, dt, row0, L, t0);
+            stage_rows_f32_t<T>(sm.u32[buf], u, row0, L, t0);
+            stage_rows_f32_t<T>(sm.d32[buf], dt, row0, L, t0);
         }
-        stage_rows_async<4>(base, 2, dy, row0, L, t0);
-        stage_bc_async(sm.b[buf], Bm, grp, L, t0);
-        stage_bc_async(sm.c[buf], Cm, grp, L, t0);
+        stage_rows_f32_t<T>(sm.dy[buf], dy, row0, L, t0);
+        stage_bc_t<T>(sm.b[buf], Bm, grp, L, t0);
+        stage_bc_t<T>(sm.c[buf], Cm, grp, L, t0);
         cp_async_commit();
     };
     prefetch(0, (n_seg - 1) * kScSeg);
@@ -244,27 +285,34 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
         const int t0 = seg * kScSeg;
         if (seg > 0) { prefetch(buf ^ 1, t0 - kScSeg); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();                                           // (also: the previous segment's outputs were stored)
-        for (int r = warp; r < kScCh; r += kScThreads / 32) {
-            float4 e = sm.udyr[buf][r][lane];
+        for (int r = warp * RPW + srow; r < kScCh; r += RPW * (kScThreads / 32)) {
+            float4 e;
             if constexpr (BF16) {
-                e.x = t0 + lane < L ? bf16_at(sm.u16[buf], r, lane) : 0.0f;
-                e.w = bf16_at(sm.d16[buf], r, lane);
+                const uint32_t wu = sm.u16[buf][r][tl >> 1], wd = sm.d16[buf][r][tl >> 1];
+                e.x = __uint_as_float((tl & 1) ? (wu & 0xffff0000u) : (wu << 16));
+                e.w = __uint_as_float((tl & 1) ? (wd & 0xffff0000u) : (wd << 16));
+            } else {
+                e.x = sm.u32[buf][r][tl];
+                e.w = sm.d32[buf][r][tl];
             }
+            const bool live = t0 + tl < L;
+            e.x = live ? e.x : 0.0f;
+            e.z = sm.dy[buf][r][tl];                               // zero-filled past L
             e.w += bias != nullptr ? __ldg(bias + ch0 + r) : 0.0f;
-            e.y = t0 + lane < L ? softplus20(e.w) : 0.0f;
-            sm.udyr[buf][r][lane] = e;
+            e.y = live ? softplus20(e.w) : 0.0f;
+            sm.udyr[r][tl] = e;
         }
-        for (int i = threadIdx.x; i < kScN * (kScT + 1); i += kScThreads) { (&sm.db[0][0])[i] = 0.0f; (&sm.dc[0][0])[i] = 0.0f; }
+        for (int i = threadIdx.x; i < kScN * (T + 1); i += kScThreads) { (&sm.db[0][0])[i] = 0.0f; (&sm.dc[0][0])[i] = 0.0f; }
         __syncthreads();
         // ---- pass 1: recompute the segment forward from its checkpoint
         {
             const float4 v = *reinterpret_cast<const float4 *>(ck + (size_t)seg * kScN);
             float h[kScNs] = {v.x, v.y, v.z, v.w};
-#pragma unroll 8
-            for (int t = 0; t < kScT; ++t) {
+#pragma unroll
+            for (int t = 0; t < T - kScSub; ++t) {                 // (the last group's entry state is all pass 2 needs)
                 if ((t & (kScSub - 1)) == 0)
                     *reinterpret_cast<float4 *>(sm.sub[t / kScSub][threadIdx.x]) = make_float4(h[0], h[1], h[2], h[3]);
-                const float4 e = sm.udyr[buf][c][t];
+                const float4 e = sm.udyr[c][t];
                 const float4 b4 = *reinterpret_cast<const float4 *>(&sm.b[buf][t][n0]);
                 const float du = e.y * e.x;
                 h[0] = fmaf(ex2(e.y * a2[0]), h[0], du * b4.x);
@@ -272,33 +320,37 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
                 h[2] = fmaf(ex2(e.y * a2[2]), h[2], du * b4.z);
                 h[3] = fmaf(ex2(e.y * a2[3]), h[3], du * b4.w);
             }
+            *reinterpret_cast<float4 *>(sm.sub[T / kScSub - 1][threadIdx.x]) = make_float4(h[0], h[1], h[2], h[3]);
         }
         // ---- pass 2: groups of 4 positions, last to first (each thread reads back only its own sub-checkpoints)
-        for (int g0 = kScT - kScSub; g0 >= 0; g0 -= kScSub) {
+        for (int g0 = T - kScSub; g0 >= 0; g0 -= kScSub) {
             float hist[kScSub + 1][kScNs];                       // hist[j] = state before position g0 + j
-            float an[kScSub][kScNs], bq[kScSub][kScNs];          // exp(delta*A) and B of the group, reused by the reverse walk
-            float4 ev[kScSub];
+            float an[kScSub][kScNs];                             // exp(delta*A) of the group, reused by the reverse walk
             {
                 const float4 v = *reinterpret_cast<const float4 *>(sm.sub[g0 / kScSub][threadIdx.x]);
                 hist[0][0] = v.x; hist[0][1] = v.y; hist[0][2] = v.z; hist[0][3] = v.w;
             }
 #pragma unroll
             for (int j = 0; j < kScSub; ++j) {
-                ev[j] = sm.udyr[buf][c][g0 + j];
+                const float4 e = sm.udyr[c][g0 + j];
                 const float4 b4 = *reinterpret_cast<const float4 *>(&sm.b[buf][g0 + j][n0]);
-                bq[j][0] = b4.x; bq[j][1] = b4.y; bq[j][2] = b4.z; bq[j][3] = b4.w;
-                const float du = ev[j].y * ev[j].x;
+                const float bq[kScNs] = {b4.x, b4.y, b4.z, b4.w};
+                const float du = e.y * e.x;
 #pragma unroll
                 for (int q = 0; q < kScNs; ++q) {
-                    an[j][q] = ex2(ev[j].y * a2[q]);
-                    hist[j + 1][q] = fmaf(an[j][q], hist[j][q], du * bq[j][q]);
+                    an[j][q] = ex2(e.y * a2[q]);
+                    hist[j + 1][q] = fmaf(an[j][q], hist[j][q], du * bq[q]);
                 }
             }
 #pragma unroll
             for (int j = kScSub - 1; j >= 0; --j) {
                 const int t = g0 + j;
-                const float ut = ev[j].x, dl = ev[j].y, gy = ev[j].z;
+                // operands are re-read from shared memory (two 16-byte loads) instead of being kept in 32 registers
+                const float4 e = sm.udyr[c][t];
+                const float ut = e.x, dl = e.y, gy = e.z;
+                const float4 b4 = *reinterpret_cast<const float4 *>(&sm.b[buf][t][n0]);
                 const float4 c4 = *reinterpret_cast<const float4 *>(&sm.c[buf][t][n0]);
+                const float bq[kScNs] = {b4.x, b4.y, b4.z, b4.w};
                 const float cq[kScNs] = {c4.x, c4.y, c4.z, c4.w};
                 float d_dl = 0.0f, d_u = 0.0f;
                 float red[2 * kScNs];                            // dB then dC contributions of this lane's 4 states
@@ -309,7 +361,7 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
                     red[kScNs + q] = gy * hist[j + 1][q];
                     red[q] = dh[q] * dlu;
                     const float dah = dh[q] * an[j][q] * hist[j][q];           // dh * a * h_{t-1}
-                    const float dhb = dh[q] * bq[j][q];
+                    const float dhb = dh[q] * bq[q];
                     d_dl = fmaf(dah, a1[q], fmaf(dhb, ut, d_dl));
                     dA[q] = fmaf(dah, dl, dA[q]);
                     d_u = fmaf(dhb, dl, d_u);
@@ -337,27 +389,28 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
                     atomicAdd(dst, red[0]);
                 }
                 if (sg == 0) {
-                    const float raw = ev[j].w;
+                    // (every lane of the channel has read udyr[c][t] before the full-mask shuffles above)
+                    const float raw = e.w;
                     d_u = fmaf(dsk, gy, d_u);
                     dD = fmaf(gy, ut, dD);
                     const float d_raw = raw > 20.0f ? d_dl : d_dl * (1.0f / (1.0f + __expf(-raw)));
                     dbias += d_raw;
-                    sm.du[c][t] = d_u;
-                    sm.ddt[c][t] = d_raw;
+                    *reinterpret_cast<float2 *>(&sm.udyr[c][t].z) = make_float2(d_u, d_raw);
                 }
             }
         }
         __syncthreads();
-        for (int r = warp; r < kScCh; r += kScThreads / 32) {
-            if (t0 + lane < L) {
-                sc_store<BF16>(g_u, (row0 + r) * (size_t)L + t0 + lane, sm.du[r][lane]);
-                sc_store<BF16>(g_dt, (row0 + r) * (size_t)L + t0 + lane, sm.ddt[r][lane]);
+        for (int r = warp * RPW + srow; r < kScCh; r += RPW * (kScThreads / 32)) {
+            if (t0 + tl < L) {
+                const float4 e = sm.udyr[r][tl];
+                sc_store<BF16>(g_u, (row0 + r) * (size_t)L + t0 + tl, e.z);
+                sc_store<BF16>(g_dt, (row0 + r) * (size_t)L + t0 + tl, e.w);
             }
         }
-        for (int n = warp; n < kScN; n += kScThreads / 32) {
-            if (t0 + lane < L) {
-                atomicAdd(g_B + (grp * kScN + n) * (size_t)L + t0 + lane, sm.db[n][lane]);
-                atomicAdd(g_C + (grp * kScN + n) * (size_t)L + t0 + lane, sm.dc[n][lane]);
+        for (int n = warp * RPW + srow; n < kScN; n += RPW * (kScThreads / 32)) {
+            if (t0 + tl < L) {
+                atomicAdd(g_B + (grp * kScN + n) * (size_t)L + t0 + tl, sm.db[n][tl]);
+                atomicAdd(g_C + (grp * kScN + n) * (size_t)L + t0 + tl, sm.dc[n][tl]);
             }
         }
     }
