@@ -221,9 +221,12 @@ class SS2D(nn.Module):
         n = self.A_logs.shape[1]
         l = h * w
         xs = cross_scan(x)
-        x_dbl = torch.einsum("b k d l, k c d -> b k c l", xs, self.x_proj_weight)
+        # the two einsums of vmamba.py:973-976 as broadcast batched GEMMs over (b, k): same contractions, but operands and
+        # results stay in their [b, k, rows, l] layout (einsum permutes xs to [k, b*l, d] and returns a [k, b, l, c]-ordered
+        # view: three extra passes over [b, 4, d, l] per call, forward and backward)
+        x_dbl = torch.matmul(self.x_proj_weight.unsqueeze(0), xs)
         dts, Bs, Cs = torch.split(x_dbl, [r, n, n], dim=2)
-        dts = torch.einsum("b k r l, k d r -> b k d l", dts, self.dt_projs_weight)
+        dts = torch.matmul(self.dt_projs_weight.unsqueeze(0), dts)
         ys = selective_scan(xs.reshape(b, -1, l), dts.contiguous().view(b, -1, l),     # fp32 or bf16: converted on load
                             -torch.exp(self.A_logs.float()), Bs.contiguous().float(), Cs.contiguous().float(),
                             self.Ds.float(), self.dt_projs_bias.view(-1).float(), True)
