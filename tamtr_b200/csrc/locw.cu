@@ -102,7 +102,7 @@ locw_bwd_kernel(const float *__restrict__ grad_loc, const float *__restrict__ gr
             g_off[2 * s + 1] = dy * sy;
             gx += dx;
             gy += dy;
-            if (RD == 4) {
+            if (RD == 4 && grad_ref) {               // `raw` may be null when the reference boxes need no gradient
                 gw = fmaf(dx, (off[2 * s] + boff[2 * s]) * (0.5f * invP), gw);
                 gh = fmaf(dy, (off[2 * s + 1] + boff[2 * s + 1]) * (0.5f * invP), gh);
             }
@@ -155,7 +155,7 @@ extern "C" int tamtr_locw_forward(const float *raw, const float *bias, const flo
 extern "C" int tamtr_locw_backward(const float *grad_loc, const float *grad_attn, const float *attn, const float *raw,
                                    const float *bias, const float *ref, float *grad_raw, float *grad_ref, int M, int H,
                                    int L, int P, int RL, int RD, const int32_t *level_shapes_host, void *stream) {
-    TAMTR_CHECK_ARG(grad_loc && grad_attn && attn && raw && bias && ref && grad_raw, TAMTR_E_BADARG,
+    TAMTR_CHECK_ARG(grad_loc && grad_attn && attn && bias && ref && grad_raw && (raw || !grad_ref), TAMTR_E_BADARG,
                     "locw_backward: null pointer");
     Levels lv;
     const int rc = check_locw(M, H, L, P, RL, RD, level_shapes_host, lv);

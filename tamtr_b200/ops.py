@@ -288,6 +288,9 @@ def _proj_gemm(q2, w_cat):
     return torch.mm(q2, w_cat.t(), out_dtype=torch.float32)
 
 
+FUSED_PROJECTION = True     # bf16 activations: tamtr_locw_tc_forward (set False to force the GEMM + epilogue pair)
+
+
 class _LocWFn(torch.autograd.Function):
     """q2 [M,C], w_cat [3*H*S, C], b_cat [3*H*S], ref [M,RL,RD] -> loc [M,H,L,P,2], attn [M,H,L,P] (fp32).
 
@@ -301,22 +304,34 @@ class _LocWFn(torch.autograd.Function):
             lp = torch.get_autocast_dtype("cuda")
         q2c = q2.contiguous().to(lp)
         w_c = w_cat.to(lp)
-        with torch.autocast("cuda", enabled=False):     # the epilogue kernel needs the fp32 GEMM output as is
-            raw = _proj_gemm(q2c, w_c)
-        assert raw.dtype == torch.float32
         bias = b_cat.contiguous().float()
         ref32 = ref.contiguous().float()
-        M = raw.shape[0]
+        M, C = q2c.shape
         RL, RD = ref32.shape[-2], ref32.shape[-1]
         if RD not in (2, 4):
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but got {RD}.")  # transformer.py:295
-        loc = torch.empty(M, H, L, P, 2, dtype=torch.float32, device=raw.device)
-        attn = torch.empty(M, H, L, P, dtype=torch.float32, device=raw.device)
-        sh, _ = _lib.shapes_array(shapes)
-        with _with_device(raw):
-            rc = _lib.lib().tamtr_locw_forward(raw.data_ptr(), bias.data_ptr(), ref32.data_ptr(), loc.data_ptr(),
-                                               attn.data_ptr(), M, H, L, P, RL, RD, sh, _lib.stream_ptr(raw.device))
-        _lib.check(rc, "locw_forward")
+        dev = q2c.device
+        loc = torch.empty(M, H, L, P, 2, dtype=torch.float32, device=dev)
+        attn = torch.empty(M, H, L, P, dtype=torch.float32, device=dev)
+        lib = _lib.lib()
+        if (FUSED_PROJECTION and lp == torch.bfloat16 and w_c.is_contiguous()
+                and lib.tamtr_locw_tc_supported(M, C, H, L, P, RL, RD)):
+            # Kernel 3 fused: projections + epilogue in one tcgen05 kernel; `raw` only exists if grad_ref will need it
+            raw = torch.empty(M, 3 * H * L * P, dtype=torch.float32, device=dev) if ctx.needs_input_grad[3] else None
+            with _with_device(q2c):
+                rc = lib.tamtr_locw_tc_forward(q2c.data_ptr(), w_c.data_ptr(), bias.data_ptr(), ref32.data_ptr(),
+                                               loc.data_ptr(), attn.data_ptr(), None if raw is None else raw.data_ptr(),
+                                               M, C, H, L, P, RL, RD, _lib.stream_ptr(dev))
+            _lib.check(rc, "locw_tc_forward")
+        else:
+            with torch.autocast("cuda", enabled=False):     # the epilogue kernel needs the fp32 GEMM output as is
+                raw = _proj_gemm(q2c, w_c)
+            assert raw.dtype == torch.float32
+            sh, _ = _lib.shapes_array(shapes)
+            with _with_device(raw):
+                rc = lib.tamtr_locw_forward(raw.data_ptr(), bias.data_ptr(), ref32.data_ptr(), loc.data_ptr(),
+                                            attn.data_ptr(), M, H, L, P, RL, RD, sh, _lib.stream_ptr(dev))
+            _lib.check(rc, "locw_forward")
         ctx.save_for_backward(q2c, w_c, raw, bias, ref32, attn)
         ctx.dims = (M, H, L, P, RL, RD)
         ctx.shapes = [list(map(int, s)) for s in shapes]
@@ -330,15 +345,16 @@ class _LocWFn(torch.autograd.Function):
         M, H, L, P, RL, RD = ctx.dims
         grad_loc = grad_loc.contiguous().float()
         grad_attn = grad_attn.contiguous().float()
-        grad_raw = torch.empty_like(raw)
+        grad_raw = torch.empty(M, 3 * H * L * P, dtype=torch.float32, device=attn.device)
         need_ref = ctx.needs_input_grad[3]
         grad_ref = torch.empty_like(ref32) if need_ref else None
         sh, _ = _lib.shapes_array(ctx.shapes)
-        with _with_device(raw):
+        with _with_device(attn):
             rc = _lib.lib().tamtr_locw_backward(grad_loc.data_ptr(), grad_attn.data_ptr(), attn.data_ptr(),
-                                                raw.data_ptr(), bias.data_ptr(), ref32.data_ptr(),
-                                                grad_raw.data_ptr(), grad_ref.data_ptr() if need_ref else None,
-                                                M, H, L, P, RL, RD, sh, _lib.stream_ptr(raw.device))
+                                                None if raw is None else raw.data_ptr(), bias.data_ptr(),
+                                                ref32.data_ptr(), grad_raw.data_ptr(),
+                                                grad_ref.data_ptr() if need_ref else None,
+                                                M, H, L, P, RL, RD, sh, _lib.stream_ptr(attn.device))
         _lib.check(rc, "locw_backward")
         qd, wd, bd, rd = ctx.in_dtypes
         g_lp = grad_raw.to(w_c.dtype)
