@@ -132,19 +132,21 @@ int tamtr_locw_forward(const float *raw, const float *bias, const float *ref, fl
 /* The same two Linears (ultralytics/nn/modules/transformer.py:278-279) AND the epilogue above as ONE tensor-core kernel
  * for bf16 activations: TMA-staged query / weight tiles, tcgen05.mma into TMEM (fp32 accumulate), the softmax and the
  * location arithmetic applied to each query's TMEM row; the [M, 3*H*L*P] GEMM result never goes through HBM.
- *   query_bf16 [M, C] bf16 row-major; w_cat_bf16 [3*H*L*P, C] bf16 (sampling_offsets.weight ++ attention_weights.weight)
+ *   query_bf16 [M, C] bf16 row-major; w_off_bf16 [2*H*L*P, C], w_attn_bf16 [H*L*P, C] bf16 = sampling_offsets.weight,
+ *   attention_weights.weight as they are (no concatenation); b_off [2*H*L*P], b_attn [H*L*P] f32 or bf16 (bias_dtype)
  *   raw [M, 3*H*L*P] f32 or NULL: the pre-bias GEMM result, only needed by tamtr_locw_backward for grad_ref
- * tamtr_locw_tc_supported() tells whether the problem fits (L*P in {12, 16}, C % 64 == 0, 3*H*L*P <= 512 and
- * divisible into equal chunks <= 256 that are multiples of 16, RL == 1, RD == 4); otherwise callers use a library GEMM
- * + tamtr_locw_forward. */
+ * The H heads of a 128-query tile are split over up to 4 CTAs so that the launch covers the SMs.
+ * tamtr_locw_tc_supported() tells whether the problem fits (L*P in {12, 16}, C % 64 == 0, a head split whose 3*Hc*L*P
+ * columns are <= 512 and divisible into equal chunks <= 256 that are multiples of 16, RL == 1, RD == 4); otherwise
+ * callers use a library GEMM + tamtr_locw_forward. */
 int tamtr_locw_tc_supported(int M, int C, int H, int L, int P, int RL, int RD);
-int tamtr_locw_tc_forward(const void *query_bf16, const void *w_cat_bf16, const float *bias, const float *ref,
-                          float *loc, float *attn, float *raw, int M, int C, int H, int L, int P, int RL, int RD,
-                          void *stream);
+int tamtr_locw_tc_forward(const void *query_bf16, const void *w_off_bf16, const void *w_attn_bf16, const void *b_off,
+                          const void *b_attn, int bias_dtype, const float *ref, float *loc, float *attn, float *raw,
+                          int M, int C, int H, int L, int P, int RL, int RD, void *stream);
 
 /* Backward: grad_raw [M, 3*H*L*P] (gradient w.r.t. the GEMM output, = per-row bias gradient) is fully written;
- * grad_ref [M, RL, RD] may be NULL (reference boxes are detached in training, transformer.py:889); `raw` may be NULL
- * when grad_ref is NULL. */
+ * grad_ref [M, RL, RD] may be NULL (reference boxes are detached in training, transformer.py:889); `raw` and `bias`
+ * may be NULL when grad_ref is NULL. */
 int tamtr_locw_backward(const float *grad_loc, const float *grad_attn, const float *attn, const float *raw,
                         const float *bias, const float *ref, float *grad_raw, float *grad_ref,
                         int M, int H, int L, int P, int RL, int RD, const int32_t *level_shapes_host, void *stream);

@@ -155,7 +155,7 @@ extern "C" int tamtr_locw_forward(const float *raw, const float *bias, const flo
 extern "C" int tamtr_locw_backward(const float *grad_loc, const float *grad_attn, const float *attn, const float *raw,
                                    const float *bias, const float *ref, float *grad_raw, float *grad_ref, int M, int H,
                                    int L, int P, int RL, int RD, const int32_t *level_shapes_host, void *stream) {
-    TAMTR_CHECK_ARG(grad_loc && grad_attn && attn && bias && ref && grad_raw && (raw || !grad_ref), TAMTR_E_BADARG,
+    TAMTR_CHECK_ARG(grad_loc && grad_attn && attn && ref && grad_raw && ((raw && bias) || !grad_ref), TAMTR_E_BADARG,
                     "locw_backward: null pointer");
     Levels lv;
     const int rc = check_locw(M, H, L, P, RL, RD, level_shapes_host, lv);

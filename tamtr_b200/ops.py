@@ -292,38 +292,50 @@ FUSED_PROJECTION = True     # bf16 activations: tamtr_locw_tc_forward (set False
 
 
 class _LocWFn(torch.autograd.Function):
-    """q2 [M,C], w_cat [3*H*S, C], b_cat [3*H*S], ref [M,RL,RD] -> loc [M,H,L,P,2], attn [M,H,L,P] (fp32).
+    """q2 [M,C], sampling_offsets (w_off [2*H*S, C], b_off), attention_weights (w_attn [H*S, C], b_attn), ref [M,RL,RD]
+    -> loc [M,H,L,P,2], attn [M,H,L,P] (fp32).
 
-    forward  = one library GEMM (both Linears of transformer.py:278-279 share their input) + tamtr_locw_forward
-    backward = tamtr_locw_backward + two library GEMMs."""
+    forward  = bf16: ONE tcgen05 kernel, projections + epilogue (tamtr_locw_tc_forward, Kernel 3 fused);
+               otherwise one library GEMM (both Linears of transformer.py:278-279 share their input) + tamtr_locw_forward
+    backward = tamtr_locw_backward + library GEMMs."""
 
     @staticmethod
-    def forward(ctx, q2, w_cat, b_cat, ref, shapes, H, L, P):
+    def forward(ctx, q2, w_off, b_off, w_attn, b_attn, ref, shapes, H, L, P):
         lp = q2.dtype if q2.dtype in (torch.bfloat16, torch.float16) else torch.float32
         if torch.is_autocast_enabled("cuda"):
             lp = torch.get_autocast_dtype("cuda")
         q2c = q2.contiguous().to(lp)
-        w_c = w_cat.to(lp)
-        bias = b_cat.contiguous().float()
         ref32 = ref.contiguous().float()
         M, C = q2c.shape
         RL, RD = ref32.shape[-2], ref32.shape[-1]
         if RD not in (2, 4):
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but got {RD}.")  # transformer.py:295
         dev = q2c.device
+        n_off = w_off.shape[0]
+        need_ref = ctx.needs_input_grad[5]
         loc = torch.empty(M, H, L, P, 2, dtype=torch.float32, device=dev)
         attn = torch.empty(M, H, L, P, dtype=torch.float32, device=dev)
         lib = _lib.lib()
-        if (FUSED_PROJECTION and lp == torch.bfloat16 and w_c.is_contiguous()
-                and lib.tamtr_locw_tc_supported(M, C, H, L, P, RL, RD)):
-            # Kernel 3 fused: projections + epilogue in one tcgen05 kernel; `raw` only exists if grad_ref will need it
-            raw = torch.empty(M, 3 * H * L * P, dtype=torch.float32, device=dev) if ctx.needs_input_grad[3] else None
+        bias = None
+        if FUSED_PROJECTION and lp == torch.bfloat16 and lib.tamtr_locw_tc_supported(M, C, H, L, P, RL, RD):
+            # Kernel 3 fused: the two weight matrices and biases are read where they are (no concatenation); `raw` (and
+            # the concatenated bias) only exist if the reference boxes will need a gradient
+            wo, wa = w_off.to(lp).contiguous(), w_attn.to(lp).contiguous()
+            if b_off.dtype != b_attn.dtype or b_off.dtype not in (torch.float32, torch.bfloat16):
+                b_off, b_attn = b_off.float(), b_attn.float()
+            bo, ba = b_off.contiguous(), b_attn.contiguous()
+            raw = torch.empty(M, 3 * H * L * P, dtype=torch.float32, device=dev) if need_ref else None
             with _with_device(q2c):
-                rc = lib.tamtr_locw_tc_forward(q2c.data_ptr(), w_c.data_ptr(), bias.data_ptr(), ref32.data_ptr(),
-                                               loc.data_ptr(), attn.data_ptr(), None if raw is None else raw.data_ptr(),
-                                               M, C, H, L, P, RL, RD, _lib.stream_ptr(dev))
+                rc = lib.tamtr_locw_tc_forward(q2c.data_ptr(), wo.data_ptr(), wa.data_ptr(), bo.data_ptr(), ba.data_ptr(),
+                                               _lib.dtype_code(bo), ref32.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                                               None if raw is None else raw.data_ptr(), M, C, H, L, P, RL, RD,
+                                               _lib.stream_ptr(dev))
             _lib.check(rc, "locw_tc_forward")
+            if need_ref:
+                bias = torch.cat([bo, ba], 0).float()
         else:
+            w_c = torch.cat([w_off, w_attn], 0).to(lp)
+            bias = torch.cat([b_off, b_attn], 0).float()
             with torch.autocast("cuda", enabled=False):     # the epilogue kernel needs the fp32 GEMM output as is
                 raw = _proj_gemm(q2c, w_c)
             assert raw.dtype == torch.float32
@@ -332,53 +344,61 @@ class _LocWFn(torch.autograd.Function):
                 rc = lib.tamtr_locw_forward(raw.data_ptr(), bias.data_ptr(), ref32.data_ptr(), loc.data_ptr(),
                                             attn.data_ptr(), M, H, L, P, RL, RD, sh, _lib.stream_ptr(dev))
             _lib.check(rc, "locw_forward")
-        ctx.save_for_backward(q2c, w_c, raw, bias, ref32, attn)
+            wo, wa = w_c[:n_off], w_c[n_off:]
+        ctx.save_for_backward(q2c, wo, wa, raw, bias, ref32, attn)
         ctx.dims = (M, H, L, P, RL, RD)
         ctx.shapes = [list(map(int, s)) for s in shapes]
-        ctx.in_dtypes = (q2.dtype, w_cat.dtype, b_cat.dtype, ref.dtype)
+        ctx.in_dtypes = (q2.dtype, w_off.dtype, b_off.dtype, w_attn.dtype, b_attn.dtype, ref.dtype)
         return loc, attn
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loc, grad_attn):
-        q2c, w_c, raw, bias, ref32, attn = ctx.saved_tensors
+        q2c, wo, wa, raw, bias, ref32, attn = ctx.saved_tensors
         M, H, L, P, RL, RD = ctx.dims
         grad_loc = grad_loc.contiguous().float()
         grad_attn = grad_attn.contiguous().float()
         grad_raw = torch.empty(M, 3 * H * L * P, dtype=torch.float32, device=attn.device)
-        need_ref = ctx.needs_input_grad[3]
+        need_ref = ctx.needs_input_grad[5]
         grad_ref = torch.empty_like(ref32) if need_ref else None
         sh, _ = _lib.shapes_array(ctx.shapes)
         with _with_device(attn):
             rc = _lib.lib().tamtr_locw_backward(grad_loc.data_ptr(), grad_attn.data_ptr(), attn.data_ptr(),
-                                                None if raw is None else raw.data_ptr(), bias.data_ptr(),
+                                                None if raw is None else raw.data_ptr(),
+                                                None if bias is None else bias.data_ptr(),
                                                 ref32.data_ptr(), grad_raw.data_ptr(),
                                                 grad_ref.data_ptr() if need_ref else None,
                                                 M, H, L, P, RL, RD, sh, _lib.stream_ptr(attn.device))
         _lib.check(rc, "locw_backward")
-        qd, wd, bd, rd = ctx.in_dtypes
-        g_lp = grad_raw.to(w_c.dtype)
-        grad_q = (g_lp @ w_c).to(qd) if ctx.needs_input_grad[0] else None
-        grad_w = None
-        if ctx.needs_input_grad[1]:
-            grad_w = (g_lp.t() @ q2c if w_c.dtype == torch.float32
-                      else torch.mm(g_lp.t(), q2c, out_dtype=torch.float32)).to(wd)
-        grad_b = col_sum(grad_raw).to(bd) if ctx.needs_input_grad[2] else None
-        return grad_q, grad_w, grad_b, (grad_ref.to(rd) if need_ref else None), None, None, None, None
+        qd, wod, bod, wad, bad, rd = ctx.in_dtypes
+        n_off = wo.shape[0]
+        g_lp = grad_raw.to(wo.dtype)
+        grad_q = None
+        if ctx.needs_input_grad[0]:
+            grad_q = (g_lp[:, :n_off] @ wo).addmm_(g_lp[:, n_off:], wa).to(qd)
+        grad_wo = grad_wa = grad_bo = grad_ba = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[3]:
+            grad_w = (g_lp.t() @ q2c if wo.dtype == torch.float32 else torch.mm(g_lp.t(), q2c, out_dtype=torch.float32))
+            grad_wo, grad_wa = grad_w[:n_off].to(wod), grad_w[n_off:].to(wad)
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[4]:
+            grad_b = col_sum(grad_raw)
+            grad_bo, grad_ba = grad_b[:n_off].to(bod), grad_b[n_off:].to(bad)
+        return (grad_q, grad_wo, grad_bo, grad_wa, grad_ba, (grad_ref.to(rd) if need_ref else None), None, None, None,
+                None)
 
 
 def sampling_locations_and_weights(query, refer_bbox, w_off, b_off, w_attn, b_attn, value_shapes, n_heads, n_levels,
                                    n_points):
-    """transformer.py:278-293 as one GEMM + one fused epilogue kernel.
+    """transformer.py:278-293: bf16 activations -> one tcgen05 kernel (projections + epilogue); otherwise one GEMM + one
+    epilogue kernel.
 
     query [B,Lq,C]; refer_bbox [B,Lq,RL,2|4]; returns loc [B,Lq,H,L,P,2] and attn [B,Lq,H,L,P], both fp32
     (index math and softmax stay fp32 whatever the activation dtype)."""
     _lib.require_cuda(query, refer_bbox)
     B, Lq, C = query.shape
-    w_cat = torch.cat([w_off, w_attn], 0)
-    b_cat = torch.cat([b_off, b_attn], 0)
     ref = refer_bbox.reshape(B * Lq, refer_bbox.shape[-2], refer_bbox.shape[-1])
-    loc, attn = _LocWFn.apply(query.reshape(B * Lq, C), w_cat, b_cat, ref, value_shapes, n_heads, n_levels, n_points)
+    loc, attn = _LocWFn.apply(query.reshape(B * Lq, C), w_off, b_off, w_attn, b_attn, ref, value_shapes, n_heads, n_levels,
+                              n_points)
     return (loc.view(B, Lq, n_heads, n_levels, n_points, 2), attn.view(B, Lq, n_heads, n_levels, n_points))
 
 

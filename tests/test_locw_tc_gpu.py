@@ -34,7 +34,7 @@ def _fp64(q, ref, w_off, b_off, w_att, b_att, H, L, P):
 
 
 @pytest.mark.parametrize("M,C,H,L,P", [(4800, 512, 8, 3, 4), (300, 256, 8, 3, 4), (77, 512, 8, 3, 4), (129, 256, 8, 4, 4),
-                                       (1000, 128, 4, 3, 4)])
+                                       (1000, 128, 4, 3, 4), (200, 512, 16, 4, 4)])
 def test_fused_projection_matches_fp64_and_unfused(cuda_lib, M, C, H, L, P):
     ops = cuda_lib.ops
     assert cuda_lib._lib.lib().tamtr_locw_tc_supported(M, C, H, L, P, 1, 4) == 1
@@ -89,7 +89,7 @@ def test_unsupported_shapes_take_the_unfused_path(cuda_lib):
     assert lib.tamtr_locw_tc_supported(100, 512, 8, 3, 4, 3, 2) == 0     # 2-d reference points per level
     assert lib.tamtr_locw_tc_supported(100, 500, 8, 3, 4, 1, 4) == 0     # C not a multiple of 64
     assert lib.tamtr_locw_tc_supported(100, 512, 8, 3, 3, 1, 4) == 0     # 9 samples
-    assert lib.tamtr_locw_tc_supported(100, 512, 16, 4, 4, 1, 4) == 0    # 768 output columns > TMEM
+    assert lib.tamtr_locw_tc_supported(100, 512, 16, 4, 4, 1, 4) == 1    # 768 columns: the heads are split over CTAs
     ops = cuda_lib.ops
     q, _, w_off, b_off, w_att, b_att = _inputs(9, 50, 512, 8, 3, 4)
     ref2 = seeding.seeded_uniform(9, "ref2", (1, 50, 3, 2))
