@@ -322,6 +322,17 @@ int tamtr_selective_scan_backward(const void *u, const void *dt, int in_dtype, c
 int tamtr_cross_scan(const void *x, void *xs, int dtype, int Bn, int D, int H, int W, void *stream);
 int tamtr_cross_merge(const void *ys, void *y, int dtype, int Bn, int D, int H, int W, void *stream);
 
+/* Depth-wise 3x3 convolution (padding 1, stride 1) + bias + SiLU of SS2D, NCHW, one kernel each way
+ * (ultralytics/nn/extra_modules/VManba/vmamba.py:1026-1027: x = act(conv2d(x)); conv2d = nn.Conv2d(d, d, 3, padding=1,
+ * groups=d), act = SiLU).
+ *   x, y, grad_y, grad_x [Bn, D, H, W] f32 | bf16 (dtype); weight f32 [D, 3, 3]; bias f32 [D] or NULL
+ *   backward: pre-activations are recomputed from x; grad_weight f32 [D, 3, 3] and grad_bias f32 [D] (or NULL) are
+ *   zeroed by the call and accumulated with fp32 atomics. */
+int tamtr_dwconv3x3_silu_forward(const void *x, const float *weight, const float *bias, void *y, int dtype, int Bn, int D,
+                                 int H, int W, void *stream);
+int tamtr_dwconv3x3_silu_backward(const void *grad_y, const void *x, const float *weight, const float *bias, void *grad_x,
+                                  float *grad_weight, float *grad_bias, int dtype, int Bn, int D, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

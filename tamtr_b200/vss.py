@@ -20,7 +20,7 @@ import torch.nn.functional as F
 
 from . import _lib
 
-__all__ = ("VSSBlock", "SS2D", "Mlp", "DropPath", "selective_scan", "cross_scan", "cross_merge")
+__all__ = ("VSSBlock", "SS2D", "Mlp", "DropPath", "selective_scan", "cross_scan", "cross_merge", "dwconv3x3_silu")
 
 
 class _SelectiveScanFn(torch.autograd.Function):
@@ -143,6 +143,54 @@ def cross_merge(ys, h, w):
     return _CrossMergeFn.apply(ys, h, w)
 
 
+class _DwConvSiluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _cross_prep(x)
+        b, d, h, w = x.shape
+        w32 = weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().tamtr_dwconv3x3_silu_forward(x.data_ptr(), w32.data_ptr(), None if b32 is None else b32.data_ptr(),
+                                                         y.data_ptr(), _lib.dtype_code(x), b, d, h, w,
+                                                         _lib.stream_ptr(x.device))
+        _lib.check(rc, "dwconv3x3_silu_forward")
+        ctx.save_for_backward(x, w32, b32)
+        ctx.dtypes = (weight.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, w32, b32 = ctx.saved_tensors
+        g = g.contiguous().to(x.dtype)
+        b, d, h, w = x.shape
+        gx = torch.empty_like(x)
+        gw = torch.empty_like(w32)                               # zeroed by the call
+        gb = None if b32 is None else torch.empty_like(b32)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().tamtr_dwconv3x3_silu_backward(g.data_ptr(), x.data_ptr(), w32.data_ptr(),
+                                                          None if b32 is None else b32.data_ptr(), gx.data_ptr(),
+                                                          gw.data_ptr(), None if gb is None else gb.data_ptr(),
+                                                          _lib.dtype_code(x), b, d, h, w, _lib.stream_ptr(x.device))
+        _lib.check(rc, "dwconv3x3_silu_backward")
+        wd, bd = ctx.dtypes
+        return gx, gw.to(wd), None if gb is None else gb.to(bd)
+
+
+def dwconv3x3_silu(x, conv):
+    """silu(conv(x)) for a depth-wise 3x3 nn.Conv2d with padding 1 (vmamba.py:1026-1027), one kernel each way."""
+    _lib.require_cuda(x)
+    return _DwConvSiluFn.apply(x, conv.weight, conv.bias)
+
+
+def _is_dw3x3(conv, x):
+    return (isinstance(conv, nn.Conv2d) and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == conv.in_channels == conv.out_channels == x.shape[1]
+            and conv.padding_mode == "zeros")
+
+
 class DropPath(nn.Module):
     """Stochastic depth per sample (timm.layers.DropPath, used at vmamba.py:1232)."""
 
@@ -238,7 +286,11 @@ class SS2D(nn.Module):
         x = self.in_proj(x)
         x, z = x.chunk(2, dim=-1)
         z = self.act(z.clone())
-        x = self.act(self.conv2d(x.permute(0, 3, 1, 2).contiguous()))
+        x = x.permute(0, 3, 1, 2).contiguous()
+        if isinstance(self.act, nn.SiLU) and _is_dw3x3(self.conv2d, x):
+            x = dwconv3x3_silu(x, self.conv2d)
+        else:
+            x = self.act(self.conv2d(x))
         y = self.forward_core(x) * z
         return self.dropout(self.out_proj(y))
 

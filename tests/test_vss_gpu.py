@@ -122,3 +122,33 @@ def test_cross_scan_and_merge_are_exact(cuda_lib, b, d, h, w, dtype):
     gp = seeding.seeded_tensor(14, "g", (b, d, h * w)).to(dtype)
     y.backward(gp.cuda())
     assert torch.equal(yg.grad.cpu(), vss_ref.cross_scan(gp.view(b, d, h, w)))
+
+
+@pytest.mark.parametrize("b,d,h,w", [(2, 8, 12, 16), (1, 5, 33, 150), (2, 3, 40, 131), (1, 4, 1, 1)])
+def test_dwconv3x3_silu_matches_library_conv(cuda_lib, b, d, h, w):
+    """csrc/dwconv.cu against silu(conv2d(x)) as SS2D runs it (vmamba.py:1026-1027), evaluated by the library in fp64
+    on the CPU: fp32 <= 1e-5 (forward, dx) / 1e-4 (weight / bias gradients: sums over b*h*w positions); bf16 activations
+    <= 2e-2 against the same reference on bf16-rounded inputs."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from tamtr_b200.vss import dwconv3x3_silu
+    conv = nn.Conv2d(d, d, 3, padding=1, groups=d)
+    with torch.no_grad():
+        conv.weight.copy_(seeding.seeded_tensor(21, "w", conv.weight.shape) * 0.4)
+        conv.bias.copy_(seeding.seeded_tensor(21, "b", conv.bias.shape) * 0.3)
+    x = seeding.seeded_tensor(22, "x", (b, d, h, w))
+    g = seeding.seeded_tensor(23, "g", (b, d, h, w))
+    for dtype, tol, tol_w in ((torch.float32, 1e-5, 1e-4), (torch.bfloat16, 2e-2, 2e-2)):
+        xr = x.to(dtype).double().requires_grad_()
+        gr = g.to(dtype).double()
+        wr, br = conv.weight.detach().double().requires_grad_(), conv.bias.detach().double().requires_grad_()
+        yr = F.silu(F.conv2d(xr, wr, br, padding=1, groups=d))
+        yr.backward(gr)
+        m = nn.Conv2d(d, d, 3, padding=1, groups=d).cuda()
+        m.load_state_dict(conv.state_dict())
+        xg = x.to(dtype).cuda().requires_grad_()
+        y = dwconv3x3_silu(xg, m)
+        y.backward(g.to(dtype).cuda())
+        assert y.dtype == dtype and xg.grad.dtype == dtype and m.weight.grad.shape == conv.weight.shape
+        assert rel_l2(y, yr) < tol and rel_l2(xg.grad, xr.grad) < tol
+        assert rel_l2(m.weight.grad, wr.grad) < tol_w and rel_l2(m.bias.grad, br.grad) < tol_w
