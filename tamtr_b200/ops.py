@@ -688,7 +688,9 @@ class _AddLayerNormFn(torch.autograd.Function):
         b32 = bias.detach().float().contiguous()
         y = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
         need = any(ctx.needs_input_grad[:4])
-        z = torch.empty(xc.shape, dtype=torch.float32, device=xc.device) if need else None
+        # no residual and fp32 input: z IS x, nothing to write (the backward reads x)
+        z_is_x = rc_ is None and xc.dtype == torch.float32
+        z = torch.empty(xc.shape, dtype=torch.float32, device=xc.device) if (need and not z_is_x) else None
         mean = torch.empty(rows, dtype=torch.float32, device=xc.device) if need else None
         rstd = torch.empty(rows, dtype=torch.float32, device=xc.device) if need else None
         with _with_device(xc):
@@ -699,7 +701,7 @@ class _AddLayerNormFn(torch.autograd.Function):
                 None if rstd is None else rstd.data_ptr(), rows, d, float(eps), _lib.stream_ptr(xc.device))
         _lib.check(rc, "add_layernorm_forward")
         if need:
-            ctx.save_for_backward(z, mean, rstd, w32)
+            ctx.save_for_backward(xc if z_is_x else z, mean, rstd, w32)
             ctx.meta = (xc.dtype, None if rc_ is None else rc_.dtype, weight.dtype, bias.dtype, rows, d)
         return y
 

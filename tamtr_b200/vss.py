@@ -191,6 +191,16 @@ def _is_dw3x3(conv, x):
             and conv.padding_mode == "zeros")
 
 
+def _layer_norm(norm, x):
+    """nn.LayerNorm over the last dimension on the one-warp-per-row kernels of csrc/layernorm.cu when they cover the width
+    (128 / 256 / 384 / 512); wider rows (d_inner = 1024 at the smallest level) stay on the library kernel."""
+    from . import ops
+    if (isinstance(norm, nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
+            and tuple(norm.normalized_shape) == (x.shape[-1],) and ops.add_layer_norm_supported(x, x.shape[-1])):
+        return ops.add_layer_norm(x, None, norm)
+    return norm(x)
+
+
 class DropPath(nn.Module):
     """Stochastic depth per sample (timm.layers.DropPath, used at vmamba.py:1232)."""
 
@@ -279,13 +289,16 @@ class SS2D(nn.Module):
                             -torch.exp(self.A_logs.float()), Bs.contiguous().float(), Cs.contiguous().float(),
                             self.Ds.float(), self.dt_projs_bias.view(-1).float(), True)
         y = cross_merge(ys.view(b, k, -1, l), h, w)
-        y = self.out_norm(y.transpose(1, 2).contiguous()).view(b, h, w, -1)
+        y = _layer_norm(self.out_norm, y.transpose(1, 2).contiguous()).view(b, h, w, -1)
         return y.to(x.dtype)
 
     def forward(self, x):
-        x = self.in_proj(x)
-        x, z = x.chunk(2, dim=-1)
-        z = self.act(z.clone())
+        # in_proj (vmamba.py:1021-1024) as two GEMMs, one per half of its output: the same numbers, but x and z come out
+        # contiguous -- no chunk views, no z.clone(), and no torch.cat of the two gradient halves in the backward
+        wgt, bias = self.in_proj.weight, self.in_proj.bias
+        d_in = wgt.shape[0] // 2
+        z = self.act(F.linear(x, wgt[d_in:], None if bias is None else bias[d_in:]))
+        x = F.linear(x, wgt[:d_in], None if bias is None else bias[:d_in])
         x = x.permute(0, 3, 1, 2).contiguous()
         if isinstance(self.act, nn.SiLU) and _is_dw3x3(self.conv2d, x):
             x = dwconv3x3_silu(x, self.conv2d)
@@ -317,5 +330,5 @@ class VSSBlock(nn.Module):
                        drop=mlp_drop_rate)
 
     def forward(self, input):
-        x = input + self.drop_path(self.op(self.norm(input)))
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        x = input + self.drop_path(self.op(_layer_norm(self.norm, input)))
+        return x + self.drop_path(self.mlp(_layer_norm(self.norm2, x)))
