@@ -225,7 +225,7 @@ template <bool BF16> struct ScBwdSmem {
     float4 udyr[kScCh][kBwT + 1];                               // {u, delta, dy, dt + bias}; .z / .w become d_u / d_raw
     float dy[2][kScCh][kBwT + 1];                               // raw tiles as they arrive, double-buffered
     float b[2][kBwT][kScBcPitch], c[2][kBwT][kScBcPitch];
-    float db[kScN][kBwT + 1], dc[kScN][kBwT + 1];               // CTA-level dB / dC of the segment
+    float dbc[kScThreads / 32][2 * kScN][kBwT + 1];             // per-warp dB (rows 0-15) / dC (rows 16-31) of the segment
     float sub[kBwT / kScSub][kScThreads][kScNs];                // states before every 4th position of the segment
     uint32_t u16[BF16 ? 2 : 1][BF16 ? kScCh : 1][kBwT / 2], d16[BF16 ? 2 : 1][BF16 ? kScCh : 1][kBwT / 2];
     float u32[BF16 ? 1 : 2][BF16 ? 1 : kScCh][kBwT + 1], d32[BF16 ? 1 : 2][BF16 ? 1 : kScCh][kBwT + 1];
@@ -265,6 +265,8 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
     const float dsk = Dv != nullptr ? __ldg(Dv + ch) : 0.0f;
     float dD = 0.0f, dbias = 0.0f;
     const float *ck = ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN + n0;
+    // after the transposition-reduction lane (v, sg) holds dB[n0 + v] (v < 4) or dC[n0 + v - 4]
+    float *my_dbc = sm.dbc[warp][(((lane >> 2) & 7) < kScNs ? 0 : kScN - kScNs) + n0 + ((lane >> 2) & 7)];
 
     auto prefetch = [&](int buf, int t0) {
         if constexpr (BF16) {
@@ -302,7 +304,6 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
             e.y = live ? softplus20(e.w) : 0.0f;
             sm.udyr[r][tl] = e;
         }
-        for (int i = threadIdx.x; i < kScN * (T + 1); i += kScThreads) { (&sm.db[0][0])[i] = 0.0f; (&sm.dc[0][0])[i] = 0.0f; }
         __syncthreads();
         // ---- pass 1: recompute the segment forward from its checkpoint
         {
@@ -383,19 +384,18 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
                         red[i] = (up ? red[i + s] : red[i]) + got;
                     }
                 }
-                {   // this lane now holds value index v = (lane >> 2) & 7 of state group sg: v < 4 -> dB, else dC
-                    const int v = (lane >> 2) & 7;
-                    float *dst = v < kScNs ? &sm.db[n0 + v][t] : &sm.dc[n0 + v - kScNs][t];
-                    atomicAdd(dst, red[0]);
-                }
-                if (sg == 0) {
+                // this lane now holds value index v = (lane >> 2) & 7 of state group sg: v < 4 -> dB, else dC.  Every warp
+                // owns a slot per (value, position) -- a plain store; fp32 atomicAdd on shared memory is a CAS spin loop
+                // (ATOMS.CAST.SPIN) and the CTA's four warps would contend on every address
+                my_dbc[t] = red[0];
+                {   // branch-free: all four lanes of the channel hold the same sums, lane 0 of them stores
                     // (every lane of the channel has read udyr[c][t] before the full-mask shuffles above)
                     const float raw = e.w;
                     d_u = fmaf(dsk, gy, d_u);
                     dD = fmaf(gy, ut, dD);
                     const float d_raw = raw > 20.0f ? d_dl : d_dl * (1.0f / (1.0f + __expf(-raw)));
                     dbias += d_raw;
-                    *reinterpret_cast<float2 *>(&sm.udyr[c][t].z) = make_float2(d_u, d_raw);
+                    if (sg == 0) *reinterpret_cast<float2 *>(&sm.udyr[c][t].z) = make_float2(d_u, d_raw);
                 }
             }
         }
@@ -407,10 +407,11 @@ sscan_bwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
                 sc_store<BF16>(g_dt, (row0 + r) * (size_t)L + t0 + tl, e.w);
             }
         }
-        for (int n = warp * RPW + srow; n < kScN; n += RPW * (kScThreads / 32)) {
+        for (int n = warp * RPW + srow; n < 2 * kScN; n += RPW * (kScThreads / 32)) {       // rows 0-15: dB, 16-31: dC
             if (t0 + tl < L) {
-                atomicAdd(g_B + (grp * kScN + n) * (size_t)L + t0 + tl, sm.db[n][tl]);
-                atomicAdd(g_C + (grp * kScN + n) * (size_t)L + t0 + tl, sm.dc[n][tl]);
+                const float v = (sm.dbc[0][n][tl] + sm.dbc[1][n][tl]) + (sm.dbc[2][n][tl] + sm.dbc[3][n][tl]);
+                float *dst = n < kScN ? g_B + (grp * kScN + n) * (size_t)L : g_C + (grp * kScN + n - kScN) * (size_t)L;
+                atomicAdd(dst + t0 + tl, v);
             }
         }
     }
