@@ -29,6 +29,8 @@ import time
 
 import torch
 
+_JSON_OUT = sys.stdout      # main() replaces it by a private duplicate of fd 1
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -238,7 +240,7 @@ def run_reference(args):
                          "sample": f"{sample} images/step of the same workload (S-yaml head, train fwd+bwd, fp32), "
                                    f"{steps} steps after {warmup} warm-up, torch CPU with {cores} threads"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }), file=_JSON_OUT, flush=True)
 
 
 LOSS_NAMES = {"detection": "RTDETRDetectionLoss(use_vfl) on encoder proposals + 3 decoder layers + denoising queries, "
@@ -278,6 +280,12 @@ def main():
                     help="eager steps only (no e2e / instrumented pass / CPU baseline): the command to run under "
                          "`ncu --metrics gpu__time_duration.sum` for profiles/launches_*.csv")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: keep a private handle on it and point fd 1 at stderr for everything else
+    # (NCCL prints its version banner to stdout at init, whatever NCCL_DEBUG_FILE says)
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -318,7 +326,7 @@ def main():
         for _ in range(args.warmup + args.steps):
             step.run()
         torch.cuda.synchronize(dev)
-        print(json.dumps({"launch_list": True, "steps": args.steps, "warmup": args.warmup}))
+        print(json.dumps({"launch_list": True, "steps": args.steps, "warmup": args.warmup}), file=_JSON_OUT, flush=True)
         return
     h2d = sum(x.numel() * x.element_size() for x in host[0][0]) + host[0][1].numel() * host[0][1].element_size()
 
@@ -513,7 +521,7 @@ def main():
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": "2 images/step of the same workload (fp32 train fwd+bwd), 2 timed steps "
                                               f"after 1 warm-up, torch CPU {cores} threads, {s:.1f} s/step"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if ws > 1:
         dist.destroy_process_group()
 
