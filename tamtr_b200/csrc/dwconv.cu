@@ -3,7 +3,8 @@
 // backward, NCHW.  The op is a 9-tap stencil per channel plane -- 2 bytes in, 2 bytes out per element, HBM-bound -- but the
 // library's depth-wise kernels take 0.9 ms forward and 2.7 ms backward on the head's largest level (B=16, 256 x 160 x 160
 // bf16: 210 MB each way, 65 us at HBM peak) and the SiLU is two more passes.  Here a CTA stages a 16-row x 128-column
-// tile (+ halo) of one plane in shared memory as fp32 and every thread slides a 3x3 window down its column.
+// tile (+ halo) of one plane in shared memory as
+// fp32 and every thread slides a 3x3 window down its column.
 //   forward : y = silu(conv(x) + b)
 //   backward: pre = conv(x) + b is recomputed from the staged x tile (x is needed for the weight gradient anyway),
 //             gp = g * silu'(pre);  dx = conv^T(gp);  dw[c, dy, dx] = sum gp * x(shifted);  db[c] = sum gp
@@ -12,7 +13,8 @@
 
 namespace tamtr {
 
-constexpr int kDwTH = 16, kDwTW = 128, kDwThreads = 256;
+// tile = kDwTH rows x TW columns (TW = 128; 64 / 32 for maps that narrow); 256 threads = (256 / TW) row groups x TW columns
+constexpr int kDwTH = 16, kDwThreads = 256;
 
 template <typename T> __device__ __forceinline__ float dw_ld(const T *p);
 template <> __device__ __forceinline__ float dw_ld<float>(const float *p) { return __ldg(p); }
@@ -23,40 +25,47 @@ template <typename T> __device__ __forceinline__ void dw_st(T *p, float v);
 template <> __device__ __forceinline__ void dw_st<float>(float *p, float v) { *p = v; }
 template <> __device__ __forceinline__ void dw_st<__nv_bfloat16>(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
-// plane tile [h0 - HALO, h0 + kDwTH + HALO) x [w0 - HALO, w0 + kDwTW + HALO) of `src` -> smem (zeros outside the image)
-template <typename T, int HALO>
-__device__ __forceinline__ void dw_stage(float (*tile)[kDwTW + 2 * HALO + 1], const T *__restrict__ src, int H, int W, int h0,
+// plane tile [h0 - HALO, h0 + kDwTH + HALO) x [w0 - HALO, w0 + TW + HALO) of `src` -> smem (zeros outside the image);
+// one warp per tile row, lanes along the row
+template <typename T, int HALO, int TW>
+__device__ __forceinline__ void dw_stage(float (*tile)[TW + 2 * HALO + 1], const T *__restrict__ src, int H, int W, int h0,
                                          int w0) {
-    constexpr int TWH = kDwTW + 2 * HALO, THH = kDwTH + 2 * HALO;
-    for (int i = threadIdx.x; i < THH * TWH; i += kDwThreads) {
-        const int r = i / TWH, c = i - r * TWH;
-        const int h = h0 - HALO + r, w = w0 - HALO + c;
-        tile[r][c] = (h >= 0 && h < H && w >= 0 && w < W) ? dw_ld(src + (size_t)h * W + w) : 0.0f;
+    constexpr int TWH = TW + 2 * HALO, THH = kDwTH + 2 * HALO;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < THH; r += kDwThreads / 32) {
+        const int h = h0 - HALO + r;
+        const bool row_ok = h >= 0 && h < H;
+        const T *row = src + (size_t)(row_ok ? h : 0) * W;
+        for (int c = lane; c < TWH; c += 32) {
+            const int w = w0 - HALO + c;
+            tile[r][c] = (row_ok && w >= 0 && w < W) ? dw_ld(row + w) : 0.0f;
+        }
     }
 }
 
-template <typename T>
+template <typename T, int TW>
 __global__ void __launch_bounds__(kDwThreads)
 dwconv3x3_silu_fwd_kernel(const T *__restrict__ x, const float *__restrict__ wgt, const float *__restrict__ bias,
                           T *__restrict__ y, int D, int H, int W) {
-    __shared__ float xs[kDwTH + 2][kDwTW + 3];
+    constexpr int RPG = kDwTH * TW / kDwThreads;       // rows per thread: 2 / 4 / 8
+    __shared__ float xs[kDwTH + 2][TW + 3];
     const int plane = blockIdx.x, c = plane % D;                 // planes on grid.x (no 65 535 limit)
-    const int h0 = blockIdx.z * kDwTH, w0 = blockIdx.y * kDwTW;
+    const int h0 = blockIdx.z * kDwTH, w0 = blockIdx.y * TW;
     const T *src = x + (size_t)plane * H * W;
-    dw_stage<T, 1>(xs, src, H, W, h0, w0);
+    dw_stage<T, 1, TW>(xs, src, H, W, h0, w0);
     float k[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) k[i] = __ldg(wgt + c * 9 + i);
     const float b = bias ? __ldg(bias + c) : 0.0f;
     __syncthreads();
-    const int col = threadIdx.x % kDwTW, r0 = (threadIdx.x / kDwTW) * (kDwTH / 2);      // 2 row groups of 8
+    const int col = threadIdx.x % TW, r0 = (threadIdx.x / TW) * RPG;
     if (w0 + col >= W) return;
     T *dst = y + (size_t)plane * H * W + w0 + col;
     float a[3], m[3], n[3];                      // window rows r-1, r, r+1 (tile coordinates: +1 halo)
 #pragma unroll
     for (int j = 0; j < 3; ++j) { a[j] = xs[r0][col + j]; m[j] = xs[r0 + 1][col + j]; }
 #pragma unroll
-    for (int r = 0; r < kDwTH / 2; ++r) {
+    for (int r = 0; r < RPG; ++r) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) n[j] = xs[r0 + r + 2][col + j];
         float pre = b;
@@ -69,44 +78,46 @@ dwconv3x3_silu_fwd_kernel(const T *__restrict__ x, const float *__restrict__ wgt
     }
 }
 
-template <typename T>
+template <typename T, int TW>
 __global__ void __launch_bounds__(kDwThreads)
 dwconv3x3_silu_bwd_kernel(const T *__restrict__ g, const T *__restrict__ x, const float *__restrict__ wgt,
                           const float *__restrict__ bias, T *__restrict__ gx, float *__restrict__ gw, float *__restrict__ gb,
                           int D, int H, int W) {
-    __shared__ float xs[kDwTH + 4][kDwTW + 5];       // x, halo 2
-    __shared__ float gs[kDwTH + 2][kDwTW + 3];       // g, then gp = g * silu'(pre), halo 1
+    constexpr int RPG = kDwTH * TW / kDwThreads;
+    __shared__ float xs[kDwTH + 4][TW + 5];          // x, halo 2
+    __shared__ float gs[kDwTH + 2][TW + 3];          // g, then gp = g * silu'(pre), halo 1
     __shared__ float red[kDwThreads / 32][10];
     const int plane = blockIdx.x, c = plane % D;                 // planes on grid.x (no 65 535 limit)
-    const int h0 = blockIdx.z * kDwTH, w0 = blockIdx.y * kDwTW;
-    dw_stage<T, 2>(xs, x + (size_t)plane * H * W, H, W, h0, w0);
-    dw_stage<T, 1>(gs, g + (size_t)plane * H * W, H, W, h0, w0);
+    const int h0 = blockIdx.z * kDwTH, w0 = blockIdx.y * TW;
+    dw_stage<T, 2, TW>(xs, x + (size_t)plane * H * W, H, W, h0, w0);
+    dw_stage<T, 1, TW>(gs, g + (size_t)plane * H * W, H, W, h0, w0);
     float k[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) k[i] = __ldg(wgt + c * 9 + i);
     const float b = bias ? __ldg(bias + c) : 0.0f;
     __syncthreads();
     // gp on the tile + halo 1 (outside the image g == 0, hence gp == 0)
-    constexpr int TW1 = kDwTW + 2, TH1 = kDwTH + 2;
-    for (int i = threadIdx.x; i < TH1 * TW1; i += kDwThreads) {
-        const int r = i / TW1, cc = i - r * TW1;      // gs coordinates; xs coordinates are +1
-        float pre = b;
+    constexpr int TW1 = TW + 2, TH1 = kDwTH + 2;
+    for (int r = threadIdx.x >> 5; r < TH1; r += kDwThreads / 32) {          // gs coordinates; xs coordinates are +1
+        for (int cc = threadIdx.x & 31; cc < TW1; cc += 32) {
+            float pre = b;
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+            for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) pre = fmaf(k[dy * 3 + dx], xs[r + dy][cc + dx], pre);
-        const float s = 1.0f / (1.0f + __expf(-pre));
-        gs[r][cc] *= s * (1.0f + pre * (1.0f - s));
+                for (int dx = 0; dx < 3; ++dx) pre = fmaf(k[dy * 3 + dx], xs[r + dy][cc + dx], pre);
+            const float s = 1.0f / (1.0f + __expf(-pre));
+            gs[r][cc] *= s * (1.0f + pre * (1.0f - s));
+        }
     }
     __syncthreads();
-    const int col = threadIdx.x % kDwTW, r0 = (threadIdx.x / kDwTW) * (kDwTH / 2);
+    const int col = threadIdx.x % TW, r0 = (threadIdx.x / TW) * RPG;
     float acc[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = 0.0f;
     if (w0 + col < W) {
         T *dst = gx + (size_t)plane * H * W + w0 + col;
 #pragma unroll 2
-        for (int r = 0; r < kDwTH / 2; ++r) {
+        for (int r = 0; r < RPG; ++r) {
             const int h = h0 + r0 + r;
             if (h >= H) break;
             const int gr = r0 + r + 1, gc = col + 1;          // this position in gs; in xs it is (+2, +2)
@@ -148,7 +159,7 @@ static int dw_check(const void *a, const void *b, const void *c, int dtype, int 
     TAMTR_CHECK_ARG(a && b && c, TAMTR_E_BADARG, "dwconv3x3_silu: null pointer");
     TAMTR_CHECK_ARG(Bn > 0 && D > 0 && H > 0 && W > 0, TAMTR_E_BADARG, "dwconv3x3_silu: non-positive size");
     TAMTR_CHECK_ARG(dtype == TAMTR_F32 || dtype == TAMTR_BF16, TAMTR_E_UNSUPPORTED, "dwconv3x3_silu: dtype %d", dtype);
-    TAMTR_CHECK_ARG((long)Bn * D <= 2147483647L && (H + kDwTH - 1) / kDwTH <= 65535 && (W + kDwTW - 1) / kDwTW <= 65535,
+    TAMTR_CHECK_ARG((long)Bn * D <= 2147483647L && (H + kDwTH - 1) / kDwTH <= 65535 && (W + 31) / 32 <= 65535,
                     TAMTR_E_UNSUPPORTED, "dwconv3x3_silu: too many planes or tiles");
     return 0;
 }
@@ -157,17 +168,22 @@ static int dw_check(const void *a, const void *b, const void *c, int dtype, int 
 
 using namespace tamtr;
 
+// 128-column tiles unless the map is narrower.  (Picking the width with the fewest padded columns -- 5 x 32 for 160-wide
+// maps instead of 2 x 128 -- was measured SLOWER, 0.71 vs 0.47 ms forward: two rows per thread lose the sliding-window
+// reuse and the row segments shrink to 64 bytes.)
+static int dw_tile_width(int W) { return W <= 32 ? 32 : W <= 64 ? 64 : 128; }
+
 extern "C" int tamtr_dwconv3x3_silu_forward(const void *x, const float *weight, const float *bias, void *y, int dtype, int Bn,
                                             int D, int H, int W, void *stream) {
     const int rc = dw_check(x, weight, y, dtype, Bn, D, H, W);
     if (rc) return rc;
-    const dim3 grid(Bn * D, (W + kDwTW - 1) / kDwTW, (H + kDwTH - 1) / kDwTH);
+    const int tw = dw_tile_width(W);
+    const dim3 grid(Bn * D, (W + tw - 1) / tw, (H + kDwTH - 1) / kDwTH);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == TAMTR_F32)
-        dwconv3x3_silu_fwd_kernel<float><<<grid, kDwThreads, 0, st>>>((const float *)x, weight, bias, (float *)y, D, H, W);
-    else
-        dwconv3x3_silu_fwd_kernel<__nv_bfloat16><<<grid, kDwThreads, 0, st>>>((const __nv_bfloat16 *)x, weight, bias,
-                                                                              (__nv_bfloat16 *)y, D, H, W);
+#define DW_FWD(T, TWV) dwconv3x3_silu_fwd_kernel<T, TWV><<<grid, kDwThreads, 0, st>>>((const T *)x, weight, bias, (T *)y, D, H, W)
+    if (dtype == TAMTR_F32) { if (tw == 32) DW_FWD(float, 32); else if (tw == 64) DW_FWD(float, 64); else DW_FWD(float, 128); }
+    else { if (tw == 32) DW_FWD(__nv_bfloat16, 32); else if (tw == 64) DW_FWD(__nv_bfloat16, 64); else DW_FWD(__nv_bfloat16, 128); }
+#undef DW_FWD
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
@@ -182,14 +198,14 @@ extern "C" int tamtr_dwconv3x3_silu_backward(const void *grad_y, const void *x, 
     cudaStream_t st = (cudaStream_t)stream;
     TAMTR_CUDA_OK(cudaMemsetAsync(grad_weight, 0, sizeof(float) * 9 * (size_t)D, st));
     if (grad_bias) TAMTR_CUDA_OK(cudaMemsetAsync(grad_bias, 0, sizeof(float) * (size_t)D, st));
-    const dim3 grid(Bn * D, (W + kDwTW - 1) / kDwTW, (H + kDwTH - 1) / kDwTH);
-    if (dtype == TAMTR_F32)
-        dwconv3x3_silu_bwd_kernel<float><<<grid, kDwThreads, 0, st>>>((const float *)grad_y, (const float *)x, weight, bias,
-                                                                      (float *)grad_x, grad_weight, grad_bias, D, H, W);
-    else
-        dwconv3x3_silu_bwd_kernel<__nv_bfloat16><<<grid, kDwThreads, 0, st>>>(
-            (const __nv_bfloat16 *)grad_y, (const __nv_bfloat16 *)x, weight, bias, (__nv_bfloat16 *)grad_x, grad_weight,
-            grad_bias, D, H, W);
+    const int tw = dw_tile_width(W);
+    const dim3 grid(Bn * D, (W + tw - 1) / tw, (H + kDwTH - 1) / kDwTH);
+#define DW_BWD(T, TWV)                                                                                                      \
+    dwconv3x3_silu_bwd_kernel<T, TWV><<<grid, kDwThreads, 0, st>>>((const T *)grad_y, (const T *)x, weight, bias, (T *)grad_x, \
+                                                                   grad_weight, grad_bias, D, H, W)
+    if (dtype == TAMTR_F32) { if (tw == 32) DW_BWD(float, 32); else if (tw == 64) DW_BWD(float, 64); else DW_BWD(float, 128); }
+    else { if (tw == 32) DW_BWD(__nv_bfloat16, 32); else if (tw == 64) DW_BWD(__nv_bfloat16, 64); else DW_BWD(__nv_bfloat16, 128); }
+#undef DW_BWD
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
