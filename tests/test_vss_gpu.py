@@ -152,3 +152,32 @@ def test_dwconv3x3_silu_matches_library_conv(cuda_lib, b, d, h, w):
         assert y.dtype == dtype and xg.grad.dtype == dtype and m.weight.grad.shape == conv.weight.shape
         assert rel_l2(y, yr) < tol and rel_l2(xg.grad, xr.grad) < tol
         assert rel_l2(m.weight.grad, wr.grad) < tol_w and rel_l2(m.bias.grad, br.grad) < tol_w
+
+
+def test_config5_size_scan_and_block(cuda_lib):
+    """BASELINE.json config 5 (1280x1280 input, batch 1 per GPU): the largest level is 320x320 = 102 400 positions.
+    The scan against the oracle recurrence on one 32-channel group per direction, linearity in u at the full channel count
+    (y(2u) - y(u) == y(u) - y(0): a size-independent property of the recurrence), and one VSSBlock forward + backward."""
+    from tamtr_b200.vss import VSSBlock, selective_scan
+    L = 320 * 320
+    ins = _scan_inputs(31, 1, 4, 32, L)
+    with torch.no_grad():
+        y = selective_scan(*[t.cuda() for t in ins], True)
+        ref = vss_ref.selective_scan(*ins, True)
+    assert rel_l2(y, ref) < 1e-4
+    u, rest = ins[0].cuda(), [t.cuda() for t in ins[1:]]
+    with torch.no_grad():
+        full = [seeding.seeded_tensor(32, "u", (1, 1024, L)).cuda(), (seeding.seeded_tensor(32, "dt", (1, 1024, L)) - 2.0).cuda(),
+                -(0.5 + 15.5 * seeding.seeded_uniform(32, "A", (1024, 16))).cuda(),
+                seeding.seeded_tensor(32, "B", (1, 4, 16, L)).cuda(), seeding.seeded_tensor(32, "C", (1, 4, 16, L)).cuda()]
+        y1 = selective_scan(*full)
+        y2 = selective_scan(2.0 * full[0], *full[1:])
+        assert rel_l2(y2, 2.0 * y1) < 1e-5
+    del y1, y2, full
+    blk = VSSBlock(hidden_dim=128, drop_path=0.0).cuda()
+    x = seeding.seeded_tensor(33, "x", (1, 320, 320, 128)).cuda().requires_grad_()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = blk(x)
+    out.float().square().mean().backward()
+    assert out.shape == x.shape and torch.isfinite(out).all() and torch.isfinite(x.grad).all()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in blk.parameters())
