@@ -502,7 +502,8 @@ def main():
                 vsec = v0.elapsed_time(v1) / 1e3
                 line["with_vss"] = {"value": B * nv / vsec, "unit": "images/s", "ms_per_step": vsec / nv * 1e3, "steps": nv,
                                     "note": "VSSBlocks on the selective-scan kernels (fp32 scan as vmamba.py:985 forces), "
-                                            "drop_path 0; parity for the scan is pinned to the published recurrence only"}
+                                            "drop_path 0; parity for the scan: published recurrence (oracle) + forward cross-check against "
+                                            "vLLM's mamba_ssm kernel; the reference's own extension is not in its tree"}
                 del step3, model_v
                 torch.cuda.empty_cache()
             except Exception as e:

@@ -16,6 +16,8 @@ zero-order-hold discretisation of Alg. 2, as implemented by that extension's `se
     delta_t = softplus(dt_t + bias)            (softplus(x) = x for x > 20)
     h_t     = exp(delta_t * A) * h_{t-1} + delta_t * B_t * u_t          (h_{-1} = 0, per channel d and state n)
     y_t     = <C_t, h_t> + D * u_t
+(A forward-only cross-check of the CUDA scan against vLLM's port of the mamba_ssm kernel -- library code in this image, the
+same kernel family -- lives in tests/test_vss_gpu.py; it narrows this gap, it does not close it.)
 Everything AROUND the scan is pinned to the unmodified reference: `install_scan_extension()` plugs this function into the
 reference's namespace under the missing extension's name so that the reference's own VSSBlock runs end to end
 (oracle/make_goldens_vss.py -> tests/golden/vss.pt).
