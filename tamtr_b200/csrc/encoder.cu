@@ -286,19 +286,35 @@ rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const
     if (row0 >= nrows) return;
     float v[TOK][PP][N];
     bool ok[TOK];
+    float rawv[TOK];
+    uint8_t vld[TOK];
     const int t0 = row0 % Lv;
+    // every global load of the warp's TOK tokens is issued up front and independently -- the validity bytes, the embedding
+    // rows (loaded whether valid or not, zeroed afterwards) and the score-GEMM row -- so that a warp pays ONE DRAM round trip
+    // (the first version chained three: valid -> E -> statistics -> raw)
 #pragma unroll
     for (int t = 0; t < TOK; ++t) {
         const int row = row0 + t;
         int tok = t0 + t;
         tok = tok >= Lv ? tok - Lv : tok;
-        ok[t] = row < nrows && valid[tok] != 0;
+        vld[t] = row < nrows ? __ldg(valid + tok) : (uint8_t)0;
+        rawv[t] = (row < nrows && nc <= 32 && lane < nc) ? __ldg(raw + (size_t)row * raw_stride + lane) : 0.f;
 #pragma unroll
         for (int p = 0; p < PP; ++p) {
             const int c = (p * 32 + lane) * N;
 #pragma unroll
             for (int i = 0; i < N; ++i) v[t][p][i] = 0.f;
-            if (ok[t] && c < d) Pack<T>::load(E + (size_t)row * d + c, v[t][p]);
+            if (row < nrows && c < d) Pack<T>::load(E + (size_t)row * d + c, v[t][p]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TOK; ++t) {
+        ok[t] = vld[t] != 0;
+        if (!ok[t]) {
+#pragma unroll
+            for (int p = 0; p < PP; ++p)
+#pragma unroll
+                for (int i = 0; i < N; ++i) v[t][p][i] = 0.f;
         }
     }
     float eb[PP][N];
@@ -355,7 +371,7 @@ rank_tokens_kernel(const T *__restrict__ E, const float *__restrict__ raw, const
         if (row < nrows) {
             if (nc <= 32) {
                 if (lane < nc) {
-                    const float r = ok[t] ? __ldg(raw + (size_t)row * raw_stride + lane) : 0.f;
+                    const float r = ok[t] ? rawv[t] : 0.f;
                     best[t] = rstd * (r + cbw - s[t] * csw) + cck;
                 }
             } else {
