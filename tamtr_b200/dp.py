@@ -212,6 +212,75 @@ class HeadTrainStep:
         return self.loss
 
 
+class HeadInferStep:
+    """Eval-mode forward of a detection head on static buffers, captured once into a CUDA graph.
+
+    Inference is sharded by image, one process per GPU, no collective.  At the batch sizes that
+    leaves per GPU the eager forward is launch-bound (the MEH head at 1280x1280 takes 5 ms for 1 image and for 8), so the
+    whole forward -- input projection, query selection, the decoder layers with their sampler / projection / contrastive
+    kernels -- is replayed as one graph.
+
+    module   : tamtr_b200.head.ManbaWorldDecoder / RTDETRDecoder (put in eval mode here)
+    example  : tuple of example inputs fixing every shape, e.g. (list of 3 feature maps, text)
+    autocast : torch dtype or None
+    run(inputs=None) copies `inputs` (same shapes) into the static buffers when given, replays, and returns the module's
+    outputs -- static tensors that the next run() overwrites."""
+
+    def __init__(self, module, example, autocast=None, use_graph=True, warmup=3):
+        self.module, self.autocast = module.eval(), autocast
+        self.device = next(module.parameters()).device
+        self.static = [self._to_static(a) for a in example]
+        self.out, self.graph, self.launches_per_step = None, None, None
+        if use_graph and self.device.type == "cuda":
+            from . import _lib
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    self._fwd()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(self.graph):
+                self.out = self._fwd()
+            self.launches_per_step = _lib.launch_count() - before
+            torch.cuda.synchronize(self.device)
+
+    def _to_static(self, a):
+        if isinstance(a, torch.Tensor):
+            return a.detach().to(self.device).clone()
+        if isinstance(a, (list, tuple)):
+            return type(a)(self._to_static(x) for x in a)
+        return a
+
+    def _fwd(self):
+        with torch.no_grad():
+            if self.autocast is not None:
+                with torch.autocast(self.device.type, dtype=self.autocast):
+                    return self.module(*self.static)
+            return self.module(*self.static)
+
+    def load_inputs(self, inputs, non_blocking=True):
+        def cp(dst, src):
+            if isinstance(dst, torch.Tensor):
+                dst.copy_(src, non_blocking=non_blocking)
+            elif isinstance(dst, (list, tuple)):
+                for d, s_ in zip(dst, src):
+                    cp(d, s_)
+        for d, s_ in zip(self.static, inputs):
+            cp(d, s_)
+
+    def run(self, inputs=None):
+        if inputs is not None:
+            self.load_inputs(inputs)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.out = self._fwd()
+        return self.out
+
+
 def max_over_ranks(seconds, device):
     """Multi-GPU timings are the max over ranks (never a wall clock of rank 0 alone)."""
     rank, ws = world()
