@@ -313,6 +313,18 @@ int tamtr_selective_scan_backward(const void *u, const void *dt, int in_dtype, c
                                   void *g_u, void *g_dt, float *g_A, float *g_B, float *g_C, float *g_D, float *g_bias,
                                   int Bn, int KD, int Dg, int N, int L, void *stream);
 
+/* Chunk-parallel forward for inference (no checkpoints), for (channel block, image) grids too small to fill the GPU --
+ * batch 1 at 1280x1280 is 32 CTAs walking 102 400 positions.  The sequence is cut into n_chunks pieces; a state pass runs
+ * the recurrence without outputs on every piece but the last from h = 0 and records its end state and sum of delta, the
+ * output pass folds h_in of each piece from the pieces before it (the recurrence is linear in h and the decay over a piece
+ * is exp(A * sum of its deltas)) and scans it.  Same arguments as tamtr_selective_scan_forward, plus
+ *   carry f32 [Bn * KD * n_chunks * 17] workspace; n_chunks >= 2 (tamtr_selective_scan_chunks() recommends a value, 1 =
+ *   use the plain forward). */
+int tamtr_selective_scan_chunks(int Bn, int KD, int L);
+int tamtr_selective_scan_forward_chunked(const void *u, const void *dt, int in_dtype, const float *A, const float *B,
+                                         const float *C, const float *D, const float *bias, float *y, float *carry,
+                                         int n_chunks, int Bn, int KD, int Dg, int N, int L, void *stream);
+
 /* The four scan orders of SS2D (ultralytics/nn/extra_modules/VManba/csms6s.py:4-47), one pass each way:
  *   tamtr_cross_scan : x [Bn, D, H, W] -> xs [Bn, 4, D, H*W]  (row-major, column-major, both reversed)   = CrossScan.forward
  *                                                                                                       = CrossMerge.backward

@@ -66,6 +66,8 @@ _SIGNATURES = {
     "tamtr_locw_tc_forward": (ctypes.c_int, [_vp] * 5 + [_i] + [_fp] * 4 + [_i] * 7 + [_vp]),
     "tamtr_dwconv3x3_silu_forward": (ctypes.c_int, [_vp, _fp, _fp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_dwconv3x3_silu_backward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _vp, _fp, _fp] + [_i] * 5 + [_vp]),
+    "tamtr_selective_scan_chunks": (ctypes.c_int, [_i] * 3),
+    "tamtr_selective_scan_forward_chunked": (ctypes.c_int, [_vp, _vp, _i] + [_fp] * 7 + [_i] * 6 + [_vp]),
     "tamtr_cross_scan": (ctypes.c_int, [_vp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_cross_merge": (ctypes.c_int, [_vp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),

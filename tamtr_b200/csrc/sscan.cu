@@ -116,12 +116,19 @@ template <bool BF16> __device__ __forceinline__ void sc_store(void *p, size_t i,
     if (BF16) reinterpret_cast<__nv_bfloat16 *>(p)[i] = __float2bfloat16_rn(v); else reinterpret_cast<float *>(p)[i] = v;
 }
 
-template <bool BF16>
+// MODE 0: the whole sequence in one CTA (training: with checkpoints).
+// Chunk-parallel inference, for grids too small to fill the GPU (batch 1 at 1280x1280: 32 CTAs of 4 warps walking 102 400
+// positions): the sequence is cut into n_chunks pieces of chunk_len positions, blockIdx.z = the piece.
+//   MODE 1: state pass -- the recurrence without outputs on pieces 0 .. n_chunks-2, started from h = 0; writes the
+//           piece's end state (carry_h [Bn, KD, n_chunks, 16]) and its sum of delta (carry_s [Bn, KD, n_chunks])
+//   MODE 2: output pass -- h_in of piece k folded from the pieces before it, h <- exp(A * sum delta_j) * h + end_j (the
+//           recurrence is linear in h, and the decay over a piece is exp(A * sum of its deltas)), then the normal loop
+template <bool BF16, int MODE>
 __global__ void __launch_bounds__(kScThreads)
 sscan_fwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, const float *__restrict__ A,
                  const float *__restrict__ Bm, const float *__restrict__ Cm, const float *__restrict__ Dv,
                  const float *__restrict__ bias, float *__restrict__ y, float *__restrict__ ckpt, int KD, int Dg, int L,
-                 int n_seg) {
+                 int n_seg, float *__restrict__ carry_h, float *__restrict__ carry_s, int n_chunks, int chunk_len) {
     using TIn = typename ScIn<BF16>::type;
     const TIn *__restrict__ u = reinterpret_cast<const TIn *>(u_);
     const TIn *__restrict__ dt = reinterpret_cast<const TIn *>(dt_);
@@ -138,7 +145,22 @@ sscan_fwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
 #pragma unroll
     for (int j = 0; j < kScNs; ++j) { a2[j] = __ldg(A + (size_t)ch * kScN + n0 + j) * kLog2e; h[j] = 0.0f; }
     const float dsk = (Dv != nullptr && sg == 0) ? __ldg(Dv + ch) : 0.0f;     // the skip term rides on lane 0's partial
-    float *ck = ckpt != nullptr ? ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN + n0 : nullptr;
+    float *ck = (MODE == 0 && ckpt != nullptr) ? ckpt + ((size_t)b * KD + ch) * (size_t)n_seg * kScN + n0 : nullptr;
+    const int piece = MODE == 0 ? 0 : (int)blockIdx.z;
+    const int tb = MODE == 0 ? 0 : piece * chunk_len;                    // chunk_len is a multiple of the tile length
+    const int te = MODE == 0 ? L : min(L, tb + chunk_len);
+    const size_t carry0 = ((size_t)b * KD + ch) * (size_t)n_chunks;
+    float sum_delta = 0.0f;
+    if constexpr (MODE == 2) {
+        for (int j = 0; j < piece; ++j) {
+            const float sj = __ldg(carry_s + carry0 + j);
+            const float4 e = __ldg(reinterpret_cast<const float4 *>(carry_h + (carry0 + j) * kScN + n0));
+            h[0] = fmaf(ex2(sj * a2[0]), h[0], e.x);
+            h[1] = fmaf(ex2(sj * a2[1]), h[1], e.y);
+            h[2] = fmaf(ex2(sj * a2[2]), h[2], e.z);
+            h[3] = fmaf(ex2(sj * a2[3]), h[3], e.w);
+        }
+    }
 
     auto prefetch = [&](int buf, int t0) {
         if constexpr (BF16) {
@@ -149,13 +171,13 @@ sscan_fwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
             stage_rows_async<2>(&s_ud[BF16 ? 0 : buf][0][0].x, 1, dt, row0, L, t0);
         }
         stage_bc_async(s_b[buf], Bm, grp, L, t0);
-        stage_bc_async(s_c[buf], Cm, grp, L, t0);
+        if constexpr (MODE != 1) stage_bc_async(s_c[buf], Cm, grp, L, t0);
         cp_async_commit();
     };
-    prefetch(0, 0);
+    prefetch(0, tb);
     int buf = 0;
-    for (int t0 = 0; t0 < L; t0 += kScT, buf ^= 1) {
-        if (t0 + kScT < L) { prefetch(buf ^ 1, t0 + kScT); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    for (int t0 = tb; t0 < te; t0 += kScT, buf ^= 1) {
+        if (t0 + kScT < te) { prefetch(buf ^ 1, t0 + kScT); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();
         // delta = softplus(dt + bias), once per element, in place (zero past L: h is then left unchanged)
         for (int r = warp; r < kScCh; r += kScThreads / 32) {
@@ -180,20 +202,30 @@ sscan_fwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
         for (int t = sgm * kScSeg; t < (sgm + 1) * kScSeg; ++t) {
             const float2 ud = s_ud[BF16 ? 0 : buf][c][t];
             const float4 b4 = *reinterpret_cast<const float4 *>(&s_b[buf][t][n0]);
-            const float4 c4 = *reinterpret_cast<const float4 *>(&s_c[buf][t][n0]);
             const float du = ud.y * ud.x;
             h[0] = fmaf(ex2(ud.y * a2[0]), h[0], du * b4.x);
             h[1] = fmaf(ex2(ud.y * a2[1]), h[1], du * b4.y);
             h[2] = fmaf(ex2(ud.y * a2[2]), h[2], du * b4.z);
             h[3] = fmaf(ex2(ud.y * a2[3]), h[3], du * b4.w);
-            s_yp[threadIdx.x][t] = fmaf(c4.x, h[0], fmaf(c4.y, h[1], fmaf(c4.z, h[2], fmaf(c4.w, h[3], dsk * ud.x))));
+            if constexpr (MODE == 1) {
+                sum_delta += ud.y;
+            } else {
+                const float4 c4 = *reinterpret_cast<const float4 *>(&s_c[buf][t][n0]);
+                s_yp[threadIdx.x][t] = fmaf(c4.x, h[0], fmaf(c4.y, h[1], fmaf(c4.z, h[2], fmaf(c4.w, h[3], dsk * ud.x))));
+            }
         }
         }
         __syncthreads();
-        for (int r = warp; r < kScCh; r += kScThreads / 32)
-            if (t0 + lane < L)
-                y[(row0 + r) * (size_t)L + t0 + lane] = (s_yp[4 * r][lane] + s_yp[4 * r + 1][lane]) + (s_yp[4 * r + 2][lane] + s_yp[4 * r + 3][lane]);
+        if constexpr (MODE != 1) {
+            for (int r = warp; r < kScCh; r += kScThreads / 32)
+                if (t0 + lane < L)
+                    y[(row0 + r) * (size_t)L + t0 + lane] = (s_yp[4 * r][lane] + s_yp[4 * r + 1][lane]) + (s_yp[4 * r + 2][lane] + s_yp[4 * r + 3][lane]);
+        }
         // (the next iteration's first __syncthreads orders these reads of s_yp before its writes)
+    }
+    if constexpr (MODE == 1) {
+        *reinterpret_cast<float4 *>(carry_h + (carry0 + piece) * kScN + n0) = make_float4(h[0], h[1], h[2], h[3]);
+        if (sg == 0) carry_s[carry0 + piece] = sum_delta;
     }
 }
 
@@ -472,12 +504,65 @@ extern "C" int tamtr_selective_scan_forward(const void *u, const void *dt, int i
     {
         KernelTimer timer(K_SSCAN_FWD, st);
         if (in_dtype == TAMTR_BF16)
-            sscan_fwd_kernel<true><<<dim3(KD / kScCh, Bn), kScThreads, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, ckpt, KD, Dg, L,
-                                                                          tamtr_selective_scan_segments(L));
+            sscan_fwd_kernel<true, 0><<<dim3(KD / kScCh, Bn), kScThreads, 0, st>>>(
+                u, dt, A, Bm, Cm, D, bias, y, ckpt, KD, Dg, L, tamtr_selective_scan_segments(L), nullptr, nullptr, 1, L);
         else
-            sscan_fwd_kernel<false><<<dim3(KD / kScCh, Bn), kScThreads, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, ckpt, KD, Dg, L,
-                                                                           tamtr_selective_scan_segments(L));
+            sscan_fwd_kernel<false, 0><<<dim3(KD / kScCh, Bn), kScThreads, 0, st>>>(
+                u, dt, A, Bm, Cm, D, bias, y, ckpt, KD, Dg, L, tamtr_selective_scan_segments(L), nullptr, nullptr, 1, L);
     }
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// How many pieces the chunk-parallel inference forward should cut the sequence into: 1 (= use the plain forward) when the
+// (channel block, image) grid already fills the GPU, otherwise enough pieces for about four CTAs per SM, at most 32, each
+// at least 1024 positions.
+extern "C" int tamtr_selective_scan_chunks(int Bn, int KD, int L) {
+    if (Bn <= 0 || KD < kScCh || L <= 0) return 1;
+    const long ctas = (long)(KD / kScCh) * Bn;
+    const long want = 4L * ::tamtr::sm_count();
+    if (ctas * 2 > want) return 1;
+    long k = (want + ctas - 1) / ctas;
+    if (k > 32) k = 32;
+    while (k > 1 && L / k < 1024) --k;
+    return (int)k;
+}
+
+extern "C" int tamtr_selective_scan_forward_chunked(const void *u, const void *dt, int in_dtype, const float *A,
+                                                    const float *Bm, const float *Cm, const float *D, const float *bias,
+                                                    float *y, float *carry, int n_chunks, int Bn, int KD, int Dg, int N,
+                                                    int L, void *stream) {
+    TAMTR_CHECK_ARG(u && dt && A && Bm && Cm && y && carry, TAMTR_E_BADARG, "selective_scan_forward_chunked: null pointer");
+    TAMTR_CHECK_ARG(n_chunks >= 2 && n_chunks <= 64, TAMTR_E_BADARG, "selective_scan_forward_chunked: n_chunks = %d", n_chunks);
+    int rc = sscan_check(Bn, KD, Dg, N, L);
+    if (rc) return rc;
+    rc = sscan_check_in(in_dtype, u, dt, L);
+    if (rc) return rc;
+    TAMTR_CHECK_ARG(n_chunks <= 65535, TAMTR_E_UNSUPPORTED, "selective_scan_forward_chunked: too many chunks");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunk_len = (((L + n_chunks - 1) / n_chunks + kScT - 1) / kScT) * kScT;
+    const int pieces = (L + chunk_len - 1) / chunk_len;              // <= n_chunks; the carry arrays keep stride n_chunks
+    float *carry_h = carry, *carry_s = carry + (size_t)Bn * KD * n_chunks * kScN;
+    const int nseg = tamtr_selective_scan_segments(L);
+    KernelTimer timer(K_SSCAN_FWD, st);
+    if (pieces > 1) {
+        const dim3 ga(KD / kScCh, Bn, pieces - 1);
+        if (in_dtype == TAMTR_BF16)
+            sscan_fwd_kernel<true, 1><<<ga, kScThreads, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, nullptr, KD, Dg, L, nseg, carry_h,
+                                                               carry_s, n_chunks, chunk_len);
+        else
+            sscan_fwd_kernel<false, 1><<<ga, kScThreads, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, nullptr, KD, Dg, L, nseg, carry_h,
+                                                                carry_s, n_chunks, chunk_len);
+        count_launch();
+    }
+    const dim3 gc(KD / kScCh, Bn, pieces);
+    if (in_dtype == TAMTR_BF16)
+        sscan_fwd_kernel<true, 2><<<gc, kScThreads, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, nullptr, KD, Dg, L, nseg, carry_h,
+                                                           carry_s, n_chunks, chunk_len);
+    else
+        sscan_fwd_kernel<false, 2><<<gc, kScThreads, 0, st>>>(u, dt, A, Bm, Cm, D, bias, y, nullptr, KD, Dg, L, nseg, carry_h,
+                                                            carry_s, n_chunks, chunk_len);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;

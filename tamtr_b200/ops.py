@@ -675,7 +675,7 @@ def add_layer_norm_supported(x, d):
 
 class _AddLayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, weight, bias, eps):
+    def forward(ctx, x, res, weight, bias, eps, track=True):
         d = x.shape[-1]
         xc = x.contiguous()
         rc_ = None if res is None else res.contiguous()
@@ -687,7 +687,9 @@ class _AddLayerNormFn(torch.autograd.Function):
         w32 = weight.detach().float().contiguous()
         b32 = bias.detach().float().contiguous()
         y = torch.empty(xc.shape, dtype=out_dtype, device=xc.device)
-        need = any(ctx.needs_input_grad[:4])
+        # `track`: grad mode at the call site (needs_input_grad alone is True for parameters even under no_grad, which
+        # made inference write z / mean / rstd for nothing)
+        need = bool(track) and any(ctx.needs_input_grad[:4])
         # no residual and fp32 input: z IS x, nothing to write (the backward reads x)
         z_is_x = rc_ is None and xc.dtype == torch.float32
         z = torch.empty(xc.shape, dtype=torch.float32, device=xc.device) if (need and not z_is_x) else None
@@ -729,7 +731,7 @@ class _AddLayerNormFn(torch.autograd.Function):
                 None if dx is None else dx.data_ptr(), 0 if dx is None else _lib.dtype_code(dx), dres_ptr,
                 0 if dres_ptr is None else _lib.dtype_code(dres), dwb.data_ptr(), rows, d, _lib.stream_ptr(dev))
         _lib.check(rc, "add_layernorm_backward")
-        return dx, dres, dwb[0].to(wdt), dwb[1].to(bdt), None
+        return dx, dres, dwb[0].to(wdt), dwb[1].to(bdt), None, None
 
 
 def add_layer_norm(x, res, norm):
@@ -737,7 +739,7 @@ def add_layer_norm(x, res, norm):
     (csrc/layernorm.cu).  Output is fp32 when an input is fp32 or under autocast (autocast runs layer_norm in fp32),
     otherwise the input dtype."""
     _lib.require_cuda(x, res)
-    return _AddLayerNormFn.apply(x, res, norm.weight, norm.bias, norm.eps)
+    return _AddLayerNormFn.apply(x, res, norm.weight, norm.bias, norm.eps, torch.is_grad_enabled())
 
 
 def to_channels_last(x):

@@ -23,9 +23,12 @@ from . import _lib
 __all__ = ("VSSBlock", "SS2D", "Mlp", "DropPath", "selective_scan", "cross_scan", "cross_merge", "dwconv3x3_silu")
 
 
+CHUNKED_INFERENCE = True    # no-grad forward on small grids: tamtr_selective_scan_forward_chunked (False: always the plain scan)
+
+
 class _SelectiveScanFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, u, delta, A, B, C, D, delta_bias):
+    def forward(ctx, u, delta, A, B, C, D, delta_bias, track):
         # u / delta may stay bf16 (converted on load inside the kernel: the same values the reference's to_fp32() produces,
         # vmamba.py:985-986, without two passes over [b, K*D, L]); everything else fp32
         lowp = (u.dtype == torch.bfloat16 and delta.dtype == torch.bfloat16 and u.shape[-1] % 2 == 0)
@@ -38,16 +41,29 @@ class _SelectiveScanFn(torch.autograd.Function):
         delta_bias = None if delta_bias is None else delta_bias.contiguous().float()
         Bn, KD, L = u.shape
         K, N = B.shape[1], A.shape[1]
-        need = any(ctx.needs_input_grad)
+        # `track` = grad mode was on at the call site and an input requires grad.  (Not any(ctx.needs_input_grad): that
+        # reports the inputs' requires_grad flags even under no_grad -- parameters such as Ds arrive as they are -- and
+        # grad mode is always off inside forward().)
+        need = bool(track)
         y = torch.empty(u.shape, dtype=torch.float32, device=u.device)
         lib = _lib.lib()
         ckpt = torch.empty(Bn, KD, lib.tamtr_selective_scan_segments(L), N, dtype=torch.float32, device=u.device) \
             if need else None
         with torch.cuda.device(u.device):
-            rc = lib.tamtr_selective_scan_forward(
-                u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
-                None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(), y.data_ptr(),
-                None if ckpt is None else ckpt.data_ptr(), Bn, KD, KD // K, N, L, _lib.stream_ptr(u.device))
+            pieces = 1 if need or not CHUNKED_INFERENCE else lib.tamtr_selective_scan_chunks(Bn, KD, L)
+            if pieces > 1:
+                # inference on a grid too small for the GPU (e.g. one 1280x1280 image): chunk-parallel forward
+                carry = torch.empty(Bn * KD * pieces * (N + 1), dtype=torch.float32, device=u.device)
+                rc = lib.tamtr_selective_scan_forward_chunked(
+                    u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
+                    None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(),
+                    y.data_ptr(), carry.data_ptr(), pieces, Bn, KD, KD // K, N, L, _lib.stream_ptr(u.device))
+            else:
+                rc = lib.tamtr_selective_scan_forward(
+                    u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
+                    None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(),
+                    y.data_ptr(), None if ckpt is None else ckpt.data_ptr(), Bn, KD, KD // K, N, L,
+                    _lib.stream_ptr(u.device))
         _lib.check(rc, "selective_scan_forward")
         if need:
             ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, ckpt)
@@ -72,7 +88,7 @@ class _SelectiveScanFn(torch.autograd.Function):
                 None if g_D is None else g_D.data_ptr(), None if g_bias is None else g_bias.data_ptr(), Bn, KD, KD // K, N,
                 L, _lib.stream_ptr(u.device))
         _lib.check(rc, "selective_scan_backward")
-        return g_u, g_dt, g_A, g_B, g_C, g_D, g_bias
+        return g_u, g_dt, g_A, g_B, g_C, g_D, g_bias, None
 
 
 def selective_scan(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=True):
@@ -81,7 +97,8 @@ def selective_scan(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=Tr
     _lib.require_cuda(u, delta, A, B, C, D, delta_bias)
     if not delta_softplus:
         raise RuntimeError("tamtr_b200: selective_scan without softplus is not on TAM-TR's path (vmamba.py:907)")
-    return _SelectiveScanFn.apply(u, delta, A, B, C, D, delta_bias)
+    track = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (u, delta, A, B, C, D, delta_bias))
+    return _SelectiveScanFn.apply(u, delta, A, B, C, D, delta_bias, track)
 
 
 def _cross_launch(fn_name, src, out, b, d, h, w):

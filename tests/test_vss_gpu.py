@@ -205,3 +205,34 @@ def test_scan_agrees_with_vllm_mamba_kernel(cuda_lib):
     if "unavailable" in res:
         pytest.skip("vLLM selective_scan_fn unavailable: " + res["unavailable"])
     assert res["rel_l2"] and all(v < 1e-5 for v in res["rel_l2"].values()), res
+
+
+@pytest.mark.parametrize("b,k,d,l", [(1, 4, 32, 4096), (1, 4, 64, 102400), (2, 4, 32, 9000), (1, 2, 32, 2050)])
+def test_chunk_parallel_inference_scan(cuda_lib, b, k, d, l):
+    """The chunk-parallel forward (state pass + output pass with folded carries) against the plain single-CTA scan of the
+    same kernels -- mathematically the same recurrence, rounded differently where a piece's entry state is formed -- and
+    against the oracle on the short case; bf16 inputs too."""
+    from tamtr_b200 import vss
+    lib = cuda_lib._lib.lib()
+    pieces = lib.tamtr_selective_scan_chunks(b, k * d, l)
+    assert pieces > 1 and lib.tamtr_selective_scan_chunks(16, 1024, 25600) == 1      # the training grid is left alone
+    ins = [t.cuda() for t in _scan_inputs(51, b, k, d, l)]
+    with torch.no_grad():
+        before = cuda_lib.launch_count()
+        y_chunked = vss.selective_scan(*ins, True)
+        assert cuda_lib.launch_count() - before == 2
+        vss.CHUNKED_INFERENCE = False
+        try:
+            y_plain = vss.selective_scan(*ins, True)
+            y16_plain = vss.selective_scan(ins[0].bfloat16(), ins[1].bfloat16(), *ins[2:], True)
+        finally:
+            vss.CHUNKED_INFERENCE = True
+        y16 = vss.selective_scan(ins[0].bfloat16(), ins[1].bfloat16(), *ins[2:], True)
+    assert rel_l2(y_chunked, y_plain) < 2e-6 and rel_l2(y16, y16_plain) < 2e-6
+    if l <= 4096:
+        assert rel_l2(y_chunked, vss_ref.selective_scan(*[t.cpu() for t in ins], True)) < 1e-4
+    # with gradients required the checkpointing forward is used (one launch), whatever the grid
+    leaf = [t.clone().requires_grad_() for t in ins]
+    before = cuda_lib.launch_count()
+    vss.selective_scan(*leaf, True)
+    assert cuda_lib.launch_count() - before == 1
