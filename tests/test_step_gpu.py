@@ -82,3 +82,28 @@ def test_graph_replay_and_fused_cast_match_plain_autocast(cuda_lib):
             assert step.launches_per_step > 0
             l2 = step.run().item()
             assert abs(l2 - loss.item()) < 2e-3 * abs(loss.item())
+
+
+@pytest.mark.parametrize("vss", [False, True])
+def test_infer_step_graph_equals_eager(cuda_lib, vss):
+    """dp.HeadInferStep: the eval forward replayed as one CUDA graph returns exactly what the eager forward returns, also
+    for a new batch copied into its static buffers, and with the VSSBlocks on (chunk-parallel scan inside the graph)."""
+    from tamtr_b200 import dp
+    from tamtr_b200.head import ManbaWorldDecoder
+    torch.manual_seed(0)
+    m = ManbaWorldDecoder(10, [128, 256, 512], 512, 50, 4, 8, 3, vss=vss).cuda().eval()
+    sizes = (64, 32, 16)
+    mk = lambda seed: ([seeding.seeded_smooth_map(seed, f"x{i}", (1, c, s, s)).bfloat16().cuda()
+                        for i, (c, s) in enumerate(zip((128, 256, 512), sizes))],
+                       torch.nn.functional.normalize(seeding.seeded_tensor(seed, "t", (1, 10, 512)), dim=-1).cuda())
+    a, b = mk(7), mk(8)
+    step = dp.HeadInferStep(m, a, autocast=torch.bfloat16)
+    assert step.graph is not None and step.launches_per_step > 0
+
+    def eager(inp):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return m(*inp)
+    for inp in (a, b):
+        got = step.run(inp)
+        want = eager(inp)
+        assert torch.equal(got[0], want[0])                 # [B, nq, 4 + nc] boxes ++ scores (head.py:1289)
