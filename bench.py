@@ -90,6 +90,36 @@ def gate_conv_roofline(dev, iters=20):
             "workload": "BTA-PAN text-guided 3x3 projection + BN + gate, B=16 C=256 80x80 (6400 tokens) N=10, bf16"}
 
 
+def infer_config5(dev, iters=20):
+    """Eval-mode forward of the MEH head at BASELINE.json configs[4] (1280x1280: levels 320^2/160^2/80^2, 900 queries,
+    batch 1 per GPU-iteration), bf16 autocast, replayed as one CUDA graph (dp.HeadInferStep); VSSBlocks identity / on."""
+    from tamtr_b200 import dp
+    from tamtr_b200.head import ManbaWorldDecoder
+    out = {"unit": "images/s per GPU", "workload": "MEH head eval forward, 1280x1280 (134 400 tokens), 900 queries, batch 1, "
+                                                   "bf16, CUDA graph; inputs resident"}
+    g = torch.Generator().manual_seed(99)
+    xs = [torch.randn(1, c, s, s, generator=g).bfloat16().to(dev) for c, s in zip(CH, (320, 160, 80))]
+    text = torch.nn.functional.normalize(torch.randn(1, NC, 512, generator=g), dim=-1).to(dev)
+    for key, vss in (("vss_identity", False), ("vss_on", True)):
+        torch.manual_seed(1234)
+        m = ManbaWorldDecoder(NC, list(CH), HD, 900, NDP, NH, NDL, vss=vss).to(dev).eval()
+        step = dp.HeadInferStep(m, (xs, text), autocast=torch.bfloat16)
+        for _ in range(3):
+            step.run()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step.run()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / iters
+        out[key] = {"ms_per_image": ms, "value": 1e3 / ms, "launches_of_ours": step.launches_per_step}
+        del step, m
+        torch.cuda.empty_cache()
+    return out
+
+
 def synthetic_targets(seed, B, lo=20, hi=100):
     """VisDrone-shaped ground truth: n ~ U{20..100} small boxes per image, 10 classes."""
     g = torch.Generator().manual_seed(seed)
@@ -508,6 +538,11 @@ def main():
                 torch.cuda.empty_cache()
             except Exception as e:
                 line["with_vss"] = {"error": str(e)[:200]}
+        if ws == 1:
+            try:        # BASELINE.json configs[4]: inference at 1280x1280, 900 queries, one image per GPU-iteration
+                line["infer_1280"] = infer_config5(dev)
+            except Exception as e:
+                line["infer_1280"] = {"error": str(e)[:200]}
         if ws == 1:
             try:
                 line["roofline_tensor"] = gate_conv_roofline(dev)
