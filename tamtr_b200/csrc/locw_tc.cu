@@ -1,15 +1,18 @@
 // Kernel 3, fused: the two query projections of MSDeformAttn AND their epilogue in one tcgen05 kernel (bf16 operands).
 //
 // Replaces /root/reference ultralytics/nn/modules/transformer.py:278-293 for 16-bit activations:
-//   raw  = query [M, C] x W_cat^T [C, 3*H*S]      sampling_offsets and attention_weights Linears (they share their input)
+//   raw  = query [M, C] x W^T [C, 3*H*S]          sampling_offsets and attention_weights Linears (they share their input)
 //   attn = softmax over the S = L*P logits of each (query, head);  loc = ref_xy + (off + b) / P * ref_wh * 0.5
-// The unfused path (library GEMM -> [M, 3*H*S] fp32 in HBM -> locw_fwd_kernel) moves the GEMM result through memory
-// twice and spends 17 us in a thread-per-(query, head) epilogue with scalar strided accesses.  Here one CTA owns 128
-// queries: warp 0 streams the query tile and the whole weight matrix through a shared-memory ring with TMA
-// (SWIZZLE_128B, K-major both), warp 1 issues tcgen05.mma (M = 128, N = 3*H*S split into chunks <= 256, K = 16) into
-// TMEM, and warps 2-5 read each query's row straight out of TMEM (tcgen05.ld: one TMEM lane = one query), apply bias,
-// softmax and the location arithmetic with the reference's op order and per-op rounding, and write loc / attn as
-// 16-byte stores.  `raw` is written only when the caller needs it (reference-box gradients).
+// The unfused path (library GEMM -> [M, 3*H*S] fp32 in HBM -> locw_fwd_kernel, plus two torch.cat of the weights and
+// biases) moves the GEMM result through memory twice.  Here one CTA owns 128 queries and Hc of the H heads (the heads of a
+// query tile are split over up to 4 CTAs so that the launch covers the SMs: a CTA's TMA ingest bounds the main loop):
+//   warp 0      streams the query tile and the heads' weight rows through a shared-memory ring with TMA (SWIZZLE_128B,
+//               K-major both); sampling_offsets.weight and attention_weights.weight are read where they are (two maps)
+//   warp 1      issues tcgen05.mma (M = 128, N = 3*Hc*S in chunks <= 256, K = 16) into TMEM
+//   warps 2-17  epilogue, 4 warps per TMEM lane quarter, one head at a time each: tcgen05.ld of the query's row (one TMEM
+//               lane = one query), bias, softmax, location arithmetic with the reference's op order and per-op rounding,
+//               16-byte stores of loc / attn
+// `raw` is written only when the caller needs it (reference-box gradients).
 #include "tc_ptx.cuh"
 
 namespace tamtr {

@@ -14,10 +14,11 @@
 // bound; splitting the states over lanes quadruples the resident warps.)  Tiles of u / delta / dy are staged through
 // shared memory with coalesced row reads (L is the contiguous dimension; softplus is applied once per element while
 // staging) and read back as conflict-free broadcasts (pitch 33); the B / C rows of the group are staged once per tile.
-// The bound is the SFU: 16 exp per position and channel.  The forward also writes the state every 32 positions; the
-// backward walks the segments in reverse, recomputes the states of a segment from its checkpoint (sub-checkpoints every
-// 4 positions in shared memory, the 4 positions in registers) and accumulates dB / dC across the CTA's channels with a
-// warp transpose-reduction before one shared-memory reduction per warp and value.
+// The nominal bound is the SFU (16 exp per position and channel); in practice issue slots and shared-memory wavefronts
+// (DESIGN.md).  The forward also writes the state every 16 positions; the backward walks these segments in reverse,
+// recomputes the states of a segment from its checkpoint (sub-checkpoints every 4 positions in shared memory, the 4 positions
+// in registers) and reduces dB / dC over a warp's channels with a transpose-reduction into a per-warp slot; the CTA's four
+// slots are added into global memory once per (state, position).  Inference on small grids: chunk-parallel forward (MODE 1/2).
 #include "common.cuh"
 
 namespace tamtr {
@@ -196,24 +197,24 @@ sscan_fwd_kernel(const void *__restrict__ u_, const void *__restrict__ dt_, cons
         // FFMA chain on h
 #pragma unroll
         for (int sgm = 0; sgm < kScT / kScSeg; ++sgm) {
-        if (ck != nullptr && t0 + sgm * kScSeg < L)         // state BEFORE the segment's first position
-            *reinterpret_cast<float4 *>(ck + (size_t)(t0 / kScSeg + sgm) * kScN) = make_float4(h[0], h[1], h[2], h[3]);
+            if (ck != nullptr && t0 + sgm * kScSeg < L)         // state BEFORE the segment's first position
+                *reinterpret_cast<float4 *>(ck + (size_t)(t0 / kScSeg + sgm) * kScN) = make_float4(h[0], h[1], h[2], h[3]);
 #pragma unroll 8
-        for (int t = sgm * kScSeg; t < (sgm + 1) * kScSeg; ++t) {
-            const float2 ud = s_ud[BF16 ? 0 : buf][c][t];
-            const float4 b4 = *reinterpret_cast<const float4 *>(&s_b[buf][t][n0]);
-            const float du = ud.y * ud.x;
-            h[0] = fmaf(ex2(ud.y * a2[0]), h[0], du * b4.x);
-            h[1] = fmaf(ex2(ud.y * a2[1]), h[1], du * b4.y);
-            h[2] = fmaf(ex2(ud.y * a2[2]), h[2], du * b4.z);
-            h[3] = fmaf(ex2(ud.y * a2[3]), h[3], du * b4.w);
-            if constexpr (MODE == 1) {
-                sum_delta += ud.y;
-            } else {
-                const float4 c4 = *reinterpret_cast<const float4 *>(&s_c[buf][t][n0]);
-                s_yp[threadIdx.x][t] = fmaf(c4.x, h[0], fmaf(c4.y, h[1], fmaf(c4.z, h[2], fmaf(c4.w, h[3], dsk * ud.x))));
+            for (int t = sgm * kScSeg; t < (sgm + 1) * kScSeg; ++t) {
+                const float2 ud = s_ud[BF16 ? 0 : buf][c][t];
+                const float4 b4 = *reinterpret_cast<const float4 *>(&s_b[buf][t][n0]);
+                const float du = ud.y * ud.x;
+                h[0] = fmaf(ex2(ud.y * a2[0]), h[0], du * b4.x);
+                h[1] = fmaf(ex2(ud.y * a2[1]), h[1], du * b4.y);
+                h[2] = fmaf(ex2(ud.y * a2[2]), h[2], du * b4.z);
+                h[3] = fmaf(ex2(ud.y * a2[3]), h[3], du * b4.w);
+                if constexpr (MODE == 1) {
+                    sum_delta += ud.y;
+                } else {
+                    const float4 c4 = *reinterpret_cast<const float4 *>(&s_c[buf][t][n0]);
+                    s_yp[threadIdx.x][t] = fmaf(c4.x, h[0], fmaf(c4.y, h[1], fmaf(c4.z, h[2], fmaf(c4.w, h[3], dsk * ud.x))));
+                }
             }
-        }
         }
         __syncthreads();
         if constexpr (MODE != 1) {
