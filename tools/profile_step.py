@@ -15,7 +15,7 @@ torch.manual_seed(1234)
 model = ManbaWorldDecoder(bench.NC, list(bench.CH), bench.HD, bench.NQ, bench.NDP, bench.NH, bench.NDL, vss=False).to(dev).train()
 xs, text = bench.synthetic_inputs(1234, bench.BATCH_PER_GPU, torch.bfloat16)
 plan = model.plan_cdn(bench.synthetic_targets(1234, bench.BATCH_PER_GPU))
-step = dp.HeadTrainStep(model, bench.loss_fn, (xs, text, plan), autocast=torch.bfloat16, use_graph=not args.eager)
+step = dp.HeadTrainStep(model, bench.surrogate_loss_fn, (xs, text, plan), autocast=torch.bfloat16, use_graph=not args.eager)
 for _ in range(3): step.run()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
