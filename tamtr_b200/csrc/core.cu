@@ -22,9 +22,16 @@ void set_error(const char *fmt, ...) {
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
+    static std::atomic<int> cache[64];        // per device id; 0 = not queried yet
     int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return n;
+    if (dev >= 0 && dev < 64) {
+        const int hit = cache[dev].load(std::memory_order_relaxed);
+        if (hit > 0) return hit;
+    }
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+    return n;
 }
 
 // ---- per-kernel CUDA-event timing (bench.py's roofline numbers): events are recorded on the launching stream,

@@ -372,8 +372,7 @@ __global__ void msda_corners_kernel(const float *__restrict__ loc, int32_t *__re
 // Persistent launch: one wave of `ctas_per_sm` CTAs per SM (or fewer when there is less work); every warp then walks
 // items qh, qh + grid*8, ... so that the prefetch of the next item overlaps the gather of the current one.
 static int persistent_grid(long total, int ctas_per_sm) {
-    static int n_sm = 0;
-    if (n_sm == 0 && cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess) n_sm = 148;
+    const int n_sm = sm_count();   // of the CURRENT device (a cached count of device 0 mis-sizes the grid elsewhere)
     const long need = (total + kWarpsPerCta - 1) / kWarpsPerCta;
     const long wave = (long)n_sm * ctas_per_sm;
     return (int)(need < wave ? need : wave);
