@@ -90,33 +90,83 @@ def gate_conv_roofline(dev, iters=20):
             "workload": "BTA-PAN text-guided 3x3 projection + BN + gate, B=16 C=256 80x80 (6400 tokens) N=10, bf16"}
 
 
-def infer_config5(dev, iters=20):
-    """Eval-mode forward of the MEH head at BASELINE.json configs[4] (1280x1280: levels 320^2/160^2/80^2, 900 queries,
-    batch 1 per GPU-iteration), bf16 autocast, replayed as one CUDA graph (dp.HeadInferStep); VSSBlocks identity / on."""
+def infer_config5(dev, rank=0, ws=1, n_images=64):
+    """BASELINE.json configs[4]: eval-mode forward of the MEH head at 1280x1280 (levels 320^2/160^2/80^2 = 134 400 tokens,
+    900 queries), `n_images` images SHARDED BY IMAGE over the ranks (dp.shard_indices, no collective), one image per
+    GPU-iteration, bf16 autocast, each forward one CUDA-graph replay (dp.HeadInferStep); VSSBlocks identity / on.
+    Inputs resident (a rotating set of 4 distinct images per rank).  value = all images / max-over-ranks device time."""
+    import torch.distributed as dist
     from tamtr_b200 import dp
     from tamtr_b200.head import ManbaWorldDecoder
-    out = {"unit": "images/s per GPU", "workload": "MEH head eval forward, 1280x1280 (134 400 tokens), 900 queries, batch 1, "
-                                                   "bf16, CUDA graph; inputs resident"}
-    g = torch.Generator().manual_seed(99)
-    xs = [torch.randn(1, c, s, s, generator=g).bfloat16().to(dev) for c, s in zip(CH, (320, 160, 80))]
-    text = torch.nn.functional.normalize(torch.randn(1, NC, 512, generator=g), dim=-1).to(dev)
+    mine = list(dp.shard_indices(n_images, rank, ws))
+    out = {"unit": "images/s", "images": n_images, "images_this_rank": len(mine), "n_gpus": ws,
+           "workload": "MEH head eval forward, 1280x1280 (134 400 tokens), 900 queries, batch 1 per GPU-iteration, bf16, "
+                       "CUDA graph; images sharded across ranks, no collective; inputs resident"}
+    g = torch.Generator().manual_seed(99 + rank)
+    pool = [([torch.randn(1, c, s, s, generator=g).bfloat16().to(dev) for c, s in zip(CH, (320, 160, 80))],
+             torch.nn.functional.normalize(torch.randn(1, NC, 512, generator=g), dim=-1).to(dev)) for _ in range(4)]
     for key, vss in (("vss_identity", False), ("vss_on", True)):
         torch.manual_seed(1234)
         m = ManbaWorldDecoder(NC, list(CH), HD, 900, NDP, NH, NDL, vss=vss).to(dev).eval()
-        step = dp.HeadInferStep(m, (xs, text), autocast=torch.bfloat16)
-        for _ in range(3):
-            step.run()
+        step = dp.HeadInferStep(m, pool[0], autocast=torch.bfloat16)
+        for i in range(3):
+            step.run(pool[i % 4])
+        if ws > 1:
+            dist.barrier()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(iters):
-            step.run()
+        for i in range(len(mine)):
+            step.run(pool[i % 4])
         e1.record()
+        if ws > 1:
+            dist.barrier()
         torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1) / iters
-        out[key] = {"ms_per_image": ms, "value": 1e3 / ms, "launches_of_ours": step.launches_per_step}
+        sec = dp.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+        out[key] = {"value": n_images / sec, "ms_per_image_per_gpu": e0.elapsed_time(e1) / max(1, len(mine)),
+                    "launches_of_ours": step.launches_per_step}
         del step, m
         torch.cuda.empty_cache()
+    return out
+
+
+def config1_sbase(dev, cpu=True):
+    """BASELINE.json configs[0]: RTDETRDecoder(nc=10, ch=(256,256,256)) eval forward, batch 2, 640x640 input (levels
+    80^2/40^2/20^2, d=256, 8 heads, 4 points, 300 queries, 6 layers), fp32 -- the reference's own CPU-runnable case, on the
+    host cores (oracle port of the reference's op sequence) and on the GPU (our path, eager and as a CUDA graph)."""
+    from tamtr_b200 import dp
+    from tamtr_b200.head import RTDETRDecoder
+    torch.manual_seed(7)
+    m = RTDETRDecoder(nc=10, ch=(256, 256, 256)).eval()
+    g = torch.Generator().manual_seed(8)
+    xs = [torch.randn(2, 256, s, s, generator=g) for s in (80, 40, 20)]
+    out = {"workload": "RTDETRDecoder eval forward, B=2, 80^2/40^2/20^2, d=256, 300 queries, 6 layers, fp32", "unit": "images/s"}
+    if cpu:
+        from oracle import head_ref                     # CPU leg only
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        torch.set_num_threads(os.cpu_count() or 1)
+        ts = []
+        with torch.no_grad():
+            for i in range(4):
+                t0 = time.perf_counter()
+                head_ref.head(sd, "", xs, 300, 6, 8, training=False)
+                ts.append(time.perf_counter() - t0)
+        cpu_s = sorted(ts[1:])[len(ts[1:]) // 2]
+        out["cpu_port"] = {"ms": cpu_s * 1e3, "value": 2 / cpu_s, "cores": os.cpu_count() or 1,
+                           "kind": "port (oracle/head_ref.py: the reference's op sequence incl. F.grid_sample)"}
+    m = m.to(dev)
+    step = dp.HeadInferStep(m, (([x.to(dev) for x in xs]),), autocast=None)
+    for _ in range(3):
+        step.run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        step.run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 20
+    out["gpu_graph"] = {"ms": ms, "value": 2e3 / ms, "launches_of_ours": step.launches_per_step}
     return out
 
 
@@ -233,19 +283,20 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------- bytes
-def sampler_bytes(B, Lq, value_bytes=2, L=3, P=4):
-    """ALGORITHMIC bytes of one sampler launch (DESIGN.md 'Roofline accounting').
-    fwd: each value byte the gather needs, once (min(dense slab, gathered)) + fp32 loc/attn + output.
-    bwd: grad_out + the same value bytes + loc/attn read + grad_loc/grad_attn write + the dense grad_value written
-         once (its zero-fill is a separate memset node and is NOT counted here, nor timed in this kernel)."""
-    Lv = sum(s * s for s in SIZES)
-    d, Dh = HD, HD // NH
-    gathered = B * Lq * NH * L * P * 4 * Dh
-    val = min(B * Lv * d, gathered) * value_bytes
+def sampler_bytes(B, Lq, value_bytes=2, P=4, sizes=SIZES):
+    """ALGORITHMIC bytes of one sampler launch ('Kernel 1').
+    fwd: each value byte the gather needs, once -- min(dense slab, gathered bytes) PER LEVEL (taken over the whole
+         pyramid the min would count the small levels, whose slabs are re-read many times, as if every read were unique:
+         that inflated round 1's fraction above the real DRAM traffic) -- + fp32 loc/attn + output.
+    bwd: grad_out + the same value bytes + loc/attn read + grad_loc/grad_attn write + the touched part of grad_value
+         written once in the value dtype.  The zero-fill of the dense gradient arena is a separate memset node: it is NOT
+         in these bytes nor in the kernel's time, and is reported next to them as roofline.zero_fill."""
+    d, Dh, L = HD, HD // NH, len(sizes)
+    touched = sum(min(B * s * s * d, B * Lq * NH * P * 4 * Dh) for s in sizes)
     locw = B * Lq * NH * L * P * 3 * 4
     out = B * Lq * d * value_bytes
-    fwd = val + locw + out
-    bwd = out + val + 2 * locw + min(B * Lv * d, gathered) * value_bytes
+    fwd = touched * value_bytes + locw + out
+    bwd = out + touched * value_bytes + 2 * locw + touched * value_bytes
     return fwd, bwd
 
 
@@ -315,6 +366,37 @@ def config_dict(loss_kind="surrogate", vss=False):
 
 
 # ----------------------------------------------------------------------------------------------------- main arm
+class Stem(torch.nn.Module):
+    """Stand-in for the backbone + neck in front of the head (they are outside this path): uint8 images -> the bf16
+    pyramid maps the head takes, on the device -- three strided average pools and fixed 1x1 projections.  It exists so that
+    the end-to-end leg moves what a real pipeline moves over PCIe (19.7 MB of uint8 images per 16-image batch) instead of
+    184 MB of pre-computed feature maps; its few kernels are inside the e2e timed region."""
+
+    def __init__(self, dev):
+        super().__init__()
+        g = torch.Generator().manual_seed(5)
+        self.w = [(torch.randn(c, 3, 1, 1, generator=g) * 2.0).bfloat16().to(dev) for c in CH]
+        self.strides = [640 // s for s in SIZES]
+
+    @torch.no_grad()
+    def forward(self, img_u8, outs):
+        x = img_u8.to(torch.bfloat16).sub_(127.5).mul_(1.0 / 64.0)
+        for w, st, o in zip(self.w, self.strides, outs):
+            o.copy_(torch.nn.functional.conv2d(torch.nn.functional.avg_pool2d(x, st), w))
+        return outs
+
+
+def timed(dev, fn, n, barrier):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / 1e3
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -334,6 +416,16 @@ def main():
                          "default: the reference cannot run them without its un-vendored CUDA extension, so the reference "
                          "arm and the head-level parity fixtures are identity-VSS; with the default the VSS-on step is "
                          "also timed once and reported as `with_vss`.")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): 16 images per GPU.  strong: BASELINE.json configs[3] as worded -- global batch 64 "
+                         "split over the GPUs (64/32/16/8 per GPU at 1/2/4/8), RTDETRDetectionLoss, clip + AdamW step.  The "
+                         "default run also times the strong-scaling step and reports it as `config4_strong`.")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="infer: BASELINE.json configs[4] only (1280x1280 eval forward, images sharded over the GPUs)")
+    ap.add_argument("--buckets", type=int, default=4,
+                    help="N > 1: gradient buckets all-reduced from inside the captured step while the backward still runs "
+                         "(0: one all-reduce of the whole flat buffer after the step)")
+    ap.add_argument("--quick", action="store_true", help="main measurement only (no secondary fields, no CPU baseline)")
     ap.add_argument("--launch-list", action="store_true",
                     help="eager steps only (no e2e / instrumented pass / CPU baseline): the command to run under "
                          "`ncu --metrics gpu__time_duration.sum` for profiles/launches_*.csv")
@@ -366,33 +458,63 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
 
-    B = BATCH_PER_GPU
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    if args.mode == "infer":
+        res = infer_config5(dev, rank, ws)
+        if rank == 0:
+            v = res["vss_identity"]
+            print(json.dumps({"metric": "head eval images/sec @1280^2", "value": v["value"], "unit": "images/s", "n_gpus": ws,
+                              "steps": res["images"], "warmup": 3, "ms_per_step": 1e3 * ws / v["value"],
+                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                              "data": "synthetic", "config": {"workload": res["workload"], "vss_blocks": "identity"},
+                              "infer_1280": res}), file=_JSON_OUT, flush=True)
+        if ws > 1:
+            dist.destroy_process_group()
+        return
+
+    strong = args.scaling == "strong"
+    B = (64 // ws) if strong else BATCH_PER_GPU
+    loss_kind = "detection" if strong else args.loss
+    optimizer = dict(lr=1e-4, weight_decay=1e-4, max_norm=0.1) if strong else None
     torch.manual_seed(1234)                                # same initial weights on every rank (DDP broadcast equivalent)
     model = ManbaWorldDecoder(NC, list(CH), HD, NQ, NDP, NH, NDL, vss=args.vss).to(dev).train()
-    # two synthetic batches per rank in pinned host memory (bf16 activations, as a bf16 neck would hand them over)
-    host = []
+    if args.vss:
+        for blk in model.VSSBlocks:
+            blk.drop_path.drop_prob = 0.0                  # stochastic depth draws random numbers: not graph-replayable
+    # two synthetic batches per rank in pinned host memory: uint8 images (what a pipeline ships) and, for the secondary
+    # e2e variant, the bf16 pyramid maps themselves
+    host, host_img = [], []
     for j in range(2):
         xs, text = synthetic_inputs(1234 + rank * 7 + j, B, torch.bfloat16)
         host.append(([x.pin_memory() for x in xs], text.pin_memory()))
+        g = torch.Generator().manual_seed(4321 + rank * 7 + j)
+        host_img.append(torch.randint(0, 256, (B, 3, 640, 640), dtype=torch.uint8, generator=g).pin_memory())
     batch = synthetic_targets(1234 + rank, B)
     plan = model.plan_cdn(batch)
     Lq = plan.n_dn + NQ
 
-    loss_fn = make_detection_loss(batch, dev) if args.loss == "detection" else surrogate_loss_fn
-    step = dp.HeadTrainStep(model, loss_fn, (host[0][0], host[0][1], plan), autocast=torch.bfloat16,
-                            use_graph=not (args.no_graph or args.launch_list))
+    loss_fn = make_detection_loss(batch, dev) if loss_kind == "detection" else surrogate_loss_fn
+    try:
+        step = dp.HeadTrainStep(model, loss_fn, (host[0][0], host[0][1], plan), autocast=torch.bfloat16,
+                                use_graph=not (args.no_graph or args.launch_list), optimizer=optimizer, buckets=args.buckets)
+    except Exception as e:
+        if ws == 1 or not args.buckets:
+            raise
+        print(f"[bench] in-graph bucketed all-reduce failed ({type(e).__name__}: {str(e)[:200]}); falling back to one "
+              "all-reduce after the step", file=sys.stderr)
+        args.buckets = 0
+        step = dp.HeadTrainStep(model, loss_fn, (host[0][0], host[0][1], plan), autocast=torch.bfloat16,
+                                use_graph=not (args.no_graph or args.launch_list), optimizer=optimizer, buckets=0)
     if args.launch_list:
         for _ in range(args.warmup + args.steps):
             step.run()
         torch.cuda.synchronize(dev)
         print(json.dumps({"launch_list": True, "steps": args.steps, "warmup": args.warmup}), file=_JSON_OUT, flush=True)
         return
-    h2d = sum(x.numel() * x.element_size() for x in host[0][0]) + host[0][1].numel() * host[0][1].element_size()
-
-    def barrier():
-        if ws > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
 
     # ------------------------------------------------------------------ device-resident timing ("value")
     for _ in range(args.warmup):
@@ -401,41 +523,40 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _lib.launch_count()
-    e0.record()
-    for _ in range(args.steps):
-        step.run()
-    e1.record()
-    barrier()
-    sec = dp.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    sec = dp.max_over_ranks(timed(dev, step.run, args.steps, barrier), dev)
     clk = clocks.stop() if rank == 0 else None
     launches = (step.launches_per_step * args.steps) if step.graph is not None else (_lib.launch_count() - launches0)
     value = ws * B * args.steps / sec
 
     # ------------------------------------------------------------------ end to end from pinned host memory ("e2e")
     copy_stream = torch.cuda.Stream(dev)
-    staging = [([torch.empty_like(x, device=dev) for x in host[0][0]], torch.empty_like(host[0][1], device=dev))
-               for _ in range(2)]
+    stem = Stem(dev)
+    stage_img = [torch.empty_like(host_img[0], device=dev) for _ in range(2)]
+    stage_feat = [([torch.empty_like(x, device=dev) for x in host[0][0]], torch.empty_like(host[0][1], device=dev))
+                  for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_done = [torch.cuda.Event() for _ in range(2)]
 
-    def stage(i):
-        s = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[s])
-            for d, h in zip(staging[s][0], host[s][0]):
-                d.copy_(h, non_blocking=True)
-            staging[s][1].copy_(host[s][1], non_blocking=True)
-            ready[s].record(copy_stream)
-
-    def e2e_loop(n):
-        """Every step: H2D of its inputs (copy stream, overlapping the previous step), the step, D2H of its loss.  The host
-        reads step i's loss right after it has enqueued step i+1 (a training loop logging its loss does the same), so the
-        device is never idle waiting for the host; every step's loss is read."""
+    def e2e_loop(n, images):
+        """Every step: H2D of its inputs (copy stream, overlapping the previous step), [the stem,] the step, D2H of its loss.
+        The host reads step i's loss right after it has enqueued step i+1 (a training loop logging its loss does the same),
+        so the device is never idle waiting for the host; every step's loss is read."""
         cur = torch.cuda.current_stream(dev)
+
+        def stage(i):
+            s = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[s])
+                if images:
+                    stage_img[s].copy_(host_img[s], non_blocking=True)
+                else:
+                    for d, h in zip(stage_feat[s][0], host[s][0]):
+                        d.copy_(h, non_blocking=True)
+                stage_feat[s][1].copy_(host[s][1], non_blocking=True)
+                ready[s].record(copy_stream)
         for s in range(2):
             consumed[s].record(cur)
         stage(0)
@@ -445,7 +566,11 @@ def main():
             if i + 1 < n:
                 stage(i + 1)                       # next step's H2D overlaps this step's compute
             cur.wait_event(ready[s])
-            step.load_inputs((staging[s][0], staging[s][1], None))   # device->static-buffer copy (graph inputs)
+            if images:
+                stem(stage_img[s], step.static[0])                   # uint8 -> pyramid, straight into the step's inputs
+                step.static[1].copy_(stage_feat[s][1], non_blocking=True)
+            else:
+                step.load_inputs((stage_feat[s][0], stage_feat[s][1], None))
             consumed[s].record(cur)
             loss = step.run()
             loss_host[s].copy_(loss, non_blocking=True)
@@ -459,133 +584,193 @@ def main():
         assert len(losses) == n
         return losses
 
-    e2e_loop(args.warmup)
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    e2e_loop(args.steps)
-    t1.record()
-    barrier()
-    e2e_sec = dp.max_over_ranks(t0.elapsed_time(t1) / 1e3, dev)
-    e2e_value = ws * B * args.steps / e2e_sec
-    # the host->device link on its own (explains e2e when it, not the step, is the longer leg)
+    e2e = {}
+    for key, images in (("images", True), ("features", False)):
+        e2e_loop(args.warmup, images)
+        t = dp.max_over_ranks(timed(dev, lambda: e2e_loop(args.steps, images), 1, barrier), dev)
+        e2e[key] = {"value": ws * B * args.steps / t, "ms_per_step": t / args.steps * 1e3}
+    text_bytes = host[0][1].numel() * host[0][1].element_size()
+    h2d_img = host_img[0].numel() + text_bytes
+    h2d_feat = sum(x.numel() * x.element_size() for x in host[0][0]) + text_bytes
+    # the host->device link on its own (explains the features-from-host variant when it, not the step, is the longer leg)
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(copy_stream):
         c0.record(copy_stream)
         for _ in range(4):
-            for d, h in zip(staging[0][0], host[0][0]):
+            for d, h in zip(stage_feat[0][0], host[0][0]):
                 d.copy_(h, non_blocking=True)
         c1.record(copy_stream)
     copy_stream.synchronize()
-    h2d_gbs = 4 * sum(x.numel() * x.element_size() for x in host[0][0]) / (c0.elapsed_time(c1) / 1e3) / 1e9
+    h2d_gbs = 4 * (h2d_feat - text_bytes) / (c0.elapsed_time(c1) / 1e3) / 1e9
 
     # ------------------------------------------------------------------ per-kernel device times (instrumented pass)
-    kern = {}
-    if rank == 0:
+    kern, zero_fill = {}, None
+    if rank == 0 and not strong:
         _lib.profile_enable(True)
         graph, step.graph = step.graph, None       # eager pass over the same buffers: the library brackets each of
+        overlap, step.overlap = step.overlap, False
         for _ in range(args.steps):                # its launches with CUDA events on the launching stream
             step.run(reduce=False)
         torch.cuda.synchronize(dev)
-        step.graph = graph
+        step.graph, step.overlap = graph, overlap
         kern = _lib.profile_read()
         _lib.profile_enable(False)
+        # the memset node that zero-fills the dense value-gradient arena once per step (outside the sampler kernels)
+        arena = torch.empty(B, sum(x * x for x in SIZES), NDL * HD, dtype=torch.bfloat16, device=dev)
+        z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.zeros_like_fast(arena)
+        z0.record()
+        for _ in range(5):
+            _lib.lib().tamtr_memset_zero(arena.data_ptr(), arena.numel() * 2, _lib.stream_ptr(dev))
+        z1.record()
+        torch.cuda.synchronize(dev)
+        zero_fill = {"bytes_per_step": arena.numel() * 2, "us_per_step": z0.elapsed_time(z1) / 5 * 1e3,
+                     "note": "one cudaMemset node per step for the dense bf16 grad_value arena of all 3 layers; not in "
+                             "roofline.algorithmic_bytes, not in the sampler kernels' time"}
+        del arena
     barrier()
 
+    line = None
     if rank == 0:
         peak, peak_src = peaks()
         fwd_b, bwd_b = sampler_bytes(B, Lq)
         per_kernel = {k: {"avg_us": ms / n * 1e3, "launches_per_step": n / args.steps} for k, (ms, n) in kern.items()}
         bwd_us = per_kernel.get("msda_bwd", {}).get("avg_us")
         fwd_us = per_kernel.get("msda_fwd", {}).get("avg_us")
-        roof = {"bound": "hbm", "kernel": "msda_bwd_kernel<bf16,LPC=8,NS=12>", "achieved": bwd_b / (bwd_us * 1e3) if bwd_us else None,
-                "peak": peak, "unit": "GB/s", "frac": (bwd_b / (bwd_us * 1e3) / peak) if bwd_us else None,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": bwd_b, "avg_us": bwd_us,
-                "fwd": {"kernel": "msda_fwd_kernel<bf16,LPC=8,NS=12>", "achieved": fwd_b / (fwd_us * 1e3) if fwd_us else None,
-                        "frac": (fwd_b / (fwd_us * 1e3) / peak) if fwd_us else None, "algorithmic_bytes": fwd_b,
-                        "avg_us": fwd_us}}
+        traffic = {}
         ncu = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(ncu):
             try:
-                roof["traffic"] = json.load(open(ncu)).get("msda_bwd_dram_bytes_per_launch")
+                traffic = json.load(open(ncu))
             except Exception:
                 pass
+        roof = {"bound": "hbm", "kernel": "msda_bwd_kernel<bf16,bf16,LPC=8,NS=12>",
+                "achieved": bwd_b / (bwd_us * 1e3) if bwd_us else None, "peak": peak, "unit": "GB/s",
+                "frac": (bwd_b / (bwd_us * 1e3) / peak) if bwd_us else None,
+                "traffic": traffic.get("msda_bwd_dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+                "peak_source": peak_src, "algorithmic_bytes": bwd_b, "avg_us": bwd_us,
+                "bytes_note": "compulsory value traffic taken per level (DESIGN.md section 3); timed eager, cold caches "
+                              "between launches are not forced: the step's working set (> 1 GB) exceeds the 126 MB L2",
+                "zero_fill": zero_fill,
+                "fwd": {"kernel": "msda_fwd_kernel<bf16,LPC=8,NS=12>", "achieved": fwd_b / (fwd_us * 1e3) if fwd_us else None,
+                        "frac": (fwd_b / (fwd_us * 1e3) / peak) if fwd_us else None, "algorithmic_bytes": fwd_b,
+                        "avg_us": fwd_us, "traffic": traffic.get("msda_fwd_dram_bytes_per_launch")}}
+        cfg = dict(config_dict(loss_kind, args.vss), queries=Lq, cuda_graph=step.graph is not None, batch_per_gpu=B,
+                   parallelism=f"dp{ws}" if ws > 1 else "single", cpus_bound_to_gpu_numa_node=numa_cpus,
+                   optimizer="clip_grad_norm_(0.1) + AdamW inside the step (csrc/optim.cu)" if optimizer else "none",
+                   gradient_exchange=("none" if ws == 1 else
+                                      f"{len(step.flat.buckets)} buckets all-reduced (NCCL AVG) inside the captured step, "
+                                      "overlapping the backward" if step.overlap else "one all-reduce after the step"))
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": ws, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": dict(config_dict(args.loss, args.vss), queries=Lq, cuda_graph=step.graph is not None,
-                               parallelism=f"dp{ws}" if ws > 1 else "single", cpus_bound_to_gpu_numa_node=numa_cpus),
-                "clocks": clk,
-                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "ms_per_step": e2e_sec / args.steps * 1e3, "h2d_link_gbs_measured": h2d_gbs,
-                        "h2d_ms_per_step_at_link_rate": h2d / h2d_gbs / 1e6},
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": cfg, "clocks": clk,
+                "e2e": {"value": e2e["images"]["value"], "unit": "images/s", "h2d_bytes_per_step": h2d_img,
+                        "d2h_bytes_per_step": 4, "ms_per_step": e2e["images"]["ms_per_step"],
+                        "input": "uint8 images [B,3,640,640] + text embeddings from pinned host memory; an on-device "
+                                 "stand-in stem (3 average pools + 1x1 projections; the backbone / neck are outside this "
+                                 "path) turns them into the pyramid maps inside the timed region; loss read back every step",
+                        "features_from_host": {"value": e2e["features"]["value"], "ms_per_step": e2e["features"]["ms_per_step"],
+                                               "h2d_bytes_per_step": h2d_feat, "h2d_link_gbs_measured": h2d_gbs,
+                                               "h2d_ms_per_step_at_link_rate": h2d_feat / h2d_gbs / 1e6,
+                                               "note": "round 1's e2e: the bf16 pyramid maps themselves streamed from the "
+                                                       "host every step (an artefact of benchmarking the head alone)"}},
                 "gpu_launches": int(launches),
                 "roofline": roof, "kernels": per_kernel}
-        if ws == 1 and args.loss == "surrogate":
-            try:        # the same step with the reference's detection loss on top (device-side Hungarian matching)
-                step2 = dp.HeadTrainStep(model, make_detection_loss(batch, dev), (host[0][0], host[0][1], plan),
-                                         autocast=torch.bfloat16, use_graph=not args.no_graph)
-                for _ in range(args.warmup):
-                    step2.run()
-                torch.cuda.synchronize(dev)
-                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                d0.record()
-                for _ in range(args.steps):
-                    step2.run()
-                d1.record()
-                torch.cuda.synchronize(dev)
-                dsec = d0.elapsed_time(d1) / 1e3
-                line["with_detection_loss"] = {"value": B * args.steps / dsec, "unit": "images/s",
-                                               "ms_per_step": dsec / args.steps * 1e3, "loss": LOSS_NAMES["detection"],
-                                               "loss_value": float(step2.loss)}
-                del step2
-            except Exception as e:
-                line["with_detection_loss"] = {"error": str(e)[:200]}
-        if ws == 1 and not args.vss:
-            try:        # the same step with the three VSSBlocks running (head.py:1092-1098,1134)
+
+    # ------------------------------------------------------------------ secondary measurements
+    def second(fn_name, fn):
+        try:
+            return fn()
+        except Exception as e:          # the headline line must not depend on a secondary measurement
+            return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+    def time_step(st, n):
+        for _ in range(2):
+            st.run()
+        t = dp.max_over_ranks(timed(dev, st.run, n, barrier), dev)
+        return t
+
+    extra = {}
+    if not args.quick and not strong:
+        def c4():
+            B4 = 64 // ws
+            torch.manual_seed(1234)
+            m4 = ManbaWorldDecoder(NC, list(CH), HD, NQ, NDP, NH, NDL, vss=False).to(dev).train()
+            xs4, text4 = synthetic_inputs(555 + rank, B4, torch.bfloat16)
+            b4 = synthetic_targets(555 + rank, B4)
+            st = dp.HeadTrainStep(m4, make_detection_loss(b4, dev), (xs4, text4, m4.plan_cdn(b4)), autocast=torch.bfloat16,
+                                  use_graph=not args.no_graph, optimizer=dict(lr=1e-4, weight_decay=1e-4, max_norm=0.1),
+                                  buckets=args.buckets, warmup=2)
+            n = max(3, args.steps // 2)
+            t = time_step(st, n)
+            return {"value": 64 * n / t, "unit": "images/s", "ms_per_step": t / n * 1e3, "global_batch": 64,
+                    "batch_per_gpu": B4, "steps": n, "scaling": "strong",
+                    "workload": "BASELINE.json configs[3]: fixed global batch 64, RTDETRDetectionLoss (device-side Hungarian "
+                                "matching), clip_grad_norm_(0.1) + AdamW, gradient all-reduce; head only, VSS identity",
+                    "loss_value": float(st.loss)}
+        extra["config4_strong"] = second("config4_strong", c4)
+        torch.cuda.empty_cache()
+        extra["infer_1280"] = second("infer_1280", lambda: infer_config5(dev, rank, ws))
+        torch.cuda.empty_cache()
+
+    if rank == 0 and not args.quick and not strong and ws == 1:
+        if args.loss == "surrogate":
+            def det():      # the same step with the reference's detection loss on top (device-side Hungarian matching)
+                st = dp.HeadTrainStep(model, make_detection_loss(batch, dev), (host[0][0], host[0][1], plan),
+                                      autocast=torch.bfloat16, use_graph=not args.no_graph)
+                t = time_step(st, args.steps)
+                return {"value": B * args.steps / t, "unit": "images/s", "ms_per_step": t / args.steps * 1e3,
+                        "loss": LOSS_NAMES["detection"], "loss_value": float(st.loss)}
+            extra["with_detection_loss"] = second("with_detection_loss", det)
+        if not args.vss:
+            def vss_on():   # the same step with the three VSSBlocks running (head.py:1092-1098,1134)
                 torch.manual_seed(1234)
-                model_v = ManbaWorldDecoder(NC, list(CH), HD, NQ, NDP, NH, NDL, vss=True).to(dev).train()
-                for blk in model_v.VSSBlocks:
-                    blk.drop_path.drop_prob = 0.0            # stochastic depth draws random numbers: not graph-replayable
-                step3 = dp.HeadTrainStep(model_v, surrogate_loss_fn, (host[0][0], host[0][1], plan),
-                                         autocast=torch.bfloat16, use_graph=not args.no_graph, warmup=1)
+                mv = ManbaWorldDecoder(NC, list(CH), HD, NQ, NDP, NH, NDL, vss=True).to(dev).train()
+                for blk in mv.VSSBlocks:
+                    blk.drop_path.drop_prob = 0.0
+                st = dp.HeadTrainStep(mv, surrogate_loss_fn, (host[0][0], host[0][1], plan), autocast=torch.bfloat16,
+                                      use_graph=not args.no_graph, warmup=1)
                 nv = max(2, args.steps // 4)
-                step3.run()
-                torch.cuda.synchronize(dev)
-                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                v0.record()
-                for _ in range(nv):
-                    step3.run()
-                v1.record()
-                torch.cuda.synchronize(dev)
-                vsec = v0.elapsed_time(v1) / 1e3
-                line["with_vss"] = {"value": B * nv / vsec, "unit": "images/s", "ms_per_step": vsec / nv * 1e3, "steps": nv,
-                                    "note": "VSSBlocks on the selective-scan kernels (fp32 scan as vmamba.py:985 forces), "
-                                            "drop_path 0; parity for the scan: published recurrence (oracle) + forward cross-check against "
-                                            "vLLM's mamba_ssm kernel; the reference's own extension is not in its tree"}
-                del step3, model_v
-                torch.cuda.empty_cache()
-            except Exception as e:
-                line["with_vss"] = {"error": str(e)[:200]}
-        if ws == 1:
-            try:        # BASELINE.json configs[4]: inference at 1280x1280, 900 queries, one image per GPU-iteration
-                line["infer_1280"] = infer_config5(dev)
-            except Exception as e:
-                line["infer_1280"] = {"error": str(e)[:200]}
-        if ws == 1:
-            try:
-                line["roofline_tensor"] = gate_conv_roofline(dev)
-                ncu = os.path.join(ROOT, "profiles", "traffic.json")
-                if os.path.exists(ncu):
-                    line["roofline_tensor"]["traffic"] = json.load(open(ncu)).get("gate_conv_dram_bytes_per_launch")
-            except Exception as e:      # the headline line must not depend on the secondary kernel
-                line["roofline_tensor"] = {"error": str(e)[:200]}
-        if not args.no_cpu_baseline and ws == 1:
+                t = time_step(st, nv)
+                return {"value": B * nv / t, "unit": "images/s", "ms_per_step": t / nv * 1e3, "steps": nv,
+                        "note": "VSSBlocks on the selective-scan kernels (fp32 scan as vmamba.py:985 forces), drop_path 0; "
+                                "parity for the scan: published recurrence (oracle, forward and backward) + cross-check "
+                                "against vLLM's mamba_ssm kernel; the reference's own extension is not in its tree"}
+            extra["with_vss"] = second("with_vss", vss_on)
+            torch.cuda.empty_cache()
+
+        def through_enable():
+            # the same step through the rebinding patch.enable() performs, on reference-shaped stand-ins (the reference
+            # itself does not travel to this box): tests/refshape.py
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import refshape
+            refshape.install_like_enable()
+            ref_like = refshape.RefMEH(model).to(dev).train()
+            st = dp.HeadTrainStep(ref_like, loss_fn, (host[0][0], host[0][1], plan), autocast=torch.bfloat16,
+                                  use_graph=not args.no_graph)
+            t = time_step(st, args.steps)
+            v = B * args.steps / t
+            return {"value": v, "unit": "images/s", "ms_per_step": t / args.steps * 1e3, "ratio_to_value": v / value,
+                    "launches_of_ours_per_step": st.launches_per_step, "value_launches_per_step": step.launches_per_step,
+                    "what": "reference-shaped stand-in classes (attributes of the reference's constructors only) with our "
+                            "functions bound exactly as tamtr_b200.enable() binds them onto the reference's classes"}
+        extra["through_enable"] = second("through_enable", through_enable)
+        extra["config1"] = second("config1", lambda: config1_sbase(dev, cpu=not args.no_cpu_baseline))
+
+        def tensor_roof():
+            r = gate_conv_roofline(dev)
+            r["traffic"] = traffic.get("gate_conv_dram_bytes_per_launch")
+            return r
+        extra["roofline_tensor"] = second("roofline_tensor", tensor_roof)
+        if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            ips, s = cpu_reference_step(2, cores, 2, 1, loss_kind=args.loss)
-            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": "2 images/step of the same workload (fp32 train fwd+bwd), 2 timed steps "
-                                              f"after 1 warm-up, torch CPU {cores} threads, {s:.1f} s/step"}
+            ips, s_ = cpu_reference_step(2, cores, 2, 1, loss_kind=args.loss)
+            extra["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                                     "sample": "2 images/step of the same workload (fp32 train fwd+bwd), 2 timed steps "
+                                               f"after 1 warm-up, torch CPU {cores} threads, {s_:.1f} s/step"}
+    if rank == 0:
+        line.update(extra)
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if ws > 1:
         dist.destroy_process_group()

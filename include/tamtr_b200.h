@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TAMTR_B200_ABI_VERSION 1
+#define TAMTR_B200_ABI_VERSION 2
 
 enum tamtr_dtype { TAMTR_F32 = 0, TAMTR_BF16 = 1 };
 
@@ -75,7 +75,10 @@ int tamtr_msda_forward(const void *value, const float *loc, const float *attn, v
 
 /* Backward of the above (what autograd derives for utils.py:42-89: grid_sampler_2d_backward + mul/sum).
  *   grad_out   [B, Lq, H*Dh]   same dtype as value
- *   grad_value [B, Lv, H, Dh]  same dtype and token stride as value; zeroed by this call when zero_grad_value != 0
+ *   grad_value [B, Lv, H, Dh]  grad_value_dtype: the value dtype, or TAMTR_F32 for bf16 values (fp32 accumulation of
+ *                              the scattered gradient: each atomic add then rounds at 2^-24 instead of 2^-9 of the
+ *                              running sum); same token stride (in elements) as value; zeroed by this call when
+ *                              zero_grad_value != 0
  *                              (otherwise the caller zeroed the whole strided buffer once for all layers), then
  *                              accumulated with vector atomics (REDG f32x4 / bf16x8) -> run-to-run bit differences,
  *                              like grid_sampler backward
@@ -87,7 +90,7 @@ int tamtr_msda_backward(const void *grad_out, const void *value, const float *lo
                         void *grad_value, float *grad_loc, float *grad_attn, int dtype,
                         int B, int Lv, int H, int Dh, int Lq, int L, int P,
                         const int32_t *level_shapes_host, int value_token_stride, int zero_grad_value,
-                        float *tap_weight_sum, void *stream);
+                        float *tap_weight_sum, int grad_value_dtype, void *stream);
 
 /* The same sampler with a different number of points on each level: the reference's "decoupled" cross-attention pair
  * multi_scale_deformable_attn_pytorch_cls (ultralytics/nn/modules/utils.py:92-140, points 2/4/6 on the three levels) and
@@ -104,7 +107,7 @@ int tamtr_msda_backward_ragged(const void *grad_out, const void *value, const fl
                                void *grad_value, float *grad_loc, float *grad_attn, int dtype,
                                int B, int Lv, int H, int Dh, int Lq, int L, const int32_t *points_host,
                                const int32_t *level_shapes_host, int value_token_stride, int zero_grad_value,
-                               float *tap_weight_sum, void *stream);
+                               float *tap_weight_sum, int grad_value_dtype, void *stream);
 int tamtr_msda_corners_ragged(const float *loc, int32_t *x0, int32_t *y0, uint8_t *inb, int B, int Lq, int H, int L,
                               const int32_t *points_host, const int32_t *level_shapes_host, void *stream);
 
@@ -344,6 +347,20 @@ int tamtr_dwconv3x3_silu_forward(const void *x, const float *weight, const float
                                  int H, int W, void *stream);
 int tamtr_dwconv3x3_silu_backward(const void *grad_y, const void *x, const float *weight, const float *bias, void *grad_x,
                                   float *grad_weight, float *grad_bias, int dtype, int Bn, int D, int H, int W, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Optimizer step on flat buffers: clip_grad_norm_(max_norm) + AdamW, the reference's optimizer_step
+ * (ultralytics/engine/trainer.py:471-477; parameter groups of build_optimizer, :654-677: weights with decay, biases
+ * and normalisation weights without).
+ *   param, grad, exp_avg, exp_avg_sq [n] f32 (n a multiple of 4); decay4 [n/4] uint8 or NULL: non-zero = the four
+ *   elements take weight decay (parameters start at multiples of 4); partial [tamtr_optim_partials(n)] f32 scratch;
+ *   step [1] f32 on the device: number of steps taken so far (incremented by the call)
+ *   max_norm <= 0: no clipping.  Same arithmetic as torch.optim.AdamW (decoupled decay, bias correction) with the global
+ *   gradient norm computed in a fixed order (deterministic).  No host synchronisation; CUDA-graph capturable. */
+int tamtr_optim_partials(long long n);
+int tamtr_adamw_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n,
+                     const unsigned char *decay4, float *partial, float *step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     float max_norm, void *stream);
 
 #ifdef __cplusplus
 }

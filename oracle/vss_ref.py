@@ -55,6 +55,36 @@ def selective_scan(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=Tr
     return y
 
 
+def selective_scan_closed_form(u, delta, A, B, C, D=None, delta_bias=None):
+    """The same map WITHOUT the recurrence: with S_t = sum_{r <= t} delta_r the state is
+        h_t = sum_{s <= t} exp(A * (S_t - S_s)) * delta_s * B_s * u_s
+    so  y_t = sum_n C_t[n] * sum_{s <= t} exp(A_n * (S_t - S_s)) * delta_s * B_s[n] * u_s + D * u_t,
+    evaluated as one masked [l, l] kernel per (b, channel, state) in fp64 (every exponent is <= 0: no overflow).  An
+    independent formulation -- a cumulative sum, an outer difference and a masked contraction instead of a loop over t --
+    whose autograd graph shares nothing with `selective_scan` above: the second opinion for the CUDA kernels' backward
+    (tests/test_vss_gpu.py) and for the recurrence restatement itself (tests/test_oracle_vss.py).  Small l only."""
+    b, kd, l = u.shape
+    k, n = B.shape[1], A.shape[1]
+    d = kd // k
+    f = torch.float64
+    dl = delta.to(f)
+    if delta_bias is not None:
+        dl = dl + delta_bias.to(f).view(1, kd, 1)
+    dl = torch.where(dl > 20.0, dl, torch.log1p(torch.exp(dl.clamp(max=20.0))))
+    S = torch.cumsum(dl, -1)                                                     # [b, kd, l]
+    diff = S.unsqueeze(-1) - S.unsqueeze(-2)                                     # [b, kd, t, s] = S_t - S_s
+    mask = torch.ones(l, l, dtype=torch.bool, device=u.device).tril()
+    decay = torch.exp(A.to(f).view(1, kd, n, 1, 1) * diff.unsqueeze(2)) * mask   # [b, kd, n, t, s]
+    Bx = B.to(f).view(b, k, 1, n, l).expand(b, k, d, n, l).reshape(b, kd, n, l)
+    Cx = C.to(f).view(b, k, 1, n, l).expand(b, k, d, n, l).reshape(b, kd, n, l)
+    src = (dl * u.to(f)).unsqueeze(2) * Bx                                       # [b, kd, n, s]
+    h = torch.einsum("bcnts,bcns->bcnt", decay, src)
+    y = (h * Cx).sum(2)
+    if D is not None:
+        y = y + D.to(f).view(1, kd, 1) * u.to(f)
+    return y
+
+
 def install_scan_extension(csms6s_module):
     """Give the reference's csms6s.py the extension object it failed to import (csms6s.py:121-126): fwd/bwd with the
     extension's call signature (csms6s.py:257,266), implemented by the restatement above + autograd."""

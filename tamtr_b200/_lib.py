@@ -30,11 +30,11 @@ _SIGNATURES = {
                                           ctypes.POINTER(ctypes.c_ulonglong)]),
     "tamtr_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),
     "tamtr_msda_forward": (ctypes.c_int, [_vp, _fp, _fp, _vp, _i] + [_i] * 7 + [_vp, _i, _vp]),
-    "tamtr_msda_backward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _i] + [_i] * 7 + [_vp, _i, _i, _fp, _vp]),
+    "tamtr_msda_backward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _i] + [_i] * 7 + [_vp, _i, _i, _fp, _i, _vp]),
     "tamtr_msda_corners": (ctypes.c_int, [_fp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp]),
     "tamtr_msda_forward_ragged": (ctypes.c_int, [_vp, _fp, _fp, _vp, _i] + [_i] * 6 + [_vp, _vp, _i, _vp]),
     "tamtr_msda_backward_ragged": (ctypes.c_int, [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _i] + [_i] * 6
-                                   + [_vp, _vp, _i, _i, _fp, _vp]),
+                                   + [_vp, _vp, _i, _i, _fp, _i, _vp]),
     "tamtr_msda_corners_ragged": (ctypes.c_int, [_fp, _vp, _vp, _vp] + [_i] * 4 + [_vp, _vp, _vp]),
     "tamtr_locw_forward": (ctypes.c_int, [_fp] * 5 + [_i] * 6 + [_vp, _vp]),
     "tamtr_locw_backward": (ctypes.c_int, [_fp] * 8 + [_i] * 6 + [_vp, _vp]),
@@ -70,6 +70,9 @@ _SIGNATURES = {
     "tamtr_selective_scan_forward_chunked": (ctypes.c_int, [_vp, _vp, _i] + [_fp] * 7 + [_i] * 6 + [_vp]),
     "tamtr_cross_scan": (ctypes.c_int, [_vp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_cross_merge": (ctypes.c_int, [_vp, _vp] + [_i] * 5 + [_vp]),
+    "tamtr_optim_partials": (ctypes.c_int, [ctypes.c_longlong]),
+    "tamtr_adamw_flat": (ctypes.c_int, [_fp, _fp, _fp, _fp, ctypes.c_longlong, _vp, _fp, _fp]
+                         + [ctypes.c_float] * 6 + [_vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }
 
@@ -99,7 +102,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args
-        if handle.tamtr_abi_version() != 1:
+        if handle.tamtr_abi_version() != 2:
             raise RuntimeError("tamtr_b200: ABI version mismatch between _lib.py and libtamtr_b200.so")
         _lib = handle
     return _lib

@@ -4,8 +4,12 @@ The reference trains with torch DDP: batch sharded by DistributedSampler, one bu
 gradients per backward (ultralytics/engine/trainer.py:241, 252; data/build.py:104).  The path shards by image with
 no data-path collective; the only exchange step is that gradient all-reduce.  B200-first restatement:
 
-* the gradients are packed into ONE flat fp32 buffer by a single multi-tensor copy at the end of the backward -> the
-  exchange is a single NCCL all-reduce over NVLink/NVSwitch, issued right after the backward;
+* the gradients live in ONE flat fp32 buffer cut into a few buckets in the order the backward finishes them (recorded
+  during warm-up); each bucket is packed by one multi-tensor copy and all-reduced (NCCL AVG over NVLink/NVSwitch) on a
+  communication stream AS SOON AS its last gradient exists, i.e. while the rest of the backward still runs -- from inside
+  the captured graph (fork/join through events), so a replay carries its own overlapped exchange;
+* parameters, gradients and the AdamW moments are flat fp32 buffers: the reference's optimizer step (clip_grad_norm_ 0.1
+  + AdamW, engine/trainer.py:471-477) is three launches of csrc/optim.cu at the end of the same graph;
 * forward + backward of the step are captured ONCE into a CUDA graph (static input buffers, the denoising group is
   planned on the host per batch exactly as the reference does and only its embedding gather is in the graph), so the
   ~1.5k small launches of the step cost one graph launch instead of Python/launch latency;
@@ -39,44 +43,73 @@ class FlatGrads:
     ~130 for the MEH head): the backward writes fresh .grad tensors, `gather()` packs them with one multi-tensor
     copy, and the exchange is a single all-reduce over the flat buffer."""
 
-    def __init__(self, params, dtype=torch.float32):
+    def __init__(self, params, dtype=torch.float32, pad_to=4, sources=None):
+        """`params`: in the order they are to be laid out; every parameter starts at a multiple of `pad_to` elements.
+        `sources`: parameter -> the tensor whose .grad receives its gradient (default: the parameter itself; the
+        training step back-propagates into low-precision leaf copies of the Linear weights)."""
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        self.src = [p if sources is None else sources.get(p, p) for p in self.params]
         dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=dtype, device=dev)
-        self.views = []
-        off = 0
+        self.offsets, off = [], 0
         for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            self.offsets.append(off)
+            off += (p.numel() + pad_to - 1) // pad_to * pad_to
+        self.flat = torch.zeros(off, dtype=dtype, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        self.buckets = [(0, len(self.params))]          # [first, last) parameter index of every bucket
 
-    def clear(self):
-        for p in self.params:
-            p.grad = None
+    def set_buckets(self, n_buckets):
+        """Cut the (already ordered) parameter list into `n_buckets` runs of about equal bytes."""
+        total = self.flat.numel()
+        cuts, first, acc = [], 0, 0
+        for i, p in enumerate(self.params):
+            acc += p.numel()
+            if acc >= total * (len(cuts) + 1) / n_buckets and len(cuts) < n_buckets - 1 and i + 1 < len(self.params):
+                cuts.append((first, i + 1))
+                first = i + 1
+        cuts.append((first, len(self.params)))
+        self.buckets = cuts
 
-    def gather(self):
-        """Pack the parameters' .grad tensors into the flat buffer (one fused multi-tensor copy)."""
+    def bucket_slice(self, b):
+        first, last = self.buckets[b]
+        end = self.flat.numel() if last == len(self.params) else self.offsets[last]
+        return self.flat[self.offsets[first]:end]
+
+    def pack_bucket(self, b):
+        first, last = self.buckets[b]
         dst, src = [], []
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
+        for t, v in zip(self.src[first:last], self.views[first:last]):
+            if t.grad is None:
                 v.zero_()
             else:
                 dst.append(v)
-                src.append(p.grad)
+                src.append(t.grad)
         if dst:
-            torch._foreach_copy_(dst, src)
+            torch._foreach_copy_(dst, src)          # (converts low-precision gradients to the buffer's fp32 on the way)
+
+    def clear(self):
+        for t in self.src:
+            t.grad = None
+
+    def gather(self):
+        """Pack all gradients into the flat buffer (one fused multi-tensor copy)."""
+        whole, self.buckets = self.buckets, [(0, len(self.params))]
+        self.pack_bucket(0)
+        self.buckets = whole
         return self.flat
 
-    def all_reduce_mean(self):
-        """One all-reduce (sum) + scale: the DDP semantics of trainer.py:241 (mean over ranks)."""
+    def all_reduce_mean(self, tensor=None):
+        """All-reduce (sum) + scale of the flat buffer or one bucket of it: the DDP semantics of trainer.py:241 (mean
+        over ranks)."""
+        t = self.flat if tensor is None else tensor
         rank, ws = world()
         if ws > 1:
             if dist.get_backend() == "nccl":
-                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)      # the division happens inside the collective
+                dist.all_reduce(t, op=dist.ReduceOp.AVG)              # the division happens inside the collective
             else:                                                     # gloo (CPU tests) has no AVG
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-                self.flat.div_(ws)
-        return self.flat
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                t.div_(ws)
+        return t
 
     def scatter(self):
         """Point every .grad at its (reduced) slice of the flat buffer, e.g. before an optimizer step."""
@@ -84,28 +117,78 @@ class FlatGrads:
             p.grad = v
 
 
-class _FusedParamCast(torch.autograd.Function):
-    """All low-precision weight copies of a step with ONE multi-tensor copy (and one more for their gradients).
+def decays(module):
+    """Parameter -> bool of the reference's optimizer groups (engine/trainer.py:654-662): weights get weight decay,
+    anything with 'bias' in its name and the weights of normalisation layers do not."""
+    norm = tuple(v for k, v in torch.nn.__dict__.items() if "Norm" in k and isinstance(v, type))
+    out = {}
+    for mname, m in module.named_modules():
+        for pname, p in m.named_parameters(recurse=False):
+            full = f"{mname}.{pname}" if mname else pname
+            out[p] = not ("bias" in full or isinstance(m, norm))
+    return out
+
+
+class FlatAdamW:
+    """clip_grad_norm_(max_norm) + AdamW (engine/trainer.py:471-477) over flat fp32 buffers.
+
+    The parameters of `flat_grads` are MOVED into one flat buffer laid out like the gradient buffer (p.data becomes a
+    view), so that the step is tamtr_adamw_flat: one pass for the global gradient norm, one pass that clips and updates
+    parameters and both moments, a device-side step counter -- three launches, no host synchronisation (CUDA only)."""
+
+    def __init__(self, flat_grads, decay_flags, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_norm=0.1):
+        """decay_flags: one bool per parameter of `flat_grads` (weight decay applies to it or not)."""
+        from . import _lib
+        self.g = flat_grads
+        self.hyper = (float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), float(max_norm))
+        dev = self.g.flat.device
+        self.param = torch.zeros_like(self.g.flat)
+        with torch.no_grad():
+            for p, o in zip(self.g.params, self.g.offsets):
+                v = self.param[o:o + p.numel()].view_as(p)
+                v.copy_(p.data)
+                p.data = v
+        # one byte per group of four elements (every parameter starts at a multiple of four)
+        self.decay4 = torch.zeros(self.param.numel() // 4, dtype=torch.uint8, device=dev)
+        for p, o, d in zip(self.g.params, self.g.offsets, decay_flags):
+            if d:
+                self.decay4[o // 4:(o + p.numel() + 3) // 4] = 1
+        self.exp_avg = torch.zeros_like(self.param)
+        self.exp_avg_sq = torch.zeros_like(self.param)
+        self.step_count = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.partial = torch.empty(_lib.lib().tamtr_optim_partials(self.param.numel()), dtype=torch.float32, device=dev)
+
+    def step(self):
+        from . import _lib
+        lr, b1, b2, eps, wd, mx = self.hyper
+        with torch.cuda.device(self.param.device):
+            rc = _lib.lib().tamtr_adamw_flat(self.param.data_ptr(), self.g.flat.data_ptr(), self.exp_avg.data_ptr(),
+                                            self.exp_avg_sq.data_ptr(), self.param.numel(), self.decay4.data_ptr(),
+                                            self.partial.data_ptr(), self.step_count.data_ptr(), lr, b1, b2, eps, wd, mx,
+                                            _lib.stream_ptr(self.param.device))
+        _lib.check(rc, "adamw_flat")
+
+
+class LowpLeaves:
+    """Low-precision working copies of the parameters autocast would cast on every use, as LEAF tensors.
 
     Under autocast every nn.Linear casts its fp32 weight and bias to bf16 on use and autograd casts the gradients
-    back: ~180 tiny launches per step for the MEH head.  The values are identical (same round-to-nearest cast)."""
+    back: ~180 tiny launches per step for the MEH head.  Here the copies are refreshed by ONE multi-tensor copy at the
+    start of a step (same round-to-nearest values) and the module is called on them; being leaves, each receives its
+    gradient the moment the backward has finished it -- which is what lets a gradient bucket leave for its all-reduce
+    while the rest of the backward is still running -- and FlatGrads converts it to fp32 while packing."""
 
-    @staticmethod
-    def forward(ctx, dtype, *params):
-        outs = [torch.empty_like(p, dtype=dtype) for p in params]
-        torch._foreach_copy_(outs, list(params))
-        ctx.src = [(p.dtype, p.shape, p.device) for p in params]
-        ctx.set_materialize_grads(False)
-        return tuple(outs)
+    def __init__(self, module, names, dtype):
+        named = dict(module.named_parameters())
+        self.names = [n for n in names if named[n].requires_grad]
+        self.params = [named[n] for n in self.names]
+        self.leaves = [torch.empty_like(p, dtype=dtype).requires_grad_() for p in self.params]
+        self.source_of = dict(zip(self.params, self.leaves))
 
-    @staticmethod
-    def backward(ctx, *grads):
-        outs = [None if g is None else torch.empty(shape, dtype=dt, device=dev)
-                for g, (dt, shape, dev) in zip(grads, ctx.src)]
-        dst = [o for o in outs if o is not None]
-        if dst:
-            torch._foreach_copy_(dst, [g for g in grads if g is not None])
-        return (None, *outs)
+    def refresh(self):
+        with torch.no_grad():
+            torch._foreach_copy_(self.leaves, [p.detach() for p in self.params])
+        return dict(zip(self.names, self.leaves))
 
 
 def lowp_param_names(module):
@@ -120,28 +203,56 @@ def lowp_param_names(module):
 
 
 class HeadTrainStep:
-    """forward + backward (+ all-reduce) of a detection head on static buffers.
+    """forward + backward (+ overlapped gradient exchange, + optimizer step) of a detection head on static buffers.
 
     module     : tamtr_b200.head.ManbaWorldDecoder / RTDETRDecoder (train mode), or any module for the CPU tests
     loss_fn    : maps the module's outputs to a scalar
     example    : tuple of example inputs (tensors / CdnPlan / None) fixing every shape
     autocast   : torch dtype or None
-    use_graph  : capture forward+backward into a CUDA graph (CUDA only).  As for any whole-network capture, eager
+    use_graph  : capture the step into a CUDA graph (CUDA only).  As for any whole-network capture, eager
                  forward/backward passes of the SAME module instance done earlier in the process must have run on a
                  side stream (autograd's gradient accumulators remember the stream of their first use); the warm-up
                  here does.
+    optimizer  : None, or a dict of FlatAdamW arguments (lr, betas, eps, weight_decay, max_norm): the reference's
+                 optimizer_step at the end of every step (inside the graph)
+    buckets    : world_size > 1 on CUDA: number of gradient buckets all-reduced from inside the step while the backward
+                 is still running (0: one all-reduce of the whole buffer after the step, round 1's behaviour)
     """
 
-    def __init__(self, module, loss_fn, example, autocast=None, use_graph=True, warmup=3, fused_param_cast=True):
+    def __init__(self, module, loss_fn, example, autocast=None, use_graph=True, warmup=3, fused_param_cast=True,
+                 optimizer=None, buckets=4):
         self.module, self.loss_fn, self.autocast = module, loss_fn, autocast
-        self.cast_names = lowp_param_names(module) if (fused_param_cast and autocast is not None) else []
-        self.flat = FlatGrads(module.parameters())
-        self.pack_grads = world()[1] > 1 or not use_graph     # single process: gradients can stay where autograd put them
-        self.device = self.flat.flat.device
+        self.lowp = LowpLeaves(module, lowp_param_names(module), autocast) \
+            if (fused_param_cast and autocast is not None) else None
+        sources = {} if self.lowp is None else self.lowp.source_of
+        params = [p for p in module.parameters() if p.requires_grad]
+        self.device = params[0].device
         self.cuda = self.device.type == "cuda"
         self.use_graph = use_graph and self.cuda
+        ws = world()[1]
+        self.overlap = bool(buckets) and ws > 1 and self.cuda
         self.static = [self._to_static(a) for a in example]
         self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.flat, self.opt, self._live = None, None, False
+        if self.overlap:
+            params = self._completion_order(params, sources)
+        self.flat = FlatGrads(params, sources=sources)
+        if self.overlap:
+            self.flat.set_buckets(int(buckets))
+            self.comm = torch.cuda.Stream(self.device)
+            self._bucket_of = {}
+            for b, (first, last) in enumerate(self.flat.buckets):
+                for t in self.flat.src[first:last]:
+                    self._bucket_of[t] = b
+            for t in self.flat.src:
+                t.register_post_accumulate_grad_hook(self._on_grad)
+        # a single process that keeps fp32 parameters all the way could leave the gradients where autograd put them
+        self.pack_grads = ws > 1 or not self.use_graph or optimizer is not None or self.lowp is not None
+        if optimizer is not None:
+            if not self.cuda:
+                raise RuntimeError("tamtr_b200: the flat AdamW step is a CUDA kernel (Not implemented on the CPU; is_cuda)")
+            dec = decays(module)
+            self.opt = FlatAdamW(self.flat, [dec.get(p, True) for p in self.flat.params], **optimizer)
         self.graph = None
         self.launches_per_step = None
         if self.use_graph:
@@ -156,14 +267,50 @@ class HeadTrainStep:
             return a.to(self.device)
         return a
 
-    def _fwd_bwd(self):
-        self.flat.clear()
+    # ---- gradient buckets -------------------------------------------------------------------------------------------
+    def _completion_order(self, params, sources):
+        """One eager backward on a side stream that records the order in which the parameters' gradients are finished:
+        buckets cut along that order complete one after the other, the first long before the backward ends."""
+        order, handles = [], []
+        back = {sources.get(p, p): p for p in params}
+        for t in back:
+            handles.append(t.register_post_accumulate_grad_hook(lambda q: order.append(back[q])))
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self._forward_backward()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        for h in handles:
+            h.remove()
+        seen = set(order)
+        for t in back:
+            t.grad = None
+        return order + [p for p in params if p not in seen]      # parameters without a gradient go last
+
+    def _on_grad(self, t):
+        if not self._live:
+            return
+        b = self._bucket_of[t]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._launch_bucket(b)
+
+    def _launch_bucket(self, b):
+        """Pack bucket b on the stream the backward is running on, then all-reduce it on the communication stream
+        (fork through an event: under capture this becomes a parallel branch of the graph)."""
+        self._launched.add(b)
+        self.flat.pack_bucket(b)
+        self.comm.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.comm):
+            self.flat.all_reduce_mean(self.flat.bucket_slice(b))
+
+    # ---- the step ---------------------------------------------------------------------------------------------------
+    def _forward_backward(self):
         if self.autocast is not None:
             with torch.autocast(self.device.type, dtype=self.autocast):
-                if self.cast_names:
-                    named = dict(self.module.named_parameters())
-                    lowp = _FusedParamCast.apply(self.autocast, *[named[n] for n in self.cast_names])
-                    out = torch.func.functional_call(self.module, dict(zip(self.cast_names, lowp)), tuple(self.static))
+                if self.lowp is not None:
+                    out = torch.func.functional_call(self.module, self.lowp.refresh(), tuple(self.static))
                 else:
                     out = self.module(*self.static)
         else:
@@ -171,8 +318,26 @@ class HeadTrainStep:
         loss = self.loss_fn(out)
         loss.backward()
         self.loss.copy_(loss.detach())
-        if self.pack_grads:
+
+    def _fwd_bwd(self):
+        if self.flat is not None:
+            self.flat.clear()
+        if self.overlap:
+            self._pending = [last - first for first, last in self.flat.buckets]
+            self._launched, self._live = set(), True
+        try:
+            self._forward_backward()
+        finally:
+            self._live = False
+        if self.overlap:
+            for b in range(len(self.flat.buckets)):             # buckets holding a parameter that received no gradient
+                if b not in self._launched:
+                    self._launch_bucket(b)
+            torch.cuda.current_stream(self.device).wait_stream(self.comm)      # join
+        elif self.pack_grads:
             self.flat.gather()
+        if self.opt is not None and (self.overlap or world()[1] == 1):
+            self.opt.step()                                     # (otherwise after the all-reduce, in run())
 
     def _capture(self, warmup):
         from . import _lib
@@ -191,13 +356,22 @@ class HeadTrainStep:
         torch.cuda.synchronize(self.device)
 
     def load_inputs(self, inputs, non_blocking=True):
-        """Copy a new batch (same shapes) into the static buffers."""
+        """Copy a new batch (same shapes) into the static buffers.  Entries that are not tensors -- a CdnPlan carries
+        the batch's denoising queries, their attention mask and counts -- are baked into a captured graph and CANNOT be
+        replaced here: pass None for them to keep the captured ones, or build a new step (dp.StepCache does so per
+        query-count bucket)."""
         def cp(dst, src):
             if isinstance(dst, torch.Tensor):
                 dst.copy_(src, non_blocking=non_blocking)
             elif isinstance(dst, (list, tuple)):
                 for d, s in zip(dst, src):
                     cp(d, s)
+            elif src is not None and src is not dst:
+                if hasattr(dst, "load"):
+                    dst.load(src, non_blocking=non_blocking)        # in-place update of a padded plan's device tensors
+                else:
+                    raise RuntimeError(f"tamtr_b200: static argument of type {type(dst).__name__} cannot be updated in a "
+                                       "captured step; pass None to keep it or build a new HeadTrainStep")
         for d, s in zip(self.static, inputs):
             cp(d, s)
 
@@ -207,8 +381,10 @@ class HeadTrainStep:
             self.graph.replay()
         else:
             self._fwd_bwd()
-        if reduce and self.pack_grads:
+        if reduce and self.pack_grads and not self.overlap and world()[1] > 1:
             self.flat.all_reduce_mean()
+            if self.opt is not None:
+                self.opt.step()
         return self.loss
 
 

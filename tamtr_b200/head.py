@@ -353,7 +353,7 @@ class ManbaWorldDecoder(_HeadBase):
         self._reset_common()
 
     def forward(self, x, text, batch=None):
-        if self.vss:        # head.py:1134: channel-last in and out
+        if getattr(self, "vss", True):        # head.py:1134: channel-last in and out (reference instances: always)
             x = [blk(f.permute(0, 2, 3, 1)).permute(0, 3, 1, 2) for blk, f in zip(self.VSSBlocks, x)]
         feats, shapes, hub = self._encode(x)
         dn_embed, dn_bbox, attn_mask, dn_meta = self._cdn(batch)

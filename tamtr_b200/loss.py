@@ -356,6 +356,7 @@ class DETRLoss(nn.Module):
 
     def forward(self, pred_bboxes, pred_scores, batch, postfix='', **kwargs):
         """pred_bboxes [l, b, query, 4], pred_scores [l, b, query, nc] (or None); batch: cls / bboxes / gt_groups."""
+        _lib.require_cuda(pred_bboxes)
         self.device = pred_bboxes.device
         match_indices = kwargs.get('match_indices', None)
         gt_cls, gt_bboxes, gt_groups = batch['cls'], batch['bboxes'], batch['gt_groups']
@@ -384,8 +385,9 @@ class RTDETRDetectionLoss(DETRLoss):
     """loss.py:376-443: the detection loss plus the denoising loss on the CDN queries (fixed matches)."""
 
     def forward(self, preds, batch, dn_bboxes=None, dn_scores=None, dn_meta=None):
+        # (explicit DETRLoss.forward instead of super(): patch.enable() binds this function onto the reference's class)
         pred_bboxes, pred_scores = preds
-        total_loss = super().forward(pred_bboxes, pred_scores, batch)
+        total_loss = DETRLoss.forward(self, pred_bboxes, pred_scores, batch)
         if dn_meta is not None:
             dn_pos_idx, dn_num_group = dn_meta['dn_pos_idx'], dn_meta['dn_num_group']
             assert len(batch['gt_groups']) == len(dn_pos_idx)
@@ -393,12 +395,12 @@ class RTDETRDetectionLoss(DETRLoss):
             # host->device index copies, which would also break CUDA-graph capture)
             cached = dn_meta.get('_tamtr_dn_match')
             if cached is None or cached[0].device != dn_bboxes.device:
-                mi = self.get_dn_match_indices(dn_pos_idx, dn_num_group, batch['gt_groups'])
+                mi = RTDETRDetectionLoss.get_dn_match_indices(dn_pos_idx, dn_num_group, batch['gt_groups'])
                 dev = dn_bboxes.device
                 cached = (torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(mi)]).long().to(dev),
                           torch.cat([src for src, _ in mi]).long().to(dev), torch.cat([dst for _, dst in mi]).to(dev))
                 dn_meta['_tamtr_dn_match'] = cached
-            dn_loss = super().forward(dn_bboxes, dn_scores, batch, postfix='_dn', match_indices=cached)
+            dn_loss = DETRLoss.forward(self, dn_bboxes, dn_scores, batch, postfix='_dn', match_indices=cached)
             total_loss.update(dn_loss)
         else:
             total_loss.update({f'{k}_dn': torch.zeros((), device=self.device) for k in total_loss.keys()})

@@ -14,6 +14,7 @@ Reference classes mirrored (file:line under /root/reference/ultralytics):
   TextDeformableTransformerDecoder     nn/modules/transformer.py:835-891
   ContrastiveHeadMLP                   nn/modules/block.py:522-541
   MaxSigmoidAttnBlock                  nn/extra_modules/block.py:194-226
+  TIAGELAN                             nn/extra_modules/block.py:171-192
   inverse_sigmoid                      nn/modules/utils.py:34-39
 """
 import copy
@@ -27,7 +28,8 @@ from . import ops
 
 __all__ = ("MLP", "MSDeformAttn", "MSDeformAttncls", "MSDeformAttnbox", "DeformableTransformerDecoderLayer",
            "DecouplingDeformableTransformerDecoderLayer", "DeformableTransformerDecoder",
-           "TextDeformableTransformerDecoder", "ContrastiveHeadMLP", "MaxSigmoidAttnBlock", "inverse_sigmoid")
+           "TextDeformableTransformerDecoder", "ContrastiveHeadMLP", "MaxSigmoidAttnBlock", "TIAGELAN",
+           "inverse_sigmoid")
 
 
 def inverse_sigmoid(x, eps=1e-5):
@@ -381,17 +383,17 @@ class ContrastiveHeadMLP(nn.Module):
 
 
 class _ConvBN(nn.Module):
-    """ultralytics Conv(c1, c2, k, act=False) = Conv2d(bias=False) + BatchNorm2d, keys `conv.*` / `bn.*`
+    """ultralytics Conv(c1, c2, k, act=...) = Conv2d(bias=False) + BatchNorm2d (+ SiLU), keys `conv.*` / `bn.*`
     (nn/modules/conv.py:23-40)."""
 
-    def __init__(self, c1, c2, k):
+    def __init__(self, c1, c2, k, act=False):
         super().__init__()
         self.conv = nn.Conv2d(c1, c2, k, 1, k // 2, bias=False)
         self.bn = nn.BatchNorm2d(c2)
-        self.act = nn.Identity()
+        self.act = nn.SiLU() if act else nn.Identity()
 
     def forward(self, x):
-        return self.bn(self.conv(x))
+        return self.act(self.bn(self.conv(x)))
 
 
 class MaxSigmoidAttnBlock(nn.Module):
@@ -415,13 +417,101 @@ class MaxSigmoidAttnBlock(nn.Module):
         aw = ops.max_sigmoid_gate(embed, guide, self.bias, self.nh)          # [B, nh, H, W]
         aw = aw * self.scale
         pc = self.proj_conv
-        if ops.gate_conv3x3_supported(x, pc.conv.weight, self.nh):
-            bn = pc.bn
-            if not (self.training or torch.is_grad_enabled()) and bn.running_var is not None:
-                # inference: conv + folded BatchNorm + gate in one tensor-core kernel (channels-last output)
-                s, t = _folded_bn(self, bn)
-                return ops.gate_conv3x3(x, pc.conv.weight, s, t, aw, self.nh)
-            y = bn(ops.conv3x3_tc(x, pc.conv.weight))
-        else:
+        conv, bn = pc.conv, getattr(pc, "bn", None)
+        infer = not (self.training or torch.is_grad_enabled())
+        if not ops.gate_conv3x3_supported(x, conv.weight, self.nh):
             y = pc(x)
+        elif bn is None:
+            # after model.fuse() (nn/tasks.py:131-136): BatchNorm folded into `conv`, which now carries a bias, and the
+            # `bn` attribute deleted -> scale 1, shift = that bias
+            shift = conv.bias if conv.bias is not None else torch.zeros(conv.out_channels, device=x.device)
+            if infer:
+                return ops.gate_conv3x3(x, conv.weight, torch.ones_like(shift, dtype=torch.float32), shift, aw, self.nh)
+            y = ops.conv3x3_tc(x, conv.weight) + shift.view(1, -1, 1, 1).to(x.dtype)
+        elif conv.bias is not None:
+            y = pc(x)
+        elif infer and bn.running_var is not None:
+            # inference: conv + folded BatchNorm + gate in one tensor-core kernel (channels-last output)
+            s, t = _folded_bn(self, bn)
+            return ops.gate_conv3x3(x, conv.weight, s, t, aw, self.nh)
+        else:
+            y = bn(ops.conv3x3_tc(x, conv.weight))
         return (y.view(bs, self.nh, -1, h, w) * aw.unsqueeze(2).to(y.dtype)).view(bs, -1, h, w)
+
+
+def _discarded_attn(attn, x):
+    """TIAGELAN calls `self.attn(y[-3], guide)` and DROPS the result (extra_modules/block.py:185), so the text-image
+    gate, the multiply and -- in eval mode -- the whole block are dead code.  What survives is the train-mode side
+    effect: the BatchNorm layers inside the block (`proj_conv.bn`, and `ec.bn` when c1 != ec) see a batch and update
+    their running statistics.  Reproduce exactly that, nothing else; no autograd graph (the reference builds one and
+    never back-propagates it: these parameters are the "unused" ones DDP is told about)."""
+    if not attn.training:
+        return
+    with torch.no_grad():
+        for unit in (attn.ec, attn.proj_conv):
+            bn = None if unit is None else getattr(unit, "bn", None)
+            if bn is None or not bn.track_running_stats:
+                continue
+            conv = unit.conv
+            if unit is attn.proj_conv and conv.bias is None and ops.gate_conv3x3_supported(x, conv.weight, 1):
+                bn(ops.conv3x3_tc(x, conv.weight))
+            else:
+                bn(conv(x))
+
+
+class _RepConvN(nn.Module):
+    """Training form of the reference's RepConvN (extra_modules/block.py:24-50): SiLU(conv3x3+BN + conv1x1+BN)."""
+
+    def __init__(self, c1, c2):
+        super().__init__()
+        self.conv1 = _ConvBN(c1, c2, 3)
+        self.conv2 = _ConvBN(c1, c2, 1)
+        self.act = nn.SiLU()
+
+    def forward(self, x):
+        return self.act(self.conv1(x) + self.conv2(x))
+
+
+class _RepNBottleneck(nn.Module):
+    def __init__(self, c):          # extra_modules/block.py:126-136 with c1 == c2, e = 1
+        super().__init__()
+        self.cv1 = _RepConvN(c, c)
+        self.cv2 = _ConvBN(c, c, 3, act=True)
+
+    def forward(self, x):
+        return x + self.cv2(self.cv1(x))
+
+
+class _RepNCSP(nn.Module):
+    def __init__(self, c1, c2, n=1):   # extra_modules/block.py:138-149
+        super().__init__()
+        c_ = c2 // 2
+        self.cv1 = _ConvBN(c1, c_, 1, act=True)
+        self.cv2 = _ConvBN(c1, c_, 1, act=True)
+        self.cv3 = _ConvBN(2 * c_, c2, 1, act=True)
+        self.m = nn.Sequential(*(_RepNBottleneck(c_) for _ in range(n)))
+
+    def forward(self, x):
+        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+
+
+class TIAGELAN(nn.Module):
+    """BTA-PAN stage (extra_modules/block.py:171-192): a CSP-ELAN block that also owns a MaxSigmoidAttnBlock whose
+    output it discards.  Same submodule names / state_dict keys as the reference; the convolutions around the attention
+    block are library calls (they are the neck, not this path).  forward(x [B,c1,H,W], guide [B,N,512]) -> [B,c2,H,W],
+    independent of `guide` (SURVEY.md KAT #4)."""
+
+    def __init__(self, c1, c2, c3, c4, c5=1, nh=8):
+        super().__init__()
+        self.c = c3 // 2
+        self.cv1 = _ConvBN(c1, c3, 1, act=True)
+        self.cv2 = nn.Sequential(_RepNCSP(c3 // 2, c4, c5), _ConvBN(c4, c4, 3, act=True))
+        self.cv3 = nn.Sequential(_RepNCSP(c4, c4, c5), _ConvBN(c4, c4, 3, act=True))
+        self.cv4 = _ConvBN(c3 + 2 * c4, c2, 1, act=True)
+        self.attn = MaxSigmoidAttnBlock(c4, c4, nh=nh, ec=c4)
+
+    def forward(self, x, guide):
+        y = list(self.cv1(x).chunk(2, 1))
+        y.extend(m(y[-1]) for m in (self.cv2, self.cv3))
+        _discarded_attn(self.attn, y[-3])
+        return self.cv4(torch.cat(y, 1))

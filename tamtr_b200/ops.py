@@ -27,6 +27,15 @@ def _value_layout(value):
     return value, H * Dh
 
 
+def _env_arena_dtype():
+    import os
+    v = os.environ.get("TAMTR_GRAD_ARENA", "").lower()
+    return torch.float32 if v in ("fp32", "f32", "float32") else None
+
+
+GRAD_ARENA_DTYPE = _env_arena_dtype()     # default gradient dtype of ValueArena (None = value dtype); TAMTR_GRAD_ARENA=fp32
+
+
 class ValueArena:
     """Shared gradient state for the value tensors of all decoder layers.
 
@@ -36,15 +45,32 @@ class ValueArena:
     dense gradient tensors and no gradient-accumulation passes over [B, Lv, d].  The bias gradient (column sums of
     that buffer) is assembled from the samplers' per-(query, head) tap-weight sums instead of re-reading it."""
 
-    def __init__(self):
+    def __init__(self, grad_dtype=None):
         self.buf = None
         self.base = None
         self.bias_grad = {}       # column offset of a layer's slice -> [d] fp32
+        self.written = set()      # column offsets whose sampler backward has run in this backward pass
+        # dtype of the gradient buffer: None = the value dtype (bf16 values -> bf16x8 vector reductions);
+        # torch.float32 = fp32 accumulation of the scattered gradient (f32x4 reductions, one cast pass before the GEMMs)
+        self.grad_dtype = grad_dtype if grad_dtype is not None else GRAD_ARENA_DTYPE
 
     def grad_buffer(self, like):
         if self.buf is None:
+            if self.grad_dtype is not None and self.grad_dtype != like.dtype:
+                like = torch.empty(like.shape, dtype=self.grad_dtype, device=like.device)
             self.buf = _lib.zeros_like_fast(like)
         return self.buf
+
+    def claim(self, col):
+        """Each layer's value view may feed ONE sampler per backward pass: its gradient is accumulated in place, so a
+        second consumer (or a second backward over a retained graph) would be added to a buffer autograd also sums."""
+        if self.base is None:
+            raise RuntimeError("tamtr_b200: the batched value projection was already back-propagated "
+                               "(retain_graph / a second backward is not supported on the shared gradient arena)")
+        if col in self.written:
+            raise RuntimeError("tamtr_b200: a projected value view was consumed by two samplers; each view returned by "
+                               "project_values() may be used once")
+        self.written.add(col)
 
 
 class _ValueProjFn(torch.autograd.Function):
@@ -72,6 +98,7 @@ class _ValueProjFn(torch.autograd.Function):
         arena, n, d = ctx.arena, ctx.n, ctx.d
         shape, dtype, device, fdt, wdt, bdt, fshape = ctx.meta
         buf, arena.buf, arena.base = arena.buf, None, None
+        written, arena.written = arena.written, set()
         if buf is None:
             buf = _lib.zeros_like_fast(torch.empty(shape, dtype=dtype, device=device))
         from_arena = True
@@ -79,10 +106,17 @@ class _ValueProjFn(torch.autograd.Function):
             if g is None:
                 continue
             sl = buf[:, :, i * d:(i + 1) * d]
-            if g.data_ptr() != sl.data_ptr():          # gradient did not come through the arena: add it
-                sl.add_(g.reshape(shape[0], shape[1], d))
-                from_arena = False
+            if i * d in written:
+                # accumulated in place by this layer's sampler backward, which hands autograd a stride-0 zero as a
+                # token; anything else means autograd summed it with another consumer's gradient
+                if any(st != 0 for st in g.stride()):
+                    raise RuntimeError("tamtr_b200: a projected value view has a consumer besides its sampler")
+                continue
+            sl.add_(g.reshape(shape[0], shape[1], d))   # gradient did not come through the arena: add it
+            from_arena = False
         g2 = buf.view(-1, shape[-1])
+        if g2.dtype != dtype:                           # fp32 arena: one cast pass in front of the two GEMMs
+            g2 = g2.to(dtype)
         grad_feats = (g2 @ w).view(fshape).to(fdt) if ctx.needs_input_grad[0] else None
         grad_w = None
         if ctx.needs_input_grad[1]:
@@ -93,7 +127,7 @@ class _ValueProjFn(torch.autograd.Function):
                 parts = [arena.bias_grad.get(i * d) for i in range(n)]
                 grad_b = torch.cat([p if p is not None else torch.zeros(d, device=device) for p in parts]).to(bdt)
             else:
-                grad_b = g2.float().sum(0).to(bdt)
+                grad_b = buf.view(-1, shape[-1]).float().sum(0).to(bdt)
         arena.bias_grad = {}
         return grad_feats, grad_w, grad_b, None, None, None
 
@@ -153,8 +187,9 @@ class _MSDeformAttnFn(torch.autograd.Function):
         if ctx.arena is not None:
             # accumulate into this layer's column slice of the shared, already zeroed buffer
             base = ctx.arena.base
+            off = value.storage_offset() - (0 if base is None else base.storage_offset())
+            ctx.arena.claim(off % value.stride(1))
             buf = ctx.arena.grad_buffer(base)
-            off = value.storage_offset() - base.storage_offset()
             grad_value = buf.view(-1)[off:].as_strided(value.shape, value.stride())
             zero = 0
             wsum = torch.empty(B, Lq, H, dtype=torch.float32, device=value.device)
@@ -182,7 +217,7 @@ class _MSDeformAttnFn(torch.autograd.Function):
                                                     attn.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(),
                                                     grad_attn.data_ptr(), _lib.dtype_code(value), B, Lv, H, Dh, Lq, L, P,
                                                     sh, tok_stride, zero, wsum.data_ptr() if wsum is not None else None,
-                                                    _lib.stream_ptr(value.device))
+                                                    _lib.dtype_code(grad_value), _lib.stream_ptr(value.device))
             else:
                 pts = _points_array(ctx.points, nl, loc, attn)
                 rc = _lib.lib().tamtr_msda_backward_ragged(grad_out.data_ptr(), value.data_ptr(), loc.data_ptr(),
@@ -190,11 +225,14 @@ class _MSDeformAttnFn(torch.autograd.Function):
                                                            grad_attn.data_ptr(), _lib.dtype_code(value), B, Lv, H, Dh, Lq,
                                                            nl, pts, sh, tok_stride, zero,
                                                            wsum.data_ptr() if wsum is not None else None,
-                                                           _lib.stream_ptr(value.device))
+                                                           _lib.dtype_code(grad_value), _lib.stream_ptr(value.device))
         _lib.check(rc, "msda_backward")
         if wsum is not None:      # value_proj bias gradient of this layer: sum_q wsum[q,h] * grad_out[q,h,:]
-            ctx.arena.bias_grad[off % base.shape[-1]] = torch.einsum(
+            ctx.arena.bias_grad[off % value.stride(1)] = torch.einsum(
                 "bqh,bqhc->hc", wsum, grad_out.view(B, Lq, H, Dh).float()).reshape(-1)
+        if ctx.arena is not None:
+            # the gradient already sits in the arena (possibly in another dtype): autograd only needs a token
+            grad_value = torch.zeros((), dtype=value.dtype, device=value.device).expand(value.shape)
         return grad_value, grad_loc, grad_attn, None, None, None
 
 

@@ -12,6 +12,7 @@ call's argument meaning (u, delta, A, B, C, D, delta_bias, delta_softplus) and r
 op of this package.  Everything around the scan is library code (GEMMs, depth-wise conv, LayerNorm), as in the
 reference.
 """
+import functools
 import math
 
 import torch
@@ -26,69 +27,103 @@ __all__ = ("VSSBlock", "SS2D", "Mlp", "DropPath", "selective_scan", "cross_scan"
 CHUNKED_INFERENCE = True    # no-grad forward on small grids: tamtr_selective_scan_forward_chunked (False: always the plain scan)
 
 
+def _scan_forward(u, delta, A, B, C, D, delta_bias, need):
+    # u / delta may stay bf16 (converted on load inside the kernel: the same values the reference's to_fp32() produces,
+    # vmamba.py:985-986, without two passes over [b, K*D, L]); everything else fp32
+    lowp = (u.dtype == torch.bfloat16 and delta.dtype == torch.bfloat16 and u.shape[-1] % 2 == 0)
+    if lowp:
+        u, delta = u.contiguous(), delta.contiguous()
+    else:
+        u, delta = u.contiguous().float(), delta.contiguous().float()
+    A, B, C = (t.contiguous().float() for t in (A, B, C))
+    D = None if D is None else D.contiguous().float()
+    delta_bias = None if delta_bias is None else delta_bias.contiguous().float()
+    Bn, KD, L = u.shape
+    K, N = B.shape[1], A.shape[1]
+    y = torch.empty(u.shape, dtype=torch.float32, device=u.device)
+    lib = _lib.lib()
+    ckpt = torch.empty(Bn, KD, lib.tamtr_selective_scan_segments(L), N, dtype=torch.float32, device=u.device) \
+        if need else None
+    with torch.cuda.device(u.device):
+        pieces = 1 if need or not CHUNKED_INFERENCE else lib.tamtr_selective_scan_chunks(Bn, KD, L)
+        if pieces > 1:
+            # inference on a grid too small for the GPU (e.g. one 1280x1280 image): chunk-parallel forward
+            carry = torch.empty(Bn * KD * pieces * (N + 1), dtype=torch.float32, device=u.device)
+            rc = lib.tamtr_selective_scan_forward_chunked(
+                u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
+                None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(),
+                y.data_ptr(), carry.data_ptr(), pieces, Bn, KD, KD // K, N, L, _lib.stream_ptr(u.device))
+        else:
+            rc = lib.tamtr_selective_scan_forward(
+                u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
+                None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(),
+                y.data_ptr(), None if ckpt is None else ckpt.data_ptr(), Bn, KD, KD // K, N, L,
+                _lib.stream_ptr(u.device))
+    _lib.check(rc, "selective_scan_forward")
+    return y, (u, delta, A, B, C, D, delta_bias, ckpt)
+
+
+def _scan_backward(u, delta, A, B, C, D, delta_bias, ckpt, dy):
+    dy = dy.contiguous().float()
+    Bn, KD, L = u.shape
+    K, N = B.shape[1], A.shape[1]
+    g_u, g_dt = torch.empty_like(u), torch.empty_like(delta)
+    g_A, g_B, g_C = torch.empty_like(A), torch.empty_like(B), torch.empty_like(C)     # zeroed by the call
+    g_D = None if D is None else torch.empty_like(D)
+    g_bias = None if delta_bias is None else torch.empty_like(delta_bias)
+    with torch.cuda.device(u.device):
+        rc = _lib.lib().tamtr_selective_scan_backward(
+            u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
+            None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(), dy.data_ptr(),
+            ckpt.data_ptr(), g_u.data_ptr(), g_dt.data_ptr(), g_A.data_ptr(), g_B.data_ptr(), g_C.data_ptr(),
+            None if g_D is None else g_D.data_ptr(), None if g_bias is None else g_bias.data_ptr(), Bn, KD, KD // K, N,
+            L, _lib.stream_ptr(u.device))
+    _lib.check(rc, "selective_scan_backward")
+    return g_u, g_dt, g_A, g_B, g_C, g_D, g_bias
+
+
 class _SelectiveScanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, delta, A, B, C, D, delta_bias, track):
-        # u / delta may stay bf16 (converted on load inside the kernel: the same values the reference's to_fp32() produces,
-        # vmamba.py:985-986, without two passes over [b, K*D, L]); everything else fp32
-        lowp = (u.dtype == torch.bfloat16 and delta.dtype == torch.bfloat16 and u.shape[-1] % 2 == 0)
-        if lowp:
-            u, delta = u.contiguous(), delta.contiguous()
-        else:
-            u, delta = u.contiguous().float(), delta.contiguous().float()
-        A, B, C = (t.contiguous().float() for t in (A, B, C))
-        D = None if D is None else D.contiguous().float()
-        delta_bias = None if delta_bias is None else delta_bias.contiguous().float()
-        Bn, KD, L = u.shape
-        K, N = B.shape[1], A.shape[1]
         # `track` = grad mode was on at the call site and an input requires grad.  (Not any(ctx.needs_input_grad): that
         # reports the inputs' requires_grad flags even under no_grad -- parameters such as Ds arrive as they are -- and
         # grad mode is always off inside forward().)
-        need = bool(track)
-        y = torch.empty(u.shape, dtype=torch.float32, device=u.device)
-        lib = _lib.lib()
-        ckpt = torch.empty(Bn, KD, lib.tamtr_selective_scan_segments(L), N, dtype=torch.float32, device=u.device) \
-            if need else None
-        with torch.cuda.device(u.device):
-            pieces = 1 if need or not CHUNKED_INFERENCE else lib.tamtr_selective_scan_chunks(Bn, KD, L)
-            if pieces > 1:
-                # inference on a grid too small for the GPU (e.g. one 1280x1280 image): chunk-parallel forward
-                carry = torch.empty(Bn * KD * pieces * (N + 1), dtype=torch.float32, device=u.device)
-                rc = lib.tamtr_selective_scan_forward_chunked(
-                    u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
-                    None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(),
-                    y.data_ptr(), carry.data_ptr(), pieces, Bn, KD, KD // K, N, L, _lib.stream_ptr(u.device))
-            else:
-                rc = lib.tamtr_selective_scan_forward(
-                    u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
-                    None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(),
-                    y.data_ptr(), None if ckpt is None else ckpt.data_ptr(), Bn, KD, KD // K, N, L,
-                    _lib.stream_ptr(u.device))
-        _lib.check(rc, "selective_scan_forward")
-        if need:
-            ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, ckpt)
+        y, saved = _scan_forward(u, delta, A, B, C, D, delta_bias, bool(track))
+        if track:
+            ctx.save_for_backward(*saved)
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         u, delta, A, B, C, D, delta_bias, ckpt = ctx.saved_tensors
-        dy = dy.contiguous().float()
-        Bn, KD, L = u.shape
-        K, N = B.shape[1], A.shape[1]
-        g_u, g_dt = torch.empty_like(u), torch.empty_like(delta)
-        g_A, g_B, g_C = torch.empty_like(A), torch.empty_like(B), torch.empty_like(C)     # zeroed by the call
-        g_D = None if D is None else torch.empty_like(D)
-        g_bias = None if delta_bias is None else torch.empty_like(delta_bias)
-        with torch.cuda.device(u.device):
-            rc = _lib.lib().tamtr_selective_scan_backward(
-                u.data_ptr(), delta.data_ptr(), _lib.dtype_code(u), A.data_ptr(), B.data_ptr(), C.data_ptr(),
-                None if D is None else D.data_ptr(), None if delta_bias is None else delta_bias.data_ptr(), dy.data_ptr(),
-                ckpt.data_ptr(), g_u.data_ptr(), g_dt.data_ptr(), g_A.data_ptr(), g_B.data_ptr(), g_C.data_ptr(),
-                None if g_D is None else g_D.data_ptr(), None if g_bias is None else g_bias.data_ptr(), Bn, KD, KD // K, N,
-                L, _lib.stream_ptr(u.device))
-        _lib.check(rc, "selective_scan_backward")
-        return g_u, g_dt, g_A, g_B, g_C, g_D, g_bias, None
+        return (*_scan_backward(u, delta, A, B, C, D, delta_bias, ckpt, dy), None)
+
+
+class ScanExtensionShim:
+    """Stands in for the `selective_scan_cuda_core` extension module the reference imports but does not ship
+    (csms6s.py:121-126; called at :257 and :266): the same two entry points over the sm_100a scan kernels, so that the
+    reference's own SelectiveScanCore autograd function runs after patch.enable().
+      fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, nrows) -> (out, x)     x = the state checkpoints
+      bwd(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, nrows) -> (du, ddelta, dA, dB, dC, dD, ddelta_bias)"""
+
+    @staticmethod
+    def fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=True, nrows=1):
+        _lib.require_cuda(u, delta, A, B, C, D, delta_bias)
+        if not delta_softplus:
+            raise RuntimeError("tamtr_b200: selective_scan without softplus is not on TAM-TR's path (vmamba.py:907)")
+        with torch.no_grad():
+            y, saved = _scan_forward(u, delta, A, B, C, D, delta_bias, True)
+        return y, saved[-1]
+
+    @staticmethod
+    def bwd(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus=True, nrows=1):
+        with torch.no_grad():
+            u, delta = u.contiguous().float(), delta.contiguous().float()
+            A, B, C = (t.contiguous().float() for t in (A, B, C))
+            D = None if D is None else D.contiguous().float()
+            delta_bias = None if delta_bias is None else delta_bias.contiguous().float()
+            return _scan_backward(u, delta, A, B, C, D, delta_bias, x, dout)
 
 
 def selective_scan(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=True):
@@ -290,39 +325,100 @@ class SS2D(nn.Module):
         self.Ds._no_weight_decay = True
 
     def forward_core(self, x):
-        """[b, d, h, w] -> [b, h, w, d] (vmamba.py:937-1017 with force_fp32, SelectiveScanCore)."""
-        b, d, h, w = x.shape
-        k, r = self.dt_projs_weight.shape[0], self.dt_projs_weight.shape[2]
-        n = self.A_logs.shape[1]
-        l = h * w
-        xs = cross_scan(x)
-        # the two einsums of vmamba.py:973-976 as broadcast batched GEMMs over (b, k): same contractions, but operands and
-        # results stay in their [b, k, rows, l] layout (einsum permutes xs to [k, b*l, d] and returns a [k, b, l, c]-ordered
-        # view: three extra passes over [b, 4, d, l] per call, forward and backward)
-        x_dbl = torch.matmul(self.x_proj_weight.unsqueeze(0), xs)
-        dts, Bs, Cs = torch.split(x_dbl, [r, n, n], dim=2)
-        dts = torch.matmul(self.dt_projs_weight.unsqueeze(0), dts)
-        ys = selective_scan(xs.reshape(b, -1, l), dts.contiguous().view(b, -1, l),     # fp32 or bf16: converted on load
-                            -torch.exp(self.A_logs.float()), Bs.contiguous().float(), Cs.contiguous().float(),
-                            self.Ds.float(), self.dt_projs_bias.view(-1).float(), True)
-        y = cross_merge(ys.view(b, k, -1, l), h, w)
-        y = _layer_norm(self.out_norm, y.transpose(1, 2).contiguous()).view(b, h, w, -1)
-        return y.to(x.dtype)
+        return _ss2d_core(self, x)
 
     def forward(self, x):
-        # in_proj (vmamba.py:1021-1024) as two GEMMs, one per half of its output: the same numbers, but x and z come out
-        # contiguous -- no chunk views, no z.clone(), and no torch.cat of the two gradient halves in the backward
-        wgt, bias = self.in_proj.weight, self.in_proj.bias
-        d_in = wgt.shape[0] // 2
-        z = self.act(F.linear(x, wgt[d_in:], None if bias is None else bias[d_in:]))
-        x = F.linear(x, wgt[:d_in], None if bias is None else bias[:d_in])
-        x = x.permute(0, 3, 1, 2).contiguous()
-        if isinstance(self.act, nn.SiLU) and _is_dw3x3(self.conv2d, x):
-            x = dwconv3x3_silu(x, self.conv2d)
-        else:
-            x = self.act(self.conv2d(x))
-        y = self.forward_core(x) * z
-        return self.dropout(self.out_proj(y))
+        return _ss2d_forward(self, x)
+
+
+# Module-level bodies: patch.enable() binds them onto the REFERENCE's SS2D / VSSBlock, whose instances carry a
+# `forward_core` attribute of their own (a functools.partial set in __initv2__, vmamba.py:466) that must not be called.
+def _ss2d_core(self, x):
+    """[b, d, h, w] -> [b, h, w, d] (vmamba.py:937-1017 with force_fp32, SelectiveScanCore)."""
+    b, d, h, w = x.shape
+    k, r = self.dt_projs_weight.shape[0], self.dt_projs_weight.shape[2]
+    n = self.A_logs.shape[1]
+    l = h * w
+    xs = cross_scan(x)
+    # the two einsums of vmamba.py:973-976 as broadcast batched GEMMs over (b, k): same contractions, but operands and
+    # results stay in their [b, k, rows, l] layout (einsum permutes xs to [k, b*l, d] and returns a [k, b, l, c]-ordered
+    # view: three extra passes over [b, 4, d, l] per call, forward and backward)
+    x_dbl = torch.matmul(self.x_proj_weight.unsqueeze(0), xs)
+    dts, Bs, Cs = torch.split(x_dbl, [r, n, n], dim=2)
+    dts = torch.matmul(self.dt_projs_weight.unsqueeze(0), dts)
+    ys = selective_scan(xs.reshape(b, -1, l), dts.contiguous().view(b, -1, l),     # fp32 or bf16: converted on load
+                        -torch.exp(self.A_logs.float()), Bs.contiguous().float(), Cs.contiguous().float(),
+                        self.Ds.float(), self.dt_projs_bias.view(-1).float(), True)
+    y = cross_merge(ys.view(b, k, -1, l), h, w)
+    y = _layer_norm(self.out_norm, y.transpose(1, 2).contiguous()).view(b, h, w, -1)
+    return y.to(x.dtype)
+
+def _ss2d_forward(self, x):
+    # in_proj (vmamba.py:1021-1024) as two GEMMs, one per half of its output: the same numbers, but x and z come out
+    # contiguous -- no chunk views, no z.clone(), and no torch.cat of the two gradient halves in the backward
+    wgt, bias = self.in_proj.weight, self.in_proj.bias
+    d_in = wgt.shape[0] // 2
+    z = self.act(F.linear(x, wgt[d_in:], None if bias is None else bias[d_in:]))
+    x = F.linear(x, wgt[:d_in], None if bias is None else bias[:d_in])
+    x = x.permute(0, 3, 1, 2).contiguous()
+    if isinstance(self.act, nn.SiLU) and _is_dw3x3(self.conv2d, x):
+        x = dwconv3x3_silu(x, self.conv2d)
+    else:
+        x = self.act(self.conv2d(x))
+    y = _ss2d_core(self, x) * z
+    return self.dropout(self.out_proj(y))
+
+
+def _ss2d_supported(m):
+    """The SS2D configuration TAM-TR builds (vmamba.py:1205-1226: forward_type "v2", 3x3 depth-wise conv, channel-last,
+    no low-rank out-projection), recognised on a reference instance by the attributes __initv2__ creates."""
+    core = getattr(m, "forward_core", None)
+    if isinstance(core, functools.partial):             # a reference instance: which scan variant did it pick?
+        if getattr(core.func, "__name__", "") != "forward_corev2":
+            return False
+        for key, same_math in (("CrossScan", ("CrossScan", "CrossScanTriton")),
+                               ("CrossMerge", ("CrossMerge", "CrossMergeTriton"))):
+            impl = core.keywords.get(key)
+            if impl is not None and getattr(impl, "__name__", "") not in same_math:
+                return False                            # the 1- / 2-direction ablations scan other orders
+    if not isinstance(getattr(m, "out_act", nn.Identity()), nn.Identity) or getattr(m, "out_norm_shape", "v0") != "v0":
+        return False
+    return (not getattr(m, "channel_first", False) and getattr(m, "d_conv", 3) == 3
+            and not getattr(m, "disable_z", False) and not getattr(m, "disable_z_act", False)
+            and not getattr(m, "out_rank", None) and not getattr(m, "oact", False) and not getattr(m, "ssm_low_rank", False)
+            and all(hasattr(m, a) for a in ("in_proj", "conv2d", "x_proj_weight", "dt_projs_weight", "dt_projs_bias",
+                                            "A_logs", "Ds", "out_norm", "out_proj", "dropout", "act"))
+            and isinstance(m.out_norm, nn.LayerNorm) and m.A_logs.shape[1] == 16)
+
+
+def ss2d_forward_on(original):
+    """SS2D.forwardv2 for the reference's class (its instances call it through an INSTANCE attribute,
+    `self.forward = self.forwardv2`, vmamba.py:364, bound at construction -- so this reaches SS2D modules built after
+    enable(); the VSSBlocks of a model built earlier are covered by VSSBlock.forward below): our path for the
+    configuration TAM-TR builds, the reference's own method for anything else."""
+    def forward(self, x, **kwargs):
+        if kwargs or not _ss2d_supported(self):
+            return original(self, x, **kwargs)
+        return _ss2d_forward(self, x)
+    return forward
+
+
+def _vssblock_forward(self, input):
+    # SS2D body called directly, not through self.op(...): a reference SS2D carries its own bound `forward`
+    op = self.op
+    y = _layer_norm(self.norm, input)
+    y = _ss2d_forward(op, y) if _ss2d_supported(op) else op(y)
+    x = input + self.drop_path(y)
+    return x + self.drop_path(self.mlp(_layer_norm(self.norm2, x)))
+
+
+def vssblock_forward_on(original):
+    def forward(self, input):
+        if (getattr(self, "ssm_branch", False) and getattr(self, "mlp_branch", False)
+                and not getattr(self, "post_norm", False) and not getattr(self, "use_checkpoint", False)):
+            return _vssblock_forward(self, input)
+        return original(self, input)
+    return forward
 
 
 class VSSBlock(nn.Module):
@@ -347,5 +443,4 @@ class VSSBlock(nn.Module):
                        drop=mlp_drop_rate)
 
     def forward(self, input):
-        x = input + self.drop_path(self.op(_layer_norm(self.norm, input)))
-        return x + self.drop_path(self.mlp(_layer_norm(self.norm2, x)))
+        return _vssblock_forward(self, input)

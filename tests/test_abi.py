@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in include/tamtr_b200.h but not exported"
     assert sorted(_lib.exported_symbols()) == declared, "ctypes binding and header are out of sync"
-    assert handle.tamtr_abi_version() == 1
+    assert handle.tamtr_abi_version() == 2
 
 
 def test_cpu_tensors_are_rejected_with_the_message_the_reference_expects():

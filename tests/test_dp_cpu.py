@@ -19,6 +19,50 @@ def test_shard_indices_partition_the_batch():
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
 
 
+def test_gradient_buckets_partition_the_flat_buffer():
+    """FlatGrads.set_buckets / bucket_slice / pack_bucket: the buckets tile the padded flat buffer without gaps and packing
+    them one by one equals packing everything at once (what the overlapped all-reduce relies on)."""
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 13), torch.nn.Linear(13, 5), torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    net(torch.randn(4, 7)).sum().backward()
+    net[2].bias.grad = None                                      # a parameter without a gradient is packed as zeros
+    flat = dp.FlatGrads(list(net.parameters()))
+    assert all(o % 4 == 0 for o in flat.offsets) and flat.flat.numel() % 4 == 0
+    whole = flat.gather().clone()
+    for n in (1, 2, 3, 8):
+        flat.set_buckets(n)
+        assert flat.buckets[0][0] == 0 and flat.buckets[-1][1] == len(flat.params)
+        assert all(a[1] == b[0] for a, b in zip(flat.buckets, flat.buckets[1:]))
+        assert sum(flat.bucket_slice(b).numel() for b in range(len(flat.buckets))) == flat.flat.numel()
+        flat.flat.fill_(7.0)
+        for b in range(len(flat.buckets)):
+            flat.pack_bucket(b)
+        pad = torch.ones_like(whole, dtype=torch.bool)
+        for o, p in zip(flat.offsets, flat.params):
+            pad[o:o + p.numel()] = False
+        assert torch.equal(flat.flat[~pad], whole[~pad])
+
+
+def test_load_inputs_refuses_what_it_cannot_update():
+    """A captured step bakes non-tensor arguments in: replacing one must fail loudly (a new CdnPlan used to be
+    ignored silently)."""
+    net = torch.nn.Linear(4, 2)
+
+    class Plan:
+        def to(self, device):
+            return self
+
+        def materialize(self, w):
+            return None
+
+    step = dp.HeadTrainStep(torch.nn.Sequential(net), lambda o: o.sum(), (torch.zeros(3, 4),), use_graph=False)
+    step.static.append(Plan())
+    step.load_inputs((torch.ones(3, 4), None))                   # None keeps the captured object
+    assert float(step.static[0].sum()) == 12.0
+    with pytest.raises(RuntimeError, match="cannot be updated"):
+        step.load_inputs((torch.ones(3, 4), Plan()))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

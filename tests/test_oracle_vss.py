@@ -47,3 +47,24 @@ def test_product_scan_rejects_cpu_tensors():
     z = torch.zeros(1, 512, 8)
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         selective_scan(z, z, torch.zeros(512, 16), torch.zeros(1, 4, 16, 8), torch.zeros(1, 4, 16, 8))
+
+
+def test_recurrence_oracle_agrees_with_the_closed_form():
+    """oracle/vss_ref.selective_scan (the loop over positions) against selective_scan_closed_form (cumulative sums + a
+    masked contraction, no loop): outputs and all seven gradients in fp64 -- two formulations that share no code."""
+    import torch
+    from oracle import seeding, vss_ref
+    b, k, d, l, n = 2, 4, 3, 37, 16
+    mk = lambda name, shape: seeding.seeded_tensor(17, name, shape).double()
+    base = [mk("u", (b, k * d, l)), mk("dt", (b, k * d, l)) - 1.5,
+            -(0.5 + 8.0 * seeding.seeded_uniform(17, "A", (k * d, n)).double()),
+            mk("B", (b, k, n, l)), mk("C", (b, k, n, l)), mk("D", (k * d,)), 0.3 * mk("bias", (k * d,))]
+    gout = mk("g", (b, k * d, l))
+    res = []
+    for fn in (vss_ref.selective_scan, vss_ref.selective_scan_closed_form):
+        leaves = [t.clone().requires_grad_() for t in base]
+        y = fn(*leaves)
+        y.backward(gout)
+        res.append([y.detach()] + [t.grad for t in leaves])
+    for a, c in zip(*res):
+        assert ((a - c).norm() / c.norm()).item() < 1e-10

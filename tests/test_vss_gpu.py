@@ -187,7 +187,7 @@ def test_scan_agrees_with_vllm_mamba_kernel(cuda_lib):
     """The extension the reference calls (selective_scan_cuda_core, VManba/csms6s.py:257) is not in its tree, so the scan has
     no reference output to pin against.  Closest independent implementation available in this image: vLLM's port of the
     mamba_ssm CUDA kernel (library code).  Forward only (vLLM ships no backward), in a subprocess (tests/scan_crosscheck_vllm.py);
-    skipped when vLLM cannot be imported or its kernel cannot run here."""
+    FAILS (does not skip) when vLLM cannot be imported or its kernel cannot run: the image ships it."""
     import json
     import os
     import subprocess
@@ -197,13 +197,14 @@ def test_scan_agrees_with_vllm_mamba_kernel(cuda_lib):
         proc = subprocess.run([sys.executable, os.path.join(here, "scan_crosscheck_vllm.py")], capture_output=True, text=True,
                               timeout=600)
     except subprocess.TimeoutExpired:
-        pytest.skip("vLLM cross-check timed out")
+        pytest.fail("vLLM cross-check timed out")
     lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
     if proc.returncode != 0 or not lines:
-        pytest.skip("vLLM cross-check did not run: " + proc.stderr[-300:])
+        pytest.fail("vLLM cross-check did not run: " + proc.stderr[-300:])
     res = json.loads(lines[-1])
     if "unavailable" in res:
-        pytest.skip("vLLM selective_scan_fn unavailable: " + res["unavailable"])
+        pytest.fail("vLLM selective_scan_fn unavailable (this image ships vLLM: the cross-check must run): "
+                    + res["unavailable"])
     assert res["rel_l2"] and all(v < 1e-5 for v in res["rel_l2"].values()), res
 
 
@@ -236,3 +237,27 @@ def test_chunk_parallel_inference_scan(cuda_lib, b, k, d, l):
     before = cuda_lib.launch_count()
     vss.selective_scan(*leaf, True)
     assert cuda_lib.launch_count() - before == 1
+
+
+@pytest.mark.parametrize("b,k,d,l", [(2, 4, 8, 48), (1, 4, 32, 95), (1, 2, 16, 130)])
+def test_scan_backward_against_the_closed_form(cuda_lib, b, k, d, l):
+    """The scan kernels' backward (all seven gradients) against an INDEPENDENT formulation: oracle/vss_ref's closed form
+    (cumulative sums + masked contraction in fp64, autograd) -- not the position loop the recurrence oracle and the kernel
+    share.  Lengths that are not multiples of the kernels' 16-position tiles included."""
+    from oracle import vss_ref
+    from tamtr_b200.vss import selective_scan
+    n = 16
+    mk = lambda name, shape: seeding.seeded_tensor(23, name, shape)
+    base = [mk("u", (b, k * d, l)), mk("dt", (b, k * d, l)) - 1.5, -(0.5 + 12.0 * seeding.seeded_uniform(23, "A", (k * d, n))),
+            mk("B", (b, k, n, l)), mk("C", (b, k, n, l)), 1.0 + 0.2 * mk("D", (k * d,)), 0.3 * mk("bias", (k * d,))]
+    gout = mk("g", (b, k * d, l))
+    ref = [t.clone().double().requires_grad_() for t in base]
+    y_ref = vss_ref.selective_scan_closed_form(*ref)
+    y_ref.backward(gout.double())
+    ours = [t.clone().cuda().requires_grad_() for t in base]
+    y = selective_scan(*ours)
+    y.backward(gout.cuda())
+    torch.cuda.synchronize()
+    assert rel_l2(y, y_ref) < 1e-5
+    for name, got, want in zip(("u", "delta", "A", "B", "C", "D", "delta_bias"), ours, ref):
+        assert rel_l2(got.grad, want.grad) < 1e-4, (name, rel_l2(got.grad, want.grad))

@@ -28,10 +28,12 @@ CASES = {
 }
 
 
-def msda_bytes(B, Lq, H, Dh, Lv, sv, L=3, P=4):
+def msda_bytes(B, Lq, H, Dh, shapes, sv, P=4):
+    """Algorithmic bytes with the compulsory value traffic taken PER LEVEL: a level whose whole slab is smaller than what
+    the gather would read from it (the 40x40 level at B=16, Lq=300) is counted once, the others by their gathered bytes."""
     d = H * Dh
-    gathered = B * Lq * H * L * P * 4 * Dh
-    val = min(B * Lv * d, gathered)
+    L = len(shapes)
+    val = sum(min(B * h * w * d, B * Lq * H * P * 4 * Dh) for h, w in shapes)
     locw = B * Lq * H * L * P * 3 * 4
     fwd = val * sv + locw + B * Lq * d * sv
     bwd = B * Lq * d * sv + val * sv + 2 * locw + val * sv   # grad_value in value dtype (bf16 path: bf16 atomics)
@@ -85,7 +87,7 @@ def main():
             def bwd():
                 torch.autograd.grad(out, (v, l, a), gout, retain_graph=True)
             bwd_us, bwd_min = time_fn(bwd, args.iters, flush)
-            fb, bb = msda_bytes(B, Lq, H, Dh, Lv, value.element_size())
+            fb, bb = msda_bytes(B, Lq, H, Dh, shapes, value.element_size())
             row = dict(case=name, dtype=dt, B=B, Lq=Lq, Dh=Dh, Lv=Lv, fwd_us=fwd_us, fwd_min_us=fwd_min,
                        bwd_us=bwd_us, bwd_min_us=bwd_min, fwd_MB=fb / 1e6, bwd_MB=bb / 1e6,
                        fwd_GBs=fb / fwd_us / 1e3, bwd_GBs=bb / bwd_us / 1e3,
