@@ -72,8 +72,8 @@ def selective_scan_closed_form(u, delta, A, B, C, D=None, delta_bias=None):
         dl = dl + delta_bias.to(f).view(1, kd, 1)
     dl = torch.where(dl > 20.0, dl, torch.log1p(torch.exp(dl.clamp(max=20.0))))
     S = torch.cumsum(dl, -1)                                                     # [b, kd, l]
-    diff = S.unsqueeze(-1) - S.unsqueeze(-2)                                     # [b, kd, t, s] = S_t - S_s
     mask = torch.ones(l, l, dtype=torch.bool, device=u.device).tril()
+    diff = (S.unsqueeze(-1) - S.unsqueeze(-2)).masked_fill(~mask, 0.0)           # [b, kd, t, s] = S_t - S_s for s <= t
     decay = torch.exp(A.to(f).view(1, kd, n, 1, 1) * diff.unsqueeze(2)) * mask   # [b, kd, n, t, s]
     Bx = B.to(f).view(b, k, 1, n, l).expand(b, k, d, n, l).reshape(b, kd, n, l)
     Cx = C.to(f).view(b, k, 1, n, l).expand(b, k, d, n, l).reshape(b, kd, n, l)

@@ -162,11 +162,11 @@ def test_scan_extension_shim_runs_the_reference_autograd_function(cuda_lib):
     from oracle import vss_ref
     from tamtr_b200 import vss
     ext = vss.ScanExtensionShim
-    u, dt = seeding.seeded_tensor(2, "u", (2, 64, 50)), seeding.seeded_tensor(2, "dt", (2, 64, 50)) - 2.0
-    A = -(0.5 + 15.0 * seeding.seeded_uniform(2, "A", (64, 16)))
+    u, dt = seeding.seeded_tensor(2, "u", (2, 128, 50)), seeding.seeded_tensor(2, "dt", (2, 128, 50)) - 2.0
+    A = -(0.5 + 15.0 * seeding.seeded_uniform(2, "A", (128, 16)))
     Bm, Cm = seeding.seeded_tensor(2, "B", (2, 4, 16, 50)), seeding.seeded_tensor(2, "C", (2, 4, 16, 50))
-    D, bias = seeding.seeded_tensor(2, "D", (64,)), seeding.seeded_tensor(2, "b", (64,)) * 0.1
-    dout = seeding.seeded_tensor(2, "g", (2, 64, 50))
+    D, bias = seeding.seeded_tensor(2, "D", (128,)), seeding.seeded_tensor(2, "b", (128,)) * 0.1
+    dout = seeding.seeded_tensor(2, "g", (2, 128, 50))
     cu = [t.cuda() for t in (u, dt, A, Bm, Cm, D, bias)]
     out, x, *rest = ext.fwd(*cu, True, 1)
     du, ddelta, dA, dB, dC, dD, dbias, *rest = ext.bwd(*cu, dout.cuda(), x, True, 1)

@@ -239,7 +239,7 @@ def test_chunk_parallel_inference_scan(cuda_lib, b, k, d, l):
     assert cuda_lib.launch_count() - before == 1
 
 
-@pytest.mark.parametrize("b,k,d,l", [(2, 4, 8, 48), (1, 4, 32, 95), (1, 2, 16, 130)])
+@pytest.mark.parametrize("b,k,d,l", [(2, 4, 32, 48), (1, 4, 32, 95), (1, 2, 64, 130)])
 def test_scan_backward_against_the_closed_form(cuda_lib, b, k, d, l):
     """The scan kernels' backward (all seven gradients) against an INDEPENDENT formulation: oracle/vss_ref's closed form
     (cumulative sums + masked contraction in fp64, autograd) -- not the position loop the recurrence oracle and the kernel
