@@ -174,7 +174,6 @@ def synthetic_targets(seed, B, lo=20, hi=100):
     """VisDrone-shaped ground truth: n ~ U{20..100} small boxes per image, 10 classes."""
     g = torch.Generator().manual_seed(seed)
     groups = [int(torch.randint(lo, hi + 1, (1,), generator=g)) for _ in range(B)]
-    groups[0] = hi                    # pin the largest group so every rank/step has the same query count
     n = sum(groups)
     boxes = torch.cat([torch.rand(n, 2, generator=g), 0.01 + 0.29 * torch.rand(n, 2, generator=g)], -1)
     cls = torch.randint(0, NC, (n,), generator=g)
@@ -236,18 +235,26 @@ def split_outputs(out):
     return dec_bboxes, dec_scores, dn_bboxes, dn_scores, dn_meta
 
 
-def make_detection_loss(batch, dev):
+def make_detection_loss():
     """The reference's training loss (nn/tasks.py:578-624: RTDETRDetectionLoss(use_vfl=True) on the encoder proposals +
-    every decoder layer + the denoising queries) with the Hungarian matching on the device."""
+    every decoder layer + the denoising queries) with the matching and the losses on the device, reading the step's own
+    ground truth (the DeviceTargets among its static inputs: refreshed in place for every batch)."""
     from tamtr_b200.loss import RTDETRDetectionLoss
     crit = RTDETRDetectionLoss(nc=NC, use_vfl=True)
-    targets = {"cls": batch["cls"].to(dev), "bboxes": batch["bboxes"].to(dev), "gt_groups": batch["gt_groups"]}
 
-    def fn(out):
+    def fn(out, static):
         db, ds, dnb, dns, meta = split_outputs(out)
-        f = (lambda t: None if t is None else t.float())
-        return sum(crit((db.float(), ds.float()), targets, dn_bboxes=f(dnb), dn_scores=f(dns), dn_meta=meta).values())
+        return sum(crit((db, ds), static[-1], dn_bboxes=dnb, dn_scores=dns, dn_meta=meta).values())
     return fn
+
+
+MAX_GT = 100        # ground-truth slots per image of the bench's DeviceTargets (synthetic_targets draws 20..100)
+
+
+def device_targets(batch, dev):
+    """The batch's ground truth in fixed-shape device tensors; denoising capacity = the bucket for <= MAX_GT boxes (200)."""
+    from tamtr_b200.loss import DeviceTargets
+    return DeviceTargets(len(batch["gt_groups"]), MAX_GT, dev, DeviceTargets.capacity_for(MAX_GT)).load(batch)
 
 
 # ----------------------------------------------------------------------------------------------------- clocks
@@ -493,11 +500,15 @@ def main():
         host.append(([x.pin_memory() for x in xs], text.pin_memory()))
         g = torch.Generator().manual_seed(4321 + rank * 7 + j)
         host_img.append(torch.randint(0, 256, (B, 3, 640, 640), dtype=torch.uint8, generator=g).pin_memory())
-    batch = synthetic_targets(1234 + rank, B)
-    plan = model.plan_cdn(batch)
-    Lq = plan.n_dn + NQ
+    # ground truth: a different synthetic batch per step parity (20..100 boxes per image, counts vary), in fixed-shape
+    # device tensors that every step refreshes in place -- the captured graph (denoising group, matching, loss included)
+    # does not depend on the counts
+    batches = [synthetic_targets(1234 + rank * 7 + j, B) for j in range(2)]
+    batch = batches[0]
+    plan = device_targets(batch, dev)
+    Lq = plan.dn_capacity + NQ
 
-    loss_fn = make_detection_loss(batch, dev) if loss_kind == "detection" else surrogate_loss_fn
+    loss_fn = make_detection_loss() if loss_kind == "detection" else surrogate_loss_fn
     try:
         step = dp.HeadTrainStep(model, loss_fn, (host[0][0], host[0][1], plan), autocast=torch.bfloat16,
                                 use_graph=not (args.no_graph or args.launch_list), optimizer=optimizer, buckets=args.buckets)
@@ -571,6 +582,7 @@ def main():
                 step.static[1].copy_(stage_feat[s][1], non_blocking=True)
             else:
                 step.load_inputs((stage_feat[s][0], stage_feat[s][1], None))
+            step.static[2].load(batches[s])        # this step's ground truth: host -> pinned -> device, in place
             consumed[s].record(cur)
             loss = step.run()
             loss_host[s].copy_(loss, non_blocking=True)
@@ -590,8 +602,9 @@ def main():
         t = dp.max_over_ranks(timed(dev, lambda: e2e_loop(args.steps, images), 1, barrier), dev)
         e2e[key] = {"value": ws * B * args.steps / t, "ms_per_step": t / args.steps * 1e3}
     text_bytes = host[0][1].numel() * host[0][1].element_size()
-    h2d_img = host_img[0].numel() + text_bytes
-    h2d_feat = sum(x.numel() * x.element_size() for x in host[0][0]) + text_bytes
+    tgt_bytes = sum(t.numel() * t.element_size() for t in (plan.boxes, plan.cls, plan.count))
+    h2d_img = host_img[0].numel() + text_bytes + tgt_bytes
+    h2d_feat = sum(x.numel() * x.element_size() for x in host[0][0]) + text_bytes + tgt_bytes
     # the host->device link on its own (explains the features-from-host variant when it, not the step, is the longer leg)
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(copy_stream):
@@ -667,7 +680,8 @@ def main():
                 "config": cfg, "clocks": clk,
                 "e2e": {"value": e2e["images"]["value"], "unit": "images/s", "h2d_bytes_per_step": h2d_img,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e["images"]["ms_per_step"],
-                        "input": "uint8 images [B,3,640,640] + text embeddings from pinned host memory; an on-device "
+                        "input": "uint8 images [B,3,640,640] + text embeddings + the batch's ground truth (boxes / classes / "
+                                 "counts, different counts every step) from pinned host memory; an on-device "
                                  "stand-in stem (3 average pools + 1x1 projections; the backbone / neck are outside this "
                                  "path) turns them into the pyramid maps inside the timed region; loss read back every step",
                         "features_from_host": {"value": e2e["features"]["value"], "ms_per_step": e2e["features"]["ms_per_step"],
@@ -699,7 +713,7 @@ def main():
             m4 = ManbaWorldDecoder(NC, list(CH), HD, NQ, NDP, NH, NDL, vss=False).to(dev).train()
             xs4, text4 = synthetic_inputs(555 + rank, B4, torch.bfloat16)
             b4 = synthetic_targets(555 + rank, B4)
-            st = dp.HeadTrainStep(m4, make_detection_loss(b4, dev), (xs4, text4, m4.plan_cdn(b4)), autocast=torch.bfloat16,
+            st = dp.HeadTrainStep(m4, make_detection_loss(), (xs4, text4, device_targets(b4, dev)), autocast=torch.bfloat16,
                                   use_graph=not args.no_graph, optimizer=dict(lr=1e-4, weight_decay=1e-4, max_norm=0.1),
                                   buckets=args.buckets, warmup=2)
             n = max(3, args.steps // 2)
@@ -717,7 +731,7 @@ def main():
     if rank == 0 and not args.quick and not strong and ws == 1:
         if args.loss == "surrogate":
             def det():      # the same step with the reference's detection loss on top (device-side Hungarian matching)
-                st = dp.HeadTrainStep(model, make_detection_loss(batch, dev), (host[0][0], host[0][1], plan),
+                st = dp.HeadTrainStep(model, make_detection_loss(), (host[0][0], host[0][1], plan),
                                       autocast=torch.bfloat16, use_graph=not args.no_graph)
                 t = time_step(st, args.steps)
                 return {"value": B * args.steps / t, "unit": "images/s", "ms_per_step": t / args.steps * 1e3,

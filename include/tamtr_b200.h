@@ -349,6 +349,42 @@ int tamtr_dwconv3x3_silu_backward(const void *grad_y, const void *x, const float
                                   float *grad_weight, float *grad_bias, int dtype, int Bn, int D, int H, int W, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Training-side glue on the device with FIXED shapes (one captured CUDA graph serves every batch): the batch's ground
+ * truth is padded -- gt_box [B, G, 4] f32 (cx, cy, w, h), gt_cls [B, G] int64, count [B] int32 on the device -- and
+ * everything that depends on the counts is decided inside the kernels.
+ *
+ * tamtr_cdn_group: contrastive denoising group, ultralytics/models/utils/ops.py:152-291.
+ *   uniforms [B, Dmax, 10] f32 in [0,1): per slot (label flip test, new label, 4 box-noise signs, 4 magnitudes) -- the
+ *     caller draws them (torch.rand: graph-safe Philox), the kernel applies the reference's formulas to them
+ *   dn_cls [B, Dmax] int64 (noised labels; 0 in empty slots), dn_box [B, Dmax, 4] f32 in logit space (0 in empty slots),
+ *   dn_valid [B, Dmax] f32 (1 = the slot holds a query: multiply the class embedding by it), attn_mask [Dmax+nq, Dmax+nq]
+ *   uint8 (1 = blocked).  Slot layout as the reference (2 * num_group copies in slots of max(count); copies
+ *   [0, num_group) positive, the rest negative; attention groups = pairs of copies); Dmax >= 2 * max(count) * num_group
+ *   is the bucket's capacity: the slots beyond are padding (blocked both ways, ignored by the loss).
+ * tamtr_match_cost: cost [NL, B, Q, G] f32 of query q against ground truth g of ITS image (ops.py:77-112, focal class
+ *   cost + L1 + (1 - RIoU); pred_box [NL, B, Q, 4] post-sigmoid, pred_score [NL, B, Q, nc] logits).
+ * tamtr_linear_sum_assignment_padded: scipy-exact assignment per (layer, image) on the first count[b] columns;
+ *   match [NL, B, Q] int32 = ground-truth index or -1.
+ * tamtr_detection_loss: losses of NL layers (loss.py:85-167, 232-326, 376-443; VFL / focal + L1 + RIoU) and the
+ *   derivatives of the three un-normalised sums w.r.t. the predictions, in one pass.
+ *   dn_group = 0: matched group (match required); 1: denoising group (targets follow from the slot layout, num_dn)
+ *   partial [NL, B, 3] scratch; out [NL*3 + 1]: (class, bbox, giou) per layer with gains and the 1/pairs normaliser
+ *   applied, then 1/pairs itself; d_l1, d_giou [NL, B, Q, 4], d_cls [NL, B, Q, nc] (multiply by gain/pairs and the
+ *   upstream gradient of the corresponding loss). */
+int tamtr_cdn_group(const float *gt_box, const long long *gt_cls, const int *count, const float *uniforms,
+                    long long *dn_cls, float *dn_box, float *dn_valid, unsigned char *attn_mask, int B, int G, int Dmax,
+                    int nq, int nc, int num_dn, float cls_noise_ratio, float box_noise_scale, void *stream);
+int tamtr_match_cost(const float *pred_box, const float *pred_score, const float *gt_box, const long long *gt_cls,
+                     float *cost, int NL, int B, int Q, int G, int nc, float alpha, float gamma, float gain_class,
+                     float gain_bbox, float gain_giou, void *stream);
+int tamtr_linear_sum_assignment_padded(const float *C, const int *count_dev, int *match, int n_layers, int bs, int nq,
+                                       int max_gt, void *stream);
+int tamtr_detection_loss(const float *pred_box, const float *pred_score, const float *gt_box, const long long *gt_cls,
+                         const int *count, const int *match, float *partial, float *out, float *d_l1, float *d_giou,
+                         float *d_cls, int NL, int B, int Q, int G, int nc, int dn_group, int num_dn, int use_vfl,
+                         float gain_class, float gain_bbox, float gain_giou, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Optimizer step on flat buffers: clip_grad_norm_(max_norm) + AdamW, the reference's optimizer_step
  * (ultralytics/engine/trainer.py:471-477; parameter groups of build_optimizer, :654-677: weights with decay, biases
  * and normalisation weights without).

@@ -70,6 +70,11 @@ _SIGNATURES = {
     "tamtr_selective_scan_forward_chunked": (ctypes.c_int, [_vp, _vp, _i] + [_fp] * 7 + [_i] * 6 + [_vp]),
     "tamtr_cross_scan": (ctypes.c_int, [_vp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_cross_merge": (ctypes.c_int, [_vp, _vp] + [_i] * 5 + [_vp]),
+    "tamtr_cdn_group": (ctypes.c_int, [_fp, _vp, _vp, _fp, _vp, _fp, _fp, _vp] + [_i] * 6 + [ctypes.c_float] * 2 + [_vp]),
+    "tamtr_match_cost": (ctypes.c_int, [_fp, _fp, _fp, _vp, _fp] + [_i] * 5 + [ctypes.c_float] * 5 + [_vp]),
+    "tamtr_linear_sum_assignment_padded": (ctypes.c_int, [_fp, _vp, _vp] + [_i] * 4 + [_vp]),
+    "tamtr_detection_loss": (ctypes.c_int, [_fp, _fp, _fp, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _fp] + [_i] * 8
+                             + [ctypes.c_float] * 3 + [_vp]),
     "tamtr_optim_partials": (ctypes.c_int, [ctypes.c_longlong]),
     "tamtr_adamw_flat": (ctypes.c_int, [_fp, _fp, _fp, _fp, ctypes.c_longlong, _vp, _fp, _fp]
                          + [ctypes.c_float] * 6 + [_vp]),

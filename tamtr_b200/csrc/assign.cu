@@ -36,10 +36,16 @@ __device__ __forceinline__ bool asg_better(const AsgKey &b, const AsgKey &a) {
 __global__ void __launch_bounds__(kAsgThreads)
 lsap_kernel(const float *__restrict__ C, const int *__restrict__ gt_start, const int *__restrict__ out_start,
             long long *__restrict__ out_q, long long *__restrict__ out_g, int bs, int nq, int c_cols, int padded,
-            int max_cols, int stage_elems, long long out_layer_stride) {
+            int max_cols, int stage_elems, long long out_layer_stride, const int *__restrict__ count,
+            int *__restrict__ match) {
     extern __shared__ unsigned char smem[];
     const int b = blockIdx.x, layer = blockIdx.y;
-    const int g0 = gt_start[b], ng = gt_start[b + 1] - g0;
+    // two ways to describe the images' ground truths: prefix sums (pair lists out) or per-image counts of a padded batch
+    // (fixed-shape output: match[layer, b, q] = ground-truth index of the image or -1)
+    const int g0 = count ? 0 : gt_start[b];
+    const int ng = count ? min(count[b], c_cols) : gt_start[b + 1] - g0;
+    if (match)
+        for (int q = threadIdx.x; q < nq; q += kAsgThreads) match[((size_t)layer * bs + b) * nq + q] = -1;
     if (ng <= 0) return;
     const int total_gt = c_cols;                                                   // row pitch of C
     const float *Cb = C + ((size_t)layer * bs + b) * (size_t)nq * total_gt + (padded ? 0 : g0);   // Cb[q * pitch + g]
@@ -146,6 +152,14 @@ lsap_kernel(const float *__restrict__ C, const int *__restrict__ gt_start, const
         __syncwarp();
     }
 
+    if (match) {
+        __syncwarp();
+        for (int q = lane; q < nq; q += 32) {
+            const int g = rows_are_gt ? row4col[q] : col4row[q];
+            if (g >= 0) match[((size_t)layer * bs + b) * nq + q] = g;
+        }
+        return;
+    }
     // pairs in ascending query order (what linear_sum_assignment returns), gt indices made global like ops.py:120
     long long *oq = out_q + layer * out_layer_stride + out_start[b];
     long long *og = out_g + layer * out_layer_stride + out_start[b];
@@ -189,7 +203,30 @@ extern "C" int tamtr_linear_sum_assignment(const float *C, const int *gt_start_d
     TAMTR_CUDA_OK(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lsap_kernel<<<dim3(bs, n_layers), kAsgThreads, smem, (cudaStream_t)stream>>>(
         C, gt_start_dev, out_start_dev, out_q, out_g, bs, nq, c_cols, padded, max_cols, (int)(want / sizeof(float)),
-        out_layer_stride);
+        out_layer_stride, nullptr, nullptr);
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tamtr_linear_sum_assignment_padded(const float *C, const int *count_dev, int *match, int n_layers, int bs,
+                                                  int nq, int max_gt, void *stream) {
+    TAMTR_CHECK_ARG(C && count_dev && match, TAMTR_E_BADARG, "linear_sum_assignment_padded: null pointer");
+    TAMTR_CHECK_ARG(n_layers > 0 && bs > 0 && nq > 0 && max_gt > 0, TAMTR_E_BADARG, "linear_sum_assignment_padded: bad sizes");
+    TAMTR_CHECK_ARG(bs <= 65535 && n_layers <= 65535, TAMTR_E_UNSUPPORTED, "linear_sum_assignment_padded: grid too large");
+    const int max_cols = nq > max_gt ? nq : max_gt;
+    const size_t fixed = (size_t)max_cols * (3 * sizeof(double) + 4 * sizeof(int) + 2) + 16;
+    int dev = 0, max_smem = 0;
+    TAMTR_CUDA_OK(cudaGetDevice(&dev));
+    TAMTR_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    TAMTR_CHECK_ARG(fixed + 1024 <= (size_t)max_smem, TAMTR_E_UNSUPPORTED,
+                    "linear_sum_assignment_padded: %d columns need more shared memory than the device has", max_cols);
+    size_t want = (size_t)nq * max_gt * sizeof(float);
+    if (fixed + want > (size_t)max_smem) want = 0;
+    const size_t smem = fixed + want;
+    TAMTR_CUDA_OK(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lsap_kernel<<<dim3(bs, n_layers), kAsgThreads, smem, (cudaStream_t)stream>>>(
+        C, nullptr, nullptr, nullptr, nullptr, bs, nq, max_gt, 1, max_cols, (int)(want / sizeof(float)), 0, count_dev, match);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;

@@ -19,6 +19,8 @@ no data-path collective; the only exchange step is that gradient all-reduce.  B2
 `HeadTrainStep` is device-agnostic where it can be: with `use_graph=False` and a CPU module it runs the same
 flat-gradient / all-reduce logic under the gloo backend, which is how tests/test_dp_cpu.py covers the N>1 path.
 """
+import inspect
+
 import torch
 import torch.distributed as dist
 
@@ -206,8 +208,11 @@ class HeadTrainStep:
     """forward + backward (+ overlapped gradient exchange, + optimizer step) of a detection head on static buffers.
 
     module     : tamtr_b200.head.ManbaWorldDecoder / RTDETRDecoder (train mode), or any module for the CPU tests
-    loss_fn    : maps the module's outputs to a scalar
-    example    : tuple of example inputs (tensors / CdnPlan / None) fixing every shape
+    loss_fn    : maps the module's outputs -- or (outputs, the step's static inputs) -- to a scalar
+    example    : tuple of example inputs (tensors / loss.DeviceTargets / CdnPlan / None) fixing every shape.  With a
+                 DeviceTargets (ground truth padded to fixed shapes, denoising group built by a kernel from the counts)
+                 the captured step serves EVERY batch: load_inputs() refreshes its tensors in place.  A host-planned
+                 CdnPlan is baked into the capture (one batch only; kept for the reference's RNG-exact queries)
     autocast   : torch dtype or None
     use_graph  : capture the step into a CUDA graph (CUDA only).  As for any whole-network capture, eager
                  forward/backward passes of the SAME module instance done earlier in the process must have run on a
@@ -220,8 +225,18 @@ class HeadTrainStep:
     """
 
     def __init__(self, module, loss_fn, example, autocast=None, use_graph=True, warmup=3, fused_param_cast=True,
-                 optimizer=None, buckets=4):
+                 optimizer=None, buckets=4, share=None):
+        if share is not None:       # another capture (other input shapes) of the SAME training state: StepCache
+            return self._init_shared(module, loss_fn, example, share, warmup)
         self.module, self.loss_fn, self.autocast = module, loss_fn, autocast
+        # loss_fn(outputs) or loss_fn(outputs, static_inputs): the second form reads the step's own (in-place refreshed)
+        # ground truth -- a loss.DeviceTargets among the inputs -- so that a captured step follows every new batch
+        try:
+            n_pos = sum(1 for q in inspect.signature(loss_fn).parameters.values()
+                        if q.kind in (q.POSITIONAL_ONLY, q.POSITIONAL_OR_KEYWORD) and q.default is q.empty)
+        except (TypeError, ValueError):
+            n_pos = 1
+        self._loss_takes_inputs = n_pos >= 2
         self.lowp = LowpLeaves(module, lowp_param_names(module), autocast) \
             if (fused_param_cast and autocast is not None) else None
         sources = {} if self.lowp is None else self.lowp.source_of
@@ -258,12 +273,31 @@ class HeadTrainStep:
         if self.use_graph:
             self._capture(warmup)
 
+    def _init_shared(self, module, loss_fn, example, share, warmup):
+        """Same module, low-precision leaves, flat gradient / parameter / moment buffers, communication stream and
+        graph memory pool as `share`; only the static inputs and the captured graph are this step's own."""
+        assert module is share.module
+        for k in ("module", "autocast", "lowp", "device", "cuda", "use_graph", "overlap", "flat", "opt", "pack_grads",
+                  "_loss_takes_inputs"):
+            setattr(self, k, getattr(share, k))
+        self.loss_fn = loss_fn
+        self.static = [self._to_static(a) for a in example]
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._live = False
+        if self.overlap:
+            self.comm, self._bucket_of = share.comm, share._bucket_of
+            for t in self.flat.src:
+                t.register_post_accumulate_grad_hook(self._on_grad)
+        self.graph, self.launches_per_step = None, None
+        if self.use_graph:
+            self._capture(warmup, pool=share.graph.pool() if share.graph is not None else None)
+
     def _to_static(self, a):
         if isinstance(a, torch.Tensor):
             return a.detach().to(self.device).clone()
         if isinstance(a, (list, tuple)):
             return type(a)(self._to_static(x) for x in a)
-        if hasattr(a, "to") and hasattr(a, "materialize"):      # CdnPlan
+        if hasattr(a, "to") and (hasattr(a, "materialize") or hasattr(a, "load")):      # CdnPlan / loss.DeviceTargets
             return a.to(self.device)
         return a
 
@@ -315,7 +349,7 @@ class HeadTrainStep:
                     out = self.module(*self.static)
         else:
             out = self.module(*self.static)
-        loss = self.loss_fn(out)
+        loss = self.loss_fn(out, self.static) if self._loss_takes_inputs else self.loss_fn(out)
         loss.backward()
         self.loss.copy_(loss.detach())
 
@@ -339,7 +373,7 @@ class HeadTrainStep:
         if self.opt is not None and (self.overlap or world()[1] == 1):
             self.opt.step()                                     # (otherwise after the all-reduce, in run())
 
-    def _capture(self, warmup):
+    def _capture(self, warmup, pool=None):
         from . import _lib
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -350,23 +384,25 @@ class HeadTrainStep:
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, pool=pool):
             self._fwd_bwd()
         self.launches_per_step = _lib.launch_count() - before
         torch.cuda.synchronize(self.device)
 
     def load_inputs(self, inputs, non_blocking=True):
-        """Copy a new batch (same shapes) into the static buffers.  Entries that are not tensors -- a CdnPlan carries
-        the batch's denoising queries, their attention mask and counts -- are baked into a captured graph and CANNOT be
-        replaced here: pass None for them to keep the captured ones, or build a new step (dp.StepCache does so per
-        query-count bucket)."""
+        """Copy a new batch (same shapes) into the static buffers.  A loss.DeviceTargets entry is refreshed in place
+        (`load`: new boxes / classes / counts, any counts that fit its capacity).  Other non-tensor entries -- a host-planned
+        CdnPlan carries one batch's denoising queries, mask and counts -- are baked into a captured graph and CANNOT be
+        replaced: pass None to keep them, or build a new step (StepCache keeps one per denoising-capacity bucket)."""
         def cp(dst, src):
+            if src is None or src is dst:
+                return
             if isinstance(dst, torch.Tensor):
                 dst.copy_(src, non_blocking=non_blocking)
             elif isinstance(dst, (list, tuple)):
                 for d, s in zip(dst, src):
                     cp(d, s)
-            elif src is not None and src is not dst:
+            else:
                 if hasattr(dst, "load"):
                     dst.load(src, non_blocking=non_blocking)        # in-place update of a padded plan's device tensors
                 else:
@@ -386,6 +422,55 @@ class HeadTrainStep:
             if self.opt is not None:
                 self.opt.step()
         return self.loss
+
+
+class StepCache:
+    """Training steps for batches whose ground-truth counts vary: ONE captured HeadTrainStep per denoising-capacity bucket.
+
+    The reference sizes its denoising group per batch -- Lq = nq + 2 * max_gt * max(1, num_dn // max_gt)
+    (ultralytics/models/utils/ops.py:194-195, 242), 200 for max_gt <= 100 and 2 * max_gt above, data-dependent -- and
+    rebuilds everything eagerly.  Here the ground truth travels in fixed-shape device tensors (loss.DeviceTargets) and the
+    group is laid out by a kernel inside a bucket of `dn_capacity` slots (padding slots are masked out of the attention
+    and ignored by the loss), so one graph serves every batch of its bucket: a VisDrone-like stream with <= 100 boxes per
+    image never leaves the first bucket; a denser batch triggers ONE more capture (same weights, gradient / optimizer
+    buffers and graph memory pool), after which that bucket replays too.
+
+    make_inputs(batch, targets) -> the example tuple for HeadTrainStep with `targets` (a DeviceTargets) in it.
+    run(batch, tensors) : batch = the reference's dict (cls / bboxes / gt_groups, host or device); tensors = the other
+    inputs in the order of the example (None entries are kept)."""
+
+    def __init__(self, module, loss_fn, make_inputs, num_dn=100, **step_args):
+        self.module, self.loss_fn, self.make_inputs, self.num_dn = module, loss_fn, make_inputs, num_dn
+        self.step_args = step_args
+        self.steps = {}
+
+    @staticmethod
+    def bucket(max_gt, num_dn=100):
+        """(dn_capacity, ground-truth slots per image) of the bucket a batch with this largest count falls into."""
+        from .loss import DeviceTargets
+        cap = DeviceTargets.capacity_for(max_gt, num_dn)
+        return cap, (max(num_dn, 1) if cap <= 2 * num_dn else cap // 2)     # largest per-image count the bucket holds
+
+    def step_for(self, batch):
+        from .loss import DeviceTargets
+        groups = [int(n) for n in batch["gt_groups"]]
+        cap, slots = self.bucket(max(groups + [0]), self.num_dn)
+        st = self.steps.get(cap)
+        if st is None:
+            dev = next(self.module.parameters()).device
+            tgt = DeviceTargets(len(groups), slots, dev, cap, self.num_dn).load(batch)
+            first = next(iter(self.steps.values()), None)
+            args = dict(self.step_args) if first is None else {"warmup": self.step_args.get("warmup", 3)}
+            st = self.steps[cap] = HeadTrainStep(self.module, self.loss_fn, self.make_inputs(batch, tgt), share=first, **args)
+            st.targets = next(a for a in st.static if isinstance(a, DeviceTargets))
+        return st
+
+    def run(self, batch, tensors=None, reduce=True):
+        st = self.step_for(batch)
+        st.targets.load(batch)
+        if tensors is not None:
+            st.load_inputs([None if a is st.targets else t for a, t in zip(st.static, tensors)])
+        return st.run(reduce=reduce)
 
 
 class HeadInferStep:

@@ -16,11 +16,12 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .loss import DeviceTargets
 from .vss import VSSBlock
 from .modules import (MLP, ContrastiveHeadMLP, DeformableTransformerDecoder, DeformableTransformerDecoderLayer,
                       TextDeformableTransformerDecoder)
 
-__all__ = ("RTDETRDecoder", "ManbaWorldDecoder", "get_cdn_group", "plan_cdn_group", "CdnPlan")
+__all__ = ("RTDETRDecoder", "ManbaWorldDecoder", "get_cdn_group", "plan_cdn_group", "CdnPlan", "cdn_group_device")
 
 
 def _xywh_to_xyxy(b):
@@ -122,6 +123,42 @@ def get_cdn_group(batch, num_classes, num_queries, class_embed, num_dn=100, cls_
     if plan is None:
         return None, None, None, None
     return plan.materialize(class_embed)
+
+
+def cdn_group_device(targets, num_classes, num_queries, class_embed, num_dn=100, cls_noise_ratio=0.5, box_noise_scale=1.0):
+    """get_cdn_group (ops.py:152-291) for a batch held in fixed-shape device tensors (loss.DeviceTargets), as ONE kernel
+    (tamtr_cdn_group) + the class-embedding gather: no host planning, no data-dependent shapes, so the training step can
+    be captured once and replayed on every batch.  The group occupies the first 2 * max_gt * num_group of
+    `targets.dn_capacity` slots exactly as the reference lays it out; the remaining slots of the bucket are padding
+    (blocked in the attention mask, ignored by the loss), so the matching and denoising queries see what they see in the
+    reference.
+
+    Randomness: the reference draws from torch's global generator with data-dependent sizes (ops.py:217-229), which no
+    fixed-shape program can reproduce draw for draw.  Contract here: ONE torch.rand([B, capacity, 10]) per step (graph-safe
+    Philox); slot (b, s) consumes its ten numbers as (label-flip test, replacement label, 4 box-noise signs, 4 box-noise
+    magnitudes) through the reference's formulas -- same distributions, and bit-identical queries for identical numbers
+    (tests/test_cdn.py checks the formulas against the reference with its RNG calls replaced by the same numbers)."""
+    from . import _lib
+    _lib.require_cuda(targets.boxes, class_embed)
+    B, G, D = targets.bs, targets.max_gt, targets.dn_capacity
+    if D is None:
+        raise RuntimeError("tamtr_b200: DeviceTargets.dn_capacity is not set (use DeviceTargets.from_batch / capacity_for)")
+    dev = targets.boxes.device
+    uni = torch.rand(B, D, 10, dtype=torch.float32, device=dev)
+    dn_cls = torch.empty(B, D, dtype=torch.int64, device=dev)
+    dn_box = torch.empty(B, D, 4, dtype=torch.float32, device=dev)
+    valid = torch.empty(B, D, dtype=torch.float32, device=dev)
+    Lq = D + num_queries
+    mask = torch.empty(Lq, Lq, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().tamtr_cdn_group(targets.boxes.data_ptr(), targets.cls.data_ptr(), targets.count.data_ptr(),
+                                        uni.data_ptr(), dn_cls.data_ptr(), dn_box.data_ptr(), valid.data_ptr(),
+                                        mask.data_ptr(), B, G, D, num_queries, num_classes, int(num_dn),
+                                        float(cls_noise_ratio), float(box_noise_scale), _lib.stream_ptr(dev))
+    _lib.check(rc, "cdn_group")
+    embed = ops.embed_rows(class_embed, dn_cls) * valid.unsqueeze(-1).to(class_embed.dtype)
+    meta = {"dn_num_split": [D, num_queries], "num_dn_cfg": int(num_dn), "dn_valid": valid, "dn_cls": dn_cls}
+    return embed, dn_box, mask.view(torch.bool), meta
 
 
 class _HeadBase(nn.Module):
@@ -255,7 +292,12 @@ class _HeadBase(nn.Module):
         return feats, shapes, hub
 
     def _cdn(self, batch):
-        if isinstance(batch, CdnPlan):      # pre-planned on the host (dp.HeadTrainStep): only the embedding gather
+        if isinstance(batch, DeviceTargets):   # ground truth in fixed-shape device tensors: the group is built by a kernel
+            if not self.training or self.num_denoising <= 0:
+                return None, None, None, None
+            return cdn_group_device(batch, self.nc, self.num_queries, self.denoising_class_embed.weight,
+                                    self.num_denoising, self.label_noise_ratio, self.box_noise_scale)
+        if isinstance(batch, CdnPlan):      # pre-planned on the host: only the embedding gather
             return batch.materialize(self.denoising_class_embed.weight)
         return get_cdn_group(batch, self.nc, self.num_queries, self.denoising_class_embed.weight,
                              self.num_denoising, self.label_noise_ratio, self.box_noise_scale, self.training)

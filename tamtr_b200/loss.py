@@ -1,79 +1,27 @@
-"""Detection loss of the TAM-TR / RT-DETR heads with the query <-> ground-truth matching ON THE DEVICE.
+"""Detection loss of the TAM-TR / RT-DETR heads, matching included, ON THE DEVICE and with fixed shapes.
 
 Mirrors (same class names, constructor arguments, forward signatures, loss-dict keys):
   HungarianMatcher       ultralytics/models/utils/ops.py:12-121
   DETRLoss               ultralytics/models/utils/loss.py:14-373
   RTDETRDetectionLoss    ultralytics/models/utils/loss.py:376-443
-  VarifocalLoss / FocalLoss  ultralytics/utils/loss.py:135-178
-  bbox_iou (IoU and RIOU branches)  ultralytics/utils/metrics.py:71-130
+The arithmetic of VarifocalLoss / FocalLoss (ultralytics/utils/loss.py:135-178) and bbox_iou's IoU / RIOU branches
+(ultralytics/utils/metrics.py:71-130) lives in csrc/detloss.cu.
 
 The reference builds the cost matrix on the GPU, copies it to the host and runs scipy.optimize.linear_sum_assignment
 per image (ops.py:116-117) -- once per decoder layer plus once for the encoder proposals, i.e. four host round trips
-in the middle of every training step.  Here the assignment is `tamtr_linear_sum_assignment` (csrc/assign.cu: the
-same shortest-augmenting-path algorithm, fp64 arithmetic and tie order as SciPy, one warp per image), all layers in
-one launch, and every index tensor that depends only on the batch's ground-truth counts is built once per distinct
-`gt_groups` -- no synchronisation, CUDA-graph capturable.
+in the middle of every training step -- and evaluates the losses layer by layer in ~150 small eager ops.  Here a
+batch's ground truth lives in padded device tensors (DeviceTargets); `tamtr_match_cost` prices every query against its
+own image's boxes, `tamtr_linear_sum_assignment_padded` (csrc/assign.cu: the same shortest-augmenting-path algorithm,
+fp64 arithmetic and tie order as SciPy, one warp per image) assigns all layers in one launch, and
+`tamtr_detection_loss` evaluates the losses of all layers AND their gradients in one pass.  Nothing depends on the
+host knowing the ground-truth counts: no synchronisation, one captured CUDA graph serves every batch.
 """
-import math
-
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib
 
-__all__ = ("HungarianMatcher", "DETRLoss", "RTDETRDetectionLoss", "VarifocalLoss", "FocalLoss", "bbox_iou",
-           "linear_sum_assignment")
-
-
-def bbox_iou(box1, box2, xywh=True, RIOU=False, eps=1e-7):
-    """IoU / RIoU of broadcastable boxes (metrics.py:71-130, the two branches this path uses), same op order."""
-    if xywh:
-        (x1, y1, w1, h1), (x2, y2, w2, h2) = box1.chunk(4, -1), box2.chunk(4, -1)
-        w1_, h1_, w2_, h2_ = w1 / 2, h1 / 2, w2 / 2, h2 / 2
-        b1_x1, b1_x2, b1_y1, b1_y2 = x1 - w1_, x1 + w1_, y1 - h1_, y1 + h1_
-        b2_x1, b2_x2, b2_y1, b2_y2 = x2 - w2_, x2 + w2_, y2 - h2_, y2 + h2_
-    else:
-        b1_x1, b1_y1, b1_x2, b1_y2 = box1.chunk(4, -1)
-        b2_x1, b2_y1, b2_x2, b2_y2 = box2.chunk(4, -1)
-        w1, h1 = b1_x2 - b1_x1, b1_y2 - b1_y1 + eps
-        w2, h2 = b2_x2 - b2_x1, b2_y2 - b2_y1 + eps
-    inter = (b1_x2.minimum(b2_x2) - b1_x1.maximum(b2_x1)).clamp_(0) * \
-            (b1_y2.minimum(b2_y2) - b1_y1.maximum(b2_y1)).clamp_(0)
-    union = w1 * h1 + w2 * h2 - inter + eps
-    iou = inter / union
-    if not RIOU:
-        return iou
-    rho2 = ((b2_x1 + b2_x2 - b1_x1 - b1_x2) ** 2 + (b2_y1 + b2_y2 - b1_y1 - b1_y2) ** 2) / 4
-    maxwh1 = torch.max(w1, h1)
-    maxwh2 = torch.max(w2, h2)
-    c2 = (maxwh1 + maxwh2 + torch.sqrt(rho2) + eps).pow(2)
-    v = (4 / math.pi ** 2) * (torch.atan(w2 / h2) - torch.atan(w1 / h1)).pow(2)
-    with torch.no_grad():
-        alpha = v / (v - iou + (1 + eps))
-    return iou - (rho2 / c2 + v * alpha)
-
-
-class VarifocalLoss(nn.Module):
-    @staticmethod
-    def forward(pred_score, gt_score, label, alpha=0.75, gamma=2.0):
-        weight = alpha * pred_score.sigmoid().pow(gamma) * (1 - label) + gt_score * label
-        with torch.autocast("cuda", enabled=False):
-            loss = (F.binary_cross_entropy_with_logits(pred_score.float(), gt_score.float(), reduction='none') *
-                    weight).mean(1).sum()
-        return loss
-
-
-class FocalLoss(nn.Module):
-    @staticmethod
-    def forward(pred, label, gamma=1.5, alpha=0.25):
-        loss = F.binary_cross_entropy_with_logits(pred, label, reduction='none')
-        pred_prob = pred.sigmoid()
-        p_t = label * pred_prob + (1 - label) * (1 - pred_prob)
-        loss = loss * (1.0 - p_t) ** gamma
-        if alpha > 0:
-            loss = loss * (label * alpha + (1 - label) * (1 - alpha))
-        return loss.mean(1).sum()
+__all__ = ("HungarianMatcher", "DETRLoss", "RTDETRDetectionLoss", "DeviceTargets", "linear_sum_assignment", "match_padded")
 
 
 # ------------------------------------------------------------------------------------------------ batch bookkeeping
@@ -97,6 +45,12 @@ class _Groups:
                                     or [torch.zeros(0, dtype=torch.long)]).to(device)
         self.max_gt = max([int(n) for n in gt_groups] + [0])
         self.total_gt = starts[-1]
+        # (image, slot) of every ground truth in a padded [B, G, .] layout, and the counts on the device
+        self.gt_image = torch.cat([torch.full((int(n),), i, dtype=torch.long) for i, n in enumerate(gt_groups)]
+                                  or [torch.zeros(0, dtype=torch.long)]).to(device)
+        self.gt_slot = torch.cat([torch.arange(int(n), dtype=torch.long) for n in gt_groups]
+                                 or [torch.zeros(0, dtype=torch.long)]).to(device)
+        self.counts_dev = torch.tensor([int(n) for n in gt_groups], dtype=torch.int32).to(device)
         # global gt index of column g of image b's own (padded) cost matrix; padding columns repeat a valid index
         pad = torch.zeros(len(gt_groups), max(self.max_gt, 1), dtype=torch.long)
         for b, n in enumerate(gt_groups):
@@ -138,9 +92,177 @@ def linear_sum_assignment(C, gt_groups, padded=False):
     return grp.pair_image, out_q, out_g
 
 
+class DeviceTargets:
+    """The ground truth of a batch in FIXED-shape device tensors -- boxes [B, G, 4] (cx, cy, w, h), cls [B, G] int64,
+    count [B] int32 -- so that one captured CUDA graph (denoising group, matching, loss) serves every batch: `load()`
+    refreshes the tensors in place; everything that depends on the counts is decided inside the kernels.
+
+    `dn_capacity`: slots reserved for denoising queries (the bucket's Lq = dn_capacity + num_queries).  The reference
+    sizes its group per batch, 2 * max_gt * max(1, num_dn // max_gt) (ops.py:194-195, 242: at most 2 * num_dn while no
+    image has more than num_dn boxes, 2 * max_gt beyond); `capacity_for()` returns the bucket that holds it."""
+
+    def __init__(self, bs, max_gt, device, dn_capacity=None, num_dn=100):
+        self.bs, self.max_gt, self.device = int(bs), int(max_gt), torch.device(device)
+        self.boxes = torch.zeros(bs, max_gt, 4, dtype=torch.float32, device=device)
+        self.cls = torch.zeros(bs, max_gt, dtype=torch.int64, device=device)
+        self.count = torch.zeros(bs, dtype=torch.int32, device=device)
+        self.dn_capacity, self.num_dn = dn_capacity, int(num_dn)
+        pin = self.device.type == "cuda"
+        self._h_boxes = torch.zeros(bs, max_gt, 4, dtype=torch.float32, pin_memory=pin)
+        self._h_cls = torch.zeros(bs, max_gt, dtype=torch.int64, pin_memory=pin)
+        self._h_count = torch.zeros(bs, dtype=torch.int32, pin_memory=pin)
+        self._copied = None         # event after the last asynchronous copy out of the pinned staging buffers
+
+    @staticmethod
+    def dn_queries(max_gt, num_dn=100):
+        return 0 if max_gt <= 0 or num_dn <= 0 else 2 * max_gt * max(1, num_dn // max_gt)
+
+    @classmethod
+    def capacity_for(cls, max_gt, num_dn=100):
+        """Bucket capacities: 2 * num_dn (every batch without an image of more than num_dn boxes: 200 by default), then
+        growing by ~1.5x in multiples of 64 (320, 512, 768, 1152 ...)."""
+        need, cap = cls.dn_queries(max_gt, num_dn), max(2 * int(num_dn), 1)
+        while cap < need:
+            cap = (cap * 3 // 2 + 63) // 64 * 64
+        return cap
+
+    def to(self, device):
+        if torch.device(device) == self.device:
+            return self
+        out = DeviceTargets(self.bs, self.max_gt, device, self.dn_capacity, self.num_dn)
+        out.boxes.copy_(self.boxes)
+        out.cls.copy_(self.cls)
+        out.count.copy_(self.count)
+        return out
+
+    def load(self, batch, non_blocking=True):
+        """batch: the reference's dict -- 'cls' [n], 'bboxes' [n, 4], 'gt_groups' [B ints], ground truths grouped image
+        by image (data/dataset collate order) -- on the host or the device, or another DeviceTargets."""
+        if isinstance(batch, DeviceTargets):
+            self.boxes.copy_(batch.boxes, non_blocking=non_blocking)
+            self.cls.copy_(batch.cls, non_blocking=non_blocking)
+            self.count.copy_(batch.count, non_blocking=non_blocking)
+            return self
+        groups = [int(n) for n in batch["gt_groups"]]
+        if len(groups) != self.bs or max(groups + [0]) > self.max_gt:
+            raise RuntimeError(f"tamtr_b200: batch with gt_groups {groups} does not fit DeviceTargets(bs={self.bs}, "
+                               f"max_gt={self.max_gt})")
+        if self.dn_capacity is not None and self.dn_queries(max(groups + [0]), self.num_dn) > self.dn_capacity:
+            raise RuntimeError("tamtr_b200: this batch needs more denoising slots than the captured bucket holds")
+        boxes, cls = batch["bboxes"], batch["cls"].reshape(-1)
+        if boxes.is_cuda:                       # already on the device (the reference's loss call): one scatter each
+            grp = _Groups.get(groups, 1, boxes.device)
+            self.boxes.zero_()
+            self.cls.zero_()
+            if grp.total_gt:
+                self.boxes[grp.gt_image, grp.gt_slot] = boxes.float()
+                self.cls[grp.gt_image, grp.gt_slot] = cls.long()
+            self.count.copy_(grp.counts_dev)
+            return self
+        if self._copied is not None:
+            self._copied.synchronize()          # the previous load's copies must have left the staging buffers
+        self._h_boxes.zero_()
+        self._h_cls.zero_()
+        start = 0
+        for b, n in enumerate(groups):
+            self._h_boxes[b, :n] = boxes[start:start + n]
+            self._h_cls[b, :n] = cls[start:start + n]
+            start += n
+        self._h_count.copy_(torch.tensor(groups, dtype=torch.int32))
+        self.boxes.copy_(self._h_boxes, non_blocking=non_blocking)
+        self.cls.copy_(self._h_cls, non_blocking=non_blocking)
+        self.count.copy_(self._h_count, non_blocking=non_blocking)
+        if self.device.type == "cuda":
+            self._copied = self._copied or torch.cuda.Event()
+            self._copied.record(torch.cuda.current_stream(self.device))
+        return self
+
+    @classmethod
+    def from_batch(cls, batch, device, max_gt=None, num_dn=100):
+        groups = [int(n) for n in batch["gt_groups"]]
+        g = max(groups + [1]) if max_gt is None else max_gt
+        return cls(len(groups), g, device, cls.capacity_for(max(groups + [0]), num_dn), num_dn).load(batch)
+
+
+def _as_targets(batch, device):
+    return batch if isinstance(batch, DeviceTargets) else DeviceTargets.from_batch(batch, device)
+
+
+def match_padded(pred_bboxes, pred_scores, tgt, alpha=0.25, gamma=2.0, gains=(2.0, 5.0, 2.0)):
+    """pred_* [NL, B, Q, .] -> match [NL, B, Q] int32 (ground-truth index inside the image, or -1): the cost matrices of
+    ops.py:77-112 (tamtr_match_cost) and scipy's assignment per (layer, image) (tamtr_linear_sum_assignment_padded), two
+    launches, no host synchronisation."""
+    _lib.require_cuda(pred_bboxes, pred_scores)
+    NL, B, Q, nc = pred_scores.shape
+    G = tgt.max_gt
+    pb = pred_bboxes.detach().float().contiguous()
+    ps = pred_scores.detach().float().contiguous()
+    cost = torch.empty(NL, B, Q, G, dtype=torch.float32, device=pb.device)
+    match = torch.empty(NL, B, Q, dtype=torch.int32, device=pb.device)
+    lib = _lib.lib()
+    with torch.cuda.device(pb.device):
+        st = _lib.stream_ptr(pb.device)
+        _lib.check(lib.tamtr_match_cost(pb.data_ptr(), ps.data_ptr(), tgt.boxes.data_ptr(), tgt.cls.data_ptr(), cost.data_ptr(),
+                                        NL, B, Q, G, nc, alpha, gamma, gains[0], gains[1], gains[2], st), "match_cost")
+        _lib.check(lib.tamtr_linear_sum_assignment_padded(cost.data_ptr(), tgt.count.data_ptr(), match.data_ptr(), NL, B, Q,
+                                                          G, st), "linear_sum_assignment_padded")
+    return match
+
+
+class _DetLossFn(torch.autograd.Function):
+    """(class, bbox, giou) losses of NL layers [NL, 3], forward values and prediction gradients from ONE kernel pass
+    (tamtr_detection_loss); the backward only scales the stored derivatives by the upstream gradients."""
+
+    @staticmethod
+    def forward(ctx, pred_bboxes, pred_scores, tgt, match, dn_group, num_dn, use_vfl, gains):
+        NL, B, Q, nc = pred_scores.shape
+        pb, ps = pred_bboxes.float().contiguous(), pred_scores.float().contiguous()
+        dev = pb.device
+        partial = torch.empty(NL, B, 3, dtype=torch.float32, device=dev)
+        out = torch.empty(NL * 3 + 1, dtype=torch.float32, device=dev)
+        d_l1, d_giou = torch.empty_like(pb), torch.empty_like(pb)
+        d_cls = torch.empty_like(ps)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().tamtr_detection_loss(
+                pb.data_ptr(), ps.data_ptr(), tgt.boxes.data_ptr(), tgt.cls.data_ptr(), tgt.count.data_ptr(),
+                None if match is None else match.data_ptr(), partial.data_ptr(), out.data_ptr(), d_l1.data_ptr(),
+                d_giou.data_ptr(), d_cls.data_ptr(), NL, B, Q, tgt.max_gt, nc, int(dn_group), int(num_dn), int(use_vfl),
+                gains[0], gains[1], gains[2], _lib.stream_ptr(dev))
+        _lib.check(rc, "detection_loss")
+        ctx.save_for_backward(d_l1, d_giou, d_cls, out)
+        ctx.gains = gains
+        ctx.dtypes = (pred_bboxes.dtype, pred_scores.dtype)
+        return out[:NL * 3].view(NL, 3)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        d_l1, d_giou, d_cls, out = ctx.saved_tensors
+        NL = g.shape[0]
+        scale = (g.float() * out[NL * 3]).view(NL, 3, 1, 1, 1)                # upstream gradient / matched pairs
+        gb = (scale[:, 1] * ctx.gains[1]) * d_l1 + (scale[:, 2] * ctx.gains[2]) * d_giou
+        gs = (scale[:, 0] * ctx.gains[0]) * d_cls
+        return gb.to(ctx.dtypes[0]), gs.to(ctx.dtypes[1]), None, None, None, None, None, None
+
+
+def _loss_dict(per_layer, aux, postfix, with_class=True):
+    """loss.py:328-373: the last layer's three losses + the sums over the auxiliary layers."""
+    out = {}
+    if with_class:
+        out[f"loss_class{postfix}"] = per_layer[-1, 0]
+    out[f"loss_bbox{postfix}"] = per_layer[-1, 1]
+    out[f"loss_giou{postfix}"] = per_layer[-1, 2]
+    if aux:
+        rest = per_layer[:-1].sum(0)
+        out[f"loss_class_aux{postfix}"] = rest[0]
+        out[f"loss_bbox_aux{postfix}"] = rest[1]
+        out[f"loss_giou_aux{postfix}"] = rest[2]
+    return out
+
+
 class HungarianMatcher(nn.Module):
     """ops.py:12-121.  forward() keeps the reference's signature and return value (a list of (query idx, gt idx) per
-    image); match_layers() is the batched form the loss uses (all decoder layers in one launch)."""
+    image); match_layers() / match_padded() are the batched forms the loss uses (all decoder layers in one launch)."""
 
     def __init__(self, cost_gain=None, use_fl=True, with_mask=False, num_sample_points=12544, alpha=0.25, gamma=2.0):
         super().__init__()
@@ -155,54 +277,32 @@ class HungarianMatcher(nn.Module):
         self.alpha = alpha
         self.gamma = gamma
 
-    def cost_matrix(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls):
-        """[..., nq, 4], [..., nq, nc] -> [..., nq, total_gt] (ops.py:77-112, same op order)."""
-        pred_scores = pred_scores.detach()
-        pred_scores = F.sigmoid(pred_scores) if self.use_fl else F.softmax(pred_scores, dim=-1)
-        pred_bboxes = pred_bboxes.detach()
-        pred_scores = pred_scores[..., gt_cls]
-        if self.use_fl:
-            neg_cost_class = (1 - self.alpha) * (pred_scores ** self.gamma) * (-(1 - pred_scores + 1e-8).log())
-            pos_cost_class = self.alpha * ((1 - pred_scores) ** self.gamma) * (-(pred_scores + 1e-8).log())
-            cost_class = pos_cost_class - neg_cost_class
-        else:
-            cost_class = -pred_scores
-        cost_bbox = (pred_bboxes.unsqueeze(-2) - gt_bboxes).abs().sum(-1)
-        cost_giou = 1.0 - bbox_iou(pred_bboxes.unsqueeze(-2), gt_bboxes, xywh=True, RIOU=True).squeeze(-1)
-        C = self.cost_gain['class'] * cost_class + self.cost_gain['bbox'] * cost_bbox + self.cost_gain['giou'] * cost_giou
-        return torch.where(torch.isfinite(C), C, torch.zeros((), dtype=C.dtype, device=C.device))
-
-    def cost_matrix_per_image(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, gt_groups):
-        """[n_layers, bs, nq, .] -> [n_layers, bs, nq, max_gt]: only each image's OWN ground truths (the reference's
-        [bs*nq, total_gt] matrix prices every query against every image's boxes and then throws all but one block per
-        image away, ops.py:104-116).  Element-wise the same arithmetic, so the kept entries are bit-identical."""
-        grp = _Groups.get(gt_groups, pred_scores.shape[2], pred_scores.device)
-        gtb = gt_bboxes[grp.pad_index].unsqueeze(1)                                    # [bs, 1, max_gt, 4]
-        cls = gt_cls[grp.pad_index]                                                    # [bs, max_gt]
-        p = pred_scores.detach()
-        p = F.sigmoid(p) if self.use_fl else F.softmax(p, dim=-1)
-        n_l, bs, nq = p.shape[:3]
-        p = torch.gather(p, 3, cls.view(1, bs, 1, -1).expand(n_l, bs, nq, -1))
-        box = pred_bboxes.detach()
-        if self.use_fl:
-            neg_cost_class = (1 - self.alpha) * (p ** self.gamma) * (-(1 - p + 1e-8).log())
-            pos_cost_class = self.alpha * ((1 - p) ** self.gamma) * (-(p + 1e-8).log())
-            cost_class = pos_cost_class - neg_cost_class
-        else:
-            cost_class = -p
-        cost_bbox = (box.unsqueeze(-2) - gtb).abs().sum(-1)
-        cost_giou = 1.0 - bbox_iou(box.unsqueeze(-2), gtb, xywh=True, RIOU=True).squeeze(-1)
-        C = self.cost_gain['class'] * cost_class + self.cost_gain['bbox'] * cost_bbox + self.cost_gain['giou'] * cost_giou
-        return torch.where(torch.isfinite(C), C, torch.zeros((), dtype=C.dtype, device=C.device))
+    def match_padded(self, pred_bboxes, pred_scores, tgt):
+        if not self.use_fl:
+            raise NotImplementedError("tamtr_b200: the softmax class cost (use_fl=False) is not on TAM-TR's path")
+        g = self.cost_gain
+        return match_padded(pred_bboxes, pred_scores, tgt, float(self.alpha), float(self.gamma),
+                            (float(g['class']), float(g['bbox']), float(g['giou'])))
 
     def match_layers(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, gt_groups):
-        """pred_* [n_layers, bs, nq, .] -> (image idx [P], query idx [n_layers, P], gt idx [n_layers, P])."""
+        """pred_* [n_layers, bs, nq, .] -> (image idx [P], query idx [n_layers, P], global gt idx [n_layers, P]), the pairs
+        of each image in ascending query order -- what scipy returns per image (ops.py:116-121).  (This list form needs the
+        number of pairs on the host; the loss itself works on the fixed-shape match array.)"""
+        n_l = pred_bboxes.shape[0]
+        dev = pred_bboxes.device
         if sum(gt_groups) == 0:
-            z = torch.zeros(0, dtype=torch.long, device=pred_bboxes.device)
-            e = torch.zeros(pred_bboxes.shape[0], 0, dtype=torch.long, device=pred_bboxes.device)
+            z = torch.zeros(0, dtype=torch.long, device=dev)
+            e = torch.zeros(n_l, 0, dtype=torch.long, device=dev)
             return z, e, e.clone()
-        C = self.cost_matrix_per_image(pred_bboxes.float(), pred_scores.float(), gt_bboxes.float(), gt_cls, gt_groups)
-        return linear_sum_assignment(C, gt_groups, padded=True)
+        tgt = DeviceTargets.from_batch({"bboxes": gt_bboxes, "cls": gt_cls, "gt_groups": gt_groups}, dev)
+        match = self.match_padded(pred_bboxes, pred_scores, tgt)                # [n_l, bs, nq]
+        grp = _Groups.get(gt_groups, pred_scores.shape[2], dev)
+        hit = match >= 0
+        img, q = hit[0].nonzero(as_tuple=True)                                  # the same count in every layer
+        qs = torch.stack([hit[l].nonzero(as_tuple=True)[1] for l in range(n_l)])
+        lay = torch.arange(n_l, device=dev).unsqueeze(1)
+        gs = match[lay, img.unsqueeze(0), qs].long() + grp.gt_start[:-1].long()[img].unsqueeze(0)
+        return img, qs, gs
 
     def forward(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, gt_groups, masks=None, gt_mask=None):
         bs, nq, nc = pred_scores.shape
@@ -214,7 +314,9 @@ class HungarianMatcher(nn.Module):
 
 
 class DETRLoss(nn.Module):
-    """loss.py:14-373 (focal / varifocal classification loss, L1 + RIoU box losses, auxiliary losses per layer)."""
+    """loss.py:14-373 (varifocal / focal classification loss, L1 + RIoU box losses, auxiliary losses per layer) on the
+    kernels of csrc/detloss.cu: matching and the losses of ALL layers in four launches, fixed shapes, no host round trip
+    (the reference matches and evaluates layer by layer, loss.py:232-243, 293-300, with scipy on the host)."""
 
     def __init__(self, nc=80, loss_gain=None, aux_loss=True, use_fl=True, use_vfl=False, use_sl=False, use_emasl=False,
                  use_svfl=False, use_emasvfl=False, use_uni_match=False, uni_match_ind=0):
@@ -227,195 +329,52 @@ class DETRLoss(nn.Module):
         self.matcher = HungarianMatcher(cost_gain={'class': 2, 'bbox': 5, 'giou': 2})
         self.loss_gain = loss_gain
         self.aux_loss = aux_loss
-        self.fl = FocalLoss() if use_fl else None
-        self.vfl = VarifocalLoss() if use_vfl else None
+        self.fl = use_fl            # (the reference stores FocalLoss() / VarifocalLoss() modules or None here; only their
+        self.vfl = use_vfl          #  truth value is used: the arithmetic of utils/loss.py:135-178 lives in the kernel)
         self.use_uni_match = use_uni_match
         self.uni_match_ind = uni_match_ind
         self.device = None
 
-    # ---- per-layer pieces (loss.py:85-167, 282-326) on pre-matched pairs
-    def _get_loss_class(self, pred_scores, targets, gt_scores, num_gts, postfix=''):
-        bs, nq = pred_scores.shape[:2]
-        one_hot = torch.zeros((bs, nq, self.nc + 1), dtype=torch.int64, device=targets.device)
-        one_hot.scatter_(2, targets.unsqueeze(-1), 1)
-        one_hot = one_hot[..., :-1]
-        gt_scores = gt_scores.view(bs, nq, 1) * one_hot
-        if self.fl:
-            if num_gts and self.vfl:
-                loss_cls = self.vfl(pred_scores, gt_scores, one_hot)
-            else:
-                loss_cls = self.fl(pred_scores, one_hot.float())
-            loss_cls = loss_cls / (max(num_gts, 1) / nq)
-        else:
-            loss_cls = nn.BCEWithLogitsLoss(reduction='none')(pred_scores, gt_scores).mean(1).sum()
-        return {f'loss_class{postfix}': loss_cls.squeeze() * self.loss_gain['class']}
-
-    def _get_loss_bbox(self, pred_bboxes, gt_bboxes, postfix=''):
-        name_bbox, name_giou = f'loss_bbox{postfix}', f'loss_giou{postfix}'
-        if len(gt_bboxes) == 0:
-            z = torch.zeros((), device=self.device)       # (a fill kernel, not a host->device copy: graph-capturable)
-            return {name_bbox: z, name_giou: z.clone()}
-        loss = {name_bbox: self.loss_gain['bbox'] * F.l1_loss(pred_bboxes, gt_bboxes, reduction='sum') / len(gt_bboxes)}
-        giou = 1.0 - bbox_iou(pred_bboxes, gt_bboxes, xywh=True, RIOU=True)
-        loss[name_giou] = self.loss_gain['giou'] * (giou.sum() / len(gt_bboxes))
-        return {k: v.squeeze() for k, v in loss.items()}
-
-    def _get_loss(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, gt_groups, masks=None, gt_mask=None, postfix='',
-                  match_indices=None):
-        """One layer.  match_indices: None (match here), the reference's list of (query idx, gt idx) per image, or the
-        flat triple (image idx, query idx, gt idx)."""
-        if match_indices is None:
-            img, q, g = self.matcher.match_layers(pred_bboxes.unsqueeze(0), pred_scores.unsqueeze(0), gt_bboxes, gt_cls,
-                                                  gt_groups)
-            match_indices = (img, q[0], g[0])
-        if isinstance(match_indices, list):
-            dev = pred_bboxes.device
-            img = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(match_indices)]).to(dev)
-            match_indices = (img, torch.cat([s for s, _ in match_indices]).to(dev),
-                             torch.cat([d for _, d in match_indices]).to(dev))
-        img, src, gt_idx = match_indices
-        idx = (img, src)
-        bs, nq = pred_bboxes.shape[:2]
-        pred_bboxes, gt_bboxes = pred_bboxes[idx], gt_bboxes[gt_idx]
-        if pred_scores is None:
-            return dict(self._get_loss_bbox(pred_bboxes, gt_bboxes, postfix))
-        targets = torch.full((bs, nq), self.nc, device=pred_scores.device, dtype=gt_cls.dtype)
-        targets[idx] = gt_cls[gt_idx]
-        gt_scores = torch.zeros([bs, nq], device=pred_scores.device)
-        if len(gt_bboxes):
-            gt_scores[idx] = bbox_iou(pred_bboxes.detach(), gt_bboxes, xywh=True).squeeze(-1)
-        loss = {}
-        loss.update(self._get_loss_class(pred_scores, targets, gt_scores, len(gt_bboxes), postfix))
-        loss.update(self._get_loss_bbox(pred_bboxes, gt_bboxes, postfix))
-        return loss
-
-    def _get_loss_aux(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, gt_groups, match_indices=None, postfix='',
-                      masks=None, gt_mask=None):
-        loss = torch.zeros(3, device=pred_bboxes.device)
-        if match_indices is None and self.use_uni_match:
-            match_indices = self.matcher(pred_bboxes[self.uni_match_ind], pred_scores[self.uni_match_ind], gt_bboxes,
-                                         gt_cls, gt_groups)
-        for i, aux_bboxes in enumerate(pred_bboxes):
-            aux_scores = None if pred_scores is None else pred_scores[i]
-            loss_ = self._get_loss(aux_bboxes, aux_scores, gt_bboxes, gt_cls, gt_groups, postfix=postfix,
-                                   match_indices=match_indices)
-            if aux_scores is not None:
-                loss[0] = loss[0] + loss_[f'loss_class{postfix}']
-            loss[1] = loss[1] + loss_[f'loss_bbox{postfix}']
-            loss[2] = loss[2] + loss_[f'loss_giou{postfix}']
-        return {f'loss_class_aux{postfix}': loss[0], f'loss_bbox_aux{postfix}': loss[1], f'loss_giou_aux{postfix}': loss[2]}
-
-    def _get_loss_layers(self, pred_bboxes, pred_scores, gt_bboxes, gt_cls, img, q, g, postfix=''):
-        """All layers at once (the reference loops, loss.py:232-243; same arithmetic per layer, one set of kernels):
-        pred_* [n_l, bs, nq, .], img [P], q / g [n_l, P] (or [P] for the fixed denoising matches).  Returns the loss dict
-        of loss.py:328-373: last layer + the sum over the auxiliary layers."""
-        n_l, bs, nq = pred_bboxes.shape[:3]
-        P = img.numel()
-        if q.dim() == 1:
-            q, g = q.expand(n_l, P), g.expand(n_l, P)
-        lay = torch.arange(n_l, device=img.device).unsqueeze(1).expand(n_l, P)
-        idx = (lay, img.expand(n_l, P), q)
-        pb, gb = pred_bboxes[idx], gt_bboxes[g]                                        # [n_l, P, 4]
-        bbox = self.loss_gain['bbox'] * (pb - gb).abs().sum((1, 2)) / P
-        giou = self.loss_gain['giou'] * ((1.0 - bbox_iou(pb, gb, xywh=True, RIOU=True)).sum((1, 2)) / P)
-        out = {}
-        if pred_scores is not None:
-            targets = torch.full((n_l, bs, nq), self.nc, device=pred_scores.device, dtype=gt_cls.dtype)
-            targets[idx] = gt_cls[g]
-            gt_scores = torch.zeros((n_l, bs, nq), device=pred_scores.device)
-            gt_scores[idx] = bbox_iou(pb.detach(), gb, xywh=True).squeeze(-1)
-            one_hot = torch.zeros((n_l, bs, nq, self.nc + 1), dtype=torch.int64, device=targets.device)
-            one_hot.scatter_(3, targets.unsqueeze(-1), 1)
-            one_hot = one_hot[..., :-1]
-            gt_s = gt_scores.unsqueeze(-1) * one_hot
-            if self.fl:
-                if self.vfl:
-                    weight = 0.75 * pred_scores.sigmoid().pow(2.0) * (1 - one_hot) + gt_s * one_hot
-                    with torch.autocast("cuda", enabled=False):
-                        cls = (F.binary_cross_entropy_with_logits(pred_scores.float(), gt_s.float(), reduction='none')
-                               * weight).mean(2).sum((1, 2))
-                else:
-                    label = one_hot.float()
-                    l = F.binary_cross_entropy_with_logits(pred_scores, label, reduction='none')
-                    pr = pred_scores.sigmoid()
-                    p_t = label * pr + (1 - label) * (1 - pr)
-                    cls = (l * (1.0 - p_t) ** 1.5 * (label * 0.25 + (1 - label) * 0.75)).mean(2).sum((1, 2))
-                cls = cls / (max(P, 1) / nq)
-            else:
-                cls = nn.BCEWithLogitsLoss(reduction='none')(pred_scores, gt_s).mean(2).sum((1, 2))
-            cls = cls * self.loss_gain['class']
-            out[f'loss_class{postfix}'] = cls[-1]
-        out[f'loss_bbox{postfix}'] = bbox[-1]
-        out[f'loss_giou{postfix}'] = giou[-1]
-        if self.aux_loss:
-            zero = torch.zeros((), device=pred_bboxes.device)
-            out[f'loss_class_aux{postfix}'] = cls[:-1].sum() if pred_scores is not None else zero
-            out[f'loss_bbox_aux{postfix}'] = bbox[:-1].sum()
-            out[f'loss_giou_aux{postfix}'] = giou[:-1].sum()
-        return out
+    def _get_loss_layers(self, pred_bboxes, pred_scores, tgt, dn_group=False, num_dn=100, postfix=''):
+        """pred_* [n_l, bs, nq, .] -> the loss dict of loss.py:328-373 for these layers."""
+        if not self.fl:
+            raise NotImplementedError("tamtr_b200: plain BCE classification (use_fl=False) is not on TAM-TR's path")
+        if self.use_uni_match:
+            raise NotImplementedError("tamtr_b200: use_uni_match is not on TAM-TR's path (nn/tasks.py:578)")
+        if not self.aux_loss:
+            pred_bboxes, pred_scores = pred_bboxes[-1:], pred_scores[-1:]
+        match = None if dn_group else self.matcher.match_padded(pred_bboxes, pred_scores, tgt)
+        g = self.loss_gain
+        per_layer = _DetLossFn.apply(pred_bboxes, pred_scores, tgt, match, dn_group, num_dn, bool(self.vfl),
+                                     (float(g['class']), float(g['bbox']), float(g['giou'])))
+        return _loss_dict(per_layer, self.aux_loss, postfix)
 
     def forward(self, pred_bboxes, pred_scores, batch, postfix='', **kwargs):
-        """pred_bboxes [l, b, query, 4], pred_scores [l, b, query, nc] (or None); batch: cls / bboxes / gt_groups."""
+        """pred_bboxes [l, b, query, 4], pred_scores [l, b, query, nc]; batch: the reference's dict (cls / bboxes /
+        gt_groups) or a DeviceTargets.  kwargs: dn_group / num_dn select the denoising targets (RTDETRDetectionLoss)."""
         _lib.require_cuda(pred_bboxes)
         self.device = pred_bboxes.device
-        match_indices = kwargs.get('match_indices', None)
-        gt_cls, gt_bboxes, gt_groups = batch['cls'], batch['bboxes'], batch['gt_groups']
-        batched = pred_bboxes.is_cuda and not self.use_uni_match and sum(gt_groups) > 0
-        if batched and isinstance(match_indices, tuple) and match_indices[0].numel() > 0:
-            # fixed matches (denoising queries): the same pairs for every layer
-            pb = pred_bboxes if self.aux_loss else pred_bboxes[-1:]
-            ps = pred_scores if (self.aux_loss or pred_scores is None) else pred_scores[-1:]
-            return self._get_loss_layers(pb, ps, gt_bboxes, gt_cls, *match_indices, postfix=postfix)
-        if batched and match_indices is None and pred_scores is not None:
-            # every layer's assignment in ONE launch (the reference matches layer by layer, loss.py:293-300, 232-243)
-            n_l = pred_bboxes.shape[0] if self.aux_loss else 1
-            img, q, g = self.matcher.match_layers(pred_bboxes[-n_l:], pred_scores[-n_l:], gt_bboxes, gt_cls, gt_groups)
-            if img.numel() > 0:
-                return self._get_loss_layers(pred_bboxes[-n_l:], pred_scores[-n_l:], gt_bboxes, gt_cls, img, q, g,
-                                             postfix=postfix)
-        total_loss = self._get_loss(pred_bboxes[-1], None if pred_scores is None else pred_scores[-1], gt_bboxes, gt_cls,
-                                    gt_groups, postfix=postfix, match_indices=match_indices)
-        if self.aux_loss:
-            total_loss.update(self._get_loss_aux(pred_bboxes[:-1], None if pred_scores is None else pred_scores[:-1],
-                                                 gt_bboxes, gt_cls, gt_groups, match_indices, postfix))
-        return total_loss
+        if pred_scores is None:
+            raise NotImplementedError("tamtr_b200: box-only losses (pred_scores=None) are not on TAM-TR's path")
+        tgt = _as_targets(batch, pred_bboxes.device)
+        return DETRLoss._get_loss_layers(self, pred_bboxes, pred_scores, tgt, kwargs.get('dn_group', False),
+                                         kwargs.get('num_dn', 100), postfix)
 
 
 class RTDETRDetectionLoss(DETRLoss):
-    """loss.py:376-443: the detection loss plus the denoising loss on the CDN queries (fixed matches)."""
+    """loss.py:376-443: the detection loss plus the denoising loss on the CDN queries (fixed matches: the positive
+    copies of the denoising layout, get_dn_match_indices)."""
 
     def forward(self, preds, batch, dn_bboxes=None, dn_scores=None, dn_meta=None):
         # (explicit DETRLoss.forward instead of super(): patch.enable() binds this function onto the reference's class)
         pred_bboxes, pred_scores = preds
-        total_loss = DETRLoss.forward(self, pred_bboxes, pred_scores, batch)
+        tgt = _as_targets(batch, pred_bboxes.device)
+        total_loss = DETRLoss.forward(self, pred_bboxes, pred_scores, tgt)
         if dn_meta is not None:
-            dn_pos_idx, dn_num_group = dn_meta['dn_pos_idx'], dn_meta['dn_num_group']
-            assert len(batch['gt_groups']) == len(dn_pos_idx)
-            # the denoising matches depend only on the batch: flat device copy built once per dn_meta (no per-step
-            # host->device index copies, which would also break CUDA-graph capture)
-            cached = dn_meta.get('_tamtr_dn_match')
-            if cached is None or cached[0].device != dn_bboxes.device:
-                mi = RTDETRDetectionLoss.get_dn_match_indices(dn_pos_idx, dn_num_group, batch['gt_groups'])
-                dev = dn_bboxes.device
-                cached = (torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(mi)]).long().to(dev),
-                          torch.cat([src for src, _ in mi]).long().to(dev), torch.cat([dst for _, dst in mi]).to(dev))
-                dn_meta['_tamtr_dn_match'] = cached
-            dn_loss = DETRLoss.forward(self, dn_bboxes, dn_scores, batch, postfix='_dn', match_indices=cached)
-            total_loss.update(dn_loss)
+            # the kernel re-derives the layout from the counts: num_dn > 0 = the head's `num_denoising` (device-built
+            # groups record it); the reference's dn_meta only carries the resulting number of groups (passed negated)
+            num_dn = dn_meta.get('num_dn_cfg') or -int(dn_meta['dn_num_group'])
+            total_loss.update(DETRLoss.forward(self, dn_bboxes, dn_scores, tgt, postfix='_dn', dn_group=True, num_dn=num_dn))
         else:
-            total_loss.update({f'{k}_dn': torch.zeros((), device=self.device) for k in total_loss.keys()})
+            total_loss.update({f'{k}_dn': torch.zeros((), device=self.device) for k in list(total_loss.keys())})
         return total_loss
-
-    @staticmethod
-    def get_dn_match_indices(dn_pos_idx, dn_num_group, gt_groups):
-        dn_match_indices = []
-        idx_groups = torch.as_tensor([0, *gt_groups[:-1]]).cumsum_(0)
-        for i, num_gt in enumerate(gt_groups):
-            if num_gt > 0:
-                gt_idx = torch.arange(end=num_gt, dtype=torch.long) + idx_groups[i]
-                gt_idx = gt_idx.repeat(dn_num_group)
-                assert len(dn_pos_idx[i]) == len(gt_idx), 'Expected the same length'
-                dn_match_indices.append((dn_pos_idx[i], gt_idx.to(dn_pos_idx[i].device)))
-            else:
-                dn_match_indices.append((torch.zeros([0], dtype=torch.long), torch.zeros([0], dtype=torch.long)))
-        return dn_match_indices

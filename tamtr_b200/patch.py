@@ -56,7 +56,7 @@ HEAD_ATTRS = ("forward", "_get_encoder_input", "_get_decoder_input", "_generate_
               "_rank_tokens", "_fusable_input_proj", "_finish", "plan_cdn", "fused_input_proj", "sparse_query_selection",
               "__getstate__")
 DECODER_ATTRS = ("forward", "_run", "_project_values", "batched_value_projection")
-MATCHER_ATTRS = ("forward", "match_layers", "cost_matrix_per_image")
+MATCHER_ATTRS = ("forward", "match_layers", "match_padded")
 LOSS_ATTRS = ("forward", "_get_loss_layers")
 
 
