@@ -328,6 +328,18 @@ int tamtr_selective_scan_forward_chunked(const void *u, const void *dt, int in_d
                                          const float *C, const float *D, const float *bias, float *y, float *carry,
                                          int n_chunks, int Bn, int KD, int Dg, int N, int L, void *stream);
 
+/* SS2D tail (ultralytics/nn/extra_modules/VManba/vmamba.py:1011-1014 out_norm, :1029-1031 gate): LayerNorm over the CHANNEL
+ * dimension of a position-major tensor, times the SiLU-activated gate, one kernel each way (csrc/vssfuse.cu):
+ *   out[b,c,l] = (LN_c(y[b,:,l]) * gamma[c] + beta[c]) * silu(z[b,c,l])
+ * y, d_y: f32 [Bn, D, L]; z, d_z: f32 | bf16 [Bn, D, L] (the raw gate half of in_proj, before the activation); out: f32 | bf16;
+ * dout: f32 | bf16; gamma, beta, d_gamma, d_beta: f32 [D]; mean, rstd: f32 [Bn, L] (written by the forward unless NULL,
+ * read by the backward).  d_gamma / d_beta are zeroed by the call and accumulated in fp32. */
+int tamtr_colnorm_gate_forward(const float *y, const void *z, int z_dtype, const float *gamma, const float *beta, void *out,
+                               int out_dtype, float *mean, float *rstd, int Bn, int D, int L, float eps, void *stream);
+int tamtr_colnorm_gate_backward(const void *dout, int dout_dtype, const float *y, const void *z, int z_dtype,
+                                const float *gamma, const float *beta, const float *mean, const float *rstd, float *d_y,
+                                void *d_z, float *d_gamma, float *d_beta, int Bn, int D, int L, void *stream);
+
 /* The four scan orders of SS2D (ultralytics/nn/extra_modules/VManba/csms6s.py:4-47), one pass each way:
  *   tamtr_cross_scan : x [Bn, D, H, W] -> xs [Bn, 4, D, H*W]  (row-major, column-major, both reversed)   = CrossScan.forward
  *                                                                                                       = CrossMerge.backward

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "tamtr_dwconv3x3_silu_backward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _vp, _fp, _fp] + [_i] * 5 + [_vp]),
     "tamtr_selective_scan_chunks": (ctypes.c_int, [_i] * 3),
     "tamtr_selective_scan_forward_chunked": (ctypes.c_int, [_vp, _vp, _i] + [_fp] * 7 + [_i] * 6 + [_vp]),
+    "tamtr_colnorm_gate_forward": (ctypes.c_int, [_fp, _vp, _i, _fp, _fp, _vp, _i, _fp, _fp, _i, _i, _i, ctypes.c_float, _vp]),
+    "tamtr_colnorm_gate_backward": (ctypes.c_int, [_vp, _i, _fp, _vp, _i, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, _vp]),
     "tamtr_cross_scan": (ctypes.c_int, [_vp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_cross_merge": (ctypes.c_int, [_vp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_cdn_group": (ctypes.c_int, [_fp, _vp, _vp, _fp, _vp, _fp, _fp, _vp] + [_i] * 6 + [ctypes.c_float] * 2 + [_vp]),

@@ -261,3 +261,59 @@ def test_scan_backward_against_the_closed_form(cuda_lib, b, k, d, l):
     assert rel_l2(y, y_ref) < 1e-5
     for name, got, want in zip(("u", "delta", "A", "B", "C", "D", "delta_bias"), ours, ref):
         assert rel_l2(got.grad, want.grad) < 1e-4, (name, rel_l2(got.grad, want.grad))
+
+
+@pytest.mark.parametrize("c,h,w,autocast", [(64, 12, 20, False), (128, 16, 16, True), (64, 7, 9, False)])
+def test_fused_ss2d_equals_the_composition(cuda_lib, c, h, w, autocast):
+    """The single-node SS2D (explicit backward, position-major GEMMs, fused out_norm + gate: vss._SS2DFn) against the
+    op-by-op composition of the same kernels / library calls, outputs and every gradient; fp32 <= 1e-4, bf16 autocast <= 2e-2.
+    (The composition itself is pinned to the unmodified reference VSSBlock by test_vss_block_matches_reference.)"""
+    from tamtr_b200 import vss
+    torch.manual_seed(3)
+    blk = vss.VSSBlock(hidden_dim=c, drop_path=0.0).cuda()
+    with torch.no_grad():
+        for prm in blk.parameters():
+            if prm.dim() == 1 and prm is not blk.op.Ds:
+                prm.add_(0.1 * torch.randn_like(prm))
+    x = seeding.seeded_tensor(9, "x", (2, h, w, c)).cuda()
+    probe = seeding.seeded_tensor(9, "p", (2, h, w, c)).cuda()
+
+    def run(fused):
+        vss.FUSED_SS2D = fused
+        try:
+            blk.zero_grad(set_to_none=True)
+            xi = x.clone().requires_grad_()
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                y = blk(xi)
+            (y.float() * probe).sum().backward()
+            return y.detach().float(), xi.grad.clone(), {k: v.grad.clone() for k, v in blk.named_parameters()}
+        finally:
+            vss.FUSED_SS2D = True
+    before = cuda_lib.launch_count()
+    y1, gx1, gp1 = run(True)
+    fused_launches = cuda_lib.launch_count() - before
+    y0, gx0, gp0 = run(False)
+    tol = 2e-2 if autocast else 1e-4
+    assert fused_launches > 0 and rel_l2(y1, y0) < tol and rel_l2(gx1, gx0) < tol, (rel_l2(y1, y0), rel_l2(gx1, gx0))
+    for name in gp0:
+        assert gp1[name].shape == gp0[name].shape and gp1[name].dtype == gp0[name].dtype
+        # sums over thousands of positions / channels in different orders (and, under autocast, bf16 partials)
+        assert rel_l2(gp1[name], gp0[name]) < (5e-2 if autocast else 1e-3), (name, rel_l2(gp1[name], gp0[name]))
+
+
+def test_colnorm_gate_matches_torch(cuda_lib):
+    """LayerNorm over the channel dimension of a position-major tensor times silu(z) (csrc/vssfuse.cu) against
+    F.layer_norm on the transposed tensor, forward values (fp32 <= 1e-5; bf16 gate and output <= 1e-2)."""
+    import torch.nn.functional as F
+    from tamtr_b200 import vss
+    norm = torch.nn.LayerNorm(96).cuda()
+    with torch.no_grad():
+        norm.weight.add_(0.2 * torch.randn_like(norm.weight))
+        norm.bias.add_(0.2 * torch.randn_like(norm.bias))
+    y = (3.0 + 2.0 * seeding.seeded_tensor(4, "y", (2, 96, 301))).cuda()
+    z = seeding.seeded_tensor(4, "z", (2, 96, 301)).cuda()
+    want = (F.layer_norm(y.transpose(1, 2), (96,), norm.weight, norm.bias, norm.eps) * F.silu(z.transpose(1, 2))).transpose(1, 2)
+    out, mean, rstd = vss.colnorm_gate(y, z, norm)
+    assert rel_l2(out, want) < 1e-5 and rel_l2(mean, y.mean(1)) < 1e-6
+    out16, _, _ = vss.colnorm_gate(y, z.bfloat16(), norm)
+    assert out16.dtype == torch.bfloat16 and rel_l2(out16.float(), want) < 1e-2
