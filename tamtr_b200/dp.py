@@ -79,14 +79,15 @@ class FlatGrads:
 
     def pack_bucket(self, b):
         first, last = self.buckets[b]
-        dst, src = [], []
-        for t, v in zip(self.src[first:last], self.views[first:last]):
-            if t.grad is None:
-                v.zero_()
+        groups = {}                                  # one multi-tensor copy per gradient dtype: a list that mixes bf16 and
+        for t, v in zip(self.src[first:last], self.views[first:last]):      # fp32 sources makes _foreach_copy_ fall back
+            if t.grad is None:                                               # to one copy kernel per tensor (~110 launches
+                v.zero_()                                                    # per step for the MEH head)
             else:
+                dst, src = groups.setdefault(t.grad.dtype, ([], []))
                 dst.append(v)
                 src.append(t.grad)
-        if dst:
+        for dst, src in groups.values():
             torch._foreach_copy_(dst, src)          # (converts low-precision gradients to the buffer's fp32 on the way)
 
     def clear(self):

@@ -856,17 +856,24 @@ def gate_conv3x3(x, weight, bn_scale, bn_shift, gate, nh):
 _IDENTITY_AFFINE = {}
 
 
+def _identity_affine(co, device):
+    key = (co, device)
+    if key not in _IDENTITY_AFFINE:
+        _IDENTITY_AFFINE[key] = (torch.ones(co, dtype=torch.float32, device=device),
+                                 torch.zeros(co, dtype=torch.float32, device=device))
+    return _IDENTITY_AFFINE[key]
+
+
 class _Conv3x3TcFn(torch.autograd.Function):
-    """The raw 3x3 convolution (stride 1, pad 1, no bias) on the tcgen05 kernel; dgrad / wgrad are library calls."""
+    """The raw 3x3 convolution (stride 1, pad 1, no bias) on the tcgen05 kernel, forward AND data gradient: dgrad of a
+    stride-1 / pad-1 3x3 convolution is the same convolution of grad_out with the filter rotated by 180 degrees and its
+    channel roles swapped (w'[ci, co, ky, kx] = w[co, ci, 2 - ky, 2 - kx]), so it runs on the same implicit-GEMM kernel
+    whenever the swapped shape is one the kernel takes.  The weight gradient (a GEMM whose K is the pixel dimension) is a
+    library call."""
 
     @staticmethod
     def forward(ctx, x, weight):
-        co = weight.shape[0]
-        key = (co, x.device)
-        if key not in _IDENTITY_AFFINE:
-            _IDENTITY_AFFINE[key] = (torch.ones(co, dtype=torch.float32, device=x.device),
-                                     torch.zeros(co, dtype=torch.float32, device=x.device))
-        one, zero = _IDENTITY_AFFINE[key]
+        one, zero = _identity_affine(weight.shape[0], x.device)
         x_cl, y = _gate_conv3x3_launch(x, weight, one, zero, None, 1)
         ctx.save_for_backward(x_cl, weight)
         return y
@@ -875,9 +882,19 @@ class _Conv3x3TcFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         x_cl, weight = ctx.saved_tensors
-        gx, gw, _ = torch.ops.aten.convolution_backward(
-            gy.to(x_cl.dtype), x_cl, weight.to(x_cl.dtype), None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
-            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        gy = gy.to(x_cl.dtype)
+        gx = gw = None
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_x:
+            w_d = weight.detach().flip(2, 3).transpose(0, 1)          # [Ci, Co, 3, 3]: rotated, channel roles swapped
+            if gate_conv3x3_supported(gy, w_d, 1):
+                one, zero = _identity_affine(w_d.shape[0], gy.device)
+                gx = _gate_conv3x3_launch(gy, w_d, one, zero, None, 1)[1]
+                need_x = False
+        if need_x or need_w:
+            gx_l, gw, _ = torch.ops.aten.convolution_backward(
+                gy, x_cl, weight.to(x_cl.dtype), None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [need_x, need_w, False])
+            gx = gx_l if need_x else gx
         return gx, None if gw is None else gw.to(weight.dtype)
 
 

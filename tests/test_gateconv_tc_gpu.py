@@ -98,17 +98,22 @@ def test_fused_block_matches_oracle(cuda_lib, B, C, nh, H, W, N):
     assert rel_l2(out, ref2) < BF16_OUT_TOL, rel_l2(out, ref2)
 
 
-def test_training_path_gradients(cuda_lib):
-    """Training: conv on the tensor-core kernel, BatchNorm statistics + gate in torch; dgrad/wgrad are library calls.
-    Compared with the fp32 oracle on bf16-rounded operands."""
+@pytest.mark.parametrize("Ci,Co,on_kernel", [(64, 96, False), (128, 64, True), (64, 64, True)])
+def test_training_path_gradients(cuda_lib, Ci, Co, on_kernel):
+    """Training: conv AND its data gradient on the tensor-core kernel (dgrad = the same conv with the rotated filter,
+    taken when the channel-swapped shape is one the kernel supports), BatchNorm statistics + gate in torch; wgrad is a
+    library call.  Compared with the fp32 oracle on bf16-rounded operands."""
     from tamtr_b200 import ops
-    B, Ci, Co, H, W = 2, 64, 96, 24, 24
+    B, H, W = 2, 24, 24
     x, w = _conv_inputs(17, B, Ci, Co, H, W)
     probe = seeding.seeded_tensor(18, "p", (B, Co, H, W))
     xr, wr = x.float().requires_grad_(), w.float().requires_grad_()
     (F.conv2d(xr, wr, None, 1, 1) * probe).sum().backward()
     xc, wc = x.cuda().requires_grad_(), w.cuda().requires_grad_()
-    (ops.conv3x3_tc(xc, wc).float() * probe.cuda()).sum().backward()
+    y = ops.conv3x3_tc(xc, wc)
+    before = cuda_lib.launch_count()
+    (y.float() * probe.cuda()).sum().backward()
+    assert (cuda_lib.launch_count() - before >= 1) == on_kernel            # the dgrad ran on csrc/gateconv_tc.cu
     assert rel_l2(xc.grad, xr.grad) < 2e-2 and rel_l2(wc.grad, wr.grad) < 2e-2
 
 
