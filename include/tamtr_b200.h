@@ -279,6 +279,11 @@ int tamtr_add_layernorm_forward(const void *x, int x_dtype, const void *res, int
 int tamtr_add_layernorm_backward(const void *dy, int dy_dtype, const float *z, const float *mean, const float *rstd,
                                  const float *w, void *dx, int dx_dtype, void *dres, int dres_dtype, float *dwb, int rows,
                                  int d, void *stream);
+/* the same with `extra` f32 [rows, d] added to d(loss)/dz: the gradient that reaches z directly through a residual
+ * connection around the normalised branch (VSSBlock: x + mlp(norm2(x)), vmamba.py:1249) */
+int tamtr_add_layernorm_backward_res(const void *dy, int dy_dtype, const float *z, const float *mean, const float *rstd,
+                                     const float *w, const float *extra, void *dx, int dx_dtype, void *dres, int dres_dtype,
+                                     float *dwb, int rows, int d, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Query <-> ground-truth matching on the device: scipy.optimize.linear_sum_assignment as the reference calls it per

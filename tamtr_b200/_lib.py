@@ -53,6 +53,7 @@ _SIGNATURES = {
     "tamtr_add_layernorm_forward": (ctypes.c_int, [_vp, _i, _vp, _i, _fp, _fp, _vp, _i, _fp, _fp, _fp, _i, _i,
                                                    ctypes.c_float, _vp]),
     "tamtr_add_layernorm_backward": (ctypes.c_int, [_vp, _i, _fp, _fp, _fp, _fp, _vp, _i, _vp, _i, _fp, _i, _i, _vp]),
+    "tamtr_add_layernorm_backward_res": (ctypes.c_int, [_vp, _i, _fp, _fp, _fp, _fp, _fp, _vp, _i, _vp, _i, _fp, _i, _i, _vp]),
     "tamtr_bn_forward_coeffs": (ctypes.c_int, [_fp, _i, ctypes.c_double, _fp, _fp, ctypes.c_double, _i, ctypes.c_double,
                                                _fp, _fp, _fp, _fp, _vp, _vp, _i, _vp]),
     "tamtr_bn_backward_coeffs": (ctypes.c_int, [_fp, _i, ctypes.c_double, _fp, _vp, _vp, _i, _fp, _fp, _fp, _fp, _fp,

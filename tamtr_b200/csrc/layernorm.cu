@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kLnThreads)
 add_layernorm_bwd_kernel(const void *__restrict__ dy, int dy_dtype, const float *__restrict__ z,
                          const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ w,
                          void *__restrict__ dx, int dx_dtype, void *__restrict__ dres, int dres_dtype,
-                         float *__restrict__ dwb, int rows) {
+                         float *__restrict__ dwb, int rows, const float *__restrict__ extra) {
     constexpr int d = 128 * PP;
     __shared__ float s_red[kLnWarps][2][d];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -128,6 +128,10 @@ add_layernorm_bwd_kernel(const void *__restrict__ dy, int dy_dtype, const float 
             o.y = rs * (g[i].y - m1 - xh[i].y * m2);
             o.z = rs * (g[i].z - m1 - xh[i].z * m2);
             o.w = rs * (g[i].w - m1 - xh[i].w * m2);
+            if (extra != nullptr) {                    // gradient reaching z on a second path (a residual connection)
+                const float4 e = *reinterpret_cast<const float4 *>(extra + idx);
+                o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+            }
             if (dx != nullptr) ln_store4(dx, dx_dtype, idx, o);
             if (dres != nullptr) ln_store4(dres, dres_dtype, idx, o);
         }
@@ -186,9 +190,9 @@ extern "C" int tamtr_add_layernorm_forward(const void *x, int x_dtype, const voi
     return 0;
 }
 
-extern "C" int tamtr_add_layernorm_backward(const void *dy, int dy_dtype, const float *z, const float *mean,
-                                            const float *rstd, const float *w, void *dx, int dx_dtype, void *dres,
-                                            int dres_dtype, float *dwb, int rows, int d, void *stream) {
+static int add_layernorm_backward_impl(const void *dy, int dy_dtype, const float *z, const float *mean, const float *rstd,
+                                       const float *w, const float *extra, void *dx, int dx_dtype, void *dres,
+                                       int dres_dtype, float *dwb, int rows, int d, void *stream) {
     TAMTR_CHECK_ARG(dy && z && mean && rstd && w && dwb, TAMTR_E_BADARG, "add_layernorm_backward: null pointer");
     TAMTR_CHECK_ARG(rows > 0, TAMTR_E_BADARG, "add_layernorm_backward: rows = %d", rows);
     TAMTR_CHECK_ARG(d % 128 == 0 && d >= 128 && d <= 512, TAMTR_E_UNSUPPORTED,
@@ -201,7 +205,7 @@ extern "C" int tamtr_add_layernorm_backward(const void *dy, int dy_dtype, const 
 #define TAMTR_LN_BWD(PP)                                                                                              \
     case PP:                                                                                                          \
         add_layernorm_bwd_kernel<PP><<<grid, kLnThreads, 0, st>>>(dy, dy_dtype, z, mean, rstd, w, dx, dx_dtype, dres, \
-                                                                  dres_dtype, dwb, rows);                           \
+                                                                  dres_dtype, dwb, rows, extra);                    \
         break;
         switch (d / 128) {
             TAMTR_LN_BWD(1) TAMTR_LN_BWD(2) TAMTR_LN_BWD(3) TAMTR_LN_BWD(4)
@@ -211,4 +215,20 @@ extern "C" int tamtr_add_layernorm_backward(const void *dy, int dy_dtype, const 
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int tamtr_add_layernorm_backward(const void *dy, int dy_dtype, const float *z, const float *mean,
+                                            const float *rstd, const float *w, void *dx, int dx_dtype, void *dres,
+                                            int dres_dtype, float *dwb, int rows, int d, void *stream) {
+    return add_layernorm_backward_impl(dy, dy_dtype, z, mean, rstd, w, nullptr, dx, dx_dtype, dres, dres_dtype, dwb, rows, d,
+                                       stream);
+}
+
+extern "C" int tamtr_add_layernorm_backward_res(const void *dy, int dy_dtype, const float *z, const float *mean,
+                                                const float *rstd, const float *w, const float *extra, void *dx,
+                                                int dx_dtype, void *dres, int dres_dtype, float *dwb, int rows, int d,
+                                                void *stream) {
+    TAMTR_CHECK_ARG(extra != nullptr, TAMTR_E_BADARG, "add_layernorm_backward_res: null pointer");
+    return add_layernorm_backward_impl(dy, dy_dtype, z, mean, rstd, w, extra, dx, dx_dtype, dres, dres_dtype, dwb, rows, d,
+                                       stream);
 }

@@ -575,11 +575,101 @@ def ss2d_forward_on(original):
     return forward
 
 
+class _VSSTailFn(torch.autograd.Function):
+    """The second half of a VSSBlock as one autograd node: x1 = input + y, out = x1 + fc2(gelu(fc1(norm2(x1))))
+    (vmamba.py:1247-1249, Mlp :107-125).  The residual add and norm2 are one kernel that also writes the normalised rows in
+    the GEMM dtype (no cast pass); the backward adds the gradient of the outer residual inside the LayerNorm-backward kernel,
+    takes both bias gradients with tamtr_col_sum and hands ONE gradient tensor to both `input` and `y`.  GEMMs and the
+    exact-erf GELU are library calls, as in the reference."""
+
+    @staticmethod
+    def forward(ctx, inp, y, nw, nb, w1, b1, w2, b2, eps, track):
+        from . import ops
+        autocast = torch.is_autocast_enabled("cuda")
+        cd = torch.get_autocast_dtype("cuda") if autocast else inp.dtype
+        if cd not in (torch.float32, torch.bfloat16):
+            cd = torch.float32
+        with torch.autocast("cuda", enabled=False):
+            c = inp.shape[-1]
+            rows = inp.numel() // c
+            x, r = inp.contiguous(), y.contiguous()
+            nw32, nb32 = nw.detach().float().contiguous(), nb.detach().float().contiguous()
+            ln = torch.empty(rows, c, dtype=cd, device=inp.device)
+            z = torch.empty(rows, c, dtype=torch.float32, device=inp.device)
+            mean = torch.empty(rows, dtype=torch.float32, device=inp.device)
+            rstd = torch.empty(rows, dtype=torch.float32, device=inp.device)
+            with torch.cuda.device(inp.device):
+                rc = _lib.lib().tamtr_add_layernorm_forward(x.data_ptr(), _lib.dtype_code(x), r.data_ptr(), _lib.dtype_code(r),
+                                                            nw32.data_ptr(), nb32.data_ptr(), ln.data_ptr(), _lib.dtype_code(ln),
+                                                            z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, c, float(eps),
+                                                            _lib.stream_ptr(inp.device))
+            _lib.check(rc, "add_layernorm_forward")
+            w1c, w2c = w1.detach().to(cd), w2.detach().to(cd)
+            h = torch.addmm(b1.detach().to(cd), ln, w1c.t())
+            a = F.gelu(h)
+            o = torch.addmm(b2.detach().to(cd), a, w2c.t())
+            out = (z + o).view(inp.shape)
+            if bool(track):
+                ctx.save_for_backward(z, mean, rstd, nw32, ln, h, a, w1c, w2c)
+                ctx.meta = (inp.dtype, y.dtype, tuple(t.dtype for t in (nw, nb, w1, b1, w2, b2)), rows, c)
+        return out if out.dtype == inp.dtype or autocast else out.to(inp.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        from . import ops
+        z, mean, rstd, nw32, ln, h, a, w1c, w2c = ctx.saved_tensors
+        xdt, ydt, (t_nw, t_nb, t_w1, t_b1, t_w2, t_b2), rows, c = ctx.meta
+        cd = ln.dtype
+        with torch.autocast("cuda", enabled=False):
+            g32 = g.reshape(rows, c).contiguous().float()
+            go = g32.to(cd)
+            da = go @ w2c
+            g_w2 = go.t() @ a
+            g_b2 = ops.col_sum(go)
+            dh = torch.ops.aten.gelu_backward(da, h)
+            del da
+            dln = dh @ w1c
+            g_w1 = dh.t() @ ln
+            g_b1 = ops.col_sum(dh)
+            dev = g.device
+            dx = torch.empty(rows, c, dtype=xdt, device=dev)
+            dres = dx if ydt == xdt else torch.empty(rows, c, dtype=ydt, device=dev)
+            dwb = torch.empty(2, c, dtype=torch.float32, device=dev)           # zeroed by the call
+            with torch.cuda.device(dev):
+                rc = _lib.lib().tamtr_add_layernorm_backward_res(
+                    dln.data_ptr(), _lib.dtype_code(dln), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), nw32.data_ptr(),
+                    g32.data_ptr(), dx.data_ptr(), _lib.dtype_code(dx), None if dres is dx else dres.data_ptr(),
+                    0 if dres is dx else _lib.dtype_code(dres), dwb.data_ptr(), rows, c, _lib.stream_ptr(dev))
+            _lib.check(rc, "add_layernorm_backward_res")
+        shape = g.shape
+        return (dx.view(shape), dres.view(shape), dwb[0].to(t_nw), dwb[1].to(t_nb), g_w1.to(t_w1), g_b1.to(t_b1), g_w2.to(t_w2),
+                g_b2.to(t_b2), None, None)
+
+
+def _tail_fusable(blk, x, y):
+    from . import ops
+    mlp, n2 = blk.mlp, blk.norm2
+    return (FUSED_SS2D and x.is_cuda and isinstance(n2, nn.LayerNorm) and n2.elementwise_affine and n2.bias is not None
+            and tuple(n2.normalized_shape) == (x.shape[-1],) and ops.add_layer_norm_supported(x, x.shape[-1])
+            and y.dtype in (torch.float32, torch.bfloat16) and y.shape == x.shape
+            and isinstance(getattr(mlp, "fc1", None), nn.Linear) and isinstance(getattr(mlp, "fc2", None), nn.Linear)
+            and mlp.fc1.bias is not None and mlp.fc2.bias is not None and isinstance(mlp.act, nn.GELU)
+            and getattr(mlp.act, "approximate", "none") == "none"
+            and (not isinstance(mlp.drop, nn.Dropout) or mlp.drop.p == 0.0 or not blk.training)
+            and (getattr(blk.drop_path, "drop_prob", 0.0) == 0.0 or not blk.training))
+
+
 def _vssblock_forward(self, input):
     # SS2D body called directly, not through self.op(...): a reference SS2D carries its own bound `forward`
     op = self.op
     y = _layer_norm(self.norm, input)
     y = _ss2d_forward(op, y) if _ss2d_supported(op) else op(y)
+    if _tail_fusable(self, input, y):
+        track = torch.is_grad_enabled() and (input.requires_grad or y.requires_grad
+                                             or any(p.requires_grad for p in self.mlp.parameters()))
+        return _VSSTailFn.apply(input, y, self.norm2.weight, self.norm2.bias, self.mlp.fc1.weight, self.mlp.fc1.bias,
+                                self.mlp.fc2.weight, self.mlp.fc2.bias, self.norm2.eps, track)
     x = input + self.drop_path(y)
     return x + self.drop_path(self.mlp(_layer_norm(self.norm2, x)))
 
