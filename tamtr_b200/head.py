@@ -12,6 +12,8 @@ csrc/sscan.cu (vss.py); `vss=False` replaces them by identities, the configurati
 """
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -366,6 +368,33 @@ class RTDETRDecoder(_HeadBase):
         return self._finish(dec_bboxes, dec_scores, enc_bboxes, enc_scores, dn_meta)
 
 
+VSS_PARALLEL_LEVELS = os.environ.get("TAMTR_VSS_PARALLEL", "1") != "0"
+_VSS_STREAMS = {}
+
+
+def _apply_vss_blocks(blocks, x):
+    """One VSSBlock per pyramid level (head.py:1134).  The levels are independent, and the selective scan of the largest
+    level runs with two warps per scheduler (16 384 channels): each level is issued on its own stream -- forked from and
+    joined to the caller's stream, so it is a parallel branch of a captured step, and autograd runs each block's backward on
+    its forward stream -- so that the smaller levels' kernels fill the SMs the big scan leaves idle."""
+    if not (VSS_PARALLEL_LEVELS and x[0].is_cuda and len(x) > 1 and not isinstance(blocks[0], nn.Identity)):
+        return [blk(f.permute(0, 2, 3, 1)).permute(0, 3, 1, 2) for blk, f in zip(blocks, x)]
+    dev = x[0].device
+    side = _VSS_STREAMS.get((dev, len(x)))
+    if side is None:
+        side = _VSS_STREAMS[(dev, len(x))] = [torch.cuda.Stream(dev) for _ in range(len(x) - 1)]
+    main = torch.cuda.current_stream(dev)
+    outs = [None] * len(x)
+    for i in range(1, len(x)):                                    # levels 1.. on side streams, level 0 on the caller's
+        side[i - 1].wait_stream(main)
+        with torch.cuda.stream(side[i - 1]):
+            outs[i] = blocks[i](x[i].permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+    outs[0] = blocks[0](x[0].permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+    for s in side:
+        main.wait_stream(s)
+    return outs
+
+
 class ManbaWorldDecoder(_HeadBase):
     """TAM-TR's Multi-modal Encoder-decoder Head (head.py:1005-1290): forward(x, text [B,K,512], batch=None).
 
@@ -396,7 +425,7 @@ class ManbaWorldDecoder(_HeadBase):
 
     def forward(self, x, text, batch=None):
         if getattr(self, "vss", True):        # head.py:1134: channel-last in and out (reference instances: always)
-            x = [blk(f.permute(0, 2, 3, 1)).permute(0, 3, 1, 2) for blk, f in zip(self.VSSBlocks, x)]
+            x = _apply_vss_blocks(self.VSSBlocks, x)
         feats, shapes, hub = self._encode(x)
         dn_embed, dn_bbox, attn_mask, dn_meta = self._cdn(batch)
         embed, refer_bbox, enc_bboxes, enc_scores = self._get_decoder_input(feats, shapes, dn_embed, dn_bbox, hub)

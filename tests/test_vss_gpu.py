@@ -317,3 +317,32 @@ def test_colnorm_gate_matches_torch(cuda_lib):
     assert rel_l2(out, want) < 1e-5 and rel_l2(mean, y.mean(1)) < 1e-6
     out16, _, _ = vss.colnorm_gate(y, z.bfloat16(), norm)
     assert out16.dtype == torch.bfloat16 and rel_l2(out16.float(), want) < 1e-2
+
+
+def test_pyramid_levels_on_parallel_streams(cuda_lib):
+    """head._apply_vss_blocks: the three levels' VSSBlocks issued on forked streams (parallel branches of a captured step)
+    give what the sequential loop gives -- outputs bit-identical (no cross-level data), input gradients to rounding (the
+    scan's dB / dC are fp32 atomics, whose order varies run to run anyway)."""
+    from tamtr_b200 import head
+    from tamtr_b200.vss import VSSBlock
+    torch.manual_seed(11)
+    blocks = torch.nn.ModuleList(VSSBlock(hidden_dim=c, drop_path=0.0) for c in (64, 128, 256)).cuda()
+    xs = [seeding.seeded_tensor(31, f"x{i}", (2, c, s, s)).cuda() for i, (c, s) in enumerate(((64, 24), (128, 12), (256, 8)))]
+
+    def run(parallel):
+        head.VSS_PARALLEL_LEVELS = parallel
+        try:
+            leaves = [x.clone().requires_grad_() for x in xs]
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                outs = head._apply_vss_blocks(blocks, leaves)
+            sum((o.float() ** 2).mean() for o in outs).backward()
+            torch.cuda.synchronize()
+            return [o.detach() for o in outs], [x.grad for x in leaves]
+        finally:
+            head.VSS_PARALLEL_LEVELS = True
+    o1, g1 = run(True)
+    o0, g0 = run(False)
+    for a, b in zip(o1, o0):
+        assert a.shape == b.shape and torch.equal(a, b)
+    for a, b in zip(g1, g0):
+        assert rel_l2(a, b) < 1e-3
