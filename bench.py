@@ -404,7 +404,35 @@ def timed(dev, fn, n, barrier):
     return e0.elapsed_time(e1) / 1e3
 
 
+def _leave(dev):
+    """End of a multi-rank run.  The captured steps hold NCCL collectives (gradient buckets all-reduced from inside the CUDA
+    graph); tearing the communicator down while those graphs are alive was seen to block forever in
+    destroy_process_group() on 2 GPUs -- after the JSON line had been printed.  All ranks meet once more, drain their GPU
+    and leave the process without running the destructors."""
+    import torch.distributed as dist
+    dbg = os.environ.get("TAMTR_BENCH_DEBUG")
+    if dbg:
+        print(f"[leave] rank {dist.get_rank()} enter {time.time():.1f}", file=sys.stderr, flush=True)
+    torch.cuda.synchronize(dev)
+    if dbg:
+        print(f"[leave] rank {dist.get_rank()} synced {time.time():.1f}", file=sys.stderr, flush=True)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    if dbg:
+        print(f"[leave] rank {dist.get_rank()} past barrier {time.time():.1f}", file=sys.stderr, flush=True)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    try:
+        _JSON_OUT.flush()
+    except Exception:
+        pass
+    os._exit(0)
+
+
 def main():
+    if os.environ.get("TAMTR_BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["TAMTR_BENCH_DEBUG"]), repeat=False, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -480,7 +508,7 @@ def main():
                               "data": "synthetic", "config": {"workload": res["workload"], "vss_blocks": "identity"},
                               "infer_1280": res}), file=_JSON_OUT, flush=True)
         if ws > 1:
-            dist.destroy_process_group()
+            _leave(dev)
         return
 
     strong = args.scaling == "strong"
@@ -787,7 +815,7 @@ def main():
         line.update(extra)
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if ws > 1:
-        dist.destroy_process_group()
+        _leave(dev)
 
 
 if __name__ == "__main__":
