@@ -688,14 +688,61 @@ class _InProjFn(torch.autograd.Function):
         return dxqk, dxv, dw, db
 
 
+class _SelfAttnFn(torch.autograd.Function):
+    """softmax(q k^T / sqrt(Dh) + mask) v on the packed projections (csrc/selfattn.cu): qk [B, L, 2d] bf16, v [B, L, d] bf16,
+    blocked u8 [L, L] or None -> o [B, L, d] bf16.  Gradients come back in the same packed layouts."""
+
+    @staticmethod
+    def forward(ctx, qk, v, blocked, n_heads):
+        B, L, d = v.shape
+        qk, v = qk.contiguous(), v.contiguous()
+        o = torch.empty_like(v)
+        lse = torch.empty(B, n_heads, L, dtype=torch.float32, device=v.device)
+        with _with_device(v):
+            rc = _lib.lib().tamtr_self_attention_forward(qk.data_ptr(), v.data_ptr(), None if blocked is None else blocked.data_ptr(),
+                                                         o.data_ptr(), lse.data_ptr(), B, L, n_heads, d // n_heads,
+                                                         _lib.stream_ptr(v.device))
+        _lib.check(rc, "self_attention_forward")
+        ctx.save_for_backward(qk, v, o, lse, blocked)
+        ctx.n_heads = n_heads
+        return o
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        qk, v, o, lse, blocked = ctx.saved_tensors
+        B, L, d = v.shape
+        H = ctx.n_heads
+        go = go.contiguous().to(v.dtype)
+        d_qk, d_v = torch.empty_like(qk), torch.empty_like(v)
+        lp = _lib.lib().tamtr_self_attention_padded_len(L)
+        scratch = torch.empty(2, B, H, lp, lp, dtype=v.dtype, device=v.device)
+        with _with_device(v):
+            rc = _lib.lib().tamtr_self_attention_backward(qk.data_ptr(), v.data_ptr(), None if blocked is None else blocked.data_ptr(),
+                                                          o.data_ptr(), go.data_ptr(), lse.data_ptr(), d_qk.data_ptr(),
+                                                          d_v.data_ptr(), scratch.data_ptr(), B, L, H, d // H,
+                                                          _lib.stream_ptr(v.device))
+        _lib.check(rc, "self_attention_backward")
+        return d_qk, d_v, None, None
+
+
+FUSED_SELF_ATTENTION = True      # False: the library's scaled_dot_product_attention (kept for A/B tests)
+
+
 def self_attention(mha, x_qk, x_v, attn_mask=None):
     """nn.MultiheadAttention(x_qk, x_qk, x_v, attn_mask=..., need_weights=False)[0] for batch-first [B, L, d] inputs
-    (the reference feeds it sequence-first through two transposes, transformer.py:546): packed in-projection,
-    F.scaled_dot_product_attention, out-projection.  attn_mask: bool [L, L] with True = blocked (nn.MultiheadAttention's
-    convention) or an additive float mask."""
+    (the reference feeds it sequence-first through two transposes, transformer.py:546): packed in-projection, attention,
+    out-projection.  attn_mask: bool [L, L] with True = blocked (nn.MultiheadAttention's convention) or an additive float
+    mask.  bf16 projections with head dimension 32 / 64 and a bool (or no) mask run on the fused kernels of csrc/selfattn.cu,
+    which read q / k / v where the projection wrote them; anything else goes through F.scaled_dot_product_attention."""
     B, L, d = x_qk.shape
     H = mha.num_heads
     qk, v = _InProjFn.apply(x_qk, x_v, mha.in_proj_weight, mha.in_proj_bias)
+    if (FUSED_SELF_ATTENTION and qk.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and d % H == 0
+            and (attn_mask is None or (attn_mask.dtype == torch.bool and tuple(attn_mask.shape) == (L, L)))
+            and (mha.dropout == 0.0 or not mha.training) and _lib.lib().tamtr_self_attention_supported(L, H, d // H)):
+        blocked = None if attn_mask is None else attn_mask.to(torch.uint8).contiguous()
+        return linear(_SelfAttnFn.apply(qk, v, blocked, H), mha.out_proj)
     q = qk[..., :d].view(B, L, H, d // H).transpose(1, 2)
     k = qk[..., d:].view(B, L, H, d // H).transpose(1, 2)
     v = v.view(B, L, H, d // H).transpose(1, 2)

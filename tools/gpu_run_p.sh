@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests/test_selfattn_gpu.py -q -x -p no:cacheprovider 2>&1 | tail -15
+python -m pytest tests/test_modules_gpu.py tests/test_step_gpu.py tests/test_patch_gpu.py -q -x -p no:cacheprovider 2>&1 | tail -4
+python bench.py --quick --steps 10 --warmup 3 > gpurun_out/bench_quick_p.json 2> gpurun_out/bench_quick_p.err
+tail -1 gpurun_out/bench_quick_p.err; head -c 230 gpurun_out/bench_quick_p.json; echo
