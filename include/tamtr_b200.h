@@ -290,17 +290,20 @@ int tamtr_add_layernorm_backward_res(const void *dy, int dy_dtype, const float *
  * q = k = embed + pos, v = embed and the denoising attention mask of models/utils/ops.py:273-284), after the packed input
  * projection -- softmax(q k^T / sqrt(Dh) + mask) v per (image, head), one fused kernel forward, two backward (csrc/selfattn.cu).
  *   qk, d_qk: bf16 [Bn, L, 2 * H * Dh] (q in the first half of every row, k in the second); v, o, d_o, d_v: bf16 [Bn, L, H * Dh];
- *   blocked : u8 [L, L], non-zero = query row may NOT attend to key column (nn.MultiheadAttention's bool mask), or NULL;
+ *   mask_bits: u64 [L, ceil(L / 64)] or NULL: the bool mask of nn.MultiheadAttention (non-zero = query row may NOT attend to
+ *             key column) packed by tamtr_self_attention_pack_mask from u8 [L, L] -- bit c of word [q][t] = key 64 t + c;
  *   lse2    : f32 [Bn, H, L], log2-sum-exp of the scaled scores, written by the forward for the backward;
  *   scratch : bf16 [2, Bn, H, Lp, Lp] with Lp = tamtr_self_attention_padded_len(L) (probabilities and score gradients).
  * Dh = 32 or 64; every pointer 16-byte aligned.  A row whose keys are all blocked yields zeros (the library yields NaN). */
 int tamtr_self_attention_supported(int L, int H, int Dh);
 int tamtr_self_attention_padded_len(int L);
-int tamtr_self_attention_forward(const void *qk, const void *v, const uint8_t *blocked, void *o, float *lse2, int Bn, int L, int H,
-                                 int Dh, void *stream);
-int tamtr_self_attention_backward(const void *qk, const void *v, const uint8_t *blocked, const void *o, const void *d_o,
-                                  const float *lse2, void *d_qk, void *d_v, void *scratch, int Bn, int L, int H, int Dh,
-                                  void *stream);
+int tamtr_self_attention_mask_words(int L);
+int tamtr_self_attention_pack_mask(const uint8_t *blocked, unsigned long long *mask_bits, int L, void *stream);
+int tamtr_self_attention_forward(const void *qk, const void *v, const unsigned long long *mask_bits, void *o, float *lse2, int Bn,
+                                 int L, int H, int Dh, void *stream);
+int tamtr_self_attention_backward(const void *qk, const void *v, const unsigned long long *mask_bits, const void *o,
+                                  const void *d_o, const float *lse2, void *d_qk, void *d_v, void *scratch, int Bn, int L, int H,
+                                  int Dh, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Query <-> ground-truth matching on the device: scipy.optimize.linear_sum_assignment as the reference calls it per

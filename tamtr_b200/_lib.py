@@ -56,6 +56,8 @@ _SIGNATURES = {
     "tamtr_add_layernorm_backward_res": (ctypes.c_int, [_vp, _i, _fp, _fp, _fp, _fp, _fp, _vp, _i, _vp, _i, _fp, _i, _i, _vp]),
     "tamtr_self_attention_supported": (ctypes.c_int, [_i] * 3),
     "tamtr_self_attention_padded_len": (ctypes.c_int, [_i]),
+    "tamtr_self_attention_mask_words": (ctypes.c_int, [_i]),
+    "tamtr_self_attention_pack_mask": (ctypes.c_int, [_vp, _vp, _i, _vp]),
     "tamtr_self_attention_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _fp] + [_i] * 4 + [_vp]),
     "tamtr_self_attention_backward": (ctypes.c_int, [_vp] * 5 + [_fp, _vp, _vp, _vp] + [_i] * 4 + [_vp]),
     "tamtr_bn_forward_coeffs": (ctypes.c_int, [_fp, _i, ctypes.c_double, _fp, _fp, ctypes.c_double, _i, ctypes.c_double,

@@ -108,25 +108,45 @@ __device__ __forceinline__ void sa_pm(float (&acc)[DH / 8][4], const float (&p)[
     }
 }
 
-// mask / bounds on the accumulators of key tile k0: s <- s * scale2 (log2 units), -inf where blocked or key >= L
-__device__ __forceinline__ void sa_mask(float (&s)[8][4], const uint8_t *__restrict__ blocked, int L, int q_lo, int k0, int lane,
-                                        float scale2) {
-    const int c = 2 * (lane & 3);
+// The mask arrives bit-packed (tamtr_self_attention_pack_mask): bits[q][t] holds the 64 keys of tile t, bit set = blocked, keys
+// past L included -- two 8-byte loads per thread and tile instead of 32 byte loads.  Without a mask only the bounds remain.
+__device__ __forceinline__ unsigned long long sa_tile_bits(const unsigned long long *__restrict__ bits, int n_tiles, int L, int q,
+                                                           int t) {
+    if (bits != nullptr) return q < L ? __ldg(bits + (size_t)q * n_tiles + t) : 0ull;
+    const int live = L - t * kSaK;                               // keys of this tile that exist
+    return live >= 64 ? 0ull : ~0ull << live;
+}
+// s <- s * scale2 (log2 units), -inf where blocked
+__device__ __forceinline__ void sa_mask(float (&s)[8][4], unsigned long long w0, unsigned long long w1, int lane, float scale2) {
+    const int sh = 2 * (lane & 3);
+    const unsigned long long a = w0 >> sh, b = w1 >> sh;         // rows lane / 4 and lane / 4 + 8
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int q = q_lo + ((e >> 1) << 3), k = k0 + 8 * j + c + (e & 1);
-            bool dead = k >= L;
-            if (!dead && blocked != nullptr && q < L) dead = blocked[(size_t)q * L + k] != 0;
-            s[j][e] = dead ? -INFINITY : s[j][e] * scale2;
-        }
+        s[j][0] = ((a >> (8 * j)) & 1ull) ? -INFINITY : s[j][0] * scale2;
+        s[j][1] = ((a >> (8 * j + 1)) & 1ull) ? -INFINITY : s[j][1] * scale2;
+        s[j][2] = ((b >> (8 * j)) & 1ull) ? -INFINITY : s[j][2] * scale2;
+        s[j][3] = ((b >> (8 * j + 1)) & 1ull) ? -INFINITY : s[j][3] * scale2;
     }
+}
+
+__global__ void selfattn_pack_mask_kernel(const uint8_t *__restrict__ blocked, unsigned long long *__restrict__ bits, int L,
+                                          int n_tiles) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L * n_tiles) return;
+    const int q = i / n_tiles, t = i % n_tiles;
+    unsigned long long w = 0ull;
+    for (int c = 0; c < 64; ++c) {
+        const int k = t * kSaK + c;
+        const bool dead = k >= L || blocked[(size_t)q * L + k] != 0;
+        w |= (unsigned long long)dead << c;
+    }
+    bits[i] = w;
 }
 
 template <int DH>
 __global__ void __launch_bounds__(kSaThreads)
-selfattn_fwd_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16 *__restrict__ v, const uint8_t *__restrict__ blocked,
+selfattn_fwd_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16 *__restrict__ v,
+                    const unsigned long long *__restrict__ bits,
                     __nv_bfloat16 *__restrict__ o, float *__restrict__ lse2, int L, int H, float scale2) {
     __shared__ __align__(16) __nv_bfloat16 qs[kSaQ][DH + 8];
     __shared__ __align__(16) __nv_bfloat16 ks[2][kSaK][DH + 8];
@@ -163,7 +183,7 @@ selfattn_fwd_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16 *_
         }
         float s[8][4];
         sa_qkT<DH>(s, qa, ks[buf], lane);
-        sa_mask(s, blocked, L, q_lo, t * kSaK, lane, scale2);
+        sa_mask(s, sa_tile_bits(bits, n_tiles, L, q_lo, t), sa_tile_bits(bits, n_tiles, L, q_lo + 8, t), lane, scale2);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {                             // online softmax, rows r = 0 (e 0,1) and 1 (e 2,3)
             float mx = -INFINITY;
@@ -208,25 +228,50 @@ selfattn_fwd_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16 *_
 }
 
 // backward 1: per query tile.  dQ, and the P / dS tiles (bf16) for backward 2.
+template <int DH> struct SaBwdQSmem {
+    __nv_bfloat16 qs[kSaQ][DH + 8];
+    __nv_bfloat16 gs[kSaQ][DH + 8];                              // dO
+    __nv_bfloat16 ks[2][kSaK][DH + 8];
+    __nv_bfloat16 vs[2][kSaK][DH + 8];
+    __nv_bfloat16 st[kSaThreads / 32][16][kSaK + 8];             // per warp: a 16 x 64 tile on its way to the scratch buffer
+    float delta[kSaQ];
+};
+
+// a warp's 16 x 64 accumulator tile -> bf16 rows of the scratch matrix (row pitch Lp), as 16-byte stores
+__device__ __forceinline__ void sa_store_tile(__nv_bfloat16 (*st)[kSaK + 8], const float (&x)[8][4], __nv_bfloat16 *__restrict__ dst,
+                                              size_t pitch, int lane) {
+    const int r = lane >> 2, c = 2 * (lane & 3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<uint32_t *>(&st[r][8 * j + c]) = sa_pack(x[j][0], x[j][1]);
+        *reinterpret_cast<uint32_t *>(&st[r + 8][8 * j + c]) = sa_pack(x[j][2], x[j][3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = lane; i < 16 * 8; i += 32) {                    // 16 rows x 8 chunks of 16 bytes
+        const int rr = i >> 3, cc = i & 7;
+        *reinterpret_cast<uint4 *>(dst + (size_t)rr * pitch + 8 * cc) = *reinterpret_cast<const uint4 *>(&st[rr][8 * cc]);
+    }
+    __syncwarp();
+}
+
 template <int DH>
 __global__ void __launch_bounds__(kSaThreads)
-selfattn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16 *__restrict__ v, const uint8_t *__restrict__ blocked,
+selfattn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16 *__restrict__ v,
+                      const unsigned long long *__restrict__ bits,
                       const __nv_bfloat16 *__restrict__ o, const __nv_bfloat16 *__restrict__ d_o, const float *__restrict__ lse2,
                       __nv_bfloat16 *__restrict__ d_qk, __nv_bfloat16 *__restrict__ p_out, __nv_bfloat16 *__restrict__ ds_out,
                       int L, int Lp, int H, float scale2, float scale) {
-    __shared__ __align__(16) __nv_bfloat16 qs[kSaQ][DH + 8];
-    __shared__ __align__(16) __nv_bfloat16 gs[kSaQ][DH + 8];              // dO
-    __shared__ __align__(16) __nv_bfloat16 ks[1][kSaK][DH + 8];           // single-buffered: 48 KB of static shared memory
-    __shared__ __align__(16) __nv_bfloat16 vs[1][kSaK][DH + 8];
-    __shared__ float delta_s[kSaQ];
+    extern __shared__ __align__(16) unsigned char sa_raw[];
+    SaBwdQSmem<DH> &sm = *reinterpret_cast<SaBwdQSmem<DH> *>(sa_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * kSaQ, h = blockIdx.y, b = blockIdx.z, d = H * DH;
     const __nv_bfloat16 *qkb = qk + (size_t)b * L * 2 * d, *vb = v + (size_t)b * L * d;
     const __nv_bfloat16 *gb = d_o + (size_t)b * L * d, *ob = o + (size_t)b * L * d;
-    sa_stage<kSaQ, DH>(qs, qkb, 2 * d, q0, L, h * DH);
-    sa_stage<kSaQ, DH>(gs, gb, d, q0, L, h * DH);
-    sa_stage<kSaK, DH>(ks[0], qkb, 2 * d, 0, L, d + h * DH);
-    sa_stage<kSaK, DH>(vs[0], vb, d, 0, L, h * DH);
+    sa_stage<kSaQ, DH>(sm.qs, qkb, 2 * d, q0, L, h * DH);
+    sa_stage<kSaQ, DH>(sm.gs, gb, d, q0, L, h * DH);
+    sa_stage<kSaK, DH>(sm.ks[0], qkb, 2 * d, 0, L, d + h * DH);
+    sa_stage<kSaK, DH>(sm.vs[0], vb, d, 0, L, h * DH);
     sa_commit();
     // delta[q] = <dO[q], O[q]> over the head's channels: two threads per row
     {
@@ -242,7 +287,7 @@ selfattn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16 
             }
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (half == 0) delta_s[r] = acc;
+        if (half == 0) sm.delta[r] = acc;
     }
     const int n_tiles = (L + kSaK - 1) / kSaK;
     uint32_t qa[DH / 16][4], ga[DH / 16][4];
@@ -251,34 +296,37 @@ selfattn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16 
     for (int j = 0; j < DH / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.0f;
     const int q_lo = q0 + 16 * warp + (lane >> 2);
     float ls[2], dl[2];
-    __nv_bfloat16 *pb = p_out + ((size_t)b * H + h) * Lp * Lp, *dsb = ds_out + ((size_t)b * H + h) * Lp * Lp;
+    __nv_bfloat16 *pb = p_out + ((size_t)b * H + h) * Lp * Lp + (size_t)(q0 + 16 * warp) * Lp;
+    __nv_bfloat16 *dsb = ds_out + ((size_t)b * H + h) * Lp * Lp + (size_t)(q0 + 16 * warp) * Lp;
     for (int t = 0; t < n_tiles; ++t) {
-        constexpr int buf = 0;
-        if (t > 0) {
-            sa_stage<kSaK, DH>(ks[0], qkb, 2 * d, t * kSaK, L, d + h * DH);
-            sa_stage<kSaK, DH>(vs[0], vb, d, t * kSaK, L, h * DH);
+        const int buf = t & 1;
+        if (t + 1 < n_tiles) {
+            sa_stage<kSaK, DH>(sm.ks[buf ^ 1], qkb, 2 * d, (t + 1) * kSaK, L, d + h * DH);
+            sa_stage<kSaK, DH>(sm.vs[buf ^ 1], vb, d, (t + 1) * kSaK, L, h * DH);
             sa_commit();
+            sa_wait<1>();
+        } else {
+            sa_wait<0>();
         }
-        sa_wait<0>();
         __syncthreads();
         if (t == 0) {
             const int ar = 16 * warp + (lane & 7) + (((lane >> 3) & 1) << 3), ac = (lane >> 4) << 3;
 #pragma unroll
             for (int ksx = 0; ksx < DH / 16; ++ksx) {
-                sa_ldsm4(qa[ksx], &qs[ar][16 * ksx + ac]);
-                sa_ldsm4(ga[ksx], &gs[ar][16 * ksx + ac]);
+                sa_ldsm4(qa[ksx], &sm.qs[ar][16 * ksx + ac]);
+                sa_ldsm4(ga[ksx], &sm.gs[ar][16 * ksx + ac]);
             }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int q = q_lo + 8 * r;
                 ls[r] = q < L ? lse2[((size_t)b * H + h) * L + q] : INFINITY;
-                dl[r] = delta_s[16 * warp + (lane >> 2) + 8 * r];
+                dl[r] = sm.delta[16 * warp + (lane >> 2) + 8 * r];
             }
         }
         float s[8][4], dp[8][4];
-        sa_qkT<DH>(s, qa, ks[buf], lane);
-        sa_mask(s, blocked, L, q_lo, t * kSaK, lane, scale2);
-        sa_qkT<DH>(dp, ga, vs[buf], lane);                           // dP = dO V^T
+        sa_qkT<DH>(s, qa, sm.ks[buf], lane);
+        sa_mask(s, sa_tile_bits(bits, n_tiles, L, q_lo, t), sa_tile_bits(bits, n_tiles, L, q_lo + 8, t), lane, scale2);
+        sa_qkT<DH>(dp, ga, sm.vs[buf], lane);                        // dP = dO V^T
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -288,22 +336,10 @@ selfattn_bwd_q_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16 
                 dp[j][e] = p * (dp[j][e] - dl[e >> 1]) * scale;         // dS with respect to q k^T, times the softmax scale
             }
         }
-        // P and dS tiles for the key-side kernel
-        {
-            const int kc = t * kSaK + 2 * (lane & 3);
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int q = q_lo + 8 * r;
-                if (q < Lp) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        *reinterpret_cast<uint32_t *>(pb + (size_t)q * Lp + kc + 8 * j) = sa_pack(s[j][2 * r], s[j][2 * r + 1]);
-                        *reinterpret_cast<uint32_t *>(dsb + (size_t)q * Lp + kc + 8 * j) = sa_pack(dp[j][2 * r], dp[j][2 * r + 1]);
-                    }
-                }
-            }
-        }
-        sa_pm<DH>(dq, dp, ks[buf], lane);                            // dQ += dS K
+        // P and dS tiles for the key-side kernel (rows q0 + 16 warp .. + 15 < Lp, columns of tile t)
+        sa_store_tile(sm.st[warp], s, pb + t * kSaK, Lp, lane);
+        sa_store_tile(sm.st[warp], dp, dsb + t * kSaK, Lp, lane);
+        sa_pm<DH>(dq, dp, sm.ks[buf], lane);                         // dQ += dS K
         __syncthreads();
     }
 #pragma unroll
@@ -337,15 +373,20 @@ __device__ __forceinline__ void sa_tTm(float (&acc)[DH / 8][4], const __nv_bfloa
 }
 
 // backward 2: per key tile.  dV = P^T dO, dK = dS^T Q.
+template <int DH> struct SaBwdKvSmem {
+    __nv_bfloat16 qs[2][kSaQ][DH + 8];
+    __nv_bfloat16 gs[2][kSaQ][DH + 8];
+    __nv_bfloat16 ps[2][kSaQ][kSaK + 8];
+    __nv_bfloat16 dss[2][kSaQ][kSaK + 8];
+};
+
 template <int DH>
 __global__ void __launch_bounds__(kSaThreads)
 selfattn_bwd_kv_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16 *__restrict__ d_o,
                        const __nv_bfloat16 *__restrict__ p_in, const __nv_bfloat16 *__restrict__ ds_in,
                        __nv_bfloat16 *__restrict__ d_qk, __nv_bfloat16 *__restrict__ d_v, int L, int Lp, int H) {
-    __shared__ __align__(16) __nv_bfloat16 qs[kSaQ][DH + 8];
-    __shared__ __align__(16) __nv_bfloat16 gs[kSaQ][DH + 8];
-    __shared__ __align__(16) __nv_bfloat16 ps[kSaQ][kSaK + 8];
-    __shared__ __align__(16) __nv_bfloat16 dss[kSaQ][kSaK + 8];
+    extern __shared__ __align__(16) unsigned char sa_raw[];
+    SaBwdKvSmem<DH> &sm = *reinterpret_cast<SaBwdKvSmem<DH> *>(sa_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k0 = blockIdx.x * kSaK, h = blockIdx.y, b = blockIdx.z, d = H * DH;
     const __nv_bfloat16 *qkb = qk + (size_t)b * L * 2 * d, *gb = d_o + (size_t)b * L * d;
@@ -356,18 +397,21 @@ selfattn_bwd_kv_kernel(const __nv_bfloat16 *__restrict__ qk, const __nv_bfloat16
         dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.0f;
         dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.0f;
     }
-    const int n_tiles = (L + kSaQ - 1) / kSaQ;
-    for (int t = 0; t < n_tiles; ++t) {
-        const int q0 = t * kSaQ;
-        sa_stage<kSaQ, DH>(qs, qkb, 2 * d, q0, L, h * DH);
-        sa_stage<kSaQ, DH>(gs, gb, d, q0, L, h * DH);
-        sa_stage<kSaQ, kSaK>(ps, pb, Lp, q0, Lp, k0);                // rows q0 .. q0 + 63 exist (Lp is a multiple of 64)
-        sa_stage<kSaQ, kSaK>(dss, dsb, Lp, q0, Lp, k0);
+    auto prefetch = [&](int buf, int q0) {
+        sa_stage<kSaQ, DH>(sm.qs[buf], qkb, 2 * d, q0, L, h * DH);
+        sa_stage<kSaQ, DH>(sm.gs[buf], gb, d, q0, L, h * DH);
+        sa_stage<kSaQ, kSaK>(sm.ps[buf], pb, Lp, q0, Lp, k0);        // rows q0 .. q0 + 63 exist (Lp is a multiple of 64)
+        sa_stage<kSaQ, kSaK>(sm.dss[buf], dsb, Lp, q0, Lp, k0);
         sa_commit();
-        sa_wait<0>();
+    };
+    const int n_tiles = (L + kSaQ - 1) / kSaQ;
+    prefetch(0, 0);
+    for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < n_tiles) { prefetch(buf ^ 1, (t + 1) * kSaQ); sa_wait<1>(); } else { sa_wait<0>(); }
         __syncthreads();
-        sa_tTm<DH>(dv, ps, 16 * warp, gs, lane);
-        sa_tTm<DH>(dk, dss, 16 * warp, qs, lane);
+        sa_tTm<DH>(dv, sm.ps[buf], 16 * warp, sm.gs[buf], lane);
+        sa_tTm<DH>(dk, sm.dss[buf], 16 * warp, sm.qs[buf], lane);
         __syncthreads();
     }
 #pragma unroll
@@ -402,8 +446,19 @@ static int sa_check(const void *a, const void *b, const void *c, int Bn, int L, 
     return 0;
 }
 
-extern "C" int tamtr_self_attention_forward(const void *qk, const void *v, const uint8_t *blocked, void *o, float *lse2, int Bn,
-                                            int L, int H, int Dh, void *stream) {
+extern "C" int tamtr_self_attention_mask_words(int L) { return L > 0 ? L * ((L + kSaK - 1) / kSaK) : 0; }
+
+extern "C" int tamtr_self_attention_pack_mask(const uint8_t *blocked, unsigned long long *bits, int L, void *stream) {
+    TAMTR_CHECK_ARG(blocked && bits && L > 0, TAMTR_E_BADARG, "self_attention_pack_mask: bad argument");
+    const int n = tamtr_self_attention_mask_words(L);
+    selfattn_pack_mask_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(blocked, bits, L, (L + kSaK - 1) / kSaK);
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tamtr_self_attention_forward(const void *qk, const void *v, const unsigned long long *mask_bits, void *o, float *lse2,
+                                            int Bn, int L, int H, int Dh, void *stream) {
     int rc = sa_check(qk, v, o, Bn, L, H, Dh);
     if (rc) return rc;
     TAMTR_CHECK_ARG(lse2 != nullptr, TAMTR_E_BADARG, "self_attention_forward: null pointer");
@@ -411,19 +466,42 @@ extern "C" int tamtr_self_attention_forward(const void *qk, const void *v, const
     const dim3 grid((L + kSaQ - 1) / kSaQ, H, Bn);
     const float scale2 = kSaLog2e / sqrtf((float)Dh);
     if (Dh == 64)
-        selfattn_fwd_kernel<64><<<grid, kSaThreads, 0, st>>>((const __nv_bfloat16 *)qk, (const __nv_bfloat16 *)v, blocked,
+        selfattn_fwd_kernel<64><<<grid, kSaThreads, 0, st>>>((const __nv_bfloat16 *)qk, (const __nv_bfloat16 *)v, mask_bits,
                                                             (__nv_bfloat16 *)o, lse2, L, H, scale2);
     else
-        selfattn_fwd_kernel<32><<<grid, kSaThreads, 0, st>>>((const __nv_bfloat16 *)qk, (const __nv_bfloat16 *)v, blocked,
+        selfattn_fwd_kernel<32><<<grid, kSaThreads, 0, st>>>((const __nv_bfloat16 *)qk, (const __nv_bfloat16 *)v, mask_bits,
                                                             (__nv_bfloat16 *)o, lse2, L, H, scale2);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-extern "C" int tamtr_self_attention_backward(const void *qk, const void *v, const uint8_t *blocked, const void *o, const void *d_o,
-                                             const float *lse2, void *d_qk, void *d_v, void *scratch, int Bn, int L, int H,
-                                             int Dh, void *stream) {
+template <int DH>
+static cudaError_t sa_backward_launch(dim3 grid, cudaStream_t st, const void *qk, const void *v, const unsigned long long *bits,
+                                      const void *o, const void *d_o, const float *lse2, void *d_qk, void *d_v, __nv_bfloat16 *p,
+                                      __nv_bfloat16 *ds, int L, int Lp, int H, float scale2, float scale) {
+    static bool done[64] = {false};                              // > 48 KB of dynamic shared memory: opt in per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        e = cudaFuncSetAttribute(selfattn_bwd_q_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaBwdQSmem<DH>));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(selfattn_bwd_kv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaBwdKvSmem<DH>));
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    selfattn_bwd_q_kernel<DH><<<grid, kSaThreads, sizeof(SaBwdQSmem<DH>), st>>>(
+        (const __nv_bfloat16 *)qk, (const __nv_bfloat16 *)v, bits, (const __nv_bfloat16 *)o, (const __nv_bfloat16 *)d_o, lse2,
+        (__nv_bfloat16 *)d_qk, p, ds, L, Lp, H, scale2, scale);
+    selfattn_bwd_kv_kernel<DH><<<grid, kSaThreads, sizeof(SaBwdKvSmem<DH>), st>>>(
+        (const __nv_bfloat16 *)qk, (const __nv_bfloat16 *)d_o, p, ds, (__nv_bfloat16 *)d_qk, (__nv_bfloat16 *)d_v, L, Lp, H);
+    return cudaGetLastError();
+}
+
+extern "C" int tamtr_self_attention_backward(const void *qk, const void *v, const unsigned long long *mask_bits, const void *o,
+                                             const void *d_o, const float *lse2, void *d_qk, void *d_v, void *scratch, int Bn,
+                                             int L, int H, int Dh, void *stream) {
     int rc = sa_check(qk, v, o, Bn, L, H, Dh);
     if (rc) return rc;
     rc = sa_check(d_o, d_qk, d_v, Bn, L, H, Dh);
@@ -434,20 +512,8 @@ extern "C" int tamtr_self_attention_backward(const void *qk, const void *v, cons
     __nv_bfloat16 *p = (__nv_bfloat16 *)scratch, *ds = p + (size_t)Bn * H * Lp * Lp;
     const dim3 grid((L + kSaQ - 1) / kSaQ, H, Bn);
     const float scale = 1.0f / sqrtf((float)Dh), scale2 = kSaLog2e * scale;
-    if (Dh == 64) {
-        selfattn_bwd_q_kernel<64><<<grid, kSaThreads, 0, st>>>(
-            (const __nv_bfloat16 *)qk, (const __nv_bfloat16 *)v, blocked, (const __nv_bfloat16 *)o, (const __nv_bfloat16 *)d_o, lse2,
-            (__nv_bfloat16 *)d_qk, p, ds, L, Lp, H, scale2, scale);
-        selfattn_bwd_kv_kernel<64><<<grid, kSaThreads, 0, st>>>((const __nv_bfloat16 *)qk, (const __nv_bfloat16 *)d_o, p, ds,
-                                                               (__nv_bfloat16 *)d_qk, (__nv_bfloat16 *)d_v, L, Lp, H);
-    } else {
-        selfattn_bwd_q_kernel<32><<<grid, kSaThreads, 0, st>>>(
-            (const __nv_bfloat16 *)qk, (const __nv_bfloat16 *)v, blocked, (const __nv_bfloat16 *)o, (const __nv_bfloat16 *)d_o, lse2,
-            (__nv_bfloat16 *)d_qk, p, ds, L, Lp, H, scale2, scale);
-        selfattn_bwd_kv_kernel<32><<<grid, kSaThreads, 0, st>>>((const __nv_bfloat16 *)qk, (const __nv_bfloat16 *)d_o, p, ds,
-                                                               (__nv_bfloat16 *)d_qk, (__nv_bfloat16 *)d_v, L, Lp, H);
-    }
+    TAMTR_CUDA_OK(Dh == 64 ? sa_backward_launch<64>(grid, st, qk, v, mask_bits, o, d_o, lse2, d_qk, d_v, p, ds, L, Lp, H, scale2, scale)
+                           : sa_backward_launch<32>(grid, st, qk, v, mask_bits, o, d_o, lse2, d_qk, d_v, p, ds, L, Lp, H, scale2, scale));
     count_launch(2);
-    TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -690,7 +690,7 @@ class _InProjFn(torch.autograd.Function):
 
 class _SelfAttnFn(torch.autograd.Function):
     """softmax(q k^T / sqrt(Dh) + mask) v on the packed projections (csrc/selfattn.cu): qk [B, L, 2d] bf16, v [B, L, d] bf16,
-    blocked u8 [L, L] or None -> o [B, L, d] bf16.  Gradients come back in the same packed layouts."""
+    blocked = attention_mask_bits(mask) or None -> o [B, L, d] bf16.  Gradients come back in the same packed layouts."""
 
     @staticmethod
     def forward(ctx, qk, v, blocked, n_heads):
@@ -726,6 +726,27 @@ class _SelfAttnFn(torch.autograd.Function):
         return d_qk, d_v, None, None
 
 
+def attention_mask_bits(attn_mask):
+    """bool [L, L] (True = blocked) -> the bit-packed form the attention kernels read (int64 [L, ceil(L / 64)]), or None.
+    Packed once per mask TENSOR: the decoder hands the same tensor to every layer of a forward."""
+    if attn_mask is None:
+        return None
+    hit = getattr(attn_mask, "_tamtr_bits", None)
+    if hit is not None and hit[0] == attn_mask._version:
+        return hit[1]
+    L = attn_mask.shape[0]
+    u8 = attn_mask.to(torch.uint8).contiguous() if attn_mask.dtype != torch.uint8 else attn_mask.contiguous()
+    bits = torch.empty(_lib.lib().tamtr_self_attention_mask_words(L), dtype=torch.int64, device=attn_mask.device)
+    with _with_device(attn_mask):
+        _lib.check(_lib.lib().tamtr_self_attention_pack_mask(u8.data_ptr(), bits.data_ptr(), L, _lib.stream_ptr(attn_mask.device)),
+                   "self_attention_pack_mask")
+    try:
+        attn_mask._tamtr_bits = (attn_mask._version, bits)
+    except Exception:
+        pass
+    return bits
+
+
 FUSED_SELF_ATTENTION = True      # False: the library's scaled_dot_product_attention (kept for A/B tests)
 
 
@@ -741,8 +762,7 @@ def self_attention(mha, x_qk, x_v, attn_mask=None):
     if (FUSED_SELF_ATTENTION and qk.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and d % H == 0
             and (attn_mask is None or (attn_mask.dtype == torch.bool and tuple(attn_mask.shape) == (L, L)))
             and (mha.dropout == 0.0 or not mha.training) and _lib.lib().tamtr_self_attention_supported(L, H, d // H)):
-        blocked = None if attn_mask is None else attn_mask.to(torch.uint8).contiguous()
-        return linear(_SelfAttnFn.apply(qk, v, blocked, H), mha.out_proj)
+        return linear(_SelfAttnFn.apply(qk, v, attention_mask_bits(attn_mask), H), mha.out_proj)
     q = qk[..., :d].view(B, L, H, d // H).transpose(1, 2)
     k = qk[..., d:].view(B, L, H, d // H).transpose(1, 2)
     v = v.view(B, L, H, d // H).transpose(1, 2)

@@ -53,7 +53,9 @@ def test_self_attention_matches_reference(cuda_lib, B, L, H, Dh, mask):
     want.backward(go.double())
     qc, vc = qk.cuda().requires_grad_(), v.cuda().requires_grad_()
     before = cuda_lib.launch_count()
-    got = ops._SelfAttnFn.apply(qc, vc, None if blocked is None else blocked.to(torch.uint8).cuda(), H)
+    bits = ops.attention_mask_bits(None if blocked is None else blocked.cuda())
+    before = cuda_lib.launch_count()
+    got = ops._SelfAttnFn.apply(qc, vc, bits, H)
     got.backward(go.cuda())
     torch.cuda.synchronize()
     assert cuda_lib.launch_count() - before == 3                     # one forward, two backward kernels

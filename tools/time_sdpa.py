@@ -79,3 +79,30 @@ for be_name, be in (("cudnn", SDPBackend.CUDNN_ATTENTION), ("efficient", SDPBack
             print(f"{be_name:10s} {vn:22s} fwd+bwd {t:7.1f} us")
         except Exception as e:
             print(f"{be_name:10s} {vn:22s} {type(e).__name__}: {str(e)[:120]}")
+
+print("---- csrc/selfattn.cu on the packed projections (CUDA graph, device time per replay)")
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tamtr_b200 import ops  # noqa: E402
+d = H * D
+qkp = torch.randn(B, L, 2 * d, device=dev, dtype=torch.bfloat16).requires_grad_()
+vp = torch.randn(B, L, d, device=dev, dtype=torch.bfloat16).requires_grad_()
+gop = torch.randn(B, L, d, device=dev, dtype=torch.bfloat16)
+blocked = ops.attention_mask_bits(~mask)
+for what in ("fwd", "fwd+bwd"):
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            qkp.grad = vp.grad = None
+            o = ops._SelfAttnFn.apply(qkp, vp, blocked, H)
+            if what != "fwd":
+                o.backward(gop)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    qkp.grad = vp.grad = None
+    with torch.cuda.graph(g):
+        o = ops._SelfAttnFn.apply(qkp, vp, blocked, H)
+        if what != "fwd":
+            o.backward(gop)
+    print(f"ours {what:8s} {timed(g.replay, 100):7.1f} us")
