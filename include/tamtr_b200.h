@@ -435,6 +435,36 @@ int tamtr_adamw_flat(float *param, const float *grad, float *exp_avg, float *exp
                      const unsigned char *decay4, float *partial, float *step, float lr, float beta1, float beta2, float eps, float weight_decay,
                      float max_norm, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Folded encoder-side projections (tcgen05 / TMEM / TMA; csrc/tokgemm.cu; algebra in tamtr_b200/fold.py).
+ * Replaces, per pyramid level l, the chain  input_proj[l] = Conv2d(1x1, bias=False) + BatchNorm2d
+ * (ultralytics/nn/modules/head.py:1202-1218)  ->  value_proj of every decoder layer (transformer.py:273)  and
+ * enc_output.0 / enc_score_head for the query-selection ranking (head.py:1229-1237): BatchNorm is affine per channel, so
+ * each consumer's first Linear folds with it and the conv into ONE weight W_fold [N, C_l] + bias [N] per level.
+ *
+ *   tamtr_tok_project:  out[b, tok, n] = sum_c x[b, c, tok] * w[n, c] + bias[n]
+ *     x     [B, C, HW] bf16 (an NCHW feature map as the backbone wrote it), C % 64 == 0, C <= 512, HW % 8 == 0
+ *     w     [N0 + N1 + NT, C] bf16,  bias [N0 + N1 + NT] f32
+ *     out0  bf16, columns [0, N0): element (b, tok, n) at out0 + b * out0_img + tok * out0_row + n  (strides in elements;
+ *           the caller passes the level's first token of a [B, Lv, N0] tensor), N0 % 64 == 0
+ *     out1  bf16, columns [N0, N0 + N1) likewise (NULL when N1 == 0), N1 % 64 == 0
+ *     raw   f32, the last NT columns (NT % 4 == 0; NULL when NT == 0)
+ *   tamtr_tok_reduce:   D[m, c] = sum_{b, tok} a[m; b, tok] * x[b, c, tok],   rs[m] = sum_{b, tok} a[m; b, tok]
+ *     a_token_major = 1: a is [B, HW, M] bf16 with strides a_img / a_row (grad_value of one level: the weight gradient of
+ *                        the folded projection and, through rs, of its bias);  = 0: a is [B, M, HW] (a = x: second moments
+ *                        and channel sums of the level, from which the BatchNorm batch statistics follow)
+ *     part_d [S, M, C] f32, part_rs [S, M] f32 with S = tamtr_tok_reduce_splits(...): per-split partial results in a fixed
+ *     order (deterministic); the caller adds them.
+ * Both only enqueue one kernel; CUDA-graph capturable. */
+int tamtr_tok_project_supported(int B, int C, int HW, int N0, int N1, int NT);
+int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row, long out0_img,
+                      void *out1, long out1_row, long out1_img, float *raw, long raw_row, long raw_img, int B, int C, int HW,
+                      int N0, int N1, int NT, void *stream);
+int tamtr_tok_reduce_supported(int B, int C, int HW, int M, int a_token_major);
+int tamtr_tok_reduce_splits(int B, int C, int HW, int M, int a_token_major);
+int tamtr_tok_reduce(const void *a_bf16, long a_row, long a_img, int a_token_major, const void *x_bf16, float *part_d,
+                     float *part_rs, int B, int C, int HW, int M, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ _DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
 
 _lib = None
 
-_vp, _i, _fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p
+_vp, _i, _fp, _l = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_long
 _SIGNATURES = {
     "tamtr_abi_version": (ctypes.c_int, []),
     "tamtr_last_error": (ctypes.c_char_p, []),
@@ -87,6 +87,11 @@ _SIGNATURES = {
     "tamtr_optim_partials": (ctypes.c_int, [ctypes.c_longlong]),
     "tamtr_adamw_flat": (ctypes.c_int, [_fp, _fp, _fp, _fp, ctypes.c_longlong, _vp, _fp, _fp]
                          + [ctypes.c_float] * 6 + [_vp]),
+    "tamtr_tok_project_supported": (ctypes.c_int, [_i] * 6),
+    "tamtr_tok_project": (ctypes.c_int, [_vp, _vp, _fp, _vp, _l, _l, _vp, _l, _l, _fp, _l, _l] + [_i] * 6 + [_vp]),
+    "tamtr_tok_reduce_supported": (ctypes.c_int, [_i] * 5),
+    "tamtr_tok_reduce_splits": (ctypes.c_int, [_i] * 5),
+    "tamtr_tok_reduce": (ctypes.c_int, [_vp, _l, _l, _i, _vp, _fp, _fp] + [_i] * 4 + [_vp]),
     "tamtr_max_sigmoid_backward": (ctypes.c_int, [_fp, _fp, _vp, _vp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
 }
 

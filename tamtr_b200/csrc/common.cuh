@@ -14,7 +14,7 @@ void count_launch(unsigned n = 1);
 int sm_count();   // SMs of the CURRENT device (148 on B200)
 
 enum KernelId { K_MSDA_FWD = 0, K_MSDA_BWD, K_LOCW_FWD, K_LOCW_BWD, K_CTR_FWD, K_CTR_BWD, K_GATE_FWD, K_GATE_BWD,
-                K_GATE_TC_FWD, K_GATE_CONV_TC, K_NHWC, K_LN_FWD, K_LN_BWD, K_SSCAN_FWD, K_SSCAN_BWD, K_COUNT };
+                K_GATE_TC_FWD, K_GATE_CONV_TC, K_NHWC, K_LN_FWD, K_LN_BWD, K_SSCAN_FWD, K_SSCAN_BWD, K_TOK_PROJECT, K_TOK_REDUCE, K_COUNT };
 
 // RAII pair of CUDA events around one kernel launch (no-op unless tamtr_profile_enable(1)).
 struct KernelTimer {

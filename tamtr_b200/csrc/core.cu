@@ -43,7 +43,7 @@ static std::vector<EventPair> g_prof[K_COUNT];
 static const char *g_names[K_COUNT] = {"msda_fwd", "msda_bwd", "locw_fwd", "locw_bwd", "contrastive_fwd",
                                        "contrastive_bwd", "max_sigmoid_fwd", "max_sigmoid_bwd", "max_sigmoid_tc_fwd", "gate_conv3x3_tc_fwd",
                                        "nchw_to_nhwc", "add_layernorm_fwd", "add_layernorm_bwd", "selective_scan_fwd",
-                                       "selective_scan_bwd"};
+                                       "selective_scan_bwd", "tok_project", "tok_reduce"};
 
 KernelTimer::KernelTimer(int id, cudaStream_t st) : id_(id), st_(st), live_(false) {
     if (!g_prof_on) return;

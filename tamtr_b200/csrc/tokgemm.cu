@@ -1,0 +1,590 @@
+// Folded encoder-side projections of the detection heads on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// The reference runs, on every pyramid level l (head.py:1202-1218, transformer.py:273, head.py:1229-1237):
+//     Y = conv1x1(X_l)  ->  M = BatchNorm(Y)  ->  value_i = value_proj_i(M) (every decoder layer i),  E = enc_output.0(M)
+// Every consumer of M starts with a Linear layer, and BatchNorm is an affine map per channel once its statistics are known,
+// so  value_i = X_l^T (W_i diag(s) Wc)^T + (W_i t + b_i)  with  s = gamma * rstd, t = beta - mu * s  (tamtr_b200/fold.py has
+// the algebra, including the statistics: mu = Wc mean(X), var = diag(Wc Cov(X) Wc^T)).  M is never materialised:
+//
+//   tamtr_tok_project   out[b, tok, :] = X_l[b, :, tok]^T W_fold^T + bias      K = C_l (128 / 256 / 512) instead of d = 512
+//                       X is read where the backbone left it (NCHW: tokens contiguous = an MN-major A operand), the
+//                       columns go to up to two bf16 tensors (value arena, ranking embedding) and an fp32 tail (scores)
+//   tamtr_tok_reduce    D[m, n] = sum over all tokens of A[m; tok] * X_l[n; tok]  (+ row sums of A through a ones block)
+//                       A = grad_value (weight gradient of the folded projection, replaces the dgrad + BatchNorm backward +
+//                       conv wgrad chain) or A = X_l (second moments for the BatchNorm statistics)
+//
+// Both are warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, the rest = epilogue (TMEM -> registers ->
+// swizzled staging tile -> TMA store / fp32 stores).  HBM-bound by construction.
+#include "tc_ptx.cuh"
+
+namespace tamtr {
+
+// ------------------------------------------------------------------------------------------------ shared helpers
+__device__ __forceinline__ void tk_tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tk_tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// K-major operand, SWIZZLE_128B: rows of 64 elements (128 B), 8-row atoms every 1024 B (SBO); a K step of 16 = +32 B
+__device__ __forceinline__ uint64_t tk_desc_k(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major operand, SWIZZLE_128B, staged as 64-wide MN blocks of `64 K rows x 128 B`: 8 K rows = one 1024 B atom (SBO),
+// the next 64 MN elements sit 8192 B further (LBO); a K step of 16 = +2048 B  (cute/atom/mma_traits_sm100.hpp:165-187,
+// same construction as csrc/maxsig_tc.cu)
+__device__ __forceinline__ uint64_t tk_desc_mn(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tk_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tk_pack2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+constexpr int kTkThreads = 64 + 256;         // producer warp, MMA warp, 8 epilogue warps
+constexpr int kTkSlot = 128 * 64 * 2;        // one 128 x 64 bf16 operand block = 16 KB
+
+// ================================================================================================ forward projection
+// One CTA owns MT * 128 consecutive tokens of one image: their X columns (all K blocks) stay resident in shared memory
+// while the CTA walks the N_all output columns 128 at a time, streaming W_fold through a 3-stage ring (W_fold is a few
+// hundred KB: L2 hits).  Two TMEM accumulator stages (MT x 128 columns each) overlap the MMAs of step n+1 with the
+// epilogue of step n.  Shared memory: A <= 128 KB, W ring 48 KB, two 16 KB staging tiles.
+constexpr int kPjWStages = 3;
+constexpr int kPjASlots = 8;
+
+struct PjBars {
+    uint64_t a_full, a_empty, w_full[kPjWStages], w_empty[kPjWStages], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+struct PjGeom {
+    int B, HW, C, n_kb;            // level geometry; n_kb = C / 64
+    int MT;                        // 128-token blocks per CTA tile (1 or 2), MT * n_kb <= 8
+    int pairs_per_img, n_pairs;    // CTA tiles
+    int N0, N1, NT, n_steps;       // bf16 columns of out0 / out1, fp32 tail columns, ceil((N0 + N1 + NT) / 128)
+    long raw_row, raw_img;         // strides (elements) of the fp32 tail tensor
+};
+
+__global__ void __launch_bounds__(kTkThreads, 1)
+tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                   const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
+                   const float *__restrict__ bias, float *__restrict__ raw, const PjGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sA = base;                                         // [MT][n_kb] slots of 16 KB
+    uint8_t *sW = base + (size_t)kPjASlots * kTkSlot;           // [stages] 16 KB
+    uint8_t *sO = sW + (size_t)kPjWStages * kTkSlot;            // [2] 16 KB staging tiles (one per epilogue group)
+    PjBars &bars = *reinterpret_cast<PjBars *>(sO + 2 * kTkSlot);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars.a_full, 1);
+        mbar_init(&bars.a_empty, 1);
+        for (int s = 0; s < kPjWStages; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars.acc_full[a], 1); mbar_init(&bars.acc_empty[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                     "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = bars.tmem_base;
+    const int tile_tok = g.MT * 128;
+
+    if (warp == 0) {
+        // ===== TMA producer
+        if (lane == 0) {
+            uint32_t wi = 0;
+            int it = 0;
+            for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x, ++it) {
+                const int b = p / g.pairs_per_img, tok0 = (p - b * g.pairs_per_img) * tile_tok;
+                mbar_wait(&bars.a_empty, (it & 1) ^ 1);
+                // 64-token boxes that start inside the image; the others are skipped (their accumulator rows are never stored)
+                int boxes = 0;
+                for (int h = 0; h < 2 * g.MT; ++h) boxes += (tok0 + 64 * h < g.HW) ? 1 : 0;
+                mbar_expect_tx(&bars.a_full, (uint32_t)(boxes * g.n_kb * 8192));
+                for (int mt = 0; mt < g.MT; ++mt)
+                    for (int kb = 0; kb < g.n_kb; ++kb)
+                        for (int h = 0; h < 2; ++h) {
+                            const int t = tok0 + mt * 128 + h * 64;
+                            if (t < g.HW)
+                                tk_tma_load_3d(sA + (size_t)(mt * g.n_kb + kb) * kTkSlot + h * 8192, &map_x, &bars.a_full, t,
+                                               kb * 64, b);
+                        }
+                for (int n = 0; n < g.n_steps; ++n)
+                    for (int kb = 0; kb < g.n_kb; ++kb, ++wi) {
+                        const uint32_t s = wi % kPjWStages;
+                        mbar_wait(&bars.w_empty[s], ((wi / kPjWStages) & 1) ^ 1);
+                        mbar_expect_tx(&bars.w_full[s], (uint32_t)kTkSlot);
+                        tma_load_2d(sW + (size_t)s * kTkSlot, &map_w, &bars.w_full[s], kb * 64, n * 128);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: D[128 tokens, 128 columns] += A (MN-major) x W (K-major), K = 16 per instruction
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t wi = 0, ai = 0;
+            int it = 0;
+            for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x, ++it) {
+                mbar_wait(&bars.a_full, it & 1);
+                for (int n = 0; n < g.n_steps; ++n, ++ai) {
+                    const uint32_t as = ai & 1;
+                    mbar_wait(&bars.acc_empty[as], ((ai >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int kb = 0; kb < g.n_kb; ++kb, ++wi) {
+                        const uint32_t s = wi % kPjWStages;
+                        mbar_wait(&bars.w_full[s], (wi / kPjWStages) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t w_addr = smem_u32(sW + (size_t)s * kTkSlot);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t bd = tk_desc_k(w_addr + k * 32);
+                            for (int mt = 0; mt < g.MT; ++mt) {
+                                const uint32_t a_addr = smem_u32(sA + (size_t)(mt * g.n_kb + kb) * kTkSlot);
+                                umma_f16(tmem_base + (as * 2 + mt) * 128, tk_desc_mn(a_addr + k * 2048), bd, idesc,
+                                         (kb | k) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(&bars.w_empty[s]);
+                    }
+                    umma_commit(&bars.acc_full[as]);
+                }
+                umma_commit(&bars.a_empty);
+            }
+        }
+    } else {
+        // ===== epilogue: two groups of four warps; warp % 4 = TMEM lane quarter.  MT == 2: group = token block, both
+        // 64-column chunks of the step; MT == 1: group = chunk.  Per chunk: TMEM -> + bias -> bf16 -> the token's 128-byte row
+        // of the group's swizzled staging tile -> one TMA store (the map clips rows past the image's last token).
+        const int quarter = warp & 3, grp = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;                       // TMEM lane = token within the 128-block
+        uint8_t *stage = sO + (size_t)grp * kTkSlot;
+        const uint32_t row_off = (uint32_t)row * 128, sw = (uint32_t)(row & 7);
+        const bool leader = (warp - 2) % 4 == 0 && lane == 0;      // issues the group's TMA stores
+        const int mt = g.MT == 2 ? grp : 0;
+        const int chunk0 = g.MT == 2 ? 0 : grp, n_chunks = g.MT == 2 ? 2 : 1;
+        const int Nmain = g.N0 + g.N1, Nall = Nmain + g.NT;
+        uint32_t ai = 0;
+        for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x) {
+            const int b = p / g.pairs_per_img, tok0 = (p - b * g.pairs_per_img) * tile_tok + mt * 128;
+            for (int n = 0; n < g.n_steps; ++n, ++ai) {
+                const uint32_t as = ai & 1;
+                mbar_wait(&bars.acc_full[as], (ai >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (as * 2 + mt) * 128;
+                for (int ci = 0; ci < n_chunks; ++ci) {
+                    const int chunk = chunk0 + ci, col0 = n * 128 + chunk * 64;
+                    if (col0 >= Nall || tok0 >= g.HW) continue;              // uniform over the group
+                    if (col0 >= Nmain) {
+                        // fp32 tail (ranking scores): direct stores of the chunk's share of the NT columns
+                        uint32_t v[32];
+                        const int tok = tok0 + row, toff = col0 - Nmain;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int cb = toff + h * 32;
+                            if (cb >= g.NT) break;                                  // uniform
+                            tk_tmem_ld32(taddr + chunk * 64 + h * 32, v);
+                            if (tok < g.HW) {
+                                float *dst = raw + (size_t)b * g.raw_img + (size_t)tok * g.raw_row + cb;
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    if (cb + j < g.NT) {
+                                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + Nmain + cb + j));
+                                        *reinterpret_cast<float4 *>(dst + j) =
+                                            make_float4(__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y,
+                                                        __uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w);
+                                    }
+                                }
+                            }
+                        }
+                        continue;
+                    }
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free again
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t v[32];
+                        tk_tmem_ld32(taddr + chunk * 64 + h * 32, v);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + col0 + h * 32 + q * 8));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + col0 + h * 32 + q * 8 + 4));
+                            const uint32_t o0 = tk_pack2(__uint_as_float(v[q * 8 + 0]) + b0.x, __uint_as_float(v[q * 8 + 1]) + b0.y);
+                            const uint32_t o1 = tk_pack2(__uint_as_float(v[q * 8 + 2]) + b0.z, __uint_as_float(v[q * 8 + 3]) + b0.w);
+                            const uint32_t o2 = tk_pack2(__uint_as_float(v[q * 8 + 4]) + b1.x, __uint_as_float(v[q * 8 + 5]) + b1.y);
+                            const uint32_t o3 = tk_pack2(__uint_as_float(v[q * 8 + 6]) + b1.z, __uint_as_float(v[q * 8 + 7]) + b1.w);
+                            const uint32_t piece = (uint32_t)(h * 4 + q) ^ sw;
+                            *reinterpret_cast<uint4 *>(stage + row_off + piece * 16) = make_uint4(o0, o1, o2, o3);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    if (leader) {
+                        if (col0 < g.N0) tk_tma_store_3d(&map_o0, stage, col0, tok0, b);
+                        else tk_tma_store_3d(&map_o1, stage, col0 - g.N0, tok0, b);
+                    }
+                }
+                // every TMEM read of this accumulator stage by this warp is complete (tcgen05.wait::ld in tk_tmem_ld32)
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.acc_empty[as]);
+            }
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// ================================================================================================ reduction over tokens
+// D[m, n] = sum_{b, tok} A[m; b, tok] * X[b, n, tok],   rs[m] = sum_{b, tok} A[m; b, tok]
+// CTA (blockIdx.x = m group * n chunks + n chunk, blockIdx.y = split): MT row blocks of 128 x NB <= 256 columns, over the
+// split's share of the (image, 64-token block) sequence; partial results are written per split (deterministic; the caller
+// adds the splits).  The row sums come from one more MMA per K step against a block of ones (N = 16).
+struct RdBars {
+    uint64_t full[4], empty[4], acc_full;
+    uint32_t tmem_base;
+};
+
+struct RdGeom {
+    int B, HW, C, M;               // X [B, C, HW]; A has M rows
+    int MT, NB, n_cchunks;         // row blocks per CTA, columns per CTA, C / NB
+    int kb_per_img, total_kb, splits, stages;
+    int a_mn;                      // 1: A given token-major [B, HW, M] (MN-major operand); 0: channel-major [B, M, HW]
+    int tmem_cols;
+};
+
+__global__ void __launch_bounds__(64 + 128, 1)
+tok_reduce_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_x,
+                  float *__restrict__ part_d, float *__restrict__ part_rs, const RdGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = g.MT * kTkSlot, b_bytes = g.NB * 128, stage_bytes = a_bytes + b_bytes;
+    uint8_t *ones = base + (size_t)g.stages * stage_bytes;                 // 16 rows x 128 B of bf16 1.0
+    RdBars &bars = *reinterpret_cast<RdBars *>(ones + 2048);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mg = blockIdx.x / g.n_cchunks, cc = blockIdx.x - mg * g.n_cchunks;
+    const int m0 = mg * g.MT * 128, c0 = cc * g.NB;
+    const int split = blockIdx.y;
+    const int kb0 = (int)((long)g.total_kb * split / g.splits), kb1 = (int)((long)g.total_kb * (split + 1) / g.splits);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
+        mbar_init(&bars.acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                     "r"(g.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(ones)[i] = 0x3F803F80u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = bars.tmem_base;
+    const uint32_t ones_col = (uint32_t)(g.MT * g.NB);           // TMEM columns of the row-sum accumulators
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = kb0, i = 0; kb < kb1; ++kb, ++i) {
+                const int s = i % g.stages;
+                mbar_wait(&bars.empty[s], ((i / g.stages) & 1) ^ 1);
+                const int b = kb / g.kb_per_img, t = (kb - b * g.kb_per_img) * 64;
+                uint8_t *a = base + (size_t)s * stage_bytes;
+                if (g.a_mn) {
+                    int boxes = 0;
+                    for (int h = 0; h < 2 * g.MT; ++h) boxes += (m0 + 64 * h < g.M) ? 1 : 0;
+                    mbar_expect_tx(&bars.full[s], (uint32_t)(boxes * 8192 + b_bytes));
+                    for (int h = 0; h < 2 * g.MT; ++h)
+                        if (m0 + 64 * h < g.M) tk_tma_load_3d(a + (size_t)h * 8192, &map_a, &bars.full[s], m0 + 64 * h, t, b);
+                } else {
+                    int blocks = 0;
+                    for (int mt = 0; mt < g.MT; ++mt) blocks += (m0 + 128 * mt < g.M) ? 1 : 0;
+                    mbar_expect_tx(&bars.full[s], (uint32_t)(blocks * kTkSlot + b_bytes));
+                    for (int mt = 0; mt < g.MT; ++mt)
+                        if (m0 + 128 * mt < g.M)
+                            tk_tma_load_3d(a + (size_t)mt * kTkSlot, &map_a, &bars.full[s], t, m0 + 128 * mt, b);
+                }
+                tk_tma_load_3d(a + a_bytes, &map_x, &bars.full[s], t, c0, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t major = g.a_mn ? (1u << 15) : 0u;
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | major | ((uint32_t)(g.NB >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | major | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t ones_addr = smem_u32(ones);
+            for (int kb = kb0, i = 0; kb < kb1; ++kb, ++i) {
+                const int s = i % g.stages;
+                mbar_wait(&bars.full[s], (i / g.stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(base + (size_t)s * stage_bytes), b_addr = a_addr + a_bytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t bd = tk_desc_k(b_addr + k * 32), od = tk_desc_k(ones_addr + k * 32);
+                    for (int mt = 0; mt < g.MT; ++mt) {
+                        const uint64_t ad = g.a_mn ? tk_desc_mn(a_addr + mt * kTkSlot + k * 2048)
+                                                   : tk_desc_k(a_addr + mt * kTkSlot + k * 32);
+                        umma_f16(tmem_base + mt * g.NB, ad, bd, idesc, (i | k) ? 1u : 0u);
+                        umma_f16(tmem_base + ones_col + mt * 16, ad, od, idesc1, (i | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&bars.empty[s]);
+            }
+            umma_commit(&bars.acc_full);
+        }
+    } else {
+        // ===== epilogue: 4 warps, lane = row of the 128-block; fp32 partials of this split
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        if (kb1 > kb0) {
+            mbar_wait(&bars.acc_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        for (int mt = 0; mt < g.MT; ++mt) {
+            const int m = m0 + mt * 128 + row;
+            float *drow = part_d + ((size_t)split * g.M + (m < g.M ? m : 0)) * g.C + c0;
+            for (int j0 = 0; j0 < g.NB; j0 += 32) {
+                uint32_t v[32];
+                if (kb1 > kb0) tk_tmem_ld32(trow + mt * g.NB + j0, v);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                if (m < g.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(drow + j0 + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                        __uint_as_float(v[j + 3]));
+                }
+            }
+            if (cc == 0) {
+                uint32_t r[4] = {0u, 0u, 0u, 0u};
+                if (kb1 > kb0) {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                                 : "r"(trow + ones_col + mt * 16));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                }
+                if (m < g.M) part_rs[(size_t)split * g.M + m] = __uint_as_float(r[0]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols));
+    }
+}
+
+}  // namespace tamtr
+
+using namespace tamtr;
+
+static int tk_encode(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                     const cuuint32_t *box, const char *what) {
+    EncodeTiledFn encode = get_encode();
+    TAMTR_CHECK_ARG(encode != nullptr, TAMTR_E_NODEVICE, "%s: cuTensorMapEncodeTiled unavailable", what);
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), dims, strides,
+                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TAMTR_CHECK_ARG(cr == CUDA_SUCCESS, TAMTR_E_BADARG, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)cr);
+    return 0;
+}
+
+static bool tk_attr_once(const void *fn, bool *flags) {
+    int dev_id = 0;
+    if (cudaGetDevice(&dev_id) != cudaSuccess) return false;
+    if (dev_id < 0 || dev_id >= 64 || !flags[dev_id]) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+        if (dev_id >= 0 && dev_id < 64) flags[dev_id] = true;
+    }
+    return true;
+}
+
+extern "C" int tamtr_tok_project_supported(int B, int C, int HW, int N0, int N1, int NT) {
+    if (B <= 0 || C <= 0 || HW <= 0 || N0 <= 0 || N1 < 0 || NT < 0) return 0;
+    if (C % 64 != 0 || C > 512 || HW % 8 != 0) return 0;               // K blocks of 64; TMA row stride of X = HW * 2 bytes
+    if (N0 % 64 != 0 || N1 % 64 != 0 || NT % 4 != 0 || NT > 1024) return 0;
+    return 1;
+}
+
+extern "C" int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row,
+                                 long out0_img, void *out1, long out1_row, long out1_img, float *raw, long raw_row,
+                                 long raw_img, int B, int C, int HW, int N0, int N1, int NT, void *stream) {
+    TAMTR_CHECK_ARG(x_bf16 && w_bf16 && bias && out0, TAMTR_E_BADARG, "tok_project: null pointer");
+    TAMTR_CHECK_ARG(tamtr_tok_project_supported(B, C, HW, N0, N1, NT), TAMTR_E_UNSUPPORTED,
+                    "tok_project: unsupported problem (B=%d C=%d HW=%d N0=%d N1=%d NT=%d): need C %% 64 == 0, C <= 512, "
+                    "HW %% 8 == 0, N0 %% 64 == 0, N1 %% 64 == 0, NT %% 4 == 0, NT <= 1024", B, C, HW, N0, N1, NT);
+    TAMTR_CHECK_ARG((N1 == 0 || out1 != nullptr) && (NT == 0 || raw != nullptr), TAMTR_E_BADARG,
+                    "tok_project: missing output tensor");
+    TAMTR_CHECK_ARG((((uintptr_t)x_bf16 | (uintptr_t)w_bf16 | (uintptr_t)bias | (uintptr_t)out0 | (uintptr_t)out1 |
+                      (uintptr_t)raw) & 15) == 0, TAMTR_E_BADARG, "tok_project: pointers must be 16-byte aligned");
+    TAMTR_CHECK_ARG(out0_row % 8 == 0 && out0_img % 8 == 0 && out1_row % 8 == 0 && out1_img % 8 == 0 && raw_row % 4 == 0 &&
+                    raw_img % 4 == 0, TAMTR_E_BADARG, "tok_project: output strides must keep 16-byte alignment");
+    const int Nall = N0 + N1 + NT;
+    CUtensorMap map_x, map_w, map_o0, map_o1;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)C * HW * 2};
+        const cuuint32_t box[3] = {64, 64, 1};
+        const int rc = tk_encode(&map_x, x_bf16, 3, dims, strides, box, "tok_project(x)");
+        if (rc) return rc;
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)Nall};
+        const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+        const cuuint32_t box[2] = {64, 128};
+        const int rc = tk_encode(&map_w, w_bf16, 2, dims, strides, box, "tok_project(w)");
+        if (rc) return rc;
+    }
+    for (int which = 0; which < 2; ++which) {
+        const bool live = which == 0 || N1 > 0;
+        const cuuint64_t dims[3] = {(cuuint64_t)(which == 0 ? N0 : (live ? N1 : N0)), (cuuint64_t)HW, (cuuint64_t)B};
+        const long row = which == 0 || !live ? out0_row : out1_row, img = which == 0 || !live ? out0_img : out1_img;
+        const cuuint64_t strides[2] = {(cuuint64_t)row * 2, (cuuint64_t)img * 2};
+        const cuuint32_t box[3] = {64, 128, 1};
+        const int rc = tk_encode(which == 0 ? &map_o0 : &map_o1, which == 0 || !live ? out0 : out1, 3, dims, strides, box,
+                                 "tok_project(out)");
+        if (rc) return rc;
+    }
+    PjGeom g;
+    g.B = B; g.HW = HW; g.C = C; g.n_kb = C / 64;
+    g.MT = (2 * g.n_kb <= kPjASlots) ? 2 : 1;
+    if (HW <= 128) g.MT = 1;
+    g.pairs_per_img = (HW + g.MT * 128 - 1) / (g.MT * 128);
+    g.n_pairs = B * g.pairs_per_img;
+    g.N0 = N0; g.N1 = N1; g.NT = NT;
+    g.n_steps = (Nall + 127) / 128;
+    g.raw_row = raw_row; g.raw_img = raw_img;
+    static bool attr[64] = {false};
+    TAMTR_CHECK_ARG(tk_attr_once((const void *)tok_project_kernel, attr), TAMTR_E_NODEVICE,
+                    "tok_project: cannot raise the dynamic shared memory limit");
+    const size_t smem = (size_t)(kPjASlots + kPjWStages + 2) * kTkSlot + sizeof(PjBars) + 1024;
+    const int n_sm = ::tamtr::sm_count();
+    const int grid = g.n_pairs < n_sm ? g.n_pairs : n_sm;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        KernelTimer timer(K_TOK_PROJECT, st);
+        tok_project_kernel<<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, bias, raw, g);
+    }
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int rd_geometry(RdGeom &g, int B, int C, int HW, int M, int a_mn) {
+    g.B = B; g.HW = HW; g.C = C; g.M = M; g.a_mn = a_mn;
+    g.NB = C <= 256 ? C : 256;
+    if (C % g.NB != 0) return TAMTR_E_UNSUPPORTED;
+    g.n_cchunks = C / g.NB;
+    g.MT = (g.NB <= 128 && M > 128) ? 2 : 1;
+    g.kb_per_img = (HW + 63) / 64;
+    g.total_kb = B * g.kb_per_img;
+    const int groups = ((M + g.MT * 128 - 1) / (g.MT * 128)) * g.n_cchunks;
+    int splits = ::tamtr::sm_count() / groups;
+    if (splits < 1) splits = 1;
+    if (splits > g.total_kb) splits = g.total_kb;
+    g.splits = splits;
+    const int stage_bytes = g.MT * kTkSlot + g.NB * 128;
+    g.stages = (200 * 1024) / stage_bytes;
+    if (g.stages > 4) g.stages = 4;
+    const int cols = g.MT * g.NB + g.MT * 16;
+    g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    return 0;
+}
+
+extern "C" int tamtr_tok_reduce_supported(int B, int C, int HW, int M, int a_token_major) {
+    if (B <= 0 || C <= 0 || HW <= 0 || M <= 0) return 0;
+    if (C % 64 != 0 || HW % 8 != 0) return 0;
+    if (C > 256 && C % 256 != 0) return 0;
+    if (a_token_major && M % 8 != 0) return 0;
+    return 1;
+}
+
+/* number of per-split partial results tamtr_tok_reduce writes for this problem */
+extern "C" int tamtr_tok_reduce_splits(int B, int C, int HW, int M, int a_token_major) {
+    if (!tamtr_tok_reduce_supported(B, C, HW, M, a_token_major)) return 0;
+    RdGeom g;
+    if (rd_geometry(g, B, C, HW, M, a_token_major)) return 0;
+    return g.splits;
+}
+
+extern "C" int tamtr_tok_reduce(const void *a_bf16, long a_row, long a_img, int a_token_major, const void *x_bf16,
+                                float *part_d, float *part_rs, int B, int C, int HW, int M, void *stream) {
+    TAMTR_CHECK_ARG(a_bf16 && x_bf16 && part_d && part_rs, TAMTR_E_BADARG, "tok_reduce: null pointer");
+    TAMTR_CHECK_ARG(tamtr_tok_reduce_supported(B, C, HW, M, a_token_major), TAMTR_E_UNSUPPORTED,
+                    "tok_reduce: unsupported problem (B=%d C=%d HW=%d M=%d): need C %% 64 == 0 (C > 256: C %% 256 == 0), "
+                    "HW %% 8 == 0", B, C, HW, M);
+    TAMTR_CHECK_ARG((((uintptr_t)a_bf16 | (uintptr_t)x_bf16 | (uintptr_t)part_d) & 15) == 0 && a_row % 8 == 0 && a_img % 8 == 0,
+                    TAMTR_E_BADARG, "tok_reduce: pointers / strides must keep 16-byte alignment");
+    RdGeom g;
+    TAMTR_CHECK_ARG(rd_geometry(g, B, C, HW, M, a_token_major ? 1 : 0) == 0, TAMTR_E_UNSUPPORTED, "tok_reduce: bad geometry");
+    CUtensorMap map_a, map_x;
+    if (a_token_major) {       // A [B, HW, M] (row = token, stride a_row): box = 64 columns (MN) x 64 tokens (K)
+        const cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)HW, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)a_row * 2, (cuuint64_t)a_img * 2};
+        const cuuint32_t box[3] = {64, 64, 1};
+        const int rc = tk_encode(&map_a, a_bf16, 3, dims, strides, box, "tok_reduce(a)");
+        if (rc) return rc;
+    } else {                   // A [B, M, HW] (row = channel, stride a_row): box = 64 tokens (K) x 128 rows
+        const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)M, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)a_row * 2, (cuuint64_t)a_img * 2};
+        const cuuint32_t box[3] = {64, 128, 1};
+        const int rc = tk_encode(&map_a, a_bf16, 3, dims, strides, box, "tok_reduce(a)");
+        if (rc) return rc;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)C * HW * 2};
+        const cuuint32_t box[3] = {64, (cuuint32_t)g.NB, 1};
+        const int rc = tk_encode(&map_x, x_bf16, 3, dims, strides, box, "tok_reduce(x)");
+        if (rc) return rc;
+    }
+    static bool attr[64] = {false};
+    TAMTR_CHECK_ARG(tk_attr_once((const void *)tok_reduce_kernel, attr), TAMTR_E_NODEVICE,
+                    "tok_reduce: cannot raise the dynamic shared memory limit");
+    const size_t smem = (size_t)g.stages * (g.MT * kTkSlot + g.NB * 128) + 2048 + sizeof(RdBars) + 1024;
+    const int groups = ((M + g.MT * 128 - 1) / (g.MT * 128)) * g.n_cchunks;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        KernelTimer timer(K_TOK_REDUCE, st);
+        tok_reduce_kernel<<<dim3(groups, g.splits), 64 + 128, smem, st>>>(map_a, map_x, part_d, part_rs, g);
+    }
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}

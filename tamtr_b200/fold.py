@@ -1,0 +1,352 @@
+"""Folded encoder side of the detection heads: input_proj + BatchNorm + the first Linear of every consumer as ONE
+projection per pyramid level, straight from the backbone's NCHW maps.
+
+Reference chain (ultralytics/nn/modules/head.py:1202-1264, transformer.py:273, 870), per level l with X_l [B, C_l, HW_l]:
+
+    Y = Conv2d(C_l, d, 1, bias=False)(X_l)            head.py:1206   (tokens x d)
+    M = BatchNorm2d(d)(Y)                             head.py:1206   -> `feats`
+    value_i = layers[i].cross_attn.value_proj(M)      transformer.py:273, once per decoder layer on the same feats
+    E = enc_output[0](valid * M)                      head.py:1229, ranked by enc_score_head(LayerNorm(E)).max(-1)
+
+BatchNorm with known statistics is affine per channel: M = Y * s + t,  s = gamma * rstd,  t = beta - mu * s.  Every
+consumer starts with a Linear, so with A = diag(s) Wc  [d, C_l]:
+
+    value_i = X_l^T (W_i A)^T + (W_i t + b_i)         K = C_l (128 / 256 / 512) instead of d = 512, no BatchNorm pass
+    E       = X_l^T (W_e A)^T +  W_e t  (+ b_e)
+
+and the batch statistics of Y follow from the first two moments of X_l (Y = Wc x):
+
+    mu = Wc mean(x),     var = diag(Wc Cov(x) Wc^T),  Cov(x) = E[x x^T] - mean mean^T
+
+So `feats` is never materialised: per level one second-moment reduction over X_l (tamtr_tok_reduce, C_l x C_l), a handful
+of [d, C_l]-sized matrix products (differentiable torch ops: autograd carries the gradients of conv weight, gamma, beta,
+value_proj and -- through the selected rows -- enc_output), one projection kernel (tamtr_tok_project) writing the value
+tensors of all decoder layers, the ranking embedding and the ranking scores, and in the backward ONE reduction
+grad_value^T X_l (tamtr_tok_reduce) in place of value_proj's dgrad, the BatchNorm backward passes and the conv's wgrad.
+At TAM-TR shapes (B = 16, 33 600 tokens, d = 512) the dense work drops from 2.8 TFLOP + 6 passes over [B, Lv, d] to
+0.85 TFLOP and no pass.  The rows picked by the query selection (B * nq of B * Lv) are recomputed from X_l through the same
+A and t, differentiably (head.py:1240-1254 only ever sends gradient to those rows).
+
+Numerics: X_l and the folded weights are bf16 operands of fp32-accumulating tensor-core products; statistics and the
+fold itself are fp32.  Compared with the reference under autocast (Y and M each rounded to bf16) the folded path rounds
+once less.  It is taken for bf16 activations only; fp32 inputs keep the unfolded kernels (ops.input_proj_tokens).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+MATH_DTYPE = torch.float32          # dtype of the fold (tests run the algebra in float64 on the CPU through the hooks below)
+
+
+# ---------------------------------------------------------------------------------------- kernel hooks (C ABI, CUDA only)
+def _kernel_reduce(a, a_row, a_img, token_major, x, M):
+    """D [M, C] = sum over (image, token) of a[m; b, tok] * x[b, c, tok], rs [M] = row sums of a (tamtr_tok_reduce)."""
+    _lib.require_cuda(a, x)
+    if a.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
+        raise RuntimeError("tamtr_b200: tok_reduce takes bf16 operands")
+    B, C = x.shape[0], x.shape[1]
+    HW = x.shape[2] * x.shape[3]
+    lib = _lib.lib()
+    S = lib.tamtr_tok_reduce_splits(B, C, HW, M, int(token_major))
+    if S <= 0:
+        raise RuntimeError(f"tamtr_b200: tok_reduce does not support B={B} C={C} HW={HW} M={M}")
+    part_d = torch.empty(S, M, C, dtype=torch.float32, device=x.device)
+    part_rs = torch.empty(S, M, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.tamtr_tok_reduce(a.data_ptr(), a_row, a_img, int(token_major), x.data_ptr(), part_d.data_ptr(),
+                                  part_rs.data_ptr(), B, C, HW, M, _lib.stream_ptr(x.device))
+    _lib.check(rc, "tok_reduce")
+    return part_d.sum(0), part_rs.sum(0)
+
+
+def _kernel_project(x, w, bias, out0, out1, raw, start, N0, N1, NT):
+    """out0[:, start:start+HW] / out1[...] / raw[...] = x^T w^T + bias, column ranges [0,N0) / [N0,N0+N1) / the rest."""
+    _lib.require_cuda(x, w, bias, out0)
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or bias.dtype != torch.float32:
+        raise RuntimeError("tamtr_b200: tok_project takes bf16 operands and an fp32 bias")
+    B, C = x.shape[0], x.shape[1]
+    HW = x.shape[2] * x.shape[3]
+    Lv = out0.shape[1]
+    es0 = out0.element_size()
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().tamtr_tok_project(
+            x.data_ptr(), w.data_ptr(), bias.data_ptr(),
+            out0.data_ptr() + start * N0 * es0, N0, Lv * N0,
+            (out1.data_ptr() + start * N1 * out1.element_size()) if N1 else None, N1, Lv * N1,
+            (raw.data_ptr() + start * NT * 4) if NT else None, NT, Lv * NT,
+            B, C, HW, N0, N1, NT, _lib.stream_ptr(x.device))
+    _lib.check(rc, "tok_project")
+
+
+def supported(xs, d, n_value_cols, n_tail=16):
+    """True when every level can go through the folded kernels (else the caller keeps the unfolded path)."""
+    if not xs or not all(x.is_cuda and x.dim() == 4 for x in xs):
+        return False
+    lib = _lib.lib()
+    B = xs[0].shape[0]
+    for x in xs:
+        C, HW = x.shape[1], x.shape[2] * x.shape[3]
+        if x.shape[0] != B or not lib.tamtr_tok_project_supported(B, C, HW, n_value_cols, d, n_tail):
+            return False
+        if not lib.tamtr_tok_reduce_supported(B, C, HW, C, 0) or not lib.tamtr_tok_reduce_supported(B, C, HW, n_value_cols, 1):
+            return False
+    return True
+
+
+# ---------------------------------------------------------------------------------------- moments of X_l
+class _TokStatsFn(torch.autograd.Function):
+    """x [B, C, H, W] bf16 -> (S1 [C] = sum over tokens of x, G [C, C] = sum over tokens of x x^T), fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, C, H, W = x.shape
+        G, S1 = _kernel_reduce(x, H * W, C * H * W, False, x, C)
+        ctx.save_for_backward(x)
+        return S1, G
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dS1, dG):
+        (x,) = ctx.saved_tensors            # only reached when the feature maps themselves require a gradient
+        B, C, H, W = x.shape
+        with torch.autocast("cuda", enabled=False):
+            sym = (dG + dG.t()).to(x.dtype)
+            dx = torch.matmul(sym, x.flatten(2)) + dS1.to(x.dtype).view(1, C, 1)
+        return dx.view(B, C, H, W)
+
+
+def _moments(x):
+    if x.requires_grad and torch.is_grad_enabled():
+        return _TokStatsFn.apply(x)
+    B, C, H, W = x.shape
+    G, S1 = _kernel_reduce(x, H * W, C * H * W, False, x, C)
+    return S1, G
+
+
+def _pad_cols(t, width):
+    return t if t.shape[-1] == width else F.pad(t, (0, width - t.shape[-1]))
+
+
+# ---------------------------------------------------------------------------------------- the projection
+class _TokProjectFn(torch.autograd.Function):
+    """values of all decoder layers (+ ranking embedding and scores as side outputs on `tokens`) from the folded weights.
+
+    Fv [L, N0, Cm + 1]: per level the folded value weights (columns [0, C_l)) and the folded bias part W t (column Cm);
+    bv [N0] the layers' own biases; Fe [L, N1 + NT, Cm + 1] likewise for the ranking branch (no gradient: head.py's dense
+    ranking pass only selects rows).  Backward: one reduction per level over the shared gradient arena."""
+
+    @staticmethod
+    def forward(ctx, tokens, arena, n_layers, n_heads, Fv, bv, Fe, *xs):
+        L, N0, Cm1 = Fv.shape
+        Cm = Cm1 - 1
+        N1, NT = tokens.d, Fe.shape[1] - tokens.d
+        B, Lv, dev = tokens.B, tokens.Lv, xs[0].device
+        W = torch.cat([Fv, Fe], 1)                                             # [L, N_all, Cm + 1]
+        bias = W[:, :, Cm].clone()
+        bias[:, :N0] += bv.to(bias.dtype)
+        lp = tokens.dtype                                                      # bf16 (the kernels take nothing else)
+        acc = torch.float32 if lp == torch.bfloat16 else W.dtype
+        bias = bias.to(acc).contiguous()
+        Wb = W[:, :, :Cm].to(lp)
+        value_all = torch.empty(B, Lv, N0, dtype=lp, device=dev)
+        E = torch.empty(B, Lv, N1, dtype=lp, device=dev)
+        raw = torch.empty(B * Lv, NT, dtype=acc, device=dev)
+        wl = []
+        for l, x in enumerate(xs):
+            C = x.shape[1]
+            w = Wb[l, :, :C].contiguous()
+            _kernel_project(x, w, bias[l], value_all, E, raw.view(B, Lv, NT), tokens.starts[l], N0, N1, NT)
+            wl.append(w[:N0])
+        tokens.E, tokens.raw = E, raw
+        d = N0 // n_layers
+        ctx.save_for_backward(*xs, *wl)
+        ctx.arena, ctx.n, ctx.d, ctx.L, ctx.Cm = arena, n_layers, d, L, Cm
+        ctx.meta = (value_all.shape, tokens.starts, tokens.hw, Fv.dtype, bv.dtype, lp)
+        ctx.set_materialize_grads(False)
+        arena.base = value_all
+        return tuple(value_all[:, :, i * d:(i + 1) * d].view(B, Lv, n_heads, d // n_heads) for i in range(n_layers))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        L, Cm, n, d = ctx.L, ctx.Cm, ctx.n, ctx.d
+        xs, wl = ctx.saved_tensors[:L], ctx.saved_tensors[L:]
+        shape, starts, hw, fdt, bdt, lp = ctx.meta
+        arena = ctx.arena
+        buf, arena.buf, arena.base = arena.buf, None, None
+        written, arena.written = arena.written, set()
+        arena.bias_grad = {}
+        dev = xs[0].device
+        if buf is None:
+            buf = _lib.zeros_like_fast(torch.empty(shape, dtype=lp, device=dev))
+        for i, g in enumerate(grads):
+            if g is None:
+                continue
+            if i * d in written:
+                if any(st != 0 for st in g.stride()):
+                    raise RuntimeError("tamtr_b200: a projected value view has a consumer besides its sampler")
+                continue
+            buf[:, :, i * d:(i + 1) * d].add_(g.reshape(shape[0], shape[1], d))
+        if buf.dtype != lp:                             # fp32 arena: one cast pass in front of the reductions
+            buf = buf.to(lp)
+        B, Lv, N0 = shape
+        dFv = torch.zeros(L, N0, Cm + 1, dtype=fdt, device=dev)
+        dxs = []
+        for l, x in enumerate(xs):
+            C = x.shape[1]
+            a = buf[:, starts[l]:]
+            D, rs = _kernel_reduce(a, N0, Lv * N0, True, x, N0)
+            dFv[l, :, :C] = D
+            dFv[l, :, Cm] = rs
+            if ctx.needs_input_grad[7 + l]:
+                with torch.autocast("cuda", enabled=False):
+                    gx = torch.matmul(wl[l].t(), buf[:, starts[l]:starts[l] + hw[l]].transpose(1, 2))    # [B, C, HW]
+                dxs.append(gx.view(x.shape).to(x.dtype))
+            else:
+                dxs.append(None)
+        dbv = dFv[:, :, Cm].sum(0).to(bdt) if ctx.needs_input_grad[5] else None
+        return (None, None, None, None, dFv, dbv, None, *dxs)
+
+
+# ---------------------------------------------------------------------------------------- the token source
+class FoldedTokens:
+    """Stands where `feats` [B, Lv, d] stands in the heads when the encoder side is folded: carries the NCHW maps and the
+    per-level affine map  M = X^T A^T + t  instead of the materialised tokens."""
+
+    is_folded = True
+
+    def __init__(self, xs, projs, training):
+        self.xs = [x.contiguous() for x in xs]
+        self.shapes = [[x.shape[2], x.shape[3]] for x in xs]
+        self.hw = [h * w for h, w in self.shapes]
+        self.starts = [sum(self.hw[:i]) for i in range(len(xs))]
+        self.B, self.Lv = xs[0].shape[0], sum(self.hw)
+        self.device, self.dtype = xs[0].device, xs[0].dtype
+        self.cs = [x.shape[1] for x in xs]
+        self.Cm = max(self.cs)
+        self.d = projs[0][0].weight.shape[0]
+        self.shape = (self.B, self.Lv, self.d)
+        self.is_cuda = xs[0].is_cuda
+        self.values = self.arena = self.E = self.raw = None
+        with torch.autocast(self.device.type, enabled=False):
+            self.A, self.t = self._coefficients(projs, training)        # [L, d, Cm] (zero beyond C_l), [L, d]
+        self.requires_grad = self.A.requires_grad
+
+    # BatchNorm2d's forward (torch/nn/modules/batchnorm.py:155-193) on statistics derived from the moments of X
+    def _coefficients(self, projs, training):
+        md, Cm, d, L = MATH_DTYPE, self.Cm, self.d, len(self.xs)
+        convs, bns = [p[0] for p in projs], [p[1] for p in projs]
+        Wc = torch.stack([_pad_cols(c.weight.reshape(d, -1).to(md), Cm) for c in convs])             # [L, d, Cm]
+        gamma = torch.stack([b.weight.to(md) for b in bns])
+        beta = torch.stack([b.bias.to(md) for b in bns])
+        eps = bns[0].eps            # python scalars only: nothing here may copy from the host (CUDA-graph capture)
+        if any(b.eps != eps for b in bns):
+            eps = torch.stack([torch.full((1,), b.eps, dtype=md, device=self.device) for b in bns])
+        batch_stats = [training or b.running_mean is None for b in bns]
+        if any(batch_stats) and not all(batch_stats):
+            raise RuntimeError("tamtr_b200: input_proj BatchNorm layers must agree on track_running_stats")
+        if batch_stats[0]:
+            S1s, Gs = [], []
+            for x, C in zip(self.xs, self.cs):
+                S1, G = _moments(x)
+                n_tok = float(x.shape[0] * x.shape[2] * x.shape[3])
+                S1s.append(_pad_cols(S1.to(md), Cm) / n_tok)
+                Gs.append(F.pad(G.to(md), (0, Cm - C, 0, Cm - C)) / n_tok)
+            mean_x = torch.stack(S1s)
+            cov = torch.stack(Gs) - mean_x.unsqueeze(2) * mean_x.unsqueeze(1)
+            mu = torch.bmm(Wc, mean_x.unsqueeze(-1)).squeeze(-1)
+            var = (torch.bmm(Wc, cov) * Wc).sum(-1).clamp_min(0)
+            if training:
+                with torch.no_grad():
+                    for l, b in enumerate(bns):
+                        if b.running_mean is None:
+                            continue
+                        mom = b.momentum if b.momentum is not None else 1.0 / float(b.num_batches_tracked + 1)
+                        n_tok = float(self.B * self.hw[l])
+                        b.running_mean.mul_(1 - mom).add_(mu[l].to(b.running_mean.dtype), alpha=mom)
+                        b.running_var.mul_(1 - mom).add_((var[l] * (n_tok / max(n_tok - 1, 1))).to(b.running_var.dtype),
+                                                         alpha=mom)
+                        b.num_batches_tracked += 1
+        else:
+            mu = torch.stack([b.running_mean.to(md) for b in bns])
+            var = torch.stack([b.running_var.to(md) for b in bns])
+        s = gamma * torch.rsqrt(var + eps)
+        t = beta - mu * s
+        return s.unsqueeze(-1) * Wc, t
+
+    # --- dense side: values of every decoder layer, ranking embedding and scores, one kernel per level
+    def project(self, attns, enc_linear, enc_norm, score_linear):
+        md = MATH_DTYPE
+        n_layers, n_heads = len(attns), attns[0].n_heads
+        with torch.autocast(self.device.type, enabled=False):
+            Wv = torch.cat([a.value_proj.weight for a in attns], 0).to(md)                          # [N0, d]
+            bv = torch.cat([a.value_proj.bias for a in attns], 0)
+            Aext = torch.cat([self.A, self.t.unsqueeze(-1)], -1)                                    # [L, d, Cm + 1]
+            Fv = torch.matmul(Wv, Aext)
+            with torch.no_grad():
+                rk = _rank_constants(enc_linear, enc_norm, score_linear, md)
+                Fe = torch.matmul(torch.cat([enc_linear.weight.to(md), rk["Wr"]], 0), Aext.detach())
+            self.rank_consts = rk
+            self.arena = ops.ValueArena()
+            if torch.is_grad_enabled() and (Fv.requires_grad or bv.requires_grad or any(x.requires_grad for x in self.xs)):
+                vals = _TokProjectFn.apply(self, self.arena, n_layers, n_heads, Fv, bv, Fe, *self.xs)
+            else:
+                ctx = _NoCtx()
+                vals = _TokProjectFn.forward(ctx, self, self.arena, n_layers, n_heads, Fv.detach(), bv.detach(), Fe, *self.xs)
+                self.arena = None
+        self.values = list(vals)
+        return self.values
+
+    def rank(self, valid_u8):
+        """max over classes of enc_score_head(LayerNorm(enc_output.0(valid * feats))) for every token -> [B, Lv] fp32."""
+        rk = self.rank_consts
+        out = torch.empty(self.B, self.Lv, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().tamtr_rank_tokens(self.E.data_ptr(), self.raw.data_ptr(), rk["eb"].data_ptr(), valid_u8.data_ptr(),
+                                              rk["bw"].data_ptr(), rk["sw"].data_ptr(), rk["ck"].data_ptr(), out.data_ptr(),
+                                              _lib.dtype_code(self.E), self.B, self.Lv, self.d, rk["nc"], rk["npad"],
+                                              float(rk["eps"]), _lib.stream_ptr(self.device))
+        _lib.check(rc, "rank_tokens")
+        return out
+
+    # --- sparse side: the selected tokens, differentiably
+    def rows(self, flat_idx):
+        """feats.reshape(-1, d)[flat_idx] (flat_idx = image * Lv + token) recomputed from X through A and t."""
+        md = MATH_DTYPE
+        img = torch.div(flat_idx, self.Lv, rounding_mode="floor")
+        tok = flat_idx - img * self.Lv
+        out = None
+        with torch.autocast(self.device.type, enabled=False):
+            for l, x in enumerate(self.xs):
+                C = self.cs[l]
+                rel = tok - self.starts[l]
+                inside = ((rel >= 0) & (rel < self.hw[l])).to(md).unsqueeze(-1)
+                xr = x.flatten(2)[img, :, rel.clamp(0, self.hw[l] - 1)].to(md)                      # [R, C_l]
+                y = (torch.addmm(self.t[l], xr, self.A[l, :, :C].t())) * inside
+                out = y if out is None else out + y
+        return out
+
+
+class _NoCtx:
+    """Stand-in for the autograd context when the projection runs without a graph (inference)."""
+    needs_input_grad = ()
+
+    def save_for_backward(self, *a):
+        pass
+
+    def set_materialize_grads(self, v):
+        pass
+
+
+def _rank_constants(enc_linear, enc_norm, score_linear, md):
+    """Constants of tamtr_rank_tokens (include/tamtr_b200.h): the score head folded with the LayerNorm weight."""
+    Wp = score_linear.weight.to(md) * enc_norm.weight.to(md)                                        # [nc, d]
+    nc, d = Wp.shape
+    npad = (nc + 15) // 16 * 16
+    Wpad = torch.zeros(npad, d, dtype=md, device=Wp.device)
+    Wpad[:nc] = Wp
+    eb = enc_linear.bias.to(md)
+    return {"Wr": Wpad @ enc_linear.weight.to(md), "eb": eb.float().contiguous(), "bw": (Wp @ eb).float().contiguous(),
+            "sw": Wp.sum(1).float().contiguous(),
+            "ck": (score_linear.weight.to(md) @ enc_norm.bias.to(md) + score_linear.bias.to(md)).float().contiguous(),
+            "nc": nc, "npad": npad, "eps": enc_norm.eps}

@@ -17,11 +17,11 @@ import os
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import fold, ops
 from .loss import DeviceTargets
 from .vss import VSSBlock
 from .modules import (MLP, ContrastiveHeadMLP, DeformableTransformerDecoder, DeformableTransformerDecoderLayer,
-                      TextDeformableTransformerDecoder)
+                      TextDeformableTransformerDecoder, is_plain_msda)
 
 __all__ = ("RTDETRDecoder", "ManbaWorldDecoder", "get_cdn_group", "plan_cdn_group", "CdnPlan", "cdn_group_device")
 
@@ -241,20 +241,35 @@ class _HeadBase(nn.Module):
     sparse_query_selection = True
 
     def _rank_tokens(self, feats, valid):
+        if getattr(feats, "is_folded", False):
+            return feats.rank(self._valid_u8(valid))
         if feats.is_cuda and feats.dtype in (torch.float32, torch.bfloat16) and self.fused_input_proj:
-            cache = self.__dict__.setdefault("_anchor_cache", {})
-            key = ("valid_u8", valid.data_ptr())
-            if key not in cache:
-                cache[key] = valid.view(-1).to(torch.uint8).contiguous()
-            return ops.rank_tokens(feats, cache[key], self.enc_output[0], self.enc_output[1], self.enc_score_head)
+            return ops.rank_tokens(feats, self._valid_u8(valid), self.enc_output[0], self.enc_output[1],
+                                   self.enc_score_head)
         with torch.no_grad():
             features = self.enc_output(valid * feats)
             return self.enc_score_head(features).max(-1).values              # [B, Lv]
 
+    def _valid_u8(self, valid):
+        cache = self.__dict__.setdefault("_anchor_cache", {})
+        key = ("valid_u8", valid.data_ptr())
+        if key not in cache:
+            cache[key] = valid.view(-1).to(torch.uint8).contiguous()
+        return cache[key]
+
     def _get_decoder_input(self, feats, shapes, dn_embed=None, dn_bbox=None, hub=None):
         bs, n_tok = feats.shape[0], feats.shape[1]
         anchors, valid = self._anchors(shapes, feats.dtype, feats.device)
-        if self.sparse_query_selection and hub is not None:
+        if getattr(feats, "is_folded", False):
+            # fold.FoldedTokens: ranking embedding and scores came out of the projection kernel; the selected rows are
+            # recomputed from the NCHW maps through the folded affine map (differentiable)
+            topk = torch.topk(self._rank_tokens(feats, valid), self.num_queries, dim=1).indices.view(-1)
+            img = torch.arange(end=bs, dtype=topk.dtype, device=topk.device).unsqueeze(-1).repeat(
+                1, self.num_queries).view(-1)
+            rows = valid.view(-1)[topk].unsqueeze(-1) * feats.rows(img * n_tok + topk)
+            top_feats = self.enc_output(rows).view(bs, self.num_queries, -1)
+            enc_scores = self.enc_score_head(top_feats)
+        elif self.sparse_query_selection and hub is not None:
             topk = torch.topk(self._rank_tokens(feats, valid), self.num_queries, dim=1).indices.view(-1)
             img = torch.arange(end=bs, dtype=topk.dtype, device=topk.device).unsqueeze(-1).repeat(
                 1, self.num_queries).view(-1)
@@ -284,8 +299,38 @@ class _HeadBase(nn.Module):
             embeddings = torch.cat([dn_embed, embeddings], 1)
         return embeddings, refer_bbox, enc_bboxes, enc_scores
 
+    # Folded encoder side (fold.py): input_proj + BatchNorm + value_proj of every layer + enc_output.0 / score head as one
+    # projection per level from the NCHW maps; `feats` is never materialised.  bf16 activations only.
+    folded_projection = os.environ.get("TAMTR_FOLD", "1") != "0"
+
+    def _fold_attns(self, x):
+        """The decoder layers' cross-attention modules when the folded path applies to this call, else None."""
+        if not (self.folded_projection and self.sparse_query_selection and self._fusable_input_proj(x)):
+            return None
+        lp = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x[0].dtype
+        dec = self.decoder
+        if lp != torch.bfloat16 or not getattr(dec, "batched_value_projection", False):
+            return None
+        n_used = dec.num_layers if self.training else dec.eval_idx + 1
+        attns = [getattr(l, "cross_attn", None) for l in dec.layers[:n_used]]
+        if not all(is_plain_msda(a) for a in attns) or any(a.n_heads != attns[0].n_heads for a in attns):
+            return None
+        d = self.hidden_dim
+        n_tail = (self.enc_score_head.weight.shape[0] + 15) // 16 * 16
+        if not (isinstance(self.enc_output, nn.Sequential) and isinstance(self.enc_output[0], nn.Linear)
+                and isinstance(self.enc_output[1], nn.LayerNorm) and isinstance(self.enc_score_head, nn.Linear)
+                and d <= 4 * 32 * 8 and all(a.value_proj.weight.shape == (d, d) for a in attns)):
+            return None
+        return attns if fold.supported(list(x), d, n_used * d, n_tail) else None
+
     def _encode(self, x):
         """input projection + (when the CUDA path applies) the gradient hub on the token tensor."""
+        attns = self._fold_attns(x)
+        if attns is not None:
+            xs = [f if f.dtype == torch.bfloat16 else f.to(torch.bfloat16) for f in x]
+            feats = fold.FoldedTokens(xs, self.input_proj, self.training)
+            feats.project(attns, self.enc_output[0], self.enc_output[1], self.enc_score_head)
+            return feats, feats.shapes, None
         feats, shapes = self._get_encoder_input(x)
         hub = None
         if self.sparse_query_selection and feats.is_cuda:

@@ -299,6 +299,12 @@ class DecouplingDeformableTransformerDecoderLayer(nn.Module):
         return out_cls, _add_norm(self, embed1, t2, self.dropout8, self.norm6)
 
 
+def is_plain_msda(a):
+    """MSDeformAttn itself (ours or the reference's class of that name, whose forward enable() rebinds) -- not the
+    ragged _cls / _box variants, whose value tensors are consumed differently."""
+    return a is not None and type(a).__name__ == "MSDeformAttn" and isinstance(getattr(a, "value_proj", None), nn.Linear)
+
+
 class _DecoderBase(nn.Module):
     def __init__(self, hidden_dim, decoder_layer, num_layers, eval_idx=-1):
         super().__init__()
@@ -312,10 +318,12 @@ class _DecoderBase(nn.Module):
     def _project_values(self, feats, padding_mask, n_used):
         """transformer.py:273 runs value_proj inside every layer on the SAME `feats` (transformer.py:870): do all
         layers with one [d, n*d] GEMM and hand each layer a column-slice view (head-major, what the sampler reads)."""
+        if getattr(feats, "is_folded", False):      # fold.FoldedTokens: the head projected them with the folded weights
+            return feats.values, feats.arena
         if not (self.batched_value_projection and feats.is_cuda and padding_mask is None and n_used > 1):
             return [None] * n_used, None
-        attns = [l.cross_attn for l in self.layers[:n_used]]
-        if any(type(a) is not MSDeformAttn for a in attns):
+        attns = [getattr(l, "cross_attn", None) for l in self.layers[:n_used]]
+        if not all(is_plain_msda(a) for a in attns):
             return [None] * n_used, None
         w = torch.cat([a.value_proj.weight for a in attns], 0)
         b = torch.cat([a.value_proj.bias for a in attns], 0)

@@ -54,7 +54,7 @@ def install(ref_cls, ours_cls, names, rebind=None):
 
 HEAD_ATTRS = ("forward", "_get_encoder_input", "_get_decoder_input", "_generate_anchors", "_encode", "_cdn", "_anchors",
               "_rank_tokens", "_fusable_input_proj", "_finish", "plan_cdn", "fused_input_proj", "sparse_query_selection",
-              "__getstate__")
+              "__getstate__", "_valid_u8", "_fold_attns", "folded_projection")
 DECODER_ATTRS = ("forward", "_run", "_project_values", "batched_value_projection")
 MATCHER_ATTRS = ("forward", "match_layers", "match_padded")
 LOSS_ATTRS = ("forward", "_get_loss_layers")

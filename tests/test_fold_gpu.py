@@ -1,0 +1,170 @@
+"""GPU tests of the folded encoder side: the two tcgen05 kernels of csrc/tokgemm.cu against fp32 restatements on the same
+bf16 operands, and the folded head against the unfolded kernels (same module, `folded_projection` off)."""
+import pytest
+import torch
+
+from helpers import rel_l2
+from oracle import seeding
+
+pytestmark = pytest.mark.gpu
+
+
+def _maps(B, C, H, W, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(B, C, H, W, generator=g) * 0.7 + 0.3).bfloat16().cuda()
+
+
+@pytest.mark.parametrize("B,C,H,W,N0,N1,NT", [
+    (2, 128, 20, 20, 256, 128, 16),        # two 128-token blocks per CTA, ragged last block (400 tokens)
+    (1, 64, 8, 8, 64, 64, 16),             # a single, partly filled block
+    (3, 256, 16, 24, 384, 256, 80),        # tail wider than one 64-column chunk (nc = 80 classes)
+    (2, 512, 10, 20, 1536, 512, 16),       # one block per CTA (C = 512), TAM-TR column counts
+    (2, 128, 40, 40, 1536, 512, 16),       # 1600 tokens: 12.5 blocks per image
+    (2, 192, 12, 12, 128, 64, 0),          # no tail
+])
+def test_tok_project_matches_fp32(cuda_lib, B, C, H, W, N0, N1, NT):
+    from tamtr_b200 import fold
+    x = _maps(B, C, H, W, 1)
+    g = torch.Generator().manual_seed(2)
+    Nall = N0 + N1 + NT
+    w = (torch.randn(Nall, C, generator=g) / C ** 0.5).bfloat16().cuda()
+    bias = torch.randn(Nall, generator=g).cuda()
+    HW, pre, post = H * W, 24, 8                       # the level sits inside a longer token axis
+    Lv = pre + HW + post
+    out0 = torch.full((B, Lv, N0), 7.0, dtype=torch.bfloat16, device="cuda")
+    out1 = torch.full((B, Lv, max(N1, 1)), 7.0, dtype=torch.bfloat16, device="cuda")[..., :N1].contiguous() if N1 else None
+    raw = torch.full((B, Lv, max(NT, 1)), 7.0, device="cuda")[..., :NT].contiguous() if NT else None
+    fold._kernel_project(x, w, bias, out0, out1 if N1 else out0, raw if NT else out0, pre, N0, N1, NT)
+    torch.cuda.synchronize()
+    ref = x.float().flatten(2).transpose(1, 2) @ w.float().t() + bias                 # [B, HW, Nall]
+    assert rel_l2(out0[:, pre:pre + HW], ref[..., :N0]) < 4e-3
+    assert (out0[:, pre:pre + HW].float() - ref[..., :N0]).abs().max() < 0.05
+    if N1:
+        assert rel_l2(out1[:, pre:pre + HW], ref[..., N0:N0 + N1]) < 4e-3
+    if NT:
+        assert rel_l2(raw[:, pre:pre + HW], ref[..., N0 + N1:]) < 1e-5
+    # nothing outside the level's token range is touched
+    for t in (out0, out1, raw):
+        if t is not None:
+            assert torch.all(t[:, :pre] == 7.0) and torch.all(t[:, pre + HW:] == 7.0)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 128, 20, 20), (1, 64, 8, 8), (3, 256, 16, 24), (2, 512, 10, 20), (4, 128, 40, 40)])
+def test_tok_reduce_moments(cuda_lib, B, C, H, W):
+    from tamtr_b200 import fold
+    x = _maps(B, C, H, W, 3)
+    G, S1 = fold._kernel_reduce(x, H * W, C * H * W, False, x, C)
+    X = x.double().flatten(2)
+    assert rel_l2(G, torch.einsum("bct,bdt->cd", X, X)) < 1e-5
+    assert rel_l2(S1, X.sum((0, 2))) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,W,M", [(2, 128, 20, 20, 256), (1, 64, 8, 8, 64), (3, 256, 16, 24, 384),
+                                       (2, 512, 10, 20, 1536), (2, 128, 40, 40, 1536), (2, 128, 12, 12, 192)])
+def test_tok_reduce_weight_gradient(cuda_lib, B, C, H, W, M):
+    from tamtr_b200 import fold
+    x = _maps(B, C, H, W, 4)
+    HW, pre, post = H * W, 16, 40
+    Lv = pre + HW + post
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(B, Lv, M, generator=g).bfloat16().cuda()
+    D, rs = fold._kernel_reduce(a[:, pre:], M, Lv * M, True, x, M)
+    A = a[:, pre:pre + HW].double()
+    assert rel_l2(D, torch.einsum("btm,bct->mc", A, x.double().flatten(2))) < 1e-5
+    assert rel_l2(rs, A.sum((0, 1))) < 1e-5
+
+
+def _head(B=2, sizes=(40, 20, 10)):
+    from tamtr_b200.head import ManbaWorldDecoder
+    torch.manual_seed(0)
+    m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3, vss=False).cuda().train()
+    seeding.seeded_fill(m, 11)
+    xs = [seeding.seeded_smooth_map(5, f"x{i}", (B, c, s, s)).bfloat16().cuda()
+          for i, (c, s) in enumerate(zip((128, 256, 512), sizes))]
+    text = torch.nn.functional.normalize(seeding.seeded_tensor(5, "t", (B, 10, 512)), dim=-1).cuda()
+    return m, xs, text
+
+
+def test_folded_encoder_matches_unfolded(cuda_lib):
+    """values of every layer, ranking scores, selected rows and the BatchNorm side effects, folded vs unfolded kernels."""
+    import copy
+    m, xs, text = _head()
+    ref = copy.deepcopy(m)
+    ref.folded_projection = False
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        tok, shapes, hub = m._encode(xs)
+        assert getattr(tok, "is_folded", False) and hub is None
+        feats, shapes2, hub2 = ref._encode(xs)
+        assert shapes == shapes2
+        vals, _ = ref.decoder._project_values(feats, None, 3)
+        for a, b in zip(tok.values, vals):
+            assert a.shape == b.shape and rel_l2(a, b) < 1.5e-2
+        anchors, valid = m._anchors(shapes, torch.bfloat16, xs[0].device)
+        r_f, r_u = m._rank_tokens(tok, valid), ref._rank_tokens(feats, valid)
+        v = valid.view(1, -1).expand_as(r_f)
+        assert rel_l2(r_f[v], r_u[v]) < 1.5e-2
+        idx = torch.randint(0, feats.shape[0] * feats.shape[1], (300,), device="cuda")
+        assert rel_l2(tok.rows(idx), feats.reshape(-1, 512)[idx]) < 1e-2
+    for p, r in zip(m.input_proj, ref.input_proj):
+        assert rel_l2(p[1].running_mean, r[1].running_mean) < 1e-2
+        assert rel_l2(p[1].running_var, r[1].running_var) < 1e-2
+        assert int(p[1].num_batches_tracked) == int(r[1].num_batches_tracked) == 1
+
+
+def _step(m, xs, text, seed=3):
+    for p in m.parameters():
+        p.grad = None
+    torch.manual_seed(seed)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(xs, text)
+    if not m.training:
+        out = out[1]
+    db, ds, eb, es = out[:4]
+    loss = db.float().square().mean() + 0.1 * ds.float().sigmoid().mean() + eb.float().square().mean() + 0.1 * es.float().sigmoid().mean()
+    loss.backward()
+    return loss.detach(), {n: p.grad.detach().float().clone() for n, p in m.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_folded_head_step_matches_unfolded(cuda_lib, train):
+    """whole head forward + backward: same loss and parameter gradients as the unfolded kernels within bf16 tolerance,
+    and the folded path launches the projection / reduction kernels instead of the BatchNorm token passes."""
+    import copy
+    from tamtr_b200 import _lib
+    m, xs, text = _head()
+    if not train:
+        m.eval()
+    ref = copy.deepcopy(m)
+    ref.folded_projection = False
+    _lib.profile_enable(True)
+    loss_f, g_f = _step(m, xs, text)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    assert prof.get("tok_project", (0, 0))[1] == 3
+    assert prof.get("tok_reduce", (0, 0))[1] == (6 if train else 3)
+    loss_u, g_u = _step(ref, xs, text)
+    assert abs(loss_f.item() - loss_u.item()) < 2e-2 * abs(loss_u.item())
+    assert set(g_f) == set(g_u)
+    flat_f = torch.cat([g_f[k].reshape(-1) for k in sorted(g_f)])
+    flat_u = torch.cat([g_u[k].reshape(-1) for k in sorted(g_u)])
+    assert rel_l2(flat_f, flat_u) < 5e-2
+    for k in ("input_proj.0.0.weight", "input_proj.2.1.weight", "input_proj.1.1.bias",
+              "decoder.layers.0.cross_attn.value_proj.weight", "decoder.layers.2.cross_attn.value_proj.bias",
+              "enc_output.0.weight"):
+        assert rel_l2(g_f[k], g_u[k]) < 6e-2, (k, rel_l2(g_f[k], g_u[k]))
+
+
+def test_folded_head_inference_matches_unfolded(cuda_lib):
+    import copy
+    m, xs, text = _head(B=1)
+    m.eval()
+    ref = copy.deepcopy(m)
+    ref.folded_projection = False
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y_f, _ = m(xs, text)
+        y_u, _ = ref(xs, text)
+    assert y_f.shape == y_u.shape
+    # the query order comes from a top-k over near-tied scores: compare as sets of (box, scores) rows
+    a, b = y_f.float(), y_u.float()
+    dist = torch.cdist(a, b).min(-1).values
+    assert (dist < 3e-2).float().mean() > 0.9
