@@ -64,27 +64,47 @@ __device__ __forceinline__ uint32_t tk_pack2(float lo, float hi) {
 constexpr int kTkThreads = 64 + 256;         // producer warp, MMA warp, 8 epilogue warps
 constexpr int kTkSlot = 128 * 64 * 2;        // one 128 x 64 bf16 operand block = 16 KB
 
+// Shared-memory descriptors split into 32-bit halves: only the low word (start address >> 4 | LBO << 16) changes between
+// MMAs, so the issue loop adds small constants to it.  The issuing warp walks its loops with uniform control flow and
+// elects one lane per instruction group: with a single divergent lane (`if (lane == 0)`) every tcgen05 / TMA instruction
+// costs an ELECT + a handful of R2UR moves, ~40 instructions per MMA -- which bounded the first version of these
+// kernels (2 500 clk per K block whatever was loaded or multiplied: profiles/tokgemm_r2_notes.txt).
+constexpr uint32_t kTkDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t tk_lo_k(uint32_t addr) { return (addr >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t tk_lo_mn(uint32_t addr) { return (addr >> 4) | ((8192u >> 4) << 16); }
+__device__ __forceinline__ uint64_t tk_desc(uint32_t lo) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kTkDescHi));
+    return d;
+}
+__device__ __forceinline__ bool tk_elect() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ================================================================================================ forward projection
 // One CTA owns MT * 128 consecutive tokens of one image: their X columns (all K blocks) stay resident in shared memory
-// while the CTA walks the N_all output columns 128 at a time, streaming W_fold through a 3-stage ring (W_fold is a few
-// hundred KB: L2 hits).  Two TMEM accumulator stages (MT x 128 columns each) overlap the MMAs of step n+1 with the
-// epilogue of step n.  Shared memory: A <= 128 KB, W ring 48 KB, two 16 KB staging tiles.
-constexpr int kPjWStages = 3;
-constexpr int kPjASlots = 8;
+// while the CTA walks the N_all output columns 128 at a time, streaming W_fold through a ring (W_fold is a few hundred
+// KB: L2 hits).  Two TMEM accumulator stages (MT x 128 columns each) overlap the MMAs of step n+1 with the epilogue of
+// step n.  Shared memory: 11 operand slots of 16 KB (A: MT * C / 64 of them, the rest is the W ring) + two staging tiles.
+constexpr int kPjSlots = 11;
+constexpr int kPjMaxWStages = 8;
 
 struct PjBars {
-    uint64_t a_full, a_empty, w_full[kPjWStages], w_empty[kPjWStages], acc_full[2], acc_empty[2];
+    uint64_t a_full, a_empty, w_full[kPjMaxWStages], w_empty[kPjMaxWStages], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
 
 struct PjGeom {
     int B, HW, C, n_kb;            // level geometry; n_kb = C / 64
-    int MT;                        // 128-token blocks per CTA tile (1 or 2), MT * n_kb <= 8
-    int pairs_per_img, n_pairs;    // CTA tiles
+    int w_stages;                  // depth of the W ring = kPjSlots - MT * n_kb (capped)
+    int pairs_per_img, n_pairs;    // CTA tiles of MT * 128 tokens
     int N0, N1, NT, n_steps;       // bf16 columns of out0 / out1, fp32 tail columns, ceil((N0 + N1 + NT) / 128)
     long raw_row, raw_img;         // strides (elements) of the fp32 tail tensor
 };
 
+template <int MT>
 __global__ void __launch_bounds__(kTkThreads, 1)
 tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                    const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
@@ -92,15 +112,15 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sA = base;                                         // [MT][n_kb] slots of 16 KB
-    uint8_t *sW = base + (size_t)kPjASlots * kTkSlot;           // [stages] 16 KB
-    uint8_t *sO = sW + (size_t)kPjWStages * kTkSlot;            // [2] 16 KB staging tiles (one per epilogue group)
+    uint8_t *sW = base + (size_t)MT * g.n_kb * kTkSlot;         // [w_stages] 16 KB
+    uint8_t *sO = base + (size_t)kPjSlots * kTkSlot;            // [2] 16 KB staging tiles (one per epilogue group)
     PjBars &bars = *reinterpret_cast<PjBars *>(sO + 2 * kTkSlot);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(&bars.a_full, 1);
         mbar_init(&bars.a_empty, 1);
-        for (int s = 0; s < kPjWStages; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_empty[s], 1); }
+        for (int s = 0; s < kPjMaxWStages; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&bars.acc_full[a], 1); mbar_init(&bars.acc_empty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -113,69 +133,81 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = bars.tmem_base;
-    const int tile_tok = g.MT * 128;
+    constexpr int tile_tok = MT * 128;
 
     if (warp == 0) {
-        // ===== TMA producer
-        if (lane == 0) {
-            uint32_t wi = 0;
-            int it = 0;
-            for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x, ++it) {
-                const int b = p / g.pairs_per_img, tok0 = (p - b * g.pairs_per_img) * tile_tok;
-                mbar_wait(&bars.a_empty, (it & 1) ^ 1);
+        // ===== TMA producer (whole warp walks the loops, one elected lane issues)
+        uint32_t ws = 0, wph = 0;
+        int it = 0;
+        for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x, ++it) {
+            const int b = p / g.pairs_per_img, tok0 = (p - b * g.pairs_per_img) * tile_tok;
+            mbar_wait(&bars.a_empty, (it & 1) ^ 1);
+            if (tk_elect()) {
                 // 64-token boxes that start inside the image; the others are skipped (their accumulator rows are never stored)
                 int boxes = 0;
-                for (int h = 0; h < 2 * g.MT; ++h) boxes += (tok0 + 64 * h < g.HW) ? 1 : 0;
+#pragma unroll
+                for (int h = 0; h < 2 * MT; ++h) boxes += (tok0 + 64 * h < g.HW) ? 1 : 0;
                 mbar_expect_tx(&bars.a_full, (uint32_t)(boxes * g.n_kb * 8192));
-                for (int mt = 0; mt < g.MT; ++mt)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
                     for (int kb = 0; kb < g.n_kb; ++kb)
+#pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int t = tok0 + mt * 128 + h * 64;
                             if (t < g.HW)
                                 tk_tma_load_3d(sA + (size_t)(mt * g.n_kb + kb) * kTkSlot + h * 8192, &map_x, &bars.a_full, t,
                                                kb * 64, b);
                         }
-                for (int n = 0; n < g.n_steps; ++n)
-                    for (int kb = 0; kb < g.n_kb; ++kb, ++wi) {
-                        const uint32_t s = wi % kPjWStages;
-                        mbar_wait(&bars.w_empty[s], ((wi / kPjWStages) & 1) ^ 1);
-                        mbar_expect_tx(&bars.w_full[s], (uint32_t)kTkSlot);
-                        tma_load_2d(sW + (size_t)s * kTkSlot, &map_w, &bars.w_full[s], kb * 64, n * 128);
-                    }
             }
+            __syncwarp();
+            for (int n = 0; n < g.n_steps; ++n)
+                for (int kb = 0; kb < g.n_kb; ++kb) {
+                    mbar_wait(&bars.w_empty[ws], wph ^ 1);
+                    if (tk_elect()) {
+                        mbar_expect_tx(&bars.w_full[ws], (uint32_t)kTkSlot);
+                        tma_load_2d(sW + (size_t)ws * kTkSlot, &map_w, &bars.w_full[ws], kb * 64, n * 128);
+                    }
+                    __syncwarp();
+                    if (++ws == (uint32_t)g.w_stages) { ws = 0; wph ^= 1; }
+                }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: D[128 tokens, 128 columns] += A (MN-major) x W (K-major), K = 16 per instruction
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-            uint32_t wi = 0, ai = 0;
-            int it = 0;
-            for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x, ++it) {
-                mbar_wait(&bars.a_full, it & 1);
-                for (int n = 0; n < g.n_steps; ++n, ++ai) {
-                    const uint32_t as = ai & 1;
-                    mbar_wait(&bars.acc_empty[as], ((ai >> 1) & 1) ^ 1);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a_lo0 = tk_lo_mn(smem_u32(sA)), w_lo0 = tk_lo_k(smem_u32(sW));
+        const uint32_t a_mt = (uint32_t)g.n_kb * (kTkSlot >> 4);          // descriptor units between the token blocks
+        uint32_t ws = 0, wph = 0, ai = 0;
+        int it = 0;
+        for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x, ++it) {
+            mbar_wait(&bars.a_full, it & 1);
+            for (int n = 0; n < g.n_steps; ++n, ++ai) {
+                const uint32_t as = ai & 1;
+                mbar_wait(&bars.acc_empty[as], ((ai >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d0 = tmem_base + as * 256;
+                for (int kb = 0; kb < g.n_kb; ++kb) {
+                    mbar_wait(&bars.w_full[ws], wph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int kb = 0; kb < g.n_kb; ++kb, ++wi) {
-                        const uint32_t s = wi % kPjWStages;
-                        mbar_wait(&bars.w_full[s], (wi / kPjWStages) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t w_addr = smem_u32(sW + (size_t)s * kTkSlot);
+                    if (tk_elect()) {
+                        const uint32_t w_lo = w_lo0 + ws * (kTkSlot >> 4), a_lo = a_lo0 + (uint32_t)kb * (kTkSlot >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t bd = tk_desc_k(w_addr + k * 32);
-                            for (int mt = 0; mt < g.MT; ++mt) {
-                                const uint32_t a_addr = smem_u32(sA + (size_t)(mt * g.n_kb + kb) * kTkSlot);
-                                umma_f16(tmem_base + (as * 2 + mt) * 128, tk_desc_mn(a_addr + k * 2048), bd, idesc,
+                            const uint64_t bd = tk_desc(w_lo + 2 * k);
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt)
+                                umma_f16(d0 + mt * 128, tk_desc(a_lo + mt * a_mt + k * (2048 >> 4)), bd, idesc,
                                          (kb | k) ? 1u : 0u);
-                            }
                         }
-                        umma_commit(&bars.w_empty[s]);
+                        umma_commit(&bars.w_empty[ws]);
                     }
-                    umma_commit(&bars.acc_full[as]);
+                    __syncwarp();
+                    if (++ws == (uint32_t)g.w_stages) { ws = 0; wph ^= 1; }
                 }
-                umma_commit(&bars.a_empty);
+                if (tk_elect()) umma_commit(&bars.acc_full[as]);
+                __syncwarp();
             }
+            if (tk_elect()) umma_commit(&bars.a_empty);
+            __syncwarp();
         }
     } else {
         // ===== epilogue: two groups of four warps; warp % 4 = TMEM lane quarter.  MT == 2: group = token block, both
@@ -186,8 +218,8 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         uint8_t *stage = sO + (size_t)grp * kTkSlot;
         const uint32_t row_off = (uint32_t)row * 128, sw = (uint32_t)(row & 7);
         const bool leader = (warp - 2) % 4 == 0 && lane == 0;      // issues the group's TMA stores
-        const int mt = g.MT == 2 ? grp : 0;
-        const int chunk0 = g.MT == 2 ? 0 : grp, n_chunks = g.MT == 2 ? 2 : 1;
+        const int mt = MT == 2 ? grp : 0;
+        const int chunk0 = MT == 2 ? 0 : grp, n_chunks = MT == 2 ? 2 : 1;
         const int Nmain = g.N0 + g.N1, Nall = Nmain + g.NT;
         uint32_t ai = 0;
         for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x) {
@@ -282,22 +314,27 @@ struct RdGeom {
     int tmem_cols;
 };
 
+constexpr uint32_t kRdOnesStep = 32;   // TMEM columns between the row-sum accumulators (32-column aligned: at 16 the sums
+                                       // of the first row block came out nondeterministic)
+
+template <int MT, bool AMN>
 __global__ void __launch_bounds__(64 + 128, 1)
 tok_reduce_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_x,
                   float *__restrict__ part_d, float *__restrict__ part_rs, const RdGeom g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int a_bytes = g.MT * kTkSlot, b_bytes = g.NB * 128, stage_bytes = a_bytes + b_bytes;
+    constexpr int a_bytes = MT * kTkSlot;
+    const int b_bytes = g.NB * 128, stage_bytes = a_bytes + b_bytes;
     uint8_t *ones = base + (size_t)g.stages * stage_bytes;                 // 16 rows x 128 B of bf16 1.0
     RdBars &bars = *reinterpret_cast<RdBars *>(ones + 2048);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mg = blockIdx.x / g.n_cchunks, cc = blockIdx.x - mg * g.n_cchunks;
-    const int m0 = mg * g.MT * 128, c0 = cc * g.NB;
+    const int m0 = mg * MT * 128, c0 = cc * g.NB;
     const int split = blockIdx.y;
     const int kb0 = (int)((long)g.total_kb * split / g.splits), kb1 = (int)((long)g.total_kb * (split + 1) / g.splits);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < g.stages; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
         mbar_init(&bars.acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -312,57 +349,72 @@ tok_reduce_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = bars.tmem_base;
-    const uint32_t ones_col = (uint32_t)(g.MT * g.NB);           // TMEM columns of the row-sum accumulators
+    const uint32_t ones_col = (uint32_t)(MT * g.NB);             // TMEM columns of the row-sum accumulators
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = kb0, i = 0; kb < kb1; ++kb, ++i) {
-                const int s = i % g.stages;
-                mbar_wait(&bars.empty[s], ((i / g.stages) & 1) ^ 1);
-                const int b = kb / g.kb_per_img, t = (kb - b * g.kb_per_img) * 64;
+        // ===== TMA producer
+        int b = kb0 / g.kb_per_img, tb = kb0 - b * g.kb_per_img;
+        uint32_t s = 0, ph = 0;
+        int boxes = 0;                                             // A boxes that start inside the M rows
+        if (AMN) { for (int h = 0; h < 2 * MT; ++h) boxes += (m0 + 64 * h < g.M) ? 1 : 0; }
+        else { for (int mt = 0; mt < MT; ++mt) boxes += (m0 + 128 * mt < g.M) ? 2 : 0; }
+        const uint32_t tx = (uint32_t)(boxes * 8192 + b_bytes);
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&bars.empty[s], ph ^ 1);
+            if (tk_elect()) {
                 uint8_t *a = base + (size_t)s * stage_bytes;
-                if (g.a_mn) {
-                    int boxes = 0;
-                    for (int h = 0; h < 2 * g.MT; ++h) boxes += (m0 + 64 * h < g.M) ? 1 : 0;
-                    mbar_expect_tx(&bars.full[s], (uint32_t)(boxes * 8192 + b_bytes));
-                    for (int h = 0; h < 2 * g.MT; ++h)
+                const int t = tb * 64;
+                mbar_expect_tx(&bars.full[s], tx);
+                if (AMN) {
+#pragma unroll
+                    for (int h = 0; h < 2 * MT; ++h)
                         if (m0 + 64 * h < g.M) tk_tma_load_3d(a + (size_t)h * 8192, &map_a, &bars.full[s], m0 + 64 * h, t, b);
                 } else {
-                    int blocks = 0;
-                    for (int mt = 0; mt < g.MT; ++mt) blocks += (m0 + 128 * mt < g.M) ? 1 : 0;
-                    mbar_expect_tx(&bars.full[s], (uint32_t)(blocks * kTkSlot + b_bytes));
-                    for (int mt = 0; mt < g.MT; ++mt)
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
                         if (m0 + 128 * mt < g.M)
                             tk_tma_load_3d(a + (size_t)mt * kTkSlot, &map_a, &bars.full[s], t, m0 + 128 * mt, b);
                 }
                 tk_tma_load_3d(a + a_bytes, &map_x, &bars.full[s], t, c0, b);
             }
+            __syncwarp();
+            if (++tb == g.kb_per_img) { tb = 0; ++b; }
+            if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t major = g.a_mn ? (1u << 15) : 0u;
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | major | ((uint32_t)(g.NB >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | major | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t ones_addr = smem_u32(ones);
-            for (int kb = kb0, i = 0; kb < kb1; ++kb, ++i) {
-                const int s = i % g.stages;
-                mbar_wait(&bars.full[s], (i / g.stages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(base + (size_t)s * stage_bytes), b_addr = a_addr + a_bytes;
+        // ===== MMA issuer
+        constexpr uint32_t major = AMN ? (1u << 15) : 0u;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | major | ((uint32_t)(g.NB >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | major | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a_lo0 = AMN ? tk_lo_mn(smem_u32(base)) : tk_lo_k(smem_u32(base));
+        const uint32_t b_lo0 = tk_lo_k(smem_u32(base + a_bytes)), o_lo = tk_lo_k(smem_u32(ones));
+        constexpr uint32_t a_k = AMN ? (2048u >> 4) : 2u;         // descriptor units per K step of 16
+        const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
+        uint32_t s = 0, ph = 0, first = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&bars.full[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tk_elect()) {
+                const uint32_t a_lo = a_lo0 + s * stage_units, b_lo = b_lo0 + s * stage_units;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint64_t bd = tk_desc_k(b_addr + k * 32), od = tk_desc_k(ones_addr + k * 32);
-                    for (int mt = 0; mt < g.MT; ++mt) {
-                        const uint64_t ad = g.a_mn ? tk_desc_mn(a_addr + mt * kTkSlot + k * 2048)
-                                                   : tk_desc_k(a_addr + mt * kTkSlot + k * 32);
-                        umma_f16(tmem_base + mt * g.NB, ad, bd, idesc, (i | k) ? 1u : 0u);
-                        umma_f16(tmem_base + ones_col + mt * 16, ad, od, idesc1, (i | k) ? 1u : 0u);
+                    const uint64_t bd = tk_desc(b_lo + 2 * k), od = tk_desc(o_lo + 2 * k);
+                    const uint32_t acc = (first | k) ? 1u : 0u;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint64_t ad = tk_desc(a_lo + mt * (kTkSlot >> 4) + k * a_k);
+                        umma_f16(tmem_base + mt * g.NB, ad, bd, idesc, acc);
+                        umma_f16(tmem_base + ones_col + mt * kRdOnesStep, ad, od, idesc1, acc);
                     }
                 }
                 umma_commit(&bars.empty[s]);
             }
-            umma_commit(&bars.acc_full);
+            __syncwarp();
+            first = 1;
+            if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1; }
         }
+        if (tk_elect()) umma_commit(&bars.acc_full);
+        __syncwarp();
     } else {
         // ===== epilogue: 4 warps, lane = row of the 128-block; fp32 partials of this split
         const int quarter = warp & 3;
@@ -372,7 +424,8 @@ tok_reduce_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        for (int mt = 0; mt < g.MT; ++mt) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
             const int m = m0 + mt * 128 + row;
             float *drow = part_d + ((size_t)split * g.M + (m < g.M ? m : 0)) * g.C + c0;
             for (int j0 = 0; j0 < g.NB; j0 += 32) {
@@ -395,7 +448,7 @@ tok_reduce_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (kb1 > kb0) {
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                                 : "r"(trow + ones_col + mt * 16));
+                                 : "r"(trow + ones_col + mt * kRdOnesStep));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 }
                 if (m < g.M) part_rs[(size_t)split * g.M + m] = __uint_as_float(r[0]);
@@ -483,23 +536,27 @@ extern "C" int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const f
     }
     PjGeom g;
     g.B = B; g.HW = HW; g.C = C; g.n_kb = C / 64;
-    g.MT = (2 * g.n_kb <= kPjASlots) ? 2 : 1;
-    if (HW <= 128) g.MT = 1;
-    g.pairs_per_img = (HW + g.MT * 128 - 1) / (g.MT * 128);
+    int MT = (2 * g.n_kb <= 8) ? 2 : 1;
+    if (HW <= 128) MT = 1;
+    g.w_stages = kPjSlots - MT * g.n_kb;
+    if (g.w_stages > kPjMaxWStages) g.w_stages = kPjMaxWStages;
+    g.pairs_per_img = (HW + MT * 128 - 1) / (MT * 128);
     g.n_pairs = B * g.pairs_per_img;
     g.N0 = N0; g.N1 = N1; g.NT = NT;
     g.n_steps = (Nall + 127) / 128;
     g.raw_row = raw_row; g.raw_img = raw_img;
-    static bool attr[64] = {false};
-    TAMTR_CHECK_ARG(tk_attr_once((const void *)tok_project_kernel, attr), TAMTR_E_NODEVICE,
+    static bool attr1[64] = {false}, attr2[64] = {false};
+    TAMTR_CHECK_ARG(tk_attr_once((const void *)tok_project_kernel<1>, attr1) &&
+                    tk_attr_once((const void *)tok_project_kernel<2>, attr2), TAMTR_E_NODEVICE,
                     "tok_project: cannot raise the dynamic shared memory limit");
-    const size_t smem = (size_t)(kPjASlots + kPjWStages + 2) * kTkSlot + sizeof(PjBars) + 1024;
+    const size_t smem = (size_t)(kPjSlots + 2) * kTkSlot + sizeof(PjBars) + 1024;
     const int n_sm = ::tamtr::sm_count();
     const int grid = g.n_pairs < n_sm ? g.n_pairs : n_sm;
     cudaStream_t st = (cudaStream_t)stream;
     {
         KernelTimer timer(K_TOK_PROJECT, st);
-        tok_project_kernel<<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, bias, raw, g);
+        if (MT == 2) tok_project_kernel<2><<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, bias, raw, g);
+        else tok_project_kernel<1><<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, bias, raw, g);
     }
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
@@ -522,7 +579,7 @@ static int rd_geometry(RdGeom &g, int B, int C, int HW, int M, int a_mn) {
     const int stage_bytes = g.MT * kTkSlot + g.NB * 128;
     g.stages = (200 * 1024) / stage_bytes;
     if (g.stages > 4) g.stages = 4;
-    const int cols = g.MT * g.NB + g.MT * 16;
+    const int cols = g.MT * g.NB + g.MT * (int)kRdOnesStep;
     g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     return 0;
 }
@@ -574,15 +631,22 @@ extern "C" int tamtr_tok_reduce(const void *a_bf16, long a_row, long a_img, int 
         const int rc = tk_encode(&map_x, x_bf16, 3, dims, strides, box, "tok_reduce(x)");
         if (rc) return rc;
     }
-    static bool attr[64] = {false};
-    TAMTR_CHECK_ARG(tk_attr_once((const void *)tok_reduce_kernel, attr), TAMTR_E_NODEVICE,
+    static bool attr[4][64] = {{false}};
+    TAMTR_CHECK_ARG(tk_attr_once((const void *)tok_reduce_kernel<1, false>, attr[0]) &&
+                    tk_attr_once((const void *)tok_reduce_kernel<2, false>, attr[1]) &&
+                    tk_attr_once((const void *)tok_reduce_kernel<1, true>, attr[2]) &&
+                    tk_attr_once((const void *)tok_reduce_kernel<2, true>, attr[3]), TAMTR_E_NODEVICE,
                     "tok_reduce: cannot raise the dynamic shared memory limit");
     const size_t smem = (size_t)g.stages * (g.MT * kTkSlot + g.NB * 128) + 2048 + sizeof(RdBars) + 1024;
     const int groups = ((M + g.MT * 128 - 1) / (g.MT * 128)) * g.n_cchunks;
     cudaStream_t st = (cudaStream_t)stream;
     {
         KernelTimer timer(K_TOK_REDUCE, st);
-        tok_reduce_kernel<<<dim3(groups, g.splits), 64 + 128, smem, st>>>(map_a, map_x, part_d, part_rs, g);
+        const dim3 grid(groups, g.splits);
+        if (g.MT == 2 && a_token_major) tok_reduce_kernel<2, true><<<grid, 64 + 128, smem, st>>>(map_a, map_x, part_d, part_rs, g);
+        else if (g.MT == 2) tok_reduce_kernel<2, false><<<grid, 64 + 128, smem, st>>>(map_a, map_x, part_d, part_rs, g);
+        else if (a_token_major) tok_reduce_kernel<1, true><<<grid, 64 + 128, smem, st>>>(map_a, map_x, part_d, part_rs, g);
+        else tok_reduce_kernel<1, false><<<grid, 64 + 128, smem, st>>>(map_a, map_x, part_d, part_rs, g);
     }
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());

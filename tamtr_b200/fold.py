@@ -124,6 +124,47 @@ def _moments(x):
     return S1, G
 
 
+class _FoldMatmulFn(torch.autograd.Function):
+    """W [N, d] @ A [L, d, K] -> [L, N, K] for the folded weights, forward and backward on the TF32 tensor-core path when
+    the operands are fp32 CUDA tensors: the products are rounded to bf16 right after (they are the projection kernel's
+    weight operand), and their gradients feed parameters whose reference gradients come out of bf16 GEMMs, so 10 mantissa
+    bits in the multiplications lose nothing -- while the fp32 SIMT GEMMs cost 0.4 ms per step at TAM-TR shapes."""
+
+    @staticmethod
+    def _mm(a, b):
+        if not (a.is_cuda and a.dtype == torch.float32):
+            return torch.matmul(a, b)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            return torch.matmul(a, b)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+
+    @staticmethod
+    def forward(ctx, W, A):
+        ctx.save_for_backward(W, A)
+        return _FoldMatmulFn._mm(W, A)
+
+    @staticmethod
+    def backward(ctx, g):
+        W, A = ctx.saved_tensors
+        dW = dA = None
+        if ctx.needs_input_grad[0]:
+            L, N, K = g.shape
+            # sum over levels of g_l @ A_l^T as one product over the concatenated (level, column) axis
+            dW = _FoldMatmulFn._mm(g.permute(1, 0, 2).reshape(N, L * K), A.permute(0, 2, 1).reshape(L * K, -1))
+        if ctx.needs_input_grad[1]:
+            dA = _FoldMatmulFn._mm(W.t(), g)
+        return dW, dA
+
+
+def _fold_matmul(W, A):
+    if torch.is_grad_enabled() and (W.requires_grad or A.requires_grad):
+        return _FoldMatmulFn.apply(W, A)
+    return _FoldMatmulFn._mm(W, A)
+
+
 def _pad_cols(t, width):
     return t if t.shape[-1] == width else F.pad(t, (0, width - t.shape[-1]))
 
@@ -246,16 +287,18 @@ class FoldedTokens:
         if any(batch_stats) and not all(batch_stats):
             raise RuntimeError("tamtr_b200: input_proj BatchNorm layers must agree on track_running_stats")
         if batch_stats[0]:
-            S1s, Gs = [], []
-            for x, C in zip(self.xs, self.cs):
+            # per level, unpadded and in full fp32: var = diag(Wc Cov Wc^T) is a difference of large terms
+            mus, vars_ = [], []
+            for l, (x, C) in enumerate(zip(self.xs, self.cs)):
                 S1, G = _moments(x)
                 n_tok = float(x.shape[0] * x.shape[2] * x.shape[3])
-                S1s.append(_pad_cols(S1.to(md), Cm) / n_tok)
-                Gs.append(F.pad(G.to(md), (0, Cm - C, 0, Cm - C)) / n_tok)
-            mean_x = torch.stack(S1s)
-            cov = torch.stack(Gs) - mean_x.unsqueeze(2) * mean_x.unsqueeze(1)
-            mu = torch.bmm(Wc, mean_x.unsqueeze(-1)).squeeze(-1)
-            var = (torch.bmm(Wc, cov) * Wc).sum(-1).clamp_min(0)
+                mean_x = S1.to(md) / n_tok
+                cov = torch.addcmul(G.to(md) / n_tok, mean_x.unsqueeze(1), mean_x.unsqueeze(0), value=-1.0)
+                w = Wc[l, :, :C]
+                mus.append(w @ mean_x)
+                vars_.append(((w @ cov) * w).sum(-1))
+            mu = torch.stack(mus)
+            var = torch.stack(vars_).clamp_min(0)
             if training:
                 with torch.no_grad():
                     for l, b in enumerate(bns):
@@ -282,10 +325,10 @@ class FoldedTokens:
             Wv = torch.cat([a.value_proj.weight for a in attns], 0).to(md)                          # [N0, d]
             bv = torch.cat([a.value_proj.bias for a in attns], 0)
             Aext = torch.cat([self.A, self.t.unsqueeze(-1)], -1)                                    # [L, d, Cm + 1]
-            Fv = torch.matmul(Wv, Aext)
+            Fv = _fold_matmul(Wv, Aext)
             with torch.no_grad():
                 rk = _rank_constants(enc_linear, enc_norm, score_linear, md)
-                Fe = torch.matmul(torch.cat([enc_linear.weight.to(md), rk["Wr"]], 0), Aext.detach())
+                Fe = _fold_matmul(torch.cat([enc_linear.weight.to(md), rk["Wr"]], 0), Aext.detach())
             self.rank_consts = rk
             self.arena = ops.ValueArena()
             if torch.is_grad_enabled() and (Fv.requires_grad or bv.requires_grad or any(x.requires_grad for x in self.xs)):

@@ -74,7 +74,7 @@ def test_tok_reduce_weight_gradient(cuda_lib, B, C, H, W, M):
     assert rel_l2(rs, A.sum((0, 1))) < 1e-5
 
 
-def _head(B=2, sizes=(40, 20, 10)):
+def _head(B=2, sizes=(48, 24, 12)):
     from tamtr_b200.head import ManbaWorldDecoder
     torch.manual_seed(0)
     m = ManbaWorldDecoder(10, [128, 256, 512], 512, 100, 4, 8, 3, vss=False).cuda().train()
@@ -82,6 +82,7 @@ def _head(B=2, sizes=(40, 20, 10)):
     xs = [seeding.seeded_smooth_map(5, f"x{i}", (B, c, s, s)).bfloat16().cuda()
           for i, (c, s) in enumerate(zip((128, 256, 512), sizes))]
     text = torch.nn.functional.normalize(seeding.seeded_tensor(5, "t", (B, 10, 512)), dim=-1).cuda()
+    m.num_denoising = 0                  # no ground truth in these tests: matching queries only
     return m, xs, text
 
 
@@ -111,11 +112,11 @@ def test_folded_encoder_matches_unfolded(cuda_lib):
         assert int(p[1].num_batches_tracked) == int(r[1].num_batches_tracked) == 1
 
 
-def _step(m, xs, text, seed=3):
+def _step(m, xs, text, seed=3, autocast=True):
     for p in m.parameters():
         p.grad = None
     torch.manual_seed(seed)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
         out = m(xs, text)
     if not m.training:
         out = out[1]
@@ -148,10 +149,15 @@ def test_folded_head_step_matches_unfolded(cuda_lib, train):
     flat_f = torch.cat([g_f[k].reshape(-1) for k in sorted(g_f)])
     flat_u = torch.cat([g_u[k].reshape(-1) for k in sorted(g_u)])
     assert rel_l2(flat_f, flat_u) < 5e-2
+    # per tensor, both bf16 paths are judged against the SAME fp32 run of the unfolded kernels: the folded path (one
+    # rounding less: Y and M are never rounded to bf16) must not be further from it than the unfolded bf16 path is
+    ref32 = copy.deepcopy(ref).float()
+    _, g_32 = _step(ref32, [x.float() for x in xs], text, autocast=False)
     for k in ("input_proj.0.0.weight", "input_proj.2.1.weight", "input_proj.1.1.bias",
               "decoder.layers.0.cross_attn.value_proj.weight", "decoder.layers.2.cross_attn.value_proj.bias",
               "enc_output.0.weight"):
-        assert rel_l2(g_f[k], g_u[k]) < 6e-2, (k, rel_l2(g_f[k], g_u[k]))
+        e_f, e_u = rel_l2(g_f[k], g_32[k]), rel_l2(g_u[k], g_32[k])
+        assert e_f < max(1.25 * e_u, 3e-2), (k, e_f, e_u)
 
 
 def test_folded_head_inference_matches_unfolded(cuda_lib):
