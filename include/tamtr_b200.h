@@ -460,6 +460,17 @@ int tamtr_tok_project_supported(int B, int C, int HW, int N0, int N1, int NT);
 int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row, long out0_img,
                       void *out1, long out1_row, long out1_img, float *raw, long raw_row, long raw_img, int B, int C, int HW,
                       int N0, int N1, int NT, void *stream);
+/* tamtr_tok_project with the query-selection ranking (head.py:1229-1237) finished in its epilogue: the N1 = d columns are
+ * E = enc_output.0(feats) without its bias, the NT tail columns are E @ (enc_score_head.weight * ln.weight)^T for the nc
+ * classes (columns [0, nc)) and E . enc_bias (column NT - 1); neither is stored.  Per token:
+ *   (mean, rstd) = LayerNorm statistics of E + enc_bias over d, from sum E, sum E^2 and E . enc_bias
+ *   rank[b, tok] = max_k rstd * (tail[k] + bw[k] - mean * sw[k]) + ck[k]     (E and the tail count as 0 where valid[tok] == 0)
+ *   rank_consts = { sum enc_bias, sum enc_bias^2, bw[NT], sw[NT], ck[NT] } f32 (the constants of tamtr_rank_tokens)
+ *   rank f32: element (b, tok) at rank + b * rank_img + tok; valid u8 [HW] (the level's slice of the anchor validity mask)
+ * nc < NT <= 64. */
+int tamtr_tok_project_rank(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row,
+                           long out0_img, float *rank, long rank_img, const uint8_t *valid, const float *rank_consts, int nc,
+                           float eps, int B, int C, int HW, int N0, int N1, int NT, void *stream);
 int tamtr_tok_reduce_supported(int B, int C, int HW, int M, int a_token_major);
 int tamtr_tok_reduce_splits(int B, int C, int HW, int M, int a_token_major);
 int tamtr_tok_reduce(const void *a_bf16, long a_row, long a_img, int a_token_major, const void *x_bf16, float *part_d,

@@ -89,6 +89,7 @@ _SIGNATURES = {
                          + [ctypes.c_float] * 6 + [_vp]),
     "tamtr_tok_project_supported": (ctypes.c_int, [_i] * 6),
     "tamtr_tok_project": (ctypes.c_int, [_vp, _vp, _fp, _vp, _l, _l, _vp, _l, _l, _fp, _l, _l] + [_i] * 6 + [_vp]),
+    "tamtr_tok_project_rank": (ctypes.c_int, [_vp, _vp, _fp, _vp, _l, _l, _fp, _l, _vp, _fp, _i, ctypes.c_float] + [_i] * 6 + [_vp]),
     "tamtr_tok_reduce_supported": (ctypes.c_int, [_i] * 5),
     "tamtr_tok_reduce_splits": (ctypes.c_int, [_i] * 5),
     "tamtr_tok_reduce": (ctypes.c_int, [_vp, _l, _l, _i, _vp, _fp, _fp] + [_i] * 4 + [_vp]),

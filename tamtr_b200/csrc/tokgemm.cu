@@ -102,21 +102,31 @@ struct PjGeom {
     int pairs_per_img, n_pairs;    // CTA tiles of MT * 128 tokens
     int N0, N1, NT, n_steps;       // bf16 columns of out0 / out1, fp32 tail columns, ceil((N0 + N1 + NT) / 128)
     long raw_row, raw_img;         // strides (elements) of the fp32 tail tensor
+    // ranking mode (rank_mode = 1): the N1 columns are the ranking embedding E and the tail its class scores; neither is
+    // stored -- the epilogue reduces them to one score per token (see tok_project_kernel)
+    int rank_mode, nc;
+    long rank_img;
+    float eps, inv_d;
 };
 
 template <int MT>
 __global__ void __launch_bounds__(kTkThreads, 1)
 tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                    const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
-                   const float *__restrict__ bias, float *__restrict__ raw, const PjGeom g) {
+                   const float *__restrict__ bias, float *__restrict__ raw, const uint8_t *__restrict__ valid,
+                   const float *__restrict__ rconst, float *__restrict__ rank_out, const PjGeom g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sA = base;                                         // [MT][n_kb] slots of 16 KB
     uint8_t *sW = base + (size_t)MT * g.n_kb * kTkSlot;         // [w_stages] 16 KB
     uint8_t *sO = base + (size_t)kPjSlots * kTkSlot;            // [2] 16 KB staging tiles (one per epilogue group)
     PjBars &bars = *reinterpret_cast<PjBars *>(sO + 2 * kTkSlot);
+    float *s_rc = reinterpret_cast<float *>(sO + 2 * kTkSlot + 256);       // ranking constants: 2 + 3 * NT floats
+    float2 *s_part = reinterpret_cast<float2 *>(s_rc + 2 + 3 * 64);        // MT == 1: partial row moments of the other group
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    if (g.rank_mode)
+        for (int i = threadIdx.x; i < 2 + 3 * g.NT; i += kTkThreads) s_rc[i] = __ldg(rconst + i);
     if (threadIdx.x == 0) {
         mbar_init(&bars.a_full, 1);
         mbar_init(&bars.a_empty, 1);
@@ -221,9 +231,13 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int mt = MT == 2 ? grp : 0;
         const int chunk0 = MT == 2 ? 0 : grp, n_chunks = MT == 2 ? 2 : 1;
         const int Nmain = g.N0 + g.N1, Nall = Nmain + g.NT;
+        // ranking mode: where the tail sits (NT <= 64: one chunk), and -- MT == 1, where two threads share a token's columns --
+        // which group finishes the token
+        const int n_tail = Nmain >> 7, tail_grp = (Nmain >> 6) & 1;
         uint32_t ai = 0;
         for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x) {
             const int b = p / g.pairs_per_img, tok0 = (p - b * g.pairs_per_img) * tile_tok + mt * 128;
+            float s1 = 0.f, s2 = 0.f;                                        // sum / sum of squares of the token's E row
             for (int n = 0; n < g.n_steps; ++n, ++ai) {
                 const uint32_t as = ai & 1;
                 mbar_wait(&bars.acc_full[as], (ai >> 1) & 1);
@@ -233,9 +247,46 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     const int chunk = chunk0 + ci, col0 = n * 128 + chunk * 64;
                     if (col0 >= Nall || tok0 >= g.HW) continue;              // uniform over the group
                     if (col0 >= Nmain) {
-                        // fp32 tail (ranking scores): direct stores of the chunk's share of the NT columns
-                        uint32_t v[32];
                         const int tok = tok0 + row, toff = col0 - Nmain;
+                        uint32_t v[32];
+                        if (g.rank_mode) {
+                            // ===== ranking score of the token (head.py:1229-1237): LayerNorm statistics of E + enc bias from
+                            // (sum E, sum E^2, E . enc_bias), folded with the class scores of the tail columns
+                            if (MT == 1) {
+                                asm volatile("bar.sync 3, 256;" ::: "memory");      // the other group's partial moments
+                                const float2 o = s_part[row];
+                                s1 += o.x; s2 += o.y;
+                            }
+                            const bool ok = tok < g.HW && __ldg(valid + (tok < g.HW ? tok : 0)) != 0;
+                            float best = -INFINITY, dot = 0.f, mean = 0.f, rstd = 0.f;
+                            // the dot product sits in the LAST tail column: read its 32-column piece first
+                            const int last = g.NT - 1;
+                            tk_tmem_ld32(taddr + chunk * 64 + (last & ~31), v);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j == (last & 31)) dot = __uint_as_float(v[j]) + __ldg(bias + Nmain + last);
+                            if (!ok) { s1 = 0.f; s2 = 0.f; dot = 0.f; }
+                            mean = (s1 + s_rc[0]) * g.inv_d;
+                            rstd = rsqrtf(fmaxf((s2 + 2.f * dot + s_rc[1]) * g.inv_d - mean * mean, 0.f) + g.eps);
+                            const float *bw = s_rc + 2, *sw_ = bw + g.NT, *ck = sw_ + g.NT;
+                            int loaded = last >> 5;                          // which 32-column piece v holds
+                            for (int h = 0; h * 32 < g.nc; ++h) {
+                                if (h != loaded) { tk_tmem_ld32(taddr + chunk * 64 + h * 32, v); loaded = h; }
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const int k = h * 32 + j;
+                                    if (k < g.nc) {
+                                        const float r = ok ? __uint_as_float(v[j]) + __ldg(bias + Nmain + k) : 0.f;
+                                        best = fmaxf(best, rstd * (r + bw[k] - mean * sw_[k]) + ck[k]);
+                                    }
+                                }
+                            }
+                            if (tok < g.HW) rank_out[(size_t)b * g.rank_img + tok] = best;
+                            if (MT == 1) asm volatile("bar.sync 3, 256;" ::: "memory");     // partials consumed
+                            (void)toff;
+                            continue;
+                        }
+                        // fp32 tail stored as it is: direct stores of the chunk's share of the NT columns
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int cb = toff + h * 32;
@@ -252,6 +303,23 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                                                         __uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w);
                                     }
                                 }
+                            }
+                        }
+                        continue;
+                    }
+                    if (g.rank_mode && col0 >= g.N0) {
+                        // ===== ranking embedding: only its row moments are needed
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t v[32];
+                            tk_tmem_ld32(taddr + chunk * 64 + h * 32, v);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + col0 + h * 32 + j));
+                                const float e0 = __uint_as_float(v[j]) + b4.x, e1 = __uint_as_float(v[j + 1]) + b4.y;
+                                const float e2 = __uint_as_float(v[j + 2]) + b4.z, e3 = __uint_as_float(v[j + 3]) + b4.w;
+                                s1 += (e0 + e1) + (e2 + e3);
+                                s2 = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, s2))));
                             }
                         }
                         continue;
@@ -280,6 +348,12 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         if (col0 < g.N0) tk_tma_store_3d(&map_o0, stage, col0, tok0, b);
                         else tk_tma_store_3d(&map_o1, stage, col0 - g.N0, tok0, b);
                     }
+                }
+                if (MT == 1 && g.rank_mode && n == n_tail && grp != tail_grp) {
+                    // this group's share of the token's moments -> the group that owns the tail chunk
+                    s_part[row] = make_float2(s1, s2);
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
                 }
                 // every TMEM read of this accumulator stage by this warp is complete (tcgen05.wait::ld in tk_tmem_ld32)
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -495,15 +569,29 @@ extern "C" int tamtr_tok_project_supported(int B, int C, int HW, int N0, int N1,
     return 1;
 }
 
-extern "C" int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row,
-                                 long out0_img, void *out1, long out1_row, long out1_img, float *raw, long raw_row,
-                                 long raw_img, int B, int C, int HW, int N0, int N1, int NT, void *stream) {
+struct PjRank {                  // ranking mode (tamtr_tok_project_rank)
+    float *rank;
+    long rank_img;
+    const uint8_t *valid;
+    const float *consts;
+    int nc;
+    float eps;
+};
+
+static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row,
+                            long out0_img, void *out1, long out1_row, long out1_img, float *raw, long raw_row,
+                            long raw_img, const PjRank *rk, int B, int C, int HW, int N0, int N1, int NT, void *stream) {
     TAMTR_CHECK_ARG(x_bf16 && w_bf16 && bias && out0, TAMTR_E_BADARG, "tok_project: null pointer");
     TAMTR_CHECK_ARG(tamtr_tok_project_supported(B, C, HW, N0, N1, NT), TAMTR_E_UNSUPPORTED,
                     "tok_project: unsupported problem (B=%d C=%d HW=%d N0=%d N1=%d NT=%d): need C %% 64 == 0, C <= 512, "
                     "HW %% 8 == 0, N0 %% 64 == 0, N1 %% 64 == 0, NT %% 4 == 0, NT <= 1024", B, C, HW, N0, N1, NT);
-    TAMTR_CHECK_ARG((N1 == 0 || out1 != nullptr) && (NT == 0 || raw != nullptr), TAMTR_E_BADARG,
+    TAMTR_CHECK_ARG(rk != nullptr || ((N1 == 0 || out1 != nullptr) && (NT == 0 || raw != nullptr)), TAMTR_E_BADARG,
                     "tok_project: missing output tensor");
+    if (rk != nullptr) {
+        TAMTR_CHECK_ARG(rk->rank && rk->valid && rk->consts, TAMTR_E_BADARG, "tok_project_rank: null pointer");
+        TAMTR_CHECK_ARG(N1 > 0 && NT >= 16 && NT <= 64 && rk->nc > 0 && rk->nc < NT, TAMTR_E_UNSUPPORTED,
+                        "tok_project_rank: need N1 > 0 and nc < NT <= 64 (nc = %d, NT = %d)", rk->nc, NT);
+    }
     TAMTR_CHECK_ARG((((uintptr_t)x_bf16 | (uintptr_t)w_bf16 | (uintptr_t)bias | (uintptr_t)out0 | (uintptr_t)out1 |
                       (uintptr_t)raw) & 15) == 0, TAMTR_E_BADARG, "tok_project: pointers must be 16-byte aligned");
     TAMTR_CHECK_ARG(out0_row % 8 == 0 && out0_img % 8 == 0 && out1_row % 8 == 0 && out1_img % 8 == 0 && raw_row % 4 == 0 &&
@@ -525,7 +613,7 @@ extern "C" int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const f
         if (rc) return rc;
     }
     for (int which = 0; which < 2; ++which) {
-        const bool live = which == 0 || N1 > 0;
+        const bool live = which == 0 || (N1 > 0 && rk == nullptr);
         const cuuint64_t dims[3] = {(cuuint64_t)(which == 0 ? N0 : (live ? N1 : N0)), (cuuint64_t)HW, (cuuint64_t)B};
         const long row = which == 0 || !live ? out0_row : out1_row, img = which == 0 || !live ? out0_img : out1_img;
         const cuuint64_t strides[2] = {(cuuint64_t)row * 2, (cuuint64_t)img * 2};
@@ -545,22 +633,48 @@ extern "C" int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const f
     g.N0 = N0; g.N1 = N1; g.NT = NT;
     g.n_steps = (Nall + 127) / 128;
     g.raw_row = raw_row; g.raw_img = raw_img;
+    g.rank_mode = rk != nullptr ? 1 : 0;
+    g.nc = rk != nullptr ? rk->nc : 0;
+    g.rank_img = rk != nullptr ? rk->rank_img : 0;
+    g.eps = rk != nullptr ? rk->eps : 0.f;
+    g.inv_d = N1 > 0 ? 1.0f / (float)N1 : 0.f;
+    const uint8_t *valid = rk != nullptr ? rk->valid : nullptr;
+    const float *rconst = rk != nullptr ? rk->consts : nullptr;
+    float *rank_out = rk != nullptr ? rk->rank : nullptr;
     static bool attr1[64] = {false}, attr2[64] = {false};
     TAMTR_CHECK_ARG(tk_attr_once((const void *)tok_project_kernel<1>, attr1) &&
                     tk_attr_once((const void *)tok_project_kernel<2>, attr2), TAMTR_E_NODEVICE,
                     "tok_project: cannot raise the dynamic shared memory limit");
-    const size_t smem = (size_t)(kPjSlots + 2) * kTkSlot + sizeof(PjBars) + 1024;
+    const size_t smem = (size_t)(kPjSlots + 2) * kTkSlot + 4096 + 1024;      // slots, barriers + ranking scratch, alignment
     const int n_sm = ::tamtr::sm_count();
     const int grid = g.n_pairs < n_sm ? g.n_pairs : n_sm;
     cudaStream_t st = (cudaStream_t)stream;
     {
         KernelTimer timer(K_TOK_PROJECT, st);
-        if (MT == 2) tok_project_kernel<2><<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, bias, raw, g);
-        else tok_project_kernel<1><<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, bias, raw, g);
+        if (MT == 2)
+            tok_project_kernel<2><<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, bias, raw, valid, rconst, rank_out, g);
+        else
+            tok_project_kernel<1><<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, bias, raw, valid, rconst, rank_out, g);
     }
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row,
+                                 long out0_img, void *out1, long out1_row, long out1_img, float *raw, long raw_row,
+                                 long raw_img, int B, int C, int HW, int N0, int N1, int NT, void *stream) {
+    return tok_project_impl(x_bf16, w_bf16, bias, out0, out0_row, out0_img, out1, out1_row, out1_img, raw, raw_row, raw_img,
+                            nullptr, B, C, HW, N0, N1, NT, stream);
+}
+
+extern "C" int tamtr_tok_project_rank(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row,
+                                      long out0_img, float *rank, long rank_img, const uint8_t *valid,
+                                      const float *rank_consts, int nc, float eps, int B, int C, int HW, int N0, int N1,
+                                      int NT, void *stream) {
+    const PjRank rk = {rank, rank_img, valid, rank_consts, nc, eps};
+    return tok_project_impl(x_bf16, w_bf16, bias, out0, out0_row, out0_img, nullptr, 0, 0, nullptr, 0, 0, &rk, B, C, HW, N0, N1,
+                            NT, stream);
 }
 
 static int rd_geometry(RdGeom &g, int B, int C, int HW, int M, int a_mn) {

@@ -60,8 +60,10 @@ def _kernel_reduce(a, a_row, a_img, token_major, x, M):
     return part_d.sum(0), part_rs.sum(0)
 
 
-def _kernel_project(x, w, bias, out0, out1, raw, start, N0, N1, NT):
-    """out0[:, start:start+HW] / out1[...] / raw[...] = x^T w^T + bias, column ranges [0,N0) / [N0,N0+N1) / the rest."""
+def _kernel_project(x, w, bias, out0, out1, raw, start, N0, N1, NT, rank=None):
+    """out0[:, start:start+HW] = x^T w[:N0]^T + bias[:N0] (bf16).  The N1 + NT remaining columns are the ranking branch:
+    stored (out1 bf16, raw fp32) when `rank` is None, else reduced in the kernel's epilogue to one score per token,
+    rank = (scores [B, Lv] fp32, valid_u8 [Lv], consts, nc, eps)  (tamtr_tok_project / tamtr_tok_project_rank)."""
     _lib.require_cuda(x, w, bias, out0)
     if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or bias.dtype != torch.float32:
         raise RuntimeError("tamtr_b200: tok_project takes bf16 operands and an fp32 bias")
@@ -70,12 +72,19 @@ def _kernel_project(x, w, bias, out0, out1, raw, start, N0, N1, NT):
     Lv = out0.shape[1]
     es0 = out0.element_size()
     with torch.cuda.device(x.device):
-        rc = _lib.lib().tamtr_tok_project(
-            x.data_ptr(), w.data_ptr(), bias.data_ptr(),
-            out0.data_ptr() + start * N0 * es0, N0, Lv * N0,
-            (out1.data_ptr() + start * N1 * out1.element_size()) if N1 else None, N1, Lv * N1,
-            (raw.data_ptr() + start * NT * 4) if NT else None, NT, Lv * NT,
-            B, C, HW, N0, N1, NT, _lib.stream_ptr(x.device))
+        if rank is None:
+            rc = _lib.lib().tamtr_tok_project(
+                x.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                out0.data_ptr() + start * N0 * es0, N0, Lv * N0,
+                (out1.data_ptr() + start * N1 * out1.element_size()) if N1 else None, N1, Lv * N1,
+                (raw.data_ptr() + start * NT * 4) if NT else None, NT, Lv * NT,
+                B, C, HW, N0, N1, NT, _lib.stream_ptr(x.device))
+        else:
+            scores, valid_u8, consts, nc, eps = rank
+            rc = _lib.lib().tamtr_tok_project_rank(
+                x.data_ptr(), w.data_ptr(), bias.data_ptr(), out0.data_ptr() + start * N0 * es0, N0, Lv * N0,
+                scores.data_ptr() + start * 4, Lv, valid_u8.data_ptr() + start, consts.data_ptr(), int(nc), float(eps),
+                B, C, HW, N0, N1, NT, _lib.stream_ptr(x.device))
     _lib.check(rc, "tok_project")
 
 
@@ -191,15 +200,23 @@ class _TokProjectFn(torch.autograd.Function):
         bias = bias.to(acc).contiguous()
         Wb = W[:, :, :Cm].to(lp)
         value_all = torch.empty(B, Lv, N0, dtype=lp, device=dev)
-        E = torch.empty(B, Lv, N1, dtype=lp, device=dev)
-        raw = torch.empty(B * Lv, NT, dtype=acc, device=dev)
+        rk = tokens.rank_consts
+        if rk["fused"]:        # ranking finished in the projection's epilogue: E and the class scores are never stored
+            E = raw = None
+            scores = torch.empty(B, Lv, dtype=acc, device=dev)
+            rank = (scores, tokens.valid_u8, rk["consts"], rk["nc"], rk["eps"])
+        else:
+            E = torch.empty(B, Lv, N1, dtype=lp, device=dev)
+            raw = torch.empty(B * Lv, NT, dtype=acc, device=dev)
+            scores = rank = None
         wl = []
         for l, x in enumerate(xs):
             C = x.shape[1]
             w = Wb[l, :, :C].contiguous()
-            _kernel_project(x, w, bias[l], value_all, E, raw.view(B, Lv, NT), tokens.starts[l], N0, N1, NT)
+            _kernel_project(x, w, bias[l], value_all, E, None if raw is None else raw.view(B, Lv, NT), tokens.starts[l],
+                            N0, N1, NT, rank)
             wl.append(w[:N0])
-        tokens.E, tokens.raw = E, raw
+        tokens.E, tokens.raw, tokens.scores = E, raw, scores
         d = N0 // n_layers
         ctx.save_for_backward(*xs, *wl)
         ctx.arena, ctx.n, ctx.d, ctx.L, ctx.Cm = arena, n_layers, d, L, Cm
@@ -268,7 +285,7 @@ class FoldedTokens:
         self.d = projs[0][0].weight.shape[0]
         self.shape = (self.B, self.Lv, self.d)
         self.is_cuda = xs[0].is_cuda
-        self.values = self.arena = self.E = self.raw = None
+        self.values = self.arena = self.E = self.raw = self.scores = self.valid_u8 = None
         with torch.autocast(self.device.type, enabled=False):
             self.A, self.t = self._coefficients(projs, training)        # [L, d, Cm] (zero beyond C_l), [L, d]
         self.requires_grad = self.A.requires_grad
@@ -318,8 +335,11 @@ class FoldedTokens:
         return s.unsqueeze(-1) * Wc, t
 
     # --- dense side: values of every decoder layer, ranking embedding and scores, one kernel per level
-    def project(self, attns, enc_linear, enc_norm, score_linear):
+    def project(self, attns, enc_linear, enc_norm, score_linear, valid_u8=None):
+        """`valid_u8` [Lv]: the anchors' validity mask (head.py:1200); with it (and at most 62 classes) the ranking scores
+        come straight out of the projection kernel, otherwise rank() runs tamtr_rank_tokens on the stored E / scores."""
         md = MATH_DTYPE
+        self.valid_u8 = valid_u8
         n_layers, n_heads = len(attns), attns[0].n_heads
         with torch.autocast(self.device.type, enabled=False):
             Wv = torch.cat([a.value_proj.weight for a in attns], 0).to(md)                          # [N0, d]
@@ -327,7 +347,7 @@ class FoldedTokens:
             Aext = torch.cat([self.A, self.t.unsqueeze(-1)], -1)                                    # [L, d, Cm + 1]
             Fv = _fold_matmul(Wv, Aext)
             with torch.no_grad():
-                rk = _rank_constants(enc_linear, enc_norm, score_linear, md)
+                rk = _rank_constants(enc_linear, enc_norm, score_linear, md, fused=valid_u8 is not None)
                 Fe = _fold_matmul(torch.cat([enc_linear.weight.to(md), rk["Wr"]], 0), Aext.detach())
             self.rank_consts = rk
             self.arena = ops.ValueArena()
@@ -342,6 +362,10 @@ class FoldedTokens:
 
     def rank(self, valid_u8):
         """max over classes of enc_score_head(LayerNorm(enc_output.0(valid * feats))) for every token -> [B, Lv] fp32."""
+        if self.scores is not None:
+            if valid_u8 is not self.valid_u8 and valid_u8.data_ptr() != self.valid_u8.data_ptr():
+                raise RuntimeError("tamtr_b200: FoldedTokens.rank() called with another validity mask than project()")
+            return self.scores
         rk = self.rank_consts
         out = torch.empty(self.B, self.Lv, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
@@ -381,15 +405,28 @@ class _NoCtx:
         pass
 
 
-def _rank_constants(enc_linear, enc_norm, score_linear, md):
-    """Constants of tamtr_rank_tokens (include/tamtr_b200.h): the score head folded with the LayerNorm weight."""
+def _rank_constants(enc_linear, enc_norm, score_linear, md, fused=False):
+    """Constants of the ranking (include/tamtr_b200.h, tamtr_rank_tokens / tamtr_tok_project_rank): the score head folded
+    with the LayerNorm weight.  Wr [npad, d]: rows of the projection's tail -- class k < nc: (score.weight * ln.weight)[k] @
+    enc_output.0.weight; fused mode: the last row is enc_bias @ enc_output.0.weight (E . enc_bias, for the statistics)."""
     Wp = score_linear.weight.to(md) * enc_norm.weight.to(md)                                        # [nc, d]
     nc, d = Wp.shape
-    npad = (nc + 15) // 16 * 16
+    fused = fused and nc + 1 <= 64
+    npad = (nc + (1 if fused else 0) + 15) // 16 * 16
+    We, eb = enc_linear.weight.to(md), enc_linear.bias.to(md)
     Wpad = torch.zeros(npad, d, dtype=md, device=Wp.device)
     Wpad[:nc] = Wp
-    eb = enc_linear.bias.to(md)
-    return {"Wr": Wpad @ enc_linear.weight.to(md), "eb": eb.float().contiguous(), "bw": (Wp @ eb).float().contiguous(),
-            "sw": Wp.sum(1).float().contiguous(),
-            "ck": (score_linear.weight.to(md) @ enc_norm.bias.to(md) + score_linear.bias.to(md)).float().contiguous(),
-            "nc": nc, "npad": npad, "eps": enc_norm.eps}
+    Wr = Wpad @ We
+    bw, sw = Wp @ eb, Wp.sum(1)
+    ck = score_linear.weight.to(md) @ enc_norm.bias.to(md) + score_linear.bias.to(md)
+    out = {"Wr": Wr, "nc": nc, "npad": npad, "eps": enc_norm.eps, "fused": fused}
+    if fused:
+        Wr[npad - 1] = eb @ We
+        consts = torch.zeros(2 + 3 * npad, dtype=md, device=Wp.device)
+        consts[0], consts[1] = eb.sum(), (eb * eb).sum()
+        consts[2:2 + nc], consts[2 + npad:2 + npad + nc], consts[2 + 2 * npad:2 + 2 * npad + nc] = bw, sw, ck
+        out["consts"] = (consts if md != torch.float32 else consts.float()).contiguous()
+    else:
+        out.update({"eb": eb.float().contiguous(), "bw": bw.float().contiguous(), "sw": sw.float().contiguous(),
+                    "ck": ck.float().contiguous()})
+    return out

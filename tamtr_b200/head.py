@@ -316,7 +316,7 @@ class _HeadBase(nn.Module):
         if not all(is_plain_msda(a) for a in attns) or any(a.n_heads != attns[0].n_heads for a in attns):
             return None
         d = self.hidden_dim
-        n_tail = (self.enc_score_head.weight.shape[0] + 15) // 16 * 16
+        n_tail = (self.enc_score_head.weight.shape[0] + 1 + 15) // 16 * 16
         if not (isinstance(self.enc_output, nn.Sequential) and isinstance(self.enc_output[0], nn.Linear)
                 and isinstance(self.enc_output[1], nn.LayerNorm) and isinstance(self.enc_score_head, nn.Linear)
                 and d <= 4 * 32 * 8 and all(a.value_proj.weight.shape == (d, d) for a in attns)):
@@ -329,7 +329,8 @@ class _HeadBase(nn.Module):
         if attns is not None:
             xs = [f if f.dtype == torch.bfloat16 else f.to(torch.bfloat16) for f in x]
             feats = fold.FoldedTokens(xs, self.input_proj, self.training)
-            feats.project(attns, self.enc_output[0], self.enc_output[1], self.enc_score_head)
+            _, valid = self._anchors(feats.shapes, feats.dtype, feats.device)
+            feats.project(attns, self.enc_output[0], self.enc_output[1], self.enc_score_head, self._valid_u8(valid))
             return feats, feats.shapes, None
         feats, shapes = self._get_encoder_input(x)
         hub = None

@@ -21,13 +21,26 @@ def _reduce(a, a_row, a_img, token_major, x, M):
     return torch.einsum("bmt,bct->mc", A, X), A.sum((0, 2))
 
 
-def _project(x, w, bias, out0, out1, raw, start, N0, N1, NT):
+def _project(x, w, bias, out0, out1, raw, start, N0, N1, NT, rank=None):
     X = x.flatten(2).transpose(1, 2)                          # [B, HW, C]
     y = X @ w.t() + bias
     hw = X.shape[1]
     out0[:, start:start + hw] = y[..., :N0]
-    out1[:, start:start + hw] = y[..., N0:N0 + N1]
-    raw[:, start:start + hw] = y[..., N0 + N1:]
+    if rank is None:
+        out1[:, start:start + hw] = y[..., N0:N0 + N1]
+        raw[:, start:start + hw] = y[..., N0 + N1:]
+        return
+    # the epilogue of tamtr_tok_project_rank (include/tamtr_b200.h), stated with the same sums
+    scores, valid_u8, consts, nc, eps = rank
+    ok = valid_u8[start:start + hw].bool().view(1, hw, 1)
+    E, tail = y[..., N0:N0 + N1] * ok, y[..., N0 + N1:] * ok
+    d = N1
+    mean = (E.sum(-1) + consts[0]) / d
+    var = ((E * E).sum(-1) + 2 * tail[..., NT - 1] + consts[1]) / d - mean * mean
+    rstd = torch.rsqrt(var.clamp_min(0) + eps)
+    bw, sw, ck = consts[2:2 + NT], consts[2 + NT:2 + 2 * NT], consts[2 + 2 * NT:2 + 3 * NT]
+    s = rstd.unsqueeze(-1) * (tail + bw - mean.unsqueeze(-1) * sw) + ck
+    scores[:, start:start + hw] = s[..., :nc].max(-1).values
 
 
 @pytest.fixture
@@ -118,3 +131,18 @@ def test_no_graph_projection(cpu_fold):
     assert tok.arena is None
     for v, r in zip(vals, ref_vals):
         assert torch.allclose(v.reshape(r.shape), r, atol=1e-10, rtol=1e-9)
+
+
+def test_fused_ranking_scores(cpu_fold):
+    """the scores the projection's epilogue computes from (sum E, sum E^2, E . enc_bias) are the reference's ranking
+    enc_score_head(LayerNorm(enc_output.0(valid * feats))).max(-1) (head.py:1229-1237)"""
+    d, B, projs, attns, enc_linear, enc_norm, score, xs = _setup(False)
+    with torch.no_grad():
+        feats, _ = _unfolded(projs, attns, xs)
+        Lv = feats.shape[1]
+        valid = (torch.rand(Lv, generator=torch.Generator().manual_seed(9)) > 0.3)
+        ref = score(enc_norm(enc_linear(valid.view(1, Lv, 1) * feats))).max(-1).values
+        tok = fold.FoldedTokens([x.detach() for x in xs], projs, False)
+        tok.project(attns, enc_linear, enc_norm, score, valid.to(torch.uint8))
+    assert tok.E is None and tok.raw is None
+    assert torch.allclose(tok.scores, ref, atol=1e-9, rtol=1e-8), (tok.scores - ref).abs().max()

@@ -49,6 +49,46 @@ def test_tok_project_matches_fp32(cuda_lib, B, C, H, W, N0, N1, NT):
             assert torch.all(t[:, :pre] == 7.0) and torch.all(t[:, pre + HW:] == 7.0)
 
 
+@pytest.mark.parametrize("B,C,H,W,N0,N1,nc", [
+    (2, 128, 20, 20, 256, 128, 10),        # two token blocks per CTA: a thread owns its token's whole row
+    (2, 512, 10, 20, 1536, 512, 10),       # one block per CTA: two threads share a token (partial moments through smem)
+    (2, 128, 40, 40, 1536, 512, 10),       # TAM-TR column counts, 12.5 blocks per image
+    (1, 256, 8, 16, 128, 192, 40),         # tail starts in the second chunk of its step; 40 classes
+])
+def test_tok_project_rank_matches_fp32(cuda_lib, B, C, H, W, N0, N1, nc):
+    """ranking scores out of the projection's epilogue == the same formulas in fp32 on the same bf16 operands"""
+    from tamtr_b200 import fold
+    x = _maps(B, C, H, W, 7)
+    g = torch.Generator().manual_seed(8)
+    NT = (nc + 1 + 15) // 16 * 16
+    Nall = N0 + N1 + NT
+    w = (torch.randn(Nall, C, generator=g) / C ** 0.5).bfloat16().cuda()
+    bias = torch.randn(Nall, generator=g).cuda()
+    consts = torch.randn(2 + 3 * NT, generator=g)
+    consts[1] = consts[1].abs() + 40.0                 # sum enc_bias^2: keeps the variance positive
+    consts = consts.cuda()
+    HW, pre, post = H * W, 24, 8
+    Lv = pre + HW + post
+    valid = (torch.rand(Lv, generator=g) > 0.25).to(torch.uint8).cuda()
+    out0 = torch.full((B, Lv, N0), 7.0, dtype=torch.bfloat16, device="cuda")
+    scores = torch.full((B, Lv), 7.0, device="cuda")
+    fold._kernel_project(x, w, bias, out0, None, None, pre, N0, N1, NT, (scores, valid, consts, nc, 1e-5))
+    torch.cuda.synchronize()
+    y = x.float().flatten(2).transpose(1, 2) @ w.float().t() + bias
+    assert rel_l2(out0[:, pre:pre + HW], y[..., :N0]) < 4e-3
+    ok = valid[pre:pre + HW].bool().view(1, HW, 1)
+    E, tail = y[..., N0:N0 + N1] * ok, y[..., N0 + N1:] * ok
+    mean = (E.sum(-1) + consts[0]) / N1
+    var = ((E * E).sum(-1) + 2 * tail[..., NT - 1] + consts[1]) / N1 - mean * mean
+    rstd = torch.rsqrt(var.clamp_min(0) + 1e-5)
+    bw, sw, ck = consts[2:2 + NT], consts[2 + NT:2 + 2 * NT], consts[2 + 2 * NT:2 + 3 * NT]
+    ref = (rstd.unsqueeze(-1) * (tail + bw - mean.unsqueeze(-1) * sw) + ck)[..., :nc].max(-1).values
+    got = scores[:, pre:pre + HW]
+    assert (got - ref).abs().max() < 2e-3 * ref.abs().max(), (got - ref).abs().max()
+    assert torch.all(scores[:, :pre] == 7.0) and torch.all(scores[:, pre + HW:] == 7.0)
+    assert torch.all(out0[:, :pre] == 7.0) and torch.all(out0[:, pre + HW:] == 7.0)
+
+
 @pytest.mark.parametrize("B,C,H,W", [(2, 128, 20, 20), (1, 64, 8, 8), (3, 256, 16, 24), (2, 512, 10, 20), (4, 128, 40, 40)])
 def test_tok_reduce_moments(cuda_lib, B, C, H, W):
     from tamtr_b200 import fold

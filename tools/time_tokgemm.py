@@ -50,6 +50,7 @@ def main():
     out0 = torch.empty(B, Lv, N0, dtype=torch.bfloat16, device=dev)
     out1 = torch.empty(B, Lv, N1, dtype=torch.bfloat16, device=dev)
     raw = torch.empty(B, Lv, NT, dtype=torch.float32, device=dev)
+    scores = torch.empty(B, Lv, dtype=torch.float32, device=dev)
     grad = torch.randn(B, Lv, N0, device=dev).bfloat16()
     rows = []
     start = 0
@@ -62,6 +63,14 @@ def main():
             t = time_fn(lambda: fold._kernel_project(x, w, bias, out0, out1, raw, start, N0, N1, NT), args.iters, flush)
             by = x.numel() * 2 + w.numel() * 2 + B * HW * ((N0 + N1) * 2 + NT * 4)
             rows.append({"kernel": "tok_project", "level": l, "C": C, "tokens": B * HW, "us": t, "bytes": by,
+                         "gbs": by / t / 1e3, "frac": by / t / 1e3 / PEAK, "tflops": 2.0 * B * HW * C * (N0 + N1 + NT) / t / 1e6})
+            consts = torch.randn(2 + 3 * NT, device=dev)
+            consts[1] = consts[1].abs() + 600.0
+            valid = torch.ones(Lv, dtype=torch.uint8, device=dev)
+            t = time_fn(lambda: fold._kernel_project(x, w, bias, out0, None, None, start, N0, N1, NT,
+                                                     (scores, valid, consts, 10, 1e-5)), args.iters, flush)
+            by = x.numel() * 2 + w.numel() * 2 + B * HW * (N0 * 2 + 4)
+            rows.append({"kernel": "tok_project_rank", "level": l, "C": C, "tokens": B * HW, "us": t, "bytes": by,
                          "gbs": by / t / 1e3, "frac": by / t / 1e3 / PEAK, "tflops": 2.0 * B * HW * C * (N0 + N1 + NT) / t / 1e6})
             t = time_fn(lambda: fold._kernel_reduce(x, HW, C * HW, False, x, C), args.iters, flush)
             by = x.numel() * 2
