@@ -696,6 +696,24 @@ def main():
                 "fwd": {"kernel": "msda_fwd_kernel<bf16,LPC=8,NS=12>", "achieved": fwd_b / (fwd_us * 1e3) if fwd_us else None,
                         "frac": (fwd_b / (fwd_us * 1e3) / peak) if fwd_us else None, "algorithmic_bytes": fwd_b,
                         "avg_us": fwd_us, "traffic": traffic.get("msda_fwd_dram_bytes_per_launch")}}
+        # the folded encoder side (csrc/tokgemm.cu): per step, all levels together.  Algorithmic bytes:
+        # projection = the NCHW maps + the value tensor of all layers written once + one fp32 score per token;
+        # reductions = the maps twice (moments, weight gradient) + grad_value read once
+        x_bytes = sum(B * c * s * s * 2 for c, s in zip(CH, SIZES))
+        tokens = B * sum(s * s for s in SIZES)
+        fold = {}
+        for name, by in (("tok_project", x_bytes + tokens * (NDL * HD * 2 + 4)),
+                         ("tok_reduce", 2 * x_bytes + tokens * NDL * HD * 2)):
+            k = per_kernel.get(name)
+            if k:
+                us = k["avg_us"] * k["launches_per_step"]
+                fold[name] = {"us_per_step": us, "launches_per_step": k["launches_per_step"], "algorithmic_bytes": by,
+                              "achieved": by / (us * 1e3), "frac": by / (us * 1e3) / peak}
+        if fold:
+            roof["fold"] = dict(fold, unit="GB/s", peak=peak,
+                                note="tamtr_tok_project_rank / tamtr_tok_reduce, all pyramid levels of one step together "
+                                     "(per level: tools/time_tokgemm.py, profiles/tokgemm_r2_notes.txt); timed eager by the "
+                                     "library's own CUDA events")
         cfg = dict(config_dict(loss_kind, args.vss), queries=Lq, cuda_graph=step.graph is not None, batch_per_gpu=B,
                    parallelism=f"dp{ws}" if ws > 1 else "single", cpus_bound_to_gpu_numa_node=numa_cpus,
                    optimizer="clip_grad_norm_(0.1) + AdamW inside the step (csrc/optim.cu)" if optimizer else "none",

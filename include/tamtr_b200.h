@@ -476,6 +476,49 @@ int tamtr_tok_reduce_splits(int B, int C, int HW, int M, int a_token_major);
 int tamtr_tok_reduce(const void *a_bf16, long a_row, long a_img, int a_token_major, const void *x_bf16, float *part_d,
                      float *part_rs, int B, int C, int HW, int M, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Glue of the folded encoder side (csrc/foldglue.cu; the algebra and its derivation are in tamtr_b200/fold.py): the
+ * element-wise work between the token reductions / projections above and the small dense products that stay library
+ * GEMMs, one launch for all pyramid levels each.  Level tables (C, S, n_tok, pointer arrays) are host arrays of L <= 8
+ * entries; every tensor is f32 unless noted.  K = max_l C_l + 1.
+ *   tamtr_fold_stats   partials of tamtr_tok_reduce(x, x) (part_d [S_l, C_l, C_l], part_rs [S_l, C_l]) and the token
+ *                      count n_tok -> mean_x [C_l], cov [C_l, C_l] = E[x x^T] - mean mean^T
+ *   tamtr_fold_bn      BatchNorm2d (torch/nn/modules/batchnorm.py:155-193) of y = wc x from P = wc cov, wc [d, C_l] and
+ *                      mean_x: mu = wc mean, var = diag(P wc^T) (batch_stats) or the running statistics; updates
+ *                      run_mean / run_var / n_batches (update_running) with the unbiased variance; s = gamma * rstd,
+ *                      t = beta - mu * s; a_ext [L, d, K] = [s * wc | 0 | t], a_ext_t [L, K, d] its transpose,
+ *                      stats [L, d, 4] = (mu, rstd, s, t)
+ *   tamtr_fold_pack    Fv [L, N0, K], Fe [L, NE, K] (folded weights, column K-1 = folded bias part), bv [N0] ->
+ *                      w_out[l] bf16 [N0 + NE, C_l] and bias [L, N0 + NE]: the operands of tamtr_tok_project
+ *   tamtr_fold_unpack  partials of tamtr_tok_reduce(grad_value, x) per level -> dF [L, N0, K], dF_t [N0, L, K], d_bv [N0]
+ *   tamtr_fold_bn_bwd  dA [L, d, K] (+ dAt [L, K, d] or NULL, added) -> d_wc[l] [d, C_l], d_gamma[l], d_beta[l]
+ *   tamtr_fold_gather  xcat [R, L * K]: for the (image, token) pair flat_idx[r] = image * Lv + token the bf16 column
+ *                      x_l[b, :, token - start_l] of its level l in block l (1 in the block's last column), 0 elsewhere:
+ *                      the rows head.py:1240 gathers from `feats` are xcat @ a_ext_t.view(L * K, d) */
+/*   tamtr_fold_rank_consts  the ranking branch's operand and constants from the parameters (enc_output.0 weight We [d, d]
+ *                      and bias eb, enc_score_head weight [nc, d] and bias, all of dtype lin_dtype; LayerNorm weight /
+ *                      bias f32): we_all [d + NT, d] = We, then the NT tail rows (class k: (score_w[k] * ln_w) @ We; the
+ *                      last row, fused mode: eb @ We), consts [2 + 3 * NT] = { sum eb, sum eb^2, bw, sw, ck } of
+ *                      tamtr_tok_project_rank (written in fused mode only) */
+int tamtr_fold_rank_consts(const void *We, const void *eb, const void *score_w, const void *score_b, const float *ln_w,
+                           const float *ln_b, float *we_all, float *consts, int d, int nc, int NT, int fused, int lin_dtype,
+                           void *stream);
+int tamtr_fold_stats(int L, const int *C, const int *S, const float *n_tok, const float *const *part_d,
+                     const float *const *part_rs, float *const *mean_x, float *const *cov, void *stream);
+int tamtr_fold_bn(int L, int d, const int *C, const float *n_tok, const float *const *wc, const float *const *P,
+                  const float *const *mean_x, const float *const *gamma, const float *const *beta, float *const *run_mean,
+                  float *const *run_var, long long *const *n_batches, const float *momentum, const float *eps,
+                  int batch_stats, int update_running, float *a_ext, float *a_ext_t, float *stats, void *stream);
+int tamtr_fold_pack(int L, const int *C, const float *Fv, const float *Fe, const float *bv, void *const *w_out, float *bias,
+                    int N0, int NE, void *stream);
+int tamtr_fold_unpack(int L, const int *C, const int *S, const float *const *part_d, const float *const *part_rs, float *dF,
+                      float *dF_t, float *d_bv, int N0, void *stream);
+int tamtr_fold_bn_bwd(int L, int d, const int *C, const float *const *wc, const float *const *P, const float *const *mean_x,
+                      const float *const *gamma, const float *dA, const float *dAt, const float *stats, int batch_stats,
+                      float *const *d_wc, float *const *d_gamma, float *const *d_beta, void *stream);
+int tamtr_fold_gather(int L, int Lv, const int *C, const int *start, const int *hw, const void *const *x_bf16,
+                      const long long *flat_idx, float *xcat, int R, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

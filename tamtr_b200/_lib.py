@@ -90,6 +90,13 @@ _SIGNATURES = {
     "tamtr_tok_project_supported": (ctypes.c_int, [_i] * 6),
     "tamtr_tok_project": (ctypes.c_int, [_vp, _vp, _fp, _vp, _l, _l, _vp, _l, _l, _fp, _l, _l] + [_i] * 6 + [_vp]),
     "tamtr_tok_project_rank": (ctypes.c_int, [_vp, _vp, _fp, _vp, _l, _l, _fp, _l, _vp, _fp, _i, ctypes.c_float] + [_i] * 6 + [_vp]),
+    "tamtr_fold_rank_consts": (ctypes.c_int, [_vp] * 4 + [_fp] * 4 + [_i] * 5 + [_vp]),
+    "tamtr_fold_stats": (ctypes.c_int, [_i] + [_vp] * 7 + [_vp]),
+    "tamtr_fold_bn": (ctypes.c_int, [_i, _i] + [_vp] * 12 + [_i, _i] + [_fp] * 3 + [_vp]),
+    "tamtr_fold_pack": (ctypes.c_int, [_i, _vp, _fp, _fp, _fp, _vp, _fp, _i, _i, _vp]),
+    "tamtr_fold_unpack": (ctypes.c_int, [_i] + [_vp] * 4 + [_fp] * 3 + [_i, _vp]),
+    "tamtr_fold_bn_bwd": (ctypes.c_int, [_i, _i] + [_vp] * 5 + [_fp] * 3 + [_i] + [_vp] * 3 + [_vp]),
+    "tamtr_fold_gather": (ctypes.c_int, [_i, _i] + [_vp] * 4 + [_vp, _fp, _i, _vp]),
     "tamtr_tok_reduce_supported": (ctypes.c_int, [_i] * 5),
     "tamtr_tok_reduce_splits": (ctypes.c_int, [_i] * 5),
     "tamtr_tok_reduce": (ctypes.c_int, [_vp, _l, _l, _i, _vp, _fp, _fp] + [_i] * 4 + [_vp]),

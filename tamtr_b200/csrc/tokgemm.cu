@@ -15,6 +15,8 @@
 //
 // Both are warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, the rest = epilogue (TMEM -> registers ->
 // swizzled staging tile -> TMA store / fp32 stores).  HBM-bound by construction.
+#include <stdlib.h>
+
 #include "tc_ptx.cuh"
 
 namespace tamtr {
@@ -55,6 +57,18 @@ __device__ __forceinline__ void tk_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tk_tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tk_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t tk_pack2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -88,7 +102,7 @@ __device__ __forceinline__ bool tk_elect() {
 // while the CTA walks the N_all output columns 128 at a time, streaming W_fold through a ring (W_fold is a few hundred
 // KB: L2 hits).  Two TMEM accumulator stages (MT x 128 columns each) overlap the MMAs of step n+1 with the epilogue of
 // step n.  Shared memory: 11 operand slots of 16 KB (A: MT * C / 64 of them, the rest is the W ring) + two staging tiles.
-constexpr int kPjSlots = 11;
+constexpr int kPjSlots = 13;                 // 16 KB slots: A (MT * C / 64), the W ring, 2 or 4 staging tiles
 constexpr int kPjMaxWStages = 8;
 
 struct PjBars {
@@ -98,7 +112,8 @@ struct PjBars {
 
 struct PjGeom {
     int B, HW, C, n_kb;            // level geometry; n_kb = C / 64
-    int w_stages;                  // depth of the W ring = kPjSlots - MT * n_kb (capped)
+    int w_stages;                  // depth of the W ring = kPjSlots - MT * n_kb - 2 * stg_depth (capped)
+    int stg_depth;                 // staging tiles per epilogue group (2 when the A block leaves room)
     int pairs_per_img, n_pairs;    // CTA tiles of MT * 128 tokens
     int N0, N1, NT, n_steps;       // bf16 columns of out0 / out1, fp32 tail columns, ceil((N0 + N1 + NT) / 128)
     long raw_row, raw_img;         // strides (elements) of the fp32 tail tensor
@@ -119,9 +134,10 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sA = base;                                         // [MT][n_kb] slots of 16 KB
     uint8_t *sW = base + (size_t)MT * g.n_kb * kTkSlot;         // [w_stages] 16 KB
-    uint8_t *sO = base + (size_t)kPjSlots * kTkSlot;            // [2] 16 KB staging tiles (one per epilogue group)
-    PjBars &bars = *reinterpret_cast<PjBars *>(sO + 2 * kTkSlot);
-    float *s_rc = reinterpret_cast<float *>(sO + 2 * kTkSlot + 256);       // ranking constants: 2 + 3 * NT floats
+    uint8_t *sO = base + (size_t)(kPjSlots - 2 * g.stg_depth) * kTkSlot;     // staging tiles: [group][stg_depth]
+    uint8_t *sEnd = base + (size_t)kPjSlots * kTkSlot;
+    PjBars &bars = *reinterpret_cast<PjBars *>(sEnd);
+    float *s_rc = reinterpret_cast<float *>(sEnd + 256);                   // ranking constants: 2 + 3 * NT floats
     float2 *s_part = reinterpret_cast<float2 *>(s_rc + 2 + 3 * 64);        // MT == 1: partial row moments of the other group
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -225,7 +241,8 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         // of the group's swizzled staging tile -> one TMA store (the map clips rows past the image's last token).
         const int quarter = warp & 3, grp = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;                       // TMEM lane = token within the 128-block
-        uint8_t *stage = sO + (size_t)grp * kTkSlot;
+        uint8_t *stage0 = sO + (size_t)grp * g.stg_depth * kTkSlot;
+        uint32_t sc = 0;                                           // stores issued by this group
         const uint32_t row_off = (uint32_t)row * 128, sw = (uint32_t)(row & 7);
         const bool leader = (warp - 2) % 4 == 0 && lane == 0;      // issues the group's TMA stores
         const int mt = MT == 2 ? grp : 0;
@@ -324,12 +341,21 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         }
                         continue;
                     }
-                    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free again
+                    // both halves of the chunk leave TMEM together while the group makes sure its staging tile is free
+                    uint32_t v0[32], v1[32];
+                    tk_tmem_ld32_nowait(taddr + chunk * 64, v0);
+                    tk_tmem_ld32_nowait(taddr + chunk * 64 + 32, v1);
+                    uint8_t *stage = stage0 + (size_t)(g.stg_depth == 2 ? (sc & 1) : 0) * kTkSlot;
+                    ++sc;
+                    if (leader) {       // the store that last read this tile (stg_depth stores ago) has finished reading
+                        if (g.stg_depth == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    tk_tmem_wait_ld();
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        uint32_t v[32];
-                        tk_tmem_ld32(taddr + chunk * 64 + h * 32, v);
+                        const uint32_t(&v)[32] = h == 0 ? v0 : v1;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + col0 + h * 32 + q * 8));
@@ -626,7 +652,9 @@ static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float 
     g.B = B; g.HW = HW; g.C = C; g.n_kb = C / 64;
     int MT = (2 * g.n_kb <= 8) ? 2 : 1;
     if (HW <= 128) MT = 1;
-    g.w_stages = kPjSlots - MT * g.n_kb;
+    g.stg_depth = (kPjSlots - MT * g.n_kb - 4 >= 4) ? 2 : 1;
+    if (getenv("TAMTR_TOK_STG1")) g.stg_depth = 1;      // (experiment switch)
+    g.w_stages = kPjSlots - MT * g.n_kb - 2 * g.stg_depth;
     if (g.w_stages > kPjMaxWStages) g.w_stages = kPjMaxWStages;
     g.pairs_per_img = (HW + MT * 128 - 1) / (MT * 128);
     g.n_pairs = B * g.pairs_per_img;
@@ -645,7 +673,7 @@ static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float 
     TAMTR_CHECK_ARG(tk_attr_once((const void *)tok_project_kernel<1>, attr1) &&
                     tk_attr_once((const void *)tok_project_kernel<2>, attr2), TAMTR_E_NODEVICE,
                     "tok_project: cannot raise the dynamic shared memory limit");
-    const size_t smem = (size_t)(kPjSlots + 2) * kTkSlot + 4096 + 1024;      // slots, barriers + ranking scratch, alignment
+    const size_t smem = (size_t)kPjSlots * kTkSlot + 4096 + 1024;      // slots, barriers + ranking scratch, alignment
     const int n_sm = ::tamtr::sm_count();
     const int grid = g.n_pairs < n_sm ? g.n_pairs : n_sm;
     cudaStream_t st = (cudaStream_t)stream;

@@ -31,6 +31,9 @@ Numerics: X_l and the folded weights are bf16 operands of fp32-accumulating tens
 fold itself are fp32.  Compared with the reference under autocast (Y and M each rounded to bf16) the folded path rounds
 once less.  It is taken for bf16 activations only; fp32 inputs keep the unfolded kernels (ops.input_proj_tokens).
 """
+import ctypes
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -40,8 +43,9 @@ MATH_DTYPE = torch.float32          # dtype of the fold (tests run the algebra i
 
 
 # ---------------------------------------------------------------------------------------- kernel hooks (C ABI, CUDA only)
-def _kernel_reduce(a, a_row, a_img, token_major, x, M):
-    """D [M, C] = sum over (image, token) of a[m; b, tok] * x[b, c, tok], rs [M] = row sums of a (tamtr_tok_reduce)."""
+def _kernel_reduce_parts(a, a_row, a_img, token_major, x, M):
+    """tamtr_tok_reduce: per-split partials (part_d [S, M, C], part_rs [S, M]) of
+    D [M, C] = sum over (image, token) of a[m; b, tok] * x[b, c, tok] and rs [M] = row sums of a."""
     _lib.require_cuda(a, x)
     if a.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
         raise RuntimeError("tamtr_b200: tok_reduce takes bf16 operands")
@@ -57,6 +61,11 @@ def _kernel_reduce(a, a_row, a_img, token_major, x, M):
         rc = lib.tamtr_tok_reduce(a.data_ptr(), a_row, a_img, int(token_major), x.data_ptr(), part_d.data_ptr(),
                                   part_rs.data_ptr(), B, C, HW, M, _lib.stream_ptr(x.device))
     _lib.check(rc, "tok_reduce")
+    return part_d, part_rs
+
+
+def _kernel_reduce(a, a_row, a_img, token_major, x, M):
+    part_d, part_rs = _kernel_reduce_parts(a, a_row, a_img, token_major, x, M)
     return part_d.sum(0), part_rs.sum(0)
 
 
@@ -191,7 +200,6 @@ class _TokProjectFn(torch.autograd.Function):
         L, N0, Cm1 = Fv.shape
         Cm = Cm1 - 1
         N1, NT = tokens.d, Fe.shape[1] - tokens.d
-        B, Lv, dev = tokens.B, tokens.Lv, xs[0].device
         W = torch.cat([Fv, Fe], 1)                                             # [L, N_all, Cm + 1]
         bias = W[:, :, Cm].clone()
         bias[:, :N0] += bv.to(bias.dtype)
@@ -199,54 +207,24 @@ class _TokProjectFn(torch.autograd.Function):
         acc = torch.float32 if lp == torch.bfloat16 else W.dtype
         bias = bias.to(acc).contiguous()
         Wb = W[:, :, :Cm].to(lp)
-        value_all = torch.empty(B, Lv, N0, dtype=lp, device=dev)
-        rk = tokens.rank_consts
-        if rk["fused"]:        # ranking finished in the projection's epilogue: E and the class scores are never stored
-            E = raw = None
-            scores = torch.empty(B, Lv, dtype=acc, device=dev)
-            rank = (scores, tokens.valid_u8, rk["consts"], rk["nc"], rk["eps"])
-        else:
-            E = torch.empty(B, Lv, N1, dtype=lp, device=dev)
-            raw = torch.empty(B * Lv, NT, dtype=acc, device=dev)
-            scores = rank = None
-        wl = []
-        for l, x in enumerate(xs):
-            C = x.shape[1]
-            w = Wb[l, :, :C].contiguous()
-            _kernel_project(x, w, bias[l], value_all, E, None if raw is None else raw.view(B, Lv, NT), tokens.starts[l],
-                            N0, N1, NT, rank)
-            wl.append(w[:N0])
-        tokens.E, tokens.raw, tokens.scores = E, raw, scores
+        ws = [Wb[l, :, :x.shape[1]].contiguous() for l, x in enumerate(xs)]
+        values = _project_levels(tokens, xs, ws, bias, N0, N1, NT, n_layers, n_heads)
+        value_all = tokens._value_all
         d = N0 // n_layers
-        ctx.save_for_backward(*xs, *wl)
+        ctx.save_for_backward(*xs, *[w[:N0] for w in ws])
         ctx.arena, ctx.n, ctx.d, ctx.L, ctx.Cm = arena, n_layers, d, L, Cm
         ctx.meta = (value_all.shape, tokens.starts, tokens.hw, Fv.dtype, bv.dtype, lp)
         ctx.set_materialize_grads(False)
         arena.base = value_all
-        return tuple(value_all[:, :, i * d:(i + 1) * d].view(B, Lv, n_heads, d // n_heads) for i in range(n_layers))
+        return values
 
     @staticmethod
     def backward(ctx, *grads):
         L, Cm, n, d = ctx.L, ctx.Cm, ctx.n, ctx.d
         xs, wl = ctx.saved_tensors[:L], ctx.saved_tensors[L:]
         shape, starts, hw, fdt, bdt, lp = ctx.meta
-        arena = ctx.arena
-        buf, arena.buf, arena.base = arena.buf, None, None
-        written, arena.written = arena.written, set()
-        arena.bias_grad = {}
         dev = xs[0].device
-        if buf is None:
-            buf = _lib.zeros_like_fast(torch.empty(shape, dtype=lp, device=dev))
-        for i, g in enumerate(grads):
-            if g is None:
-                continue
-            if i * d in written:
-                if any(st != 0 for st in g.stride()):
-                    raise RuntimeError("tamtr_b200: a projected value view has a consumer besides its sampler")
-                continue
-            buf[:, :, i * d:(i + 1) * d].add_(g.reshape(shape[0], shape[1], d))
-        if buf.dtype != lp:                             # fp32 arena: one cast pass in front of the reductions
-            buf = buf.to(lp)
+        buf = _arena_gradient(ctx.arena, grads, shape, d, lp, dev)
         B, Lv, N0 = shape
         dFv = torch.zeros(L, N0, Cm + 1, dtype=fdt, device=dev)
         dxs = []
@@ -264,6 +242,234 @@ class _TokProjectFn(torch.autograd.Function):
                 dxs.append(None)
         dbv = dFv[:, :, Cm].sum(0).to(bdt) if ctx.needs_input_grad[5] else None
         return (None, None, None, None, dFv, dbv, None, *dxs)
+
+
+# ---------------------------------------------------------------------------------------- fused glue (csrc/foldglue.cu)
+FUSED_GLUE = os.environ.get("TAMTR_FOLD_GLUE", "1") != "0"    # the whole fold as ONE autograd node over a handful of
+                                                             # kernels (False: the differentiable torch ops)
+
+_MAXL = 8
+
+
+def _parr(ts):
+    return (ctypes.c_void_p * _MAXL)(*([None if t is None else t.data_ptr() for t in ts] + [None] * (_MAXL - len(ts))))
+
+
+def _iarr(v):
+    return (ctypes.c_int * _MAXL)(*(list(map(int, v)) + [0] * (_MAXL - len(v))))
+
+
+def _farr(v):
+    return (ctypes.c_float * _MAXL)(*(list(map(float, v)) + [0.0] * (_MAXL - len(v))))
+
+
+def _mm_tf32(a, b):
+    return _FoldMatmulFn._mm(a, b)
+
+
+def _mm_fp32(a, b):
+    """true-fp32 product whatever the global TF32 switch says (variance of the conv output: a difference of large terms)"""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return torch.mm(a, b)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def fused_glue_applies(tokens, projs, attns):
+    if not (FUSED_GLUE and tokens.is_cuda and MATH_DTYPE == torch.float32 and len(tokens.xs) <= _MAXL):
+        return False
+    if any(x.requires_grad for x in tokens.xs) and torch.is_grad_enabled():
+        return False            # gradients to the feature maps go through the differentiable torch path
+    for conv, bn in projs:
+        ts = [conv.weight, bn.weight, bn.bias] + ([bn.running_mean, bn.running_var] if bn.running_mean is not None else [])
+        if any(t.dtype != torch.float32 or not t.is_contiguous() for t in ts):
+            return False
+    stats = [bn.running_mean is None for _, bn in projs]
+    return all(stats) or not any(stats)
+
+
+class _FusedFoldFn(torch.autograd.Function):
+    """The folded encoder side as one autograd node: moments -> BatchNorm coefficients -> folded weights -> projection
+    (forward), weight-gradient reductions -> d(folded weights) -> d(value_proj), d(A) -> d(conv weight, gamma, beta)
+    (backward), over tamtr_tok_reduce / tamtr_tok_project* and the glue kernels of csrc/foldglue.cu.  The products that
+    stay library GEMMs: conv_w @ Cov (fp32) and value_proj / ranking weights @ A_ext (TF32), 2 + L launches.
+
+    Outputs: a_ext_t [L, K, d] (differentiable: the selected rows are Xcat @ a_ext_t, see FoldedTokens.rows) and the
+    value views of the decoder layers."""
+
+    @staticmethod
+    def forward(ctx, tokens, arena, training, bns, n_layers, n_heads, We_all, *t):
+        L = len(tokens.xs)
+        convs, gammas, betas = t[:L], t[L:2 * L], t[2 * L:3 * L]
+        wvs, bvs = t[3 * L:3 * L + n_layers], t[3 * L + n_layers:]
+        xs, cs, d, Cm = tokens.xs, tokens.cs, tokens.d, tokens.Cm
+        K, dev, lib = Cm + 1, tokens.device, _lib.lib()
+        st = _lib.stream_ptr(dev)
+        n_tok = [float(tokens.B * n) for n in tokens.hw]
+        batch_stats = training or bns[0].running_mean is None
+        update = batch_stats and training and bns[0].running_mean is not None
+        C_arr = _iarr(cs)
+        P, mean_x = [None] * L, [None] * L
+        with torch.cuda.device(dev):
+            if batch_stats:
+                parts = [_kernel_reduce_parts(x, x.shape[2] * x.shape[3], x.shape[1] * x.shape[2] * x.shape[3], False, x,
+                                              x.shape[1]) for x in xs]
+                mean_flat = torch.empty(sum(cs), dtype=torch.float32, device=dev)
+                cov_flat = torch.empty(sum(c * c for c in cs), dtype=torch.float32, device=dev)
+                o1 = o2 = 0
+                covs = []
+                for l, c in enumerate(cs):
+                    mean_x[l] = mean_flat[o1:o1 + c]
+                    covs.append(cov_flat[o2:o2 + c * c].view(c, c))
+                    o1, o2 = o1 + c, o2 + c * c
+                _lib.check(lib.tamtr_fold_stats(L, C_arr, _iarr([p[0].shape[0] for p in parts]), _farr(n_tok),
+                                                _parr([p[0] for p in parts]), _parr([p[1] for p in parts]),
+                                                _parr(mean_x), _parr(covs), st), "fold_stats")
+                P = [_mm_fp32(convs[l].view(d, cs[l]), covs[l]) for l in range(L)]
+            mom = [0.0] * L
+            if update:
+                mom = [b.momentum if b.momentum is not None else 1.0 / float(b.num_batches_tracked + 1) for b in bns]
+            a_ext = torch.empty(L, d, K, dtype=torch.float32, device=dev)
+            a_ext_t = torch.empty(L, K, d, dtype=torch.float32, device=dev)
+            stats = torch.empty(L, d, 4, dtype=torch.float32, device=dev)
+            has_run = bns[0].running_mean is not None
+            _lib.check(lib.tamtr_fold_bn(
+                L, d, C_arr, _farr(n_tok), _parr([c.view(d, -1) for c in convs]), _parr(P) if batch_stats else None,
+                _parr(mean_x) if batch_stats else None, _parr(gammas), _parr(betas),
+                _parr([b.running_mean for b in bns]) if has_run else None,
+                _parr([b.running_var for b in bns]) if has_run else None,
+                _parr([b.num_batches_tracked for b in bns]) if has_run else None, _farr(mom), _farr([b.eps for b in bns]),
+                int(batch_stats), int(update), a_ext.data_ptr(), a_ext_t.data_ptr(), stats.data_ptr(), st), "fold_bn")
+            Wv = torch.cat(wvs, 0).float()
+            bv = torch.cat(bvs, 0).float()
+            Fv = _mm_tf32(Wv, a_ext)                                      # [L, N0, K]
+            Fe = _mm_tf32(We_all, a_ext)                                  # [L, NE, K]
+            N0, NE = Wv.shape[0], We_all.shape[0]
+            w_out = [torch.empty(N0 + NE, c, dtype=torch.bfloat16, device=dev) for c in cs]
+            bias = torch.empty(L, N0 + NE, dtype=torch.float32, device=dev)
+            _lib.check(lib.tamtr_fold_pack(L, C_arr, Fv.data_ptr(), Fe.data_ptr(), bv.data_ptr(), _parr(w_out),
+                                           bias.data_ptr(), N0, NE, st), "fold_pack")
+        values = _project_levels(tokens, xs, w_out, bias, N0, tokens.d, NE - tokens.d, n_layers, n_heads)
+        value_all = tokens._value_all
+        ctx.save_for_backward(*xs, *convs, *gammas, *[p for p in P if p is not None],
+                              *([mean_flat] if batch_stats else []), stats, a_ext_t, Wv)
+        ctx.arena, ctx.L, ctx.n, ctx.batch_stats = arena, L, n_layers, batch_stats
+        ctx.meta = (value_all.shape, tokens.starts, tokens.hw, cs, d, Cm, [w.dtype for w in wvs], [b.dtype for b in bvs],
+                    [c.shape for c in convs])
+        ctx.set_materialize_grads(False)
+        arena.base = value_all
+        return (a_ext_t, *values)
+
+    @staticmethod
+    def backward(ctx, d_aext_t, *grads):
+        L, n = ctx.L, ctx.n
+        shape, starts, hw, cs, d, Cm, wdts, bdts, cshapes = ctx.meta
+        sv = ctx.saved_tensors
+        xs, convs, gammas = sv[:L], sv[L:2 * L], sv[2 * L:3 * L]
+        k = 3 * L
+        P = mean_flat = None
+        if ctx.batch_stats:
+            P, mean_flat = sv[k:k + L], sv[k + L]
+            k += L + 1
+        stats, a_ext_t, Wv = sv[k], sv[k + 1], sv[k + 2]
+        K, dev, lib = Cm + 1, xs[0].device, _lib.lib()
+        st = _lib.stream_ptr(dev)
+        buf = _arena_gradient(ctx.arena, grads, shape, Wv.shape[0] // n, torch.bfloat16, dev)
+        B, Lv, N0 = shape
+        C_arr = _iarr(cs)
+        with torch.cuda.device(dev):
+            parts = [_kernel_reduce_parts(buf[:, starts[l]:], N0, Lv * N0, True, xs[l], N0) for l in range(L)]
+            dF = torch.empty(L, N0, K, dtype=torch.float32, device=dev)
+            dF_t = torch.empty(N0, L, K, dtype=torch.float32, device=dev)
+            d_bv = torch.empty(N0, dtype=torch.float32, device=dev)
+            _lib.check(lib.tamtr_fold_unpack(L, C_arr, _iarr([p[0].shape[0] for p in parts]), _parr([p[0] for p in parts]),
+                                             _parr([p[1] for p in parts]), dF.data_ptr(), dF_t.data_ptr(), d_bv.data_ptr(),
+                                             N0, st), "fold_unpack")
+            dWv = _mm_tf32(dF_t.view(N0, L * K), a_ext_t.view(L * K, d))
+            dA = _mm_tf32(Wv.t(), dF)                                      # [L, d, K]
+            d_wc = [torch.empty(d, c, dtype=torch.float32, device=dev) for c in cs]
+            d_gamma = [torch.empty(d, dtype=torch.float32, device=dev) for _ in cs]
+            d_beta = [torch.empty(d, dtype=torch.float32, device=dev) for _ in cs]
+            mean_x = None
+            if ctx.batch_stats:
+                o, mean_x = 0, []
+                for c in cs:
+                    mean_x.append(mean_flat[o:o + c])
+                    o += c
+            dAt = None if d_aext_t is None else d_aext_t.contiguous()
+            _lib.check(lib.tamtr_fold_bn_bwd(
+                L, d, C_arr, _parr([c.view(d, -1) for c in convs]), _parr(P) if P is not None else None,
+                _parr(mean_x) if mean_x is not None else None, _parr(gammas), dA.data_ptr(),
+                None if dAt is None else dAt.data_ptr(), stats.data_ptr(), int(ctx.batch_stats), _parr(d_wc),
+                _parr(d_gamma), _parr(d_beta), st), "fold_bn_bwd")
+        dd = Wv.shape[0] // n
+        dWv_c = dWv if all(t == torch.float32 for t in wdts) else dWv.to(wdts[0])
+        d_bv_c = d_bv if all(t == torch.float32 for t in bdts) else d_bv.to(bdts[0])
+        g_wv = [dWv_c[i * dd:(i + 1) * dd].to(wdts[i]) for i in range(n)]
+        g_bv = [d_bv_c[i * dd:(i + 1) * dd].to(bdts[i]) for i in range(n)]
+        return (None,) * 7 + tuple(g.view(s) for g, s in zip(d_wc, cshapes)) + tuple(d_gamma) + tuple(d_beta) \
+            + tuple(g_wv) + tuple(g_bv)
+
+
+class _RowsFn(torch.autograd.Function):
+    """feats rows = Xcat [R, L*K] @ A_ext^T [L*K, d] (TF32 forward and backward); Xcat carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, xcat, a_ext_t):
+        ctx.save_for_backward(xcat)
+        ctx.shape = a_ext_t.shape
+        return _mm_tf32(xcat, a_ext_t.reshape(-1, a_ext_t.shape[-1]))
+
+    @staticmethod
+    def backward(ctx, g):
+        (xcat,) = ctx.saved_tensors
+        return None, _mm_tf32(xcat.t(), g.float().contiguous()).view(ctx.shape)
+
+
+def _arena_gradient(arena, grads, shape, d, lp, dev):
+    """The gradient of the projected values: what the samplers accumulated in the shared arena (+ whatever reached a
+    value view through plain autograd), as one [B, Lv, N0] tensor of dtype `lp`."""
+    buf, arena.buf, arena.base = arena.buf, None, None
+    written, arena.written = arena.written, set()
+    arena.bias_grad = {}
+    if buf is None:
+        buf = _lib.zeros_like_fast(torch.empty(shape, dtype=lp, device=dev))
+    for i, g in enumerate(grads):
+        if g is None:
+            continue
+        if i * d in written:
+            if any(st != 0 for st in g.stride()):
+                raise RuntimeError("tamtr_b200: a projected value view has a consumer besides its sampler")
+            continue
+        buf[:, :, i * d:(i + 1) * d].add_(g.reshape(shape[0], shape[1], d))
+    if buf.dtype != lp:                             # fp32 arena: one cast pass in front of the reductions
+        buf = buf.to(lp)
+    return buf
+
+
+def _project_levels(tokens, xs, ws, bias, N0, N1, NT, n_layers, n_heads):
+    """One tamtr_tok_project(_rank) launch per level into the value tensor of all layers (+ the ranking side outputs on
+    `tokens`); returns the per-layer views [B, Lv, H, Dh]."""
+    B, Lv, dev, lp = tokens.B, tokens.Lv, xs[0].device, tokens.dtype
+    acc = torch.float32 if lp == torch.bfloat16 else bias.dtype
+    value_all = torch.empty(B, Lv, N0, dtype=lp, device=dev)
+    rk = tokens.rank_consts
+    if rk["fused"]:        # ranking finished in the projection's epilogue: E and the class scores are never stored
+        E = raw = None
+        scores = torch.empty(B, Lv, dtype=acc, device=dev)
+        rank = (scores, tokens.valid_u8, rk["consts"], rk["nc"], rk["eps"])
+    else:
+        E = torch.empty(B, Lv, N1, dtype=lp, device=dev)
+        raw = torch.empty(B * Lv, NT, dtype=acc, device=dev)
+        scores = rank = None
+    for l, x in enumerate(xs):
+        _kernel_project(x, ws[l], bias[l], value_all, E, None if raw is None else raw.view(B, Lv, NT), tokens.starts[l],
+                        N0, N1, NT, rank)
+    tokens.E, tokens.raw, tokens.scores, tokens._value_all = E, raw, scores, value_all
+    d = N0 // n_layers
+    return tuple(value_all[:, :, i * d:(i + 1) * d].view(B, Lv, n_heads, d // n_heads) for i in range(n_layers))
 
 
 # ---------------------------------------------------------------------------------------- the token source
@@ -286,9 +492,8 @@ class FoldedTokens:
         self.shape = (self.B, self.Lv, self.d)
         self.is_cuda = xs[0].is_cuda
         self.values = self.arena = self.E = self.raw = self.scores = self.valid_u8 = None
-        with torch.autocast(self.device.type, enabled=False):
-            self.A, self.t = self._coefficients(projs, training)        # [L, d, Cm] (zero beyond C_l), [L, d]
-        self.requires_grad = self.A.requires_grad
+        self.projs, self.training = projs, training
+        self.A = self.t = self.a_ext_t = None       # set by project(): A [L, d, Cm], t [L, d]  or  a_ext_t [L, Cm + 1, d]
 
     # BatchNorm2d's forward (torch/nn/modules/batchnorm.py:155-193) on statistics derived from the moments of X
     def _coefficients(self, projs, training):
@@ -341,21 +546,41 @@ class FoldedTokens:
         md = MATH_DTYPE
         self.valid_u8 = valid_u8
         n_layers, n_heads = len(attns), attns[0].n_heads
+        grad = torch.is_grad_enabled()
         with torch.autocast(self.device.type, enabled=False):
+            with torch.no_grad():
+                rk = _rank_constants_fused(enc_linear, enc_norm, score_linear, valid_u8 is not None) \
+                    if (FUSED_GLUE and self.is_cuda and md == torch.float32) else None
+                if rk is None:
+                    rk = _rank_constants(enc_linear, enc_norm, score_linear, md, fused=valid_u8 is not None)
+                    rk["We_all"] = torch.cat([enc_linear.weight.to(md), rk["Wr"]], 0)
+                We_all = rk["We_all"]
+            self.rank_consts = rk
+            self.arena = ops.ValueArena()
+            if fused_glue_applies(self, self.projs, attns):
+                convs, bns = [p[0] for p in self.projs], [p[1] for p in self.projs]
+                t = [c.weight for c in convs] + [b.weight for b in bns] + [b.bias for b in bns] \
+                    + [a.value_proj.weight for a in attns] + [a.value_proj.bias for a in attns]
+                if grad and any(p.requires_grad for p in t):
+                    out = _FusedFoldFn.apply(self, self.arena, self.training, bns, n_layers, n_heads, We_all, *t)
+                else:
+                    out = _FusedFoldFn.forward(_NoCtx(), self, self.arena, self.training, bns, n_layers, n_heads, We_all,
+                                               *[p.detach() for p in t])
+                    self.arena = None
+                self.a_ext_t, self.values = out[0], list(out[1:])
+                return self.values
+            self.A, self.t = self._coefficients(self.projs, self.training)       # [L, d, Cm] (zero beyond C_l), [L, d]
             Wv = torch.cat([a.value_proj.weight for a in attns], 0).to(md)                          # [N0, d]
             bv = torch.cat([a.value_proj.bias for a in attns], 0)
             Aext = torch.cat([self.A, self.t.unsqueeze(-1)], -1)                                    # [L, d, Cm + 1]
             Fv = _fold_matmul(Wv, Aext)
             with torch.no_grad():
-                rk = _rank_constants(enc_linear, enc_norm, score_linear, md, fused=valid_u8 is not None)
-                Fe = _fold_matmul(torch.cat([enc_linear.weight.to(md), rk["Wr"]], 0), Aext.detach())
-            self.rank_consts = rk
-            self.arena = ops.ValueArena()
-            if torch.is_grad_enabled() and (Fv.requires_grad or bv.requires_grad or any(x.requires_grad for x in self.xs)):
+                Fe = _fold_matmul(We_all, Aext.detach())
+            if grad and (Fv.requires_grad or bv.requires_grad or any(x.requires_grad for x in self.xs)):
                 vals = _TokProjectFn.apply(self, self.arena, n_layers, n_heads, Fv, bv, Fe, *self.xs)
             else:
-                ctx = _NoCtx()
-                vals = _TokProjectFn.forward(ctx, self, self.arena, n_layers, n_heads, Fv.detach(), bv.detach(), Fe, *self.xs)
+                vals = _TokProjectFn.forward(_NoCtx(), self, self.arena, n_layers, n_heads, Fv.detach(), bv.detach(), Fe,
+                                             *self.xs)
                 self.arena = None
         self.values = list(vals)
         return self.values
@@ -380,6 +605,19 @@ class FoldedTokens:
     def rows(self, flat_idx):
         """feats.reshape(-1, d)[flat_idx] (flat_idx = image * Lv + token) recomputed from X through A and t."""
         md = MATH_DTYPE
+        if self.a_ext_t is not None:        # fused glue: one gather kernel + one product
+            L, K, R = len(self.xs), self.Cm + 1, flat_idx.numel()
+            xcat = torch.empty(R, L * K, dtype=torch.float32, device=self.device)
+            idx = flat_idx.contiguous().long()
+            with torch.cuda.device(self.device):
+                rc = _lib.lib().tamtr_fold_gather(L, self.Lv, _iarr(self.cs), _iarr(self.starts), _iarr(self.hw),
+                                                  _parr(self.xs), idx.data_ptr(), xcat.data_ptr(), R,
+                                                  _lib.stream_ptr(self.device))
+            _lib.check(rc, "fold_gather")
+            with torch.autocast(self.device.type, enabled=False):
+                if torch.is_grad_enabled() and self.a_ext_t.requires_grad:
+                    return _RowsFn.apply(xcat, self.a_ext_t)
+                return _mm_tf32(xcat, self.a_ext_t.reshape(L * K, -1))
         img = torch.div(flat_idx, self.Lv, rounding_mode="floor")
         tok = flat_idx - img * self.Lv
         out = None
@@ -403,6 +641,31 @@ class _NoCtx:
 
     def set_materialize_grads(self, v):
         pass
+
+
+def _rank_constants_fused(enc_linear, enc_norm, score_linear, fused):
+    """_rank_constants + the ranking operand in one kernel (tamtr_fold_rank_consts); None when the parameters do not fit it."""
+    We, eb, sw, sb = enc_linear.weight, enc_linear.bias, score_linear.weight, score_linear.bias
+    lw, lb = enc_norm.weight, enc_norm.bias
+    lin = [We, eb, sw, sb]
+    if eb is None or sb is None or lw is None or lb is None or not all(t.is_cuda and t.is_contiguous() for t in lin + [lw, lb]):
+        return None
+    if any(t.dtype != We.dtype for t in lin) or We.dtype not in (torch.float32, torch.bfloat16) \
+            or lw.dtype != torch.float32 or lb.dtype != torch.float32:
+        return None
+    nc, d = sw.shape
+    fused = fused and nc + 1 <= 64
+    npad = (nc + (1 if fused else 0) + 15) // 16 * 16
+    if not fused:
+        return None             # (tamtr_rank_tokens wants its constants as separate vectors: the torch path builds them)
+    we_all = torch.empty(d + npad, d, dtype=torch.float32, device=We.device)
+    consts = torch.empty(2 + 3 * npad, dtype=torch.float32, device=We.device)
+    with torch.cuda.device(We.device):
+        rc = _lib.lib().tamtr_fold_rank_consts(We.data_ptr(), eb.data_ptr(), sw.data_ptr(), sb.data_ptr(), lw.data_ptr(),
+                                               lb.data_ptr(), we_all.data_ptr(), consts.data_ptr(), d, nc, npad, 1,
+                                               _lib.dtype_code(We), _lib.stream_ptr(We.device))
+    _lib.check(rc, "fold_rank_consts")
+    return {"We_all": we_all, "nc": nc, "npad": npad, "eps": enc_norm.eps, "fused": True, "consts": consts}
 
 
 def _rank_constants(enc_linear, enc_norm, score_linear, md, fused=False):

@@ -214,3 +214,62 @@ def test_folded_head_inference_matches_unfolded(cuda_lib):
     a, b = y_f.float(), y_u.float()
     dist = torch.cdist(a, b).min(-1).values
     assert (dist < 3e-2).float().mean() > 0.9
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_fused_glue_matches_torch_path(cuda_lib, train, monkeypatch):
+    """the fold as one autograd node over the glue kernels (csrc/foldglue.cu) == the same fold as differentiable torch ops:
+    values, selected rows, BatchNorm side effects and every parameter gradient"""
+    import copy
+    from tamtr_b200 import fold
+    m, xs, text = _head()
+    if not train:
+        m.eval()
+    ref = copy.deepcopy(m)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        tok, shapes, _ = m._encode(xs)
+        assert tok.a_ext_t is not None                     # fused path taken
+        monkeypatch.setattr(fold, "FUSED_GLUE", False)
+        tok_r, _, _ = ref._encode(xs)
+        assert tok_r.a_ext_t is None and tok_r.A is not None
+        monkeypatch.setattr(fold, "FUSED_GLUE", True)
+        for a, b in zip(tok.values, tok_r.values):
+            assert rel_l2(a, b) < 4e-3
+        assert rel_l2(tok.scores, tok_r.scores) < 2e-3
+        idx = torch.randint(0, tok.B * tok.Lv, (257,), device="cuda")
+        assert rel_l2(tok.rows(idx), tok_r.rows(idx)) < 2e-3
+    for p, r in zip(m.input_proj, ref.input_proj):
+        assert rel_l2(p[1].running_mean, r[1].running_mean) < 1e-5
+        assert rel_l2(p[1].running_var, r[1].running_var) < 1e-5
+        assert int(p[1].num_batches_tracked) == int(r[1].num_batches_tracked)
+    loss_f, g_f = _step(m, xs, text)
+    monkeypatch.setattr(fold, "FUSED_GLUE", False)
+    loss_u, g_u = _step(ref, xs, text)
+    assert abs(loss_f.item() - loss_u.item()) < 2e-3 * abs(loss_u.item())
+    assert set(g_f) == set(g_u)
+    for k in sorted(g_f):
+        if k.startswith("input_proj") or "value_proj" in k or k.startswith("enc_output"):
+            # (the two runs differ by the order of the samplers' bf16 atomic adds; the bias gradients -- column sums over
+            #  all tokens with heavy cancellation -- feel it most)
+            tol = 5e-2 if k.endswith("value_proj.bias") else 2e-2
+            assert rel_l2(g_f[k], g_u[k]) < tol, (k, rel_l2(g_f[k], g_u[k]))
+
+
+def test_rank_constants_kernel_matches_torch(cuda_lib):
+    """tamtr_fold_rank_consts == the torch construction of the ranking operand and constants (fp32 and bf16 parameters)"""
+    from tamtr_b200 import fold
+    torch.manual_seed(4)
+    d, nc = 512, 10
+    lin = torch.nn.Linear(d, d).cuda()
+    ln = torch.nn.LayerNorm(d).cuda()
+    torch.nn.init.uniform_(ln.weight, 0.5, 1.5)
+    torch.nn.init.uniform_(ln.bias, -0.5, 0.5)
+    sc = torch.nn.Linear(d, nc).cuda()
+    for lowp in (False, True):
+        a, b = (lin.bfloat16(), sc.bfloat16()) if lowp else (lin, sc)
+        ref = fold._rank_constants(a, ln, b, torch.float32, fused=True)
+        got = fold._rank_constants_fused(a, ln, b, True)
+        assert got["npad"] == ref["npad"] == 16 and got["fused"]
+        we_all = torch.cat([a.weight.float(), ref["Wr"]], 0)
+        assert rel_l2(got["We_all"], we_all) < 1e-5
+        assert torch.allclose(got["consts"], ref["consts"], rtol=1e-4, atol=1e-4), (got["consts"] - ref["consts"]).abs().max()
