@@ -497,9 +497,10 @@ int tamtr_tok_reduce(const void *a_bf16, long a_row, long a_img, int a_token_maj
  *                      the rows head.py:1240 gathers from `feats` are xcat @ a_ext_t.view(L * K, d) */
 /*   tamtr_fold_rank_consts  the ranking branch's operand and constants from the parameters (enc_output.0 weight We [d, d]
  *                      and bias eb, enc_score_head weight [nc, d] and bias, all of dtype lin_dtype; LayerNorm weight /
- *                      bias f32): we_all [d + NT, d] = We, then the NT tail rows (class k: (score_w[k] * ln_w) @ We; the
- *                      last row, fused mode: eb @ We), consts [2 + 3 * NT] = { sum eb, sum eb^2, bw, sw, ck } of
- *                      tamtr_tok_project_rank (written in fused mode only) */
+ *                      bias f32): we_all [d + NT, d] = We (f32), then the NT COEFFICIENT rows of the tail (class k:
+ *                      score_w[k] * ln_w; the last row, fused mode: eb) -- the caller multiplies them by We in place, one
+ *                      small GEMM; consts [2 + 3 * NT] = { sum eb, sum eb^2, bw, sw, ck } of tamtr_tok_project_rank
+ *                      (written in fused mode only) */
 int tamtr_fold_rank_consts(const void *We, const void *eb, const void *score_w, const void *score_b, const float *ln_w,
                            const float *ln_b, float *we_all, float *consts, int d, int nc, int NT, int fused, int lin_dtype,
                            void *stream);

@@ -42,22 +42,41 @@ struct FoldPtrs {
 };
 
 __global__ void fold_stats_kernel(const FoldPtrs p) {
+    // block = 256 consecutive entries e = r * C + c of one level's [C, C] matrix; the means of all C channels are first
+    // formed in shared memory by the block (S * C coalesced loads), then every thread sums the S partials of its entry
+    __shared__ float s_mean[512];
     const int l = blockIdx.y, C = p.C[l], S = p.S[l];
+    if ((long)blockIdx.x * blockDim.x >= (long)C * C) return;
+    const float *pd = p.part_d[l], *pr = p.part_rs[l];
+    const float inv = 1.0f / p.n_tok[l];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+        int s = 0;
+        for (; s + 3 < S; s += 4) {
+            m0 += __ldg(pr + (size_t)s * C + c);
+            m1 += __ldg(pr + (size_t)(s + 1) * C + c);
+            m2 += __ldg(pr + (size_t)(s + 2) * C + c);
+            m3 += __ldg(pr + (size_t)(s + 3) * C + c);
+        }
+        for (; s < S; ++s) m0 += __ldg(pr + (size_t)s * C + c);
+        s_mean[c] = ((m0 + m1) + (m2 + m3)) * inv;
+    }
+    __syncthreads();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= C * C) return;
     const int r = e / C, c = e - r * C;
-    const float *pd = p.part_d[l], *pr = p.part_rs[l];
-    float g = 0.f, mr = 0.f, mc = 0.f;
-    for (int s = 0; s < S; ++s) {
-        g += __ldg(pd + (size_t)s * C * C + e);
-        mr += __ldg(pr + (size_t)s * C + r);
-        mc += __ldg(pr + (size_t)s * C + c);
+    const size_t cc = (size_t)C * C;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+    int s = 0;
+    for (; s + 3 < S; s += 4) {
+        g0 += __ldg(pd + (size_t)s * cc + e);
+        g1 += __ldg(pd + (size_t)(s + 1) * cc + e);
+        g2 += __ldg(pd + (size_t)(s + 2) * cc + e);
+        g3 += __ldg(pd + (size_t)(s + 3) * cc + e);
     }
-    const float inv = 1.0f / p.n_tok[l];
-    mr *= inv;
-    mc *= inv;
-    p.cov[l][e] = g * inv - mr * mc;
-    if (c == 0) p.mean_x[l][r] = mr;
+    for (; s < S; ++s) g0 += __ldg(pd + (size_t)s * cc + e);
+    p.cov[l][e] = ((g0 + g1) + (g2 + g3)) * inv - s_mean[r] * s_mean[c];
+    if (c == 0) p.mean_x[l][r] = s_mean[r];
 }
 
 // one warp per (level, output channel j)
@@ -214,10 +233,11 @@ __device__ __forceinline__ float fold_ld(const void *p, size_t i, int bf16) {
 }
 
 // Constants of the ranking (tamtr_tok_project_rank) from the parameters, one launch:
-//   we_all [d + NT, d] f32: rows [0, d) = enc_output.0.weight; row d + k (k < nc) = (score_w[k] * ln_w) @ We; row d + NT - 1 =
-//   enc_bias @ We (fused mode); other rows 0.   consts = { sum eb, sum eb^2, bw[NT], sw[NT], ck[NT] }:
-//   bw[k] = Wp[k] . eb, sw[k] = sum Wp[k], ck[k] = score_w[k] . ln_b + score_b[k],  Wp[k] = score_w[k] * ln_w.
-// Block r < d copies a row of We; block d + k builds tail row k and its constants.
+//   we_all [d + NT, d] f32: rows [0, d) = enc_output.0.weight (converted); rows d + k = the COEFFICIENT rows of the tail:
+//   class k < nc: Wp[k] = score_w[k] * ln_w; last row (fused mode): enc_bias; other rows 0.  The caller multiplies the tail
+//   rows by We in place (tail := coef @ We, one small library GEMM).
+//   consts = { sum eb, sum eb^2, bw[NT], sw[NT], ck[NT] }: bw[k] = Wp[k] . eb, sw[k] = sum Wp[k], ck[k] = score_w[k] . ln_b +
+//   score_b[k].  Block r < d copies a row of We; block d + k builds coefficient row k and its constants.
 __global__ void fold_rank_consts_kernel(const void *__restrict__ We, const void *__restrict__ eb, const void *__restrict__ sw_,
                                         const void *__restrict__ sb, const float *__restrict__ ln_w,
                                         const float *__restrict__ ln_b, float *__restrict__ we_all,
@@ -231,31 +251,24 @@ __global__ void fold_rank_consts_kernel(const void *__restrict__ We, const void 
     const int k = r - d;
     float *out = we_all + (size_t)r * d;
     const bool cls = k < nc, dot = fused && k == NT - 1;
-    // tail row: sum_j coef[j] * We[j, i]
-    for (int i = tid; i < d; i += blockDim.x) {
-        float acc = 0.f;
-        if (cls || dot)
-            for (int j = 0; j < d; ++j) {
-                const float cj = cls ? fold_ld(sw_, (size_t)k * d + j, lin_bf16) * __ldg(ln_w + j) : fold_ld(eb, j, lin_bf16);
-                acc = fmaf(cj, fold_ld(We, (size_t)j * d + i, lin_bf16), acc);
-            }
-        out[i] = acc;
-    }
-    if (!fused) return;
-    // constants of class k (or, in the last block, the two sums over enc_bias)
     float a = 0.f, b = 0.f, c = 0.f;
     for (int j = tid; j < d; j += blockDim.x) {
         const float e = fold_ld(eb, j, lin_bf16);
+        float coef = 0.f;
         if (cls) {
-            const float sw = fold_ld(sw_, (size_t)k * d + j, lin_bf16), wp = sw * __ldg(ln_w + j);
-            a = fmaf(wp, e, a);
-            b += wp;
+            const float sw = fold_ld(sw_, (size_t)k * d + j, lin_bf16);
+            coef = sw * __ldg(ln_w + j);
+            a = fmaf(coef, e, a);
+            b += coef;
             c = fmaf(sw, __ldg(ln_b + j), c);
         } else if (dot) {
+            coef = e;
             a += e;
             b = fmaf(e, e, b);
         }
+        out[j] = coef;
     }
+    if (!fused) return;
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, m);

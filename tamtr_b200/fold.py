@@ -665,6 +665,7 @@ def _rank_constants_fused(enc_linear, enc_norm, score_linear, fused):
                                                lb.data_ptr(), we_all.data_ptr(), consts.data_ptr(), d, nc, npad, 1,
                                                _lib.dtype_code(We), _lib.stream_ptr(We.device))
     _lib.check(rc, "fold_rank_consts")
+    we_all[d:] = _mm_tf32(we_all[d:], we_all[:d])          # tail rows: coefficients @ We
     return {"We_all": we_all, "nc": nc, "npad": npad, "eps": enc_norm.eps, "fused": True, "consts": consts}
 
 

@@ -242,17 +242,23 @@ def test_fused_glue_matches_torch_path(cuda_lib, train, monkeypatch):
         assert rel_l2(p[1].running_mean, r[1].running_mean) < 1e-5
         assert rel_l2(p[1].running_var, r[1].running_var) < 1e-5
         assert int(p[1].num_batches_tracked) == int(r[1].num_batches_tracked)
-    loss_f, g_f = _step(m, xs, text)
+    # gradients through a probe on the projected values and the selected rows themselves (a whole-head loss would also
+    # compare which near-tied tokens the two runs happened to select)
+    def grads(model, tokens):
+        for p in model.parameters():
+            p.grad = None
+        gen = torch.Generator(device="cuda").manual_seed(21)
+        loss = sum((v.float() * torch.randn(v.shape, generator=gen, device="cuda")).sum() for v in tokens.values)
+        r = tokens.rows(idx)
+        loss = loss + (r.float() * torch.randn(r.shape, generator=gen, device="cuda")).sum() * 50.0
+        loss.backward()
+        return {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+    g_f = grads(m, tok)
     monkeypatch.setattr(fold, "FUSED_GLUE", False)
-    loss_u, g_u = _step(ref, xs, text)
-    assert abs(loss_f.item() - loss_u.item()) < 2e-3 * abs(loss_u.item())
-    assert set(g_f) == set(g_u)
+    g_u = grads(ref, tok_r)
+    assert set(g_f) == set(g_u) and any(k.startswith("input_proj.0.0") for k in g_f)
     for k in sorted(g_f):
-        if k.startswith("input_proj") or "value_proj" in k or k.startswith("enc_output"):
-            # (the two runs differ by the order of the samplers' bf16 atomic adds; the bias gradients -- column sums over
-            #  all tokens with heavy cancellation -- feel it most)
-            tol = 5e-2 if k.endswith("value_proj.bias") else 2e-2
-            assert rel_l2(g_f[k], g_u[k]) < tol, (k, rel_l2(g_f[k], g_u[k]))
+        assert rel_l2(g_f[k], g_u[k]) < 5e-3, (k, rel_l2(g_f[k], g_u[k]))
 
 
 def test_rank_constants_kernel_matches_torch(cuda_lib):
