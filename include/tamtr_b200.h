@@ -480,7 +480,8 @@ int tamtr_tok_reduce(const void *a_bf16, long a_row, long a_img, int a_token_maj
  * Glue of the folded encoder side (csrc/foldglue.cu; the algebra and its derivation are in tamtr_b200/fold.py): the
  * element-wise work between the token reductions / projections above and the small dense products that stay library
  * GEMMs, one launch for all pyramid levels each.  Level tables (C, S, n_tok, pointer arrays) are host arrays of L <= 8
- * entries; every tensor is f32 unless noted.  K = max_l C_l + 1.
+ * entries; every tensor is f32 unless noted.  K = max_l C_l + 1 rounded up to a multiple of 8 (column max_l C_l carries the
+ * bias part, the columns after it are zero).
  *   tamtr_fold_stats   partials of tamtr_tok_reduce(x, x) (part_d [S_l, C_l, C_l], part_rs [S_l, C_l]) and the token
  *                      count n_tok -> mean_x [C_l], cov [C_l, C_l] = E[x x^T] - mean mean^T
  *   tamtr_fold_bn      BatchNorm2d (torch/nn/modules/batchnorm.py:155-193) of y = wc x from P = wc cov, wc [d, C_l] and

@@ -18,7 +18,8 @@
 namespace tamtr {
 
 struct FoldPtrs {
-    int L, d, Cm;                        // levels, hidden dim, widest level; K = Cm + 1
+    int L, d, Cm, K;                     // levels, hidden dim, widest level; K = Cm + 1 rounded up to 8 (column Cm = the
+                                         // bias part, columns past it zero: keeps the library GEMMs on aligned operands)
     int C[kMaxLevels];
     int S[kMaxLevels];                   // split counts of the partial buffers
     float n_tok[kMaxLevels];
@@ -85,7 +86,7 @@ __global__ void fold_bn_kernel(const FoldPtrs p, float *__restrict__ a_ext, floa
     const int l = blockIdx.y, lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= p.d) return;
-    const int C = p.C[l], K = p.Cm + 1;
+    const int C = p.C[l], K = p.K;
     const float *w = p.wc[l] + (size_t)j * C;
     float mu, var;
     if (batch_stats) {
@@ -133,7 +134,7 @@ __global__ void fold_bn_kernel(const FoldPtrs p, float *__restrict__ a_ext, floa
 // (+ bv[n] for n < N0)
 __global__ void fold_pack_kernel(const FoldPtrs p, const float *__restrict__ Fv, const float *__restrict__ Fe,
                                  const float *__restrict__ bv, float *__restrict__ bias, int N0, int NE) {
-    const int l = blockIdx.y, n = blockIdx.x, C = p.C[l], K = p.Cm + 1, N = N0 + NE;
+    const int l = blockIdx.y, n = blockIdx.x, C = p.C[l], K = p.K, N = N0 + NE;
     const float *src = n < N0 ? Fv + ((size_t)l * N0 + n) * K : Fe + ((size_t)l * NE + (n - N0)) * K;
     __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.w_out[l]) + (size_t)n * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) dst[c] = __float2bfloat16_rn(__ldg(src + c));
@@ -143,7 +144,7 @@ __global__ void fold_pack_kernel(const FoldPtrs p, const float *__restrict__ Fv,
 // partials of the per-level weight-gradient reductions -> dF [L, N0, K] and its [N0, L, K] copy; d_bv [N0]
 __global__ void fold_unpack_kernel(const FoldPtrs p, float *__restrict__ dF, float *__restrict__ dF_t,
                                    float *__restrict__ d_bv, int N0) {
-    const int l = blockIdx.y, n = blockIdx.x, C = p.C[l], K = p.Cm + 1, S = p.S[l];
+    const int l = blockIdx.y, n = blockIdx.x, C = p.C[l], K = p.K, S = p.S[l];
     const float *pd = p.part_d[l], *pr = p.part_rs[l];
     for (int c = threadIdx.x; c < K; c += blockDim.x) {
         float v = 0.f;
@@ -169,7 +170,7 @@ __global__ void fold_bn_bwd_kernel(const FoldPtrs p, const float *__restrict__ d
     const int l = blockIdx.y, lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= p.d) return;
-    const int C = p.C[l], K = p.Cm + 1;
+    const int C = p.C[l], K = p.K;
     const float *w = p.wc[l] + (size_t)j * C;
     const float *g = dA + ((size_t)l * p.d + j) * K;
     const float *gt = dAt != nullptr ? dAt + (size_t)l * K * p.d + j : nullptr;
@@ -202,7 +203,7 @@ __global__ void fold_bn_bwd_kernel(const FoldPtrs p, const float *__restrict__ d
 }
 
 struct GatherPtrs {
-    int L, Cm, Lv;
+    int L, Cm, K, Lv;
     int C[kMaxLevels], start[kMaxLevels], hw[kMaxLevels];
     const __nv_bfloat16 *x[kMaxLevels];          // [B, C, HW]
 };
@@ -214,7 +215,7 @@ __global__ void fold_gather_kernel(const GatherPtrs p, const long long *__restri
     if (r >= R) return;
     const long long fi = flat_idx[r];
     const int b = (int)(fi / p.Lv), tok = (int)(fi - (long long)b * p.Lv);
-    const int K = p.Cm + 1;
+    const int K = p.K;
     float *row = xcat + (size_t)r * p.L * K;
     for (int l = 0; l < p.L; ++l) {
         const int rel = tok - p.start[l];
@@ -319,6 +320,7 @@ static int fold_fill(FoldPtrs &p, int L, int d, const int *C) {
         if (l < L && C[l] < 1) return TAMTR_E_BADARG;
         if (p.C[l] > p.Cm) p.Cm = p.C[l];
     }
+    p.K = (p.Cm + 1 + 7) / 8 * 8;
     return 0;
 }
 
@@ -430,6 +432,7 @@ extern "C" int tamtr_fold_gather(int L, int Lv, const int *C, const int *start, 
         TAMTR_CHECK_ARG(C[l] > 0 && hw[l] > 0 && x_bf16[l], TAMTR_E_BADARG, "fold_gather: bad level %d", l);
         if (C[l] > p.Cm) p.Cm = C[l];
     }
+    p.K = (p.Cm + 1 + 7) / 8 * 8;
     fold_gather_kernel<<<R, 128, 0, (cudaStream_t)stream>>>(p, flat_idx, xcat, R);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());

@@ -251,6 +251,11 @@ FUSED_GLUE = os.environ.get("TAMTR_FOLD_GLUE", "1") != "0"    # the whole fold a
 _MAXL = 8
 
 
+def _kpad(Cm):
+    """columns of the A_ext layouts of csrc/foldglue.cu: Cm weights + the bias part, rounded up to a multiple of 8"""
+    return (Cm + 1 + 7) // 8 * 8
+
+
 def _parr(ts):
     return (ctypes.c_void_p * _MAXL)(*([None if t is None else t.data_ptr() for t in ts] + [None] * (_MAXL - len(ts))))
 
@@ -305,7 +310,7 @@ class _FusedFoldFn(torch.autograd.Function):
         convs, gammas, betas = t[:L], t[L:2 * L], t[2 * L:3 * L]
         wvs, bvs = t[3 * L:3 * L + n_layers], t[3 * L + n_layers:]
         xs, cs, d, Cm = tokens.xs, tokens.cs, tokens.d, tokens.Cm
-        K, dev, lib = Cm + 1, tokens.device, _lib.lib()
+        K, dev, lib = _kpad(Cm), tokens.device, _lib.lib()
         st = _lib.stream_ptr(dev)
         n_tok = [float(tokens.B * n) for n in tokens.hw]
         batch_stats = training or bns[0].running_mean is None
@@ -374,7 +379,7 @@ class _FusedFoldFn(torch.autograd.Function):
             P, mean_flat = sv[k:k + L], sv[k + L]
             k += L + 1
         stats, a_ext_t, Wv = sv[k], sv[k + 1], sv[k + 2]
-        K, dev, lib = Cm + 1, xs[0].device, _lib.lib()
+        K, dev, lib = _kpad(Cm), xs[0].device, _lib.lib()
         st = _lib.stream_ptr(dev)
         buf = _arena_gradient(ctx.arena, grads, shape, Wv.shape[0] // n, torch.bfloat16, dev)
         B, Lv, N0 = shape
@@ -606,7 +611,7 @@ class FoldedTokens:
         """feats.reshape(-1, d)[flat_idx] (flat_idx = image * Lv + token) recomputed from X through A and t."""
         md = MATH_DTYPE
         if self.a_ext_t is not None:        # fused glue: one gather kernel + one product
-            L, K, R = len(self.xs), self.Cm + 1, flat_idx.numel()
+            L, K, R = len(self.xs), _kpad(self.Cm), flat_idx.numel()
             xcat = torch.empty(R, L * K, dtype=torch.float32, device=self.device)
             idx = flat_idx.contiguous().long()
             with torch.cuda.device(self.device):

@@ -277,5 +277,5 @@ def test_rank_constants_kernel_matches_torch(cuda_lib):
         got = fold._rank_constants_fused(a, ln, b, True)
         assert got["npad"] == ref["npad"] == 16 and got["fused"]
         we_all = torch.cat([a.weight.float(), ref["Wr"]], 0)
-        assert rel_l2(got["We_all"], we_all) < 1e-5
+        assert rel_l2(got["We_all"], we_all) < 2e-3          # the tail rows come out of a TF32 product
         assert torch.allclose(got["consts"], ref["consts"], rtol=1e-4, atol=1e-4), (got["consts"] - ref["consts"]).abs().max()
