@@ -114,6 +114,8 @@ struct PjGeom {
     int B, HW, C, n_kb;            // level geometry; n_kb = C / 64
     int w_stages;                  // depth of the W ring = kPjSlots - MT * n_kb - 2 * stg_depth (capped)
     int stg_depth;                 // staging tiles per epilogue group (2 when the A block leaves room)
+    int n_rot;                     // the first n_rot column steps (the stored value columns) are walked in a per-CTA rotated
+                                   // order, so that the CTAs do not all pull the same W tile out of L2 at the same time
     int pairs_per_img, n_pairs;    // CTA tiles of MT * 128 tokens
     int N0, N1, NT, n_steps;       // bf16 columns of out0 / out1, fp32 tail columns, ceil((N0 + N1 + NT) / 128)
     long raw_row, raw_img;         // strides (elements) of the fp32 tail tensor
@@ -160,6 +162,7 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = bars.tmem_base;
     constexpr int tile_tok = MT * 128;
+    const int n0 = g.n_rot > 0 ? (int)(blockIdx.x % (unsigned)g.n_rot) : 0;
 
     if (warp == 0) {
         // ===== TMA producer (whole warp walks the loops, one elected lane issues)
@@ -186,7 +189,8 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         }
             }
             __syncwarp();
-            for (int n = 0; n < g.n_steps; ++n)
+            for (int ns = 0; ns < g.n_steps; ++ns) {
+                const int n = ns < g.n_rot ? (ns + n0 < g.n_rot ? ns + n0 : ns + n0 - g.n_rot) : ns;
                 for (int kb = 0; kb < g.n_kb; ++kb) {
                     mbar_wait(&bars.w_empty[ws], wph ^ 1);
                     if (tk_elect()) {
@@ -196,6 +200,7 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     __syncwarp();
                     if (++ws == (uint32_t)g.w_stages) { ws = 0; wph ^= 1; }
                 }
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: D[128 tokens, 128 columns] += A (MN-major) x W (K-major), K = 16 per instruction
@@ -255,7 +260,8 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x) {
             const int b = p / g.pairs_per_img, tok0 = (p - b * g.pairs_per_img) * tile_tok + mt * 128;
             float s1 = 0.f, s2 = 0.f;                                        // sum / sum of squares of the token's E row
-            for (int n = 0; n < g.n_steps; ++n, ++ai) {
+            for (int ns = 0; ns < g.n_steps; ++ns, ++ai) {
+                const int n = ns < g.n_rot ? (ns + n0 < g.n_rot ? ns + n0 : ns + n0 - g.n_rot) : ns;
                 const uint32_t as = ai & 1;
                 mbar_wait(&bars.acc_full[as], (ai >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -652,6 +658,7 @@ static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float 
     g.B = B; g.HW = HW; g.C = C; g.n_kb = C / 64;
     int MT = (2 * g.n_kb <= 8) ? 2 : 1;
     if (HW <= 128) MT = 1;
+    if (g.n_kb > 2 && !getenv("TAMTR_TOK_MT2")) MT = 1;      // C > 128: a deeper W ring beats sharing W between two token blocks
     g.stg_depth = (kPjSlots - MT * g.n_kb - 4 >= 4) ? 2 : 1;
     if (getenv("TAMTR_TOK_STG1")) g.stg_depth = 1;      // (experiment switch)
     g.w_stages = kPjSlots - MT * g.n_kb - 2 * g.stg_depth;
@@ -661,6 +668,7 @@ static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float 
     g.N0 = N0; g.N1 = N1; g.NT = NT;
     g.n_steps = (Nall + 127) / 128;
     g.raw_row = raw_row; g.raw_img = raw_img;
+    g.n_rot = (N0 % 128 == 0 && !getenv("TAMTR_TOK_NOROT")) ? N0 / 128 : 0;
     g.rank_mode = rk != nullptr ? 1 : 0;
     g.nc = rk != nullptr ? rk->nc : 0;
     g.rank_img = rk != nullptr ? rk->rank_img : 0;
