@@ -447,6 +447,8 @@ int tamtr_adamw_flat(float *param, const float *grad, float *exp_avg, float *exp
  *     w     [N0 + N1 + NT, C] bf16,  bias [N0 + N1 + NT] f32
  *     out0  bf16, columns [0, N0): element (b, tok, n) at out0 + b * out0_img + tok * out0_row + n  (strides in elements;
  *           the caller passes the level's first token of a [B, Lv, N0] tensor), N0 % 64 == 0
+ *     zero0 NULL, or a second bf16 tensor laid out like out0: the same (token, column) range is filled with zeros (the
+ *           gradient arena the samplers' backward accumulates into: saves the 1.65 GB memset node of the training step)
  *     out1  bf16, columns [N0, N0 + N1) likewise (NULL when N1 == 0), N1 % 64 == 0
  *     raw   f32, the last NT columns (NT % 4 == 0; NULL when NT == 0)
  *   tamtr_tok_reduce:   D[m, c] = sum_{b, tok} a[m; b, tok] * x[b, c, tok],   rs[m] = sum_{b, tok} a[m; b, tok]
@@ -457,9 +459,9 @@ int tamtr_adamw_flat(float *param, const float *grad, float *exp_avg, float *exp
  *     order (deterministic); the caller adds them.
  * Both only enqueue one kernel; CUDA-graph capturable. */
 int tamtr_tok_project_supported(int B, int C, int HW, int N0, int N1, int NT);
-int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row, long out0_img,
-                      void *out1, long out1_row, long out1_img, float *raw, long raw_row, long raw_img, int B, int C, int HW,
-                      int N0, int N1, int NT, void *stream);
+int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, void *zero0, long out0_row,
+                      long out0_img, void *out1, long out1_row, long out1_img, float *raw, long raw_row, long raw_img, int B,
+                      int C, int HW, int N0, int N1, int NT, void *stream);
 /* tamtr_tok_project with the query-selection ranking (head.py:1229-1237) finished in its epilogue: the N1 = d columns are
  * E = enc_output.0(feats) without its bias, the NT tail columns are E @ (enc_score_head.weight * ln.weight)^T for the nc
  * classes (columns [0, nc)) and E . enc_bias (column NT - 1); neither is stored.  Per token:
@@ -468,8 +470,8 @@ int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const float *bias,
  *   rank_consts = { sum enc_bias, sum enc_bias^2, bw[NT], sw[NT], ck[NT] } f32 (the constants of tamtr_rank_tokens)
  *   rank f32: element (b, tok) at rank + b * rank_img + tok; valid u8 [HW] (the level's slice of the anchor validity mask)
  * nc < NT <= 64. */
-int tamtr_tok_project_rank(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row,
-                           long out0_img, float *rank, long rank_img, const uint8_t *valid, const float *rank_consts, int nc,
+int tamtr_tok_project_rank(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, void *zero0,
+                           long out0_row, long out0_img, float *rank, long rank_img, const uint8_t *valid, const float *rank_consts, int nc,
                            float eps, int B, int C, int HW, int N0, int N1, int NT, void *stream);
 int tamtr_tok_reduce_supported(int B, int C, int HW, int M, int a_token_major);
 int tamtr_tok_reduce_splits(int B, int C, int HW, int M, int a_token_major);

@@ -88,8 +88,8 @@ _SIGNATURES = {
     "tamtr_adamw_flat": (ctypes.c_int, [_fp, _fp, _fp, _fp, ctypes.c_longlong, _vp, _fp, _fp]
                          + [ctypes.c_float] * 6 + [_vp]),
     "tamtr_tok_project_supported": (ctypes.c_int, [_i] * 6),
-    "tamtr_tok_project": (ctypes.c_int, [_vp, _vp, _fp, _vp, _l, _l, _vp, _l, _l, _fp, _l, _l] + [_i] * 6 + [_vp]),
-    "tamtr_tok_project_rank": (ctypes.c_int, [_vp, _vp, _fp, _vp, _l, _l, _fp, _l, _vp, _fp, _i, ctypes.c_float] + [_i] * 6 + [_vp]),
+    "tamtr_tok_project": (ctypes.c_int, [_vp, _vp, _fp, _vp, _vp, _l, _l, _vp, _l, _l, _fp, _l, _l] + [_i] * 6 + [_vp]),
+    "tamtr_tok_project_rank": (ctypes.c_int, [_vp, _vp, _fp, _vp, _vp, _l, _l, _fp, _l, _vp, _fp, _i, ctypes.c_float] + [_i] * 6 + [_vp]),
     "tamtr_fold_rank_consts": (ctypes.c_int, [_vp] * 4 + [_fp] * 4 + [_i] * 5 + [_vp]),
     "tamtr_fold_stats": (ctypes.c_int, [_i] + [_vp] * 7 + [_vp]),
     "tamtr_fold_bn": (ctypes.c_int, [_i, _i] + [_vp] * 12 + [_i, _i] + [_fp] * 3 + [_vp]),

@@ -32,8 +32,8 @@ __device__ __forceinline__ void tk_tma_store_3d(const CUtensorMap *map, const vo
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tk_tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // K-major operand, SWIZZLE_128B: rows of 64 elements (128 B), 8-row atoms every 1024 B (SBO); a K step of 16 = +32 B
 __device__ __forceinline__ uint64_t tk_desc_k(uint32_t addr) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -122,6 +122,7 @@ struct PjGeom {
     // ranking mode (rank_mode = 1): the N1 columns are the ranking embedding E and the tail its class scores; neither is
     // stored -- the epilogue reduces them to one score per token (see tok_project_kernel)
     int rank_mode, nc;
+    int zero_fill;                 // also write zeros over the same (token, value column) range of a second tensor (map_z)
     long rank_img;
     float eps, inv_d;
 };
@@ -130,7 +131,8 @@ template <int MT>
 __global__ void __launch_bounds__(kTkThreads, 1)
 tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                    const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
-                   const float *__restrict__ bias, float *__restrict__ raw, const uint8_t *__restrict__ valid,
+                   const __grid_constant__ CUtensorMap map_z, const float *__restrict__ bias, float *__restrict__ raw,
+                   const uint8_t *__restrict__ valid,
                    const float *__restrict__ rconst, float *__restrict__ rank_out, const PjGeom g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -141,10 +143,15 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     PjBars &bars = *reinterpret_cast<PjBars *>(sEnd);
     float *s_rc = reinterpret_cast<float *>(sEnd + 256);                   // ranking constants: 2 + 3 * NT floats
     float2 *s_part = reinterpret_cast<float2 *>(s_rc + 2 + 3 * 64);        // MT == 1: partial row moments of the other group
+    uint8_t *s_zero = sEnd + 4096;                                         // 32 rows x 128 B of zeros (zero_fill)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (g.rank_mode)
         for (int i = threadIdx.x; i < 2 + 3 * g.NT; i += kTkThreads) s_rc[i] = __ldg(rconst + i);
+    if (g.zero_fill) {
+        for (int i = threadIdx.x; i < 4096 / 16; i += kTkThreads) reinterpret_cast<uint4 *>(s_zero)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (threadIdx.x == 0) {
         mbar_init(&bars.a_full, 1);
         mbar_init(&bars.a_empty, 1);
@@ -376,9 +383,18 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                    if (leader) {
-                        if (col0 < g.N0) tk_tma_store_3d(&map_o0, stage, col0, tok0, b);
-                        else tk_tma_store_3d(&map_o1, stage, col0 - g.N0, tok0, b);
+                    if (leader) {       // one bulk group per chunk: the data tile (+ four 32-row zero tiles over the same range)
+                        if (col0 < g.N0) {
+                            tk_tma_store_3d(&map_o0, stage, col0, tok0, b);
+                            if (g.zero_fill) {
+#pragma unroll
+                                for (int r4 = 0; r4 < 4; ++r4)
+                                    if (tok0 + 32 * r4 < g.HW) tk_tma_store_3d(&map_z, s_zero, col0, tok0 + 32 * r4, b);
+                            }
+                        } else {
+                            tk_tma_store_3d(&map_o1, stage, col0 - g.N0, tok0, b);
+                        }
+                        tk_tma_commit();
                     }
                 }
                 if (MT == 1 && g.rank_mode && n == n_tail && grp != tail_grp) {
@@ -610,7 +626,7 @@ struct PjRank {                  // ranking mode (tamtr_tok_project_rank)
     float eps;
 };
 
-static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row,
+static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, void *zero0, long out0_row,
                             long out0_img, void *out1, long out1_row, long out1_img, float *raw, long raw_row,
                             long raw_img, const PjRank *rk, int B, int C, int HW, int N0, int N1, int NT, void *stream) {
     TAMTR_CHECK_ARG(x_bf16 && w_bf16 && bias && out0, TAMTR_E_BADARG, "tok_project: null pointer");
@@ -629,7 +645,8 @@ static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float 
     TAMTR_CHECK_ARG(out0_row % 8 == 0 && out0_img % 8 == 0 && out1_row % 8 == 0 && out1_img % 8 == 0 && raw_row % 4 == 0 &&
                     raw_img % 4 == 0, TAMTR_E_BADARG, "tok_project: output strides must keep 16-byte alignment");
     const int Nall = N0 + N1 + NT;
-    CUtensorMap map_x, map_w, map_o0, map_o1;
+    TAMTR_CHECK_ARG(((uintptr_t)zero0 & 15) == 0, TAMTR_E_BADARG, "tok_project: zero0 must be 16-byte aligned");
+    CUtensorMap map_x, map_w, map_o0, map_o1, map_z;
     {
         const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)C * HW * 2};
@@ -654,7 +671,18 @@ static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float 
                                  "tok_project(out)");
         if (rc) return rc;
     }
+    {       // the tensor zero-filled alongside out0 (same layout; plain 32-row boxes of the shared zero tile)
+        EncodeTiledFn encode = get_encode();
+        const cuuint64_t dims[3] = {(cuuint64_t)N0, (cuuint64_t)HW, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)out0_row * 2, (cuuint64_t)out0_img * 2};
+        const cuuint32_t box[3] = {64, 32, 1}, estr[3] = {1, 1, 1};
+        const CUresult cr = encode(&map_z, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, zero0 != nullptr ? zero0 : out0, dims, strides, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TAMTR_CHECK_ARG(cr == CUDA_SUCCESS, TAMTR_E_BADARG, "tok_project: zero-fill tensor map failed (%d)", (int)cr);
+    }
     PjGeom g;
+    g.zero_fill = zero0 != nullptr ? 1 : 0;
     g.B = B; g.HW = HW; g.C = C; g.n_kb = C / 64;
     int MT = (2 * g.n_kb <= 8) ? 2 : 1;
     if (HW <= 128) MT = 1;
@@ -681,36 +709,36 @@ static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float 
     TAMTR_CHECK_ARG(tk_attr_once((const void *)tok_project_kernel<1>, attr1) &&
                     tk_attr_once((const void *)tok_project_kernel<2>, attr2), TAMTR_E_NODEVICE,
                     "tok_project: cannot raise the dynamic shared memory limit");
-    const size_t smem = (size_t)kPjSlots * kTkSlot + 4096 + 1024;      // slots, barriers + ranking scratch, alignment
+    const size_t smem = (size_t)kPjSlots * kTkSlot + 4096 + 4096 + 1024;      // slots, barriers + ranking scratch, zero tile, alignment
     const int n_sm = ::tamtr::sm_count();
     const int grid = g.n_pairs < n_sm ? g.n_pairs : n_sm;
     cudaStream_t st = (cudaStream_t)stream;
     {
         KernelTimer timer(K_TOK_PROJECT, st);
         if (MT == 2)
-            tok_project_kernel<2><<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, bias, raw, valid, rconst, rank_out, g);
+            tok_project_kernel<2><<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, map_z, bias, raw, valid, rconst, rank_out, g);
         else
-            tok_project_kernel<1><<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, bias, raw, valid, rconst, rank_out, g);
+            tok_project_kernel<1><<<grid, kTkThreads, smem, st>>>(map_x, map_w, map_o0, map_o1, map_z, bias, raw, valid, rconst, rank_out, g);
     }
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-extern "C" int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row,
-                                 long out0_img, void *out1, long out1_row, long out1_img, float *raw, long raw_row,
-                                 long raw_img, int B, int C, int HW, int N0, int N1, int NT, void *stream) {
-    return tok_project_impl(x_bf16, w_bf16, bias, out0, out0_row, out0_img, out1, out1_row, out1_img, raw, raw_row, raw_img,
-                            nullptr, B, C, HW, N0, N1, NT, stream);
+extern "C" int tamtr_tok_project(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, void *zero0,
+                                 long out0_row, long out0_img, void *out1, long out1_row, long out1_img, float *raw,
+                                 long raw_row, long raw_img, int B, int C, int HW, int N0, int N1, int NT, void *stream) {
+    return tok_project_impl(x_bf16, w_bf16, bias, out0, zero0, out0_row, out0_img, out1, out1_row, out1_img, raw, raw_row,
+                            raw_img, nullptr, B, C, HW, N0, N1, NT, stream);
 }
 
-extern "C" int tamtr_tok_project_rank(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, long out0_row,
-                                      long out0_img, float *rank, long rank_img, const uint8_t *valid,
+extern "C" int tamtr_tok_project_rank(const void *x_bf16, const void *w_bf16, const float *bias, void *out0, void *zero0,
+                                      long out0_row, long out0_img, float *rank, long rank_img, const uint8_t *valid,
                                       const float *rank_consts, int nc, float eps, int B, int C, int HW, int N0, int N1,
                                       int NT, void *stream) {
     const PjRank rk = {rank, rank_img, valid, rank_consts, nc, eps};
-    return tok_project_impl(x_bf16, w_bf16, bias, out0, out0_row, out0_img, nullptr, 0, 0, nullptr, 0, 0, &rk, B, C, HW, N0, N1,
-                            NT, stream);
+    return tok_project_impl(x_bf16, w_bf16, bias, out0, zero0, out0_row, out0_img, nullptr, 0, 0, nullptr, 0, 0, &rk, B, C, HW, N0,
+                            N1, NT, stream);
 }
 
 static int rd_geometry(RdGeom &g, int B, int C, int HW, int M, int a_mn) {

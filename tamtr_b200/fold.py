@@ -69,10 +69,11 @@ def _kernel_reduce(a, a_row, a_img, token_major, x, M):
     return part_d.sum(0), part_rs.sum(0)
 
 
-def _kernel_project(x, w, bias, out0, out1, raw, start, N0, N1, NT, rank=None):
+def _kernel_project(x, w, bias, out0, out1, raw, start, N0, N1, NT, rank=None, zero=None):
     """out0[:, start:start+HW] = x^T w[:N0]^T + bias[:N0] (bf16).  The N1 + NT remaining columns are the ranking branch:
     stored (out1 bf16, raw fp32) when `rank` is None, else reduced in the kernel's epilogue to one score per token,
-    rank = (scores [B, Lv] fp32, valid_u8 [Lv], consts, nc, eps)  (tamtr_tok_project / tamtr_tok_project_rank)."""
+    rank = (scores [B, Lv] fp32, valid_u8 [Lv], consts, nc, eps)  (tamtr_tok_project / tamtr_tok_project_rank).
+    `zero`: a second tensor like out0 whose same rows are filled with zeros (the samplers' gradient arena)."""
     _lib.require_cuda(x, w, bias, out0)
     if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or bias.dtype != torch.float32:
         raise RuntimeError("tamtr_b200: tok_project takes bf16 operands and an fp32 bias")
@@ -80,18 +81,21 @@ def _kernel_project(x, w, bias, out0, out1, raw, start, N0, N1, NT, rank=None):
     HW = x.shape[2] * x.shape[3]
     Lv = out0.shape[1]
     es0 = out0.element_size()
+    if zero is not None and (zero.shape != out0.shape or zero.dtype != out0.dtype or not zero.is_contiguous()):
+        raise RuntimeError("tamtr_b200: the zero-filled tensor must be laid out like the projected values")
+    zp = None if zero is None else zero.data_ptr() + start * N0 * es0
     with torch.cuda.device(x.device):
         if rank is None:
             rc = _lib.lib().tamtr_tok_project(
                 x.data_ptr(), w.data_ptr(), bias.data_ptr(),
-                out0.data_ptr() + start * N0 * es0, N0, Lv * N0,
+                out0.data_ptr() + start * N0 * es0, zp, N0, Lv * N0,
                 (out1.data_ptr() + start * N1 * out1.element_size()) if N1 else None, N1, Lv * N1,
                 (raw.data_ptr() + start * NT * 4) if NT else None, NT, Lv * NT,
                 B, C, HW, N0, N1, NT, _lib.stream_ptr(x.device))
         else:
             scores, valid_u8, consts, nc, eps = rank
             rc = _lib.lib().tamtr_tok_project_rank(
-                x.data_ptr(), w.data_ptr(), bias.data_ptr(), out0.data_ptr() + start * N0 * es0, N0, Lv * N0,
+                x.data_ptr(), w.data_ptr(), bias.data_ptr(), out0.data_ptr() + start * N0 * es0, zp, N0, Lv * N0,
                 scores.data_ptr() + start * 4, Lv, valid_u8.data_ptr() + start, consts.data_ptr(), int(nc), float(eps),
                 B, C, HW, N0, N1, NT, _lib.stream_ptr(x.device))
     _lib.check(rc, "tok_project")
@@ -208,7 +212,8 @@ class _TokProjectFn(torch.autograd.Function):
         bias = bias.to(acc).contiguous()
         Wb = W[:, :, :Cm].to(lp)
         ws = [Wb[l, :, :x.shape[1]].contiguous() for l, x in enumerate(xs)]
-        values = _project_levels(tokens, xs, ws, bias, N0, N1, NT, n_layers, n_heads)
+        values = _project_levels(tokens, xs, ws, bias, N0, N1, NT, n_layers, n_heads,
+                                 None if isinstance(ctx, _NoCtx) else arena)
         value_all = tokens._value_all
         d = N0 // n_layers
         ctx.save_for_backward(*xs, *[w[:N0] for w in ws])
@@ -245,6 +250,9 @@ class _TokProjectFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------- fused glue (csrc/foldglue.cu)
+# Gradient arena zeroed by tamtr_tok_project's own stores instead of a memset node in the backward.  Measured: the projection
+# gets slower by exactly the memset's 265 us (its extra 1.65 GB of stores are HBM-write-bound either way), so it is off.
+ZERO_FILL_IN_PROJECTION = os.environ.get("TAMTR_FOLD_ZERO", "0") != "0"
 FUSED_GLUE = os.environ.get("TAMTR_FOLD_GLUE", "1") != "0"    # the whole fold as ONE autograd node over a handful of
                                                              # kernels (False: the differentiable torch ops)
 
@@ -356,7 +364,8 @@ class _FusedFoldFn(torch.autograd.Function):
             bias = torch.empty(L, N0 + NE, dtype=torch.float32, device=dev)
             _lib.check(lib.tamtr_fold_pack(L, C_arr, Fv.data_ptr(), Fe.data_ptr(), bv.data_ptr(), _parr(w_out),
                                            bias.data_ptr(), N0, NE, st), "fold_pack")
-        values = _project_levels(tokens, xs, w_out, bias, N0, tokens.d, NE - tokens.d, n_layers, n_heads)
+        values = _project_levels(tokens, xs, w_out, bias, N0, tokens.d, NE - tokens.d, n_layers, n_heads,
+                                 None if isinstance(ctx, _NoCtx) else arena)
         value_all = tokens._value_all
         ctx.save_for_backward(*xs, *convs, *gammas, *[p for p in P if p is not None],
                               *([mean_flat] if batch_stats else []), stats, a_ext_t, Wv)
@@ -454,12 +463,17 @@ def _arena_gradient(arena, grads, shape, d, lp, dev):
     return buf
 
 
-def _project_levels(tokens, xs, ws, bias, N0, N1, NT, n_layers, n_heads):
+def _project_levels(tokens, xs, ws, bias, N0, N1, NT, n_layers, n_heads, arena=None):
     """One tamtr_tok_project(_rank) launch per level into the value tensor of all layers (+ the ranking side outputs on
-    `tokens`); returns the per-layer views [B, Lv, H, Dh]."""
+    `tokens`); returns the per-layer views [B, Lv, H, Dh].  `arena` (a backward will follow): the samplers' gradient buffer
+    is allocated here and zero-filled by the same kernels -- its 1.65 GB memset node per step disappears."""
     B, Lv, dev, lp = tokens.B, tokens.Lv, xs[0].device, tokens.dtype
     acc = torch.float32 if lp == torch.bfloat16 else bias.dtype
     value_all = torch.empty(B, Lv, N0, dtype=lp, device=dev)
+    zero = None
+    if arena is not None and ZERO_FILL_IN_PROJECTION and lp == torch.bfloat16 and arena.grad_dtype in (None, lp) \
+            and arena.buf is None:
+        zero = torch.empty_like(value_all)
     rk = tokens.rank_consts
     if rk["fused"]:        # ranking finished in the projection's epilogue: E and the class scores are never stored
         E = raw = None
@@ -471,7 +485,9 @@ def _project_levels(tokens, xs, ws, bias, N0, N1, NT, n_layers, n_heads):
         scores = rank = None
     for l, x in enumerate(xs):
         _kernel_project(x, ws[l], bias[l], value_all, E, None if raw is None else raw.view(B, Lv, NT), tokens.starts[l],
-                        N0, N1, NT, rank)
+                        N0, N1, NT, rank, zero)
+    if zero is not None:
+        arena.buf = zero
     tokens.E, tokens.raw, tokens.scores, tokens._value_all = E, raw, scores, value_all
     d = N0 // n_layers
     return tuple(value_all[:, :, i * d:(i + 1) * d].view(B, Lv, n_heads, d // n_heads) for i in range(n_layers))

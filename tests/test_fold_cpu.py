@@ -21,11 +21,13 @@ def _reduce(a, a_row, a_img, token_major, x, M):
     return torch.einsum("bmt,bct->mc", A, X), A.sum((0, 2))
 
 
-def _project(x, w, bias, out0, out1, raw, start, N0, N1, NT, rank=None):
+def _project(x, w, bias, out0, out1, raw, start, N0, N1, NT, rank=None, zero=None):
     X = x.flatten(2).transpose(1, 2)                          # [B, HW, C]
     y = X @ w.t() + bias
     hw = X.shape[1]
     out0[:, start:start + hw] = y[..., :N0]
+    if zero is not None:
+        zero[:, start:start + hw] = 0
     if rank is None:
         out1[:, start:start + hw] = y[..., N0:N0 + N1]
         raw[:, start:start + hw] = y[..., N0 + N1:]

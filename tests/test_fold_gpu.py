@@ -71,9 +71,11 @@ def test_tok_project_rank_matches_fp32(cuda_lib, B, C, H, W, N0, N1, nc):
     Lv = pre + HW + post
     valid = (torch.rand(Lv, generator=g) > 0.25).to(torch.uint8).cuda()
     out0 = torch.full((B, Lv, N0), 7.0, dtype=torch.bfloat16, device="cuda")
+    zero = torch.full((B, Lv, N0), 7.0, dtype=torch.bfloat16, device="cuda")      # the gradient arena zeroed alongside
     scores = torch.full((B, Lv), 7.0, device="cuda")
-    fold._kernel_project(x, w, bias, out0, None, None, pre, N0, N1, NT, (scores, valid, consts, nc, 1e-5))
+    fold._kernel_project(x, w, bias, out0, None, None, pre, N0, N1, NT, (scores, valid, consts, nc, 1e-5), zero)
     torch.cuda.synchronize()
+    assert torch.all(zero[:, pre:pre + HW] == 0) and torch.all(zero[:, :pre] == 7.0) and torch.all(zero[:, pre + HW:] == 7.0)
     y = x.float().flatten(2).transpose(1, 2) @ w.float().t() + bias
     assert rel_l2(out0[:, pre:pre + HW], y[..., :N0]) < 4e-3
     ok = valid[pre:pre + HW].bool().view(1, HW, 1)
