@@ -710,6 +710,9 @@ def main():
                 fold[name] = {"us_per_step": us, "launches_per_step": k["launches_per_step"], "algorithmic_bytes": by,
                               "achieved": by / (us * 1e3), "frac": by / (us * 1e3) / peak}
         if fold:
+            fold["traffic_level0"] = {k: traffic.get(k) for k in ("tok_project_rank_l0_dram_bytes_per_launch",
+                                                                  "tok_reduce_wgrad_l0_dram_bytes_per_launch",
+                                                                  "tok_reduce_moments_l0_dram_bytes_per_launch", "tok_source")}
             roof["fold"] = dict(fold, unit="GB/s", peak=peak,
                                 note="tamtr_tok_project_rank / tamtr_tok_reduce, all pyramid levels of one step together "
                                      "(per level: tools/time_tokgemm.py, profiles/tokgemm_r2_notes.txt); timed eager by the "
