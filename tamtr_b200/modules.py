@@ -54,7 +54,7 @@ class MLP(nn.Module):
     def forward(self, x):
         last = self.num_layers - 1
         for i, layer in enumerate(self.layers):
-            x = ops.linear(x, layer) if i == last else F.relu(ops.linear(x, layer))
+            x = ops.linear(x, layer) if i == last else ops.linear_relu(x, layer)
         return x
 
 
@@ -173,7 +173,11 @@ def _add_norm(layer, x, y, drop, norm):
 
 
 def _ffn(layer, tgt):
-    tgt2 = ops.linear(layer.dropout3(layer.act(ops.linear(tgt, layer.linear1))), layer.linear2)
+    if isinstance(layer.act, nn.ReLU):
+        hidden = ops.linear_relu(tgt, layer.linear1)
+    else:
+        hidden = layer.act(ops.linear(tgt, layer.linear1))
+    tgt2 = ops.linear(layer.dropout3(hidden), layer.linear2)
     return _add_norm(layer, tgt, tgt2, layer.dropout4, layer.norm3)
 
 

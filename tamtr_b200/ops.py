@@ -647,6 +647,39 @@ def linear(x, layer):
     return _LinearFn.apply(x, layer.weight, layer.bias)
 
 
+class _LinearReluFn(torch.autograd.Function):
+    """relu(F.linear(x)) with the ReLU in the GEMM epilogue (one launch instead of two; the pre-activation is never
+    stored: the backward masks the incoming gradient with the output's sign)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lp = _lowp(x)
+        x2 = x.reshape(-1, x.shape[-1]).to(lp)
+        w = weight.to(lp)
+        y = torch._addmm_activation(bias.to(lp), x2, w.t(), use_gelu=False)
+        ctx.save_for_backward(x2, w, y)
+        ctx.meta = (x.shape, x.dtype, weight.dtype, bias.dtype)
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x2, w, y = ctx.saved_tensors
+        xshape, xdt, wdt, bdt = ctx.meta
+        g2 = torch.ops.aten.threshold_backward(g.reshape(-1, g.shape[-1]).to(w.dtype), y, 0).contiguous()
+        dx = (g2 @ w).view(xshape).to(xdt) if ctx.needs_input_grad[0] else None
+        dw = (g2.t() @ x2).to(wdt) if ctx.needs_input_grad[1] else None
+        db = col_sum(g2).to(bdt) if ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear_relu(x, layer):
+    """relu(layer(x)) for an nn.Linear (the hidden layers of transformer.py:162-176 MLP and of the decoder FFN, :609-619)."""
+    if not x.is_cuda or layer.bias is None:
+        return torch.relu(linear(x, layer))
+    return _LinearReluFn.apply(x, layer.weight, layer.bias)
+
+
 class _InProjFn(torch.autograd.Function):
     """Packed input projection of nn.MultiheadAttention when query and key share their input (decoder self-attention,
     transformer.py:544-547: q = k = embed + pos, v = embed): two GEMMs, gradients written into ONE [3d, d] / [3d]
