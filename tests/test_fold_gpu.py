@@ -281,3 +281,36 @@ def test_rank_constants_kernel_matches_torch(cuda_lib):
         we_all = torch.cat([a.weight.float(), ref["Wr"]], 0)
         assert rel_l2(got["We_all"], we_all) < 2e-3          # the tail rows come out of a TF32 product
         assert torch.allclose(got["consts"], ref["consts"], rtol=1e-4, atol=1e-4), (got["consts"] - ref["consts"]).abs().max()
+
+
+def test_feature_maps_that_require_a_gradient(cuda_lib):
+    """real training: the backbone's maps require a gradient -> the folded path (differentiable torch glue) hands
+    d(loss)/d(maps) back through the projection, the statistics and the selected rows.  Judged like the parameter
+    gradients: against an fp32 run of the unfolded kernels, the folded bf16 result must not be further away than the
+    unfolded bf16 one (with the seeded weights both sit ~20 % from fp32: d(maps) is what is left after BatchNorm's
+    backward has projected the batch mean and variance directions out)."""
+    import copy
+    m, xs, text = _head()
+    ref = copy.deepcopy(m)
+    ref.folded_projection = False
+    ref32 = copy.deepcopy(ref).float()
+
+    def run(model, maps, autocast=True):
+        maps = [x.detach().clone().requires_grad_() for x in maps]
+        for p in model.parameters():
+            p.grad = None
+        torch.manual_seed(3)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            tok, shapes, hub = model._encode(maps)
+            out = model(maps, text)
+        db, ds, eb, es = out[:4]
+        loss = db.float().square().mean() + 0.1 * ds.float().sigmoid().mean() + eb.float().square().mean() + 0.1 * es.float().sigmoid().mean()
+        loss.backward()
+        return tok, [x.grad.float() for x in maps]
+    tok, gx_f = run(m, xs)
+    assert getattr(tok, "is_folded", False) and tok.a_ext_t is None        # folded, general (torch glue) path
+    _, gx_u = run(ref, xs)
+    _, gx_32 = run(ref32, [x.float() for x in xs], autocast=False)
+    for a, b, c in zip(gx_f, gx_u, gx_32):
+        e_f, e_u = rel_l2(a, c), rel_l2(b, c)
+        assert a.shape == c.shape and e_f < max(1.25 * e_u, 3e-2), (e_f, e_u)
