@@ -494,7 +494,8 @@ int tamtr_tok_reduce(const void *a_bf16, long a_row, long a_img, int a_token_maj
  *   tamtr_fold_pack    Fv [L, N0, K], Fe [L, NE, K] (folded weights, column K-1 = folded bias part), bv [N0] ->
  *                      w_out[l] bf16 [N0 + NE, C_l] and bias [L, N0 + NE]: the operands of tamtr_tok_project
  *   tamtr_fold_unpack  partials of tamtr_tok_reduce(grad_value, x) per level -> dF [L, N0, K], dF_t [N0, L, K], d_bv [N0]
- *   tamtr_fold_bn_bwd  dA [L, d, K] (+ dAt [L, K, d] or NULL, added) -> d_wc[l] [d, C_l], d_gamma[l], d_beta[l]
+ *   tamtr_fold_bn_bwd  dA [L, d, K] (+ dAt [L, K, d] or NULL, added) -> d_wc[l] [d, C_l], d_gamma[l], d_beta[l]; d_stat [L, d, 2]
+ *                      (or NULL) = (d mu, d var) per channel, for callers that carry the gradient on to the feature maps
  *   tamtr_fold_gather  xcat [R, L * K]: for the (image, token) pair flat_idx[r] = image * Lv + token the bf16 column
  *                      x_l[b, :, token - start_l] of its level l in block l (1 in the block's last column), 0 elsewhere:
  *                      the rows head.py:1240 gathers from `feats` are xcat @ a_ext_t.view(L * K, d) */
@@ -519,7 +520,7 @@ int tamtr_fold_unpack(int L, const int *C, const int *S, const float *const *par
                       float *dF_t, float *d_bv, int N0, void *stream);
 int tamtr_fold_bn_bwd(int L, int d, const int *C, const float *const *wc, const float *const *P, const float *const *mean_x,
                       const float *const *gamma, const float *dA, const float *dAt, const float *stats, int batch_stats,
-                      float *const *d_wc, float *const *d_gamma, float *const *d_beta, void *stream);
+                      float *const *d_wc, float *const *d_gamma, float *const *d_beta, float *d_stat, void *stream);
 int tamtr_fold_gather(int L, int Lv, const int *C, const int *start, const int *hw, const void *const *x_bf16,
                       const long long *flat_idx, float *xcat, int R, void *stream);
 

@@ -95,7 +95,7 @@ _SIGNATURES = {
     "tamtr_fold_bn": (ctypes.c_int, [_i, _i] + [_vp] * 12 + [_i, _i] + [_fp] * 3 + [_vp]),
     "tamtr_fold_pack": (ctypes.c_int, [_i, _vp, _fp, _fp, _fp, _vp, _fp, _i, _i, _vp]),
     "tamtr_fold_unpack": (ctypes.c_int, [_i] + [_vp] * 4 + [_fp] * 3 + [_i, _vp]),
-    "tamtr_fold_bn_bwd": (ctypes.c_int, [_i, _i] + [_vp] * 5 + [_fp] * 3 + [_i] + [_vp] * 3 + [_vp]),
+    "tamtr_fold_bn_bwd": (ctypes.c_int, [_i, _i] + [_vp] * 5 + [_fp] * 3 + [_i] + [_vp] * 3 + [_fp, _vp]),
     "tamtr_fold_gather": (ctypes.c_int, [_i, _i] + [_vp] * 4 + [_vp, _fp, _i, _vp]),
     "tamtr_tok_reduce_supported": (ctypes.c_int, [_i] * 5),
     "tamtr_tok_reduce_splits": (ctypes.c_int, [_i] * 5),

@@ -166,7 +166,7 @@ __global__ void fold_unpack_kernel(const FoldPtrs p, float *__restrict__ dF, flo
 
 // one warp per (level, channel j): dA [L, d, K] (+ the transposed contribution dAt [L, K, d] of the selected rows, or NULL)
 __global__ void fold_bn_bwd_kernel(const FoldPtrs p, const float *__restrict__ dA, const float *__restrict__ dAt,
-                                   const float *__restrict__ stats, int batch_stats) {
+                                   const float *__restrict__ stats, int batch_stats, float *__restrict__ d_stat) {
     const int l = blockIdx.y, lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= p.d) return;
@@ -191,6 +191,10 @@ __global__ void fold_bn_bwd_kernel(const FoldPtrs p, const float *__restrict__ d
     if (lane == 0) {
         p.d_gamma[l][j] = ds * r;
         p.d_beta[l][j] = dt;
+        if (d_stat != nullptr) {            // d(loss)/d(mu_j), d(loss)/d(var_j): the caller carries them on to the feature maps
+            d_stat[((size_t)l * p.d + j) * 2] = dmu;
+            d_stat[((size_t)l * p.d + j) * 2 + 1] = dvar;
+        }
     }
     float *dw = p.d_wc[l] + (size_t)j * C;
     const float *Pj = batch_stats ? p.P[l] + (size_t)j * C : nullptr, *mx = batch_stats ? p.mean_x[l] : nullptr;
@@ -402,7 +406,7 @@ extern "C" int tamtr_fold_unpack(int L, const int *C, const int *S, const float 
 extern "C" int tamtr_fold_bn_bwd(int L, int d, const int *C, const float *const *wc, const float *const *P,
                                  const float *const *mean_x, const float *const *gamma, const float *dA, const float *dAt,
                                  const float *stats, int batch_stats, float *const *d_wc, float *const *d_gamma,
-                                 float *const *d_beta, void *stream) {
+                                 float *const *d_beta, float *d_stat, void *stream) {
     TAMTR_CHECK_ARG(C && wc && gamma && dA && stats && d_wc && d_gamma && d_beta, TAMTR_E_BADARG, "fold_bn_bwd: null pointer");
     TAMTR_CHECK_ARG(!batch_stats || (P && mean_x), TAMTR_E_BADARG, "fold_bn_bwd: batch statistics need P and mean_x");
     FoldPtrs p = {};
@@ -413,7 +417,7 @@ extern "C" int tamtr_fold_bn_bwd(int L, int d, const int *C, const float *const 
         p.d_wc[l] = d_wc[l]; p.d_gamma[l] = d_gamma[l]; p.d_beta[l] = d_beta[l];
         TAMTR_CHECK_ARG(wc[l] && gamma[l] && d_wc[l] && d_gamma[l] && d_beta[l], TAMTR_E_BADARG, "fold_bn_bwd: bad level %d", l);
     }
-    fold_bn_bwd_kernel<<<dim3((d + 7) / 8, L), 256, 0, (cudaStream_t)stream>>>(p, dA, dAt, stats, batch_stats);
+    fold_bn_bwd_kernel<<<dim3((d + 7) / 8, L), 256, 0, (cudaStream_t)stream>>>(p, dA, dAt, stats, batch_stats, d_stat);
     count_launch();
     TAMTR_CUDA_OK(cudaGetLastError());
     return 0;

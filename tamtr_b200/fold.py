@@ -293,8 +293,6 @@ def _mm_fp32(a, b):
 def fused_glue_applies(tokens, projs, attns):
     if not (FUSED_GLUE and tokens.is_cuda and MATH_DTYPE == torch.float32 and len(tokens.xs) <= _MAXL):
         return False
-    if any(x.requires_grad for x in tokens.xs) and torch.is_grad_enabled():
-        return False            # gradients to the feature maps go through the differentiable torch path
     for conv, bn in projs:
         ts = [conv.weight, bn.weight, bn.bias] + ([bn.running_mean, bn.running_var] if bn.running_mean is not None else [])
         if any(t.dtype != torch.float32 or not t.is_contiguous() for t in ts):
@@ -315,9 +313,9 @@ class _FusedFoldFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tokens, arena, training, bns, n_layers, n_heads, We_all, *t):
         L = len(tokens.xs)
-        convs, gammas, betas = t[:L], t[L:2 * L], t[2 * L:3 * L]
-        wvs, bvs = t[3 * L:3 * L + n_layers], t[3 * L + n_layers:]
-        xs, cs, d, Cm = tokens.xs, tokens.cs, tokens.d, tokens.Cm
+        xs, convs, gammas, betas = t[:L], t[L:2 * L], t[2 * L:3 * L], t[3 * L:4 * L]
+        wvs, bvs = t[4 * L:4 * L + n_layers], t[4 * L + n_layers:]
+        cs, d, Cm = tokens.cs, tokens.d, tokens.Cm
         K, dev, lib = _kpad(Cm), tokens.device, _lib.lib()
         st = _lib.stream_ptr(dev)
         n_tok = [float(tokens.B * n) for n in tokens.hw]
@@ -368,8 +366,9 @@ class _FusedFoldFn(torch.autograd.Function):
                                  None if isinstance(ctx, _NoCtx) else arena)
         value_all = tokens._value_all
         ctx.save_for_backward(*xs, *convs, *gammas, *[p for p in P if p is not None],
-                              *([mean_flat] if batch_stats else []), stats, a_ext_t, Wv)
-        ctx.arena, ctx.L, ctx.n, ctx.batch_stats = arena, L, n_layers, batch_stats
+                              *([mean_flat] if batch_stats else []), stats, a_ext_t, Wv, *w_out)
+        ctx.arena, ctx.L, ctx.n, ctx.batch_stats, ctx.tokens = arena, L, n_layers, batch_stats, tokens
+        ctx.n_tok = n_tok
         ctx.meta = (value_all.shape, tokens.starts, tokens.hw, cs, d, Cm, [w.dtype for w in wvs], [b.dtype for b in bvs],
                     [c.shape for c in convs])
         ctx.set_materialize_grads(False)
@@ -388,6 +387,8 @@ class _FusedFoldFn(torch.autograd.Function):
             P, mean_flat = sv[k:k + L], sv[k + L]
             k += L + 1
         stats, a_ext_t, Wv = sv[k], sv[k + 1], sv[k + 2]
+        w_out = sv[k + 3:k + 3 + L]
+        need_dx = [bool(f) for f in ctx.needs_input_grad[7:7 + L]]
         K, dev, lib = _kpad(Cm), xs[0].device, _lib.lib()
         st = _lib.stream_ptr(dev)
         buf = _arena_gradient(ctx.arena, grads, shape, Wv.shape[0] // n, torch.bfloat16, dev)
@@ -413,33 +414,78 @@ class _FusedFoldFn(torch.autograd.Function):
                     mean_x.append(mean_flat[o:o + c])
                     o += c
             dAt = None if d_aext_t is None else d_aext_t.contiguous()
+            d_stat = torch.empty(L, d, 2, dtype=torch.float32, device=dev) if (any(need_dx) and ctx.batch_stats) else None
             _lib.check(lib.tamtr_fold_bn_bwd(
                 L, d, C_arr, _parr([c.view(d, -1) for c in convs]), _parr(P) if P is not None else None,
                 _parr(mean_x) if mean_x is not None else None, _parr(gammas), dA.data_ptr(),
                 None if dAt is None else dAt.data_ptr(), stats.data_ptr(), int(ctx.batch_stats), _parr(d_wc),
-                _parr(d_gamma), _parr(d_beta), st), "fold_bn_bwd")
+                _parr(d_gamma), _parr(d_beta), None if d_stat is None else d_stat.data_ptr(), st), "fold_bn_bwd")
+            dxs = [None] * L
+            for l in range(L):
+                if need_dx[l]:
+                    dxs[l] = _maps_gradient(ctx.tokens, l, xs[l], w_out[l][:N0], buf[:, starts[l]:starts[l] + hw[l]],
+                                            convs[l].view(d, -1), None if d_stat is None else d_stat[l],
+                                            None if mean_x is None else mean_x[l], ctx.n_tok[l])
+            ctx.tokens._row_grads = []
         dd = Wv.shape[0] // n
         dWv_c = dWv if all(t == torch.float32 for t in wdts) else dWv.to(wdts[0])
         d_bv_c = d_bv if all(t == torch.float32 for t in bdts) else d_bv.to(bdts[0])
         g_wv = [dWv_c[i * dd:(i + 1) * dd].to(wdts[i]) for i in range(n)]
         g_bv = [d_bv_c[i * dd:(i + 1) * dd].to(bdts[i]) for i in range(n)]
-        return (None,) * 7 + tuple(g.view(s) for g, s in zip(d_wc, cshapes)) + tuple(d_gamma) + tuple(d_beta) \
-            + tuple(g_wv) + tuple(g_bv)
+        return (None,) * 7 + tuple(dxs) + tuple(g.view(s) for g, s in zip(d_wc, cshapes)) + tuple(d_gamma) \
+            + tuple(d_beta) + tuple(g_wv) + tuple(g_bv)
+
+
+def _bmm_f32(a, b):
+    """batched bf16 product with an fp32 result"""
+    try:
+        return torch.bmm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return torch.bmm(a.float(), b.float())
+
+
+def _maps_gradient(tokens, l, x, w_v, g_l, wc, d_stat, mean_x, n_tok):
+    """d(loss)/d(X_l) of the fused fold, assembled in fp32 and rounded once:
+      W_fold^T grad_value^T                          the projection (X enters it linearly)
+      (2 / n) dCov X + dS1                           through the batch statistics: mu = Wc mean(x), var = diag(Wc Cov Wc^T),
+                                                     Cov = G / n - m m^T   (dCov = Wc^T diag(dvar) Wc, dmean = Wc^T dmu)
+      row-sparse terms of the selected tokens        (FoldedTokens.rows: Xcat @ A_ext^T)"""
+    B, C = x.shape[0], x.shape[1]
+    X = x.flatten(2)                                                                  # [B, C, HW]
+    gx = _bmm_f32(w_v.t().unsqueeze(0).expand(B, -1, -1), g_l.transpose(1, 2))        # [B, C, HW] fp32
+    if d_stat is not None:
+        dmu, dvar = d_stat[:, 0], d_stat[:, 1]
+        dcov = _mm_fp32((wc * dvar.unsqueeze(1)).t().contiguous(), wc)                # [C, C]
+        ds1 = (dmu @ wc - 2.0 * (dcov @ mean_x)) / n_tok
+        gx = gx + _bmm_f32((dcov * (2.0 / n_tok)).to(x.dtype).unsqueeze(0).expand(B, -1, -1), X) + ds1.view(1, C, 1)
+    K = _kpad(tokens.Cm)
+    for flat_idx, dxcat in tokens._row_grads:                                         # [R], [R, L * K] fp32
+        img = torch.div(flat_idx, tokens.Lv, rounding_mode="floor")
+        rel = flat_idx - img * tokens.Lv - tokens.starts[l]
+        inside = ((rel >= 0) & (rel < tokens.hw[l])).to(dxcat.dtype).unsqueeze(1)
+        vals = dxcat[:, l * K:l * K + C] * inside
+        gx.permute(0, 2, 1).index_put_((img, rel.clamp(0, tokens.hw[l] - 1)), vals, accumulate=True)
+    return gx.to(x.dtype).view(x.shape)
 
 
 class _RowsFn(torch.autograd.Function):
-    """feats rows = Xcat [R, L*K] @ A_ext^T [L*K, d] (TF32 forward and backward); Xcat carries no gradient."""
+    """feats rows = Xcat [R, L*K] @ A_ext^T [L*K, d] (TF32 forward and backward).  Xcat is gathered by a kernel; when the
+    feature maps require a gradient its row-sparse gradient is left on `tokens` for _FusedFoldFn.backward, which runs
+    after this node (it consumes d(A_ext^T)) and adds it into the dense d(maps)."""
 
     @staticmethod
-    def forward(ctx, xcat, a_ext_t):
-        ctx.save_for_backward(xcat)
-        ctx.shape = a_ext_t.shape
+    def forward(ctx, tokens, flat_idx, xcat, a_ext_t):
+        ctx.save_for_backward(xcat, a_ext_t, flat_idx)
+        ctx.tokens = tokens
         return _mm_tf32(xcat, a_ext_t.reshape(-1, a_ext_t.shape[-1]))
 
     @staticmethod
     def backward(ctx, g):
-        (xcat,) = ctx.saved_tensors
-        return None, _mm_tf32(xcat.t(), g.float().contiguous()).view(ctx.shape)
+        xcat, a_ext_t, flat_idx = ctx.saved_tensors
+        g = g.float().contiguous()
+        if ctx.tokens.maps_need_grad:
+            ctx.tokens._row_grads.append((flat_idx, _mm_tf32(g, a_ext_t.reshape(-1, a_ext_t.shape[-1]).t())))
+        return None, None, None, _mm_tf32(xcat.t(), g).view(a_ext_t.shape)
 
 
 def _arena_gradient(arena, grads, shape, d, lp, dev):
@@ -514,6 +560,7 @@ class FoldedTokens:
         self.is_cuda = xs[0].is_cuda
         self.values = self.arena = self.E = self.raw = self.scores = self.valid_u8 = None
         self.projs, self.training = projs, training
+        self.maps_need_grad, self._row_grads = False, []
         self.A = self.t = self.a_ext_t = None       # set by project(): A [L, d, Cm], t [L, d]  or  a_ext_t [L, Cm + 1, d]
 
     # BatchNorm2d's forward (torch/nn/modules/batchnorm.py:155-193) on statistics derived from the moments of X
@@ -580,8 +627,10 @@ class FoldedTokens:
             self.arena = ops.ValueArena()
             if fused_glue_applies(self, self.projs, attns):
                 convs, bns = [p[0] for p in self.projs], [p[1] for p in self.projs]
-                t = [c.weight for c in convs] + [b.weight for b in bns] + [b.bias for b in bns] \
+                t = list(self.xs) + [c.weight for c in convs] + [b.weight for b in bns] + [b.bias for b in bns] \
                     + [a.value_proj.weight for a in attns] + [a.value_proj.bias for a in attns]
+                self.maps_need_grad = grad and any(x.requires_grad for x in self.xs)
+                self._row_grads = []
                 if grad and any(p.requires_grad for p in t):
                     out = _FusedFoldFn.apply(self, self.arena, self.training, bns, n_layers, n_heads, We_all, *t)
                 else:
@@ -637,7 +686,7 @@ class FoldedTokens:
             _lib.check(rc, "fold_gather")
             with torch.autocast(self.device.type, enabled=False):
                 if torch.is_grad_enabled() and self.a_ext_t.requires_grad:
-                    return _RowsFn.apply(xcat, self.a_ext_t)
+                    return _RowsFn.apply(self, idx, xcat, self.a_ext_t)
                 return _mm_tf32(xcat, self.a_ext_t.reshape(L * K, -1))
         img = torch.div(flat_idx, self.Lv, rounding_mode="floor")
         tok = flat_idx - img * self.Lv

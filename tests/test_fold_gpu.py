@@ -285,7 +285,8 @@ def test_rank_constants_kernel_matches_torch(cuda_lib):
 
 def test_feature_maps_that_require_a_gradient(cuda_lib):
     """real training: the backbone's maps require a gradient -> the folded path (differentiable torch glue) hands
-    d(loss)/d(maps) back through the projection, the statistics and the selected rows.  Judged like the parameter
+    d(loss)/d(maps) back through the projection, the statistics and the selected rows (fused glue: assembled in fp32 by
+    fold._maps_gradient; torch glue: by autograd).  Judged like the parameter
     gradients: against an fp32 run of the unfolded kernels, the folded bf16 result must not be further away than the
     unfolded bf16 one (with the seeded weights both sit ~20 % from fp32: d(maps) is what is left after BatchNorm's
     backward has projected the batch mean and variance directions out)."""
@@ -307,10 +308,18 @@ def test_feature_maps_that_require_a_gradient(cuda_lib):
         loss = db.float().square().mean() + 0.1 * ds.float().sigmoid().mean() + eb.float().square().mean() + 0.1 * es.float().sigmoid().mean()
         loss.backward()
         return tok, [x.grad.float() for x in maps]
+    from tamtr_b200 import fold
     tok, gx_f = run(m, xs)
-    assert getattr(tok, "is_folded", False) and tok.a_ext_t is None        # folded, general (torch glue) path
+    assert getattr(tok, "is_folded", False) and tok.a_ext_t is not None    # folded, fused glue
+    try:
+        fold.FUSED_GLUE = False
+        tok_g, gx_g = run(m, xs)                                            # same module, torch glue
+        assert tok_g.a_ext_t is None and tok_g.A is not None
+    finally:
+        fold.FUSED_GLUE = True
     _, gx_u = run(ref, xs)
     _, gx_32 = run(ref32, [x.float() for x in xs], autocast=False)
-    for a, b, c in zip(gx_f, gx_u, gx_32):
-        e_f, e_u = rel_l2(a, c), rel_l2(b, c)
+    for a, g, b, c in zip(gx_f, gx_g, gx_u, gx_32):
+        e_f, e_g, e_u = rel_l2(a, c), rel_l2(g, c), rel_l2(b, c)
         assert a.shape == c.shape and e_f < max(1.25 * e_u, 3e-2), (e_f, e_u)
+        assert e_g < max(1.25 * e_u, 3e-2), (e_g, e_u)
