@@ -389,7 +389,8 @@ class Stem(torch.nn.Module):
     def forward(self, img_u8, outs):
         x = img_u8.to(torch.bfloat16).sub_(127.5).mul_(1.0 / 64.0)
         for w, st, o in zip(self.w, self.strides, outs):
-            o.copy_(torch.nn.functional.conv2d(torch.nn.functional.avg_pool2d(x, st), w))
+            # 1x1 projection of the pooled image as a batched [C, 3] x [3, HW] product written straight into the step's input
+            torch.matmul(w.view(w.shape[0], 3), torch.nn.functional.avg_pool2d(x, st).flatten(2), out=o.view(o.shape[0], o.shape[1], -1))
         return outs
 
 

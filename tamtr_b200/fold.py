@@ -367,8 +367,9 @@ class _FusedFoldFn(torch.autograd.Function):
         value_all = tokens._value_all
         ctx.save_for_backward(*xs, *convs, *gammas, *[p for p in P if p is not None],
                               *([mean_flat] if batch_stats else []), stats, a_ext_t, Wv, *w_out)
-        ctx.arena, ctx.L, ctx.n, ctx.batch_stats, ctx.tokens = arena, L, n_layers, batch_stats, tokens
-        ctx.n_tok = n_tok
+        ctx.arena, ctx.L, ctx.n, ctx.batch_stats = arena, L, n_layers, batch_stats
+        # (no reference to `tokens` itself: it holds a_ext_t, whose grad_fn is this node -- a cycle would keep the graph alive)
+        ctx.n_tok, ctx.row_grads, ctx.geom = n_tok, tokens._row_grads, (tokens.Lv, tokens.starts, tokens.hw, tokens.Cm)
         ctx.meta = (value_all.shape, tokens.starts, tokens.hw, cs, d, Cm, [w.dtype for w in wvs], [b.dtype for b in bvs],
                     [c.shape for c in convs])
         ctx.set_materialize_grads(False)
@@ -423,10 +424,11 @@ class _FusedFoldFn(torch.autograd.Function):
             dxs = [None] * L
             for l in range(L):
                 if need_dx[l]:
-                    dxs[l] = _maps_gradient(ctx.tokens, l, xs[l], w_out[l][:N0], buf[:, starts[l]:starts[l] + hw[l]],
-                                            convs[l].view(d, -1), None if d_stat is None else d_stat[l],
-                                            None if mean_x is None else mean_x[l], ctx.n_tok[l])
-            ctx.tokens._row_grads = []
+                    dxs[l] = _maps_gradient(ctx.geom, ctx.row_grads, l, xs[l], w_out[l][:N0],
+                                            buf[:, starts[l]:starts[l] + hw[l]], convs[l].view(d, -1),
+                                            None if d_stat is None else d_stat[l], None if mean_x is None else mean_x[l],
+                                            ctx.n_tok[l])
+            del ctx.row_grads[:]
         dd = Wv.shape[0] // n
         dWv_c = dWv if all(t == torch.float32 for t in wdts) else dWv.to(wdts[0])
         d_bv_c = d_bv if all(t == torch.float32 for t in bdts) else d_bv.to(bdts[0])
@@ -444,7 +446,7 @@ def _bmm_f32(a, b):
         return torch.bmm(a.float(), b.float())
 
 
-def _maps_gradient(tokens, l, x, w_v, g_l, wc, d_stat, mean_x, n_tok):
+def _maps_gradient(geom, row_grads, l, x, w_v, g_l, wc, d_stat, mean_x, n_tok):
     """d(loss)/d(X_l) of the fused fold, assembled in fp32 and rounded once:
       W_fold^T grad_value^T                          the projection (X enters it linearly)
       (2 / n) dCov X + dS1                           through the batch statistics: mu = Wc mean(x), var = diag(Wc Cov Wc^T),
@@ -458,13 +460,14 @@ def _maps_gradient(tokens, l, x, w_v, g_l, wc, d_stat, mean_x, n_tok):
         dcov = _mm_fp32((wc * dvar.unsqueeze(1)).t().contiguous(), wc)                # [C, C]
         ds1 = (dmu @ wc - 2.0 * (dcov @ mean_x)) / n_tok
         gx = gx + _bmm_f32((dcov * (2.0 / n_tok)).to(x.dtype).unsqueeze(0).expand(B, -1, -1), X) + ds1.view(1, C, 1)
-    K = _kpad(tokens.Cm)
-    for flat_idx, dxcat in tokens._row_grads:                                         # [R], [R, L * K] fp32
-        img = torch.div(flat_idx, tokens.Lv, rounding_mode="floor")
-        rel = flat_idx - img * tokens.Lv - tokens.starts[l]
-        inside = ((rel >= 0) & (rel < tokens.hw[l])).to(dxcat.dtype).unsqueeze(1)
+    Lv, starts, hw, Cm = geom
+    K = _kpad(Cm)
+    for flat_idx, dxcat in row_grads:                                                 # [R], [R, L * K] fp32
+        img = torch.div(flat_idx, Lv, rounding_mode="floor")
+        rel = flat_idx - img * Lv - starts[l]
+        inside = ((rel >= 0) & (rel < hw[l])).to(dxcat.dtype).unsqueeze(1)
         vals = dxcat[:, l * K:l * K + C] * inside
-        gx.permute(0, 2, 1).index_put_((img, rel.clamp(0, tokens.hw[l] - 1)), vals, accumulate=True)
+        gx.permute(0, 2, 1).index_put_((img, rel.clamp(0, hw[l] - 1)), vals, accumulate=True)
     return gx.to(x.dtype).view(x.shape)
 
 
@@ -476,15 +479,15 @@ class _RowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tokens, flat_idx, xcat, a_ext_t):
         ctx.save_for_backward(xcat, a_ext_t, flat_idx)
-        ctx.tokens = tokens
+        ctx.row_grads = tokens._row_grads if tokens.maps_need_grad else None     # (the list, not `tokens`: no cycle)
         return _mm_tf32(xcat, a_ext_t.reshape(-1, a_ext_t.shape[-1]))
 
     @staticmethod
     def backward(ctx, g):
         xcat, a_ext_t, flat_idx = ctx.saved_tensors
         g = g.float().contiguous()
-        if ctx.tokens.maps_need_grad:
-            ctx.tokens._row_grads.append((flat_idx, _mm_tf32(g, a_ext_t.reshape(-1, a_ext_t.shape[-1]).t())))
+        if ctx.row_grads is not None:
+            ctx.row_grads.append((flat_idx, _mm_tf32(g, a_ext_t.reshape(-1, a_ext_t.shape[-1]).t())))
         return None, None, None, _mm_tf32(xcat.t(), g).view(a_ext_t.shape)
 
 
