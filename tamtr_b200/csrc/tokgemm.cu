@@ -122,6 +122,8 @@ struct PjGeom {
     // ranking mode (rank_mode = 1): the N1 columns are the ranking embedding E and the tail its class scores; neither is
     // stored -- the epilogue reduces them to one score per token (see tok_project_kernel)
     int rank_mode, nc;
+    int defer;                     // ranking mode, NT == 16: the tail values wait in registers and the score is finished at the
+                                   // end of the tile, so that ALL column steps can be walked in the rotated order
     int zero_fill;                 // also write zeros over the same (token, value column) range of a second tensor (map_z)
     long rank_img;
     float eps, inv_d;
@@ -267,6 +269,9 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         for (int p = blockIdx.x; p < g.n_pairs; p += gridDim.x) {
             const int b = p / g.pairs_per_img, tok0 = (p - b * g.pairs_per_img) * tile_tok + mt * 128;
             float s1 = 0.f, s2 = 0.f;                                        // sum / sum of squares of the token's E row
+            float tv[16];                                                    // deferred mode: the token's 16 tail values
+#pragma unroll
+            for (int j = 0; j < 16; ++j) tv[j] = 0.f;
             for (int ns = 0; ns < g.n_steps; ++ns, ++ai) {
                 const int n = ns < g.n_rot ? (ns + n0 < g.n_rot ? ns + n0 : ns + n0 - g.n_rot) : ns;
                 const uint32_t as = ai & 1;
@@ -279,6 +284,12 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     if (col0 >= Nmain) {
                         const int tok = tok0 + row, toff = col0 - Nmain;
                         uint32_t v[32];
+                        if (g.rank_mode && g.defer) {
+                            tk_tmem_ld32(taddr + chunk * 64, v);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) tv[j] = __uint_as_float(v[j]) + __ldg(bias + Nmain + j);
+                            continue;
+                        }
                         if (g.rank_mode) {
                             // ===== ranking score of the token (head.py:1229-1237): LayerNorm statistics of E + enc bias from
                             // (sum E, sum E^2, E . enc_bias), folded with the class scores of the tail columns
@@ -397,7 +408,7 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         tk_tma_commit();
                     }
                 }
-                if (MT == 1 && g.rank_mode && n == n_tail && grp != tail_grp) {
+                if (MT == 1 && g.rank_mode && !g.defer && n == n_tail && grp != tail_grp) {
                     // this group's share of the token's moments -> the group that owns the tail chunk
                     s_part[row] = make_float2(s1, s2);
                     asm volatile("bar.sync 3, 256;" ::: "memory");
@@ -407,6 +418,29 @@ tok_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars.acc_empty[as]);
+            }
+            if (g.rank_mode && g.defer) {
+                // ===== ranking score of the tile's tokens, after all of their column steps (same arithmetic as above)
+                if (MT == 1) {
+                    if (grp != tail_grp) s_part[row] = make_float2(s1, s2);
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    if (grp == tail_grp) { const float2 o = s_part[row]; s1 += o.x; s2 += o.y; }
+                }
+                const int tok = tok0 + row;
+                if ((MT == 2 || grp == tail_grp) && tok < g.HW) {
+                    const bool ok = __ldg(valid + tok) != 0;
+                    const float dot = ok ? tv[15] : 0.f;
+                    if (!ok) { s1 = 0.f; s2 = 0.f; }
+                    const float mean = (s1 + s_rc[0]) * g.inv_d;
+                    const float rstd = rsqrtf(fmaxf((s2 + 2.f * dot + s_rc[1]) * g.inv_d - mean * mean, 0.f) + g.eps);
+                    const float *bw = s_rc + 2, *sw_ = bw + 16, *ck = sw_ + 16;
+                    float best = -INFINITY;
+#pragma unroll
+                    for (int k = 0; k < 15; ++k)
+                        if (k < g.nc) best = fmaxf(best, rstd * ((ok ? tv[k] : 0.f) + bw[k] - mean * sw_[k]) + ck[k]);
+                    rank_out[(size_t)b * g.rank_img + tok] = best;
+                }
+                if (MT == 1) asm volatile("bar.sync 3, 256;" ::: "memory");
             }
         }
         if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -697,11 +731,16 @@ static int tok_project_impl(const void *x_bf16, const void *w_bf16, const float 
     g.n_steps = (Nall + 127) / 128;
     g.raw_row = raw_row; g.raw_img = raw_img;
     g.n_rot = (N0 % 128 == 0 && !getenv("TAMTR_TOK_NOROT")) ? N0 / 128 : 0;
+    g.defer = 0;
     g.rank_mode = rk != nullptr ? 1 : 0;
     g.nc = rk != nullptr ? rk->nc : 0;
     g.rank_img = rk != nullptr ? rk->rank_img : 0;
     g.eps = rk != nullptr ? rk->eps : 0.f;
     g.inv_d = N1 > 0 ? 1.0f / (float)N1 : 0.f;
+    if (rk != nullptr && NT == 16 && g.n_rot > 0 && (N0 + N1) % 128 == 0 && !getenv("TAMTR_TOK_NODEFER")) {
+        g.defer = 1;
+        g.n_rot = g.n_steps;                // every column step, the E and tail steps included
+    }
     const uint8_t *valid = rk != nullptr ? rk->valid : nullptr;
     const float *rconst = rk != nullptr ? rk->consts : nullptr;
     float *rank_out = rk != nullptr ? rk->rank : nullptr;
