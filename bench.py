@@ -478,7 +478,7 @@ def main():
 
     import torch.distributed as dist
     import tamtr_b200
-    from tamtr_b200 import _lib, dp
+    from tamtr_b200 import _lib, dp, ops
     from tamtr_b200.head import ManbaWorldDecoder
 
     rank = int(os.environ.get("RANK", 0))
@@ -666,9 +666,20 @@ def main():
             _lib.lib().tamtr_memset_zero(arena.data_ptr(), arena.numel() * 2, _lib.stream_ptr(dev))
         z1.record()
         torch.cuda.synchronize(dev)
+        memset_us = z0.elapsed_time(z1) / 5 * 1e3
+        z0.record()
+        for _ in range(5):
+            _lib.lib().tamtr_zero_fill_background(arena.data_ptr(), arena.numel() * 2, 0, _lib.stream_ptr(dev))
+        z1.record()
+        torch.cuda.synchronize(dev)
         zero_fill = {"bytes_per_step": arena.numel() * 2, "us_per_step": z0.elapsed_time(z1) / 5 * 1e3,
-                     "note": "one cudaMemset node per step for the dense bf16 grad_value arena of all 3 layers; not in "
-                             "roofline.algorithmic_bytes, not in the sampler kernels' time"}
+                     "cuda_memset_us": memset_us,
+                     "forked": bool(ops.ARENA_PREFILL), "fill_ctas": ops.ARENA_FILL_CTAS,
+                     "note": "zero fill of the dense bf16 grad_value arena of all 3 layers, once per step, timed alone "
+                             "here; in the step it is a bulk-store kernel of small co-resident CTAs forked to a side "
+                             "stream after the projection and joined by the first sampler backward, i.e. beside the "
+                             "decoder forward (round-2 start: a cudaMemset node in front of the first sampler "
+                             "backward); not in roofline.algorithmic_bytes, not in the sampler kernels' time"}
         del arena
     barrier()
 

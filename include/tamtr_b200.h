@@ -47,6 +47,11 @@ enum tamtr_kernel {
 };
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (a memset node is ~1.5x faster than a fill kernel for GB-sized buffers) */
 int tamtr_memset_zero(void *ptr, unsigned long long bytes, void *stream);
+/* Zero `bytes` at `ptr` (16-byte aligned) with a kernel of `n_ctas` small CTAs (<= 0: one per SM; ~62 GB/s each) issuing bulk shared->global
+ * stores: meant to run on a side stream BESIDE latency-bound work (the gradient arena of the samplers' backward,
+ * zeroed during the decoder forward; replaces torch.zeros_like in the reference's autograd of transformer.py:273),
+ * where a full-grid memset node would take every SM and the whole memory system. */
+int tamtr_zero_fill_background(void *ptr, unsigned long long bytes, int n_ctas, void *stream);
 int tamtr_profile_enable(int on);
 int tamtr_profile_read(int kernel_id, double *total_ms, unsigned long long *launches);
 const char *tamtr_kernel_name(int kernel_id);

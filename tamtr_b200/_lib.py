@@ -25,6 +25,7 @@ _SIGNATURES = {
     "tamtr_last_error": (ctypes.c_char_p, []),
     "tamtr_launch_count": (ctypes.c_ulonglong, []),
     "tamtr_memset_zero": (ctypes.c_int, [_vp, ctypes.c_ulonglong, _vp]),
+    "tamtr_zero_fill_background": (ctypes.c_int, [_vp, ctypes.c_ulonglong, _i, _vp]),
     "tamtr_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "tamtr_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_ulonglong)]),

@@ -95,6 +95,53 @@ extern "C" const char *tamtr_kernel_name(int kernel_id) {
     return (kernel_id >= 0 && kernel_id < tamtr::K_COUNT) ? tamtr::g_names[kernel_id] : "";
 }
 
+// ---- background zero fill: small CTAs, one issuing thread each, bulk shared->global stores of a zeroed 32 KB tile.
+// A cudaMemsetAsync of a GB-sized buffer is a full-grid kernel: forked beside other work it takes every SM's CTA slots
+// for its 0.23 ms and nothing is hidden (measured: the step got 0.03 ms slower).  This one occupies 128 threads + 32 KB
+// per CTA, so other kernels' CTAs co-reside with it, and its rate is n_ctas x 62 GB/s (8 x 32 KB stores in flight per CTA:
+// 16 CTAs 1.0 TB/s, 64 CTAs 3.8 TB/s, 148 CTAs 6.3 TB/s) -- the caller picks how hard it leans on the memory system.
+namespace tamtr {
+constexpr unsigned kFillTile = 32768;
+constexpr int kFillInFlight = 8;
+
+__global__ void __launch_bounds__(128) zero_fill_bg_kernel(unsigned char *dst, unsigned long long bytes) {
+    __shared__ __align__(128) unsigned char tile[kFillTile];
+    for (unsigned i = threadIdx.x; i < kFillTile / 16; i += blockDim.x) reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const unsigned long long n_tiles = bytes / kFillTile;
+    if (threadIdx.x == 0) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(tile);
+        for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {     // interleaved: all channels busy
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + t * kFillTile), "r"(src),
+                         "r"(kFillTile)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kFillInFlight) : "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");                 // stores complete before the CTA leaves
+    }
+    if (blockIdx.x == gridDim.x - 1) {                                              // ragged tail (< one tile)
+        const unsigned long long done = n_tiles * kFillTile;
+        for (unsigned long long i = done + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = 0;
+    }
+}
+}  // namespace tamtr
+
+extern "C" int tamtr_zero_fill_background(void *ptr, unsigned long long bytes, int n_ctas, void *stream) {
+    TAMTR_CHECK_ARG(ptr != nullptr, TAMTR_E_BADARG, "zero_fill_background: null pointer");
+    TAMTR_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, TAMTR_E_BADARG,
+                    "zero_fill_background: pointer must be 16-byte aligned");
+    if (bytes == 0) return 0;
+    if (n_ctas <= 0) n_ctas = tamtr::sm_count();
+    const unsigned long long n_tiles = bytes / tamtr::kFillTile;
+    if ((unsigned long long)n_ctas > n_tiles) n_ctas = n_tiles ? (int)n_tiles : 1;
+    tamtr::zero_fill_bg_kernel<<<n_ctas, 128, 0, (cudaStream_t)stream>>>(static_cast<unsigned char *>(ptr), bytes);
+    TAMTR_CUDA_OK(cudaGetLastError());
+    tamtr::count_launch();
+    return 0;
+}
+
 extern "C" int tamtr_memset_zero(void *ptr, unsigned long long bytes, void *stream) {
     TAMTR_CHECK_ARG(ptr != nullptr, TAMTR_E_BADARG, "memset_zero: null pointer");
     TAMTR_CUDA_OK(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));

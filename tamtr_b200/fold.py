@@ -494,8 +494,7 @@ class _RowsFn(torch.autograd.Function):
 def _arena_gradient(arena, grads, shape, d, lp, dev):
     """The gradient of the projected values: what the samplers accumulated in the shared arena (+ whatever reached a
     value view through plain autograd), as one [B, Lv, N0] tensor of dtype `lp`."""
-    buf, arena.buf, arena.base = arena.buf, None, None
-    written, arena.written = arena.written, set()
+    buf, written = arena.take()
     arena.bias_grad = {}
     if buf is None:
         buf = _lib.zeros_like_fast(torch.empty(shape, dtype=lp, device=dev))
@@ -537,6 +536,8 @@ def _project_levels(tokens, xs, ws, bias, N0, N1, NT, n_layers, n_heads, arena=N
                         N0, N1, NT, rank, zero)
     if zero is not None:
         arena.buf = zero
+    elif arena is not None:
+        arena.prefill(value_all.shape, lp, dev)     # zero fill forked here, beside the (latency-bound) decoder forward
     tokens.E, tokens.raw, tokens.scores, tokens._value_all = E, raw, scores, value_all
     d = N0 // n_layers
     return tuple(value_all[:, :, i * d:(i + 1) * d].view(B, Lv, n_heads, d // n_heads) for i in range(n_layers))

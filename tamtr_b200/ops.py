@@ -5,6 +5,7 @@ ultralytics/nn/modules/utils.py:42 multi_scale_deformable_attn_pytorch(value, va
 sampling_locations, attention_weights) so that tamtr_b200.enable() can rebind that name to it.
 """
 import ctypes
+import os
 
 import torch
 
@@ -28,9 +29,26 @@ def _value_layout(value):
 
 
 def _env_arena_dtype():
-    import os
     v = os.environ.get("TAMTR_GRAD_ARENA", "").lower()
     return torch.float32 if v in ("fp32", "f32", "float32") else None
+
+
+ARENA_PREFILL = os.environ.get("TAMTR_ARENA_PREFILL", "1") != "0"
+# CTAs of the forked fill kernel: 0 = one per SM (measured at S-yaml B=16: 64 CTAs -0.22 ms, 148 CTAs -0.23 ms per step,
+# 32 CTAs +0.07 ms: the window up to the first sampler backward is ~0.7 ms); "memset" = a cudaMemsetAsync node on the side
+# stream (no gain: +0.03 ms -- a full-grid memset beside the decoder hides nothing)
+ARENA_FILL_CTAS = os.environ.get("TAMTR_ARENA_FILL_CTAS", "0")
+ARENA_FILL_CTAS = ARENA_FILL_CTAS if ARENA_FILL_CTAS == "memset" else int(ARENA_FILL_CTAS)
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One side stream per device for work forked off the step (the gradient arena's zero fill)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(idx)
+    if st is None:
+        st = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return st
 
 
 GRAD_ARENA_DTYPE = _env_arena_dtype()     # default gradient dtype of ValueArena (None = value dtype); TAMTR_GRAD_ARENA=fp32
@@ -47,6 +65,7 @@ class ValueArena:
 
     def __init__(self, grad_dtype=None):
         self.buf = None
+        self._ready = None        # event of a zero fill forked to the side stream (prefill), pending a join
         self.base = None
         self.bias_grad = {}       # column offset of a layer's slice -> [d] fp32
         self.written = set()      # column offsets whose sampler backward has run in this backward pass
@@ -54,7 +73,48 @@ class ValueArena:
         # torch.float32 = fp32 accumulation of the scattered gradient (f32x4 reductions, one cast pass before the GEMMs)
         self.grad_dtype = grad_dtype if grad_dtype is not None else GRAD_ARENA_DTYPE
 
+    def prefill(self, shape, dtype, device):
+        """Zero-fill the gradient buffer AHEAD of the backward, on a side stream forked from the caller's stream here
+        (call it right after the value projection was launched) and joined by the first consumer (`grad_buffer` /
+        `take`).  The 1.65 GB memset node of the S-yaml step is pure HBM write time (0.26 ms); on the main stream it sits
+        in front of the first sampler backward with nothing beside it, while the decoder forward between the projection
+        and that point is latency-bound small kernels that leave the memory system idle.  In a captured step the fork
+        and the join become parallel branches of the graph.  Only call it when a backward will follow: a capture that
+        ends with the branch unjoined is an error (TAMTR_ARENA_PREFILL=0 keeps the memset in the backward)."""
+        if not ARENA_PREFILL or self.buf is not None or device.type != "cuda":
+            return
+        gdt = self.grad_dtype if self.grad_dtype is not None else dtype
+        buf = torch.empty(shape, dtype=gdt, device=device)                   # allocated on (and owned by) the main stream
+        main, side = torch.cuda.current_stream(device), _side_stream(device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            nbytes = buf.numel() * buf.element_size()
+            if ARENA_FILL_CTAS != "memset":     # small co-resident CTAs beside the decoder's kernels, not a full-grid memset
+                _lib.check(_lib.lib().tamtr_zero_fill_background(buf.data_ptr(), nbytes, ARENA_FILL_CTAS,
+                                                                 _lib.stream_ptr(device)), "zero_fill_background")
+            else:
+                _lib.check(_lib.lib().tamtr_memset_zero(buf.data_ptr(), nbytes, _lib.stream_ptr(device)), "memset_zero")
+            self._ready = torch.cuda.Event()
+            self._ready.record(side)
+        if not torch.cuda.is_current_stream_capturing():
+            buf.record_stream(side)
+        self.buf = buf
+
+    def join(self):
+        """Make the current stream wait for a pending prefill (no-op otherwise)."""
+        ev, self._ready = self._ready, None
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def take(self):
+        """-> (buffer or None, written column offsets); resets the arena for the next pass."""
+        self.join()
+        buf, self.buf, self.base = self.buf, None, None
+        written, self.written = self.written, set()
+        return buf, written
+
     def grad_buffer(self, like):
+        self.join()
         if self.buf is None:
             if self.grad_dtype is not None and self.grad_dtype != like.dtype:
                 like = torch.empty(like.shape, dtype=self.grad_dtype, device=like.device)
@@ -90,6 +150,8 @@ class _ValueProjFn(torch.autograd.Function):
         ctx.meta = (value_all.shape, value_all.dtype, value_all.device, feats.dtype, w_cat.dtype, b_cat.dtype, feats.shape)
         ctx.set_materialize_grads(False)
         arena.base = value_all
+        if any(ctx.needs_input_grad[:3]):
+            arena.prefill(value_all.shape, value_all.dtype, value_all.device)
         return tuple(value_all[:, :, i * d:(i + 1) * d].view(B, Lv, H, d // H) for i in range(n))
 
     @staticmethod
@@ -97,8 +159,7 @@ class _ValueProjFn(torch.autograd.Function):
         f2, w = ctx.saved_tensors
         arena, n, d = ctx.arena, ctx.n, ctx.d
         shape, dtype, device, fdt, wdt, bdt, fshape = ctx.meta
-        buf, arena.buf, arena.base = arena.buf, None, None
-        written, arena.written = arena.written, set()
+        buf, written = arena.take()
         if buf is None:
             buf = _lib.zeros_like_fast(torch.empty(shape, dtype=dtype, device=device))
         from_arena = True

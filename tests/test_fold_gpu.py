@@ -323,3 +323,39 @@ def test_feature_maps_that_require_a_gradient(cuda_lib):
         e_f, e_g, e_u = rel_l2(a, c), rel_l2(g, c), rel_l2(b, c)
         assert a.shape == c.shape and e_f < max(1.25 * e_u, 3e-2), (e_f, e_u)
         assert e_g < max(1.25 * e_u, 3e-2), (e_g, e_u)
+
+
+@pytest.mark.parametrize("nbytes,n_ctas", [(16, 4), (32768, 1), (32768 * 5 + 48, 3), (32768 * 257 + 7, 32), (1 << 20, 148)])
+def test_zero_fill_background(cuda_lib, nbytes, n_ctas):
+    """tamtr_zero_fill_background zeroes exactly [ptr, ptr + bytes): whole 32 KB tiles by bulk stores, the ragged tail by
+    byte stores, nothing before or after."""
+    from tamtr_b200 import _lib
+    pad = 256
+    buf = torch.full((pad + nbytes + pad,), 0xAB, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib().tamtr_zero_fill_background(buf.data_ptr() + pad, nbytes, n_ctas, _lib.stream_ptr(buf.device)),
+               "zero_fill_background")
+    torch.cuda.synchronize()
+    assert int(buf[pad:pad + nbytes].max()) == 0
+    assert int(buf[:pad].min()) == 0xAB and int(buf[pad + nbytes:].min()) == 0xAB
+
+
+def test_arena_zero_fill_forked_beside_the_decoder_is_the_same_step(cuda_lib, monkeypatch):
+    """ValueArena.prefill (zero fill of the samplers' gradient buffer on a side stream, forked after the projection and
+    joined by the first sampler backward) against the memset in the backward: same loss, and gradients equal up to the
+    order of the samplers' atomic adds (the captured step, where fork and join become branches of the graph, is covered by
+    tests/test_step_gpu.py: the forked fill is the default)."""
+    import copy
+    from tamtr_b200 import ops
+    m, xs, text = _head()
+    ref = copy.deepcopy(m)
+    monkeypatch.setattr(ops, "ARENA_PREFILL", False)
+    loss_0, g_0 = _step(ref, xs, text)
+    monkeypatch.setattr(ops, "ARENA_PREFILL", True)
+    for ctas in (0, 32, "memset"):
+        monkeypatch.setattr(ops, "ARENA_FILL_CTAS", ctas)
+        mm = copy.deepcopy(m)
+        loss_1, g_1 = _step(mm, xs, text)
+        assert loss_1.item() == loss_0.item()
+        assert set(g_1) == set(g_0)
+        for k in g_0:
+            assert rel_l2(g_1[k], g_0[k]) < 2e-2, k
