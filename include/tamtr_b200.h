@@ -290,6 +290,28 @@ int tamtr_add_layernorm_backward_res(const void *dy, int dy_dtype, const float *
                                      const float *w, const float *extra, void *dx, int dx_dtype, void *dres, int dres_dtype,
                                      float *dwb, int rows, int d, void *stream);
 
+/* Decoder layer under bf16 autocast (transformer.py:544-557): the normalised stream stays fp32, but every consumer of it
+ * (the attention projections, the FFN) computes in bf16, on `embed` or on `embed + query_pos`.  The casts and the
+ * `with_pos_embed` adds autocast puts between them are side outputs / side gradients of the kernels above:
+ *   forward_sides : also writes y_bf16 = bf16(y) and q_bf16 = bf16(y + pos) (pos [rows, d] f32|bf16; either output may be
+ *                   NULL) -- the values autocast's casts would produce.
+ *   backward_sides: dy (may be NULL) + the gradients of the two bf16 outputs (bf16 [rows, d], either may be NULL) are
+ *                   summed in fp32 while they are loaded.
+ *   pos_cast      : x_bf16 = bf16(x), q_bf16 = bf16(x + pos) for the layer's input (n elements, n % 4 == 0).
+ *   grad_sum3     : out = a + b + c (any two may be NULL; fp32 sum): the gradient of that input, which also feeds the
+ *                   residual connection. */
+int tamtr_add_layernorm_forward_sides(const void *x, int x_dtype, const void *res, int res_dtype, const float *w,
+                                      const float *b, void *y, int y_dtype, float *z, float *mean, float *rstd,
+                                      const void *pos, int pos_dtype, void *y_bf16, void *q_bf16, int rows, int d, float eps,
+                                      void *stream);
+int tamtr_add_layernorm_backward_sides(const void *dy, int dy_dtype, const void *g_y_bf16, const void *g_q_bf16,
+                                       const float *z, const float *mean, const float *rstd, const float *w, void *dx,
+                                       int dx_dtype, void *dres, int dres_dtype, float *dwb, int rows, int d, void *stream);
+int tamtr_pos_cast(const void *x, int x_dtype, const void *pos, int pos_dtype, void *x_bf16, void *q_bf16, long n,
+                   void *stream);
+int tamtr_grad_sum3(const void *a, int a_dtype, const void *b, int b_dtype, const void *c, int c_dtype, void *out,
+                    int out_dtype, long n, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Query self-attention of the decoder layers (ultralytics/nn/modules/transformer.py:544-548: nn.MultiheadAttention with
  * q = k = embed + pos, v = embed and the denoising attention mask of models/utils/ops.py:273-284), after the packed input

@@ -54,6 +54,12 @@ _SIGNATURES = {
     "tamtr_add_layernorm_forward": (ctypes.c_int, [_vp, _i, _vp, _i, _fp, _fp, _vp, _i, _fp, _fp, _fp, _i, _i,
                                                    ctypes.c_float, _vp]),
     "tamtr_add_layernorm_backward": (ctypes.c_int, [_vp, _i, _fp, _fp, _fp, _fp, _vp, _i, _vp, _i, _fp, _i, _i, _vp]),
+    "tamtr_add_layernorm_forward_sides": (ctypes.c_int, [_vp, _i, _vp, _i, _fp, _fp, _vp, _i, _fp, _fp, _fp, _vp, _i, _vp, _vp,
+                                                         _i, _i, ctypes.c_float, _vp]),
+    "tamtr_add_layernorm_backward_sides": (ctypes.c_int, [_vp, _i, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _i, _vp, _i, _fp, _i, _i,
+                                                          _vp]),
+    "tamtr_pos_cast": (ctypes.c_int, [_vp, _i, _vp, _i, _vp, _vp, _l, _vp]),
+    "tamtr_grad_sum3": (ctypes.c_int, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _l, _vp]),
     "tamtr_add_layernorm_backward_res": (ctypes.c_int, [_vp, _i, _fp, _fp, _fp, _fp, _fp, _vp, _i, _vp, _i, _fp, _i, _i, _vp]),
     "tamtr_self_attention_supported": (ctypes.c_int, [_i] * 3),
     "tamtr_self_attention_padded_len": (ctypes.c_int, [_i]),

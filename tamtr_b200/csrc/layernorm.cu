@@ -42,7 +42,8 @@ template <int PP>   // float4 packs per lane: d = 128 * PP
 __global__ void __launch_bounds__(kLnThreads)
 add_layernorm_fwd_kernel(const void *__restrict__ x, int x_dtype, const void *__restrict__ res, int res_dtype,
                          const float *__restrict__ w, const float *__restrict__ b, void *__restrict__ y, int y_dtype,
-                         float *__restrict__ z, float *__restrict__ mean, float *__restrict__ rstd, int rows, float eps) {
+                         float *__restrict__ z, float *__restrict__ mean, float *__restrict__ rstd, int rows, float eps,
+                         const void *__restrict__ pos, int pos_dtype, void *__restrict__ y_lp, void *__restrict__ q_lp) {
     constexpr int d = 128 * PP;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
@@ -83,6 +84,12 @@ add_layernorm_fwd_kernel(const void *__restrict__ x, int x_dtype, const void *__
         o.z = fmaf((v[i].z - mu) * rs, ww.z, bb.z);
         o.w = fmaf((v[i].w - mu) * rs, ww.w, bb.w);
         ln_store4(y, y_dtype, base + col, o);
+        // side outputs for the consumers that compute in bf16 (what autocast's casts of y and of y + pos would produce)
+        if (y_lp != nullptr) ln_store4(y_lp, TAMTR_BF16, base + col, o);
+        if (q_lp != nullptr) {
+            const float4 p = ln_load4(pos, pos_dtype, base + col);
+            ln_store4(q_lp, TAMTR_BF16, base + col, make_float4(o.x + p.x, o.y + p.y, o.z + p.z, o.w + p.w));
+        }
     }
 }
 
@@ -91,7 +98,8 @@ __global__ void __launch_bounds__(kLnThreads)
 add_layernorm_bwd_kernel(const void *__restrict__ dy, int dy_dtype, const float *__restrict__ z,
                          const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ w,
                          void *__restrict__ dx, int dx_dtype, void *__restrict__ dres, int dres_dtype,
-                         float *__restrict__ dwb, int rows, const float *__restrict__ extra) {
+                         float *__restrict__ dwb, int rows, const float *__restrict__ extra,
+                         const void *__restrict__ g1, const void *__restrict__ g2) {
     constexpr int d = 128 * PP;
     __shared__ float s_red[kLnWarps][2][d];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -109,7 +117,15 @@ add_layernorm_bwd_kernel(const void *__restrict__ dy, int dy_dtype, const float 
 #pragma unroll
         for (int i = 0; i < PP; ++i) {
             const size_t idx = base + (size_t)(i * 32 + lane) * 4;
-            const float4 gy = ln_load4(dy, dy_dtype, idx);
+            float4 gy = dy != nullptr ? ln_load4(dy, dy_dtype, idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g1 != nullptr) {                       // gradients of the bf16 side outputs (y_lp, q_lp): same dy
+                const float4 e = ln_load4(g1, TAMTR_BF16, idx);
+                gy.x += e.x; gy.y += e.y; gy.z += e.z; gy.w += e.w;
+            }
+            if (g2 != nullptr) {
+                const float4 e = ln_load4(g2, TAMTR_BF16, idx);
+                gy.x += e.x; gy.y += e.y; gy.z += e.z; gy.w += e.w;
+            }
             const float4 zz = *reinterpret_cast<const float4 *>(z + idx);
             xh[i] = make_float4((zz.x - mu) * rs, (zz.y - mu) * rs, (zz.z - mu) * rs, (zz.w - mu) * rs);
             g[i] = make_float4(gy.x * ww[i].x, gy.y * ww[i].y, gy.z * ww[i].z, gy.w * ww[i].w);
@@ -153,6 +169,40 @@ add_layernorm_bwd_kernel(const void *__restrict__ dy, int dy_dtype, const float 
     }
 }
 
+// q_lp = bf16(x + pos), x_lp = bf16(x): the casts autocast puts in front of the self-attention projections
+// (transformer.py:544-547: q = k = embed + query_pos, v = embed) as one pass over x.
+__global__ void __launch_bounds__(256) pos_cast_kernel(const void *__restrict__ x, int x_dtype, const void *__restrict__ pos,
+                                                       int pos_dtype, void *__restrict__ x_lp, void *__restrict__ q_lp,
+                                                       size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = ln_load4(x, x_dtype, i * 4);
+        if (x_lp != nullptr) ln_store4(x_lp, TAMTR_BF16, i * 4, v);
+        if (q_lp != nullptr) {
+            const float4 p = ln_load4(pos, pos_dtype, i * 4);
+            ln_store4(q_lp, TAMTR_BF16, i * 4, make_float4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w));
+        }
+    }
+}
+
+// out = a + b + c (each optional but one; fp32 sum): the gradient of a tensor that fed pos_cast and a residual connection
+__global__ void __launch_bounds__(256) grad_sum3_kernel(const void *__restrict__ a, int a_dtype, const void *__restrict__ b,
+                                                        int b_dtype, const void *__restrict__ c, int c_dtype,
+                                                        void *__restrict__ out, int out_dtype, size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a != nullptr) s = ln_load4(a, a_dtype, i * 4);
+        if (b != nullptr) {
+            const float4 e = ln_load4(b, b_dtype, i * 4);
+            s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
+        }
+        if (c != nullptr) {
+            const float4 e = ln_load4(c, c_dtype, i * 4);
+            s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
+        }
+        ln_store4(out, out_dtype, i * 4, s);
+    }
+}
+
 static int ln_ctas(int rows) {
     int n_sm = 148;
     n_sm = ::tamtr::sm_count();
@@ -164,10 +214,12 @@ static int ln_ctas(int rows) {
 
 using namespace tamtr;
 
-extern "C" int tamtr_add_layernorm_forward(const void *x, int x_dtype, const void *res, int res_dtype, const float *w,
-                                           const float *b, void *y, int y_dtype, float *z, float *mean, float *rstd,
-                                           int rows, int d, float eps, void *stream) {
+static int add_layernorm_forward_impl(const void *x, int x_dtype, const void *res, int res_dtype, const float *w,
+                                      const float *b, void *y, int y_dtype, float *z, float *mean, float *rstd,
+                                      const void *pos, int pos_dtype, void *y_lp, void *q_lp, int rows, int d, float eps,
+                                      void *stream) {
     TAMTR_CHECK_ARG(x && w && b && y, TAMTR_E_BADARG, "add_layernorm_forward: null pointer");
+    TAMTR_CHECK_ARG(q_lp == nullptr || pos != nullptr, TAMTR_E_BADARG, "add_layernorm_forward: q_lp needs pos");
     TAMTR_CHECK_ARG(rows > 0, TAMTR_E_BADARG, "add_layernorm_forward: rows = %d", rows);
     TAMTR_CHECK_ARG(d % 128 == 0 && d >= 128 && d <= 512, TAMTR_E_UNSUPPORTED,
                     "add_layernorm: d = %d must be a multiple of 128 in [128, 512]", d);
@@ -178,7 +230,7 @@ extern "C" int tamtr_add_layernorm_forward(const void *x, int x_dtype, const voi
 #define TAMTR_LN_FWD(PP)                                                                                              \
     case PP:                                                                                                          \
         add_layernorm_fwd_kernel<PP><<<grid, kLnThreads, 0, st>>>(x, x_dtype, res, res_dtype, w, b, y, y_dtype, z,   \
-                                                                  mean, rstd, rows, eps);                            \
+                                                                  mean, rstd, rows, eps, pos, pos_dtype, y_lp, q_lp); \
         break;
         switch (d / 128) {
             TAMTR_LN_FWD(1) TAMTR_LN_FWD(2) TAMTR_LN_FWD(3) TAMTR_LN_FWD(4)
@@ -190,10 +242,27 @@ extern "C" int tamtr_add_layernorm_forward(const void *x, int x_dtype, const voi
     return 0;
 }
 
+extern "C" int tamtr_add_layernorm_forward(const void *x, int x_dtype, const void *res, int res_dtype, const float *w,
+                                           const float *b, void *y, int y_dtype, float *z, float *mean, float *rstd,
+                                           int rows, int d, float eps, void *stream) {
+    return add_layernorm_forward_impl(x, x_dtype, res, res_dtype, w, b, y, y_dtype, z, mean, rstd, nullptr, 0, nullptr,
+                                      nullptr, rows, d, eps, stream);
+}
+
+extern "C" int tamtr_add_layernorm_forward_sides(const void *x, int x_dtype, const void *res, int res_dtype, const float *w,
+                                                 const float *b, void *y, int y_dtype, float *z, float *mean, float *rstd,
+                                                 const void *pos, int pos_dtype, void *y_bf16, void *q_bf16, int rows,
+                                                 int d, float eps, void *stream) {
+    return add_layernorm_forward_impl(x, x_dtype, res, res_dtype, w, b, y, y_dtype, z, mean, rstd, pos, pos_dtype, y_bf16,
+                                      q_bf16, rows, d, eps, stream);
+}
+
 static int add_layernorm_backward_impl(const void *dy, int dy_dtype, const float *z, const float *mean, const float *rstd,
                                        const float *w, const float *extra, void *dx, int dx_dtype, void *dres,
-                                       int dres_dtype, float *dwb, int rows, int d, void *stream) {
-    TAMTR_CHECK_ARG(dy && z && mean && rstd && w && dwb, TAMTR_E_BADARG, "add_layernorm_backward: null pointer");
+                                       int dres_dtype, float *dwb, int rows, int d, void *stream,
+                                       const void *g1 = nullptr, const void *g2 = nullptr) {
+    TAMTR_CHECK_ARG((dy || g1 || g2) && z && mean && rstd && w && dwb, TAMTR_E_BADARG,
+                    "add_layernorm_backward: null pointer");
     TAMTR_CHECK_ARG(rows > 0, TAMTR_E_BADARG, "add_layernorm_backward: rows = %d", rows);
     TAMTR_CHECK_ARG(d % 128 == 0 && d >= 128 && d <= 512, TAMTR_E_UNSUPPORTED,
                     "add_layernorm: d = %d must be a multiple of 128 in [128, 512]", d);
@@ -205,7 +274,7 @@ static int add_layernorm_backward_impl(const void *dy, int dy_dtype, const float
 #define TAMTR_LN_BWD(PP)                                                                                              \
     case PP:                                                                                                          \
         add_layernorm_bwd_kernel<PP><<<grid, kLnThreads, 0, st>>>(dy, dy_dtype, z, mean, rstd, w, dx, dx_dtype, dres, \
-                                                                  dres_dtype, dwb, rows, extra);                    \
+                                                                  dres_dtype, dwb, rows, extra, g1, g2);            \
         break;
         switch (d / 128) {
             TAMTR_LN_BWD(1) TAMTR_LN_BWD(2) TAMTR_LN_BWD(3) TAMTR_LN_BWD(4)
@@ -231,4 +300,41 @@ extern "C" int tamtr_add_layernorm_backward_res(const void *dy, int dy_dtype, co
     TAMTR_CHECK_ARG(extra != nullptr, TAMTR_E_BADARG, "add_layernorm_backward_res: null pointer");
     return add_layernorm_backward_impl(dy, dy_dtype, z, mean, rstd, w, extra, dx, dx_dtype, dres, dres_dtype, dwb, rows, d,
                                        stream);
+}
+
+extern "C" int tamtr_add_layernorm_backward_sides(const void *dy, int dy_dtype, const void *g_y_bf16, const void *g_q_bf16,
+                                                  const float *z, const float *mean, const float *rstd, const float *w,
+                                                  void *dx, int dx_dtype, void *dres, int dres_dtype, float *dwb, int rows,
+                                                  int d, void *stream) {
+    return add_layernorm_backward_impl(dy, dy_dtype, z, mean, rstd, w, nullptr, dx, dx_dtype, dres, dres_dtype, dwb, rows, d,
+                                       stream, g_y_bf16, g_q_bf16);
+}
+
+static int ew_grid(size_t n4) {
+    const size_t need = (n4 + 255) / 256;
+    const size_t cap = (size_t)::tamtr::sm_count() * 8;
+    return (int)(need < cap ? need : cap);
+}
+
+extern "C" int tamtr_pos_cast(const void *x, int x_dtype, const void *pos, int pos_dtype, void *x_bf16, void *q_bf16,
+                              long n, void *stream) {
+    TAMTR_CHECK_ARG(x && (x_bf16 || q_bf16), TAMTR_E_BADARG, "pos_cast: null pointer");
+    TAMTR_CHECK_ARG(q_bf16 == nullptr || pos != nullptr, TAMTR_E_BADARG, "pos_cast: q needs pos");
+    TAMTR_CHECK_ARG(n > 0 && n % 4 == 0, TAMTR_E_UNSUPPORTED, "pos_cast: n = %ld must be a positive multiple of 4", n);
+    pos_cast_kernel<<<ew_grid((size_t)n / 4), 256, 0, (cudaStream_t)stream>>>(x, x_dtype, pos, pos_dtype, x_bf16, q_bf16,
+                                                                              (size_t)n / 4);
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tamtr_grad_sum3(const void *a, int a_dtype, const void *b, int b_dtype, const void *c, int c_dtype, void *out,
+                               int out_dtype, long n, void *stream) {
+    TAMTR_CHECK_ARG(out && (a || b || c), TAMTR_E_BADARG, "grad_sum3: null pointer");
+    TAMTR_CHECK_ARG(n > 0 && n % 4 == 0, TAMTR_E_UNSUPPORTED, "grad_sum3: n = %ld must be a positive multiple of 4", n);
+    grad_sum3_kernel<<<ew_grid((size_t)n / 4), 256, 0, (cudaStream_t)stream>>>(a, a_dtype, b, b_dtype, c, c_dtype, out,
+                                                                               out_dtype, (size_t)n / 4);
+    count_launch();
+    TAMTR_CUDA_OK(cudaGetLastError());
+    return 0;
 }

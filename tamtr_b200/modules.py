@@ -19,6 +19,7 @@ Reference classes mirrored (file:line under /root/reference/ultralytics):
 """
 import copy
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -181,6 +182,48 @@ def _ffn(layer, tgt):
     return _add_norm(layer, tgt, tgt2, layer.dropout4, layer.norm3)
 
 
+LOWP_LAYER = os.environ.get("TAMTR_LOWP_LAYER", "1") != "0"
+
+
+def _plain_norm(layer, drop, norm, d):
+    return ((drop.p == 0.0 or not layer.training) and isinstance(norm, nn.LayerNorm) and norm.elementwise_affine
+            and norm.bias is not None and tuple(norm.normalized_shape) == (d,))
+
+
+def _layer_lowp_applies(layer, embed, query_pos):
+    """bf16 autocast over an fp32 query stream: the case where autocast surrounds every projection of the layer with casts
+    (and the `+ query_pos` adds run in fp32) -- those become side outputs of the add + LayerNorm kernels."""
+    if not (LOWP_LAYER and embed.is_cuda and embed.dtype == torch.float32 and query_pos is not None
+            and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+        return False
+    d = embed.shape[-1]
+    mha = layer.self_attn
+    return (query_pos.shape == embed.shape and query_pos.dtype in (torch.float32, torch.bfloat16)
+            and embed.numel() % 4 == 0 and ops.add_layer_norm_supported(embed, d)
+            and mha._qkv_same_embed_dim and mha.in_proj_bias is not None and mha.bias_k is None and not mha.add_zero_attn
+            and _plain_norm(layer, layer.dropout1, layer.norm1, d) and _plain_norm(layer, layer.dropout2, layer.norm2, d)
+            and _plain_norm(layer, layer.dropout4, layer.norm3, d) and (layer.dropout3.p == 0.0 or not layer.training))
+
+
+def _layer_forward_lowp(layer, embed, refer_bbox, feats, shapes, padding_mask, attn_mask, query_pos, projected_value, arena):
+    """DeformableTransformerDecoderLayer.forward (transformer.py:535-558) with the same arithmetic as the autocast path --
+    fp32 stream, bf16 operands rounded from the same fp32 values -- in 1 + 3 element-wise launches per layer instead of
+    3 + 6: bf16(embed) / bf16(embed + pos) come from one pass over the layer's input, bf16(norm1(..) + pos) and
+    bf16(norm2(..)) from the add + LayerNorm kernels, and the backward sums the gradients of those copies inside the
+    kernels that consume them."""
+    embed, e_lp, q_lp = ops.pos_cast(embed, query_pos)
+    tgt = ops.self_attention(layer.self_attn, q_lp, e_lp, attn_mask)
+    embed, _, q_lp = ops.add_layer_norm_sides(embed, tgt, layer.norm1, pos=query_pos)
+    tgt = layer.cross_attn(q_lp, refer_bbox.unsqueeze(2), feats, shapes, padding_mask, projected_value, arena)
+    embed, e_lp, _ = ops.add_layer_norm_sides(embed, tgt, layer.norm2, want_lp=True)
+    if isinstance(layer.act, nn.ReLU):
+        hidden = ops.linear_relu(e_lp, layer.linear1)
+    else:
+        hidden = layer.act(ops.linear(e_lp, layer.linear1))
+    tgt2 = ops.linear(layer.dropout3(hidden), layer.linear2)
+    return ops.add_layer_norm(embed, tgt2, layer.norm3)
+
+
 def _folded_bn(block, bn):
     """BatchNorm2d in eval mode as a per-channel affine (fp32), cached on the block until a parameter or statistic
     changes (the entry keeps the four source tensors and is valid only for those very objects at those versions)."""
@@ -221,6 +264,9 @@ class DeformableTransformerDecoderLayer(nn.Module):
 
     def forward(self, embed, refer_bbox, feats, shapes, padding_mask=None, attn_mask=None, query_pos=None,
                 projected_value=None, arena=None):
+        if _layer_lowp_applies(self, embed, query_pos):
+            return _layer_forward_lowp(self, embed, refer_bbox, feats, shapes, padding_mask, attn_mask, query_pos,
+                                       projected_value, arena)
         q = k = self.with_pos_embed(embed, query_pos)
         # need_weights=False: the reference discards the averaged attention map ([0] only, transformer.py:546-547),
         # so the fused SDPA kernels can be used; the output is the same.

@@ -941,6 +941,130 @@ def add_layer_norm(x, res, norm):
     return _AddLayerNormFn.apply(x, res, norm.weight, norm.bias, norm.eps, torch.is_grad_enabled())
 
 
+class _AddLayerNormSidesFn(torch.autograd.Function):
+    """norm(x + res) -> (y fp32, bf16(y) | None, bf16(y + pos) | None): the add + LayerNorm kernel also writes what the
+    bf16 consumers of the normalised stream read, and its backward sums the gradients of all three outputs while it loads
+    them (tamtr_add_layernorm_forward_sides / _backward_sides)."""
+
+    @staticmethod
+    def forward(ctx, x, res, weight, bias, eps, pos, want_lp, track):
+        d = x.shape[-1]
+        xc, rc_ = x.contiguous(), res.contiguous()
+        pc = None if pos is None else pos.contiguous()
+        rows = xc.numel() // d
+        dev = xc.device
+        w32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        y = torch.empty(xc.shape, dtype=torch.float32, device=dev)
+        y_lp = torch.empty(xc.shape, dtype=torch.bfloat16, device=dev) if want_lp else None
+        q_lp = torch.empty(xc.shape, dtype=torch.bfloat16, device=dev) if pc is not None else None
+        need = bool(track) and any(ctx.needs_input_grad[:4] + (ctx.needs_input_grad[5],))
+        z = torch.empty(xc.shape, dtype=torch.float32, device=dev) if need else None
+        mean = torch.empty(rows, dtype=torch.float32, device=dev) if need else None
+        rstd = torch.empty(rows, dtype=torch.float32, device=dev) if need else None
+        ptr = lambda t: None if t is None else t.data_ptr()                         # noqa: E731
+        with _with_device(xc):
+            rc = _lib.lib().tamtr_add_layernorm_forward_sides(
+                xc.data_ptr(), _lib.dtype_code(xc), rc_.data_ptr(), _lib.dtype_code(rc_), w32.data_ptr(), b32.data_ptr(),
+                y.data_ptr(), _lib.dtype_code(y), ptr(z), ptr(mean), ptr(rstd), ptr(pc),
+                0 if pc is None else _lib.dtype_code(pc), ptr(y_lp), ptr(q_lp), rows, d, float(eps), _lib.stream_ptr(dev))
+        _lib.check(rc, "add_layernorm_forward_sides")
+        if need:
+            ctx.save_for_backward(z, mean, rstd, w32)
+            ctx.meta = (xc.dtype, rc_.dtype, weight.dtype, bias.dtype, None if pc is None else pc.dtype, rows, d)
+        ctx.set_materialize_grads(False)
+        return y, y_lp, q_lp
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy, g_ylp, g_qlp):
+        if gy is None and g_ylp is None and g_qlp is None:
+            return (None,) * 8
+        z, mean, rstd, w32 = ctx.saved_tensors
+        xdt, rdt, wdt, bdt, pdt, rows, d = ctx.meta
+        dev = z.device
+        if gy is not None:
+            gy = gy.contiguous()
+            if gy.dtype not in (torch.float32, torch.bfloat16):
+                gy = gy.float()
+        g1 = None if g_ylp is None else g_ylp.contiguous().to(torch.bfloat16)
+        g2 = None if g_qlp is None else g_qlp.contiguous().to(torch.bfloat16)
+        need_x, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dx = torch.empty(z.shape, dtype=xdt, device=dev) if need_x else None
+        if need_r and need_x and rdt == xdt:
+            dres, dres_ptr = dx, None
+        else:
+            dres = torch.empty(z.shape, dtype=rdt, device=dev) if need_r else None
+            dres_ptr = None if dres is None else dres.data_ptr()
+        dwb = torch.empty(2, d, dtype=torch.float32, device=dev)       # zeroed by the call
+        ptr = lambda t: None if t is None else t.data_ptr()                         # noqa: E731
+        with _with_device(z):
+            rc = _lib.lib().tamtr_add_layernorm_backward_sides(
+                ptr(gy), 0 if gy is None else _lib.dtype_code(gy), ptr(g1), ptr(g2), z.data_ptr(), mean.data_ptr(),
+                rstd.data_ptr(), w32.data_ptr(), ptr(dx), 0 if dx is None else _lib.dtype_code(dx), dres_ptr,
+                0 if dres_ptr is None else _lib.dtype_code(dres), dwb.data_ptr(), rows, d, _lib.stream_ptr(dev))
+        _lib.check(rc, "add_layernorm_backward_sides")
+        d_pos = None
+        if ctx.needs_input_grad[5] and g2 is not None:
+            d_pos = g2 if pdt == g2.dtype else g2.to(pdt)              # d(y + pos)/d(pos) = 1
+        return dx, dres, dwb[0].to(wdt), dwb[1].to(bdt), None, d_pos, None, None
+
+
+def add_layer_norm_sides(x, res, norm, pos=None, want_lp=False):
+    """(norm(x + res) in fp32, its bf16 copy if `want_lp`, bf16(norm(x + res) + pos) if `pos` is given) -- one kernel each
+    way.  For the decoder layers under bf16 autocast (modules._layer_forward_lowp)."""
+    _lib.require_cuda(x, res)
+    return _AddLayerNormSidesFn.apply(x, res, norm.weight, norm.bias, norm.eps, pos, bool(want_lp), torch.is_grad_enabled())
+
+
+class _PosCastFn(torch.autograd.Function):
+    """x -> (x, bf16(x), bf16(x + pos)): the operands of the self-attention projections (transformer.py:544-547) from one
+    pass over x.  x itself is handed through so that the gradient of its other consumer (the residual connection) arrives
+    at this node and is summed with the two bf16 gradients by one kernel."""
+
+    @staticmethod
+    def forward(ctx, x, pos):
+        xc, pc = x.contiguous(), pos.contiguous()
+        x_lp = torch.empty(xc.shape, dtype=torch.bfloat16, device=xc.device)
+        q_lp = torch.empty(xc.shape, dtype=torch.bfloat16, device=xc.device)
+        with _with_device(xc):
+            rc = _lib.lib().tamtr_pos_cast(xc.data_ptr(), _lib.dtype_code(xc), pc.data_ptr(), _lib.dtype_code(pc),
+                                           x_lp.data_ptr(), q_lp.data_ptr(), xc.numel(), _lib.stream_ptr(xc.device))
+        _lib.check(rc, "pos_cast")
+        ctx.meta = (x.dtype, pos.dtype, x.shape)
+        ctx.set_materialize_grads(False)
+        return x.view_as(x), x_lp, q_lp
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gx, g_xlp, g_qlp):
+        xdt, pdt, shape = ctx.meta
+        gs = [g.contiguous() for g in (gx, g_xlp, g_qlp) if g is not None]
+        d_pos = None
+        if ctx.needs_input_grad[1] and g_qlp is not None:
+            d_pos = g_qlp if g_qlp.dtype == pdt else g_qlp.to(pdt)
+        if not gs or not ctx.needs_input_grad[0]:
+            return None, d_pos
+        if len(gs) == 1 and gs[0].dtype == xdt:
+            return gs[0], d_pos
+        if any(g.dtype not in (torch.float32, torch.bfloat16) for g in gs):
+            gs = [g.float() for g in gs]
+        gs += [None] * (3 - len(gs))
+        out = torch.empty(shape, dtype=xdt, device=gs[0].device)
+        ptr = lambda t: None if t is None else t.data_ptr()                         # noqa: E731
+        code = lambda t: 0 if t is None else _lib.dtype_code(t)                     # noqa: E731
+        with _with_device(out):
+            rc = _lib.lib().tamtr_grad_sum3(ptr(gs[0]), code(gs[0]), ptr(gs[1]), code(gs[1]), ptr(gs[2]), code(gs[2]),
+                                            out.data_ptr(), _lib.dtype_code(out), out.numel(), _lib.stream_ptr(out.device))
+        _lib.check(rc, "grad_sum3")
+        return out, d_pos
+
+
+def pos_cast(x, pos):
+    """-> (x, bf16(x), bf16(x + pos)) with one kernel forward and one backward."""
+    _lib.require_cuda(x, pos)
+    return _PosCastFn.apply(x, pos)
+
+
 def to_channels_last(x):
     """[B, C, H, W] -> the same logical tensor in channels-last memory ([B, H, W, C] storage).  No copy when the caller
     already holds channels-last maps; otherwise one pass of tamtr_nchw_to_nhwc."""

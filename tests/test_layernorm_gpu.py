@@ -70,6 +70,129 @@ def test_decoder_layer_uses_fused_norms(cuda_lib):
     assert prof["add_layernorm_fwd"][1] == 3 and prof["add_layernorm_bwd"][1] == 3
 
 
+@pytest.mark.parametrize("rows_shape,d", [((16, 290), 512), ((2, 37), 256), ((1, 1), 128)])
+@pytest.mark.parametrize("pdt", [torch.bfloat16, torch.float32, None])
+@pytest.mark.parametrize("want_lp", [True, False])
+def test_add_layer_norm_side_outputs(cuda_lib, rows_shape, d, pdt, want_lp):
+    """norm(x + res) with the bf16 side outputs against the op sequence autocast runs (transformer.py:548-552:
+    embed = norm(embed + tgt); query = embed + pos, both rounded to bf16 in front of the projections): the forward values are
+    the same roundings of the same fp32 numbers (bit-equal), the backward sums the three output gradients in fp32."""
+    from tamtr_b200 import ops
+    shape = (*rows_shape, d)
+    x = (seeding.seeded_tensor(d, "x", shape) * 2 + 0.5).cuda()
+    res = seeding.seeded_tensor(d, "r", shape).bfloat16().cuda()
+    pos = None if pdt is None else seeding.seeded_tensor(d, "pos", shape).to(pdt).cuda()
+    norm = nn.LayerNorm(d)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.2 * seeding.seeded_tensor(d, "w", (d,)))
+        norm.bias.copy_(0.1 * seeding.seeded_tensor(d, "b", (d,)))
+    norm = norm.cuda()
+    probes = [seeding.seeded_tensor(d, f"p{i}", shape).cuda() for i in range(3)]
+
+    def run(fused):
+        xs, rs = x.clone().requires_grad_(), res.clone().requires_grad_()
+        ps = None if pos is None else pos.clone().requires_grad_()
+        norm.zero_grad(set_to_none=True)
+        if fused:
+            y, y_lp, q_lp = ops.add_layer_norm_sides(xs, rs, norm, pos=ps, want_lp=want_lp)
+        else:
+            y = ops.add_layer_norm(xs, rs, norm)
+            y_lp = y.to(torch.bfloat16) if want_lp else None
+            q_lp = None if ps is None else (y + ps).to(torch.bfloat16)
+        loss = (y * probes[0]).sum()
+        if y_lp is not None:
+            loss = loss + (y_lp * probes[1].bfloat16()).float().sum()
+        if q_lp is not None:
+            loss = loss + (q_lp * probes[2].bfloat16()).float().sum()
+        loss.backward()
+        return (y, y_lp, q_lp), (xs.grad, rs.grad, None if ps is None else ps.grad, norm.weight.grad.clone(),
+                                 norm.bias.grad.clone())
+
+    outs_f, grads_f = run(True)
+    outs_u, grads_u = run(False)
+    for a, b in zip(outs_f, outs_u):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a.dtype == b.dtype and torch.equal(a, b)
+    for a, b in zip(grads_f, grads_u):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a.dtype == b.dtype and rel_l2(a.float(), b.float()) < 5e-3
+
+
+def test_pos_cast_and_its_gradient(cuda_lib):
+    from tamtr_b200 import ops
+    shape = (3, 41, 256)
+    x = seeding.seeded_tensor(1, "x", shape).cuda().requires_grad_()
+    pos = seeding.seeded_tensor(1, "pos", shape).bfloat16().cuda().requires_grad_()
+    p = [seeding.seeded_tensor(1, f"p{i}", shape).cuda() for i in range(3)]
+    x0, x_lp, q_lp = ops.pos_cast(x, pos)
+    assert torch.equal(x0, x) and torch.equal(x_lp, x.to(torch.bfloat16)) and torch.equal(q_lp, (x + pos).to(torch.bfloat16))
+    ((x0 * p[0]).sum() + (x_lp * p[1].bfloat16()).float().sum() + (q_lp * p[2].bfloat16()).float().sum()).backward()
+    gx, gp = x.grad.clone(), pos.grad.clone()
+    x.grad = pos.grad = None
+    ((x * p[0]).sum() + (x.to(torch.bfloat16) * p[1].bfloat16()).float().sum()
+     + ((x + pos).to(torch.bfloat16) * p[2].bfloat16()).float().sum()).backward()
+    assert gx.dtype == x.grad.dtype and rel_l2(gx, x.grad) < 1e-6
+    assert gp.dtype == pos.grad.dtype and torch.equal(gp, pos.grad)
+    # a single consumer: the gradient passes through
+    x.grad = None
+    x0, x_lp, q_lp = ops.pos_cast(x, pos)
+    (x_lp.float() * p[1]).sum().backward()
+    assert rel_l2(x.grad, p[1].bfloat16().float()) < 1e-6
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_decoder_layer_low_precision_operands_from_the_norm_kernels(cuda_lib, monkeypatch, train):
+    """Under bf16 autocast the layer takes its bf16 operands from the add + LayerNorm / pos_cast kernels: same forward
+    values as the autocast op sequence (bit-equal), gradients equal up to the order of the fp32 sums, and no ATen cast or
+    add launch of the stream's size left in the forward."""
+    from tamtr_b200 import modules
+    from tamtr_b200.modules import DeformableTransformerDecoderLayer
+    torch.manual_seed(0)
+    layer = DeformableTransformerDecoderLayer(256, 8, 512, 0.0, nn.ReLU(), 3, 4).cuda().train(train)
+    seeding.seeded_fill(layer, 5)
+    shapes = [[20, 20], [10, 10], [5, 5]]
+    B, Lq = 2, 50
+    embed = seeding.seeded_tensor(2, "e", (B, Lq, 256)).cuda()
+    feats = seeding.seeded_tensor(2, "f", (B, 525, 256)).cuda()
+    refer = seeding.seeded_tensor(2, "r", (B, Lq, 4)).sigmoid().cuda()
+    pos = seeding.seeded_tensor(2, "pos", (B, Lq, 256)).bfloat16().cuda()
+    probe = seeding.seeded_tensor(2, "probe", (B, Lq, 256)).cuda()
+
+    def run(lowp):
+        monkeypatch.setattr(modules, "LOWP_LAYER", lowp)
+        e, p = embed.clone().requires_grad_(), pos.clone().requires_grad_()
+        layer.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = layer(e, refer, feats, shapes, None, None, p)
+        (out.float() * probe).sum().backward()
+        grads = {n: q.grad.float().clone() for n, q in layer.named_parameters() if q.grad is not None}
+        grads["embed"], grads["pos"] = e.grad.clone(), p.grad.float().clone()
+        return out.detach(), grads
+
+    out_l, g_l = run(True)
+    out_u, g_u = run(False)
+    assert out_l.dtype == out_u.dtype and torch.equal(out_l, out_u)
+    assert set(g_l) == set(g_u)
+    for k in g_u:
+        assert rel_l2(g_l[k], g_u[k]) < 1e-2, k
+    # launch census of the forward
+    from torch.profiler import profile, ProfilerActivity
+    counts = {}
+    for lowp in (True, False):
+        monkeypatch.setattr(modules, "LOWP_LAYER", lowp)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            layer(embed, refer, feats, shapes, None, None, pos)
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                layer(embed, refer, feats, shapes, None, None, pos)
+                torch.cuda.synchronize()
+        counts[lowp] = sum(1 for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA
+                           and "elementwise_kernel" in ev.name)
+    assert counts[True] + 5 <= counts[False], counts
+
+
 # ---------------------------------------------------------------------------------------------- Linear / self-attention
 @pytest.mark.parametrize("rows,n,dt", [(4800, 512, torch.bfloat16), (4800, 1024, torch.float32), (37, 8, torch.bfloat16),
                                        (1, 1536, torch.float32), (1000, 136, torch.bfloat16)])
