@@ -47,8 +47,8 @@ enum tamtr_kernel {
 };
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (a memset node is ~1.5x faster than a fill kernel for GB-sized buffers) */
 int tamtr_memset_zero(void *ptr, unsigned long long bytes, void *stream);
-/* Zero `bytes` at `ptr` (16-byte aligned) with a kernel of `n_ctas` small CTAs (<= 0: one per SM; ~62 GB/s each) issuing bulk shared->global
- * stores: meant to run on a side stream BESIDE latency-bound work (the gradient arena of the samplers' backward,
+/* Zero `bytes` at `ptr` (16-byte aligned) with a kernel of `n_ctas` small CTAs (0: one per SM; ~62 GB/s each) issuing bulk shared->global
+ * stores (n_ctas < 0: -n_ctas CTAs storing from registers, no shared memory at all): meant to run on a side stream BESIDE latency-bound work (the gradient arena of the samplers' backward,
  * zeroed during the decoder forward; replaces torch.zeros_like in the reference's autograd of transformer.py:273),
  * where a full-grid memset node would take every SM and the whole memory system. */
 int tamtr_zero_fill_background(void *ptr, unsigned long long bytes, int n_ctas, void *stream);
@@ -268,6 +268,17 @@ int tamtr_col_sum(const void *g, float *out, int dtype, int rows, int n, void *s
 int tamtr_rank_tokens(const void *E, const float *raw, const float *enc_bias, const uint8_t *valid, const float *bw,
                       const float *sw, const float *ck, float *out, int dtype, int B, int Lv, int d, int nc,
                       int raw_stride, float eps, void *stream);
+
+/* Query selection proper (head.py:1240 and :437: `torch.topk(scores, num_queries, dim=1).indices` over the ranking scores
+ * of tamtr_rank_tokens / tamtr_tok_project_rank): scores [rows, n] f32 -> out_idx [rows, k] int64 (and, unless NULL,
+ * out_val [rows, k] f32), best first; equal scores in order of their index (torch leaves that order unspecified).
+ * One CTA per row: order-preserving 32-bit keys in shared memory (re-read from global memory when the row does not
+ * fit), 12 + 12 + 8 bit radix select over the few keys that can still be winners, one ordered collection pass, ranking by
+ * counting.  1 <= k <= min(n, 4096).  _supported: 0 = no, 2 = yes with the row in shared memory (n up to ~47 000: 24 us for
+ * 16 x 33 600, k = 300, the library's ~10 launches take 70-140 us), 1 = yes but re-reading the row from L2 on every pass
+ * (slower than the library on long rows; callers use it only for its tie order). */
+int tamtr_topk_rows_supported(int n, int k);
+int tamtr_topk_rows(const float *scores, long long *out_idx, float *out_val, int rows, int n, int k, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Residual add + LayerNorm of the decoder layers (ultralytics/nn/modules/transformer.py:548,553,537:

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "tamtr_max_sigmoid_tc_forward": (ctypes.c_int, [_vp, _fp, _fp, _fp, _vp] + [_i] * 5 + [_vp]),
     "tamtr_gate_conv3x3_tc_forward": (ctypes.c_int, [_vp, _vp, _fp, _fp, _fp, _vp] + [_i] * 6 + [_vp]),
     "tamtr_nchw_to_nhwc": (ctypes.c_int, [_vp, _vp] + [_i] * 4 + [_vp]),
+    "tamtr_topk_rows_supported": (ctypes.c_int, [_i, _i]),
+    "tamtr_topk_rows": (ctypes.c_int, [_fp, _vp, _fp, _i, _i, _i, _vp]),
     "tamtr_add_layernorm_forward": (ctypes.c_int, [_vp, _i, _vp, _i, _fp, _fp, _vp, _i, _fp, _fp, _fp, _i, _i,
                                                    ctypes.c_float, _vp]),
     "tamtr_add_layernorm_backward": (ctypes.c_int, [_vp, _i, _fp, _fp, _fp, _fp, _vp, _i, _vp, _i, _fp, _i, _i, _vp]),

@@ -126,6 +126,18 @@ __global__ void __launch_bounds__(128) zero_fill_bg_kernel(unsigned char *dst, u
         for (unsigned long long i = done + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = 0;
     }
 }
+
+// Variant without shared memory: 16-byte stores from registers, grid-strided (a warp writes 512 contiguous bytes).  A CTA
+// of it asks nothing of an SM but 128 thread slots, so kernels that want (nearly) all of the shared memory can start on
+// the same SM while it runs; the kernel prefers the largest shared-memory carve-out so that its presence does not pin an
+// SM to a small one.
+__global__ void __launch_bounds__(128) zero_fill_bg_regs_kernel(uint4 *dst, unsigned long long n16, unsigned char *tail,
+                                                                unsigned n_tail) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) __stcs(dst + i, z);
+    if (blockIdx.x == 0 && threadIdx.x < n_tail) tail[threadIdx.x] = 0;
+}
 }  // namespace tamtr
 
 extern "C" int tamtr_zero_fill_background(void *ptr, unsigned long long bytes, int n_ctas, void *stream) {
@@ -133,7 +145,23 @@ extern "C" int tamtr_zero_fill_background(void *ptr, unsigned long long bytes, i
     TAMTR_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, TAMTR_E_BADARG,
                     "zero_fill_background: pointer must be 16-byte aligned");
     if (bytes == 0) return 0;
-    if (n_ctas <= 0) n_ctas = tamtr::sm_count();
+    if (n_ctas < 0) {                  // register-store variant, -n_ctas CTAs
+        static bool carve[64] = {false};
+        int dev = 0;
+        TAMTR_CUDA_OK(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !carve[dev]) {
+            TAMTR_CUDA_OK(cudaFuncSetAttribute(tamtr::zero_fill_bg_regs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               (int)cudaSharedmemCarveoutMaxShared));
+            carve[dev] = true;
+        }
+        const unsigned long long n16 = bytes / 16;
+        tamtr::zero_fill_bg_regs_kernel<<<-n_ctas, 128, 0, (cudaStream_t)stream>>>(
+            static_cast<uint4 *>(ptr), n16, static_cast<unsigned char *>(ptr) + n16 * 16, (unsigned)(bytes - n16 * 16));
+        TAMTR_CUDA_OK(cudaGetLastError());
+        tamtr::count_launch();
+        return 0;
+    }
+    if (n_ctas == 0) n_ctas = tamtr::sm_count();
     const unsigned long long n_tiles = bytes / tamtr::kFillTile;
     if ((unsigned long long)n_ctas > n_tiles) n_ctas = n_tiles ? (int)n_tiles : 1;
     tamtr::zero_fill_bg_kernel<<<n_ctas, 128, 0, (cudaStream_t)stream>>>(static_cast<unsigned char *>(ptr), bytes);

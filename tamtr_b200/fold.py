@@ -629,6 +629,7 @@ class FoldedTokens:
                 We_all = rk["We_all"]
             self.rank_consts = rk
             self.arena = ops.ValueArena()
+            self.arena.defer = True         # the heads fork the zero fill after their query selection (start_prefill)
             if fused_glue_applies(self, self.projs, attns):
                 convs, bns = [p[0] for p in self.projs], [p[1] for p in self.projs]
                 t = list(self.xs) + [c.weight for c in convs] + [b.weight for b in bns] + [b.bias for b in bns] \

@@ -263,14 +263,16 @@ class _HeadBase(nn.Module):
         if getattr(feats, "is_folded", False):
             # fold.FoldedTokens: ranking embedding and scores came out of the projection kernel; the selected rows are
             # recomputed from the NCHW maps through the folded affine map (differentiable)
-            topk = torch.topk(self._rank_tokens(feats, valid), self.num_queries, dim=1).indices.view(-1)
+            topk = ops.topk_rows(self._rank_tokens(feats, valid), self.num_queries).view(-1)
+            if feats.arena is not None:
+                feats.arena.start_prefill()     # the gradient arena's zero fill, forked behind the top-k kernel
             img = torch.arange(end=bs, dtype=topk.dtype, device=topk.device).unsqueeze(-1).repeat(
                 1, self.num_queries).view(-1)
             rows = valid.view(-1)[topk].unsqueeze(-1) * feats.rows(img * n_tok + topk)
             top_feats = self.enc_output(rows).view(bs, self.num_queries, -1)
             enc_scores = self.enc_score_head(top_feats)
         elif self.sparse_query_selection and hub is not None:
-            topk = torch.topk(self._rank_tokens(feats, valid), self.num_queries, dim=1).indices.view(-1)
+            topk = ops.topk_rows(self._rank_tokens(feats, valid), self.num_queries).view(-1)
             img = torch.arange(end=bs, dtype=topk.dtype, device=topk.device).unsqueeze(-1).repeat(
                 1, self.num_queries).view(-1)
             rows = ops.select_rows(feats, img * n_tok + topk, hub)              # [B*nq, d]
@@ -280,7 +282,7 @@ class _HeadBase(nn.Module):
         else:
             features = self.enc_output(valid * feats)
             scores = self.enc_score_head(features)
-            topk = torch.topk(scores.max(-1).values, self.num_queries, dim=1).indices.view(-1)
+            topk = ops.topk_rows(scores.max(-1).values, self.num_queries).view(-1)
             img = torch.arange(end=bs, dtype=topk.dtype, device=topk.device).unsqueeze(-1).repeat(
                 1, self.num_queries).view(-1)
             top_feats = features[img, topk].view(bs, self.num_queries, -1)

@@ -39,6 +39,10 @@ ARENA_PREFILL = os.environ.get("TAMTR_ARENA_PREFILL", "1") != "0"
 # stream (no gain: +0.03 ms -- a full-grid memset beside the decoder hides nothing)
 ARENA_FILL_CTAS = os.environ.get("TAMTR_ARENA_FILL_CTAS", "0")
 ARENA_FILL_CTAS = ARENA_FILL_CTAS if ARENA_FILL_CTAS == "memset" else int(ARENA_FILL_CTAS)
+# fill kernel: "bulk" = bulk stores from a zeroed 32 KB shared tile; "regs" = 16-byte stores from registers, no shared memory
+# (measured equal: both give 4.21 ms on most processes and 4.02 ms on some)
+ARENA_FILL_KERNEL = os.environ.get("TAMTR_ARENA_FILL_KERNEL", "bulk")
+ARENA_DEFER = os.environ.get("TAMTR_ARENA_DEFER", "1") != "0"     # fork the fill behind the query selection's top-k
 _SIDE_STREAMS = {}
 
 
@@ -66,6 +70,8 @@ class ValueArena:
     def __init__(self, grad_dtype=None):
         self.buf = None
         self._ready = None        # event of a zero fill forked to the side stream (prefill), pending a join
+        self.defer = False        # prefill() only notes the request; start_prefill() forks the fill (see there)
+        self._pending = None
         self.base = None
         self.bias_grad = {}       # column offset of a layer's slice -> [d] fp32
         self.written = set()      # column offsets whose sampler backward has run in this backward pass
@@ -83,6 +89,9 @@ class ValueArena:
         ends with the branch unjoined is an error (TAMTR_ARENA_PREFILL=0 keeps the memset in the backward)."""
         if not ARENA_PREFILL or self.buf is not None or device.type != "cuda":
             return
+        if self.defer and ARENA_DEFER:
+            self._pending = (tuple(shape), dtype, device)
+            return
         gdt = self.grad_dtype if self.grad_dtype is not None else dtype
         buf = torch.empty(shape, dtype=gdt, device=device)                   # allocated on (and owned by) the main stream
         main, side = torch.cuda.current_stream(device), _side_stream(device)
@@ -90,7 +99,10 @@ class ValueArena:
         with torch.cuda.stream(side):
             nbytes = buf.numel() * buf.element_size()
             if ARENA_FILL_CTAS != "memset":     # small co-resident CTAs beside the decoder's kernels, not a full-grid memset
-                _lib.check(_lib.lib().tamtr_zero_fill_background(buf.data_ptr(), nbytes, ARENA_FILL_CTAS,
+                n_ctas = ARENA_FILL_CTAS
+                if ARENA_FILL_KERNEL == "regs" and n_ctas >= 0:
+                    n_ctas = -(n_ctas or torch.cuda.get_device_properties(device).multi_processor_count)
+                _lib.check(_lib.lib().tamtr_zero_fill_background(buf.data_ptr(), nbytes, n_ctas,
                                                                  _lib.stream_ptr(device)), "zero_fill_background")
             else:
                 _lib.check(_lib.lib().tamtr_memset_zero(buf.data_ptr(), nbytes, _lib.stream_ptr(device)), "memset_zero")
@@ -99,6 +111,16 @@ class ValueArena:
         if not torch.cuda.is_current_stream_capturing():
             buf.record_stream(side)
         self.buf = buf
+
+    def start_prefill(self):
+        """Fork a prefill that was requested while `defer` was set.  The fill keeps one small CTA on every SM for its whole
+        0.28 ms; a kernel that wants (nearly) all of an SM's shared memory cannot start beside it, so the caller forks the
+        fill only after the last such kernel that follows the projection closely (the query selection's top-k, which keeps
+        a row of scores in shared memory).  A request that is never started costs nothing: the backward then zero-fills
+        the buffer itself."""
+        req, self._pending, self.defer = self._pending, None, False
+        if req is not None:
+            self.prefill(*req)
 
     def join(self):
         """Make the current stream wait for a pending prefill (no-op otherwise)."""
@@ -1431,6 +1453,27 @@ def input_proj_tokens(xs, projs, training):
     feats = _InputProjFn.apply(bns, training, n, *xs, *[c.weight for c in convs], *[b.weight for b in bns],
                                *[b.bias for b in bns])
     return feats, [[x.shape[2], x.shape[3]] for x in xs]
+
+
+TOPK_KERNEL = os.environ.get("TAMTR_TOPK", "1") != "0"      # 0: the library's torch.topk (A/B switch)
+
+
+def topk_rows(scores, k):
+    """`torch.topk(scores, k, dim=1).indices` for the query selection (head.py:1240, :437): scores [B, n] -> int64 [B, k],
+    best first.  fp32 CUDA rows that fit in shared memory go through tamtr_topk_rows (one launch; equal scores come out
+    in index order, where torch leaves the order unspecified); anything else is the library call."""
+    if not (TOPK_KERNEL and scores.is_cuda and scores.dtype == torch.float32 and scores.dim() == 2):
+        return torch.topk(scores, k, dim=1).indices
+    B, n = scores.shape
+    L = _lib.lib()
+    if L.tamtr_topk_rows_supported(n, k) != 2:           # rows too long for shared memory: the library is faster
+        return torch.topk(scores, k, dim=1).indices
+    scores = scores.detach().contiguous()
+    out = torch.empty(B, k, dtype=torch.int64, device=scores.device)
+    with _with_device(scores):
+        _lib.check(L.tamtr_topk_rows(scores.data_ptr(), out.data_ptr(), None, B, n, k, _lib.stream_ptr(scores.device)),
+                   "topk_rows")
+    return out
 
 
 def rank_tokens(feats, valid_u8, enc_linear, enc_norm, score_linear):

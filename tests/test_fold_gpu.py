@@ -325,10 +325,11 @@ def test_feature_maps_that_require_a_gradient(cuda_lib):
         assert e_g < max(1.25 * e_u, 3e-2), (e_g, e_u)
 
 
-@pytest.mark.parametrize("nbytes,n_ctas", [(16, 4), (32768, 1), (32768 * 5 + 48, 3), (32768 * 257 + 7, 32), (1 << 20, 148)])
+@pytest.mark.parametrize("nbytes,n_ctas", [(16, 4), (32768, 1), (32768 * 5 + 48, 3), (32768 * 257 + 7, 32), (1 << 20, 148),
+                                           (7, -2), (16, -1), (32768 * 5 + 48, -3), (32768 * 257 + 7, -148)])
 def test_zero_fill_background(cuda_lib, nbytes, n_ctas):
     """tamtr_zero_fill_background zeroes exactly [ptr, ptr + bytes): whole 32 KB tiles by bulk stores, the ragged tail by
-    byte stores, nothing before or after."""
+    byte stores, nothing before or after (n_ctas < 0: the variant storing 16 bytes at a time from registers)."""
     from tamtr_b200 import _lib
     pad = 256
     buf = torch.full((pad + nbytes + pad,), 0xAB, dtype=torch.uint8, device="cuda")
@@ -351,8 +352,9 @@ def test_arena_zero_fill_forked_beside_the_decoder_is_the_same_step(cuda_lib, mo
     monkeypatch.setattr(ops, "ARENA_PREFILL", False)
     loss_0, g_0 = _step(ref, xs, text)
     monkeypatch.setattr(ops, "ARENA_PREFILL", True)
-    for ctas in (0, 32, "memset"):
+    for ctas, kernel in ((0, "bulk"), (32, "bulk"), (0, "regs"), ("memset", "bulk")):
         monkeypatch.setattr(ops, "ARENA_FILL_CTAS", ctas)
+        monkeypatch.setattr(ops, "ARENA_FILL_KERNEL", kernel)
         mm = copy.deepcopy(m)
         loss_1, g_1 = _step(mm, xs, text)
         assert loss_1.item() == loss_0.item()
