@@ -11,6 +11,7 @@ from tamtr_b200.head import ManbaWorldDecoder
 ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=4); ap.add_argument("--gaps", type=int, default=12)
 ap.add_argument("--device-targets", action="store_true", help="ground truth as loss.DeviceTargets (bench.py's step) instead of a host plan")
 ap.add_argument("--no-profile", action="store_true")
+ap.add_argument("--loops", type=int, default=4, help="timed loops of 20 replays (many: does the mode change while the GPU stays busy?)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.manual_seed(1234)
@@ -23,12 +24,15 @@ for _ in range(5): step.run()
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ts = []
-for _ in range(4):
+for _ in range(args.loops):
     a.record()
     for _ in range(20): step.run()
     b.record(); torch.cuda.synchronize()
     ts.append(a.elapsed_time(b) / 20)
-print("events: " + " ".join(f"{t:.4f}" for t in ts) + " ms/step (20 replays back to back, 4 times)")
+    if args.loops > 8:
+        import datetime
+        print(datetime.datetime.now().strftime('%H:%M:%S.%f')[:-3], f'{ts[-1]:.3f}', flush=True)
+print("events: " + " ".join(f"{t:.4f}" if args.loops <= 8 else f"{t:.2f}" for t in ts) + f" ms/step (20 replays back to back, {args.loops} times)")
 if args.no_profile:
     sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
