@@ -23,8 +23,9 @@ constexpr int kTopkCand = 4096;      // capacity of the candidate list
 
 __device__ __forceinline__ uint32_t topk_key(float v) {
     uint32_t u = __float_as_uint(v);
+    if (v != v) return 0xffffffffu;                      // NaN of either sign ranks first, as for torch.topk / torch.sort
     if (u == 0x80000000u) u = 0u;                        // -0.0 == +0.0
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // larger float <=> larger key (NaN with a clear sign bit on top)
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // larger float <=> larger key
 }
 
 template <bool IN_SMEM>
