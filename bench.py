@@ -601,9 +601,11 @@ def main():
     launches = (step.launches_per_step * args.steps) if step.graph is not None else (_lib.launch_count() - launches0)
     value = ws * B * args.steps / sec
     steady = None
-    if rank == 0 and ws == 1 and not args.quick and step.graph is not None:
+    steady_s = os.environ.get("TAMTR_STEADY_S")          # seconds of extra replays; set: also with --quick, 0: off
+    if rank == 0 and ws == 1 and step.graph is not None and (float(steady_s) > 0 if steady_s else not args.quick):
         try:
-            steady = steady_state_probe(lambda: timed(dev, step.run, args.steps, barrier), args.steps, B)
+            steady = steady_state_probe(lambda: timed(dev, step.run, args.steps, barrier), args.steps, B,
+                                        budget_s=float(steady_s) if steady_s else 9.0)
         except Exception as e:          # the headline line must not depend on a secondary measurement
             steady = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
