@@ -118,3 +118,21 @@ def test_out_of_range_locations_give_zero():
     loc = loc.view(1, 6, 1, 1, 1, 2)
     out = msda.forward_c(value, shapes, loc, torch.ones(1, 6, 1, 1, 1))
     assert torch.equal(out, torch.zeros_like(out))
+
+
+def test_topk_oracle_pinned_to_the_reference_call():
+    """oracle/topk.py against the reference's own call, torch.topk(scores, nq, dim=1).indices (head.py:1240, :437): equal
+    indices wherever the scores are distinct, equal values always; its documented tie order (lower index first), NaN first,
+    -0.0 == +0.0."""
+    from oracle import topk
+    g = torch.Generator().manual_seed(3)
+    for B, n, k in [(2, 8400, 300), (3, 33600, 300), (1, 1000, 1000), (4, 17, 1)]:
+        scores = torch.stack([torch.randperm(n, generator=g).float() for _ in range(B)]) * (8.0 / n) - 4.6   # distinct
+        assert all(len(set(r.tolist())) == n for r in scores)
+        ref = torch.topk(scores, k, dim=1)
+        got = topk.topk_indices(scores, k)
+        assert got.dtype == torch.int64 and torch.equal(got, ref.indices)
+        tied = torch.round(scores * 2) / 2                                  # ~20 distinct values
+        assert torch.equal(torch.gather(tied, 1, topk.topk_indices(tied, k)), torch.topk(tied, k, dim=1).values)
+    row = torch.tensor([[0.5, float("nan"), 0.5, -0.0, 0.0, float("inf"), 0.5, float("-inf")]])
+    assert topk.topk_indices(row, 8).tolist() == [[1, 5, 0, 2, 6, 3, 4, 7]]

@@ -1,17 +1,17 @@
 """GPU parity of the query-selection top-k kernel (csrc/topk.cu) with `torch.topk(scores, nq, dim=1).indices`
-(ultralytics/nn/modules/head.py:1240, :437).  Index work: bit-exact.  The oracle is a stable descending sort on the CPU --
+(ultralytics/nn/modules/head.py:1240, :437).  Index work: bit-exact.  The oracle (oracle/topk.py) is a stable descending sort on the CPU --
 (score descending, index ascending), the order the kernel documents -- which coincides with torch.topk wherever the scores
 are distinct; torch.topk's own values are compared as well."""
-import ctypes
-
 import pytest
 import torch
+
+from oracle import topk as oracle_topk
 
 pytestmark = pytest.mark.gpu
 
 
 def _oracle(scores, k):
-    return torch.sort(scores.cpu(), dim=1, descending=True, stable=True).indices[:, :k]
+    return oracle_topk.topk_indices(scores, k)
 
 
 def _kernel(scores, k):
